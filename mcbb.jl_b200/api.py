@@ -1,0 +1,667 @@
+"""Host-side mirror of the MCBB.jl interface for the hot path, on top of the C-ABI library.
+
+The reference's host language (Julia) is not available in this image, so this module plays the role of the
+Julia glue (mcbb.jl_b200/julia/MCBBB200.jl): same names, argument meaning and error behaviour as
+
+    DEMCBBProblem / solve / DEMCBBSol      src/setup_mc_prob.jl:334-376, 462-472, 1098-1128
+    eval_ode_run                           src/eval_mc_prob.jl:75-198
+    distance_matrix / DistanceMatrix       src/eval_clustering.jl:32-38, 164-241
+    dbscan / DbscanResult                  src/eval_clustering.jl:84, src/sparse_clustering.jl:126-209
+    cluster_membership, cluster_n_noise    src/eval_clustering.jl:1154-1265, 1434-1457
+
+Problem setup, sorting and cluster_membership stay host code exactly as in the reference (SURVEY §8(a) A1-A4,
+A14); integration+featurization, the distance matrix and DBSCAN go through libmcbb_b200.so.
+Indices exposed to the user are 1-based where the reference's are (seeds, state_filter).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi as abi
+from ._lib import check, lib, MCBBError
+
+# ------------------------------------------------------------------------------------------------------------
+# systems (src/systems.jl)
+# ------------------------------------------------------------------------------------------------------------
+
+
+class DEParameters:
+    """Abstract parameter type (systems.jl:15)."""
+    _system = None
+    _fields = ()
+
+    def reconstruct(self, **kw):
+        """Parameters.jl `reconstruct(pars; name=value)` (setup_mc_prob.jl:65, 94)."""
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        for k, v in kw.items():
+            if k not in self._fields:
+                raise KeyError("type %s has no field %s" % (type(self).__name__, k))
+            setattr(new, k, v)
+        return new
+
+
+class logistic_parameters(DEParameters):
+    _system = abi.SYS_LOGISTIC
+    _fields = ("r",)
+    _slots = {"r": 0}
+
+    def __init__(self, r):
+        self.r = float(r)
+
+    def n_dim(self):
+        return 1
+
+    def pack(self, par_names):
+        return abi.PackedSystem(self._system, 1, 1, [self.r], [self._slots[p] for p in par_names])
+
+
+class kuramoto_parameters(DEParameters):
+    _system = abi.SYS_KURAMOTO
+    _fields = ("K", "w", "N")
+    _slots = {"K": 0}
+
+    def __init__(self, K, w, N):
+        self.K, self.w, self.N = float(K), np.asarray(w, dtype=np.float64), int(N)
+
+    def n_dim(self):
+        return self.N
+
+    def pack(self, par_names):
+        return abi.PackedSystem(self._system, self.N, self.N, [self.K], [self._slots[p] for p in par_names],
+                                vec_a=self.w)
+
+
+class kuramoto_network_parameters(DEParameters):
+    _system = abi.SYS_KURAMOTO_NETWORK
+    _fields = ("K", "w", "N", "A")
+    _slots = {"K": 0}
+
+    def __init__(self, K, w, N, A):
+        self.K, self.w, self.N = float(K), np.asarray(w, dtype=np.float64), int(N)
+        self.A = np.asarray(A, dtype=np.float64)
+        if self.A.shape != (self.N, self.N) or self.w.shape != (self.N,):
+            raise ValueError("kuramoto_network_parameters: A must be N x N and w of length N")
+
+    def n_dim(self):
+        return self.N
+
+    def pack(self, par_names):
+        return abi.PackedSystem(self._system, self.N, self.N, [self.K], [self._slots[p] for p in par_names],
+                                mat_a=self.A, vec_a=self.w)
+
+
+class second_order_kuramoto_parameters(DEParameters):
+    _system = abi.SYS_SECOND_ORDER_KURAMOTO
+    _fields = ("systemsize", "damping", "coupling", "incidence", "drive")
+    _slots = {"damping": 0, "coupling": 1}
+
+    def __init__(self, systemsize, damping=0.1, coupling=8.0, incidence=None, drive=None):
+        self.systemsize = int(systemsize)
+        self.damping, self.coupling = float(damping), float(coupling)
+        self.incidence = np.asarray(incidence, dtype=np.float64)
+        self.drive = np.asarray(drive, dtype=np.float64)
+        if self.incidence.shape[0] != self.systemsize:
+            raise ValueError("incidence must be systemsize x n_edges")
+
+    def n_dim(self):
+        return 2 * self.systemsize
+
+    def pack(self, par_names):
+        return abi.PackedSystem(self._system, self.systemsize, 2 * self.systemsize,
+                                [self.damping, self.coupling], [self._slots[p] for p in par_names],
+                                mat_a=self.incidence, vec_a=self.drive, n_edges=self.incidence.shape[1])
+
+
+class non_local_kuramoto_ring_parameters(DEParameters):
+    _system = abi.SYS_NONLOCAL_KURAMOTO_RING
+    _fields = ("N", "fak", "omega_0", "phase_delay", "coupling_function")
+    _slots = {"omega_0": 0, "phase_delay": 1}
+
+    def __init__(self, N, omega_0, phase_delay, coupling_function, fak=None):
+        self.N = int(N)
+        self.fak = (2 * math.pi) / self.N if fak is None else float(fak)
+        self.omega_0, self.phase_delay = float(omega_0), float(phase_delay)
+        self.coupling_function = coupling_function
+
+    def n_dim(self):
+        return self.N
+
+    def pack(self, par_names):
+        # the Julia closure cannot cross the ABI: tabulate G(fak*(k-j)) for k-j = -(N-1)..(N-1)
+        G = np.array([self.coupling_function(self.fak * d) for d in range(-(self.N - 1), self.N)],
+                     dtype=np.float64)
+        return abi.PackedSystem(self._system, self.N, self.N, [self.omega_0, self.phase_delay, self.fak],
+                                [self._slots[p] for p in par_names], mat_a=G)
+
+
+class roessler_parameters(DEParameters):
+    _system = abi.SYS_ROESSLER_NETWORK
+    _fields = ("a", "b", "c", "K", "L", "N")
+    _slots = {"K": 0}
+
+    def __init__(self, a, b, c, K, L, N):
+        self.a, self.b, self.c = (np.asarray(v, dtype=np.float64) for v in (a, b, c))
+        self.K, self.L, self.N = float(K), np.asarray(L, dtype=np.float64), int(N)
+
+    def n_dim(self):
+        return 3 * self.N
+
+    def pack(self, par_names):
+        return abi.PackedSystem(self._system, self.N, 3 * self.N, [self.K], [self._slots[p] for p in par_names],
+                                mat_a=self.L, vec_a=self.a, vec_b=self.b, vec_c=self.c)
+
+
+class stuart_landau_sathiyadevi_pars(DEParameters):
+    """paper/stuartlandau/stuart_landau_sathiyadevi-standard-config.ipynb cell 1."""
+    _system = abi.SYS_STUART_LANDAU
+    _fields = ("lambda_", "omega", "eps", "N", "P_1", "P_2", "A_1", "A_2")
+    _slots = {"eps": 0, "lambda_": 1, "omega": 2}
+
+    def __init__(self, lambda_, omega, eps, N, P_1, P_2, A_1, A_2):
+        self.lambda_, self.omega, self.eps = float(lambda_), float(omega), float(eps)
+        self.N, self.P_1, self.P_2 = int(N), int(P_1), int(P_2)
+        self.A_1 = np.asarray(A_1, dtype=np.float64)
+        self.A_2 = np.asarray(A_2, dtype=np.float64)
+
+    def n_dim(self):
+        return 2 * self.N
+
+    def pack(self, par_names):
+        return abi.PackedSystem(self._system, self.N, 2 * self.N,
+                                [self.eps, self.lambda_, self.omega, float(self.P_1), float(self.P_2)],
+                                [self._slots[p] for p in par_names], mat_a=self.A_1, mat_b=self.A_2)
+
+
+def _sysfun(name, system):
+    def f(du, u, p, t):  # the RHS itself runs on the device; this symbol only names the system
+        raise MCBBError("%s is evaluated inside libmcbb_b200.so; call solve(DEMCBBProblem(...))" % name)
+
+    f.__name__ = name
+    f.system = system
+    return f
+
+
+logistic = _sysfun("logistic", abi.SYS_LOGISTIC)
+kuramoto = _sysfun("kuramoto", abi.SYS_KURAMOTO)
+kuramoto_network = _sysfun("kuramoto_network", abi.SYS_KURAMOTO_NETWORK)
+second_order_kuramoto = _sysfun("second_order_kuramoto", abi.SYS_SECOND_ORDER_KURAMOTO)
+non_local_kuramoto_ring = _sysfun("non_local_kuramoto_ring", abi.SYS_NONLOCAL_KURAMOTO_RING)
+roessler_network = _sysfun("roessler_network", abi.SYS_ROESSLER_NETWORK)
+stuart_landau_sathiyadevi = _sysfun("stuart_landau_sathiyadevi!", abi.SYS_STUART_LANDAU)
+
+
+def order_parameter(u, N):
+    """systems.jl:246-248"""
+    u = np.asarray(u)
+    return 1.0 / N * math.sqrt(np.sum(np.sin(u)) ** 2 + np.sum(np.cos(u)) ** 2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DifferentialEquations.jl problem / algorithm stand-ins (only what solve(prob::DEMCBBProblem) reads)
+# ------------------------------------------------------------------------------------------------------------
+class ODEProblem:
+    discrete = False
+
+    def __init__(self, f, u0, tspan, p):
+        if p._system != f.system:
+            raise MCBBError("parameter struct does not belong to system %s" % f.__name__)
+        self.f, self.u0, self.tspan, self.p = f, np.asarray(u0), (float(tspan[0]), float(tspan[1])), p
+
+
+class DiscreteProblem(ODEProblem):
+    discrete = True
+
+
+class Tsit5:
+    alg = abi.ALG_TSIT5
+
+
+class RK4:
+    alg = abi.ALG_RK4
+
+
+class FunctionMap:
+    alg = abi.ALG_FUNCTIONMAP
+
+
+# ------------------------------------------------------------------------------------------------------------
+# eval_ode_run (src/eval_mc_prob.jl:75-198) as a descriptor: the closure cannot cross the ABI
+# ------------------------------------------------------------------------------------------------------------
+mean = "mean"
+std = "std"
+empirical_1D_KL_divergence_hist = "kl_hist"
+correlation_ecdf = "correlation_ecdf"
+_MEAS = {"mean": abi.MEAS_MEAN, "std": abi.MEAS_STD, "kl_hist": abi.MEAS_KL_HIST, "mean_real": abi.MEAS_MEAN,
+         "std_real": abi.MEAS_STD, "kl_real": abi.MEAS_KL_HIST, "mean_imag": abi.MEAS_MEAN,
+         "std_imag": abi.MEAS_STD, "kl_imag": abi.MEAS_KL_HIST}
+
+
+class EvalOdeRun:
+    """eval_ode_run(sol, i, state_filter, eval_funcs, matrix_eval_funcs, global_eval_funcs; cyclic_setback=...)"""
+
+    def __init__(self, state_filter=None, eval_funcs=(mean, std, empirical_1D_KL_divergence_hist),
+                 matrix_eval_funcs=None, global_eval_funcs=None, failure_handling="None", cyclic_setback=False,
+                 flag_past_measures=True):
+        if len(eval_funcs) < 1:
+            raise MCBBError("No per dimension measures")  # eval_mc_prob.jl:79-81
+        if failure_handling not in ("None", "Inf", "Repeat"):
+            raise MCBBError("failure_handling symbol not known")  # eval_mc_prob.jl:124-126
+        self.state_filter = None if state_filter is None else [int(i) for i in state_filter]
+        self.eval_funcs = list(eval_funcs)
+        self.matrix_eval_funcs = list(matrix_eval_funcs or [])
+        self.global_eval_funcs = list(global_eval_funcs or [])
+        self.failure_handling = failure_handling
+        self.cyclic_setback = bool(cyclic_setback)
+
+    def pack(self):
+        meas = [_MEAS[f] for f in self.eval_funcs]
+        comp = [1 if f.endswith("_imag") else 0 for f in self.eval_funcs]
+        mat = abi.MAT_CORR_ECDF if self.matrix_eval_funcs else abi.MAT_NONE
+        glob = [abi.GLOB_SUM for _ in self.global_eval_funcs]
+        return abi.PackedFeat(meas, comp, self.state_filter, self.cyclic_setback, mat, 30, glob)
+
+
+eval_ode_run = EvalOdeRun()  # default: mean, std (corrected, given mean), KL-hist — eval_mc_prob.jl:191-198
+
+# ------------------------------------------------------------------------------------------------------------
+# DEMCBBProblem (src/setup_mc_prob.jl:334-376, 686-708, 850-969)
+# ------------------------------------------------------------------------------------------------------------
+
+
+class DEMCBBProblem:
+    """DEMCBBProblem(p, ic_gens | ic_ranges, [N_ic,] pars, (name, range | generator), eval_ode_func, tail_frac)
+
+    * ic_ranges: list of arrays + parameter array      -> cartesian product, IC index fastest (:850-882)
+    * ic generator(s), N_ic, parameter generator       -> N_ic random runs                     (:888-923)
+    * ic generator(s), N_ic, parameter array           -> identical ICs per parameter value    (:929-969)
+    Generators are Python callables `()->value`; a single generator returning an array sets all dimensions.
+    """
+
+    def __init__(self, p, ic, *args):
+        if len(args) >= 2 and isinstance(args[0], (int, np.integer)) and not isinstance(args[0], bool) \
+                and isinstance(args[1], DEParameters):
+            N_ic, pars, par_var = int(args[0]), args[1], args[2]
+            rest = args[3:]
+        else:
+            N_ic, pars, par_var = None, args[0], args[1]
+            rest = args[2:]
+        eval_func = rest[0] if len(rest) > 0 else eval_ode_run
+        tail_frac = rest[1] if len(rest) > 1 else 0.9
+        self.p = p
+        self.pars = pars
+        self.eval_ode_func = eval_func
+        self.rel_transient_time = float(tail_frac)
+        name, values = par_var[0], par_var[1]
+        self.par_var = (name, values)
+        self.par_names = [name]
+        n_dim = pars.n_dim() if not np.iscomplexobj(p.u0) else len(p.u0)
+        if callable(ic) or (isinstance(ic, (list, tuple)) and len(ic) > 0 and callable(ic[0])):
+            gens = [ic] if callable(ic) else list(ic)
+            if N_ic is None:
+                raise MCBBError("random initial conditions need N_ic")
+            ics = self._draw_ics(gens, N_ic, n_dim)
+            if callable(values):  # random x random, :888-923
+                self.ic = ics
+                self.par = np.array([[values()] for _ in range(N_ic)], dtype=np.float64)
+            else:  # identical ICs per parameter value, :929-969 (IC index fastest)
+                vals = np.asarray(list(values), dtype=np.float64)
+                self.ic = np.tile(ics, (len(vals), 1))
+                self.par = np.repeat(vals, N_ic)[:, None]
+        else:  # ranges x range, cartesian product, first IC dimension fastest (:850-882)
+            ranges = [np.asarray(list(r)) for r in ic]
+            vals = np.asarray(list(values), dtype=np.float64)
+            grids = np.meshgrid(*ranges, vals, indexing="ij")
+            cols = [g.reshape(-1, order="F") for g in grids]
+            self.ic = np.stack(cols[:-1], axis=1)
+            self.par = cols[-1][:, None].astype(np.float64)
+        self.ic = np.asfortranarray(self.ic)
+        self.par = np.asfortranarray(self.par)
+        self.N_mc = self.ic.shape[0]
+        if self.N_mc == 0:
+            raise MCBBError("Zero inital conditions. Either at least one of the ranges has length 0 or an "
+                            "overflow occured")
+
+    @staticmethod
+    def _draw_ics(gens, N_ic, n_dim):
+        first = gens[0]()
+        if len(gens) == 1 and np.ndim(first) > 0:
+            rows = [np.asarray(first)] + [np.asarray(gens[0]()) for _ in range(N_ic - 1)]
+            return np.stack(rows, axis=0)
+        if n_dim % len(gens) != 0:
+            raise MCBBError("Number of initial cond. genators and Number of initial cond. doesn't fit together")
+        out = np.zeros((N_ic, n_dim), dtype=np.result_type(type(first), np.float64))
+        for i in range(N_ic):
+            for d in range(n_dim):
+                out[i, d] = first if (i == 0 and d == 0) else gens[d % len(gens)]()
+        return out
+
+
+def parameter(prob, i=None):
+    """parameter(prob) — vector for one parameter, matrix otherwise (setup_mc_prob.jl:424-436)."""
+    if i is not None:
+        return prob.par[:, i - 1]
+    return prob.par[:, 0] if prob.par.shape[1] == 1 else prob.par
+
+
+def tsave_array(prob, N_t, rel_transient_time=0.7):
+    """tsave_array (setup_mc_prob.jl:1166-1180) — computed by the library so every caller sees the same grid."""
+    alg = abi.ALG_FUNCTIONMAP if prob.discrete else abi.ALG_TSIT5
+    o = abi.solver_opts(alg, prob.tspan)
+    n = C.c_int32(0)
+    check(lib().mcbb_tsave_array(C.byref(o), int(N_t), float(rel_transient_time), abi.c_double_p(), C.byref(n)))
+    out = np.zeros(n.value)
+    check(lib().mcbb_tsave_array(C.byref(o), int(N_t), float(rel_transient_time),
+                                 out.ctypes.data_as(abi.c_double_p), C.byref(n)))
+    return out
+
+
+class DEMCBBSol:
+    """DEMCBBSol (setup_mc_prob.jl:462-472).  `sol[i]` is the tuple of measures of run i (0-based here),
+    `get_measure(sol, k)` the N_mc x N_dim matrix of measure k (1-based k as in the reference)."""
+
+    def __init__(self, feat, matrix, glob, retcode, nsteps, N_t, solve_command):
+        self.feat = feat  # [N_mc, n_filter, n_meas]
+        self.matrix = matrix
+        self.glob = glob
+        self.retcode = retcode
+        self.nsteps = nsteps
+        self.N_mc, self.N_dim, self.N_meas_dim = feat.shape
+        self.N_meas_matrix = 0 if matrix is None else 1
+        self.N_meas_global = 0 if glob is None else glob.shape[1]
+        self.N_meas = self.N_meas_dim + self.N_meas_matrix + self.N_meas_global
+        self.N_t = N_t
+        self.solve_command = solve_command
+
+    def __getitem__(self, i):
+        out = [self.feat[i, :, m] for m in range(self.N_meas_dim)]
+        if self.matrix is not None:
+            out.append(self.matrix[i])
+        if self.glob is not None:
+            out.extend(self.glob[i, g] for g in range(self.glob.shape[1]))
+        return tuple(out)
+
+    @property
+    def sol(self):
+        return [self[i] for i in range(self.N_mc)]
+
+
+def get_measure(sol, k):
+    """get_measure(sol, k) (setup_mc_prob.jl:601-624), k 1-based."""
+    k -= 1
+    if k < sol.N_meas_dim:
+        return sol.feat[:, :, k]
+    k -= sol.N_meas_dim
+    if k < sol.N_meas_matrix:
+        return sol.matrix
+    k -= sol.N_meas_matrix
+    return sol.glob[:, k]
+
+
+def check_inf_nan(sol):
+    """check_inf_nan (eval_mc_prob.jl:264-279): indices [run, measure] (1-based) with Inf / NaN entries."""
+    res = {"Inf": [], "NaN": []}
+    for m in range(sol.N_meas):
+        a = np.asarray(get_measure(sol, m + 1)).reshape(sol.N_mc, -1)
+        for i in np.nonzero(np.isnan(a).any(axis=1))[0]:
+            res["NaN"].append([int(i) + 1, m + 1])
+        for i in np.nonzero(np.isinf(a).any(axis=1))[0]:
+            res["Inf"].append([int(i) + 1, m + 1])
+    return res
+
+
+def _solver_opts(prob, alg, kwargs):
+    a = alg.alg if alg is not None else (abi.ALG_FUNCTIONMAP if prob.p.discrete else abi.ALG_TSIT5)
+    known = ("abstol", "reltol", "dt", "dtmin", "dtmax", "maxiters", "qmin", "qmax", "gamma", "beta1", "beta2",
+             "qoldinit")
+    for k in kwargs:
+        if k not in known:
+            raise MCBBError("solve: unsupported keyword %r for the B200 integrator" % k)
+    return abi.solver_opts(a, prob.p.tspan, **kwargs)
+
+
+def custom_solve_b200(prob, t_save, alg=None, **kwargs):
+    """The `custom_solve(prob, t_save)` plug-in (setup_mc_prob.jl:1102-1104): integrates and featurizes the
+    whole ensemble on the GPU and returns the per-run measures in the caller's run order."""
+    names = prob.par_names
+    psys = prob.pars.pack(names)
+    pfeat = prob.eval_ode_func.pack()
+    o = _solver_opts(prob, alg, kwargs)
+    ic = prob.ic
+    if np.iscomplexobj(ic):  # Matrix{Complex{Float64}} -> interleaved (re, im) per oscillator
+        ic = np.stack([ic.real, ic.imag], axis=2).reshape(ic.shape[0], -1)
+    ic = np.asfortranarray(ic, dtype=np.float64)
+    par = np.asfortranarray(prob.par, dtype=np.float64)
+    t_save = np.ascontiguousarray(t_save, dtype=np.float64)
+    n_mc = ic.shape[0]
+    if ic.shape[1] != psys.n_dim:
+        raise MCBBError("initial conditions have %d dimensions, the system has %d" % (ic.shape[1], psys.n_dim))
+    nf = pfeat.n_filter(psys)
+    feat = np.full((n_mc, nf, pfeat.n_meas), np.nan, order="F")
+    mat = np.full((n_mc, pfeat.corr_nbins), np.nan, order="F") if pfeat.matrix_meas else None
+    glob = np.full((n_mc, pfeat.n_global), np.nan, order="F") if pfeat.n_global else None
+    ret = np.zeros(n_mc, dtype=np.int32)
+    nsteps = np.zeros((n_mc, 2), dtype=np.int64, order="F")
+    dp = abi.c_double_p
+    check(lib().mcbb_solve_features(
+        C.byref(psys.desc), C.byref(o), C.byref(pfeat.opts), n_mc, ic.ctypes.data_as(dp), par.ctypes.data_as(dp),
+        t_save.ctypes.data_as(dp), len(t_save), feat.ctypes.data_as(dp),
+        mat.ctypes.data_as(dp) if mat is not None else dp(), glob.ctypes.data_as(dp) if glob is not None else dp(),
+        ret.ctypes.data_as(abi.c_int32_p), nsteps.ctypes.data_as(abi.c_int64_p)))
+    if prob.eval_ode_func.failure_handling == "Inf":  # eval_mc_prob.jl:97-119
+        bad = (ret == abi.RET_DTLESSTHANMIN) | (ret == abi.RET_UNSTABLE)
+        feat[bad] = np.inf
+        if mat is not None:
+            mat[bad] = np.inf
+        if glob is not None:
+            glob[bad] = np.inf
+    return feat, mat, glob, ret, nsteps
+
+
+def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, custom_solve=None,
+          sort_results=True, **kwargs):
+    """solve(prob::DEMCBBProblem, alg, N_t, parallel_type; ...) -> DEMCBBSol (setup_mc_prob.jl:1098-1128).
+
+    Integrates N_mc trajectories, keeps only the post-transient statistics and sorts by parameter value.
+    """
+    t_save = tsave_array(prob.p, N_t, prob.rel_transient_time)
+    if custom_solve is None:
+        custom_solve = custom_solve_b200
+    feat, mat, glob, ret, nsteps = custom_solve(prob, t_save, alg=alg, **kwargs)
+    sol = DEMCBBSol(feat, mat, glob, ret, nsteps, N_t, custom_solve)
+    if flag_check_inf_nan:
+        inf_nan = check_inf_nan(sol)
+        if len(inf_nan["Inf"]) > 0 or len(inf_nan["NaN"]) > 0:
+            import warnings
+            warnings.warn("Some elements of the solution are Inf or NaN, check the solution with check_inf_nan "
+                          "again!")
+    if sort_results:
+        sort_(sol, prob)
+    return sol
+
+
+def sort_(sol, prob, i=1):
+    """sort!(sol, prob, i) (setup_mc_prob.jl:520-536): stable sortperm on parameter i, permutes sol, prob.ic
+    and prob.par in place."""
+    p = parameter(prob, i)
+    key = np.abs(p) if np.iscomplexobj(p) else p
+    idx = np.argsort(key, kind="stable")
+    prob.ic[:, :] = prob.ic[idx, :]
+    prob.par[:, :] = prob.par[idx, :]
+    sol.feat = np.asfortranarray(sol.feat[idx])
+    if sol.matrix is not None:
+        sol.matrix = np.asfortranarray(sol.matrix[idx])
+    if sol.glob is not None:
+        sol.glob = np.asfortranarray(sol.glob[idx])
+    sol.retcode = sol.retcode[idx]
+    sol.nsteps = sol.nsteps[idx]
+    return idx
+
+
+# ------------------------------------------------------------------------------------------------------------
+# distance_matrix / dbscan (src/eval_clustering.jl:164-241, 84)
+# ------------------------------------------------------------------------------------------------------------
+class DistanceMatrix:
+    """DistanceMatrix (eval_clustering.jl:32-38): `.data` is the dense N x N Float64 matrix."""
+
+    def __init__(self, data, weights, relative_parameter):
+        self.data, self.weights, self.relative_parameter = data, list(weights), relative_parameter
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __getitem__(self, ij):
+        return self.data[ij]
+
+
+class B200FeatureMatrix:
+    """AbstractDistanceMatrix stand-in that holds the feature matrix instead of the N x N distances; dbscan on it
+    recomputes distances tile by tile on the device (the reference's large-N answers are distance_matrix_mmap /
+    distance_matrix_sparse, eval_clustering.jl:317, 451)."""
+
+    def __init__(self, X, group_len, group_weight, weights, relative_parameter):
+        self.X, self.group_len, self.group_weight = X, group_len, group_weight
+        self.weights, self.relative_parameter = list(weights), relative_parameter
+
+    @property
+    def shape(self):
+        return (self.X.shape[0], self.X.shape[0])
+
+
+def _relative_parameter(prob):
+    """_relative_parameter (eval_clustering.jl:568-580): (par - min) / max   (sic: divides by max)."""
+    par = np.array(prob.par, dtype=np.float64, copy=True)
+    for i in range(par.shape[1]):
+        par[:, i] = (par[:, i] - par[:, i].min()) / par[:, i].max()
+    return par
+
+
+def feature_groups(sol, prob, weights, relative_parameter=False):
+    """Packs measures and parameters into the [N_mc, F] feature matrix + (group_len, group_weight) the C-ABI
+    takes; group order = measure order of distance_matrix (per-dim, matrix, global, then parameters)."""
+    n_par = prob.par.shape[1]
+    if len(weights) != sol.N_meas + n_par:
+        raise MCBBError("Amount of weights not the same as Measures + Parameters")
+    cols, glen = [], []
+    for m in range(sol.N_meas_dim):
+        cols.append(sol.feat[:, :, m])
+        glen.append(sol.N_dim)
+    if sol.matrix is not None:
+        cols.append(sol.matrix)
+        glen.append(sol.matrix.shape[1])
+    if sol.glob is not None:
+        for g in range(sol.glob.shape[1]):
+            cols.append(sol.glob[:, g:g + 1])
+            glen.append(1)
+    par = _relative_parameter(prob) if relative_parameter else prob.par
+    for p in range(n_par):
+        cols.append(np.asarray(par[:, p:p + 1], dtype=np.float64))
+        glen.append(1)
+    X = np.asfortranarray(np.concatenate(cols, axis=1), dtype=np.float64)
+    return X, np.asarray(glen, dtype=np.int32), np.asarray(weights, dtype=np.float64)
+
+
+def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=False, materialize=True):
+    """distance_matrix(sol, prob, weights; relative_parameter) with the default L1 distance_func
+    (eval_clustering.jl:164-241).  materialize=False returns a B200FeatureMatrix for large N."""
+    if histograms:
+        raise MCBBError("histograms=true is not implemented in the B200 back end yet")
+    X, glen, gw = feature_groups(sol, prob, weights, relative_parameter)
+    if not materialize:
+        return B200FeatureMatrix(X, glen, gw, weights, relative_parameter)
+    n = X.shape[0]
+    D = np.zeros((n, n), order="F")
+    check(lib().mcbb_distance_matrix(X.ctypes.data_as(abi.c_double_p), n, len(glen),
+                                     glen.ctypes.data_as(abi.c_int32_p), gw.ctypes.data_as(abi.c_double_p),
+                                     D.ctypes.data_as(abi.c_double_p)))
+    if np.isnan(D).any():
+        import warnings
+        warnings.warn("There are some elements NaN in the distance matrix")
+    if np.isinf(D).any():
+        import warnings
+        warnings.warn("There are some elements Inf in the distance matrix")
+    return DistanceMatrix(D, weights, relative_parameter)
+
+
+class DbscanResult:
+    """Clustering.DbscanResult: seeds (1-based), assignments (0 = noise), counts."""
+
+    def __init__(self, seeds, assignments, counts):
+        self.seeds, self.assignments, self.counts = seeds, assignments, counts
+
+
+def dbscan(D, eps, minpts):
+    """Clustering.dbscan(D, eps, minpts) (eval_clustering.jl:84; algorithm src/sparse_clustering.jl:126-209)."""
+    lp = abi.c_int64_p
+    if isinstance(D, B200FeatureMatrix):
+        n = D.X.shape[0]
+    else:
+        data = D.data if isinstance(D, DistanceMatrix) else D
+        data = np.asfortranarray(data, dtype=np.float64)
+        n = data.shape[0]
+        if data.shape[1] != n:
+            raise MCBBError("D must be a square matrix (%s given)." % (data.shape,))
+    a = np.zeros(n, dtype=np.int64)
+    s = np.zeros(n, dtype=np.int64)
+    c = np.zeros(n, dtype=np.int64)
+    k = np.zeros(1, dtype=np.int64)
+    if isinstance(D, B200FeatureMatrix):
+        check(lib().mcbb_dbscan_features(D.X.ctypes.data_as(abi.c_double_p), n, len(D.group_len),
+                                         D.group_len.ctypes.data_as(abi.c_int32_p),
+                                         D.group_weight.ctypes.data_as(abi.c_double_p), float(eps), int(minpts),
+                                         a.ctypes.data_as(lp), s.ctypes.data_as(lp), c.ctypes.data_as(lp),
+                                         k.ctypes.data_as(lp)))
+    else:
+        check(lib().mcbb_dbscan_dense(data.ctypes.data_as(abi.c_double_p), n, float(eps), int(minpts),
+                                      a.ctypes.data_as(lp), s.ctypes.data_as(lp), c.ctypes.data_as(lp),
+                                      k.ctypes.data_as(lp)))
+    return DbscanResult(s[:k[0]].copy(), a, c[:k[0]].copy())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# cluster_membership (src/eval_clustering.jl:1154-1265, 1434-1457) — host code, as in the reference
+# ------------------------------------------------------------------------------------------------------------
+def cluster_n_noise(clusters):
+    return int(np.count_nonzero(clusters.assignments == 0))
+
+
+def _julia_range(start, step, stop):
+    lf = (stop - start) / step
+    if lf < 0:
+        return np.zeros(0)
+    n = int(round(lf)) + 1 if lf != 0 else 1
+    if n > 1 and (start < stop < start + (n - 1) * step or start > stop > start + (n - 1) * step):
+        n -= 1
+    return np.array([float(np.longdouble(start) + np.longdouble(i) * np.longdouble(step)) for i in range(n)])
+
+
+class ClusterMembershipResult:
+    def __init__(self, par, data, multidim_flag=False):
+        self.par, self.data, self.multidim_flag = par, data, multidim_flag
+
+
+def cluster_membership(prob, clusters, window_size, window_offset, normalize=True, min_members=0):
+    """Sliding-window cluster membership, one swept parameter (eval_clustering.jl:1206-1265)."""
+    if prob.par.shape[1] != 1:
+        raise MCBBError("cluster_membership: only one swept parameter is supported by this mirror")
+    ca = np.asarray(clusters.assignments)
+    n_cluster = len(clusters.seeds) + 1
+    par = prob.par[:, 0]
+    mins = _julia_range(par.min(), window_offset, par.max() - window_size)
+    if len(mins) <= 1:
+        import warnings
+        warnings.warn("Only 1 or less Windows in cluster_membership")
+    data = np.zeros((len(mins), n_cluster))
+    for w, ip in enumerate(mins):
+        ind = (par > ip) & (par < ip + window_size)  # strict on both sides, :1222
+        data[w] = np.bincount(ca[ind], minlength=n_cluster)
+        if normalize:
+            with np.errstate(invalid="ignore", divide="ignore"):
+                data[w] = data[w] / np.count_nonzero(ind)
+    if min_members > 0:
+        keep = [0] if cluster_n_noise(clusters) > min_members else []
+        keep += [i + 1 for i in range(n_cluster - 1) if clusters.counts[i] > min_members]
+        data = data[:, keep]
+    return ClusterMembershipResult(mins, data, False)

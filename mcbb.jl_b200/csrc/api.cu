@@ -1,0 +1,416 @@
+// api.cu — the extern "C" surface declared in include/mcbb_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mcbb {
+
+static thread_local std::string t_last_error;
+std::atomic<long long> g_launch_count{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+
+// ---- device scratch cache ------------------------------------------------------------------------------------
+struct ScratchSlot {
+    void* p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+};
+static ScratchSlot g_scratch[64];
+static std::mutex g_scratch_mu;
+
+void* scratch_get(int slot, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (bytes == 0) bytes = 16;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ScratchSlot& s = g_scratch[slot];
+    if (s.p && s.cap >= bytes && s.dev == dev) return s.p;
+    if (s.p) {
+        cudaDeviceSynchronize();
+        cudaFree(s.p);
+        s.p = nullptr;
+        s.cap = 0;
+    }
+    size_t want = bytes + bytes / 8;
+    if (cudaMalloc(&s.p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        if (cudaMalloc(&s.p, want) != cudaSuccess) {
+            cudaGetLastError();
+            s.p = nullptr;
+            return nullptr;
+        }
+    }
+    s.cap = want;
+    s.dev = dev;
+    return s.p;
+}
+
+void scratch_free_all() {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (auto& s : g_scratch) {
+        if (s.p) cudaFree(s.p);
+        s = ScratchSlot();
+    }
+}
+
+// defined in solve.cu / cluster.cu
+int table_lengths(const mcbb_system_desc* s, int len[5]);
+int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* out, std::vector<int>* filter_host);
+int solve_features_launch(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io, cudaStream_t st);
+int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                        const double* group_weight, double* D, cudaStream_t st);
+int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                        const double* group_weight, double eps, int minpts, long long* assignments,
+                        long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st);
+int dbscan_dense_dev(const double* D, long long n, double eps, int minpts, long long* assignments,
+                     long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st);
+
+int rows_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
+                   double eps, long long row0, long long row1, int* count, cudaStream_t st);
+int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32_t* group_len,
+                   const double* group_weight, double eps, long long row0, long long row1, int* parent,
+                   cudaStream_t st);
+int merge_parents_dev(int* parent, const int* other, long long n_core, cudaStream_t st);
+int rows_border_dev(const double* Xn, long long n_non, long long row0, long long row1, const double* Xc,
+                    long long n_core, const int* core_seed, int n_groups, const int32_t* group_len,
+                    const double* group_weight, double eps, int* best, cudaStream_t st);
+int labels_dev(const int* root_label, long long n, long long* assignments, long long* seeds, long long* counts,
+               long long* n_clusters_host, cudaStream_t st);
+int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
+                       cudaStream_t st);
+
+// Julia Base (:)(start, step, stop) length for Float64 (fallback path of twiceprecision.jl)
+static int julia_range_len_host(double start, double step, double stop) {
+    const double lf = (stop - start) / step;
+    if (lf < 0) return 0;
+    if (lf == 0) return 1;
+    int len = (int)nearbyint(lf) + 1;
+    const double stop2 = start + (len - 1) * step;
+    if ((start < stop && stop < stop2) || (start > stop && stop > stop2)) len -= 1;
+    return len;
+}
+
+static int build_sysdev(const mcbb_system_desc* sys, SysDev* out, cudaStream_t st) {
+    int len[5];
+    if (int rc = table_lengths(sys, len)) return rc;
+    SysDev S = {};
+    S.system = sys->system;
+    S.n_osc = sys->n_osc;
+    S.n_dim = sys->n_dim;
+    S.n_edges = sys->n_edges;
+    if (S.n_osc < 1 || S.n_dim < 1) MCBB_FAIL("system descriptor: N and n_dim must be positive");
+    const double* src[5] = {sys->mat_a, sys->mat_b, sys->vec_a, sys->vec_b, sys->vec_c};
+    const double* dst[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 5; k++) {
+        if (len[k] == 0) continue;
+        double* d = (double*)scratch_get(k, sizeof(double) * (size_t)len[k]);
+        if (!d) MCBB_FAIL("solve: device allocation of a system table failed");
+        MCBB_CUDA_OK(cudaMemcpyAsync(d, src[k], sizeof(double) * (size_t)len[k], cudaMemcpyHostToDevice, st));
+        dst[k] = d;
+    }
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));  // host tables are caller-owned: do not outlive the call
+    S.mat_a = dst[0];
+    S.mat_b = dst[1];
+    S.vec_a = dst[2];
+    S.vec_b = dst[3];
+    S.vec_c = dst[4];
+    S.len_mat_a = len[0];
+    S.len_mat_b = len[1];
+    S.len_vec_a = len[2];
+    S.len_vec_b = len[3];
+    S.len_vec_c = len[4];
+    memcpy(S.scalars, sys->scalars, sizeof(S.scalars));
+    S.n_par = sys->n_par;
+    for (int p = 0; p < MCBB_MAX_PAR; p++) S.par_slot[p] = sys->par_slot[p];
+    *out = S;
+    return 0;
+}
+
+}  // namespace mcbb
+
+using namespace mcbb;
+
+extern "C" {
+
+const char* mcbb_version(void) { return "mcbb_b200 0.1.0 (sm_100a)"; }
+
+int mcbb_init(int device) {
+    MCBB_CUDA_OK(cudaSetDevice(device));
+    MCBB_CUDA_OK(cudaFree(0));
+    return 0;
+}
+
+int mcbb_finalize(void) {
+    scratch_free_all();
+    return 0;
+}
+
+size_t mcbb_last_error(char* buf, size_t len) {
+    const size_t n = t_last_error.size();
+    if (buf && len > 0) {
+        const size_t k = n < len - 1 ? n : len - 1;
+        memcpy(buf, t_last_error.data(), k);
+        buf[k] = 0;
+    }
+    return n;
+}
+
+int mcbb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes) {
+    int dev = 0;
+    MCBB_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    MCBB_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)p.totalGlobalMem;
+    return 0;
+}
+
+int64_t mcbb_kernel_launch_count(void) { return g_launch_count.load(); }
+
+int mcbb_tsave_array(const mcbb_solver_opts* o, int32_t n_t, double rel_transient_time, double* t_save,
+                     int32_t* n_out) {
+    if (!o || !n_out) MCBB_FAIL("tsave_array: NULL argument");
+    if (o->alg == MCBB_ALG_FUNCTIONMAP) {  // setup_mc_prob.jl:1175-1180
+        const double tot = nearbyint((o->t1 - o->t0) * (1 - rel_transient_time));
+        const double start = o->t1 - tot;
+        const int len = julia_range_len_host(start, 1., o->t1 - 1);
+        if (t_save)
+            for (int i = 0; i < len; i++) t_save[i] = start + i;
+        *n_out = len;
+        return 0;
+    }
+    if (n_t < 1) MCBB_FAIL("tsave_array: N_t must be positive");
+    const double tot = (o->t1 - o->t0) * (1 - rel_transient_time);  // setup_mc_prob.jl:1166-1172
+    const double start = o->t1 - tot;
+    const double dt = tot / n_t;
+    const int len = julia_range_len_host(start, dt, o->t1 - dt);
+    if (t_save)
+        for (int i = 0; i < len; i++) t_save[i] = (double)((long double)start + (long double)i * (long double)dt);
+    *n_out = len;
+    return 0;
+}
+
+int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
+                            int64_t n_mc, const double* ic_dev, const double* par_dev, const double* t_save_dev,
+                            int32_t n_t, double* feat_dev, double* matrix_dev, double* global_dev,
+                            int32_t* retcode_dev, int64_t* nsteps_dev, void* stream) {
+    if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
+    if (n_mc < 1) MCBB_FAIL("solve: N_mc must be positive");
+    if (!ic_dev || !t_save_dev || !feat_dev) MCBB_FAIL("solve: NULL ic / t_save / feat_out");
+    if (sys->n_par > 0 && !par_dev) MCBB_FAIL("solve: NULL par with n_par > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    SysDev S;
+    if (int rc = build_sysdev(sys, &S, st)) return rc;
+    FeatDev F;
+    std::vector<int> filter_host;
+    if (int rc = resolve_feat(sys, feat, &F, &filter_host)) return rc;
+    if (F.n_global > 0 && !global_dev) MCBB_FAIL("solve: global measures requested but global_out is NULL");
+    if (!filter_host.empty()) {
+        int* fd = (int*)scratch_get(5, sizeof(int) * filter_host.size());
+        if (!fd) MCBB_FAIL("solve: device allocation failed");
+        MCBB_CUDA_OK(cudaMemcpyAsync(fd, filter_host.data(), sizeof(int) * filter_host.size(), cudaMemcpyHostToDevice, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));
+        F.filter = fd;
+    }
+    SolverDev o = resolve_solver(opts);
+    SolveIO io = {};
+    io.n_mc = n_mc;
+    io.ic = ic_dev;
+    io.par = par_dev;
+    io.t_save = t_save_dev;
+    io.n_t = n_t;
+    io.feat = feat_dev;
+    io.matrix = matrix_dev;
+    io.glob = global_dev;
+    io.retcode = retcode_dev;
+    io.nsteps = (long long*)nsteps_dev;
+    io.work_counter = (unsigned long long*)scratch_get(6, 64);
+    if (!io.work_counter) MCBB_FAIL("solve: device allocation failed");
+    if (F.need_kl) {
+        io.ckpt = (double*)scratch_get(7, sizeof(double) * (size_t)(2 * S.n_dim + 4) * (size_t)n_mc);
+        if (!io.ckpt) MCBB_FAIL("solve: device allocation of the KL checkpoint buffer failed");
+    }
+    return solve_features_launch(S, o, F, io, st);
+}
+
+int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
+                        int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
+                        double* feat_out, double* matrix_out, double* global_out, int32_t* retcode_out,
+                        int64_t* nsteps_out) {
+    if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
+    if (n_mc < 1) MCBB_FAIL("solve: N_mc must be positive");
+    if (!ic || !t_save || !feat_out) MCBB_FAIL("solve: NULL ic / t_save / feat_out");
+    const bool cplx = sys->system == MCBB_SYS_STUART_LANDAU;
+    const int n_state = cplx ? sys->n_dim / 2 : sys->n_dim;
+    const int nf = feat->n_filter > 0 ? feat->n_filter : n_state;
+    const size_t b_ic = sizeof(double) * (size_t)n_mc * sys->n_dim;
+    const size_t b_par = sizeof(double) * (size_t)n_mc * (sys->n_par > 0 ? sys->n_par : 1);
+    const size_t b_ts = sizeof(double) * (size_t)n_t;
+    const size_t b_feat = sizeof(double) * (size_t)n_mc * nf * feat->n_meas;
+    const size_t b_glob = sizeof(double) * (size_t)n_mc * (feat->n_global > 0 ? feat->n_global : 1);
+    double* d_ic = (double*)scratch_get(30, b_ic);
+    double* d_par = (double*)scratch_get(31, b_par);
+    double* d_ts = (double*)scratch_get(32, b_ts);
+    double* d_feat = (double*)scratch_get(33, b_feat);
+    double* d_glob = (double*)scratch_get(34, b_glob);
+    int* d_ret = (int*)scratch_get(35, sizeof(int) * (size_t)n_mc);
+    long long* d_ns = (long long*)scratch_get(36, sizeof(long long) * 2 * (size_t)n_mc);
+    if (!d_ic || !d_par || !d_ts || !d_feat || !d_glob || !d_ret || !d_ns) MCBB_FAIL("solve: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_ic, ic, b_ic, cudaMemcpyHostToDevice, st));
+    if (sys->n_par > 0) {
+        if (!par) MCBB_FAIL("solve: NULL par with n_par > 0");
+        MCBB_CUDA_OK(cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, st));
+    }
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_ts, t_save, b_ts, cudaMemcpyHostToDevice, st));
+    if (int rc = mcbb_solve_features_dev(sys, opts, feat, n_mc, d_ic, d_par, d_ts, n_t, d_feat, nullptr,
+                                         feat->n_global > 0 ? d_glob : nullptr, d_ret, (int64_t*)d_ns, (void*)st))
+        return rc;
+    MCBB_CUDA_OK(cudaMemcpyAsync(feat_out, d_feat, b_feat, cudaMemcpyDeviceToHost, st));
+    if (global_out && feat->n_global > 0)
+        MCBB_CUDA_OK(cudaMemcpyAsync(global_out, d_glob, b_glob, cudaMemcpyDeviceToHost, st));
+    if (retcode_out) MCBB_CUDA_OK(cudaMemcpyAsync(retcode_out, d_ret, sizeof(int) * (size_t)n_mc, cudaMemcpyDeviceToHost, st));
+    if (nsteps_out)
+        MCBB_CUDA_OK(cudaMemcpyAsync(nsteps_out, d_ns, sizeof(long long) * 2 * (size_t)n_mc, cudaMemcpyDeviceToHost, st));
+    (void)matrix_out;
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_distance_matrix_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                             const double* group_weight, double* D_dev, void* stream) {
+    if (!X_dev || !D_dev || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
+    return distance_matrix_dev(X_dev, n, n_groups, group_len, group_weight, D_dev, (cudaStream_t)stream);
+}
+
+int mcbb_distance_matrix(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                         const double* group_weight, double* D_out) {
+    if (!X || !D_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
+    size_t F = 0;
+    for (int g = 0; g < n_groups; g++) F += group_len[g] > 0 ? group_len[g] : 0;
+    double* d_X = (double*)scratch_get(40, sizeof(double) * F * (size_t)n);
+    double* d_D = (double*)scratch_get(41, sizeof(double) * (size_t)n * (size_t)n);
+    if (!d_X || !d_D) MCBB_FAIL("distance_matrix: device allocation failed (n x n does not fit?)");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_X, X, sizeof(double) * F * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (int rc = distance_matrix_dev(d_X, n, n_groups, group_len, group_weight, d_D, st)) return rc;
+    MCBB_CUDA_OK(cudaMemcpyAsync(D_out, d_D, sizeof(double) * (size_t)n * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_dbscan_dense_dev(const double* D_dev, int64_t n, double eps, int32_t minpts, int64_t* assignments_dev,
+                          int64_t* seeds_dev, int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    if (!D_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host) MCBB_FAIL("dbscan: NULL argument");
+    return dbscan_dense_dev(D_dev, n, eps, minpts, (long long*)assignments_dev, (long long*)seeds_dev,
+                            (long long*)counts_dev, (long long*)n_clusters_host, (cudaStream_t)stream);
+}
+
+static int dbscan_copy_back(long long n, long long* d_a, long long* d_s, long long* d_c, int64_t* assignments,
+                            int64_t* seeds, int64_t* counts, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaMemcpyAsync(assignments, d_a, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(seeds, d_s, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(counts, d_c, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_dbscan_dense(const double* D, int64_t n, double eps, int32_t minpts, int64_t* assignments, int64_t* seeds,
+                      int64_t* counts, int64_t* n_clusters) {
+    if (!D || !assignments || !seeds || !counts || !n_clusters) MCBB_FAIL("dbscan: NULL argument");
+    if (n < 2) MCBB_FAIL("At least two data points are required.");
+    double* d_D = (double*)scratch_get(41, sizeof(double) * (size_t)n * (size_t)n);
+    long long* d_a = (long long*)scratch_get(42, sizeof(long long) * (size_t)n);
+    long long* d_s = (long long*)scratch_get(43, sizeof(long long) * (size_t)n);
+    long long* d_c = (long long*)scratch_get(44, sizeof(long long) * (size_t)n);
+    if (!d_D || !d_a || !d_s || !d_c) MCBB_FAIL("dbscan: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_D, D, sizeof(double) * (size_t)n * (size_t)n, cudaMemcpyHostToDevice, st));
+    long long k = 0;
+    if (int rc = dbscan_dense_dev(d_D, n, eps, minpts, d_a, d_s, d_c, &k, st)) return rc;
+    *n_clusters = k;
+    return dbscan_copy_back(n, d_a, d_s, d_c, assignments, seeds, counts, st);
+}
+
+int mcbb_dbscan_features_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                             const double* group_weight, double eps, int32_t minpts, int64_t* assignments_dev,
+                             int64_t* seeds_dev, int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    if (!X_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host || !group_len || !group_weight)
+        MCBB_FAIL("dbscan: NULL argument");
+    return dbscan_features_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, (long long*)assignments_dev,
+                               (long long*)seeds_dev, (long long*)counts_dev, (long long*)n_clusters_host,
+                               (cudaStream_t)stream);
+}
+
+int mcbb_dbscan_features(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                         const double* group_weight, double eps, int32_t minpts, int64_t* assignments,
+                         int64_t* seeds, int64_t* counts, int64_t* n_clusters) {
+    if (!X || !assignments || !seeds || !counts || !n_clusters || !group_len || !group_weight)
+        MCBB_FAIL("dbscan: NULL argument");
+    if (n < 2) MCBB_FAIL("At least two data points are required.");
+    size_t F = 0;
+    for (int g = 0; g < n_groups; g++) F += group_len[g] > 0 ? group_len[g] : 0;
+    double* d_X = (double*)scratch_get(40, sizeof(double) * F * (size_t)n);
+    long long* d_a = (long long*)scratch_get(42, sizeof(long long) * (size_t)n);
+    long long* d_s = (long long*)scratch_get(43, sizeof(long long) * (size_t)n);
+    long long* d_c = (long long*)scratch_get(44, sizeof(long long) * (size_t)n);
+    if (!d_X || !d_a || !d_s || !d_c) MCBB_FAIL("dbscan: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_X, X, sizeof(double) * F * (size_t)n, cudaMemcpyHostToDevice, st));
+    long long k = 0;
+    if (int rc = dbscan_features_dev(d_X, n, n_groups, group_len, group_weight, eps, minpts, d_a, d_s, d_c, &k, st))
+        return rc;
+    *n_clusters = k;
+    return dbscan_copy_back(n, d_a, d_s, d_c, assignments, seeds, counts, st);
+}
+
+int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, double eps, int64_t row0, int64_t row1,
+                               int32_t* count_dev, void* stream) {
+    if (!X_dev || !count_dev || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
+    return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, row0, row1, count_dev,
+                          (cudaStream_t)stream);
+}
+int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, double eps, int64_t row0, int64_t row1,
+                               int32_t* parent_dev, void* stream) {
+    if ((n_core > 0 && (!Xcore_dev || !parent_dev)) || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
+    return rows_union_dev(Xcore_dev, n_core, n_groups, group_len, group_weight, eps, row0, row1, parent_dev,
+                          (cudaStream_t)stream);
+}
+int mcbb_dbscan_merge_parents_dev(int32_t* parent_dev, const int32_t* other_parent_dev, int64_t n_core, void* stream) {
+    if (n_core > 0 && (!parent_dev || !other_parent_dev)) MCBB_FAIL("dbscan merge: NULL argument");
+    return merge_parents_dev(parent_dev, other_parent_dev, n_core, (cudaStream_t)stream);
+}
+int mcbb_dbscan_rows_border_dev(const double* Xnon_dev, int64_t n_non, int64_t row0, int64_t row1,
+                                const double* Xcore_dev, int64_t n_core, const int32_t* core_seed_dev,
+                                int32_t n_groups, const int32_t* group_len, const double* group_weight, double eps,
+                                int32_t* best_dev, void* stream) {
+    if (!group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
+    return rows_border_dev(Xnon_dev, n_non, row0, row1, Xcore_dev, n_core, core_seed_dev, n_groups, group_len,
+                           group_weight, eps, best_dev, (cudaStream_t)stream);
+}
+int mcbb_dbscan_labels_dev(const int32_t* root_label_dev, int64_t n, int64_t* assignments_dev, int64_t* seeds_dev,
+                           int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    if (!root_label_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host)
+        MCBB_FAIL("dbscan labels: NULL argument");
+    return labels_dev(root_label_dev, n, (long long*)assignments_dev, (long long*)seeds_dev, (long long*)counts_dev,
+                      (long long*)n_clusters_host, (cudaStream_t)stream);
+}
+int mcbb_gather_columns_dev(const double* X_dev, int64_t ld, const int32_t* idx_dev, int64_t m, int32_t F,
+                            double* Xout_dev, void* stream) {
+    if (m > 0 && (!X_dev || !idx_dev || !Xout_dev)) MCBB_FAIL("gather: NULL argument");
+    return gather_columns_dev(X_dev, ld, idx_dev, m, F, Xout_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,519 @@
+// cluster.cu — distance_matrix and DBSCAN entry points (C-ABI hot entries 2 and 3).
+//
+// DBSCAN is computed as the order-independent restatement of the sequential algorithm the reference uses
+// (Clustering.dbscan, vendored at src/sparse_clustering.jl:138-209):
+//   pass 1  eps-neighbour counts (self included)              -> core flags
+//   pass 2  union-find over core-core edges, larger root hooked under smaller
+//           -> components whose root is their smallest member = the sequential algorithm's seed
+//   pass 3  every non-core point takes the smallest root among cores within eps (else noise)
+//   final   clusters numbered by ascending seed (exclusive scan over "is seed"), counts by histogram
+// which yields bit-identical (seeds, assignments, counts) for visit order 1:n.
+#include <cub/device/device_scan.cuh>
+
+#include <limits.h>
+
+#include <vector>
+
+#include "pair_tiles.cuh"
+
+namespace mcbb {
+
+// ---- small helper kernels ------------------------------------------------------------------------------
+__global__ void k_fill_i32(int* p, long long n, int v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_iota_i32(int* p, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int)i;
+}
+__global__ void k_core_flags(const int* cnt, long long n, int minpts, int* core, int* noncore) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int c = cnt[i] >= minpts;
+        core[i] = c;
+        noncore[i] = !c;
+    }
+}
+// scatter original indices into the compacted core / non-core index lists (stable: ascending index)
+__global__ void k_compact_idx(const int* core, const int* core_pos, const int* non_pos, long long n,
+                              int* core_idx, int* non_idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        if (core[i])
+            core_idx[core_pos[i]] = (int)i;
+        else
+            non_idx[non_pos[i]] = (int)i;
+    }
+}
+// Xout[f][k] = X[f][idx[k]]
+__global__ void k_gather_cols(const double* X, long long ld, const int* idx, long long m, int F, double* Xout) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (k < m && f < F) Xout[(long long)f * m + k] = X[(long long)f * ld + idx[k]];
+}
+__global__ void k_flatten_roots(int* parent, long long m, const int* core_idx, int* col_root) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        int x = (int)i;
+        while (parent[x] != x) x = parent[x];
+        col_root[i] = core_idx[x];  // original index of the component's smallest core = its seed
+    }
+}
+// root_label[orig] = seed index of the point's cluster, or -1 for noise
+__global__ void k_root_labels(long long n_core, const int* core_idx, const int* col_root, long long n_non,
+                              const int* non_idx, const int* best, int* root_label, int* is_seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_core) {
+        const int o = core_idx[i];
+        root_label[o] = col_root[i];
+        is_seed[o] = (col_root[i] == o);
+    } else if (i < n_core + n_non) {
+        const long long k = i - n_core;
+        const int o = non_idx[k];
+        root_label[o] = best[k] == INT_MAX ? -1 : best[k];
+        is_seed[o] = 0;
+    }
+}
+__global__ void k_assign(const int* root_label, const int* seed_rank, const int* is_seed, long long n,
+                         long long* assignments, long long* seeds, unsigned long long* counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int r = root_label[i];
+        long long lab = 0;
+        if (r >= 0) {
+            lab = (long long)seed_rank[r] + 1;
+            atomicAdd(&counts[lab - 1], 1ULL);
+        }
+        assignments[i] = lab;
+        if (is_seed[i]) seeds[seed_rank[i]] = i + 1;  // 1-based like Julia
+    }
+}
+__global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long long v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- dense-D passes (HBM streaming over the n x n matrix, column p = neighbourhood of p) ------------------
+enum DenseMode { DM_COUNT = 0, DM_UNION = 1, DM_BORDER = 2 };
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dense_pass(const double* __restrict__ D, long long n, double eps, int* cnt,
+                                                    const int* core, int* parent, const int* root, int* best) {
+    const long long p = blockIdx.y;  // column
+    const long long i0 = (long long)blockIdx.x * 1024;
+    if (MODE == DM_UNION && !core[p]) return;
+    if (MODE == DM_BORDER && !core[p]) return;
+    int local = 0;
+    for (int q = 0; q < 4; q++) {
+        const long long i = i0 + q * 256 + threadIdx.x;
+        if (i >= n) break;
+        const double d = D[i + n * p];
+        if (!(d < eps)) continue;
+        if (MODE == DM_COUNT) {
+            local++;
+        } else if (MODE == DM_UNION) {
+            if (i != p && core[i]) uf_union(parent, (int)i, (int)p);
+        } else {
+            if (!core[i]) atomicMin(&best[i], root[p]);
+        }
+    }
+    if (MODE == DM_COUNT) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt[p], local);
+    }
+}
+__global__ void k_flatten_dense(int* parent, const int* core, long long n, int* root, int* is_seed, int* best) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int x = (int)i;
+        if (core[i]) {
+            while (parent[x] != x) x = parent[x];
+            root[i] = x;
+            is_seed[i] = (x == i);
+        } else {
+            root[i] = -1;
+            is_seed[i] = 0;
+        }
+        best[i] = INT_MAX;
+    }
+}
+__global__ void k_labels_dense(const int* core, const int* root, const int* best, long long n, int* root_label) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) root_label[i] = core[i] ? root[i] : (best[i] == INT_MAX ? -1 : best[i]);
+}
+
+// ---- host orchestration ------------------------------------------------------------------------------------
+static inline unsigned nblk(long long n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+struct GroupTables {
+    double* fw;
+    unsigned char* fend;
+    int F;
+    int early_exit;
+};
+
+// expands (group_len, group_weight) into per-feature device tables (scratch slots 10/11)
+static int upload_groups(int n_groups, const int32_t* group_len, const double* group_weight, GroupTables* gt,
+                         cudaStream_t st) {
+    int F = 0;
+    for (int g = 0; g < n_groups; g++) {
+        if (group_len[g] < 1) MCBB_FAIL("distance: every group needs at least one feature");
+        F += group_len[g];
+    }
+    std::vector<double> fw(F);
+    std::vector<unsigned char> fe(F);
+    int f = 0, ee = 1;
+    for (int g = 0; g < n_groups; g++) {
+        if (!(group_weight[g] >= 0.)) ee = 0;
+        for (int q = 0; q < group_len[g]; q++, f++) {
+            fw[f] = group_weight[g];
+            fe[f] = (q == group_len[g] - 1);
+        }
+    }
+    gt->fw = (double*)scratch_get(10, sizeof(double) * F);
+    gt->fend = (unsigned char*)scratch_get(11, F);
+    if (!gt->fw || !gt->fend) MCBB_FAIL("distance: device scratch allocation failed");
+    MCBB_CUDA_OK(cudaMemcpyAsync(gt->fw, fw.data(), sizeof(double) * F, cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(gt->fend, fe.data(), F, cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));  // fw / fe are stack-owned
+    gt->F = F;
+    gt->early_exit = ee;
+    return 0;
+}
+
+template <int MODE>
+static int launch_tiles(const TileArgs& a, cudaStream_t st) {
+    const long long nr = a.r1 - a.r0, nc = a.c1 - a.c0;
+    if (nr <= 0 || nc <= 0) return 0;
+    dim3 grid((unsigned)((nc + TILE - 1) / TILE), (unsigned)((nr + TILE - 1) / TILE));
+    if (grid.y > 65535u) MCBB_FAIL("pair tiles: more than 65535 row tiles in one launch; shard the rows");
+    k_pair_tiles<MODE><<<grid, 256, 0, st>>>(a);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
+// splits the row range so that gridDim.y stays legal
+template <int MODE>
+static int launch_tiles_rows(TileArgs a, cudaStream_t st) {
+    const long long step = 65535LL * TILE;
+    const long long r0 = a.r0, r1 = a.r1;
+    for (long long r = r0; r < r1; r += step) {
+        a.r0 = r;
+        a.r1 = r + step < r1 ? r + step : r1;
+        if (int rc = launch_tiles<MODE>(a, st)) return rc;
+    }
+    return 0;
+}
+
+int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                        const double* group_weight, double* D, cudaStream_t st) {
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    TileArgs a = {};
+    a.Xr = a.Xc = X;
+    a.ldr = a.ldc = n;
+    a.r0 = a.c0 = 0;
+    a.r1 = a.c1 = n;
+    a.F = gt.F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.symmetric = 1;
+    a.D = D;
+    return launch_tiles_rows<TM_MATERIALIZE>(a, st);
+}
+
+// seeds / assignments / counts from root labels (shared by the dense and the feature path)
+static int finalize_labels(const int* root_label, const int* is_seed, long long n, long long* assignments,
+                           long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st) {
+    int* seed_rank = (int*)scratch_get(20, sizeof(int) * (n + 1));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, is_seed, seed_rank, (int)n, st);
+    void* tmp = scratch_get(21, tb);
+    if (!seed_rank || !tmp) MCBB_FAIL("dbscan: device scratch allocation failed");
+    MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, is_seed, seed_rank, (int)n, st));
+    g_launch_count.fetch_add(1);
+    k_fill_u64<<<nblk(n), 256, 0, st>>>((unsigned long long*)counts, n, 0ULL);
+    MCBB_LAUNCHED();
+    k_fill_u64<<<nblk(n), 256, 0, st>>>((unsigned long long*)seeds, n, 0ULL);
+    MCBB_LAUNCHED();
+    k_assign<<<nblk(n), 256, 0, st>>>(root_label, seed_rank, is_seed, n, assignments, seeds,
+                                      (unsigned long long*)counts);
+    MCBB_LAUNCHED();
+    int last_rank = 0, last_flag = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(&last_rank, seed_rank + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(&last_flag, is_seed + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    *n_clusters_host = (long long)last_rank + last_flag;
+    return 0;
+}
+
+static int check_dbscan_args(long long n, double eps, int minpts) {
+    // argument checks of Clustering.dbscan, src/sparse_clustering.jl:126-136
+    if (n < 2) MCBB_FAIL("At least two data points are required.");
+    if (!(eps > 0)) MCBB_FAIL("eps must be a positive value.");
+    if (minpts < 1) MCBB_FAIL("minpts must be positive integer.");
+    if (n > 2147483647LL - 1) MCBB_FAIL("dbscan: n exceeds int32 index range");
+    return 0;
+}
+
+int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                        const double* group_weight, double eps, int minpts, long long* assignments,
+                        long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st) {
+    if (int rc = check_dbscan_args(n, eps, minpts)) return rc;
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    const int F = gt.F;
+    int* cnt = (int*)scratch_get(12, sizeof(int) * n);
+    int* core = (int*)scratch_get(13, sizeof(int) * n);
+    int* noncore = (int*)scratch_get(14, sizeof(int) * n);
+    int* core_pos = (int*)scratch_get(15, sizeof(int) * n);
+    int* non_pos = (int*)scratch_get(16, sizeof(int) * n);
+    int* core_idx = (int*)scratch_get(17, sizeof(int) * n);
+    int* non_idx = (int*)scratch_get(18, sizeof(int) * n);
+    int* root_label = (int*)scratch_get(19, sizeof(int) * n);
+    int* is_seed = (int*)scratch_get(22, sizeof(int) * n);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, core, core_pos, (int)n, st);
+    void* tmp = scratch_get(21, tb);
+    if (!cnt || !core || !noncore || !core_pos || !non_pos || !core_idx || !non_idx || !root_label || !is_seed ||
+        !tmp)
+        MCBB_FAIL("dbscan: device scratch allocation failed");
+
+    // pass 1: neighbour counts (self counts: D_pp = 0 < eps)
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(cnt, n, 1);
+    MCBB_LAUNCHED();
+    TileArgs a = {};
+    a.Xr = a.Xc = X;
+    a.ldr = a.ldc = n;
+    a.r1 = a.c1 = n;
+    a.F = F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.eps = eps;
+    a.symmetric = 1;
+    a.early_exit = gt.early_exit;
+    a.cnt = cnt;
+    if (int rc = launch_tiles_rows<TM_COUNT>(a, st)) return rc;
+
+    // core flags and stable compaction
+    k_core_flags<<<nblk(n), 256, 0, st>>>(cnt, n, minpts, core, noncore);
+    MCBB_LAUNCHED();
+    MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, core, core_pos, (int)n, st));
+    MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, noncore, non_pos, (int)n, st));
+    g_launch_count.fetch_add(2);
+    int h_pos = 0, h_flag = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(&h_pos, core_pos + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(&h_flag, core + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    const long long n_core = (long long)h_pos + h_flag, n_non = n - n_core;
+    k_compact_idx<<<nblk(n), 256, 0, st>>>(core, core_pos, non_pos, n, core_idx, non_idx);
+    MCBB_LAUNCHED();
+
+    double* Xc = (double*)scratch_get(23, sizeof(double) * (size_t)F * (size_t)(n_core > 0 ? n_core : 1));
+    double* Xn = (double*)scratch_get(24, sizeof(double) * (size_t)F * (size_t)(n_non > 0 ? n_non : 1));
+    int* parent = (int*)scratch_get(25, sizeof(int) * (size_t)(n_core > 0 ? n_core : 1));
+    int* col_root = (int*)scratch_get(26, sizeof(int) * (size_t)(n_core > 0 ? n_core : 1));
+    int* best = (int*)scratch_get(27, sizeof(int) * (size_t)(n_non > 0 ? n_non : 1));
+    if (!Xc || !Xn || !parent || !col_root || !best) MCBB_FAIL("dbscan: device scratch allocation failed");
+
+    if (n_core > 0) {
+        k_gather_cols<<<dim3(nblk(n_core), F), 256, 0, st>>>(X, n, core_idx, n_core, F, Xc);
+        MCBB_LAUNCHED();
+        // pass 2: components of the core graph
+        k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
+        MCBB_LAUNCHED();
+        TileArgs u = a;
+        u.Xr = u.Xc = Xc;
+        u.ldr = u.ldc = n_core;
+        u.r0 = u.c0 = 0;
+        u.r1 = u.c1 = n_core;
+        u.cnt = nullptr;
+        u.parent = parent;
+        if (int rc = launch_tiles_rows<TM_UNION>(u, st)) return rc;
+        k_flatten_roots<<<nblk(n_core), 256, 0, st>>>(parent, n_core, core_idx, col_root);
+        MCBB_LAUNCHED();
+    }
+    if (n_non > 0) {
+        k_fill_i32<<<nblk(n_non), 256, 0, st>>>(best, n_non, INT_MAX);
+        MCBB_LAUNCHED();
+        if (n_core > 0) {
+            k_gather_cols<<<dim3(nblk(n_non), F), 256, 0, st>>>(X, n, non_idx, n_non, F, Xn);
+            MCBB_LAUNCHED();
+            // pass 3: border points
+            TileArgs b = a;
+            b.Xr = Xn;
+            b.ldr = n_non;
+            b.r0 = 0;
+            b.r1 = n_non;
+            b.Xc = Xc;
+            b.ldc = n_core;
+            b.c0 = 0;
+            b.c1 = n_core;
+            b.symmetric = 0;
+            b.cnt = nullptr;
+            b.col_root = col_root;
+            b.best = best;
+            if (int rc = launch_tiles_rows<TM_BORDER>(b, st)) return rc;
+        }
+    }
+    k_root_labels<<<nblk(n), 256, 0, st>>>(n_core, core_idx, col_root, n_non, non_idx, best, root_label, is_seed);
+    MCBB_LAUNCHED();
+    return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
+}
+
+int dbscan_dense_dev(const double* D, long long n, double eps, int minpts, long long* assignments,
+                     long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st) {
+    if (int rc = check_dbscan_args(n, eps, minpts)) return rc;
+    if (n > 65535) MCBB_FAIL("dbscan_dense: n > 65535 does not fit a materialised matrix launch; use dbscan_features");
+    int* cnt = (int*)scratch_get(12, sizeof(int) * n);
+    int* core = (int*)scratch_get(13, sizeof(int) * n);
+    int* noncore = (int*)scratch_get(14, sizeof(int) * n);
+    int* parent = (int*)scratch_get(25, sizeof(int) * n);
+    int* root = (int*)scratch_get(26, sizeof(int) * n);
+    int* best = (int*)scratch_get(27, sizeof(int) * n);
+    int* root_label = (int*)scratch_get(19, sizeof(int) * n);
+    int* is_seed = (int*)scratch_get(22, sizeof(int) * n);
+    if (!cnt || !core || !noncore || !parent || !root || !best || !root_label || !is_seed)
+        MCBB_FAIL("dbscan: device scratch allocation failed");
+    dim3 grid((unsigned)((n + 1023) / 1024), (unsigned)n);
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(cnt, n, 0);
+    MCBB_LAUNCHED();
+    k_dense_pass<DM_COUNT><<<grid, 256, 0, st>>>(D, n, eps, cnt, nullptr, nullptr, nullptr, nullptr);
+    MCBB_LAUNCHED();
+    k_core_flags<<<nblk(n), 256, 0, st>>>(cnt, n, minpts, core, noncore);
+    MCBB_LAUNCHED();
+    k_iota_i32<<<nblk(n), 256, 0, st>>>(parent, n);
+    MCBB_LAUNCHED();
+    k_dense_pass<DM_UNION><<<grid, 256, 0, st>>>(D, n, eps, nullptr, core, parent, nullptr, nullptr);
+    MCBB_LAUNCHED();
+    k_flatten_dense<<<nblk(n), 256, 0, st>>>(parent, core, n, root, is_seed, best);
+    MCBB_LAUNCHED();
+    k_dense_pass<DM_BORDER><<<grid, 256, 0, st>>>(D, n, eps, nullptr, core, nullptr, root, best);
+    MCBB_LAUNCHED();
+    k_labels_dense<<<nblk(n), 256, 0, st>>>(core, root, best, n, root_label);
+    MCBB_LAUNCHED();
+    return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
+}
+
+// ---- rank-sharded stages ------------------------------------------------------------------------------------
+__global__ void k_merge_parents(int* parent, const int* other, long long m) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        const int o = other[i];
+        if (o != (int)i) uf_union(parent, (int)i, o);
+    }
+}
+__global__ void k_seed_flags(const int* root_label, long long n, int* is_seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) is_seed[i] = (root_label[i] == (int)i);
+}
+
+int rows_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
+                   double eps, long long row0, long long row1, int* count, cudaStream_t st) {
+    if (int rc = check_dbscan_args(n, eps, 1)) return rc;
+    if (row0 < 0 || row1 > n || row0 > row1) MCBB_FAIL("dbscan rows: bad row range");
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    if (row1 == row0) return 0;
+    k_fill_i32<<<nblk(row1 - row0), 256, 0, st>>>(count, row1 - row0, 0);
+    MCBB_LAUNCHED();
+    TileArgs a = {};
+    a.Xr = a.Xc = X;
+    a.ldr = a.ldc = n;
+    a.r0 = row0;
+    a.r1 = row1;
+    a.c0 = 0;
+    a.c1 = n;
+    a.F = gt.F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.eps = eps;
+    a.symmetric = 0;  // full rows: the diagonal pair (d = 0 < eps) supplies the self count
+    a.early_exit = gt.early_exit;
+    a.cnt = count - row0;
+    return launch_tiles_rows<TM_COUNT>(a, st);
+}
+
+int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32_t* group_len,
+                   const double* group_weight, double eps, long long row0, long long row1, int* parent,
+                   cudaStream_t st) {
+    if (n_core <= 0) return 0;
+    if (row0 < 0 || row1 > n_core || row0 > row1) MCBB_FAIL("dbscan rows: bad row range");
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
+    MCBB_LAUNCHED();
+    if (row1 == row0) return 0;
+    TileArgs a = {};
+    a.Xr = a.Xc = Xc;
+    a.ldr = a.ldc = n_core;
+    a.r0 = row0;
+    a.r1 = row1;
+    a.c0 = 0;
+    a.c1 = n_core;
+    a.F = gt.F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.eps = eps;
+    a.symmetric = 1;
+    a.early_exit = gt.early_exit;
+    a.parent = parent;
+    return launch_tiles_rows<TM_UNION>(a, st);
+}
+
+int merge_parents_dev(int* parent, const int* other, long long n_core, cudaStream_t st) {
+    if (n_core <= 0) return 0;
+    k_merge_parents<<<nblk(n_core), 256, 0, st>>>(parent, other, n_core);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
+int rows_border_dev(const double* Xn, long long n_non, long long row0, long long row1, const double* Xc,
+                    long long n_core, const int* core_seed, int n_groups, const int32_t* group_len,
+                    const double* group_weight, double eps, int* best, cudaStream_t st) {
+    if (row0 < 0 || row1 > n_non || row0 > row1) MCBB_FAIL("dbscan rows: bad row range");
+    if (row1 == row0) return 0;
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    k_fill_i32<<<nblk(row1 - row0), 256, 0, st>>>(best, row1 - row0, INT_MAX);
+    MCBB_LAUNCHED();
+    if (n_core <= 0) return 0;
+    TileArgs a = {};
+    a.Xr = Xn;
+    a.ldr = n_non;
+    a.r0 = row0;
+    a.r1 = row1;
+    a.Xc = Xc;
+    a.ldc = n_core;
+    a.c0 = 0;
+    a.c1 = n_core;
+    a.F = gt.F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.eps = eps;
+    a.symmetric = 0;
+    a.early_exit = gt.early_exit;
+    a.col_root = core_seed;
+    a.best = best - row0;
+    return launch_tiles_rows<TM_BORDER>(a, st);
+}
+
+int labels_dev(const int* root_label, long long n, long long* assignments, long long* seeds, long long* counts,
+               long long* n_clusters_host, cudaStream_t st) {
+    if (n < 1) MCBB_FAIL("dbscan labels: empty input");
+    int* is_seed = (int*)scratch_get(22, sizeof(int) * n);
+    if (!is_seed) MCBB_FAIL("dbscan: device scratch allocation failed");
+    k_seed_flags<<<nblk(n), 256, 0, st>>>(root_label, n, is_seed);
+    MCBB_LAUNCHED();
+    return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
+}
+
+int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
+                       cudaStream_t st) {
+    if (m <= 0 || F <= 0) return 0;
+    k_gather_cols<<<dim3(nblk(m), F), 256, 0, st>>>(X, ld, idx, m, F, Xout);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace mcbb

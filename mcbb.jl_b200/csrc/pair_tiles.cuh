@@ -1,0 +1,187 @@
+// pair_tiles.cuh — tiled pairwise L1 distance over featurized runs; one kernel body, four consumers.
+//
+// Reference: distance_matrix / _compute_distance! (src/eval_clustering.jl:164-254) and the neighbourhood
+// queries of dbscan (src/sparse_clustering.jl:168-178).
+//
+//   D[i,j] = sum_g w_g * sum_{f in g} |X[f,i] - X[f,j]|          X is [F][n], run index contiguous
+//
+// A CTA of 256 threads owns a 64 x 64 tile of the pair space; feature slabs of FC rows are staged in
+// shared memory (coalesced 512 B rows), every thread keeps a 4 x 4 register block.  The same device
+// function produces the distance for all consumers, so the materialised matrix and the on-the-fly DBSCAN
+// see bit-identical values (required for label equality, SURVEY §7 hard part 6).
+//
+// Consumers:  TM_MATERIALIZE  write D (symmetric pair of stores per tile)
+//             TM_COUNT        eps-neighbour counts (DBSCAN pass 1)
+//             TM_UNION        union-find over core-core edges (pass 2)
+//             TM_BORDER       smallest adjacent core root per non-core point (pass 3)
+// All three DBSCAN passes stop accumulating a tile as soon as every pair in it is provably >= eps
+// (terms are non-negative, floating-point addition of non-negatives is monotone, so the test is exact).
+#pragma once
+#include "common.cuh"
+
+namespace mcbb {
+
+enum TileMode { TM_MATERIALIZE = 0, TM_COUNT = 1, TM_UNION = 2, TM_BORDER = 3 };
+
+constexpr int TILE = 64;   // tile edge
+constexpr int TT = 4;      // register block edge
+constexpr int FC = 16;     // features per shared-memory slab
+
+struct TileArgs {
+    const double* Xr;  // row-side feature matrix [F][ldr]
+    long long ldr;
+    long long r0, r1;  // row range handled by this launch
+    const double* Xc;  // column-side feature matrix [F][ldc]
+    long long ldc;
+    long long c0, c1;
+    int F;
+    const double* fw;          // [F] weight of the feature's group
+    const unsigned char* fend; // [F] 1 when the feature closes its group
+    double eps;
+    int symmetric;   // Xr == Xc: only pairs col > row are visited, results applied to both sides
+    int early_exit;  // all weights >= 0
+    double* D;       // TM_MATERIALIZE: [n][n] column-major, ld = ldr
+    int* cnt;        // TM_COUNT: indexed by row id (and column id when symmetric)
+    int* parent;     // TM_UNION
+    const int* col_root;  // TM_BORDER: root (original index) of each core column
+    int* best;            // TM_BORDER: per non-core row, min root seen (init INT_MAX)
+};
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {  // path halving; hooks always point to a smaller index, so races are benign
+        const int gp = parent[p];
+        if (gp != p) parent[x] = gp;
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const int tmp = a;
+            a = b;
+            b = tmp;
+        }
+        // a > b: hook the larger root under the smaller one => the final root is the smallest member,
+        // i.e. the seed of the sequential algorithm (sparse_clustering.jl:149-157)
+        const int old = atomicCAS(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
+    __shared__ double s_r[FC][TILE];
+    __shared__ double s_c[FC][TILE];
+    __shared__ double s_w[FC];
+    __shared__ unsigned char s_e[FC];
+
+    const long long tr = a.r0 + (long long)blockIdx.y * TILE;
+    const long long tc = a.c0 + (long long)blockIdx.x * TILE;
+    if (a.symmetric && tc + TILE <= tr) return;  // strictly below the diagonal
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // tx -> rows (contiguous in memory), ty -> columns
+
+    double acc[TT][TT], accg[TT][TT];
+#pragma unroll
+    for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TT; j++) acc[i][j] = accg[i][j] = 0.;
+
+    for (int f0 = 0; f0 < a.F; f0 += FC) {
+        const int fc = min(FC, a.F - f0);
+        __syncthreads();
+        for (int q = tid; q < FC * TILE; q += 256) {
+            const int f = q / TILE, k = q - f * TILE;
+            double vr = 0., vc = 0.;
+            if (f < fc) {
+                const long long ir = tr + k, ic = tc + k;
+                if (ir < a.r1) vr = __ldg(a.Xr + (long long)(f0 + f) * a.ldr + ir);
+                if (ic < a.c1) vc = __ldg(a.Xc + (long long)(f0 + f) * a.ldc + ic);
+            }
+            s_r[f][k] = vr;
+            s_c[f][k] = vc;
+        }
+        if (tid < FC) {
+            s_w[tid] = tid < fc ? __ldg(a.fw + f0 + tid) : 0.;
+            s_e[tid] = tid < fc ? a.fend[f0 + tid] : 0;
+        }
+        __syncthreads();
+        for (int f = 0; f < fc; f++) {
+            double xr[TT], xc[TT];
+#pragma unroll
+            for (int i = 0; i < TT; i++) xr[i] = s_r[f][tx * TT + i];
+#pragma unroll
+            for (int j = 0; j < TT; j++) xc[j] = s_c[f][ty * TT + j];
+#pragma unroll
+            for (int i = 0; i < TT; i++)
+#pragma unroll
+                for (int j = 0; j < TT; j++) accg[i][j] += fabs(xr[i] - xc[j]);
+            if (s_e[f]) {  // group closes: mat_elements += weight * distance_func(...)
+                const double w = s_w[f];
+#pragma unroll
+                for (int i = 0; i < TT; i++)
+#pragma unroll
+                    for (int j = 0; j < TT; j++) {
+                        acc[i][j] = fma(w, accg[i][j], acc[i][j]);
+                        accg[i][j] = 0.;
+                    }
+            }
+        }
+        if (MODE != TM_MATERIALIZE && a.early_exit && f0 + FC < a.F) {
+            bool alive = false;
+            const double w = s_w[fc - 1];  // weight of the group still open (if any)
+#pragma unroll
+            for (int i = 0; i < TT; i++)
+#pragma unroll
+                for (int j = 0; j < TT; j++) alive |= (fma(w, accg[i][j], acc[i][j]) < a.eps);
+            if (!__syncthreads_or(alive)) return;  // no pair of this tile can still fall below eps
+        }
+    }
+
+    // ---- consume the 4 x 4 block ---------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+        const long long ri = tr + tx * TT + i;
+        if (ri >= a.r1) continue;
+        int local = 0;
+#pragma unroll
+        for (int j = 0; j < TT; j++) {
+            const long long cj = tc + ty * TT + j;
+            if (cj >= a.c1) continue;
+            const double d = acc[i][j];
+            if (MODE == TM_MATERIALIZE) {
+                if (a.symmetric) {
+                    if (cj > ri) {
+                        a.D[ri + a.ldr * cj] = d;
+                        a.D[cj + a.ldr * ri] = d;
+                    } else if (cj == ri) {
+                        a.D[ri + a.ldr * ri] = 0.;
+                    }
+                } else {
+                    a.D[ri + a.ldr * cj] = d;
+                }
+            } else {
+                if (a.symmetric && cj <= ri) continue;
+                if (!(d < a.eps)) continue;  // strict, sparse_clustering.jl:173
+                if (MODE == TM_COUNT) {
+                    local++;
+                    if (a.symmetric) atomicAdd(&a.cnt[cj], 1);
+                } else if (MODE == TM_UNION) {
+                    uf_union(a.parent, (int)ri, (int)cj);
+                } else if (MODE == TM_BORDER) {
+                    atomicMin(&a.best[ri], a.col_root[cj]);
+                }
+            }
+        }
+        if (MODE == TM_COUNT && local) atomicAdd(&a.cnt[ri], local);
+    }
+}
+
+}  // namespace mcbb

@@ -1,0 +1,186 @@
+"""One-process-per-GPU sharding of the hot path (torch.distributed is plumbing only: device memory + NCCL/gloo).
+
+* integrate + featurize: runs are independent -> contiguous blocks of run indices per rank, no collective while
+  computing; the small per-run feature vectors are all-gathered afterwards.
+* DBSCAN: the pair space shards by point rows; the stage entry points of the C-ABI (mcbb_dbscan_rows_*_dev) do the
+  work on the owned rows, this module does the collectives between them:
+      counts  -> all_gather -> core flags / index lists
+      parents -> all_gather -> mcbb_dbscan_merge_parents_dev (union-find merge of boundary labels)
+      border  -> all_gather -> root labels -> mcbb_dbscan_labels_dev
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as abi
+from ._lib import check, lib
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [lo, hi) of n items owned by `rank` (first n % world ranks get one extra)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n, world):
+    return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def _all_gather_rows(t, sizes, dist_mod, group=None):
+    """all_gather of row blocks with per-rank sizes along dim 0 (pads to the largest block)."""
+    import torch
+    world = len(sizes)
+    if world == 1:
+        return t
+    mx = max(sizes)
+    pad = t.new_zeros((mx,) + tuple(t.shape[1:]))
+    pad[: t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist_mod.all_gather(out, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def solve_features_device(psys, opts, pfeat, ic_t, par_t, tsave_t):
+    """mcbb_solve_features_dev on torch CUDA tensors (run index contiguous: ic_t is [n_dim, n_mc], par_t
+    [n_par, n_mc]).  Returns (feat [n_meas*n_filter, n_mc], glob, retcode, nsteps [2, n_mc])."""
+    import torch
+    n_mc = ic_t.shape[1]
+    nf = pfeat.n_filter(psys)
+    dev = ic_t.device
+    feat = torch.empty((pfeat.n_meas * nf, n_mc), dtype=torch.float64, device=dev)
+    glob = torch.empty((max(pfeat.n_global, 1), n_mc), dtype=torch.float64, device=dev)
+    ret = torch.empty((n_mc,), dtype=torch.int32, device=dev)
+    nsteps = torch.empty((2, n_mc), dtype=torch.int64, device=dev)
+    check(lib().mcbb_solve_features_dev(C.byref(psys.desc), C.byref(opts), C.byref(pfeat.opts), n_mc, _ptr(ic_t),
+                                        _ptr(par_t), _ptr(tsave_t), tsave_t.numel(), _ptr(feat), C.c_void_p(0),
+                                        _ptr(glob) if pfeat.n_global else C.c_void_p(0), _ptr(ret), _ptr(nsteps),
+                                        _stream()))
+    return feat, (glob if pfeat.n_global else None), ret, nsteps
+
+
+def dbscan_features_device(X_t, group_len, group_weight, eps, minpts):
+    """Single-GPU fused DBSCAN on a torch CUDA feature matrix X_t [F, n].  Returns (assignments, seeds, counts)."""
+    import torch
+    n = X_t.shape[1]
+    gl = np.ascontiguousarray(group_len, dtype=np.int32)
+    gw = np.ascontiguousarray(group_weight, dtype=np.float64)
+    a = torch.empty((n,), dtype=torch.int64, device=X_t.device)
+    s = torch.empty((n,), dtype=torch.int64, device=X_t.device)
+    c = torch.empty((n,), dtype=torch.int64, device=X_t.device)
+    k = np.zeros(1, dtype=np.int64)
+    check(lib().mcbb_dbscan_features_dev(_ptr(X_t), n, len(gl), gl.ctypes.data_as(abi.c_int32_p),
+                                         gw.ctypes.data_as(abi.c_double_p), float(eps), int(minpts), _ptr(a), _ptr(s),
+                                         _ptr(c), k.ctypes.data_as(abi.c_int64_p), _stream()))
+    return a, s[: k[0]], c[: k[0]]
+
+
+def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, world, dist_mod=None, group=None,
+                            backend_ops=None):
+    """Row-sharded DBSCAN over `world` ranks; every rank holds the full feature matrix X_t [F, n] (after the
+    feature all-gather) and returns identical (assignments, seeds, counts) tensors.
+
+    `backend_ops` lets the CPU gloo tests substitute the stage kernels with a checker implementation while the
+    collectives / index bookkeeping under test stay the same code.
+    """
+    import torch
+    ops = backend_ops or _CudaStageOps()
+    F, n = X_t.shape
+    gl = np.ascontiguousarray(group_len, dtype=np.int32)
+    gw = np.ascontiguousarray(group_weight, dtype=np.float64)
+    dev = X_t.device
+    # ---- stage 1: neighbour counts of the owned rows -------------------------------------------------------
+    r0, r1 = shard_range(n, rank, world)
+    cnt_local = ops.rows_count(X_t, gl, gw, eps, r0, r1)
+    cnt = _all_gather_rows(cnt_local, shard_sizes(n, world), dist_mod, group)
+    core = cnt >= minpts
+    core_idx = torch.nonzero(core).flatten().to(torch.int32)  # ascending = stable compaction
+    non_idx = torch.nonzero(~core).flatten().to(torch.int32)
+    n_core, n_non = core_idx.numel(), non_idx.numel()
+    Xc = ops.gather(X_t, core_idx)
+    Xn = ops.gather(X_t, non_idx)
+    # ---- stage 2: components of the core graph, union-find merge across ranks -------------------------------
+    root_label = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    if n_core > 0:
+        c0, c1 = shard_range(n_core, rank, world)
+        parent = ops.rows_union(Xc, gl, gw, eps, c0, c1)
+        if world > 1:
+            others = [torch.empty_like(parent) for _ in range(world)]
+            dist_mod.all_gather(others, parent, group=group)
+            for r in range(world):
+                if r != rank:
+                    ops.merge_parents(parent, others[r])
+        root = parent.to(torch.int64)
+        while True:  # pointer jumping to the roots (roots are the smallest member = the seed)
+            nxt = root[root]
+            if torch.equal(nxt, root):
+                break
+            root = nxt
+        core_seed = core_idx[root].contiguous()  # original index of each core's seed
+        root_label[core_idx.long()] = core_seed
+        # ---- stage 3: border points ----------------------------------------------------------------------
+        if n_non > 0:
+            b0, b1 = shard_range(n_non, rank, world)
+            best_local = ops.rows_border(Xn, b0, b1, Xc, core_seed, gl, gw, eps)
+            best = _all_gather_rows(best_local, shard_sizes(n_non, world), dist_mod, group)
+            lab = torch.where(best == torch.iinfo(torch.int32).max, torch.full_like(best, -1), best)
+            root_label[non_idx.long()] = lab
+    return ops.labels(root_label)
+
+
+class _CudaStageOps:
+    """Stage kernels through the C-ABI (device pointers of torch CUDA tensors)."""
+
+    def rows_count(self, X, gl, gw, eps, r0, r1):
+        import torch
+        out = torch.empty((r1 - r0,), dtype=torch.int32, device=X.device)
+        check(lib().mcbb_dbscan_rows_count_dev(_ptr(X), X.shape[1], len(gl), gl.ctypes.data_as(abi.c_int32_p),
+                                               gw.ctypes.data_as(abi.c_double_p), float(eps), r0, r1, _ptr(out),
+                                               _stream()))
+        return out
+
+    def gather(self, X, idx):
+        import torch
+        out = torch.empty((X.shape[0], idx.numel()), dtype=torch.float64, device=X.device)
+        check(lib().mcbb_gather_columns_dev(_ptr(X), X.shape[1], _ptr(idx), idx.numel(), X.shape[0], _ptr(out),
+                                            _stream()))
+        return out
+
+    def rows_union(self, Xc, gl, gw, eps, c0, c1):
+        import torch
+        parent = torch.empty((Xc.shape[1],), dtype=torch.int32, device=Xc.device)
+        check(lib().mcbb_dbscan_rows_union_dev(_ptr(Xc), Xc.shape[1], len(gl), gl.ctypes.data_as(abi.c_int32_p),
+                                               gw.ctypes.data_as(abi.c_double_p), float(eps), c0, c1, _ptr(parent),
+                                               _stream()))
+        return parent
+
+    def merge_parents(self, parent, other):
+        check(lib().mcbb_dbscan_merge_parents_dev(_ptr(parent), _ptr(other), parent.numel(), _stream()))
+
+    def rows_border(self, Xn, b0, b1, Xc, core_seed, gl, gw, eps):
+        import torch
+        out = torch.empty((b1 - b0,), dtype=torch.int32, device=Xn.device)
+        check(lib().mcbb_dbscan_rows_border_dev(_ptr(Xn), Xn.shape[1], b0, b1, _ptr(Xc), Xc.shape[1], _ptr(core_seed),
+                                                len(gl), gl.ctypes.data_as(abi.c_int32_p),
+                                                gw.ctypes.data_as(abi.c_double_p), float(eps), _ptr(out), _stream()))
+        return out
+
+    def labels(self, root_label):
+        import torch
+        n = root_label.numel()
+        a = torch.empty((n,), dtype=torch.int64, device=root_label.device)
+        s = torch.empty((n,), dtype=torch.int64, device=root_label.device)
+        c = torch.empty((n,), dtype=torch.int64, device=root_label.device)
+        k = np.zeros(1, dtype=np.int64)
+        check(lib().mcbb_dbscan_labels_dev(_ptr(root_label), n, _ptr(a), _ptr(s), _ptr(c),
+                                           k.ctypes.data_as(abi.c_int64_p), _stream()))
+        return a, s[: k[0]], c[: k[0]]

@@ -1,0 +1,127 @@
+"""Seeded problem builders (shapes of the reference's test scripts / BASELINE configs) and the parity checker
+used by tests/, __graft_entry__.smoke() and bench.py.  Inputs come from numpy PCG64 streams so the oracle and the
+GPU path consume identical bytes."""
+import numpy as np
+
+RTOL = 1e-6          # north_star: features within 1e-6 relative (FP64)
+ATOL_SCALE = 1e-10   # absolute floor = ATOL_SCALE * max(1, max |mean| of the run)  (SURVEY §7 hard part 3)
+
+
+def c1_problem(m, n_ics=500, seed=1, N=6, tspan=(0.0, 40.0), ks=(1.0, 1.5, 2.0, 2.5, 3.0), tail=0.9,
+               eval_funcs=None, cyclic=False):
+    """C1: Kuramoto network N=6, A=ones, w~N(0.5,0.01), random ICs x K range (test/ode_prob_example.jl:36-41)."""
+    rng = np.random.default_rng(seed)
+    w = rng.normal(0.5, 0.01, N)
+    A = np.ones((N, N))
+    pars = m.kuramoto_network_parameters(0.5, w, N, A)
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), tspan, pars)
+    ev = m.EvalOdeRun(eval_funcs=eval_funcs or (m.mean, m.std, m.empirical_1D_KL_divergence_hist),
+                      cyclic_setback=cyclic)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), n_ics, pars, ("K", list(ks)), ev, tail)
+    weights = [1.0] + [0.5] * (len(ev.eval_funcs) - 1) + [1.0]
+    return prob, weights
+
+
+def c2_problem(m, n_mc=2000, seed=3, tspan=(0.0, 1000.0), tail=0.8):
+    """C2: logistic map, r~U(2.5,4), x0~U(0.1,0.99) (test/discrete_prob_example.jl, docs/src/basic_usage.md:26-78)."""
+    rng = np.random.default_rng(seed)
+    pars = m.logistic_parameters(2.5)
+    dp = m.DiscreteProblem(m.logistic, np.array([0.5]), tspan, pars)
+    r_gen = np.random.default_rng(seed + 1)
+    prob = m.DEMCBBProblem(dp, lambda: rng.uniform(0.1, 0.99), n_mc, pars, ("r", lambda: r_gen.uniform(2.5, 4.0)),
+                           m.eval_ode_run, tail)
+    return prob, [1.0, 0.75, 0.5, 1.0]
+
+
+def ring_incidence(N, chords):
+    edges = [(i, (i + 1) % N) for i in range(N)] + list(chords)
+    E = np.zeros((N, len(edges)))
+    for e, (a, b) in enumerate(edges):
+        E[a, e] = -1.0
+        E[b, e] = 1.0
+    return E
+
+
+def c3_problem(m, n_mc=400, seed=5, N=10, tspan=(0.0, 200.0), tail=0.9, lam_max=2.0):
+    """C3 shape: second-order Kuramoto power grid (paper/kuramoto/1-simulate.jl), features on the frequencies."""
+    rng = np.random.default_rng(seed)
+    E = ring_incidence(N, [(i, (i + N // 2) % N) for i in range(N // 2)])
+    drive = np.array([1.0, -1.0] * (N // 2))
+    pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, drive)
+    rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), tspan, pars)
+    ev = m.EvalOdeRun(state_filter=list(range(N + 1, 2 * N + 1)), eval_funcs=(m.mean, m.std))
+    lam = np.random.default_rng(seed + 1)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), n_mc, pars,
+                           ("coupling", lambda: lam.uniform(0.05, lam_max)), ev, tail)
+    return prob, [1.0, 0.0, 1.0]
+
+
+def erdos_renyi(N, p, seed):
+    rng = np.random.default_rng(seed)
+    U = np.triu(rng.random((N, N)) < p, 1)
+    return (U | U.T).astype(np.float64)
+
+
+def c5_problem(m, n_mc, N=100, seed=10, tspan=(0.0, 1000.0), tail=0.9, kmax=8.0):
+    """C5: Kuramoto network N=100, Erdos-Renyi p=0.2, w~N(0.5,0.1), K~U(0,8) (docs/src/hpc.md:44-59 shape),
+    measures [mean, std] with cyclic_setback."""
+    A = erdos_renyi(N, 0.2, seed)
+    w = np.random.default_rng(seed + 1).normal(0.5, 0.1, N)
+    pars = m.kuramoto_network_parameters(0.5, w, N, A)
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), tspan, pars)
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std), cyclic_setback=True)
+    rng = np.random.default_rng(seed + 2)
+    kr = np.random.default_rng(seed + 3)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi, N), n_mc, pars, ("K", lambda: kr.uniform(0, kmax)),
+                           ev, tail)
+    return prob, [1.0, 0.5, 1.0]
+
+
+def feature_tolerance(ref_feat):
+    """|a-b| <= RTOL*|b| + ATOL_SCALE*scale, scale = max(1, max |value| of the run's first measure)."""
+    scale = np.maximum(1.0, np.nanmax(np.abs(ref_feat[:, :, 0]), axis=1))
+    return RTOL * np.abs(ref_feat) + ATOL_SCALE * scale[:, None, None]
+
+
+def compare_features(feat, ref, orc, psys, opts, pfeat, ic, par, t_save, min_checked=0.6, allow_bad=0):
+    """Parity of GPU features against the oracle on identical inputs.
+
+    * mean / std (and any non-KL measure): within feature_tolerance on every NON-CHAOTIC run, where a run counts as
+      chaotic / ill-conditioned when the oracle itself moves by more than the tolerance under a 1e-13 relative
+      perturbation of the initial condition.
+    * KL-hist: Julia's `mu-k*bw:bw:mu+k*bw` has 31 or 30 elements depending on the last bits of (mu, sig)
+      ("KL range-length quirk"); the GPU value must match the oracle under one of the two lengths.
+    Returns a dict of counts; raises AssertionError on mismatch."""
+    abi = orc.abi
+    ref_feat = ref["feat"]
+    tol = feature_tolerance(ref_feat)
+    pert = orc.solve_features(psys, opts, pfeat, np.asarray(ic) * (1.0 + 1e-13), par, t_save)["feat"]
+    is_kl = np.array([pfeat.opts.meas[m] == abi.MEAS_KL_HIST for m in range(pfeat.n_meas)])
+    nk = ~is_kl
+    with np.errstate(invalid="ignore"):
+        stable = (np.abs(pert[:, :, nk] - ref_feat[:, :, nk]) <= 0.1 * tol[:, :, nk]).all(axis=(1, 2))
+    both_nan = np.isnan(feat) & np.isnan(ref_feat)
+    with np.errstate(invalid="ignore"):
+        ok = (np.abs(feat - ref_feat) <= tol) | both_nan
+    bad_runs = ~ok[:, :, nk].all(axis=(1, 2)) & stable
+    stats = dict(n=len(stable), checked=int(stable.sum()), bad=int(bad_runs.sum()))
+    assert stats["checked"] >= min_checked * stats["n"], "too few non-chaotic runs to check: %s" % stats
+    assert stats["bad"] <= allow_bad, "features differ from the oracle on non-chaotic runs: %s, worst %s" % (
+        stats, np.nanmax(np.abs(feat - ref_feat)[stable][:, :, nk] / tol[stable][:, :, nk]))
+    if is_kl.any():
+        nb = pfeat.opts.kl_bins if pfeat.opts.kl_bins > 0 else 31
+        nb += (nb % 2 == 0)
+        v_a = orc.solve_features(psys, opts, pfeat, ic, par, t_save, kl_force_len=nb)["feat"]
+        v_b = orc.solve_features(psys, opts, pfeat, ic, par, t_save, kl_force_len=nb - 1)["feat"]
+        kl_tol = lambda v: RTOL * np.abs(v) + 1e-9
+        with np.errstate(invalid="ignore"):
+            okk = (np.abs(feat - v_a) <= kl_tol(v_a)) | (np.abs(feat - v_b) <= kl_tol(v_b)) | both_nan
+        # the sig < 1e-4 => 0 switch (eval_mc_prob.jl:314-316) is a discontinuity: skip dims sitting on it
+        std_idx = [m for m in range(pfeat.n_meas) if pfeat.opts.meas[m] == abi.MEAS_STD]
+        on_switch = np.zeros(feat.shape[:2], dtype=bool)
+        for m in std_idx:
+            on_switch |= np.abs(ref_feat[:, :, m] - 1e-4) < 1e-9
+        bad_kl = (~okk[:, :, is_kl]).any(axis=2) & ~on_switch & stable[:, None]
+        stats["kl_bad"] = int(bad_kl.sum())
+        assert stats["kl_bad"] <= allow_bad, "KL-hist differs from both oracle variants: %s" % stats
+    return stats

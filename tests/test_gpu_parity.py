@@ -1,0 +1,285 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on identical
+seeded inputs.  Bit-exact for integer work (DBSCAN labels / seeds / counts), 1e-6 for FP64 features
+(north_star), 1e-12 for distances."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_ref(m, orc, prob, ic0, par0, alg=None, n_t=400, **kw):
+    psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+    a = alg.alg if alg is not None else (m.abi.ALG_FUNCTIONMAP if prob.p.discrete else m.abi.ALG_TSIT5)
+    o = m.abi.solver_opts(a, prob.p.tspan, **kw)
+    ts = m.tsave_array(prob.p, n_t, prob.rel_transient_time)
+    idx = np.argsort(par0[:, 0], kind="stable")
+    ic, par = ic0[idx], par0[idx]
+    return orc.solve_features(psys, o, pfeat, ic, par, ts), (psys, o, pfeat, ic, par, ts)
+
+
+def test_loaded_library_is_the_cuda_one(gpu):
+    sm, maj, mnr, mem = (C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64())
+    gpu.check(gpu.lib().mcbb_device_info(C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
+    assert maj.value == 10, "expected a Blackwell (sm_100) device, got cc %d.%d" % (maj.value, mnr.value)
+    assert sm.value >= 100
+
+
+def test_c1_kuramoto_solve_features(gpu, orc):
+    """C1: Kuramoto N=6, 500 ICs x 5 K, Tsit5, default eval_ode_run (mean, std, KL)."""
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=500)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    before = m.kernel_launch_count()
+    sol = m.solve(prob)
+    assert m.kernel_launch_count() > before, "no CUDA kernel was launched"
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0)
+    assert np.array_equal(prob.par[:, 0], np.sort(par0[:, 0]))  # sort!(sol, prob) permuted the problem
+    assert np.array_equal(sol.retcode, ref["retcode"])
+    assert np.array_equal(sol.nsteps, ref["nsteps"]), "step sequences differ from the oracle"
+    stats = cases.compare_features(sol.feat, ref, orc, *ctx)
+    assert stats["checked"] >= 0.95 * stats["n"]
+
+
+def test_c1_variants_cyclic_filter_global(gpu, orc):
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=100, seed=7, eval_funcs=(m.mean, m.std), cyclic=True)
+    prob.eval_ode_func = m.EvalOdeRun(state_filter=[2, 3, 4], eval_funcs=(m.mean, m.std),
+                                      global_eval_funcs=["sum"], cyclic_setback=True)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0)
+    assert sol.feat.shape == (500, 3, 2)
+    cases.compare_features(sol.feat, ref, orc, *ctx)
+    assert np.allclose(sol.glob, ref["glob"], rtol=1e-6)
+
+
+def test_c1_rk4_fixed_step(gpu, orc):
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=40, seed=11)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob, m.RK4(), dt=0.05)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, alg=m.RK4(), dt=0.05)
+    assert np.array_equal(sol.nsteps, ref["nsteps"])
+    cases.compare_features(sol.feat, ref, orc, *ctx)
+
+
+def test_c2_logistic_map(gpu, orc):
+    """C2: logistic map (DiscreteProblem / FunctionMap), 10^4 runs."""
+    m = gpu
+    prob, _ = cases.c2_problem(m, n_mc=10000)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0)
+    assert np.array_equal(sol.nsteps[:, 0], ref["nsteps"][:, 0])
+    # the map is evaluated with the reference's literal expression: even chaotic orbits agree
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.3)
+    # known answers: fixed point x* = 1 - 1/r for r < 3 => mean = x*, std = 0, KL = 0
+    r = prob.par[:, 0]
+    fp = r < 2.95
+    assert np.allclose(sol.feat[fp, 0, 0], 1 - 1 / r[fp], atol=1e-9)
+    assert np.all(sol.feat[fp, 0, 1] < 1e-6) and np.all(sol.feat[fp, 0, 2] == 0.0)
+
+
+def test_c3_second_order_kuramoto(gpu, orc):
+    m = gpu
+    prob, _ = cases.c3_problem(m, n_mc=600)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0)
+    assert np.array_equal(sol.retcode, ref["retcode"])
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.3)
+
+
+def test_other_systems_small(gpu, orc):
+    """kuramoto (all-to-all), non_local_kuramoto_ring, roessler_network, Stuart-Landau at small N."""
+    m = gpu
+    rng = np.random.default_rng(21)
+    N = 8
+    checks = []
+    # all-to-all Kuramoto
+    pars = m.kuramoto_parameters(1.0, rng.normal(0.5, 0.05, N), N)
+    checks.append((pars, m.kuramoto, N, "K", (0.5, 3.0), (0.0, 60.0), m.EvalOdeRun(eval_funcs=(m.mean, m.std)), False))
+    # non-local ring with exponential kernel
+    pars = m.non_local_kuramoto_ring_parameters(N, 0.3, 0.2, lambda x: np.exp(-abs(x)) / (2 * np.pi))
+    checks.append((pars, m.non_local_kuramoto_ring, N, "phase_delay", (0.0, 1.4), (0.0, 60.0),
+                   m.EvalOdeRun(eval_funcs=(m.mean, m.std), cyclic_setback=True), False))
+    # Roessler network on a ring Laplacian
+    Nr = 4
+    Lp = 2 * np.eye(Nr) - np.roll(np.eye(Nr), 1, 0) - np.roll(np.eye(Nr), -1, 0)
+    pars = m.roessler_parameters(0.2 * np.ones(Nr), 0.2 * np.ones(Nr), 5.7 * np.ones(Nr), 0.05, Lp, Nr)
+    checks.append((pars, m.roessler_network, 3 * Nr, "K", (0.0, 0.1), (0.0, 30.0),
+                   m.EvalOdeRun(eval_funcs=(m.mean, m.std)), False))
+    # Stuart-Landau, complex state
+    Ns = 8
+    A1 = np.roll(np.eye(Ns), 1, 0) + np.roll(np.eye(Ns), -1, 0)
+    A2 = A1 + np.roll(np.eye(Ns), 2, 0) + np.roll(np.eye(Ns), -2, 0)
+    pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.9, Ns, 1, 2, A1, A2)
+    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"))
+    checks.append((pars, m.stuart_landau_sathiyadevi, Ns, "eps", (1.8, 2.1), (0.0, 50.0), ev, True))
+    for pars, f, ndim, pname, prange, tspan, ev, cplx in checks:
+        prng = np.random.default_rng(5)
+        if cplx:
+            gen = lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1))
+            u0 = np.zeros(ndim, dtype=complex)
+        else:
+            gen = lambda: rng.uniform(-1.0, 1.0)
+            u0 = np.zeros(ndim)
+        rp = m.ODEProblem(f, u0, tspan, pars)
+        prob = m.DEMCBBProblem(rp, gen, 96, pars, (pname, lambda: prng.uniform(*prange)), ev, 0.8)
+        ic0, par0 = prob.ic.copy(), prob.par.copy()
+        sol = m.solve(prob)
+        if cplx:
+            ic0 = np.stack([ic0.real, ic0.imag], axis=2).reshape(ic0.shape[0], -1)
+        ref, ctx = _oracle_ref(m, orc, prob, ic0, par0)
+        assert np.array_equal(sol.retcode, ref["retcode"]), f.__name__
+        cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.3)
+
+
+def test_retcodes_maxiters_and_unstable(gpu, orc):
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=8, seed=2)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob, maxiters=5, flag_check_inf_nan=False)
+    ref, _ = _oracle_ref(m, orc, prob, ic0, par0, maxiters=5)
+    assert np.all(sol.retcode == m.abi.RET_MAXITERS) and np.array_equal(sol.retcode, ref["retcode"])
+    assert np.isnan(sol.feat).all()
+    # logistic with r > 4 escapes to -inf -> NaN -> Unstable
+    pars = m.logistic_parameters(4.5)
+    dp = m.DiscreteProblem(m.logistic, np.array([0.5]), (0.0, 2000.0), pars)
+    prob = m.DEMCBBProblem(dp, lambda: 0.3, 4, pars, ("r", [4.5, 4.6]), m.eval_ode_run, 0.8)
+    sol = m.solve(prob, flag_check_inf_nan=False)
+    assert np.all(sol.retcode == m.abi.RET_UNSTABLE)
+
+
+def test_error_behaviour(gpu):
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=4)
+    with pytest.raises(m.MCBBError, match="fixed-step"):
+        m.solve(prob, m.RK4())
+    with pytest.raises(m.MCBBError, match="At least two data points"):
+        m.dbscan(np.zeros((1, 1)), 1.0, 2)
+    with pytest.raises(m.MCBBError, match="eps must be a positive value"):
+        m.dbscan(np.zeros((3, 3)), 0.0, 2)
+    with pytest.raises(m.MCBBError, match="minpts must be positive"):
+        m.dbscan(np.zeros((3, 3)), 1.0, 0)
+
+
+def test_distance_matrix_matches_oracle(gpu, orc):
+    m = gpu
+    rng = np.random.default_rng(0)
+    for n, glen, gw in [(257, [6, 6, 6, 1], [1, 0.5, 0.5, 1]), (1000, [10, 10, 1], [1.0, 0.0, 1.0]),
+                        (63, [1], [2.0]), (130, [33, 30, 1, 1], [0.25, 1.0, 0.3, 1.0])]:
+        X = np.asfortranarray(rng.normal(size=(n, sum(glen))))
+        gl, w = np.asarray(glen, dtype=np.int32), np.asarray(gw, dtype=np.float64)
+        D = np.zeros((n, n), order="F")
+        m.check(m.lib().mcbb_distance_matrix(X.ctypes.data_as(m.abi.c_double_p), n, len(gl),
+                                             gl.ctypes.data_as(m.abi.c_int32_p), w.ctypes.data_as(m.abi.c_double_p),
+                                             D.ctypes.data_as(m.abi.c_double_p)))
+        Dref = orc.distance_matrix(X, gl, w)
+        assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+        assert np.allclose(D, Dref, rtol=1e-12, atol=1e-13)
+
+
+def _dbscan_cases():
+    rng = np.random.default_rng(42)
+    out = []
+    # blobs + noise, generic
+    pts = np.concatenate([rng.normal(c, 0.3, size=(60, 2)) for c in [(0, 0), (4, 0), (0, 4)]] +
+                         [rng.uniform(-3, 7, size=(40, 2))])
+    out.append(("blobs", pts, 0.5, 5))
+    # integer lattice: many exact ties d == eps (strict '<' matters) and border points adjacent to two clusters
+    g = np.array([(i, j) for i in range(12) for j in range(12)], dtype=float)
+    g = g[rng.permutation(len(g))][:110]
+    out.append(("lattice_ties", g, 1.0, 3))
+    out.append(("lattice_ties2", g, 2.0, 4))
+    out.append(("minpts1", pts[:50], 0.4, 1))
+    out.append(("all_noise", pts[:80], 1e-6, 3))
+    out.append(("single_cluster", pts[:80], 100.0, 3))
+    # chain where border points touch two clusters
+    chain = np.array([[0, 0], [0.1, 0], [0.2, 0], [1.0, 0], [1.8, 0], [1.9, 0], [2.0, 0]], dtype=float)
+    out.append(("two_clusters_shared_border", chain, 0.85, 3))
+    return out
+
+
+@pytest.mark.parametrize("name,pts,eps,minpts", _dbscan_cases(), ids=[c[0] for c in _dbscan_cases()])
+def test_dbscan_bit_exact_vs_oracle(gpu, orc, name, pts, eps, minpts):
+    """DBSCAN labels from the oracle's distance matrix must be bit-exact (seeds, assignments, counts), for the
+    dense path and for the fused feature path."""
+    m = gpu
+    X = np.asfortranarray(pts)
+    gl = np.array([X.shape[1]], dtype=np.int32)
+    gw = np.array([1.0])
+    Dref = orc.distance_matrix(X, gl, gw)
+    ref = orc.dbscan(Dref, eps, minpts)
+    res = m.dbscan(Dref, eps, minpts)
+    assert np.array_equal(res.assignments, ref["assignments"])
+    assert np.array_equal(res.seeds, ref["seeds"]) and np.array_equal(res.counts, ref["counts"])
+    fm = m.B200FeatureMatrix(X, gl, gw, [1.0], False)
+    res2 = m.dbscan(fm, eps, minpts)
+    assert np.array_equal(res2.assignments, ref["assignments"])
+    assert np.array_equal(res2.seeds, ref["seeds"]) and np.array_equal(res2.counts, ref["counts"])
+
+
+def test_dbscan_random_matrices_property(gpu, orc):
+    """Parallel restatement == sequential transcription on random symmetric D with quantised (tie-rich) values."""
+    m = gpu
+    rng = np.random.default_rng(9)
+    for trial in range(12):
+        n = int(rng.integers(2, 300))
+        U = np.round(rng.random((n, n)) * 20) / 20
+        D = np.triu(U, 1)
+        D = np.asfortranarray(D + D.T)
+        eps = float(rng.choice([0.05, 0.1, 0.15, 0.3]))
+        minpts = int(rng.integers(1, 8))
+        ref = orc.dbscan(D, eps, minpts)
+        res = m.dbscan(D, eps, minpts)
+        assert np.array_equal(res.assignments, ref["assignments"]), (trial, n, eps, minpts)
+        assert np.array_equal(res.seeds, ref["seeds"]) and np.array_equal(res.counts, ref["counts"])
+
+
+def test_end_to_end_c1_cluster_membership(gpu, orc):
+    """solve -> distance_matrix -> dbscan -> cluster_membership against the oracle pipeline (ARI >= 0.99)."""
+    from sklearn.metrics import adjusted_rand_score
+    m = gpu
+    prob, weights = cases.c1_problem(m, n_ics=300, ks=np.arange(0.25, 3.01, 0.25), tspan=(0.0, 200.0))
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob)
+    D = m.distance_matrix(sol, prob, weights)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0)
+    rsol = m.DEMCBBSol(ref["feat"], None, None, ref["retcode"], ref["nsteps"], 400, None)
+    Xr, gl, gw = m.feature_groups(rsol, prob, weights)
+    Dref = orc.distance_matrix(Xr, gl, gw)
+    eps = float(np.median(np.sort(Dref, axis=0)[5]))
+    res = m.dbscan(D, eps, 5)
+    rdb = orc.dbscan(Dref, eps, 5)
+    assert adjusted_rand_score(rdb["assignments"], res.assignments) >= 0.99
+    cm = m.cluster_membership(prob, res, 0.5, 0.25)
+    mesh, rcm = orc.cluster_membership(prob.par[:, 0], res.assignments, len(res.seeds), 0.5, 0.25)
+    assert np.allclose(cm.par, mesh) and np.allclose(cm.data, rcm, equal_nan=True)
+
+
+def test_fused_dbscan_large_roundtrip_properties(gpu):
+    """Full-size style check without an oracle pass: the fused path on 20000 points must equal the dense path on
+    the library's own materialised matrix (same distance function), and labels must be permutation-consistent."""
+    m = gpu
+    rng = np.random.default_rng(4)
+    n, F = 20000, 12
+    centers = rng.normal(0, 4, size=(6, F))
+    X = np.asfortranarray(centers[rng.integers(0, 6, n)] + rng.normal(0, 0.4, size=(n, F)))
+    gl = np.array([5, 6, 1], dtype=np.int32)
+    gw = np.array([1.0, 0.5, 1.0])
+    fm = m.B200FeatureMatrix(X, gl, gw, [1, 0.5, 1], False)
+    res = m.dbscan(fm, 2.2, 10)
+    D = np.zeros((n, n), order="F")
+    m.check(m.lib().mcbb_distance_matrix(X.ctypes.data_as(m.abi.c_double_p), n, 3, gl.ctypes.data_as(m.abi.c_int32_p),
+                                         gw.ctypes.data_as(m.abi.c_double_p), D.ctypes.data_as(m.abi.c_double_p)))
+    res_d = m.dbscan(D, 2.2, 10)
+    assert np.array_equal(res.assignments, res_d.assignments)
+    assert np.array_equal(res.seeds, res_d.seeds) and np.array_equal(res.counts, res_d.counts)
+    assert res.counts.sum() + m.cluster_n_noise(res) == n
+    assert np.all(np.diff(res.seeds) > 0)  # clusters numbered by ascending seed
+    assert np.array_equal(res.assignments[res.seeds - 1], np.arange(1, len(res.seeds) + 1))
