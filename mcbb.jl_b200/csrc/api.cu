@@ -62,7 +62,8 @@ void scratch_free_all() {
 // defined in solve.cu / cluster.cu
 int table_lengths(const mcbb_system_desc* s, int len[5]);
 int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* out, std::vector<int>* filter_host);
-int solve_features_launch(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io, cudaStream_t st);
+int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                          const SolveIO& io, cudaStream_t st);
 int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
                         const double* group_weight, double* D, cudaStream_t st);
 int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
@@ -238,7 +239,7 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
         io.ckpt = (double*)scratch_get(7, sizeof(double) * (size_t)(2 * S.n_dim + 4) * (size_t)n_mc);
         if (!io.ckpt) MCBB_FAIL("solve: device allocation of the KL checkpoint buffer failed");
     }
-    return solve_features_launch(S, o, F, io, st);
+    return solve_features_launch(sys, S, o, F, io, st);
 }
 
 int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,

@@ -246,11 +246,12 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
     return 0;
 }
 
-int launch_batched_kuramoto(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io,
-                            cudaStream_t st, bool* handled);
+int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                            const SolveIO& io, cudaStream_t st, bool* handled);
 
 // everything on the device already; tables in S are device pointers
-int solve_features_launch(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io, cudaStream_t st) {
+int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                          const SolveIO& io, cudaStream_t st) {
     if (o.alg == MCBB_ALG_FUNCTIONMAP && S.system != MCBB_SYS_LOGISTIC)
         MCBB_FAIL("FunctionMap stepping is only defined for the map systems (logistic)");
     if (o.alg != MCBB_ALG_FUNCTIONMAP && S.system == MCBB_SYS_LOGISTIC)
@@ -260,7 +261,7 @@ int solve_features_launch(const SysDev& S, const SolverDev& o, const FeatDev& F,
     if (!(o.t1 > o.t0)) MCBB_FAIL("tspan must be increasing");
     if (io.n_t < 2) MCBB_FAIL("need at least two save times (the first saved sample is dropped)");
     bool handled = false;
-    if (int rc = launch_batched_kuramoto(S, o, F, io, st, &handled)) return rc;
+    if (int rc = launch_batched_kuramoto(hs, S, o, F, io, st, &handled)) return rc;
     if (handled) return 0;
     switch (S.system) {
     case MCBB_SYS_LOGISTIC:

@@ -87,19 +87,27 @@ def compare_features(feat, ref, orc, psys, opts, pfeat, ic, par, t_save, min_che
     """Parity of GPU features against the oracle on identical inputs.
 
     * mean / std (and any non-KL measure): within feature_tolerance on every NON-CHAOTIC run, where a run counts as
-      chaotic / ill-conditioned when the oracle itself moves by more than the tolerance under a 1e-13 relative
-      perturbation of the initial condition.
+      chaotic / ill-conditioned when the oracle itself moves by more than half the tolerance under 1e-12 relative
+      perturbations of the initial condition.
     * KL-hist: Julia's `mu-k*bw:bw:mu+k*bw` has 31 or 30 elements depending on the last bits of (mu, sig)
       ("KL range-length quirk"); the GPU value must match the oracle under one of the two lengths.
     Returns a dict of counts; raises AssertionError on mismatch."""
     abi = orc.abi
     ref_feat = ref["feat"]
     tol = feature_tolerance(ref_feat)
-    pert = orc.solve_features(psys, opts, pfeat, np.asarray(ic) * (1.0 + 1e-13), par, t_save)["feat"]
     is_kl = np.array([pfeat.opts.meas[m] == abi.MEAS_KL_HIST for m in range(pfeat.n_meas)])
     nk = ~is_kl
-    with np.errstate(invalid="ignore"):
-        stable = (np.abs(pert[:, :, nk] - ref_feat[:, :, nk]) <= 0.1 * tol[:, :, nk]).all(axis=(1, 2))
+    # sensitivity probe: three seeded random relative perturbations of size 1e-12 (about 100x the rounding
+    # differences between two correct FP64 implementations); a run is "non-chaotic" when the oracle stays
+    # within half the tolerance under all of them
+    prng = np.random.default_rng(12345)
+    stable = np.ones(ref_feat.shape[0], dtype=bool)
+    ic_a = np.asarray(ic, dtype=np.float64)
+    for _ in range(3):
+        pert_ic = ic_a * (1.0 + 1e-12 * prng.standard_normal(ic_a.shape))
+        pert = orc.solve_features(psys, opts, pfeat, pert_ic, par, t_save)["feat"]
+        with np.errstate(invalid="ignore"):
+            stable &= (np.abs(pert[:, :, nk] - ref_feat[:, :, nk]) <= 0.5 * tol[:, :, nk]).all(axis=(1, 2))
     both_nan = np.isnan(feat) & np.isnan(ref_feat)
     with np.errstate(invalid="ignore"):
         ok = (np.abs(feat - ref_feat) <= tol) | both_nan
