@@ -410,9 +410,14 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
                     }
                     const double mean = ACCS(0, e);
                     const double delta = x - mean;
-                    const double mnew = fma(delta, rk, mean);
-                    ACCS(0, e) = mnew;
-                    ACCS(1, e) = fma(delta, x - mnew, ACCS(1, e));
+                    if (fabs(delta) <= 1.7976931348623157e308) {
+                        const double mnew = fma(delta, rk, mean);
+                        ACCS(0, e) = mnew;
+                        ACCS(1, e) = fma(delta, x - mnew, ACCS(1, e));
+                    } else {
+                        ACCS(0, e) = nonfinite_mean(mean, x);
+                        ACCS(1, e) = nan("");
+                    }
                 }
             }
 #pragma unroll
@@ -454,7 +459,8 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
                 const int pos = a.filter_pos[i];
                 if (pos < 0) continue;
                 const double mean = ok ? ACCS(0, e) : nan("");
-                const double sd = ok ? sqrt(fmax(ACCS(1, e), 0.) / (double)(n_t - 2)) : nan("");
+                const double m2 = ACCS(1, e);
+                const double sd = ok ? sqrt((m2 < 0. ? 0. : m2) / (double)(n_t - 2)) : nan("");
                 for (int m = 0; m < a.n_meas; m++)
                     a.io.feat[((long long)m * a.n_filter + pos) * n_mc + run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
             }

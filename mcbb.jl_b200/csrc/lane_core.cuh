@@ -73,6 +73,14 @@ MCBB_HD int julia_range_len(const double start, const double step, const double 
     return len;
 }
 
+// running "sum" state once a sample or the mean is Inf / NaN (finite+inf=inf, inf+inf=inf, inf-inf=NaN)
+MCBB_HD double nonfinite_mean(const double mean, const double x) {
+    const double big = 1.7976931348623157e308;
+    if (fabs(mean) <= big) return x;
+    if (fabs(x) <= big || x == mean) return mean;
+    return nan("");
+}
+
 // accumulator slots per channel
 enum { ACC_MEAN = 0, ACC_M2 = 1, ACC_SUBTR = 2, ACC_START = 3, ACC_BW = 4, ACC_NC = 5, ACC_SLOTS_KL = 6, ACC_SLOTS = 3 };
 enum { SLOT_U = 0, SLOT_K1 = 1, SLOT_TMP = 8, SLOT_SCR = 9 };
@@ -207,6 +215,7 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                 int nc = 0;
                 if (sig >= F.kl_tol) nc = julia_range_len(start, bw, stop);
                 if (nc > nb) nc = nb;
+                if (sig != sig) nc = -1;  // NaN std (non-finite samples): the reference's KL is NaN
                 A(ACC_START, ch) = start;
                 A(ACC_BW, ch) = bw;
                 A(ACC_NC, ch) = (double)nc;
@@ -239,9 +248,14 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                 if (pass == 0) {  // online mean / M2
                     const double mean = A(ACC_MEAN, ch);
                     const double delta = x - mean;
-                    const double mnew = fma(delta, rk, mean);
-                    A(ACC_MEAN, ch) = mnew;
-                    A(ACC_M2, ch) = fma(delta, x - mnew, A(ACC_M2, ch));
+                    if (fabs(delta) <= 1.7976931348623157e308) {
+                        const double mnew = fma(delta, rk, mean);
+                        A(ACC_MEAN, ch) = mnew;
+                        A(ACC_M2, ch) = fma(delta, x - mnew, A(ACC_M2, ch));
+                    } else {  // Inf / NaN samples: keep sum(x)/n and sum((x-m)^2) semantics of the reference
+                        A(ACC_MEAN, ch) = nonfinite_mean(mean, x);
+                        A(ACC_M2, ch) = NaN;
+                    }
                 } else {  // fit(Histogram, u, edges; closed=:left): searchsortedlast on the edge VECTOR
                     const int nc = (int)A(ACC_NC, ch);
                     if (nc > 0) {
@@ -279,7 +293,10 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                 write_nan_features();
             } else {
                 for (int ch = 0; ch < n_ch; ch++)  // std(u; mean, corrected=true)
-                    A(ACC_M2, ch) = sqrt(fmax(A(ACC_M2, ch), 0.) / (double)(ns_used - 1));
+                    {
+                    const double m2 = A(ACC_M2, ch);  // fmax would swallow a NaN
+                    A(ACC_M2, ch) = sqrt((m2 < 0. ? 0. : m2) / (double)(ns_used - 1));
+                }
                 for (int m = 0; m < F.n_meas; m++) {
                     if (F.meas[m] == MCBB_MEAS_KL_HIST) continue;
                     const int slot = F.meas[m] == MCBB_MEAS_MEAN ? ACC_MEAN : ACC_M2;
@@ -306,7 +323,7 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                 for (int ii = 0; ii < F.n_filter; ii++) {
                     const int ch = ii * F.n_comp + F.comp[m];
                     const int nc = (int)A(ACC_NC, ch);
-                    double kl = 0.;
+                    double kl = nc < 0 ? NaN : 0.;
                     if (nc > 0) {  // sig >= sig_tol
                         const double mu = A(ACC_MEAN, ch), sig = A(ACC_M2, ch);
                         const double start = A(ACC_START, ch), bw = A(ACC_BW, ch);
