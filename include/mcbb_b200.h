@@ -133,6 +133,10 @@ int mcbb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, in
 /* number of library kernels launched by this process so far (bench.py's gpu_launches) */
 int64_t mcbb_kernel_launch_count(void);
 
+/* FP64 FMA-pipe peak of the current device in TFLOP/s (DFMA micro-benchmark, best of 5) — the roofline
+ * denominator of the ensemble integrator; MEASURED_PEAKS.json carries no FP64 figure. */
+int mcbb_measure_fp64_fma_peak(double* tflops_out, double* sm_mhz_est_out);
+
 /* number of saved samples a solve will consume; fills t_save (may be NULL to query the length).
  * Restates tsave_array, src/setup_mc_prob.jl:1166-1180 (ODE and Discrete variants). */
 int mcbb_tsave_array(const mcbb_solver_opts* opts, int32_t n_t, double rel_transient_time,

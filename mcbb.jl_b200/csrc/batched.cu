@@ -22,17 +22,16 @@
 
 namespace mcbb {
 
-constexpr int TI = 5;
-constexpr int TB = 4;
-constexpr int NE = TI * TB;
 constexpr int NSLOT = 8;  // u, k1..k7
 
 struct BatchArgs {
     int N, IG, BG, B, nthreads;
-    int n_cols;           // padded length of the per-row-group column lists
-    const int* jlist;     // [IG][n_cols]
-    const double* aval;   // [IG][n_cols][TI]
-    const double* bias;   // [IG*TI]
+    int n_cols;            // length of the per-row-group column lists (padded, +2 sentinel entries)
+    const int* jlist;      // [IG][n_cols+2]            (weighted path, global)
+    const double* aval;    // [IG][n_cols+2][TI]        (weighted path, global)
+    const unsigned short* ent;  // [IG][n_cols+2] column | row-mask << 8   (unit-weight path, staged in smem)
+    double unit_weight;    // common value of the non-zero couplings (unit-weight path)
+    const double* bias;    // [IG*TI]
     const int* filter_pos;  // [IG*TI]: output position of oscillator i, or -1
     int system;
     double scalars[MCBB_N_SCALARS];
@@ -72,18 +71,32 @@ __device__ __forceinline__ void sincos_fast(const double x, double* s, double* c
     *c = ((q + 1) & 2) ? -b : b;
 }
 
+template <int TB>
+__device__ __forceinline__ void load_panel(const double* p, double* out) {
+    static_assert(TB % 2 == 0, "TB must be even (16-byte shared-memory loads)");
+#pragma unroll
+    for (int q = 0; q < TB; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(p + q);
+        out[q] = v.x;
+        out[q + 1] = v.y;
+    }
+}
+
 struct SlotCtl {  // per-trajectory control block (shared memory, one per batch slot)
     long long run, iter, nrej, natt;
     double t, dt, dts, qold, al1, al2, d0, d1, dt0, t_old, dts_old;
     int mode, isave, ret, clipped, accept, fresh, finished, s0, s1;
 };
 
-__global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
+template <int TI, int TB, bool UNIT>
+__global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
+    constexpr int NE = TI * TB;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nt = a.nthreads;
     const int ig = tid / a.BG, bg = tid - ig * a.BG;
     const int B = a.B, N = a.N;
     const int NP = a.IG * TI;
+    const int ncp = a.n_cols + 2;
     double* sm_k = (double*)smem;                                    // [NSLOT][NE][nt]
     double* sm_S = sm_k + (size_t)NSLOT * NE * nt;                   // [NP][B]
     double* sm_C = sm_S + (size_t)NP * B;                            // [NP][B]
@@ -91,6 +104,7 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
     double* sm_red1 = sm_red0 + (size_t)a.IG * B;                    // [IG][B]
     double* sm_ts = sm_red1 + (size_t)a.IG * B;                      // [n_t]
     SlotCtl* ctl = (SlotCtl*)(sm_ts + ((a.io.n_t + 1) & ~1));        // [B]
+    unsigned short* sm_ent = (unsigned short*)(ctl + B);             // [IG][ncp]  (unit-weight path)
     const SolverDev& o = a.o;
     const int n_t = a.io.n_t;
     const long long n_mc = a.io.n_mc;
@@ -100,6 +114,8 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
 #define ACCS(k, e) acc[((size_t)(k)*NE + (e)) * nt]
 
     for (int i = tid; i < n_t; i += nt) sm_ts[i] = a.io.t_save[i];
+    if (UNIT)
+        for (int i = tid; i < a.IG * ncp; i += nt) sm_ent[i] = a.ent[i];
     if (tid < B) {
         ctl[tid].mode = MODE_FETCH;
         ctl[tid].fresh = 0;
@@ -146,11 +162,15 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
                     if (a.system == MCBB_SYS_KURAMOTO_NETWORK) {
                         c.al1 = sc[0] / (double)N;  // K/N, systems.jl:128
                         c.al2 = 0.;
-                    } else {  // non_local_kuramoto_ring: omega_0 = sc[0] is carried by bias only if not swept
+                    } else {  // non_local_kuramoto_ring: omega_0 is carried by the bias table
                         double sa, ca;
                         sincos(sc[1], &sa, &ca);
                         c.al1 = ca / sc[2];
                         c.al2 = -sa / sc[2];
+                    }
+                    if (UNIT) {
+                        c.al1 *= a.unit_weight;
+                        c.al2 *= a.unit_weight;
                     }
                     c.run = run;
                     c.t = o.t0;
@@ -167,7 +187,7 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
         }
         const bool all_done = __syncthreads_and(tid >= B || ctl[tid].mode == MODE_DONE);
         if (all_done) break;
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < TB; q++) {
             const int b = bg * TB + q;
             if (ctl[b].fresh) {
@@ -184,67 +204,111 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
         }
 
         // ---- one round: 6 right-hand-side evaluations of the whole batch -----------------------------------
+#pragma unroll 1
         for (int s = 0; s < 6; s++) {
             // (a) stage input Y -> sin, cos into the shared S / C panels
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < TB; q++) {
                 const int b = bg * TB + q;
                 const int mode = ctl[b].mode;
                 const double h = (mode == MODE_RUN) ? ctl[b].dts : ctl[b].dt0;
+                double y[TI];
+#pragma unroll
+                for (int r = 0; r < TI; r++) y[r] = KS(0, r * TB + q);
+                if (mode == MODE_RUN) {
+                    double lin[TI];
+                    const double a0 = TS_A(s, 0);
+#pragma unroll
+                    for (int r = 0; r < TI; r++) lin[r] = a0 * KS(1, r * TB + q);
+                    for (int j = 1; j <= s; j++) {
+                        const double aj = TS_A(s, j);
+#pragma unroll
+                        for (int r = 0; r < TI; r++) lin[r] = fma(aj, KS(1 + j, r * TB + q), lin[r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < TI; r++) y[r] = fma(h, lin[r], y[r]);
+                } else if (mode == MODE_INIT && s == 1) {
+#pragma unroll
+                    for (int r = 0; r < TI; r++) y[r] = fma(h, KS(1, r * TB + q), y[r]);
+                }
 #pragma unroll
                 for (int r = 0; r < TI; r++) {
-                    const int e = r * TB + q;
-                    double y = KS(0, e);
-                    if (mode == MODE_RUN) {
-                        double lin = TS_A(s, 0) * KS(1, e);
-                        for (int j = 1; j <= s; j++) lin = fma(TS_A(s, j), KS(1 + j, e), lin);
-                        y = fma(h, lin, y);
-                    } else if (mode == MODE_INIT && s == 1) {
-                        y = fma(h, KS(1, e), y);
-                    }
                     double sv, cv;
-                    sincos_fast(y, &sv, &cv);
+                    sincos_fast(y[r], &sv, &cv);
                     sm_S[(size_t)(ig * TI + r) * B + b] = sv;
                     sm_C[(size_t)(ig * TI + r) * B + b] = cv;
                 }
             }
             __syncthreads();
-            // (b) [P | Q] = M . [S | C] for this thread's 5 x 4 block
+            // (b) [P | Q] = M . [S | C] for this thread's TI x TB block
             double P[TI][TB], Q[TI][TB];
 #pragma unroll
             for (int r = 0; r < TI; r++)
 #pragma unroll
                 for (int q = 0; q < TB; q++) P[r][q] = Q[r][q] = 0.;
             {
-                const int* jl = a.jlist + (size_t)ig * a.n_cols;
-                const double* av = a.aval + (size_t)ig * a.n_cols * TI;
                 const double* Sb = sm_S + bg * TB;
                 const double* Cb = sm_C + bg * TB;
-                int jn = __ldg(jl);
-                double an[TI];
+                if (UNIT) {
+                    // adjacency as (column, row-mask) entries in shared memory; S / C rows one column ahead
+                    const unsigned short* en = sm_ent + ig * ncp;
+                    unsigned e1 = en[1];
+                    int j = en[0] & 0xff;
+                    unsigned mask = en[0] >> 8;
+                    double sq[TB], cq[TB];
+                    load_panel<TB>(Sb + (size_t)j * B, sq);
+                    load_panel<TB>(Cb + (size_t)j * B, cq);
+#pragma unroll 2
+                    for (int c = 0; c < a.n_cols; c++) {
+                        const unsigned e2 = en[c + 2];
+                        const int jn = e1 & 0xff;
+                        double sn[TB], cn[TB];
+                        load_panel<TB>(Sb + (size_t)jn * B, sn);
+                        load_panel<TB>(Cb + (size_t)jn * B, cn);
 #pragma unroll
-                for (int r = 0; r < TI; r++) an[r] = __ldg(av + r);
-                for (int c = 0; c < a.n_cols; c++) {
-                    const int j = jn;
-                    double ar[TI];
+                        for (int r = 0; r < TI; r++) {
+                            const double mr = ((mask >> r) & 1u) ? 1.0 : 0.0;
 #pragma unroll
-                    for (int r = 0; r < TI; r++) ar[r] = an[r];
-                    if (c + 1 < a.n_cols) {  // prefetch the next column's coefficients (L2 / L1 resident)
-                        jn = __ldg(jl + c + 1);
-#pragma unroll
-                        for (int r = 0; r < TI; r++) an[r] = __ldg(av + (size_t)(c + 1) * TI + r);
-                    }
-                    const double4 s4 = *reinterpret_cast<const double4*>(Sb + (size_t)j * B);
-                    const double4 c4 = *reinterpret_cast<const double4*>(Cb + (size_t)j * B);
-                    const double sq[TB] = {s4.x, s4.y, s4.z, s4.w};
-                    const double cq[TB] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                    for (int r = 0; r < TI; r++)
+                            for (int q = 0; q < TB; q++) {
+                                P[r][q] = fma(mr, sq[q], P[r][q]);
+                                Q[r][q] = fma(mr, cq[q], Q[r][q]);
+                            }
+                        }
+                        mask = e1 >> 8;
+                        e1 = e2;
 #pragma unroll
                         for (int q = 0; q < TB; q++) {
-                            P[r][q] = fma(ar[r], sq[q], P[r][q]);
-                            Q[r][q] = fma(ar[r], cq[q], Q[r][q]);
+                            sq[q] = sn[q];
+                            cq[q] = cn[q];
                         }
+                    }
+                } else {
+                    const int* jl = a.jlist + (size_t)ig * ncp;
+                    const double* av = a.aval + (size_t)ig * ncp * TI;
+                    int jn = __ldg(jl);
+                    double an[TI];
+#pragma unroll
+                    for (int r = 0; r < TI; r++) an[r] = __ldg(av + r);
+#pragma unroll 2
+                    for (int c = 0; c < a.n_cols; c++) {
+                        const int j = jn;
+                        double ar[TI];
+#pragma unroll
+                        for (int r = 0; r < TI; r++) ar[r] = an[r];
+                        jn = __ldg(jl + c + 1);  // sentinel entries make c+1 always valid
+#pragma unroll
+                        for (int r = 0; r < TI; r++) an[r] = __ldg(av + (size_t)(c + 1) * TI + r);
+                        double sq[TB], cq[TB];
+                        load_panel<TB>(Sb + (size_t)j * B, sq);
+                        load_panel<TB>(Cb + (size_t)j * B, cq);
+#pragma unroll
+                        for (int r = 0; r < TI; r++)
+#pragma unroll
+                            for (int q = 0; q < TB; q++) {
+                                P[r][q] = fma(ar[r], sq[q], P[r][q]);
+                                Q[r][q] = fma(ar[r], cq[q], Q[r][q]);
+                            }
+                    }
                 }
             }
             // (c) k = a1 (c P - s Q) + a2 (s P + c Q) + bias  -> thread-private stage slot
@@ -309,7 +373,7 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
         }
 
         // ---- error estimate partials (running slots) -----------------------------------------------------------
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < TB; q++) {
             const int b = bg * TB + q;
             if (ctl[b].mode != MODE_RUN) continue;
@@ -377,11 +441,9 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
         __syncthreads();
 
         // ---- accepted steps: fused featurizer on the saved samples, then u <- u_new, k1 <- k7 ----------------
-        bool bad_any[TB];
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < TB; q++) {
             const int b = bg * TB + q;
-            bad_any[q] = false;
             if (!ctl[b].accept) continue;
             const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
             for (int k = ctl[b].s0; k < ctl[b].s1; k++) {
@@ -420,6 +482,7 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
                     }
                 }
             }
+            bool bad = false;
 #pragma unroll
             for (int r = 0; r < TI; r++) {
                 const int e = r * TB + q;
@@ -427,11 +490,11 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
 #pragma unroll
                 for (int j = 1; j < 6; j++) lu = fma(TS_A(5, j), KS(1 + j, e), lu);
                 const double un = fma(dts, lu, KS(0, e));
-                bad_any[q] |= (un != un);
+                bad |= (un != un);
                 KS(0, e) = un;
                 KS(1, e) = KS(7, e);  // FSAL
             }
-            if (bad_any[q]) ctl[b].ret = MCBB_RET_UNSTABLE;  // benign race: every writer stores the same value
+            if (bad) ctl[b].ret = MCBB_RET_UNSTABLE;  // benign race: every writer stores the same value
         }
         __syncthreads();
         if (tid < B) {
@@ -446,7 +509,7 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
         }
         __syncthreads();
         // ---- finished trajectories: write mean / std of the owned oscillators -----------------------------------
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < TB; q++) {
             const int b = bg * TB + q;
             if (!ctl[b].finished) continue;
@@ -483,10 +546,22 @@ __global__ void __launch_bounds__(160, 1) k_solve_batched(const BatchArgs a) {
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
+constexpr int TI_ = 5;
+
+template <int TB, bool UNIT>
+static int launch_variant(BatchArgs& a, size_t smem, int grid, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched<TI_, TB, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    k_solve_batched<TI_, TB, UNIT><<<grid, a.nthreads, smem, st>>>(a);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
 int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
                             const SolveIO& io, cudaStream_t st, bool* handled) {
     *handled = false;
     const int N = S.n_osc;
+    constexpr int TI = TI_;
     if (S.system != MCBB_SYS_KURAMOTO_NETWORK && S.system != MCBB_SYS_NONLOCAL_KURAMOTO_RING) return 0;
     if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1) return 0;
     if (N < 24 || N > 160 || hs == nullptr) return 0;
@@ -509,6 +584,18 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
         for (int k = 0; k < N; k++)
             for (int j = 0; j < N; j++) M[(size_t)k * N + j] = hs->mat_a[(k - j) + N - 1];
     }
+    // unit-weight adjacency: every non-zero coupling has the same value (the usual MCBB network)
+    bool unit = true;
+    double uw = 0.;
+    for (size_t q = 0; q < M.size() && unit; q++)
+        if (M[q] != 0.) {
+            if (uw == 0.) uw = M[q];
+            unit = (M[q] == uw);
+        }
+    if (uw == 0.) {
+        unit = true;
+        uw = 1.;
+    }
     // per 5-row group: the columns where any row is non-zero (ascending j = the reference's summation order)
     std::vector<std::vector<int>> cols(a.IG);
     int n_cols = 1;
@@ -520,14 +607,23 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
         }
         n_cols = std::max(n_cols, (int)cols[g].size());
     }
+    n_cols = (n_cols + 1) & ~1;  // the column loop is unrolled by two
     a.n_cols = n_cols;
-    std::vector<int> jl((size_t)a.IG * n_cols, 0);
-    std::vector<double> av((size_t)a.IG * n_cols * TI, 0.);
+    const int ncp = n_cols + 2;  // two sentinel entries so the software pipeline never reads out of bounds
+    std::vector<int> jl((size_t)a.IG * ncp, 0);
+    std::vector<double> av((size_t)a.IG * ncp * TI, 0.);
+    std::vector<unsigned short> ent((size_t)a.IG * ncp, 0);
     for (int g = 0; g < a.IG; g++)
         for (size_t c = 0; c < cols[g].size(); c++) {
-            jl[(size_t)g * n_cols + c] = cols[g][c];
-            for (int r = 0; r < TI; r++)
-                av[((size_t)g * n_cols + c) * TI + r] = M[(size_t)(g * TI + r) * N + cols[g][c]];
+            const int j = cols[g][c];
+            jl[(size_t)g * ncp + c] = j;
+            unsigned mask = 0;
+            for (int r = 0; r < TI; r++) {
+                const double v = M[(size_t)(g * TI + r) * N + j];
+                av[((size_t)g * ncp + c) * TI + r] = v;
+                if (v != 0.) mask |= 1u << r;
+            }
+            ent[(size_t)g * ncp + c] = (unsigned short)(j | (mask << 8));
         }
     std::vector<double> bias(NP, 0.);
     for (int i = 0; i < N; i++) bias[i] = (S.system == MCBB_SYS_KURAMOTO_NETWORK) ? hs->vec_a[i] : hs->scalars[0];
@@ -544,14 +640,18 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     double* d_av = (double*)scratch_get(51, sizeof(double) * av.size());
     double* d_bias = (double*)scratch_get(52, sizeof(double) * bias.size());
     int* d_fpos = (int*)scratch_get(53, sizeof(int) * fpos.size());
-    if (!d_jl || !d_av || !d_bias || !d_fpos) MCBB_FAIL("solve: device allocation failed");
+    unsigned short* d_ent = (unsigned short*)scratch_get(55, sizeof(unsigned short) * ent.size());
+    if (!d_jl || !d_av || !d_bias || !d_fpos || !d_ent) MCBB_FAIL("solve: device allocation failed");
     MCBB_CUDA_OK(cudaMemcpyAsync(d_jl, jl.data(), sizeof(int) * jl.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(d_av, av.data(), sizeof(double) * av.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(d_bias, bias.data(), sizeof(double) * bias.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(d_fpos, fpos.data(), sizeof(int) * fpos.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_ent, ent.data(), sizeof(unsigned short) * ent.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));
     a.jlist = d_jl;
     a.aval = d_av;
+    a.ent = d_ent;
+    a.unit_weight = uw;
     a.bias = d_bias;
     a.filter_pos = d_fpos;
     a.system = S.system;
@@ -565,15 +665,19 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     a.cyclic = F.cyclic;
     a.io = io;
 
-    // batch size: as many 4-trajectory groups as shared memory holds (<= 160 threads)
+    // register block width: 2 trajectories per thread doubles the resident warps (latency hiding) at the same
+    // shared-memory footprint; MCBB_BATCH_TB=4 selects the wider block for experiments
+    int TB = 2;
+    if (const char* e = getenv("MCBB_BATCH_TB")) TB = (atoi(e) == 4) ? 4 : 2;
+    // batch size: as many TB-trajectory groups as shared memory holds (<= 256 threads)
     const size_t cap = 227 * 1024;
     int BG = 0;
     size_t smem = 0;
-    for (int cand = 160 / a.IG; cand >= 1; cand--) {
+    for (int cand = 256 / a.IG; cand >= 1; cand--) {
         const int nt = a.IG * cand, B = cand * TB;
-        const size_t need = sizeof(double) * ((size_t)NSLOT * NE * nt + 2 * (size_t)NP * B + 2 * (size_t)a.IG * B +
+        const size_t need = sizeof(double) * ((size_t)NSLOT * TI * TB * nt + 2 * (size_t)NP * B + 2 * (size_t)a.IG * B +
                                               (size_t)((io.n_t + 1) & ~1)) +
-                            sizeof(SlotCtl) * (size_t)B + 16;
+                            sizeof(SlotCtl) * (size_t)B + sizeof(unsigned short) * (size_t)a.IG * ncp + 32;
         if (need <= cap) {
             BG = cand;
             smem = need;
@@ -589,12 +693,15 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long want = (io.n_mc + a.B - 1) / a.B;
     const int grid = (int)std::min<long long>(want, sms);
-    a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * NE * a.nthreads);
+    a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * TI * TB * a.nthreads);
     if (!a.acc) MCBB_FAIL("solve: device allocation failed");
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-    k_solve_batched<<<grid, a.nthreads, smem, st>>>(a);
-    MCBB_LAUNCHED();
+    int rc;
+    if (TB == 2)
+        rc = unit ? launch_variant<2, true>(a, smem, grid, st) : launch_variant<2, false>(a, smem, grid, st);
+    else
+        rc = unit ? launch_variant<4, true>(a, smem, grid, st) : launch_variant<4, false>(a, smem, grid, st);
+    if (rc) return rc;
     *handled = true;
     return 0;
 }
