@@ -1,0 +1,674 @@
+// batched_imma.cu — block-cooperative ensemble Tsit5 for kuramoto_network (src/systems.jl:119-130) with a
+// UNIT-WEIGHT adjacency (A_ij in {0, a}: the adjacency matrices MCBB is used with), coupling sums on the INT8
+// tensor cores, statistics of eval_ode_run (mean / std, eval_mc_prob.jl:191-198) fused into the tail.
+//
+// Per right-hand-side evaluation of a batch of B trajectories the coupling needs
+//        P = A sin(Y),  Q = A cos(Y)          A: N x N in {0,1},  sin/cos(Y): N x B in [-1,1]
+// The FP64 pipe does this at <= 37 TFLOP/s (measured, and DMMA is no faster on B200); the same sums are EXACT
+// integers once sin/cos are written in fixed point:
+//        u = round(x * 2^50) + 2^51            52-bit unsigned, |error| <= 2^-51 per term
+//        u = sum_k d_k 2^(8k),  d_k in [0,255] seven byte slices
+//        A u = sum_k 2^(8k) (A d_k)            seven s8 x u8 -> s32 GEMMs, exact (|A d_k| <= 128 * 255)
+// recombined in int64 and converted to double ONCE, so the sum carries a single rounding (better than the
+// N-term FP64 summation it replaces).  mma.sync.m16n8k32 INT8 measured 1.14 POP/s on this B200
+// (profiles/microbench/imma_peak.cu).
+//
+// Work split: one warp per 16-row tile of A (its A fragments live in registers for the whole kernel); the
+// accumulator fragment layout decides element ownership: lane (g, t) of warp w owns oscillators 16w+g and
+// 16w+g+8 of trajectories 4c+t, c = 0..CT-1.  All Runge-Kutta stage vectors of those elements sit in
+// thread-private shared memory; sin/cos stay in registers between the digit store and the post-combine.
+#include <algorithm>
+#include <vector>
+
+#include "lane_core.cuh"
+
+namespace mcbb {
+
+constexpr int IM_NSLOT = 8;   // u, k1..k7
+constexpr int IM_NSLICE = 7;  // 52-bit fixed point in bytes
+
+struct ImmaArgs {
+    int N, MT, KS, B, nthreads;
+    int kstr;                 // byte stride between digit columns (KS*32 + 16: conflict-free fragment loads)
+    const unsigned* afrag;    // [MT][4][4][32] A fragments: m-tile, k-step, register, lane
+    const int* deg;           // [MT*16] number of non-zero couplings per row
+    double unit_weight;
+    const double* bias;       // [MT*16]
+    const int* filter_pos;    // [MT*16]
+    double scalars[MCBB_N_SCALARS];
+    int n_par;
+    int par_slot[MCBB_MAX_PAR];
+    SolverDev o;
+    int n_meas, meas[MCBB_MAX_MEAS], n_filter, cyclic;
+    SolveIO io;
+    double* acc;  // [grid][3][N][B]  mean, M2, cyclic offset (L2-resident scratch)
+};
+
+__device__ __forceinline__ void sincos_fast2(const double x, double* s, double* c) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double qd = fma(x, 0.6366197723675814, magic);
+    const int q = __double2loint(qd);
+    const double qf = qd - magic;
+    double r = fma(-qf, 1.5707963267948966, x);
+    r = fma(-qf, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double a = (q & 1) ? cr : sr;
+    const double b = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -a : a;
+    *c = ((q + 1) & 2) ? -b : b;
+}
+
+struct ImSlotCtl {
+    long long run, iter, nrej, natt;
+    double t, dt, dts, qold, al1, d0, d1, dt0, t_old, dts_old;
+    int mode, isave, ret, clipped, accept, fresh, finished, s0, s1;
+};
+
+// x in [-1, 1] -> seven byte slices of round(x * 2^50) + 2^51, stored at p[slice * slice_stride]
+__device__ __forceinline__ void store_digits(unsigned char* p, const int slice_stride, const double x) {
+    const double t = fma(x, 1125899906842624.0 /* 2^50 */, 6755399441055744.0 /* 1.5 * 2^52 */);
+    const unsigned lo = (unsigned)__double2loint(t);
+    const unsigned hi = (unsigned)__double2hiint(t) & 0xFFFFFu;
+    p[0] = (unsigned char)lo;
+    p[slice_stride] = (unsigned char)(lo >> 8);
+    p[2 * slice_stride] = (unsigned char)(lo >> 16);
+    p[3 * slice_stride] = (unsigned char)(lo >> 24);
+    p[4 * slice_stride] = (unsigned char)hi;
+    p[5 * slice_stride] = (unsigned char)(hi >> 8);
+    p[6 * slice_stride] = (unsigned char)(hi >> 16);
+}
+
+__device__ __forceinline__ void mma_s8u8(int (&c)[4], const unsigned (&a)[4], const unsigned b0, const unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Shared-memory panels are indexed by (oscillator row, trajectory b): idx = row * B + b.  A warp's 64-bit
+// accesses split into half-warps of rows g = 0..3 / 4..7; with B = 20 the row stride is 40 words, so the four
+// rows of a half-warp land on banks 0, 8, 16, 24 (+2t): conflict-free.
+__global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int N = a.N, B = a.B, CT = a.B >> 2;
+    const int kstr = a.kstr;
+    const int slice_stride = 2 * B * kstr;
+    const int pstride = N * B;                                      // one panel
+    double* sm_k = (double*)smem;                                   // [8][N][B]  u, k1..k7
+    double* sm_sc = sm_k + (size_t)IM_NSLOT * pstride;              // [2][N][B]  sin, cos of the stage input
+    double* sm_red0 = sm_sc + (size_t)2 * pstride;                  // [MT][B]
+    double* sm_red1 = sm_red0 + (size_t)a.MT * B;                   // [MT][B]
+    double* sm_ts = sm_red1 + (size_t)a.MT * B;                     // [n_t]
+    ImSlotCtl* ctl = (ImSlotCtl*)(sm_ts + ((a.io.n_t + 1) & ~1));   // [B]
+    unsigned char* sm_dig = (unsigned char*)(ctl + B);              // [NSLICE][2B][kstr]
+    const SolverDev& o = a.o;
+    const int n_t = a.io.n_t;
+    const long long n_mc = a.io.n_mc;
+    double* acc = a.acc + (size_t)blockIdx.x * 3 * pstride;         // [3][N][B]
+    const int row0 = warp * 16 + g, row1 = row0 + 8;
+    const bool v0 = row0 < N, v1 = row1 < N;
+
+#define KP(slot, idx) sm_k[(size_t)(slot)*pstride + (idx)]
+#define ACCS(k, idx) acc[(size_t)(k)*pstride + (idx)]
+
+    for (int i = tid; i < n_t; i += blockDim.x) sm_ts[i] = a.io.t_save[i];
+    for (int i = tid; i < IM_NSLICE * slice_stride / 4; i += blockDim.x) ((unsigned*)sm_dig)[i] = 0u;
+    if (tid < B) {
+        ctl[tid].mode = MODE_FETCH;
+        ctl[tid].fresh = 0;
+        ctl[tid].finished = 0;
+        ctl[tid].accept = 0;
+    }
+    unsigned afr[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) afr[ks][r] = a.afrag[(((size_t)warp * 4 + ks) * 4 + r) * 32 + lane];
+    const double bias0 = a.bias[row0], bias1 = a.bias[row1];
+    const long long deg0 = (long long)a.deg[row0] << 51, deg1 = (long long)a.deg[row1] << 51;
+    __syncthreads();
+
+    auto begin_attempt = [&](ImSlotCtl& c) -> bool {
+        if (++c.iter > o.maxiters) {
+            c.ret = MCBB_RET_MAXITERS;
+            return false;
+        }
+        c.dts = c.dt;
+        c.clipped = 0;
+        if (c.dts >= o.t1 - c.t) {
+            c.dts = o.t1 - c.t;
+            c.clipped = 1;
+        }
+        if (!c.clipped && c.dts <= o.dtmin) {
+            c.ret = MCBB_RET_DTLESSTHANMIN;
+            return false;
+        }
+        return true;
+    };
+
+    for (;;) {
+        // ---- refill finished slots from the global queue ------------------------------------------------
+        if (tid < B) {
+            ImSlotCtl& c = ctl[tid];
+            c.fresh = 0;
+            if (c.mode == MODE_FETCH) {
+                const long long run = (long long)atomicAdd(a.io.work_counter, 1ULL);
+                if (run >= n_mc) {
+                    c.mode = MODE_DONE;
+                } else {
+                    double sc[MCBB_N_SCALARS];
+                    for (int q = 0; q < MCBB_N_SCALARS; q++) sc[q] = a.scalars[q];
+                    for (int p = 0; p < a.n_par; p++) sc[a.par_slot[p]] = a.io.par[(long long)p * n_mc + run];
+                    c.al1 = (sc[0] / (double)N) * a.unit_weight;  // K/N (systems.jl:128) times the coupling value
+                    c.run = run;
+                    c.t = o.t0;
+                    c.iter = 0;
+                    c.nrej = 0;
+                    c.natt = 0;
+                    c.qold = o.qoldinit;
+                    c.isave = 0;
+                    c.ret = 0;
+                    c.mode = MODE_INIT;
+                    c.fresh = 1;
+                }
+            }
+        }
+        const bool all_done = __syncthreads_and(tid >= B || ctl[tid].mode == MODE_DONE);
+        if (all_done) break;
+#pragma unroll 1
+        for (int ct = 0; ct < CT; ct++) {
+            const int b = ct * 4 + t4;
+            if (ctl[b].fresh) {
+                const long long run = ctl[b].run;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = h ? row1 : row0;
+                    if (row < N) {
+                        const int idx = row * B + b;
+                        KP(0, idx) = a.io.ic[(long long)row * n_mc + run];
+                        ACCS(0, idx) = 0.;
+                        ACCS(1, idx) = 0.;
+                        ACCS(2, idx) = 0.;
+                    }
+                }
+            }
+        }
+
+        // ---- one round: 6 right-hand-side evaluations of the whole batch -----------------------------------
+#pragma unroll 1
+        for (int s = 0; s < 6; s++) {
+            // (a) stage input Y -> sin, cos -> fixed-point byte slices (shared digit panels)
+#pragma unroll 1
+            for (int ct = 0; ct < CT; ct++) {
+                const int b = ct * 4 + t4;
+                const int mode = ctl[b].mode;
+                const double hstep = (mode == MODE_RUN) ? ctl[b].dts : ctl[b].dt0;
+                double y[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = h ? row1 : row0;
+                    const int idx = (row < N ? row : 0) * B + b;
+                    y[h] = KP(0, idx);
+                    if (mode == MODE_RUN) {
+                        double lin = TS_A(s, 0) * KP(1, idx);
+                        for (int j = 1; j <= s; j++) lin = fma(TS_A(s, j), KP(1 + j, idx), lin);
+                        y[h] = fma(hstep, lin, y[h]);
+                    } else if (mode == MODE_INIT && s == 1) {
+                        y[h] = fma(hstep, KP(1, idx), y[h]);
+                    }
+                }
+                double sv[2], cv[2];
+                sincos_fast2(y[0], &sv[0], &cv[0]);
+                sincos_fast2(y[1], &sv[1], &cv[1]);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = h ? row1 : row0;
+                    if (row < N) {
+                        const int idx = row * B + b;
+                        sm_sc[idx] = sv[h];
+                        sm_sc[pstride + idx] = cv[h];
+                        unsigned char* p = sm_dig + (size_t)(2 * b) * kstr + row;
+                        store_digits(p, slice_stride, sv[h]);
+                        store_digits(p + kstr, slice_stride, cv[h]);
+                    }
+                }
+            }
+            __syncthreads();
+            // (b) seven s8 x u8 GEMM slices per column tile, (c) int64 recombination and k = a1 (c P - s Q) + w
+#pragma unroll 1
+            for (int ct = 0; ct < CT; ct++) {
+                int cacc[IM_NSLICE][4];
+#pragma unroll
+                for (int sl = 0; sl < IM_NSLICE; sl++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) cacc[sl][r] = 0;
+                const unsigned char* colp = sm_dig + (size_t)(ct * 8 + g) * kstr + 4 * t4;
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    if (ks < a.KS) {
+#pragma unroll
+                        for (int sl = 0; sl < IM_NSLICE; sl++) {
+                            const unsigned char* q = colp + (size_t)sl * slice_stride + ks * 32;
+                            const unsigned b0 = *reinterpret_cast<const unsigned*>(q);
+                            const unsigned b1 = *reinterpret_cast<const unsigned*>(q + 16);
+                            mma_s8u8(cacc[sl], afr[ks], b0, b1);
+                        }
+                    }
+                }
+                // lane holds (row0, P) (row0, Q) (row1, P) (row1, Q) of trajectory b = 4 ct + t4
+                long long v[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    long long sum = 0;
+#pragma unroll
+                    for (int sl = IM_NSLICE - 1; sl >= 0; sl--) sum = (sum << 8) + (long long)cacc[sl][r];
+                    v[r] = sum;
+                }
+                const int b = ct * 4 + t4;
+                const int mode = ctl[b].mode;
+                const double al1 = ctl[b].al1;
+                const double scale = 8.881784197001252e-16;  // 2^-50
+                double p0 = 0., p1 = 0.;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = h ? row1 : row0;
+                    if (row < N) {
+                        const int idx = row * B + b;
+                        const long long dg = h ? deg1 : deg0;
+                        const double P = (double)(v[2 * h] - dg) * scale;
+                        const double Q = (double)(v[2 * h + 1] - dg) * scale;
+                        const double kv = fma(al1, sm_sc[pstride + idx] * P - sm_sc[idx] * Q, h ? bias1 : bias0);
+                        if (mode == MODE_RUN) {
+                            KP(2 + s, idx) = kv;
+                        } else if (mode == MODE_INIT && s < 2) {  // OrdinaryDiffEq initdt.jl norms
+                            const double u0 = KP(0, idx);
+                            const double sk = o.abstol + fabs(u0) * o.reltol;
+                            if (s == 0) {
+                                KP(1, idx) = kv;
+                                const double w0 = u0 / sk, w1 = kv / sk;
+                                p0 = fma(w0, w0, p0);
+                                p1 = fma(w1, w1, p1);
+                            } else {
+                                const double vv = (kv - KP(1, idx)) / sk;
+                                p0 = fma(vv, vv, p0);
+                            }
+                        }
+                    }
+                }
+                if (s < 2) {  // warp-level reduction over the 8 row groups (fixed tree: deterministic)
+#pragma unroll
+                    for (int off = 4; off < 32; off <<= 1) {
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, off);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, off);
+                    }
+                    if (g == 0 && mode == MODE_INIT) {
+                        sm_red0[warp * B + b] = p0;
+                        sm_red1[warp * B + b] = p1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (s < 2 && tid < B && ctl[tid].mode == MODE_INIT) {
+                ImSlotCtl& c = ctl[tid];
+                double r0 = 0., r1 = 0.;
+                for (int w = 0; w < a.MT; w++) {
+                    r0 += sm_red0[w * B + tid];
+                    r1 += sm_red1[w * B + tid];
+                }
+                if (o.dt_user > 0) {
+                    c.dt = o.dt_user;
+                    c.dt0 = 0.;
+                } else if (s == 0) {
+                    c.d0 = sqrt(r0 / N);
+                    c.d1 = sqrt(r1 / N);
+                    double dt0 = (c.d0 < 1e-5 || c.d1 < 1e-5) ? 1e-6 : 0.01 * (c.d0 / c.d1);
+                    c.dt0 = fmin(dt0, o.dtmax);
+                } else {
+                    const double d2 = sqrt(r0 / N) / c.dt0;
+                    const double dm = fmax(c.d1, d2);
+                    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, c.dt0 * 1e-3) : pow(10., -(2. + log10(dm)) / 5.);
+                    c.dt = fmin(fmin(100. * c.dt0, dt1), o.dtmax);
+                }
+            }
+            if (s < 2) __syncthreads();
+        }
+
+        // ---- error estimate partials (running slots) -----------------------------------------------------------
+#pragma unroll 1
+        for (int ct = 0; ct < CT; ct++) {
+            const int b = ct * 4 + t4;
+            const bool run = ctl[b].mode == MODE_RUN;
+            const double dts = ctl[b].dts;
+            double p = 0.;
+            if (run) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = h ? row1 : row0;
+                    if (row < N) {
+                        const int idx = row * B + b;
+                        double lin = TS_BT(0) * KP(1, idx);
+                        double lu = TS_A(5, 0) * KP(1, idx);
+#pragma unroll
+                        for (int j = 1; j < 7; j++) {
+                            const double kj = KP(1 + j, idx);
+                            lin = fma(TS_BT(j), kj, lin);
+                            if (j < 6) lu = fma(TS_A(5, j), kj, lu);
+                        }
+                        const double u0 = KP(0, idx);
+                        const double un = fma(dts, lu, u0);
+                        const double rr = (dts * lin) / (o.abstol + fmax(fabs(u0), fabs(un)) * o.reltol);
+                        p = fma(rr, rr, p);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+            if (g == 0 && run) sm_red0[warp * B + b] = p;
+        }
+        __syncthreads();
+
+        // ---- per-trajectory control: PI controller, accept / reject, save window ---------------------------------
+        if (tid < B) {
+            ImSlotCtl& c = ctl[tid];
+            c.accept = 0;
+            c.finished = 0;
+            if (c.mode == MODE_INIT) {
+                c.mode = MODE_RUN;
+                if (!begin_attempt(c)) c.finished = 1;
+            } else if (c.mode == MODE_RUN) {
+                c.natt++;
+                double e2 = 0.;
+                for (int w = 0; w < a.MT; w++) e2 += sm_red0[w * B + tid];
+                const double EEst = sqrt(e2 / N);
+                double q, q11 = 0.;
+                if (EEst == 0.) {
+                    q = 1. / o.qmax;
+                } else {
+                    q11 = pow(EEst, o.beta1);
+                    q = q11 / pow(c.qold, o.beta2);
+                    q = fmax(1. / o.qmax, fmin(1. / o.qmin, q / o.gamma));
+                }
+                if (!(EEst > 1.)) {
+                    c.qold = fmax(EEst, o.qoldinit);
+                    const double tnew = c.clipped ? o.t1 : c.t + c.dts;
+                    int k1 = c.isave;
+                    while (k1 < n_t && sm_ts[k1] <= tnew) k1++;
+                    c.s0 = c.isave;
+                    c.s1 = k1;
+                    c.isave = k1;
+                    c.t_old = c.t;
+                    c.dts_old = c.dts;
+                    c.t = tnew;
+                    c.dt = fmin(o.dtmax, fmax(o.dtmin, c.dts / q));
+                    c.accept = 1;
+                } else {
+                    c.nrej++;
+                    c.dt = c.dts / fmin(1. / o.qmin, q11 / o.gamma);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- accepted steps: fused featurizer on the saved samples, then u <- u_new, k1 <- k7 ----------------
+#pragma unroll 1
+        for (int ct = 0; ct < CT; ct++) {
+            const int b = ct * 4 + t4;
+            if (!ctl[b].accept) continue;
+            const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
+            const int ks0 = ctl[b].s0 < 1 ? 1 : ctl[b].s0, ks1 = ctl[b].s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
+            if (ks0 < ks1) {
+                // Welford state of the two owned elements: one global (L2) round trip per accepted step, the
+                // per-sample updates stay in registers
+                const int idx0 = (v0 ? row0 : 0) * B + b, idx1 = (v1 ? row1 : 0) * B + b;
+                double am[2] = {ACCS(0, idx0), ACCS(0, idx1)};
+                double a2[2] = {ACCS(1, idx0), ACCS(1, idx1)};
+                double as[2] = {ACCS(2, idx0), ACCS(2, idx1)};
+                double kk[2][8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    kk[0][j] = KP(j, idx0);
+                    kk[1][j] = KP(j, idx1);
+                }
+                for (int k = ks0; k < ks1; k++) {
+                    const double ts = sm_ts[k];
+                    double bth[7];
+                    tsit5_btheta((ts - t_old) / dts, bth);
+                    const double rk = 1. / (double)k;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        double lin = kk[h][1] * bth[0];
+#pragma unroll
+                        for (int j = 1; j < 7; j++) lin = fma(kk[h][1 + j], bth[j], lin);
+                        double x = fma(dts, lin, kk[h][0]);
+                        if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
+                            if (k == 1) {
+                                const double twopi = 6.283185307179586, pi = 3.141592653589793;
+                                double vv = julia_mod_pos(x, twopi);
+                                if (vv > pi) vv -= twopi;
+                                as[h] = x - vv;
+                                x = vv;
+                            } else {
+                                x = x - as[h];
+                            }
+                        }
+                        const double delta = x - am[h];
+                        if (fabs(delta) <= 1.7976931348623157e308) {
+                            const double mnew = fma(delta, rk, am[h]);
+                            a2[h] = fma(delta, x - mnew, a2[h]);
+                            am[h] = mnew;
+                        } else {
+                            am[h] = nonfinite_mean(am[h], x);
+                            a2[h] = nan("");
+                        }
+                    }
+                }
+                if (v0) {
+                    ACCS(0, idx0) = am[0];
+                    ACCS(1, idx0) = a2[0];
+                    ACCS(2, idx0) = as[0];
+                }
+                if (v1) {
+                    ACCS(0, idx1) = am[1];
+                    ACCS(1, idx1) = a2[1];
+                    ACCS(2, idx1) = as[1];
+                }
+            }
+            bool bad = false;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = h ? row1 : row0;
+                if (row >= N) continue;
+                const int idx = row * B + b;
+                double lu = TS_A(5, 0) * KP(1, idx);
+#pragma unroll
+                for (int j = 1; j < 6; j++) lu = fma(TS_A(5, j), KP(1 + j, idx), lu);
+                const double un = fma(dts, lu, KP(0, idx));
+                bad |= (un != un);
+                KP(0, idx) = un;
+                KP(1, idx) = KP(7, idx);  // FSAL
+            }
+            if (bad) ctl[b].ret = MCBB_RET_UNSTABLE;  // benign race: every writer stores the same value
+        }
+        __syncthreads();
+        if (tid < B) {
+            ImSlotCtl& c = ctl[tid];
+            if (c.mode == MODE_RUN && !c.finished) {
+                if (c.ret != 0 || (c.accept && !(c.t < o.t1))) {
+                    c.finished = 1;
+                } else if (!begin_attempt(c)) {
+                    c.finished = 1;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- finished trajectories: write mean / std of the owned oscillators -----------------------------------
+#pragma unroll 1
+        for (int ct = 0; ct < CT; ct++) {
+            const int b = ct * 4 + t4;
+            if (!ctl[b].finished) continue;
+            const long long run = ctl[b].run;
+            const bool ok = (ctl[b].ret == 0) && ctl[b].isave >= n_t;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = h ? row1 : row0;
+                if (row >= N) continue;
+                const int idx = row * B + b;
+                const int pos = a.filter_pos[row];
+                if (pos < 0) continue;
+                const double mean = ok ? ACCS(0, idx) : nan("");
+                const double m2 = ACCS(1, idx);
+                const double sd = ok ? sqrt((m2 < 0. ? 0. : m2) / (double)(n_t - 2)) : nan("");
+                for (int m = 0; m < a.n_meas; m++)
+                    a.io.feat[((long long)m * a.n_filter + pos) * n_mc + run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
+            }
+        }
+        __syncthreads();
+        if (tid < B && ctl[tid].finished) {
+            ImSlotCtl& c = ctl[tid];
+            if (a.io.retcode) a.io.retcode[c.run] = c.ret;
+            if (a.io.nsteps) {
+                a.io.nsteps[c.run] = c.natt;
+                a.io.nsteps[n_mc + c.run] = c.nrej;
+            }
+            c.mode = MODE_FETCH;
+            c.finished = 0;
+        }
+    }
+#undef KP
+#undef ACCS
+}
+
+static int launch_imma(ImmaArgs& a, size_t smem, int grid, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_imma<<<grid, a.nthreads, smem, st>>>(a);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
+// Returns handled = true when the problem was run on the INT8 tensor-core path.
+int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                        const SolveIO& io, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const int N = S.n_osc;
+    if (S.system != MCBB_SYS_KURAMOTO_NETWORK || hs == nullptr) return 0;
+    if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1) return 0;
+    if (N < 24 || N > 128) return 0;
+    if (getenv("MCBB_NO_IMMA")) return 0;
+    for (int m = 0; m < F.n_meas; m++)
+        if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
+    // unit-weight adjacency?
+    double uw = 0.;
+    for (size_t q = 0; q < (size_t)N * N; q++) {
+        const double v = hs->mat_a[q];
+        if (v != 0.) {
+            if (uw == 0.) uw = v;
+            if (v != uw) return 0;  // weighted couplings: the FP64 kernel (batched.cu) handles them
+        }
+    }
+    if (uw == 0.) uw = 1.;
+
+    ImmaArgs a = {};
+    a.N = N;
+    a.MT = (N + 15) / 16;
+    a.KS = (N + 31) / 32;
+    a.kstr = a.KS * 32 + 16;
+    a.nthreads = a.MT * 32;
+    a.unit_weight = uw;
+    const int NP = a.MT * 16;
+    std::vector<unsigned> afrag((size_t)a.MT * 4 * 4 * 32, 0u);
+    std::vector<int> deg(NP, 0);
+    auto A01 = [&](int i, int j) -> unsigned { return (i < N && j < N && hs->mat_a[i + (size_t)N * j] != 0.) ? 1u : 0u; };
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) deg[i] += (int)A01(i, j);
+    for (int mt = 0; mt < a.MT; mt++)
+        for (int ks = 0; ks < 4; ks++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, t = lane & 3;
+                for (int r = 0; r < 4; r++) {  // PTX ISA m16n8k32 A fragment: a0 (g, 4t..), a1 (g+8, 4t..), a2 (g, 16+4t..), a3 (g+8, 16+4t..)
+                    const int row = mt * 16 + g + ((r & 1) ? 8 : 0);
+                    const int col = ks * 32 + 4 * t + ((r & 2) ? 16 : 0);
+                    unsigned w = 0;
+                    for (int q = 0; q < 4; q++) w |= A01(row, col + q) << (8 * q);
+                    afrag[(((size_t)mt * 4 + ks) * 4 + r) * 32 + lane] = w;
+                }
+            }
+    std::vector<double> bias(NP, 0.);
+    for (int i = 0; i < N; i++) bias[i] = hs->vec_a[i];
+    std::vector<int> fpos(NP, -1);
+    if (F.filter) {
+        std::vector<int> fh(F.n_filter);
+        MCBB_CUDA_OK(cudaMemcpyAsync(fh.data(), F.filter, sizeof(int) * F.n_filter, cudaMemcpyDeviceToHost, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));
+        for (int ii = 0; ii < F.n_filter; ii++) fpos[fh[ii] - 1] = ii;
+    } else {
+        for (int i = 0; i < N; i++) fpos[i] = i;
+    }
+    unsigned* d_af = (unsigned*)scratch_get(56, sizeof(unsigned) * afrag.size());
+    int* d_deg = (int*)scratch_get(57, sizeof(int) * deg.size());
+    double* d_bias = (double*)scratch_get(52, sizeof(double) * bias.size());
+    int* d_fpos = (int*)scratch_get(53, sizeof(int) * fpos.size());
+    if (!d_af || !d_deg || !d_bias || !d_fpos) MCBB_FAIL("solve: device allocation failed");
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_af, afrag.data(), sizeof(unsigned) * afrag.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_deg, deg.data(), sizeof(int) * deg.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_bias, bias.data(), sizeof(double) * bias.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_fpos, fpos.data(), sizeof(int) * fpos.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    a.afrag = d_af;
+    a.deg = d_deg;
+    a.bias = d_bias;
+    a.filter_pos = d_fpos;
+    for (int q = 0; q < MCBB_N_SCALARS; q++) a.scalars[q] = S.scalars[q];
+    a.n_par = S.n_par;
+    for (int p = 0; p < MCBB_MAX_PAR; p++) a.par_slot[p] = S.par_slot[p];
+    a.o = o;
+    a.n_meas = F.n_meas;
+    for (int m = 0; m < F.n_meas; m++) a.meas[m] = F.meas[m];
+    a.n_filter = F.n_filter;
+    a.cyclic = F.cyclic;
+    a.io = io;
+
+    const size_t cap = 227 * 1024;
+    int CT = 0;
+    size_t smem = 0;
+    for (int cand = 8; cand >= 1; cand--) {
+        const int B = 4 * cand;
+        const size_t need = sizeof(double) * ((size_t)(IM_NSLOT + 2) * N * B + 2 * (size_t)a.MT * B +
+                                              (size_t)((io.n_t + 1) & ~1)) +
+                            sizeof(ImSlotCtl) * (size_t)B + (size_t)IM_NSLICE * 2 * B * a.kstr + 64;
+        if (need <= cap) {
+            CT = cand;
+            smem = need;
+            break;
+        }
+    }
+    if (CT == 0) return 0;
+    a.B = 4 * CT;
+    int dev = 0, sms = 148;
+    MCBB_CUDA_OK(cudaGetDevice(&dev));
+    MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long want = (io.n_mc + a.B - 1) / a.B;
+    const int grid = (int)std::min<long long>(want, sms);
+    a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * N * a.B);
+    if (!a.acc) MCBB_FAIL("solve: device allocation failed");
+    MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
+    int rc = launch_imma(a, smem, grid, st);
+    if (rc) return rc;
+    *handled = true;
+    return 0;
+}
+
+}  // namespace mcbb
