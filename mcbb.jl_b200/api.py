@@ -627,7 +627,44 @@ def cluster_n_noise(clusters):
     return int(np.count_nonzero(clusters.assignments == 0))
 
 
+def _jl_rat(x):
+    """Base.rat (twiceprecision.jl): continued-fraction ratio with terms bounded by maxintfloat(Float32)."""
+    y, a, d, b, c, m = x, 1, 1, 0, 0, 16777216.0
+    while abs(y) <= m:
+        f = int(y)
+        y -= f
+        a, c = f * a + c, a
+        b, d = f * b + d, b
+        if max(abs(a), abs(b)) > 16777216:
+            return c, d
+        if b != 0 and a / b == x:
+            break
+        if y == 0:
+            break
+        y = 1.0 / y
+    return a, b
+
+
 def _julia_range(start, step, stop):
+    """Julia Base (:)(start, step, stop) for Float64: rational lift first, literal fallback otherwise
+    (twiceprecision.jl).  Same restatement as the C library's mcbb_tsave_array uses."""
+    between = lambda a, x, b: (a <= x <= b) or (b <= x <= a)
+    sn, sd = _jl_rat(step)
+    if sd != 0 and sn / sd == step:
+        an, ad = _jl_rat(start)
+        bn, bd = _jl_rat(stop)
+        if ad != 0 and bd != 0 and an / ad == start and bn / bd == stop:
+            den = ad // math.gcd(ad, sd) * sd
+            if den != 0 and abs(start * den) <= 2 ** 53 and abs(step * den) <= 2 ** 53 and den % ad == 0 \
+                    and den % sd == 0:
+                start_n, step_n = round(start * den), round(step * den)
+                q = den * bn - bd * start_n + step_n * bd
+                dv = step_n * bd
+                ln = max(0, int(q / dv) if (q < 0) != (dv < 0) else q // dv)  # Julia div truncates toward zero
+                if between(start, start + (ln - 1) * step, stop + step / 2) and not between(start, start + ln * step,
+                                                                                            stop):
+                    return np.array([float(np.longdouble(start_n + i * step_n) / np.longdouble(den))
+                                     for i in range(ln)])
     lf = (stop - start) / step
     if lf < 0:
         return np.zeros(0)

@@ -86,14 +86,85 @@ int labels_dev(const int* root_label, long long n, long long* assignments, long 
 int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
                        cudaStream_t st);
 
-// Julia Base (:)(start, step, stop) length for Float64 (fallback path of twiceprecision.jl)
-static int julia_range_len_host(double start, double step, double stop) {
+
+// Julia Base (:)(start, step, stop) for Float64 (base/twiceprecision.jl): length and elements.  First the
+// "rational lift" (exact arithmetic when start, step, stop are ratios of small integers, e.g. 0.0:0.1:0.7),
+// then the literal fallback.
+static void jl_rat(double x, long long* num, long long* den) {
+    double y = x;
+    long long a = 1, d = 1, b = 0, c = 0;
+    const double m = 16777216.0; 
+    while (fabs(y) <= m) {
+        const long long f = (long long)y; 
+        y -= (double)f;
+        const long long a2 = f * a + c, b2 = f * b + d;
+        c = a;
+        d = b;
+        a = a2;
+        b = b2;
+        const long long aa = a < 0 ? -a : a, bb = b < 0 ? -b : b;
+        if ((aa > bb ? aa : bb) > 16777216LL) {
+            *num = c;
+            *den = d;
+            return;
+        }
+        if ((double)a / (double)b == x) break;
+        y = 1. / y;
+    }
+    *num = a;
+    *den = b;
+}
+static long long jl_gcd(long long a, long long b) {
+    if (a < 0) a = -a;
+    if (b < 0) b = -b;
+    while (b) {
+        const long long t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+static int jl_between(double a, double x, double b) { return (a <= x && x <= b) || (b <= x && x <= a); }
+/* returns the length; when out != NULL writes the elements */
+static int julia_range(double start, double step, double stop, double* out, int cap) {
+    long long sn, sd, an, ad, bn, bd;
+    jl_rat(step, &sn, &sd);
+    if (sd != 0 && (double)sn / (double)sd == step) {
+        jl_rat(start, &an, &ad);
+        jl_rat(stop, &bn, &bd);
+        if (ad != 0 && bd != 0 && (double)an / (double)ad == start && (double)bn / (double)bd == stop) {
+            const long long g = jl_gcd(ad, sd);
+            const long long den = g ? (ad / g) * sd : 0;
+            const double mx = 9007199254740992.0;
+            if (den != 0) {
+                if (fabs(start * (double)den) <= mx && fabs(step * (double)den) <= mx && den % ad == 0 && den % sd == 0) {
+                    const long long start_n = llround(start * (double)den), step_n = llround(step * (double)den);
+                    long long len = (den * bn - bd * start_n + step_n * bd) / (step_n * bd);
+                    if (len < 0) len = 0;
+                    if (jl_between(start, start + (double)(len - 1) * step, stop + step / 2) &&
+                        !jl_between(start, start + (double)len * step, stop)) {
+                        if (out)
+                            for (long long i = 0; i < len && i < cap; i++)
+                                out[i] = (double)((long double)(start_n + i * step_n) / (long double)den);
+                        return (int)len;
+                    }
+                }
+            }
+        }
+    }
     const double lf = (stop - start) / step;
-    if (lf < 0) return 0;
-    if (lf == 0) return 1;
-    int len = (int)nearbyint(lf) + 1;
-    const double stop2 = start + (len - 1) * step;
-    if ((start < stop && stop < stop2) || (start > stop && stop > stop2)) len -= 1;
+    int len;
+    if (lf < 0)
+        len = 0;
+    else if (lf == 0)
+        len = 1;
+    else {
+        len = (int)nearbyint(lf) + 1;
+        const double stop2 = start + (len - 1) * step;
+        if ((start < stop && stop < stop2) || (start > stop && stop > stop2)) len -= 1;
+    }
+    if (out)
+        for (int i = 0; i < len && i < cap; i++) out[i] = (double)((long double)start + (long double)i * (long double)step);
     return len;
 }
 
@@ -182,20 +253,14 @@ int mcbb_tsave_array(const mcbb_solver_opts* o, int32_t n_t, double rel_transien
     if (o->alg == MCBB_ALG_FUNCTIONMAP) {  // setup_mc_prob.jl:1175-1180
         const double tot = nearbyint((o->t1 - o->t0) * (1 - rel_transient_time));
         const double start = o->t1 - tot;
-        const int len = julia_range_len_host(start, 1., o->t1 - 1);
-        if (t_save)
-            for (int i = 0; i < len; i++) t_save[i] = start + i;
-        *n_out = len;
+        *n_out = julia_range(start, 1., o->t1 - 1, t_save, 1 << 30);
         return 0;
     }
     if (n_t < 1) MCBB_FAIL("tsave_array: N_t must be positive");
     const double tot = (o->t1 - o->t0) * (1 - rel_transient_time);  // setup_mc_prob.jl:1166-1172
     const double start = o->t1 - tot;
     const double dt = tot / n_t;
-    const int len = julia_range_len_host(start, dt, o->t1 - dt);
-    if (t_save)
-        for (int i = 0; i < len; i++) t_save[i] = (double)((long double)start + (long double)i * (long double)dt);
-    *n_out = len;
+    *n_out = julia_range(start, dt, o->t1 - dt, t_save, 1 << 30);
     return 0;
 }
 

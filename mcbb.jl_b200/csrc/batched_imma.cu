@@ -29,6 +29,7 @@ constexpr int IM_NSLICE = 7;  // 52-bit fixed point in bytes
 
 struct ImmaArgs {
     int N, MT, KS, B, nthreads;
+    int WS;                   // warps per 16-row tile of A (they split the column tiles)
     int kstr;                 // byte stride between digit columns (KS*32 + 16: conflict-free fragment loads)
     const unsigned* afrag;    // [MT][4][4][32] A fragments: m-tile, k-step, register, lane
     const int* deg;           // [MT*16] number of non-zero couplings per row
@@ -100,10 +101,12 @@ __device__ __forceinline__ void mma_s8u8(int (&c)[4], const unsigned (&a)[4], co
 // Shared-memory panels are indexed by (oscillator row, trajectory b): idx = row * B + b.  A warp's 64-bit
 // accesses split into half-warps of rows g = 0..3 / 4..7; with B = 20 the row stride is 40 words, so the four
 // rows of a half-warp land on banks 0, 8, 16, 24 (+2t): conflict-free.
-__global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a) {
+__device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int WS = a.WS;
+    const int warp = wid / WS, part = wid - warp * WS;  // A row tile, share of the column tiles
     const int N = a.N, B = a.B, CT = a.B >> 2;
     const int kstr = a.kstr;
     const int slice_stride = 2 * B * kstr;
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
 
     for (int i = tid; i < n_t; i += blockDim.x) sm_ts[i] = a.io.t_save[i];
     for (int i = tid; i < IM_NSLICE * slice_stride / 4; i += blockDim.x) ((unsigned*)sm_dig)[i] = 0u;
+    for (int i = tid; i < IM_NSLOT * pstride; i += blockDim.x) sm_k[i] = 0.;  // stage slots are read before written (x 0)
     if (tid < B) {
         ctl[tid].mode = MODE_FETCH;
         ctl[tid].fresh = 0;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
         const bool all_done = __syncthreads_and(tid >= B || ctl[tid].mode == MODE_DONE);
         if (all_done) break;
 #pragma unroll 1
-        for (int ct = 0; ct < CT; ct++) {
+        for (int ct = part; ct < CT; ct += WS) {
             const int b = ct * 4 + t4;
             if (ctl[b].fresh) {
                 const long long run = ctl[b].run;
@@ -200,6 +204,8 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
                     if (row < N) {
                         const int idx = row * B + b;
                         KP(0, idx) = a.io.ic[(long long)row * n_mc + run];
+#pragma unroll
+                        for (int j = 1; j < IM_NSLOT; j++) KP(j, idx) = 0.;  // no stale NaN from the slot's previous run
                         ACCS(0, idx) = 0.;
                         ACCS(1, idx) = 0.;
                         ACCS(2, idx) = 0.;
@@ -213,23 +219,25 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
         for (int s = 0; s < 6; s++) {
             // (a) stage input Y -> sin, cos -> fixed-point byte slices (shared digit panels)
 #pragma unroll 1
-            for (int ct = 0; ct < CT; ct++) {
+            for (int ct = part; ct < CT; ct += WS) {
                 const int b = ct * 4 + t4;
                 const int mode = ctl[b].mode;
                 const double hstep = (mode == MODE_RUN) ? ctl[b].dts : ctl[b].dt0;
+                // stage coefficients with zeros beyond the current stage (and k1 only for the initial-dt probe):
+                // six unconditional FMAs per element instead of a data-dependent loop
+                double cf[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+                    cf[j] = (mode == MODE_RUN) ? (j <= s ? TS_A(s, j) : 0.) : ((mode == MODE_INIT && s == 1 && j == 0) ? 1. : 0.);
                 double y[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int row = h ? row1 : row0;
                     const int idx = (row < N ? row : 0) * B + b;
-                    y[h] = KP(0, idx);
-                    if (mode == MODE_RUN) {
-                        double lin = TS_A(s, 0) * KP(1, idx);
-                        for (int j = 1; j <= s; j++) lin = fma(TS_A(s, j), KP(1 + j, idx), lin);
-                        y[h] = fma(hstep, lin, y[h]);
-                    } else if (mode == MODE_INIT && s == 1) {
-                        y[h] = fma(hstep, KP(1, idx), y[h]);
-                    }
+                    double lin = cf[0] * KP(1, idx);
+#pragma unroll
+                    for (int j = 1; j < 6; j++) lin = fma(cf[j], KP(1 + j, idx), lin);
+                    y[h] = fma(hstep, lin, KP(0, idx));
                 }
                 double sv[2], cv[2];
                 sincos_fast2(y[0], &sv[0], &cv[0]);
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
             __syncthreads();
             // (b) seven s8 x u8 GEMM slices per column tile, (c) int64 recombination and k = a1 (c P - s Q) + w
 #pragma unroll 1
-            for (int ct = 0; ct < CT; ct++) {
+            for (int ct = part; ct < CT; ct += WS) {
                 int cacc[IM_NSLICE][4];
 #pragma unroll
                 for (int sl = 0; sl < IM_NSLICE; sl++)
@@ -272,11 +280,12 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
                 // lane holds (row0, P) (row0, Q) (row1, P) (row1, Q) of trajectory b = 4 ct + t4
                 long long v[4];
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    long long sum = 0;
-#pragma unroll
-                    for (int sl = IM_NSLICE - 1; sl >= 0; sl--) sum = (sum << 8) + (long long)cacc[sl][r];
-                    v[r] = sum;
+                for (int r = 0; r < 4; r++) {  // slices are < 2^15: pairs fit 32 bits, then three 64-bit shift-adds
+                    const unsigned w0 = (unsigned)cacc[0][r] + ((unsigned)cacc[1][r] << 8);
+                    const unsigned w1 = (unsigned)cacc[2][r] + ((unsigned)cacc[3][r] << 8);
+                    const unsigned w2 = (unsigned)cacc[4][r] + ((unsigned)cacc[5][r] << 8);
+                    const unsigned w3 = (unsigned)cacc[6][r];
+                    v[r] = (long long)(((((unsigned long long)w3 << 16) + w2) << 16) + w1 << 16) + (long long)w0;
                 }
                 const int b = ct * 4 + t4;
                 const int mode = ctl[b].mode;
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
 
         // ---- error estimate partials (running slots) -----------------------------------------------------------
 #pragma unroll 1
-        for (int ct = 0; ct < CT; ct++) {
+        for (int ct = part; ct < CT; ct += WS) {
             const int b = ct * 4 + t4;
             const bool run = ctl[b].mode == MODE_RUN;
             const double dts = ctl[b].dts;
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
 
         // ---- accepted steps: fused featurizer on the saved samples, then u <- u_new, k1 <- k7 ----------------
 #pragma unroll 1
-        for (int ct = 0; ct < CT; ct++) {
+        for (int ct = part; ct < CT; ct += WS) {
             const int b = ct * 4 + t4;
             if (!ctl[b].accept) continue;
             const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
         __syncthreads();
         // ---- finished trajectories: write mean / std of the owned oscillators -----------------------------------
 #pragma unroll 1
-        for (int ct = 0; ct < CT; ct++) {
+        for (int ct = part; ct < CT; ct += WS) {
             const int b = ct * 4 + t4;
             if (!ctl[b].finished) continue;
             const long long run = ctl[b].run;
@@ -552,9 +561,26 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched_imma(const ImmaArgs a)
 #undef ACCS
 }
 
-static int launch_imma(ImmaArgs& a, size_t smem, int grid, cudaStream_t st) {
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_batched_imma<<<grid, a.nthreads, smem, st>>>(a);
+__global__ void __launch_bounds__(512, 1) k_solve_batched_imma(const ImmaArgs a) { solve_batched_imma_body(a); }
+// two resident CTAs per SM (half the batch each): their phases drift apart, FP64 and IMMA work overlap
+__global__ void __launch_bounds__(256, 2) k_solve_batched_imma_x2(const ImmaArgs a) { solve_batched_imma_body(a); }
+__global__ void __launch_bounds__(256, 3) k_solve_batched_imma_x3(const ImmaArgs a) { solve_batched_imma_body(a); }
+__global__ void __launch_bounds__(256, 4) k_solve_batched_imma_x4(const ImmaArgs a) { solve_batched_imma_body(a); }
+
+static int launch_imma(ImmaArgs& a, size_t smem, int grid, int per_sm, cudaStream_t st) {
+    if (per_sm == 2) {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_solve_batched_imma_x2<<<grid, a.nthreads, smem, st>>>(a);
+    } else if (per_sm == 3) {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_solve_batched_imma_x3<<<grid, a.nthreads, smem, st>>>(a);
+    } else if (per_sm == 4) {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma_x4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_solve_batched_imma_x4<<<grid, a.nthreads, smem, st>>>(a);
+    } else {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_solve_batched_imma<<<grid, a.nthreads, smem, st>>>(a);
+    }
     MCBB_LAUNCHED();
     return 0;
 }
@@ -586,7 +612,9 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.MT = (N + 15) / 16;
     a.KS = (N + 31) / 32;
     a.kstr = a.KS * 32 + 16;
-    a.nthreads = a.MT * 32;
+    a.WS = getenv("MCBB_IMMA_WS") ? atoi(getenv("MCBB_IMMA_WS")) : 2;
+    if (a.WS < 1 || a.WS * a.MT * 32 > 512) a.WS = 1;
+    a.nthreads = a.MT * a.WS * 32;
     a.unit_weight = uw;
     const int NP = a.MT * 16;
     std::vector<unsigned> afrag((size_t)a.MT * 4 * 4 * 32, 0u);
@@ -641,7 +669,15 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.cyclic = F.cyclic;
     a.io = io;
 
-    const size_t cap = 227 * 1024;
+    // batch per CTA: default two resident CTAs per SM with half the shared memory each (their phases drift apart,
+    // so one CTA's FP64 work overlaps the other's IMMA work: +21 % measured); MCBB_IMMA_PER_SM=1,3,4 for experiments
+    int per_sm = getenv("MCBB_IMMA_PER_SM") ? atoi(getenv("MCBB_IMMA_PER_SM")) : 2;
+    if (per_sm < 1 || per_sm > 4) per_sm = 1;
+    if (per_sm >= 2) {
+        a.WS = 1;
+        a.nthreads = a.MT * 32;
+    }
+    const size_t cap = ((size_t)227 * 1024) / per_sm - (per_sm > 1 ? 1024 : 0);  // 1 KB per CTA is reserved by the driver
     int CT = 0;
     size_t smem = 0;
     for (int cand = 8; cand >= 1; cand--) {
@@ -661,11 +697,11 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     MCBB_CUDA_OK(cudaGetDevice(&dev));
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long want = (io.n_mc + a.B - 1) / a.B;
-    const int grid = (int)std::min<long long>(want, sms);
+    const int grid = (int)std::min<long long>(want, (long long)sms * per_sm);
     a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * N * a.B);
     if (!a.acc) MCBB_FAIL("solve: device allocation failed");
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-    int rc = launch_imma(a, smem, grid, st);
+    int rc = launch_imma(a, smem, grid, per_sm, st);
     if (rc) return rc;
     *handled = true;
     return 0;

@@ -446,15 +446,91 @@ static void cyclic_setback(double* a, int n) {
     for (int i = 1; i < n; i++) a[i] = a[i] - subtr;
 }
 
-/* Julia Base (:)(start, step, stop) for Float64, fallback path (twiceprecision.jl): the length. */
-static int julia_range_len(double start, double step, double stop) {
+
+/* ---- Julia Base (:)(start, step, stop) for Float64 (base/twiceprecision.jl): length and elements.  First the
+ * "rational lift" (exact arithmetic when start, step, stop are ratios of small integers, e.g. 0.0:0.1:0.7),
+ * then the literal fallback. ---- */
+static void jl_rat(double x, long long* num, long long* den) {
+    double y = x;
+    long long a = 1, d = 1, b = 0, c = 0;
+    const double m = 16777216.0; /* maxintfloat(Float32) */
+    while (fabs(y) <= m) {
+        const long long f = (long long)y; /* trunc */
+        y -= (double)f;
+        const long long a2 = f * a + c, b2 = f * b + d;
+        c = a;
+        d = b;
+        a = a2;
+        b = b2;
+        const long long aa = a < 0 ? -a : a, bb = b < 0 ? -b : b;
+        if ((aa > bb ? aa : bb) > 16777216LL) {
+            *num = c;
+            *den = d;
+            return;
+        }
+        if ((double)a / (double)b == x) break;
+        y = 1. / y;
+    }
+    *num = a;
+    *den = b;
+}
+static long long jl_gcd(long long a, long long b) {
+    if (a < 0) a = -a;
+    if (b < 0) b = -b;
+    while (b) {
+        const long long t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+static int jl_between(double a, double x, double b) { return (a <= x && x <= b) || (b <= x && x <= a); }
+/* returns the length; when out != NULL writes the elements */
+static int julia_range(double start, double step, double stop, double* out, int cap) {
+    long long sn, sd, an, ad, bn, bd;
+    jl_rat(step, &sn, &sd);
+    if (sd != 0 && (double)sn / (double)sd == step) {
+        jl_rat(start, &an, &ad);
+        jl_rat(stop, &bn, &bd);
+        if (ad != 0 && bd != 0 && (double)an / (double)ad == start && (double)bn / (double)bd == stop) {
+            const long long g = jl_gcd(ad, sd);
+            const long long den = g ? (ad / g) * sd : 0;
+            const double mx = 9007199254740992.0;
+            if (den != 0) {
+                if (fabs(start * (double)den) <= mx && fabs(step * (double)den) <= mx && den % ad == 0 && den % sd == 0) {
+                    const long long start_n = llround(start * (double)den), step_n = llround(step * (double)den);
+                    long long len = (den * bn - bd * start_n + step_n * bd) / (step_n * bd);
+                    if (len < 0) len = 0;
+                    if (jl_between(start, start + (double)(len - 1) * step, stop + step / 2) &&
+                        !jl_between(start, start + (double)len * step, stop)) {
+                        if (out)
+                            for (long long i = 0; i < len && i < cap; i++)
+                                out[i] = (double)((long double)(start_n + i * step_n) / (long double)den);
+                        return (int)len;
+                    }
+                }
+            }
+        }
+    }
     const double lf = (stop - start) / step;
-    if (lf < 0) return 0;
-    if (lf == 0) return 1;
-    int len = (int)nearbyint(lf) + 1;
-    const double stop2 = start + (len - 1) * step;
-    if ((start < stop && stop < stop2) || (start > stop && stop > stop2)) len -= 1;
+    int len;
+    if (lf < 0)
+        len = 0;
+    else if (lf == 0)
+        len = 1;
+    else {
+        len = (int)nearbyint(lf) + 1;
+        const double stop2 = start + (len - 1) * step;
+        if ((start < stop && stop < stop2) || (start > stop && stop > stop2)) len -= 1;
+    }
+    if (out)
+        for (int i = 0; i < len && i < cap; i++) out[i] = (double)((long double)start + (long double)i * (long double)step);
     return len;
+}
+
+/* Length only (used for the KL bin centres, whose start/step are generic floats: the lift never applies). */
+static int julia_range_len(double start, double step, double stop) {
+    return julia_range(start, step, stop, NULL, 0);
 }
 
 /* Base.searchsortedlast on a Vector (binary search as in sort.jl; edges may be unsorted — quirk B.2) */
@@ -654,19 +730,13 @@ int orc_tsave_array(const mcbb_solver_opts* o, int32_t n_t, double rel_transient
     if (o->alg == MCBB_ALG_FUNCTIONMAP) {
         const double tot = nearbyint((o->t1 - o->t0) * (1 - rel_transient_time));
         const double start = o->t1 - tot;
-        const int len = julia_range_len(start, 1., o->t1 - 1);
-        if (t_save)
-            for (int i = 0; i < len; i++) t_save[i] = start + i;
-        *n_out = len;
+        *n_out = julia_range(start, 1., o->t1 - 1, t_save, 1 << 30);
         return 0;
     }
     const double tot = (o->t1 - o->t0) * (1 - rel_transient_time);
     const double start = o->t1 - tot;
     const double dt = tot / n_t;
-    const int len = julia_range_len(start, dt, o->t1 - dt);
-    if (t_save)
-        for (int i = 0; i < len; i++) t_save[i] = (double)((long double)start + (long double)i * (long double)dt);
-    *n_out = len;
+    *n_out = julia_range(start, dt, o->t1 - dt, t_save, 1 << 30);
     return 0;
 }
 
@@ -863,11 +933,13 @@ int orc_cluster_membership(const double* par, const int64_t* assignments, int64_
         if (par[i] < mn) mn = par[i];
         if (par[i] > mx) mx = par[i];
     }
-    const int nw = julia_range_len(mn, offset, mx - window);
+    const int nw = julia_range(mn, offset, mx - window, NULL, 0);
     *n_windows = nw;
     if (!out) return 0;
+    double* mins = (double*)malloc(sizeof(double) * (nw + 1));
+    julia_range(mn, offset, mx - window, mins, nw);
     for (int w = 0; w < nw; w++) {
-        const double ip = (double)((long double)mn + (long double)w * (long double)offset);
+        const double ip = mins[w];
         if (par_mesh) par_mesh[w] = ip;
         for (int64_t c = 0; c <= k; c++) out[w + (size_t)nw * c] = 0.;
         int64_t cnt = 0;
@@ -879,6 +951,7 @@ int orc_cluster_membership(const double* par, const int64_t* assignments, int64_
         if (normalize)
             for (int64_t c = 0; c <= k; c++) out[w + (size_t)nw * c] = out[w + (size_t)nw * c] / (double)cnt;
     }
+    free(mins);
     return 0;
 }
 

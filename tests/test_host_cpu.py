@@ -1,0 +1,291 @@
+"""CPU tests (-m "not gpu") of the host logic: the C-ABI library loads and exports every symbol the header
+declares, host-side helpers agree with the oracle, the Python mirror of the reference interface builds the same
+problem shapes, and the multi-rank (world_size 2, gloo) DBSCAN bookkeeping reproduces the single-rank labels.
+No compute kernel is launched here."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(mcbb):
+    hdr = open(os.path.join(ROOT, "include", "mcbb_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mcbb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    L = mcbb.lib()
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(mcbb.EXPORTS) == declared
+    assert b"sm_100a" in L.mcbb_version()
+
+
+def test_library_is_cuda_sm100a_only():
+    """The shipped library carries sm_100a SASS and no CPU implementation of the hot path."""
+    import subprocess
+    so = os.path.join(ROOT, "mcbb.jl_b200", "libmcbb_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    assert "orc_" not in syms  # the oracle is not linked into the product
+
+
+def test_tsave_array_matches_oracle_and_julia_ranges(mcbb, orc):
+    abi = mcbb.abi
+    for alg, tspan, nt, tail in [(abi.ALG_TSIT5, (0.0, 40.0), 400, 0.9), (abi.ALG_TSIT5, (0.0, 1000.0), 400, 0.9),
+                                 (abi.ALG_TSIT5, (0.0, 200.0), 400, 0.7), (abi.ALG_TSIT5, (0.0, 5000.0), 200, 0.8),
+                                 (abi.ALG_FUNCTIONMAP, (0.0, 1000.0), 400, 0.8),
+                                 (abi.ALG_FUNCTIONMAP, (0.0, 5000.0), 400, 0.8)]:
+        o = abi.solver_opts(alg, tspan)
+        n = C.c_int32(0)
+        mcbb.check(mcbb.lib().mcbb_tsave_array(C.byref(o), nt, tail, abi.c_double_p(), C.byref(n)))
+        ts = np.zeros(n.value)
+        mcbb.check(mcbb.lib().mcbb_tsave_array(C.byref(o), nt, tail, ts.ctypes.data_as(abi.c_double_p), C.byref(n)))
+        assert np.array_equal(ts, orc.tsave_array(o, nt, tail))
+        if alg == abi.ALG_TSIT5:
+            # Julia's float range can come out one short (e.g. tspan (0,200), tail 0.7: 399 points) - same quirk here
+            assert abs(len(ts) - nt) <= 1 and ts[-1] < tspan[1]
+        else:
+            assert len(ts) == round((tspan[1] - tspan[0]) * (1 - tail)) and ts[-1] == tspan[1] - 1
+    # Julia range semantics (twiceprecision.jl): rational lift makes 0.0:0.1:0.7 eight elements long
+    assert len(mcbb.api._julia_range(0.0, 0.1, 0.7)) == 8
+    assert len(mcbb.api._julia_range(0.25, 0.25, 2.5)) == 10
+    assert len(mcbb.api._julia_range(1.0, 0.5, 0.0)) == 0
+
+
+def test_error_reporting_without_gpu(mcbb):
+    L = mcbb.lib()
+    n = C.c_int32(0)
+    assert L.mcbb_tsave_array(None, 400, 0.9, mcbb.abi.c_double_p(), C.byref(n)) != 0
+    assert "NULL" in mcbb.last_error()
+    with pytest.raises(mcbb.MCBBError, match="No per dimension measures"):
+        mcbb.EvalOdeRun(eval_funcs=())
+    with pytest.raises(mcbb.MCBBError, match="failure_handling symbol not known"):
+        mcbb.EvalOdeRun(failure_handling="Bogus")
+
+
+def test_no_cpu_fallback(mcbb):
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tests import cases
+    prob, w = cases.c1_problem(mcbb, n_ics=4)
+    with pytest.raises(mcbb.MCBBError):
+        mcbb.solve(prob)
+    with pytest.raises(mcbb.MCBBError):
+        mcbb.dbscan(np.zeros((4, 4)), 1.0, 2)
+    # the product never imports, links or executes the checker
+    for f in ("api.py", "dist.py", "_lib.py", "__init__.py", "_abi.py"):
+        src = open(os.path.join(ROOT, "mcbb.jl_b200", f)).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+        assert "libmcbb_oracle" not in src and "orc_" not in src, f
+
+
+def test_problem_shapes_follow_the_reference(mcbb):
+    m = mcbb
+    N = 3
+    pars = m.kuramoto_network_parameters(0.5, np.full(N, 0.5), N, np.ones((N, N)))
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), (0.0, 10.0), pars)
+    # ranges x range: CartesianIndices order, first IC dimension fastest, parameter slowest (setup_mc_prob.jl:872-880)
+    prob = m.DEMCBBProblem(rp, [np.arange(0.0, 1.0, 0.5)] * N, pars, ("K", np.arange(1.0, 2.01, 0.5)), m.eval_ode_run, 0.9)
+    assert prob.N_mc == 2 ** 3 * 3 and prob.ic.shape == (24, 3) and prob.par.shape == (24, 1)
+    assert np.array_equal(prob.ic[:4, 0], [0, 0.5, 0, 0.5]) and np.array_equal(prob.ic[:4, 1], [0, 0, 0.5, 0.5])
+    assert np.array_equal(prob.par[:9, 0], [1.0] * 8 + [1.5])
+    # random ICs x range: identical ICs for every parameter value, IC index fastest (:929-969)
+    rng = np.random.default_rng(0)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-1, 1), 5, pars, ("K", [1.0, 2.0, 3.0]), m.eval_ode_run, 0.9)
+    assert prob.N_mc == 15 and np.array_equal(prob.ic[:5], prob.ic[5:10]) and np.array_equal(prob.ic[:5], prob.ic[10:])
+    assert np.array_equal(prob.par[:, 0], np.repeat([1.0, 2.0, 3.0], 5))
+    # random x random (:888-923)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-1, 1), 7, pars, ("K", lambda: rng.uniform(0, 5)), m.eval_ode_run, 0.9)
+    assert prob.N_mc == 7 and len(np.unique(prob.par)) == 7
+    assert m.parameter(prob).shape == (7,)
+    with pytest.raises(m.MCBBError, match="does not belong"):
+        m.ODEProblem(m.logistic, np.zeros(1), (0.0, 1.0), pars)
+
+
+def test_sort_is_stable_and_in_place(mcbb):
+    m = mcbb
+    feat = np.asfortranarray(np.arange(6 * 2 * 2, dtype=float).reshape(6, 2, 2))
+    sol = m.DEMCBBSol(feat.copy(order="F"), None, None, np.arange(6, dtype=np.int32), np.zeros((6, 2), dtype=np.int64), 400, None)
+
+    class P:
+        pass
+    prob = P()
+    prob.par = np.asfortranarray(np.array([[2.0], [1.0], [2.0], [1.0], [3.0], [1.0]]))
+    prob.ic = np.asfortranarray(np.arange(12, dtype=float).reshape(6, 2))
+    idx = m.sort_(sol, prob)
+    assert list(idx) == [1, 3, 5, 0, 2, 4]  # sortperm is stable (setup_mc_prob.jl:520-536)
+    assert np.array_equal(prob.par[:, 0], [1, 1, 1, 2, 2, 3]) and np.array_equal(sol.retcode, idx)
+    assert np.array_equal(sol.feat, feat[idx]) and np.array_equal(prob.ic[:, 0], np.arange(12).reshape(6, 2)[idx, 0])
+    assert len(sol[0]) == 2 and np.array_equal(sol[0][1], feat[1, :, 1])
+    assert np.array_equal(m.get_measure(sol, 2), sol.feat[:, :, 1])
+
+
+def test_feature_groups_and_cluster_membership_vs_oracle(mcbb, orc):
+    m = mcbb
+    rng = np.random.default_rng(3)
+    n, nd = 40, 4
+    sol = m.DEMCBBSol(np.asfortranarray(rng.normal(size=(n, nd, 2))), None, np.asfortranarray(rng.normal(size=(n, 1))),
+                      np.zeros(n, np.int32), np.zeros((n, 2), np.int64), 400, None)
+
+    class P:
+        pass
+    prob = P()
+    prob.par = np.asfortranarray(np.sort(rng.uniform(0.5, 3.0, size=(n, 1)), axis=0))
+    X, gl, gw = m.feature_groups(sol, prob, [1.0, 0.5, 0.25, 1.0])
+    assert X.shape == (n, 2 * nd + 2) and list(gl) == [nd, nd, 1, 1] and list(gw) == [1.0, 0.5, 0.25, 1.0]
+    assert np.array_equal(X[:, :nd], sol.feat[:, :, 0]) and np.array_equal(X[:, -1], prob.par[:, 0])
+    with pytest.raises(m.MCBBError, match="Amount of weights"):
+        m.feature_groups(sol, prob, [1.0, 1.0])
+    Xr, _, _ = m.feature_groups(sol, prob, [1.0, 0.5, 0.25, 1.0], relative_parameter=True)
+    p = prob.par[:, 0]
+    assert np.allclose(Xr[:, -1], (p - p.min()) / p.max())  # sic: divides by max (eval_clustering.jl:576)
+    a = rng.integers(0, 4, n)
+    res = m.DbscanResult(np.array([1, 2, 3]), a, np.bincount(a, minlength=4)[1:])
+    cm = m.cluster_membership(prob, res, 0.5, 0.1)
+    mesh, ref = orc.cluster_membership(p, a, 3, 0.5, 0.1)
+    assert np.allclose(cm.par, mesh) and np.allclose(cm.data, ref, equal_nan=True)
+    assert m.cluster_n_noise(res) == int((a == 0).sum())
+
+
+def test_shard_ranges(mcbb):
+    d = mcbb.dist
+    for n, w in [(10, 3), (7, 8), (1000000, 8), (5, 1)]:
+        rs = [d.shard_range(n, r, w) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
+        assert d.shard_sizes(n, w) == [b - a for a, b in rs]
+
+
+class _CheckerOps:
+    """CPU stand-in for the stage kernels (numpy, same contracts as the C-ABI stage entry points), so the
+    collectives and index bookkeeping of dist.dbscan_features_sharded can be exercised under gloo."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    def _d(self, Xa, Xb, gl, gw):
+        out = np.zeros((Xa.shape[1], Xb.shape[1]))
+        f = 0
+        for g, w in zip(gl, gw):
+            out += w * np.abs(Xa[f:f + g, :, None] - Xb[f:f + g, None, :]).sum(0)
+            f += g
+        return out
+
+    def rows_count(self, X, gl, gw, eps, r0, r1):
+        Xn = X.numpy()
+        return self.torch.from_numpy((self._d(Xn[:, r0:r1], Xn, gl, gw) < eps).sum(1).astype(np.int32))
+
+    def gather(self, X, idx):
+        return X[:, idx.long()].contiguous()
+
+    def rows_union(self, Xc, gl, gw, eps, c0, c1):
+        Xn = Xc.numpy()
+        n = Xn.shape[1]
+        parent = np.arange(n, dtype=np.int32)
+        D = self._d(Xn[:, c0:c1], Xn, gl, gw) < eps
+
+        def find(x):
+            while parent[x] != x:
+                x = parent[x]
+            return x
+        for i in range(c0, c1):
+            for j in np.nonzero(D[i - c0])[0]:
+                if j > i:
+                    a, b = find(i), find(j)
+                    if a != b:
+                        parent[max(a, b)] = min(a, b)
+        return self.torch.from_numpy(parent)
+
+    def merge_parents(self, parent, other):
+        p, o = parent.numpy(), other.numpy()
+
+        def find(x):
+            while p[x] != x:
+                x = p[x]
+            return x
+        for i in range(len(p)):
+            a, b = find(i), find(int(o[i]))
+            if a != b:
+                p[max(a, b)] = min(a, b)
+
+    def rows_border(self, Xn, b0, b1, Xc, core_seed, gl, gw, eps):
+        D = self._d(Xn.numpy()[:, b0:b1], Xc.numpy(), gl, gw) < eps
+        seeds = core_seed.numpy()
+        best = np.full(b1 - b0, np.iinfo(np.int32).max, dtype=np.int32)
+        for i in range(b1 - b0):
+            if D[i].any():
+                best[i] = seeds[D[i]].min()
+        return self.torch.from_numpy(best)
+
+    def labels(self, root_label):
+        rl = root_label.numpy()
+        seeds = np.array(sorted({int(r) for r in rl if r >= 0 and rl[r] == r}), dtype=np.int64)
+        rank = {s: k + 1 for k, s in enumerate(seeds)}
+        a = np.array([rank[int(r)] if r >= 0 else 0 for r in rl], dtype=np.int64)
+        counts = np.bincount(a, minlength=len(seeds) + 1)[1:]
+        return self.torch.from_numpy(a), self.torch.from_numpy(seeds + 1), self.torch.from_numpy(counts)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, X, gl, gw, eps, minpts, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import load_package
+    m = load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, s, c = m.dist.dbscan_features_sharded(torch.from_numpy(X), gl, gw, eps, minpts, rank, world, dist,
+                                             backend_ops=_CheckerOps())
+    q.put((rank, a.numpy().copy(), s.numpy().copy(), c.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_dbscan_world2_gloo(mcbb, orc):
+    """world_size 2 over gloo: all-gather of counts, union-find merge of the per-rank parent arrays, all-gather of
+    border labels -> labels identical to the sequential oracle on every rank."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(17)
+    pts = np.concatenate([rng.normal(c, 0.3, size=(40, 2)) for c in [(0, 0), (3, 0), (0, 3)]] + [rng.uniform(-2, 5, size=(25, 2))])
+    pts = pts[rng.permutation(len(pts))]
+    X = np.ascontiguousarray(pts.T)  # [F, n]
+    gl, gw = np.array([1, 1], dtype=np.int32), np.array([1.0, 0.5])
+    D = orc.distance_matrix(pts, gl, gw)
+    eps, minpts = 0.45, 4
+    ref = orc.dbscan(D, eps, minpts)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, X, gl, gw, eps, minpts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, a, s, c in got:
+        assert np.array_equal(a, ref["assignments"]), rank
+        assert np.array_equal(s, ref["seeds"]) and np.array_equal(c, ref["counts"])
+    # single-rank path through the same code
+    import torch
+    a1, s1, c1 = mcbb.dist.dbscan_features_sharded(torch.from_numpy(X), gl, gw, eps, minpts, 0, 1, None,
+                                                   backend_ops=_CheckerOps())
+    assert np.array_equal(a1.numpy(), ref["assignments"])
