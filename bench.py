@@ -103,10 +103,11 @@ def cpu_baseline(m, A, psys, pfeat, opts, ts, n_sample, seed_offset=0):
     rng = np.random.default_rng(1000 + seed_offset)
     ic = np.asfortranarray(rng.uniform(-np.pi, np.pi, size=(n_sample, N_OSC)))
     par = np.asfortranarray(rng.uniform(0.0, 8.0, size=(n_sample, 1)))
+    threads = os.cpu_count() or 1  # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     t0 = time.perf_counter()
-    orc.solve_features(psys, opts, pfeat, ic, par, ts)
+    orc.solve_features(psys, opts, pfeat, ic, par, ts, n_threads=threads)
     dt = time.perf_counter() - t0
-    return n_sample / dt, dt, orc.num_threads()
+    return n_sample / dt, dt, threads
 
 
 def run_reference(args):
@@ -316,7 +317,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # reported at N=1 only (rank 0)
             v, dt, threads = cpu_baseline(m, A, psys, pfeat, opts, ts, args.cpu_sample)
             cpu = {"value": v, "unit": "trajectories/s", "cores": threads, "kind": "port",
                    "sample": "%d trajectories of the same C5 workload in %.1f s (oracle restatement of the reference's "

@@ -1,0 +1,225 @@
+# MCBBB200.jl — reference-side binding of libmcbb_b200.so (B200, sm_100a) for the MCBB.jl hot path.
+#
+# UNTESTED HERE: no `julia` binary exists in the build image or on the GPU box, so this file is the binding a
+# maintainer would add; every ccall below is exercised through the identical C-ABI by the Python mirror
+# (mcbb.jl_b200/api.py) in tests/.  Written against the reference's pinned environment (Julia 1.3,
+# DiffEqBase 6.10.1, Clustering 0.13.3).
+#
+# Drop-in points (SURVEY §8(b)):
+#   1. solve(prob::DEMCBBProblem, ...; custom_solve = MCBBB200.custom_solve_b200)   src/setup_mc_prob.jl:1098-1104
+#      NOTE the reference bug on that branch: `solve_i_command = nothing` is passed to the `::Function` field of
+#      DEMCBBSol (setup_mc_prob.jl:471, 1104, 1116).  `solve_b200` below repeats lines 1100-1127 with a valid
+#      solve_command instead of patching the reference.
+#   2. distance_matrix_b200(sol, prob, weights; relative_parameter) -> DistanceMatrix        eval_clustering.jl:164-241
+#      feature_matrix_b200(sol, prob, weights)                      -> B200FeatureMatrix <: AbstractDistanceMatrix
+#   3. Clustering.dbscan(::B200FeatureMatrix, eps, minpts) / dbscan_b200(D, eps, minpts)     eval_clustering.jl:84
+module MCBBB200
+
+using MCBB
+using DiffEqBase, Clustering
+import Clustering: dbscan
+
+const LIB = get(ENV, "MCBB_B200_LIB", "libmcbb_b200.so")
+
+const MAX_MEAS, MAX_PAR, MAX_GLOBAL, N_SCALARS = 8, 4, 4, 8
+
+# ---- mirrors of the C structs (include/mcbb_b200.h); isbits, passed by reference -----------------------------
+struct SystemDesc
+    system::Int32; n_osc::Int32; n_dim::Int32; n_edges::Int32
+    mat_a::Ptr{Float64}; mat_b::Ptr{Float64}; vec_a::Ptr{Float64}; vec_b::Ptr{Float64}; vec_c::Ptr{Float64}
+    scalars::NTuple{N_SCALARS,Float64}
+    n_par::Int32
+    par_slot::NTuple{MAX_PAR,Int32}
+end
+
+struct SolverOpts
+    alg::Int32; reserved::Int32
+    t0::Float64; t1::Float64; abstol::Float64; reltol::Float64; dt::Float64; dtmin::Float64; dtmax::Float64
+    maxiters::Int64
+    qmin::Float64; qmax::Float64; gamma::Float64; beta1::Float64; beta2::Float64; qoldinit::Float64
+end
+
+struct FeatOpts
+    n_meas::Int32
+    meas::NTuple{MAX_MEAS,Int32}
+    meas_comp::NTuple{MAX_MEAS,Int32}
+    n_filter::Int32
+    state_filter::Ptr{Int32}
+    cyclic_setback::Int32; matrix_meas::Int32; corr_nbins::Int32
+    n_global::Int32
+    global_meas::NTuple{MAX_GLOBAL,Int32}
+    kl_bins::Int32
+    kl_n_stds::Float64; kl_sig_tol::Float64
+end
+
+const SYS_LOGISTIC, SYS_KURAMOTO_NETWORK, SYS_SECOND_ORDER_KURAMOTO, SYS_NONLOCAL_RING, SYS_STUART_LANDAU,
+      SYS_ROESSLER, SYS_KURAMOTO = Int32.(0:6)
+const ALG_TSIT5, ALG_RK4, ALG_FUNCTIONMAP = Int32.(0:2)
+const MEAS_MEAN, MEAS_STD, MEAS_KL_HIST = Int32.(0:2)
+
+function check(status::Cint)
+    status == 0 && return
+    buf = Vector{UInt8}(undef, 2048)
+    ccall((:mcbb_last_error, LIB), Csize_t, (Ptr{UInt8}, Csize_t), buf, length(buf))
+    error(unsafe_string(pointer(buf)))
+end
+
+pad(t, n, z) = ntuple(i -> i <= length(t) ? t[i] : z, n)
+
+# ---- system descriptors: the flat form of the @with_kw parameter structs of src/systems.jl --------------------
+# Returns (SystemDesc, keep_alive): the arrays the descriptor points into must outlive the ccall.
+function system_desc(p::MCBB.kuramoto_network_parameters, names)
+    A = Matrix{Float64}(p.A); w = Vector{Float64}(p.w)
+    slots = Dict(:K => 0)
+    SystemDesc(SYS_KURAMOTO_NETWORK, p.N, p.N, 0, pointer(A), C_NULL, pointer(w), C_NULL, C_NULL,
+               pad((Float64(p.K),), N_SCALARS, 0.0), length(names), pad(Int32[slots[n] for n in names], MAX_PAR, Int32(0))), (A, w)
+end
+function system_desc(p::MCBB.logistic_parameters, names)
+    SystemDesc(SYS_LOGISTIC, 1, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, pad((p.r,), N_SCALARS, 0.0),
+               length(names), pad(Int32[0 for _ in names], MAX_PAR, Int32(0))), ()
+end
+function system_desc(p::MCBB.second_order_kuramoto_parameters, names)
+    E = Matrix{Float64}(p.incidence); d = Vector{Float64}(p.drive)
+    slots = Dict(:damping => 0, :coupling => 1)
+    SystemDesc(SYS_SECOND_ORDER_KURAMOTO, p.systemsize, 2p.systemsize, size(E, 2), pointer(E), C_NULL, pointer(d), C_NULL,
+               C_NULL, pad((p.damping, p.coupling), N_SCALARS, 0.0), length(names),
+               pad(Int32[slots[n] for n in names], MAX_PAR, Int32(0))), (E, d)
+end
+function system_desc(p::MCBB.non_local_kuramoto_ring_parameters, names)
+    # the coupling_function closure cannot cross the ABI: tabulate G(fak*(k-j)), k-j = -(N-1):(N-1)
+    G = Float64[p.coupling_function(p.fak * d) for d in -(p.N - 1):(p.N - 1)]
+    slots = Dict(:omega_0 => 0, :phase_delay => 1)
+    SystemDesc(SYS_NONLOCAL_RING, p.N, p.N, 0, pointer(G), C_NULL, C_NULL, C_NULL, C_NULL,
+               pad((Float64(p.omega_0), Float64(p.phase_delay), p.fak), N_SCALARS, 0.0), length(names),
+               pad(Int32[slots[n] for n in names], MAX_PAR, Int32(0))), (G,)
+end
+function system_desc(p::MCBB.roessler_parameters, names)
+    L = Matrix{Float64}(p.L)
+    SystemDesc(SYS_ROESSLER, p.N, 3p.N, 0, pointer(L), C_NULL, pointer(p.a), pointer(p.b), pointer(p.c),
+               pad((p.K,), N_SCALARS, 0.0), length(names), pad(Int32[0 for _ in names], MAX_PAR, Int32(0))), (L,)
+end
+
+# ---- eval_ode_run as data: the closure is opaque, the user states what it computes ---------------------------
+"""
+    B200Eval(; measures=[:mean, :std, :kl_hist], state_filter=nothing, cyclic_setback=false)
+
+Describes the `eval_ode_run` variant the problem was built with (src/eval_mc_prob.jl:75-198).  The default is the
+reference's default `eval_ode_run(sol, i)` (eval_mc_prob.jl:191-198).
+"""
+Base.@kwdef struct B200Eval
+    measures::Vector{Symbol} = [:mean, :std, :kl_hist]
+    state_filter::Union{Nothing,Vector{Int}} = nothing
+    cyclic_setback::Bool = false
+end
+const MEAS_ID = Dict(:mean => MEAS_MEAN, :std => MEAS_STD, :kl_hist => MEAS_KL_HIST)
+
+"""
+    custom_solve_b200(prob::DEMCBBProblem, t_save; eval=B200Eval(), alg=ALG_TSIT5, kwargs...)
+
+The `custom_solve(prob, t_save)` plug-in of `MCBB.solve` (src/setup_mc_prob.jl:1102-1104): integrates and
+featurizes all `prob.N_mc` trajectories on the GPU and returns an `EnsembleSolution` whose `u[i]` is the tuple of
+measure vectors `eval_ode_run` would have produced, in the original run order.
+"""
+function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eval::B200Eval=B200Eval(),
+                           alg::Int32=(prob.p.prob isa DiscreteProblem ? ALG_FUNCTIONMAP : ALG_TSIT5),
+                           abstol=0.0, reltol=0.0, dt=0.0, maxiters=0)
+    names = [prob.par_var[i].name for i in 1:length(prob.par_var)]
+    desc, keep = system_desc(prob.p.prob.p, names)
+    tspan = prob.p.prob.tspan
+    opts = SolverOpts(alg, 0, tspan[1], tspan[2], abstol, reltol, dt, 0.0, 0.0, maxiters, 0, 0, 0, 0, 0, 0)
+    filt = eval.state_filter === nothing ? Int32[] : Int32.(eval.state_filter)
+    nf = eval.state_filter === nothing ? size(prob.ic, 2) : length(filt)
+    nm = length(eval.measures)
+    fo = FeatOpts(nm, pad(Int32[MEAS_ID[m] for m in eval.measures], MAX_MEAS, Int32(0)), pad(Int32[], MAX_MEAS, Int32(0)),
+                  length(filt), isempty(filt) ? C_NULL : pointer(filt), eval.cyclic_setback, 0, 30, 0,
+                  pad(Int32[], MAX_GLOBAL, Int32(0)), 31, 3.0, 1e-4)
+    ic = Matrix{Float64}(prob.ic)            # N_mc x N_dim, column-major: already struct-of-arrays over runs
+    par = Matrix{Float64}(prob.par)
+    ts = Vector{Float64}(t_save)
+    feat = Array{Float64}(undef, prob.N_mc, nf, nm)
+    retcode = Vector{Int32}(undef, prob.N_mc)
+    nsteps = Matrix{Int64}(undef, prob.N_mc, 2)
+    GC.@preserve keep filt ic par ts feat retcode nsteps begin
+        check(ccall((:mcbb_solve_features, LIB), Cint,
+                    (Ref{SystemDesc}, Ref{SolverOpts}, Ref{FeatOpts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
+                    desc, opts, fo, prob.N_mc, ic, par, ts, length(ts), feat, C_NULL, C_NULL, retcode, nsteps))
+    end
+    u = [ntuple(m -> feat[i, :, m], nm) for i in 1:prob.N_mc]
+    DiffEqBase.EnsembleSolution(u, 0.0, true)
+end
+
+"`solve` of src/setup_mc_prob.jl:1098-1128 with the GPU back end and a valid `solve_command` (see header)."
+function solve_b200(prob::MCBB.DEMCBBProblem, N_t::Int=400; eval::B200Eval=B200Eval(), sort_results=true, kwargs...)
+    t_save = collect(MCBB.tsave_array(prob.p.prob, N_t, prob.rel_transient_time))
+    sol = custom_solve_b200(prob, t_save; eval=eval, kwargs...)
+    solve_i = (prob_i) -> DiffEqBase.solve(prob_i, dense=false, save_everystep=false, saveat=t_save, savestart=false)
+    mysol = MCBB.DEMCBBSol(sol, prob.N_mc, N_t, length(sol[1][1]), MCBB.get_measure_dimensions(sol, length(sol[1][1]))..., solve_i)
+    inf_nan = MCBB.check_inf_nan(mysol)
+    (length(inf_nan["Inf"]) > 0) | (length(inf_nan["NaN"]) > 0) &&
+        @warn "Some elements of the solution are Inf or NaN, check the solution with check_inf_nan again!"
+    sort_results && MCBB.sort!(mysol, prob)
+    mysol
+end
+
+# ---- distance matrix / DBSCAN ----------------------------------------------------------------------------------
+"Feature matrix [N_mc x F] + (group_len, group_weight) in distance_matrix's measure order (eval_clustering.jl:205-224)."
+function feature_groups(sol::MCBB.myMCSol, prob::MCBB.myMCProblem, weights::AbstractVector; relative_parameter::Bool=false)
+    cols = Matrix{Float64}[]; glen = Int32[]
+    for k in 1:sol.N_meas
+        M = MCBB.get_measure(sol, k)
+        M = ndims(M) == 1 ? reshape(Vector{Float64}(M), :, 1) : Matrix{Float64}(M)
+        push!(cols, M); push!(glen, size(M, 2))
+    end
+    par = relative_parameter ? MCBB._relative_parameter(prob) : MCBB.parameter(prob)
+    par = ndims(par) == 1 ? reshape(Vector{Float64}(par), :, 1) : Matrix{Float64}(par)
+    for p in 1:size(par, 2)
+        push!(cols, par[:, p:p]); push!(glen, 1)
+    end
+    length(weights) == length(glen) || error("Amount of weights not the same as Measures + Parameters")
+    hcat(cols...), glen, Vector{Float64}(weights)
+end
+
+function distance_matrix_b200(sol, prob, weights; relative_parameter::Bool=false)
+    X, glen, gw = feature_groups(sol, prob, weights; relative_parameter=relative_parameter)
+    n = size(X, 1)
+    D = Matrix{Float64}(undef, n, n)
+    check(ccall((:mcbb_distance_matrix, LIB), Cint, (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                X, n, length(glen), glen, gw, D))
+    MCBB.DistanceMatrix(D, weights, (x, y) -> sum(abs.(x .- y)), nothing, relative_parameter)
+end
+
+"Holds the featurized runs instead of the N x N matrix; `dbscan` recomputes distances tile by tile on the device."
+struct B200FeatureMatrix <: MCBB.AbstractDistanceMatrix{Float64}
+    X::Matrix{Float64}; group_len::Vector{Int32}; group_weight::Vector{Float64}
+    weights::AbstractVector; relative_parameter::Bool
+end
+Base.size(fm::B200FeatureMatrix) = (size(fm.X, 1), size(fm.X, 1))
+feature_matrix_b200(sol, prob, weights; relative_parameter::Bool=false) =
+    B200FeatureMatrix(feature_groups(sol, prob, weights; relative_parameter=relative_parameter)..., weights, relative_parameter)
+
+function _dbscan_result(n, f)
+    a = Vector{Int64}(undef, n); s = Vector{Int64}(undef, n); c = Vector{Int64}(undef, n); k = Ref{Int64}(0)
+    check(f(a, s, c, k))
+    Clustering.DbscanResult(s[1:k[]], a, c[1:k[]])
+end
+
+function dbscan(fm::B200FeatureMatrix, eps::Real, minpts::Int)
+    n = size(fm.X, 1)
+    _dbscan_result(n, (a, s, c, k) -> ccall((:mcbb_dbscan_features, LIB), Cint,
+        (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Float64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}),
+        fm.X, n, length(fm.group_len), fm.group_len, fm.group_weight, Float64(eps), Int32(minpts), a, s, c, k))
+end
+
+"GPU replacement of `Clustering.dbscan(D.data, eps, minpts)` on a materialised matrix (eval_clustering.jl:84)."
+function dbscan_b200(D::AbstractMatrix{Float64}, eps::Real, minpts::Int)
+    n = size(D, 1)
+    size(D, 2) == n || throw(ArgumentError("D must be a square matrix ($(size(D)) given)."))
+    Dd = Matrix{Float64}(D)
+    _dbscan_result(n, (a, s, c, k) -> ccall((:mcbb_dbscan_dense, LIB), Cint,
+        (Ptr{Float64}, Int64, Float64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}),
+        Dd, n, Float64(eps), Int32(minpts), a, s, c, k))
+end
+dbscan_b200(D::MCBB.AbstractDistanceMatrix, eps::Real, minpts::Int) = dbscan_b200(D.data, eps, minpts)
+
+end # module
