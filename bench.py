@@ -285,6 +285,10 @@ def main():
         else:
             X, t_gather = Xl, 0.0
         X = torch.nan_to_num(X, nan=1e30)
+        # MCBB.solve sorts the runs by parameter before any clustering (sort!, setup_mc_prob.jl:1124-1126):
+        # stable sort on the parameter row, identical on every rank
+        order = torch.sort(X[-1], stable=True).indices
+        X = X[:, order].contiguous()
         n_all = X.shape[1]
         gl = np.array([nf, nf, 1], dtype=np.int32)
         gw = np.array([1.0, 0.5, 1.0])

@@ -101,21 +101,26 @@ __device__ __forceinline__ void mma_s8u8(int (&c)[4], const unsigned (&a)[4], co
 // Shared-memory panels are indexed by (oscillator row, trajectory b): idx = row * B + b.  A warp's 64-bit
 // accesses split into half-warps of rows g = 0..3 / 4..7; with B = 20 the row stride is 40 words, so the four
 // rows of a half-warp land on banks 0, 8, 16, 24 (+2t): conflict-free.
+template <int CT_T, int KS_T>
 __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int WS = a.WS;
     const int warp = wid / WS, part = wid - warp * WS;  // A row tile, share of the column tiles
-    const int N = a.N, B = a.B, CT = a.B >> 2;
-    const int kstr = a.kstr;
+    // CT_T / KS_T > 0: compile-time batch width and K depth => digit-panel strides become immediates
+    const int N = a.N;
+    const int CT = CT_T > 0 ? CT_T : (a.B >> 2);
+    const int B = 4 * CT;
+    const int KSTEPS = KS_T > 0 ? KS_T : a.KS;
+    const int kstr = KS_T > 0 ? (KS_T * 32 + 16) : a.kstr;
     const int slice_stride = 2 * B * kstr;
     const int pstride = N * B;                                      // one panel
     double* sm_k = (double*)smem;                                   // [8][N][B]  u, k1..k7
-    double* sm_sc = sm_k + (size_t)IM_NSLOT * pstride;              // [2][N][B]  sin, cos of the stage input
-    double* sm_red0 = sm_sc + (size_t)2 * pstride;                  // [MT][B]
-    double* sm_red1 = sm_red0 + (size_t)a.MT * B;                   // [MT][B]
-    double* sm_ts = sm_red1 + (size_t)a.MT * B;                     // [n_t]
+    double* sm_sc = sm_k + IM_NSLOT * pstride;              // [2][N][B]  sin, cos of the stage input
+    double* sm_red0 = sm_sc + 2 * pstride;                  // [MT][B]
+    double* sm_red1 = sm_red0 + a.MT * B;                   // [MT][B]
+    double* sm_ts = sm_red1 + a.MT * B;                     // [n_t]
     ImSlotCtl* ctl = (ImSlotCtl*)(sm_ts + ((a.io.n_t + 1) & ~1));   // [B]
     unsigned char* sm_dig = (unsigned char*)(ctl + B);              // [NSLICE][2B][kstr]
     const SolverDev& o = a.o;
@@ -125,8 +130,8 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
     const int row0 = warp * 16 + g, row1 = row0 + 8;
     const bool v0 = row0 < N, v1 = row1 < N;
 
-#define KP(slot, idx) sm_k[(size_t)(slot)*pstride + (idx)]
-#define ACCS(k, idx) acc[(size_t)(k)*pstride + (idx)]
+#define KP(slot, idx) sm_k[(slot)*pstride + (idx)]
+#define ACCS(k, idx) acc[(k)*pstride + (idx)]
 
     for (int i = tid; i < n_t; i += blockDim.x) sm_ts[i] = a.io.t_save[i];
     for (int i = tid; i < IM_NSLICE * slice_stride / 4; i += blockDim.x) ((unsigned*)sm_dig)[i] = 0u;
@@ -249,7 +254,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                         const int idx = row * B + b;
                         sm_sc[idx] = sv[h];
                         sm_sc[pstride + idx] = cv[h];
-                        unsigned char* p = sm_dig + (size_t)(2 * b) * kstr + row;
+                        unsigned char* p = sm_dig + (2 * b) * kstr + row;
                         store_digits(p, slice_stride, sv[h]);
                         store_digits(p + kstr, slice_stride, cv[h]);
                     }
@@ -264,13 +269,13 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                 for (int sl = 0; sl < IM_NSLICE; sl++)
 #pragma unroll
                     for (int r = 0; r < 4; r++) cacc[sl][r] = 0;
-                const unsigned char* colp = sm_dig + (size_t)(ct * 8 + g) * kstr + 4 * t4;
+                const unsigned char* colp = sm_dig + (ct * 8 + g) * kstr + 4 * t4;
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
-                    if (ks < a.KS) {
+                    if (ks < KSTEPS) {
 #pragma unroll
                         for (int sl = 0; sl < IM_NSLICE; sl++) {
-                            const unsigned char* q = colp + (size_t)sl * slice_stride + ks * 32;
+                            const unsigned char* q = colp + sl * slice_stride + ks * 32;
                             const unsigned b0 = *reinterpret_cast<const unsigned*>(q);
                             const unsigned b1 = *reinterpret_cast<const unsigned*>(q + 16);
                             mma_s8u8(cacc[sl], afr[ks], b0, b1);
@@ -561,13 +566,30 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
 #undef ACCS
 }
 
-__global__ void __launch_bounds__(512, 1) k_solve_batched_imma(const ImmaArgs a) { solve_batched_imma_body(a); }
+__global__ void __launch_bounds__(512, 1) k_solve_batched_imma(const ImmaArgs a) { solve_batched_imma_body<0, 0>(a); }
 // two resident CTAs per SM (half the batch each): their phases drift apart, FP64 and IMMA work overlap
-__global__ void __launch_bounds__(256, 2) k_solve_batched_imma_x2(const ImmaArgs a) { solve_batched_imma_body(a); }
-__global__ void __launch_bounds__(256, 3) k_solve_batched_imma_x3(const ImmaArgs a) { solve_batched_imma_body(a); }
-__global__ void __launch_bounds__(256, 4) k_solve_batched_imma_x4(const ImmaArgs a) { solve_batched_imma_body(a); }
+__global__ void __launch_bounds__(256, 2) k_solve_batched_imma_x2(const ImmaArgs a) { solve_batched_imma_body<0, 0>(a); }
+__global__ void __launch_bounds__(256, 3) k_solve_batched_imma_x3(const ImmaArgs a) { solve_batched_imma_body<0, 0>(a); }
+__global__ void __launch_bounds__(256, 4) k_solve_batched_imma_x4(const ImmaArgs a) { solve_batched_imma_body<0, 0>(a); }
+// specialised: compile-time (column tiles, K steps), two CTAs per SM
+template <int CT_T, int KS_T>
+__global__ void __launch_bounds__(256, 2) k_solve_batched_imma_x2s(const ImmaArgs a) { solve_batched_imma_body<CT_T, KS_T>(a); }
+
+template <int CT_T, int KS_T>
+static int launch_imma_spec(ImmaArgs& a, size_t smem, int grid, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma_x2s<CT_T, KS_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_imma_x2s<CT_T, KS_T><<<grid, a.nthreads, smem, st>>>(a);
+    MCBB_LAUNCHED();
+    return 0;
+}
 
 static int launch_imma(ImmaArgs& a, size_t smem, int grid, int per_sm, cudaStream_t st) {
+    if (per_sm == 2 && a.WS == 1 && !getenv("MCBB_IMMA_GENERIC")) {
+        const int CT = a.B / 4;
+#define MCBB_SPEC(c, k) if (CT == c && a.KS == k) return launch_imma_spec<c, k>(a, smem, grid, st);
+        MCBB_SPEC(1, 4) MCBB_SPEC(2, 4) MCBB_SPEC(2, 3) MCBB_SPEC(3, 3) MCBB_SPEC(3, 2) MCBB_SPEC(4, 2)
+#undef MCBB_SPEC
+    }
     if (per_sm == 2) {
         MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_imma_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_solve_batched_imma_x2<<<grid, a.nthreads, smem, st>>>(a);

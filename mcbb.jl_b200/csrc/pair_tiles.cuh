@@ -77,8 +77,10 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
-    __shared__ double s_r[FC][TILE];
-    __shared__ double s_c[FC][TILE];
+    __shared__ double s_slab[2][FC][TILE];  // row-side and column-side feature slabs (contiguous: reused as the
+                                            // 32 x 64 staging buffer of the materialising store)
+    double (*s_r)[TILE] = s_slab[0];
+    double (*s_c)[TILE] = s_slab[1];
     __shared__ double s_w[FC];
     __shared__ unsigned char s_e[FC];
 
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
             s_e[tid] = tid < fc ? a.fend[f0 + tid] : 0;
         }
         __syncthreads();
+#pragma unroll 4
         for (int f = 0; f < fc; f++) {
             double xr[TT], xc[TT];
 #pragma unroll
@@ -146,41 +149,98 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
     }
 
     // ---- consume the 4 x 4 block ---------------------------------------------------------------------
+    if (MODE == TM_MATERIALIZE) {
+        // Stage the tile in shared memory (reusing the feature slabs: 2 x 16 x 64 doubles = one 64 x 32 half
+        // at a time) so that BOTH D[tile] and its mirror D[tile]^T leave as 512-byte coalesced rows.
+        double* s_t = &s_r[0][0];  // 32 x 64 doubles = 16 KB (s_r and s_c are contiguous)
+        static_assert(2 * FC == 32, "staging buffer is 32 x 64 doubles");
+        const bool diag = a.symmetric && (tc == tr);
+#pragma unroll
+        for (int half = 0; half < 2; half++) {  // columns [32*half, 32*half+32) of the tile
+            __syncthreads();
+            if ((ty >> 3) == half) {
+#pragma unroll
+                for (int i = 0; i < TT; i++)
+#pragma unroll
+                    for (int j = 0; j < TT; j++) {
+                        const int cl = (ty & 7) * TT + j, rl = tx * TT + i;
+                        s_t[cl * TILE + (rl ^ cl)] = acc[i][j];  // XOR swizzle: both read orientations conflict-free
+                    }
+            }
+            __syncthreads();
+            // direct orientation: for each of the 32 columns, 64 contiguous rows
+            for (int q = tid; q < 32 * TILE; q += 256) {
+                const int cl = q >> 6, rl = q & 63;
+                const long long ri = tr + rl, cj = tc + 32 * half + cl;
+                if (ri < a.r1 && cj < a.c1) {
+                    double d = s_t[cl * TILE + (rl ^ cl)];
+                    if (a.symmetric) {
+                        if (cj < ri && diag) continue;      // lower part of a diagonal tile comes from the mirror
+                        if (cj == ri) d = 0.;
+                    }
+                    a.D[ri + a.ldr * cj] = d;
+                }
+            }
+            // mirrored orientation (symmetric only): D[cj, ri] — contiguous in cj for fixed ri
+            if (a.symmetric) {
+                for (int q = tid; q < 32 * TILE; q += 256) {
+                    const int rl = q >> 5, cl = q & 31;
+                    const long long ri = tr + rl, cj = tc + 32 * half + cl;
+                    if (ri < a.r1 && cj < a.c1 && cj > ri) a.D[cj + a.ldr * ri] = s_t[cl * TILE + (rl ^ cl)];
+                }
+            }
+        }
+        return;
+    }
+    if (MODE == TM_COUNT) {
+        // neighbour counts aggregated per tile in shared memory: one global atomic per row / column and tile
+        __shared__ int s_cnt[2 * TILE];
+        __syncthreads();
+        if (tid < 2 * TILE) s_cnt[tid] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < TT; i++) {
+            const long long ri = tr + tx * TT + i;
+            if (ri >= a.r1) continue;
+            int local = 0;
+#pragma unroll
+            for (int j = 0; j < TT; j++) {
+                const long long cj = tc + ty * TT + j;
+                if (cj >= a.c1) continue;
+                if (a.symmetric && cj <= ri) continue;
+                if (!(acc[i][j] < a.eps)) continue;  // strict, sparse_clustering.jl:173
+                local++;
+                if (a.symmetric) atomicAdd(&s_cnt[TILE + ty * TT + j], 1);
+            }
+            if (local) atomicAdd(&s_cnt[tx * TT + i], local);
+        }
+        __syncthreads();
+        if (tid < TILE) {
+            const long long ri = tr + tid;
+            if (s_cnt[tid] && ri < a.r1) atomicAdd(&a.cnt[ri], s_cnt[tid]);
+        } else if (tid < 2 * TILE && a.symmetric) {
+            const long long cj = tc + (tid - TILE);
+            if (s_cnt[tid] && cj < a.c1) atomicAdd(&a.cnt[cj], s_cnt[tid]);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < TT; i++) {
         const long long ri = tr + tx * TT + i;
         if (ri >= a.r1) continue;
-        int local = 0;
 #pragma unroll
         for (int j = 0; j < TT; j++) {
             const long long cj = tc + ty * TT + j;
             if (cj >= a.c1) continue;
             const double d = acc[i][j];
-            if (MODE == TM_MATERIALIZE) {
-                if (a.symmetric) {
-                    if (cj > ri) {
-                        a.D[ri + a.ldr * cj] = d;
-                        a.D[cj + a.ldr * ri] = d;
-                    } else if (cj == ri) {
-                        a.D[ri + a.ldr * ri] = 0.;
-                    }
-                } else {
-                    a.D[ri + a.ldr * cj] = d;
-                }
-            } else {
-                if (a.symmetric && cj <= ri) continue;
-                if (!(d < a.eps)) continue;  // strict, sparse_clustering.jl:173
-                if (MODE == TM_COUNT) {
-                    local++;
-                    if (a.symmetric) atomicAdd(&a.cnt[cj], 1);
-                } else if (MODE == TM_UNION) {
-                    uf_union(a.parent, (int)ri, (int)cj);
-                } else if (MODE == TM_BORDER) {
-                    atomicMin(&a.best[ri], a.col_root[cj]);
-                }
+            if (a.symmetric && cj <= ri) continue;
+            if (!(d < a.eps)) continue;  // strict, sparse_clustering.jl:173
+            if (MODE == TM_UNION) {
+                uf_union(a.parent, (int)ri, (int)cj);
+            } else if (MODE == TM_BORDER) {
+                atomicMin(&a.best[ri], a.col_root[cj]);
             }
         }
-        if (MODE == TM_COUNT && local) atomicAdd(&a.cnt[ri], local);
     }
 }
 
