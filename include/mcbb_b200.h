@@ -205,6 +205,14 @@ int mcbb_dbscan_features_dev(const double* X_dev, int64_t n, int32_t n_groups, c
                              int64_t* assignments_dev, int64_t* seeds_dev, int64_t* counts_dev,
                              int64_t* n_clusters_host, void* stream);
 
+/* ---- eps-selection helpers -----------------------------------------------------------------------------------
+ * Replace k_dist / KNN_dist / KNN_dist_relative (src/eval_clustering.jl:1504-1553): every row of the (symmetric)
+ * distance matrix is sorted ascending on the device; kth_out[i] = sort(D[i,:])[k] (1-based k, the zero self-distance
+ * counts, as in the reference), cum_out[i] = sum(sort(D[i,:])[1:K]).  Either output may be NULL. */
+int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double* kth_out, double* cum_out);
+int mcbb_knn_dist_dense_dev(const double* D_dev, int64_t n, int32_t k, int32_t K, double* kth_dev,
+                            double* cum_dev, void* stream);
+
 /* ---- rank-sharded DBSCAN stages (one process per GPU; the collectives stay with the caller) --------------
  * The pair space shards by point rows; rank r owns rows [row0,row1).  All pointers are device pointers.
  *   1  mcbb_dbscan_rows_count_dev    neighbour counts (self included) of the owned rows against all n columns

@@ -17,7 +17,7 @@ EXPORTS = [
     "mcbb_distance_matrix", "mcbb_distance_matrix_dev", "mcbb_dbscan_dense", "mcbb_dbscan_dense_dev",
     "mcbb_dbscan_features", "mcbb_dbscan_features_dev", "mcbb_dbscan_rows_count_dev",
     "mcbb_dbscan_rows_union_dev", "mcbb_dbscan_merge_parents_dev", "mcbb_dbscan_rows_border_dev",
-    "mcbb_dbscan_labels_dev", "mcbb_gather_columns_dev", "mcbb_measure_fp64_fma_peak",
+    "mcbb_dbscan_labels_dev", "mcbb_gather_columns_dev", "mcbb_measure_fp64_fma_peak", "mcbb_knn_dist_dense", "mcbb_knn_dist_dense_dev",
 ]
 
 _lib = None
@@ -63,6 +63,8 @@ def lib():
                                               ip, dp, C.c_double, vp, vp]
     L.mcbb_dbscan_labels_dev.argtypes = [vp, C.c_int64, vp, vp, vp, lp, vp]
     L.mcbb_measure_fp64_fma_peak.argtypes = [dp, dp]
+    L.mcbb_knn_dist_dense.argtypes = [dp, C.c_int64, C.c_int32, C.c_int32, dp, dp]
+    L.mcbb_knn_dist_dense_dev.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp]
     L.mcbb_gather_columns_dev.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp]
     _lib = L
     return L

@@ -297,8 +297,10 @@ class DEMCBBProblem:
         self.par_var = (name, values)
         self.par_names = [name]
         n_dim = pars.n_dim() if not np.iscomplexobj(p.u0) else len(p.u0)
+        self.ic_gens = None
         if callable(ic) or (isinstance(ic, (list, tuple)) and len(ic) > 0 and callable(ic[0])):
             gens = [ic] if callable(ic) else list(ic)
+            self.ic_gens = gens
             if N_ic is None:
                 raise MCBBError("random initial conditions need N_ic")
             ics = self._draw_ics(gens, N_ic, n_dim)
@@ -322,6 +324,15 @@ class DEMCBBProblem:
         if self.N_mc == 0:
             raise MCBBError("Zero inital conditions. Either at least one of the ranges has length 0 or an "
                             "overflow occured")
+
+    def redraw(self, idx):
+        """A sub-problem over runs `idx` with freshly drawn initial conditions (failure_handling=:Repeat)."""
+        import copy
+        sub = copy.copy(self)
+        sub.ic = np.asfortranarray(self._draw_ics(self.ic_gens, len(idx), self.ic.shape[1]))
+        sub.par = np.asfortranarray(self.par[idx])
+        sub.N_mc = len(idx)
+        return sub
 
     @staticmethod
     def _draw_ics(gens, N_ic, n_dim):
@@ -469,6 +480,28 @@ def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, 
     if custom_solve is None:
         custom_solve = custom_solve_b200
     feat, mat, glob, ret, nsteps = custom_solve(prob, t_save, alg=alg, **kwargs)
+    if prob.eval_ode_func.failure_handling == "Repeat":
+        # eval_ode_run returns ((), true) for a failed run and the ensemble loop redraws its initial condition,
+        # at most 10 times (eval_mc_prob.jl:120-123, setup_mc_prob.jl:790-813)
+        for rep in range(10):
+            bad = np.nonzero(ret != abi.RET_SUCCESS)[0]
+            if len(bad) == 0:
+                break
+            if prob.ic_gens is None:
+                raise MCBBError("Integration failed and repeated with new IC, but the IC are not random, so the "
+                                "result will not change")
+            sub = prob.redraw(bad)
+            f2, m2, g2, r2, n2 = custom_solve(sub, t_save, alg=alg, **kwargs)
+            prob.ic[bad] = sub.ic
+            feat[bad], ret[bad], nsteps[bad] = f2, r2, n2
+            if mat is not None:
+                mat[bad] = m2
+            if glob is not None:
+                glob[bad] = g2
+        else:
+            if np.any(ret != abi.RET_SUCCESS):
+                raise MCBBError("More than 10 Repeats of a Problem in the Monte Carlo Run, there might me something "
+                                "wrong here!")
     sol = DEMCBBSol(feat, mat, glob, ret, nsteps, N_t, custom_solve)
     if flag_check_inf_nan:
         inf_nan = check_inf_nan(sol)
@@ -702,3 +735,37 @@ def cluster_membership(prob, clusters, window_size, window_offset, normalize=Tru
         keep += [i + 1 for i in range(n_cluster - 1) if clusters.counts[i] > min_members]
         data = data[:, keep]
     return ClusterMembershipResult(mins, data, False)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# eps-selection helpers (src/eval_clustering.jl:1504-1553)
+# ------------------------------------------------------------------------------------------------------------
+def _knn(D, k, K):
+    data = D.data if isinstance(D, DistanceMatrix) else D
+    data = np.asfortranarray(data, dtype=np.float64)
+    n = data.shape[0]
+    if data.shape[1] != n:
+        raise MCBBError("k_dist: Input Matrix has to be a square matrix")
+    kth = np.zeros(n)
+    cum = np.zeros(n)
+    check(lib().mcbb_knn_dist_dense(data.ctypes.data_as(abi.c_double_p), n, int(k), int(K),
+                                    kth.ctypes.data_as(abi.c_double_p), cum.ctypes.data_as(abi.c_double_p)))
+    return kth, cum
+
+
+def k_dist(D, k=4):
+    """k_dist(D, k): distance to the k-th nearest neighbour of every point, sorted descending (:1504-1516)."""
+    kth, _ = _knn(D, k, 1)
+    return np.sort(kth)[::-1]
+
+
+def KNN_dist(D, K):
+    """KNN_dist(D, K): cumulative distance to the K nearest neighbours, N x 1 like sum(k_d, dims=2) (:1536-1553)."""
+    _, cum = _knn(D, 1, K)
+    return cum[:, None]
+
+
+def KNN_dist_relative(D, rel_K=0.005):
+    """KNN_dist_relative(D, rel_K): K = round(N * rel_K) (:1526-1530)."""
+    n = (D.data if isinstance(D, DistanceMatrix) else np.asarray(D)).shape[0]
+    return KNN_dist(D, int(round(n * rel_K)))

@@ -85,6 +85,7 @@ int labels_dev(const int* root_label, long long n, long long* assignments, long 
                long long* n_clusters_host, cudaStream_t st);
 int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
                        cudaStream_t st);
+int knn_dist_dense_dev(const double* D, long long n, int k, int K, double* kth, double* cum, cudaStream_t st);
 
 
 // Julia Base (:)(start, step, stop) for Float64 (base/twiceprecision.jl): length and elements.  First the
@@ -279,6 +280,7 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
     std::vector<int> filter_host;
     if (int rc = resolve_feat(sys, feat, &F, &filter_host)) return rc;
     if (F.n_global > 0 && !global_dev) MCBB_FAIL("solve: global measures requested but global_out is NULL");
+    if (F.matrix_meas != MCBB_MAT_NONE && !matrix_dev) MCBB_FAIL("solve: a matrix measure is requested but matrix_out is NULL");
     if (!filter_host.empty()) {
         int* fd = (int*)scratch_get(5, sizeof(int) * filter_host.size());
         if (!fd) MCBB_FAIL("solve: device allocation failed");
@@ -327,6 +329,10 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
     double* d_ts = (double*)scratch_get(32, b_ts);
     double* d_feat = (double*)scratch_get(33, b_feat);
     double* d_glob = (double*)scratch_get(34, b_glob);
+    const int nbins = feat->corr_nbins > 0 ? feat->corr_nbins : 30;
+    const size_t b_mat = sizeof(double) * (size_t)n_mc * nbins;
+    double* d_mat = (double*)scratch_get(37, b_mat);
+    if (!d_mat) MCBB_FAIL("solve: device allocation failed");
     int* d_ret = (int*)scratch_get(35, sizeof(int) * (size_t)n_mc);
     long long* d_ns = (long long*)scratch_get(36, sizeof(long long) * 2 * (size_t)n_mc);
     if (!d_ic || !d_par || !d_ts || !d_feat || !d_glob || !d_ret || !d_ns) MCBB_FAIL("solve: device allocation failed");
@@ -337,7 +343,8 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
         MCBB_CUDA_OK(cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, st));
     }
     MCBB_CUDA_OK(cudaMemcpyAsync(d_ts, t_save, b_ts, cudaMemcpyHostToDevice, st));
-    if (int rc = mcbb_solve_features_dev(sys, opts, feat, n_mc, d_ic, d_par, d_ts, n_t, d_feat, nullptr,
+    if (int rc = mcbb_solve_features_dev(sys, opts, feat, n_mc, d_ic, d_par, d_ts, n_t, d_feat,
+                                         feat->matrix_meas != MCBB_MAT_NONE ? d_mat : nullptr,
                                          feat->n_global > 0 ? d_glob : nullptr, d_ret, (int64_t*)d_ns, (void*)st))
         return rc;
     MCBB_CUDA_OK(cudaMemcpyAsync(feat_out, d_feat, b_feat, cudaMemcpyDeviceToHost, st));
@@ -346,7 +353,8 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
     if (retcode_out) MCBB_CUDA_OK(cudaMemcpyAsync(retcode_out, d_ret, sizeof(int) * (size_t)n_mc, cudaMemcpyDeviceToHost, st));
     if (nsteps_out)
         MCBB_CUDA_OK(cudaMemcpyAsync(nsteps_out, d_ns, sizeof(long long) * 2 * (size_t)n_mc, cudaMemcpyDeviceToHost, st));
-    (void)matrix_out;
+    if (matrix_out && feat->matrix_meas != MCBB_MAT_NONE)
+        MCBB_CUDA_OK(cudaMemcpyAsync(matrix_out, d_mat, b_mat, cudaMemcpyDeviceToHost, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -477,6 +485,27 @@ int mcbb_gather_columns_dev(const double* X_dev, int64_t ld, const int32_t* idx_
                             double* Xout_dev, void* stream) {
     if (m > 0 && (!X_dev || !idx_dev || !Xout_dev)) MCBB_FAIL("gather: NULL argument");
     return gather_columns_dev(X_dev, ld, idx_dev, m, F, Xout_dev, (cudaStream_t)stream);
+}
+
+int mcbb_knn_dist_dense_dev(const double* D_dev, int64_t n, int32_t k, int32_t K, double* kth_dev, double* cum_dev,
+                            void* stream) {
+    if (!D_dev || (!kth_dev && !cum_dev)) MCBB_FAIL("k_dist: NULL argument");
+    return knn_dist_dense_dev(D_dev, n, k, K, kth_dev, cum_dev, (cudaStream_t)stream);
+}
+int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double* kth_out, double* cum_out) {
+    if (!D || (!kth_out && !cum_out)) MCBB_FAIL("k_dist: NULL argument");
+    if (n < 1) MCBB_FAIL("k_dist: empty matrix");
+    double* d_D = (double*)scratch_get(41, sizeof(double) * (size_t)n * (size_t)n);
+    double* d_k = (double*)scratch_get(48, sizeof(double) * (size_t)n);
+    double* d_c = (double*)scratch_get(49, sizeof(double) * (size_t)n);
+    if (!d_D || !d_k || !d_c) MCBB_FAIL("k_dist: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_D, D, sizeof(double) * (size_t)n * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (int rc = knn_dist_dense_dev(d_D, n, k, K, kth_out ? d_k : nullptr, cum_out ? d_c : nullptr, st)) return rc;
+    if (kth_out) MCBB_CUDA_OK(cudaMemcpyAsync(kth_out, d_k, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (cum_out) MCBB_CUDA_OK(cudaMemcpyAsync(cum_out, d_c, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 }  // extern "C"

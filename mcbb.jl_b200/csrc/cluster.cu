@@ -9,6 +9,7 @@
 //   final   clusters numbered by ascending seed (exclusive scan over "is seed"), counts by histogram
 // which yields bit-identical (seeds, assignments, counts) for visit order 1:n.
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 #include <limits.h>
 
@@ -512,6 +513,47 @@ int gather_columns_dev(const double* X, long long ld, const int* idx, long long 
                        cudaStream_t st) {
     if (m <= 0 || F <= 0) return 0;
     k_gather_cols<<<dim3(nblk(m), F), 256, 0, st>>>(X, ld, idx, m, F, Xout);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
+// ---- k_dist / KNN_dist (src/eval_clustering.jl:1504-1553): every row of D sorted ascending -----------------------
+__global__ void k_row_offsets(long long* off, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) off[i] = i * n;
+}
+// kth[i] = sorted_row_i[k-1];  cum[i] = sum of the K smallest entries of row i (the zero self-distance included,
+// exactly like `sort(D[i,:])[1:K]` in the reference)
+__global__ void k_knn_pick(const double* sorted, long long n, int k, int K, double* kth, double* cum) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double* row = sorted + i * n;
+        if (kth) kth[i] = row[k - 1];
+        if (cum) {
+            double s = 0.;
+            for (int q = 0; q < K; q++) s += row[q];
+            cum[i] = s;
+        }
+    }
+}
+
+int knn_dist_dense_dev(const double* D, long long n, int k, int K, double* kth, double* cum, cudaStream_t st) {
+    if (n < 1) MCBB_FAIL("k_dist: empty matrix");
+    if ((kth && (k < 1 || k > n)) || (cum && (K < 1 || K > n))) MCBB_FAIL("k_dist: k out of range");
+    if (n > 46000) MCBB_FAIL("k_dist: n too large for a materialised sort");
+    double* sorted = (double*)scratch_get(45, sizeof(double) * (size_t)n * (size_t)n);
+    long long* off = (long long*)scratch_get(46, sizeof(long long) * (size_t)(n + 1));
+    if (!sorted || !off) MCBB_FAIL("k_dist: device scratch allocation failed");
+    k_row_offsets<<<nblk(n + 1), 256, 0, st>>>(off, n);
+    MCBB_LAUNCHED();
+    size_t tb = 0;
+    // D is symmetric: row i == column i, contiguous in the column-major layout
+    cub::DeviceSegmentedSort::SortKeys(nullptr, tb, D, sorted, (int)(n * n), (int)n, off, off + 1, st);
+    void* tmp = scratch_get(47, tb);
+    if (!tmp) MCBB_FAIL("k_dist: device scratch allocation failed");
+    MCBB_CUDA_OK(cub::DeviceSegmentedSort::SortKeys(tmp, tb, D, sorted, (int)(n * n), (int)n, off, off + 1, st));
+    g_launch_count.fetch_add(1);
+    k_knn_pick<<<nblk(n), 256, 0, st>>>(sorted, n, k, K, kth, cum);
     MCBB_LAUNCHED();
     return 0;
 }

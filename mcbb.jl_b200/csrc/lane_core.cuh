@@ -82,7 +82,8 @@ MCBB_HD double nonfinite_mean(const double mean, const double x) {
 }
 
 // accumulator slots per channel
-enum { ACC_MEAN = 0, ACC_M2 = 1, ACC_SUBTR = 2, ACC_START = 3, ACC_BW = 4, ACC_NC = 5, ACC_SLOTS_KL = 6, ACC_SLOTS = 3 };
+enum { ACC_MEAN = 0, ACC_M2 = 1, ACC_SUBTR = 2, ACC_START = 3, ACC_BW = 4, ACC_NC = 5, ACC_SLOTS_KL = 6, ACC_SLOTS = 3,
+       ACC_DELTA = 6, ACC_RESID = 7, ACC_SLOTS_CORR = 8 };
 enum { SLOT_U = 0, SLOT_K1 = 1, SLOT_TMP = 8, SLOT_SCR = 9 };
 enum { MODE_FETCH = 0, MODE_INIT = 1, MODE_RUN = 2, MODE_DONE = 3 };
 
@@ -93,8 +94,8 @@ struct LaneShared {  // CTA-wide read-only data staged in shared memory
 
 template <int SYS, class WorkQ>
 MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io,
-                       const LaneShared& L, double* st, double* acc, unsigned short* bins, const int bs,
-                       WorkQ& wq) {
+                       const LaneShared& L, double* st, double* acc, unsigned short* bins, double* como,
+                       const int bs, WorkQ& wq) {
     const int n = S.n_dim;
     const int n_ch = F.n_ch;
     const int nb = F.kl_bins;
@@ -108,6 +109,8 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
 #define X(slot, d) st[((size_t)(slot)*n + (d)) * bs]
 #define A(slot, ch) acc[((size_t)(slot)*n_ch + (ch)) * bs]
 #define B(ch, b) bins[((size_t)(ch)*nb + (b)) * bs]
+#define CM(p) como[(size_t)(p)*bs]  /* co-moments of channel pairs (i > j), p = i(i-1)/2 + j */
+    const bool corr = F.matrix_meas == MCBB_MAT_CORR_ECDF;
 
     int mode = MODE_FETCH;
     long long run = -1;
@@ -189,6 +192,8 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                 A(ACC_M2, ch) = 0.;
                 A(ACC_SUBTR, ch) = 0.;
             }
+            if (corr)
+                for (int p = 0; p < n_ch * (n_ch - 1) / 2; p++) CM(p) = 0.;
             if (alg == MCBB_ALG_FUNCTIONMAP) {
                 mode = MODE_RUN;
                 if (!begin_attempt()) mode = MODE_FETCH;  // only maxiters < 1
@@ -252,9 +257,17 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                         const double mnew = fma(delta, rk, mean);
                         A(ACC_MEAN, ch) = mnew;
                         A(ACC_M2, ch) = fma(delta, x - mnew, A(ACC_M2, ch));
+                        if (corr) {
+                            A(ACC_DELTA, ch) = delta;
+                            A(ACC_RESID, ch) = x - mnew;
+                        }
                     } else {  // Inf / NaN samples: keep sum(x)/n and sum((x-m)^2) semantics of the reference
                         A(ACC_MEAN, ch) = nonfinite_mean(mean, x);
                         A(ACC_M2, ch) = NaN;
+                        if (corr) {
+                            A(ACC_DELTA, ch) = NaN;
+                            A(ACC_RESID, ch) = NaN;
+                        }
                     }
                 } else {  // fit(Histogram, u, edges; closed=:left): searchsortedlast on the edge VECTOR
                     const int nc = (int)A(ACC_NC, ch);
@@ -275,6 +288,13 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                     }
                 }
             }
+            if (corr && pass == 0) {  // online co-moments: C_ij += (x_i - mean_i_old)(x_j - mean_j_new)
+                int p = 0;
+                for (int i = 1; i < n_ch; i++) {
+                    const double di = A(ACC_DELTA, i);
+                    for (int j = 0; j < i; j++, p++) CM(p) = fma(di, A(ACC_RESID, j), CM(p));
+                }
+            }
         }
         isave++;
     };
@@ -284,6 +304,8 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
             for (int ii = 0; ii < F.n_filter; ii++) io.feat[((long long)m * F.n_filter + ii) * io.n_mc + run] = NaN;
         for (int g = 0; g < F.n_global; g++)
             if (io.glob) io.glob[(long long)g * io.n_mc + run] = NaN;
+        if (corr && io.matrix)
+            for (int b = 0; b < F.corr_nbins; b++) io.matrix[(long long)b * io.n_mc + run] = NaN;
     };
 
     auto end_pass = [&]() {
@@ -292,6 +314,30 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
             if (!ok) {
                 write_nan_features();
             } else {
+                if (corr && io.matrix) {  // correlation_ecdf, eval_mc_prob.jl:462-488
+                    const int nbn = F.corr_nbins;
+                    int h[64];
+                    for (int b = 0; b < nbn; b++) h[b] = 0;
+                    const double step = 1. / (double)nbn;
+                    int p = 0;
+                    for (int i = 1; i < n_ch; i++)
+                        for (int j = 0; j < i; j++, p++) {
+                            double c = CM(p) / (sqrt(A(ACC_M2, i)) * sqrt(A(ACC_M2, j)));
+                            c = fabs(fmin(1., fmax(-1., c)));  // clampcor, then abs
+                            if (c != c) continue;              // zero-variance dimension: dropped
+                            double f = c / step + 1.;          // Base.searchsortedlast on the range 0:1/nbins:1
+                            f = fmin(fmax(f, 1.), (double)(nbn + 1));
+                            const int n0 = (int)rint(f);
+                            const int idx = (c < (double)(n0 - 1) / (double)nbn) ? n0 - 1 : n0;
+                            if (idx >= 1 && idx <= nbn) h[idx - 1] += 2;  // (i,j) and (j,i); the diagonal (1.0) is dropped
+                        }
+                    double cum = 0., tot = 0.;
+                    for (int b = 0; b < nbn; b++) tot += (double)h[b];
+                    for (int b = 0; b < nbn; b++) {  // ecdf_hist, eval_clustering.jl:759-762
+                        cum += (double)h[b];
+                        io.matrix[(long long)b * io.n_mc + run] = cum / tot;
+                    }
+                }
                 for (int ch = 0; ch < n_ch; ch++)  // std(u; mean, corrected=true)
                     {
                     const double m2 = A(ACC_M2, ch);  // fmax would swallow a NaN
@@ -517,6 +563,7 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
 #undef X
 #undef A
 #undef B
+#undef CM
 }
 
 }  // namespace mcbb

@@ -13,7 +13,7 @@ struct DevWorkQ {
 };
 
 struct LaneLayout {  // byte offsets into dynamic shared memory
-    int off_tsave, off_tabs[5], off_state, off_acc, off_bins;
+    int off_tsave, off_tabs[5], off_state, off_acc, off_bins, off_como;
     int stage_tabs;
     int n_slots, n_acc;
 };
@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(128) k_solve_lane(const SysDev S, const Solver
     double* st = (double*)(smem + lay.off_state) + tid;
     double* acc = (double*)(smem + lay.off_acc) + tid;
     unsigned short* bins = (unsigned short*)(smem + lay.off_bins) + tid;
+    double* como = (double*)(smem + lay.off_como) + tid;
     DevWorkQ wq{io.work_counter};
-    lane_main<SYS>(S, o, F, io, L, st, acc, bins, bs, wq);
+    lane_main<SYS>(S, o, F, io, L, st, acc, bins, como, bs, wq);
 }
 
 SolverDev resolve_solver(const mcbb_solver_opts* o) {
@@ -175,7 +176,11 @@ int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* 
     F.cyclic = f->cyclic_setback != 0;
     F.matrix_meas = f->matrix_meas;
     F.corr_nbins = f->corr_nbins > 0 ? f->corr_nbins : 30;
-    if (F.matrix_meas != MCBB_MAT_NONE) MCBB_FAIL("matrix measures (correlation_ecdf) are not implemented on the device yet");
+    if (F.matrix_meas != MCBB_MAT_NONE && F.matrix_meas != MCBB_MAT_CORR_ECDF) MCBB_FAIL("unknown matrix measure id");
+    if (F.matrix_meas == MCBB_MAT_CORR_ECDF) {
+        if (cplx) MCBB_FAIL("correlation_ecdf of complex states is not implemented on the device yet");
+        if (F.corr_nbins > 64) MCBB_FAIL("correlation_ecdf: at most 64 bins");
+    }
     F.n_global = f->n_global;
     if (F.n_global < 0 || F.n_global > MCBB_MAX_GLOBAL) MCBB_FAIL("n_global out of range");
     for (int g = 0; g < F.n_global; g++) {
@@ -196,11 +201,13 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
     const int n = S.n_dim;
     LaneLayout lay = {};
     lay.n_slots = 9 + n_scratch_for(SYS);
-    lay.n_acc = F.need_kl ? ACC_SLOTS_KL : ACC_SLOTS;
+    const bool corr = F.matrix_meas == MCBB_MAT_CORR_ECDF;
+    const int n_pairs = corr ? F.n_ch * (F.n_ch - 1) / 2 : 0;
+    lay.n_acc = corr ? ACC_SLOTS_CORR : (F.need_kl ? ACC_SLOTS_KL : ACC_SLOTS);
     const int lens[5] = {S.len_mat_a, S.len_mat_b, S.len_vec_a, S.len_vec_b, S.len_vec_c};
     size_t tab_bytes = 0;
     for (int k = 0; k < 5; k++) tab_bytes += sizeof(double) * (size_t)lens[k];
-    const size_t per_lane = sizeof(double) * ((size_t)lay.n_slots * n + (size_t)lay.n_acc * F.n_ch) +
+    const size_t per_lane = sizeof(double) * ((size_t)lay.n_slots * n + (size_t)lay.n_acc * F.n_ch + (size_t)n_pairs) +
                             (F.need_kl ? sizeof(unsigned short) * (size_t)F.n_ch * F.kl_bins : 0);
     const size_t fixed = sizeof(double) * (size_t)io.n_t + 64;
     const size_t cap = 227 * 1024;
@@ -229,6 +236,8 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
     off += sizeof(double) * (size_t)lay.n_slots * n * bs;
     lay.off_acc = (int)off;
     off += sizeof(double) * (size_t)lay.n_acc * F.n_ch * bs;
+    lay.off_como = (int)off;
+    off += sizeof(double) * (size_t)n_pairs * bs;
     lay.off_bins = (int)off;
     off += F.need_kl ? sizeof(unsigned short) * (size_t)F.n_ch * F.kl_bins * bs : 0;
     const size_t smem = off;

@@ -20,18 +20,20 @@ struct HostWorkQ {
 template <int SYS>
 static void run_host(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io) {
     const int n = S.n_dim;
-    std::vector<double> st((size_t)(9 + SysTraits<SYS>::n_scratch) * n + 8), acc((size_t)ACC_SLOTS_KL * F.n_ch + 8);
+    std::vector<double> st((size_t)(9 + SysTraits<SYS>::n_scratch) * n + 8), acc((size_t)ACC_SLOTS_CORR * F.n_ch + 8);
+    std::vector<double> como((size_t)F.n_ch * F.n_ch + 8);
     std::vector<unsigned short> bins((size_t)F.n_ch * F.kl_bins + 8);
     LaneShared L;
     L.t_save = io.t_save;
     L.tabs = SysTabs{S.mat_a, S.mat_b, S.vec_a, S.vec_b, S.vec_c};
     HostWorkQ wq;
-    lane_main<SYS>(S, o, F, io, L, st.data(), acc.data(), bins.data(), 1, wq);
+    lane_main<SYS>(S, o, F, io, L, st.data(), acc.data(), bins.data(), como.data(), 1, wq);
 }
 
 extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
                                    int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
-                                   double* feat_out, double* global_out, int32_t* retcode_out, int64_t* nsteps_out) {
+                                   double* feat_out, double* global_out, int32_t* retcode_out, int64_t* nsteps_out,
+                                   double* matrix_out) {
     int len[5];
     if (table_lengths(sys, len)) return 1;
     SysDev S = {};
@@ -48,7 +50,7 @@ extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solve
     std::vector<double> ckpt((size_t)(2 * S.n_dim + 4) * n_mc);
     SolveIO io = {};
     io.n_mc = n_mc; io.ic = ic; io.par = par; io.t_save = t_save; io.n_t = n_t; io.feat = feat_out;
-    io.glob = global_out; io.retcode = retcode_out; io.nsteps = (long long*)nsteps_out; io.ckpt = ckpt.data();
+    io.glob = global_out; io.matrix = matrix_out; io.retcode = retcode_out; io.nsteps = (long long*)nsteps_out; io.ckpt = ckpt.data();
     switch (S.system) {
     case MCBB_SYS_LOGISTIC: run_host<MCBB_SYS_LOGISTIC>(S, o, F, io); break;
     case MCBB_SYS_KURAMOTO: run_host<MCBB_SYS_KURAMOTO>(S, o, F, io); break;

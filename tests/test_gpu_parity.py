@@ -355,3 +355,77 @@ def test_solve_is_deterministic(gpu):
         a = m.solve(build())
         b = m.solve(build())
         assert np.array_equal(a.feat, b.feat, equal_nan=True) and np.array_equal(a.nsteps, b.nsteps)
+
+
+def test_all_measures_correlation_ecdf_and_sum(gpu, orc):
+    """test/ode_prob_example.jl:49-64 `eval_ode_run_all_test`: [mean, std] + correlation_ecdf + global sum, then the
+    distance matrix over per-dim, matrix, global and parameter groups."""
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=60, seed=13, N=5)
+    prob.eval_ode_func = m.EvalOdeRun(eval_funcs=(m.mean, m.std), matrix_eval_funcs=[m.correlation_ecdf],
+                                      global_eval_funcs=["sum"])
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob, reltol=1e-9, abstol=1e-9, flag_check_inf_nan=False)
+    assert (sol.N_meas, sol.N_meas_dim, sol.N_meas_matrix, sol.N_meas_global) == (4, 2, 1, 1)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, reltol=1e-9, abstol=1e-9)
+    cases.compare_features(sol.feat, ref, orc, *ctx)
+    # the ECDF is a step function of the correlations: equal wherever no |cor| sits within rounding of a bin edge
+    # (fully synchronised runs have |cor| == 1 everywhere: every entry falls outside [0,1) and the ECDF is 0/0 = NaN,
+    # in the reference as well)
+    both_nan = np.isnan(sol.matrix) & np.isnan(ref["matrix"])
+    with np.errstate(invalid="ignore"):
+        same = np.all((np.abs(sol.matrix - ref["matrix"]) < 1e-12) | both_nan, axis=1)
+    assert same.mean() >= 0.95, same.mean()
+    ok = ~np.isnan(sol.matrix[:, -1])
+    assert ok.sum() >= 10 and np.allclose(sol.matrix[ok, -1], 1.0) and np.all(np.diff(sol.matrix[ok], axis=1) >= 0)
+    assert np.allclose(sol.glob, ref["glob"], rtol=1e-8)
+    weights = [1.0, 0.5, 0.5, 0.25, 1.0]
+    D = m.distance_matrix(sol, prob, weights)
+    X, gl, gw = m.feature_groups(sol, prob, weights)
+    assert list(gl) == [5, 5, 30, 1, 1]
+    assert np.allclose(D.data, orc.distance_matrix(X, gl, gw), rtol=1e-12, atol=1e-13, equal_nan=True)
+
+
+def test_k_dist_and_knn_helpers(gpu):
+    """k_dist / KNN_dist / KNN_dist_relative (eval_clustering.jl:1504-1553) against numpy on the same matrix."""
+    m = gpu
+    rng = np.random.default_rng(3)
+    pts = rng.normal(size=(700, 3))
+    D = np.abs(pts[:, None, :] - pts[None, :, :]).sum(-1)
+    Ds = np.sort(D, axis=1)
+    assert np.array_equal(m.k_dist(D, 4), np.sort(Ds[:, 3])[::-1])
+    assert np.allclose(m.KNN_dist(D, 7)[:, 0], Ds[:, :7].sum(1), rtol=1e-14)
+    K = int(round(700 * 0.005))
+    assert np.allclose(m.KNN_dist_relative(D)[:, 0], Ds[:, :K].sum(1), rtol=1e-14)
+    with pytest.raises(m.MCBBError, match="k out of range"):
+        m.k_dist(D, 0)
+
+
+def test_failure_handling_repeat_and_inf(gpu):
+    """failure_handling = :Repeat redraws the ICs of failed runs, at most 10 times (eval_mc_prob.jl:120-123,
+    setup_mc_prob.jl:790-813); :Inf fills the measures of DtLessThanMin / Unstable runs with Inf (:97-119)."""
+    m = gpu
+    # one K value: the number of step attempts then depends on the initial condition only, so a redraw can succeed
+    mk = lambda: cases.c1_problem(m, n_ics=200, seed=21, ks=(2.0,), eval_funcs=(m.mean, m.std))[0]
+    prob = mk()
+    base = m.solve(prob, sort_results=False)
+    limit = int(np.percentile(base.nsteps[:, 0], 80))  # ~20 % of the runs exceed this many step attempts
+    prob = mk()
+    plain = m.solve(prob, maxiters=limit, sort_results=False, flag_check_inf_nan=False)
+    failed = plain.retcode == m.abi.RET_MAXITERS
+    assert 0.02 < failed.mean() < 0.5 and np.isnan(plain.feat[failed]).all()
+    prob = mk()
+    prob.eval_ode_func = m.EvalOdeRun(eval_funcs=(m.mean, m.std), failure_handling="Repeat")
+    ic_before = prob.ic.copy()
+    sol = m.solve(prob, maxiters=limit, sort_results=False)
+    assert np.all(sol.retcode == m.abi.RET_SUCCESS) and np.all(np.isfinite(sol.feat))
+    changed = np.any(prob.ic != ic_before, axis=1)
+    assert np.array_equal(changed, failed)  # exactly the failed runs got new initial conditions
+    # non-random ICs cannot be repeated
+    N = 6
+    pars = prob.pars
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), (0.0, 40.0), pars)
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std), failure_handling="Repeat")
+    prob2 = m.DEMCBBProblem(rp, [np.array([0.1, 2.0])] * N, pars, ("K", [1.0, 2.0]), ev, 0.9)
+    with pytest.raises(m.MCBBError, match="IC are not random"):
+        m.solve(prob2, maxiters=5, flag_check_inf_nan=False)
