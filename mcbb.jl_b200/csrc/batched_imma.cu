@@ -91,6 +91,37 @@ __device__ __forceinline__ void store_digits(unsigned char* p, const int slice_s
     p[6 * slice_stride] = (unsigned char)(hi >> 16);
 }
 
+// Physical byte offset of logical K index k inside a digit column.  Two k-steps (64 K values) form a 64-byte
+// block in which lane t of a fragment load finds its 16 bytes contiguous: [b0(ks), b1(ks), b0(ks+1), b1(ks+1)],
+// so one LDS.128 feeds two IMMAs.  Groups of four consecutive k stay contiguous (word stores).
+__host__ __device__ __forceinline__ int dig_phys(const int k) {
+    const int blk = k >> 6, kk = k & 63;
+    return blk * 64 + ((kk & 15) >> 2) * 16 + (kk >> 5) * 8 + ((kk >> 4) & 1) * 4 + (kk & 3);
+}
+
+// Fixed-point digits of four values (consecutive oscillators, one trajectory) as seven 32-bit words, one per
+// byte slice: word[sl] = {digit_sl(x0), digit_sl(x1), digit_sl(x2), digit_sl(x3)}  (4 x 4 byte transposes, PRMT)
+__device__ __forceinline__ void digit_words(const double (&x)[4], unsigned (&w)[7]) {
+    unsigned lo[4], hi[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const double t = fma(x[q], 1125899906842624.0 /* 2^50 */, 6755399441055744.0 /* 1.5 * 2^52 */);
+        lo[q] = (unsigned)__double2loint(t);
+        hi[q] = (unsigned)__double2hiint(t) & 0xFFFFFu;
+    }
+    const unsigned a0 = __byte_perm(lo[0], lo[1], 0x5140), a1 = __byte_perm(lo[2], lo[3], 0x5140);
+    const unsigned a2 = __byte_perm(lo[0], lo[1], 0x7362), a3 = __byte_perm(lo[2], lo[3], 0x7362);
+    w[0] = __byte_perm(a0, a1, 0x5410);
+    w[1] = __byte_perm(a0, a1, 0x7632);
+    w[2] = __byte_perm(a2, a3, 0x5410);
+    w[3] = __byte_perm(a2, a3, 0x7632);
+    const unsigned c0 = __byte_perm(hi[0], hi[1], 0x5140), c1 = __byte_perm(hi[2], hi[3], 0x5140);
+    const unsigned c2 = __byte_perm(hi[0], hi[1], 0x7362), c3 = __byte_perm(hi[2], hi[3], 0x7362);
+    w[4] = __byte_perm(c0, c1, 0x5410);
+    w[5] = __byte_perm(c0, c1, 0x7632);
+    w[6] = __byte_perm(c2, c3, 0x5410);
+}
+
 __device__ __forceinline__ void mma_s8u8(int (&c)[4], const unsigned (&a)[4], const unsigned b0, const unsigned b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -98,7 +129,7 @@ __device__ __forceinline__ void mma_s8u8(int (&c)[4], const unsigned (&a)[4], co
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Shared-memory panels are indexed by (oscillator row, trajectory b): idx = row * B + b.  A warp's 64-bit
+// Shared-memory panels are indexed by (oscillator row, trajectory b): idx = row * BP + b.  A warp's 64-bit
 // accesses split into half-warps of rows g = 0..3 / 4..7; with B = 20 the row stride is 40 words, so the four
 // rows of a half-warp land on banks 0, 8, 16, 24 (+2t): conflict-free.
 template <int CT_T, int KS_T>
@@ -112,10 +143,12 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
     const int N = a.N;
     const int CT = CT_T > 0 ? CT_T : (a.B >> 2);
     const int B = 4 * CT;
+    const int BP = B + 2;  // padded row stride of the (oscillator, trajectory) panels: conflict-free quad loads
     const int KSTEPS = KS_T > 0 ? KS_T : a.KS;
-    const int kstr = KS_T > 0 ? (KS_T * 32 + 16) : a.kstr;
+    const int KPAIRS = (KSTEPS + 1) >> 1;
+    const int kstr = (KPAIRS * 64) % 128 == 0 ? KPAIRS * 64 + 64 : KPAIRS * 64;  // == 64 (mod 128): LDS.128 conflict-free
     const int slice_stride = 2 * B * kstr;
-    const int pstride = N * B;                                      // one panel
+    const int pstride = N * BP;                                     // one panel
     double* sm_k = (double*)smem;                                   // [8][N][B]  u, k1..k7
     double* sm_sc = sm_k + IM_NSLOT * pstride;              // [2][N][B]  sin, cos of the stage input
     double* sm_red0 = sm_sc + 2 * pstride;                  // [MT][B]
@@ -207,7 +240,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                 for (int h = 0; h < 2; h++) {
                     const int row = h ? row1 : row0;
                     if (row < N) {
-                        const int idx = row * B + b;
+                        const int idx = row * BP + b;
                         KP(0, idx) = a.io.ic[(long long)row * n_mc + run];
 #pragma unroll
                         for (int j = 1; j < IM_NSLOT; j++) KP(j, idx) = 0.;  // no stale NaN from the slot's previous run
@@ -222,41 +255,43 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
         // ---- one round: 6 right-hand-side evaluations of the whole batch -----------------------------------
 #pragma unroll 1
         for (int s = 0; s < 6; s++) {
-            // (a) stage input Y -> sin, cos -> fixed-point byte slices (shared digit panels)
+            // (a) stage input Y -> sin, cos -> fixed-point digit words.  Work item = four consecutive oscillators of
+            //     one trajectory: four independent sincos chains in flight, digits leave as 32-bit words.
+            {
+                const int NQ = (N + 3) >> 2;
 #pragma unroll 1
-            for (int ct = part; ct < CT; ct += WS) {
-                const int b = ct * 4 + t4;
-                const int mode = ctl[b].mode;
-                const double hstep = (mode == MODE_RUN) ? ctl[b].dts : ctl[b].dt0;
-                // stage coefficients with zeros beyond the current stage (and k1 only for the initial-dt probe):
-                // six unconditional FMAs per element instead of a data-dependent loop
-                double cf[6];
+                for (int item = tid; item < NQ * B; item += (int)blockDim.x) {
+                    const int rq = item / B, b = item - rq * B;
+                    const int mode = ctl[b].mode;
+                    const double hstep = (mode == MODE_RUN) ? ctl[b].dts : ctl[b].dt0;
+                    // stage coefficients with zeros beyond the current stage (k1 only for the initial-dt probe)
+                    double cf[6];
 #pragma unroll
-                for (int j = 0; j < 6; j++)
-                    cf[j] = (mode == MODE_RUN) ? (j <= s ? TS_A(s, j) : 0.) : ((mode == MODE_INIT && s == 1 && j == 0) ? 1. : 0.);
-                double y[2];
+                    for (int jj = 0; jj < 6; jj++)
+                        cf[jj] = (mode == MODE_RUN) ? (jj <= s ? TS_A(s, jj) : 0.)
+                                                    : ((mode == MODE_INIT && s == 1 && jj == 0) ? 1. : 0.);
+                    double sv[4], cv[4];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int row = h ? row1 : row0;
-                    const int idx = (row < N ? row : 0) * B + b;
-                    double lin = cf[0] * KP(1, idx);
+                    for (int q = 0; q < 4; q++) {
+                        const int row = 4 * rq + q;
+                        const int idx = (row < N ? row : N - 1) * BP + b;
+                        double lin = cf[0] * KP(1, idx);
 #pragma unroll
-                    for (int j = 1; j < 6; j++) lin = fma(cf[j], KP(1 + j, idx), lin);
-                    y[h] = fma(hstep, lin, KP(0, idx));
-                }
-                double sv[2], cv[2];
-                sincos_fast2(y[0], &sv[0], &cv[0]);
-                sincos_fast2(y[1], &sv[1], &cv[1]);
+                        for (int jj = 1; jj < 6; jj++) lin = fma(cf[jj], KP(1 + jj, idx), lin);
+                        sincos_fast2(fma(hstep, lin, KP(0, idx)), &sv[q], &cv[q]);
+                        if (row < N) {
+                            sm_sc[idx] = sv[q];
+                            sm_sc[pstride + idx] = cv[q];
+                        }
+                    }
+                    unsigned ws[7], wc[7];
+                    digit_words(sv, ws);
+                    digit_words(cv, wc);
+                    unsigned char* p = sm_dig + (2 * b) * kstr + dig_phys(4 * rq);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int row = h ? row1 : row0;
-                    if (row < N) {
-                        const int idx = row * B + b;
-                        sm_sc[idx] = sv[h];
-                        sm_sc[pstride + idx] = cv[h];
-                        unsigned char* p = sm_dig + (2 * b) * kstr + row;
-                        store_digits(p, slice_stride, sv[h]);
-                        store_digits(p + kstr, slice_stride, cv[h]);
+                    for (int sl = 0; sl < IM_NSLICE; sl++) {
+                        *reinterpret_cast<unsigned*>(p + sl * slice_stride) = ws[sl];
+                        *reinterpret_cast<unsigned*>(p + sl * slice_stride + kstr) = wc[sl];
                     }
                 }
             }
@@ -269,16 +304,15 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                 for (int sl = 0; sl < IM_NSLICE; sl++)
 #pragma unroll
                     for (int r = 0; r < 4; r++) cacc[sl][r] = 0;
-                const unsigned char* colp = sm_dig + (ct * 8 + g) * kstr + 4 * t4;
+                const unsigned char* colp = sm_dig + (ct * 8 + g) * kstr + 16 * t4;
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    if (ks < KSTEPS) {
+                for (int kp = 0; kp < 2; kp++) {
+                    if (kp < KPAIRS) {
 #pragma unroll
                         for (int sl = 0; sl < IM_NSLICE; sl++) {
-                            const unsigned char* q = colp + sl * slice_stride + ks * 32;
-                            const unsigned b0 = *reinterpret_cast<const unsigned*>(q);
-                            const unsigned b1 = *reinterpret_cast<const unsigned*>(q + 16);
-                            mma_s8u8(cacc[sl], afr[ks], b0, b1);
+                            const uint4 bq = *reinterpret_cast<const uint4*>(colp + sl * slice_stride + kp * 64);
+                            mma_s8u8(cacc[sl], afr[2 * kp], bq.x, bq.y);
+                            if (2 * kp + 1 < KSTEPS) mma_s8u8(cacc[sl], afr[2 * kp + 1], bq.z, bq.w);
                         }
                     }
                 }
@@ -301,7 +335,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                 for (int h = 0; h < 2; h++) {
                     const int row = h ? row1 : row0;
                     if (row < N) {
-                        const int idx = row * B + b;
+                        const int idx = row * BP + b;
                         const long long dg = h ? deg1 : deg0;
                         const double P = (double)(v[2 * h] - dg) * scale;
                         const double Q = (double)(v[2 * h + 1] - dg) * scale;
@@ -373,7 +407,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                 for (int h = 0; h < 2; h++) {
                     const int row = h ? row1 : row0;
                     if (row < N) {
-                        const int idx = row * B + b;
+                        const int idx = row * BP + b;
                         double lin = TS_BT(0) * KP(1, idx);
                         double lu = TS_A(5, 0) * KP(1, idx);
 #pragma unroll
@@ -447,7 +481,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
             if (ks0 < ks1) {
                 // Welford state of the two owned elements: one global (L2) round trip per accepted step, the
                 // per-sample updates stay in registers
-                const int idx0 = (v0 ? row0 : 0) * B + b, idx1 = (v1 ? row1 : 0) * B + b;
+                const int idx0 = (v0 ? row0 : 0) * BP + b, idx1 = (v1 ? row1 : 0) * BP + b;
                 double am[2] = {ACCS(0, idx0), ACCS(0, idx1)};
                 double a2[2] = {ACCS(1, idx0), ACCS(1, idx1)};
                 double as[2] = {ACCS(2, idx0), ACCS(2, idx1)};
@@ -506,7 +540,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
             for (int h = 0; h < 2; h++) {
                 const int row = h ? row1 : row0;
                 if (row >= N) continue;
-                const int idx = row * B + b;
+                const int idx = row * BP + b;
                 double lu = TS_A(5, 0) * KP(1, idx);
 #pragma unroll
                 for (int j = 1; j < 6; j++) lu = fma(TS_A(5, j), KP(1 + j, idx), lu);
@@ -540,7 +574,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
             for (int h = 0; h < 2; h++) {
                 const int row = h ? row1 : row0;
                 if (row >= N) continue;
-                const int idx = row * B + b;
+                const int idx = row * BP + b;
                 const int pos = a.filter_pos[row];
                 if (pos < 0) continue;
                 const double mean = ok ? ACCS(0, idx) : nan("");
@@ -633,7 +667,10 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.N = N;
     a.MT = (N + 15) / 16;
     a.KS = (N + 31) / 32;
-    a.kstr = a.KS * 32 + 16;
+    {
+        const int kpairs = (a.KS + 1) / 2;
+        a.kstr = (kpairs * 64) % 128 == 0 ? kpairs * 64 + 64 : kpairs * 64;
+    }
     a.WS = getenv("MCBB_IMMA_WS") ? atoi(getenv("MCBB_IMMA_WS")) : 2;
     if (a.WS < 1 || a.WS * a.MT * 32 > 512) a.WS = 1;
     a.nthreads = a.MT * a.WS * 32;
@@ -704,7 +741,7 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     size_t smem = 0;
     for (int cand = 8; cand >= 1; cand--) {
         const int B = 4 * cand;
-        const size_t need = sizeof(double) * ((size_t)(IM_NSLOT + 2) * N * B + 2 * (size_t)a.MT * B +
+        const size_t need = sizeof(double) * ((size_t)(IM_NSLOT + 2) * N * (B + 2) + 2 * (size_t)a.MT * B +
                                               (size_t)((io.n_t + 1) & ~1)) +
                             sizeof(ImSlotCtl) * (size_t)B + (size_t)IM_NSLICE * 2 * B * a.kstr + 64;
         if (need <= cap) {
@@ -720,7 +757,7 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long want = (io.n_mc + a.B - 1) / a.B;
     const int grid = (int)std::min<long long>(want, (long long)sms * per_sm);
-    a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * N * a.B);
+    a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * N * (a.B + 2));
     if (!a.acc) MCBB_FAIL("solve: device allocation failed");
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     int rc = launch_imma(a, smem, grid, per_sm, st);

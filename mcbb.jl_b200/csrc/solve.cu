@@ -53,6 +53,27 @@ __global__ void __launch_bounds__(128) k_solve_lane(const SysDev S, const Solver
     lane_main<SYS>(S, o, F, io, L, st, acc, bins, como, bs, wq);
 }
 
+// Large systems (state does not fit shared memory, no batched kernel for the system): same lane state machine,
+// per-lane state vectors in an L2/HBM-resident scratch laid out [slot][dim][lane] (coalesced across lanes).
+// Correct for any size; throughput is bounded by L2/HBM traffic of the stage vectors, not by the FP64 pipe.
+template <int SYS>
+__global__ void __launch_bounds__(128) k_solve_lane_gmem(const SysDev S, const SolverDev o, const FeatDev F,
+                                                         const SolveIO io, double* state, double* accs,
+                                                         unsigned short* bins_g, double* como_g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    double* s_tsave = (double*)smem;
+    for (int i = tid; i < io.n_t; i += blockDim.x) s_tsave[i] = io.t_save[i];
+    __syncthreads();
+    LaneShared L;
+    L.t_save = s_tsave;
+    L.tabs = SysTabs{S.mat_a, S.mat_b, S.vec_a, S.vec_b, S.vec_c};
+    const int lanes = gridDim.x * blockDim.x;
+    const int lane = blockIdx.x * blockDim.x + tid;
+    DevWorkQ wq{io.work_counter};
+    lane_main<SYS>(S, o, F, io, L, state + lane, accs + lane, bins_g + lane, como_g + lane, lanes, wq);
+}
+
 SolverDev resolve_solver(const mcbb_solver_opts* o) {
     SolverDev s;
     s.alg = o->alg;
@@ -220,9 +241,28 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
             break;
         }
     }
-    if (bs == 0)
-        MCBB_FAIL("solve: state dimension too large for the one-trajectory-per-lane kernel (needs " +
-                  std::to_string(per_lane) + " B of shared memory per trajectory)");
+    if (bs == 0) {
+        // state in global memory: at most ~64 MB of stage vectors in flight so that they stay L2-resident
+        int dev = 0, sms = 148;
+        MCBB_CUDA_OK(cudaGetDevice(&dev));
+        MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int block = 64;
+        long long lanes = std::min<long long>((long long)sms * 8 * block, std::max<long long>(block, (64LL << 20) / (long long)per_lane));
+        lanes = std::min<long long>(lanes, (io.n_mc + block - 1) / block * block);
+        lanes = std::max<long long>(block, lanes / block * block);
+        const int grid = (int)(lanes / block);
+        double* state = (double*)scratch_get(8, sizeof(double) * (size_t)lay.n_slots * n * lanes);
+        double* accs = (double*)scratch_get(9, sizeof(double) * (size_t)lay.n_acc * F.n_ch * lanes);
+        unsigned short* bins_g = (unsigned short*)scratch_get(28, sizeof(unsigned short) * (size_t)(F.need_kl ? F.n_ch * F.kl_bins : 1) * lanes);
+        double* como_g = (double*)scratch_get(29, sizeof(double) * (size_t)(n_pairs > 0 ? n_pairs : 1) * lanes);
+        if (!state || !accs || !bins_g || !como_g) MCBB_FAIL("solve: device allocation of the lane state failed");
+        const size_t smem_g = sizeof(double) * (size_t)io.n_t + 16;
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_lane_gmem<SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
+        k_solve_lane_gmem<SYS><<<grid, block, smem_g, st>>>(S, o, F, io, state, accs, bins_g, como_g);
+        MCBB_LAUNCHED();
+        return 0;
+    }
     // prefer two resident CTAs per SM when that costs nothing
     while (bs > 32 && base + per_lane * bs > cap / 2 && base + per_lane * (bs / 2) <= cap / 2) bs /= 2;
     size_t off = 0;

@@ -429,3 +429,32 @@ def test_failure_handling_repeat_and_inf(gpu):
     prob2 = m.DEMCBBProblem(rp, [np.array([0.1, 2.0])] * N, pars, ("K", [1.0, 2.0]), ev, 0.9)
     with pytest.raises(m.MCBBError, match="IC are not random"):
         m.solve(prob2, maxiters=5, flag_check_inf_nan=False)
+
+
+def test_c4_stuart_landau_n100_global_state_path(gpu, orc):
+    """C4's system at its real size: Stuart-Landau ring N=100 (200 real state dimensions; A_1 degree 2, A_2 degree 44),
+    eps swept, measures mean/std/KL of real and imaginary parts.  The state does not fit shared memory, so this runs
+    the lane kernel with L2-resident state."""
+    m = gpu
+    N = 100
+    rng = np.random.default_rng(7)
+
+    def ring_adj(P):
+        A = np.zeros((N, N))
+        for d in range(1, P + 1):
+            A += np.roll(np.eye(N), d, 0) + np.roll(np.eye(N), -d, 0)
+        return A
+    pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.925, N, 1, 22, ring_adj(1), ring_adj(22))
+    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"))
+    rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(N, dtype=complex), (0.0, 20.0), pars)
+    prng = np.random.default_rng(8)
+    prob = m.DEMCBBProblem(rp, lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1)), 48, pars,
+                           ("eps", lambda: prng.uniform(1.8, 2.1)), ev, 0.7)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    kw = dict(reltol=1e-8, abstol=1e-8, maxiters=10 ** 6)
+    sol = m.solve(prob, **kw)
+    assert sol.feat.shape == (48, 100, 6)
+    ic0 = np.stack([ic0.real, ic0.imag], axis=2).reshape(ic0.shape[0], -1)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
+    assert np.array_equal(sol.retcode, ref["retcode"])
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.5)
