@@ -225,8 +225,10 @@ int mcbb_knn_dist_dense_dev(const double* D_dev, int64_t n, int32_t k, int32_t K
  *      -- caller all-gathers, builds root_label[n] (seed index of the point's cluster, -1 = noise)
  *   4  mcbb_dbscan_labels_dev        seeds / assignments / counts from root labels (any rank)          */
 int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
-                               const double* group_weight, double eps, int64_t row0, int64_t row1,
-                               int32_t* count_dev /* row1-row0 */, void* stream);
+                               const double* group_weight, double eps, int32_t minpts, int64_t row0,
+                               int64_t row1, int32_t* count_dev /* row1-row0, exact below minpts and a lower
+                               bound >= minpts above it: counting stops once core-ness is decided */,
+                               void* stream);
 int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups,
                                const int32_t* group_len, const double* group_weight, double eps, int64_t row0,
                                int64_t row1, int32_t* parent_dev /* n_core */, void* stream);

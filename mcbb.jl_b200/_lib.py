@@ -54,8 +54,8 @@ def lib():
     L.mcbb_dbscan_features.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int32, lp, lp, lp, lp]
     L.mcbb_dbscan_features_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int32, vp, vp, vp,
                                            lp, vp]
-    L.mcbb_dbscan_rows_count_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int64, C.c_int64,
-                                             vp, vp]
+    L.mcbb_dbscan_rows_count_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int32, C.c_int64,
+                                             C.c_int64, vp, vp]
     L.mcbb_dbscan_rows_union_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int64, C.c_int64,
                                              vp, vp]
     L.mcbb_dbscan_merge_parents_dev.argtypes = [vp, vp, C.c_int64, vp]

@@ -73,7 +73,7 @@ int dbscan_dense_dev(const double* D, long long n, double eps, int minpts, long 
                      long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st);
 
 int rows_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
-                   double eps, long long row0, long long row1, int* count, cudaStream_t st);
+                   double eps, int minpts, long long row0, long long row1, int* count, cudaStream_t st);
 int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32_t* group_len,
                    const double* group_weight, double eps, long long row0, long long row1, int* parent,
                    cudaStream_t st);
@@ -449,10 +449,10 @@ int mcbb_dbscan_features(const double* X, int64_t n, int32_t n_groups, const int
 }
 
 int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
-                               const double* group_weight, double eps, int64_t row0, int64_t row1,
+                               const double* group_weight, double eps, int32_t minpts, int64_t row0, int64_t row1,
                                int32_t* count_dev, void* stream) {
     if (!X_dev || !count_dev || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
-    return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, row0, row1, count_dev,
+    return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, row0, row1, count_dev,
                           (cudaStream_t)stream);
 }
 int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups, const int32_t* group_len,

@@ -95,6 +95,23 @@ __global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long lon
     if (i < n) p[i] = v;
 }
 
+__global__ void k_flag_below(const int* cnt, long long n, int thr, int* flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = cnt[i] < thr;
+}
+__global__ void k_compact_flagged(const int* flag, const int* pos, long long n, int* idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) idx[pos[i]] = (int)i;
+}
+__global__ void k_gather_i32(const int* src, const int* idx, long long m, int* dst) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) dst[k] = src[idx[k]];
+}
+__global__ void k_scatter_i32(const int* src, const int* idx, long long m, int* dst) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) dst[idx[k]] = src[k];
+}
+
 // ---- dense-D passes (HBM streaming over the n x n matrix, column p = neighbourhood of p) ------------------
 enum DenseMode { DM_COUNT = 0, DM_UNION = 1, DM_BORDER = 2 };
 template <int MODE>
@@ -144,6 +161,34 @@ __global__ void k_labels_dense(const int* core, const int* root, const int* best
 }
 
 // ---- host orchestration ------------------------------------------------------------------------------------
+struct PassTimer {  // MCBB_TRACE=1: per-pass device times on stderr
+    cudaStream_t st;
+    cudaEvent_t e0, e1;
+    bool on;
+    explicit PassTimer(cudaStream_t s) : st(s), on(getenv("MCBB_TRACE") != nullptr) {
+        if (on) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, st);
+        }
+    }
+    void lap(const char* name) {
+        if (!on) return;
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[mcbb trace] %-28s %9.3f ms\n", name, ms);
+        cudaEventRecord(e0, st);
+    }
+    ~PassTimer() {
+        if (on) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+    }
+};
+
 static inline unsigned nblk(long long n, int b = 256) { return (unsigned)((n + b - 1) / b); }
 
 struct GroupTables {
@@ -187,6 +232,8 @@ static int launch_tiles(const TileArgs& a, cudaStream_t st) {
     const long long nr = a.r1 - a.r0, nc = a.c1 - a.c0;
     if (nr <= 0 || nc <= 0) return 0;
     dim3 grid((unsigned)((nc + TILE - 1) / TILE), (unsigned)((nr + TILE - 1) / TILE));
+    if (a.band > 0) grid.x = a.symmetric ? (unsigned)(a.band + 1) : (unsigned)(2 * a.band + 1);
+    if (a.col_mod > 1 && a.col_sel == 1) grid.x = (grid.x + a.col_mod - 1) / a.col_mod;
     if (grid.y > 65535u) MCBB_FAIL("pair tiles: more than 65535 row tiles in one launch; shard the rows");
     k_pair_tiles<MODE><<<grid, 256, 0, st>>>(a);
     MCBB_LAUNCHED();
@@ -206,6 +253,117 @@ static int launch_tiles_rows(TileArgs a, cudaStream_t st) {
     return 0;
 }
 
+
+constexpr int BAND_TILES = 4;
+constexpr int COL_SAMPLE = 32;
+
+// eps-neighbour counts of rows [row0,row1) against all n columns, exact below minpts and >= minpts otherwise.
+// Proving a point NON-core needs its whole row; proving it core needs only minpts hits.  So:
+//   (a) every row against an evenly spread 1/32 sample of the column tiles — dense (core) points saturate here;
+//   (b) the rows still below minpts are compacted and finish against the remaining 31/32 of the column tiles.
+// Work ~ n^2/32 + |unsaturated| n instead of n^2/2; counts add up exactly (disjoint column sets).
+static int count_rows(const double* X, long long n, const GroupTables& gt, double eps, int minpts, long long row0,
+                      long long row1, int* cnt /* row1-row0 */, cudaStream_t st, PassTimer* pt) {
+    const long long m = row1 - row0;
+    if (m <= 0) return 0;
+    k_fill_i32<<<nblk(m), 256, 0, st>>>(cnt, m, 0);
+    MCBB_LAUNCHED();
+    TileArgs a = {};
+    a.Xr = a.Xc = X;
+    a.ldr = a.ldc = n;
+    a.r0 = row0;
+    a.r1 = row1;
+    a.c0 = 0;
+    a.c1 = n;
+    a.F = gt.F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.eps = eps;
+    a.symmetric = 0;  // full rows: the diagonal pair (d = 0 < eps) supplies the self count
+    a.early_exit = gt.early_exit;
+    a.cnt = cnt - row0;
+    a.sat_count = minpts;
+    a.sat_seed = -1;
+    if (n >= (long long)COL_SAMPLE * TILE * 8) {
+        a.col_mod = COL_SAMPLE;
+        a.col_sel = 1;
+        if (int rc = launch_tiles_rows<TM_COUNT>(a, st)) return rc;
+        if (pt) pt->lap("pass 1a sampled columns");
+        int* flag = (int*)scratch_get(13, sizeof(int) * m);
+        int* pos = (int*)scratch_get(15, sizeof(int) * m);
+        int* uidx = (int*)scratch_get(17, sizeof(int) * m);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)m, st);
+        void* tmp = scratch_get(21, tb);
+        if (!flag || !pos || !uidx || !tmp) MCBB_FAIL("dbscan: device scratch allocation failed");
+        k_flag_below<<<nblk(m), 256, 0, st>>>(cnt, m, minpts, flag);
+        MCBB_LAUNCHED();
+        MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, pos, (int)m, st));
+        g_launch_count.fetch_add(1);
+        int h_pos = 0, h_flag = 0;
+        MCBB_CUDA_OK(cudaMemcpyAsync(&h_pos, pos + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        MCBB_CUDA_OK(cudaMemcpyAsync(&h_flag, flag + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));
+        const long long nu = (long long)h_pos + h_flag;
+        if (nu == 0) return 0;
+        k_compact_flagged<<<nblk(m), 256, 0, st>>>(flag, pos, m, uidx);  // indices relative to row0
+        MCBB_LAUNCHED();
+        double* Xu = (double*)scratch_get(24, sizeof(double) * (size_t)gt.F * (size_t)nu);
+        int* cu = (int*)scratch_get(16, sizeof(int) * (size_t)nu);
+        if (!Xu || !cu) MCBB_FAIL("dbscan: device scratch allocation failed");
+        k_gather_cols<<<dim3(nblk(nu), gt.F), 256, 0, st>>>(X + row0, n, uidx, nu, gt.F, Xu);
+        MCBB_LAUNCHED();
+        k_gather_i32<<<nblk(nu), 256, 0, st>>>(cnt, uidx, nu, cu);  // carry the sampled-column counts over
+        MCBB_LAUNCHED();
+        TileArgs b = a;
+        b.Xr = Xu;
+        b.ldr = nu;
+        b.r0 = 0;
+        b.r1 = nu;
+        b.cnt = cu;
+        b.col_sel = 2;
+        if (int rc = launch_tiles_rows<TM_COUNT>(b, st)) return rc;
+        k_scatter_i32<<<nblk(nu), 256, 0, st>>>(cu, uidx, nu, cnt);
+        MCBB_LAUNCHED();
+        if (pt) pt->lap("pass 1b unsaturated rows");
+        return 0;
+    }
+    if (int rc = launch_tiles_rows<TM_COUNT>(a, st)) return rc;
+    if (pt) pt->lap("pass 1 count");
+    return 0;
+}
+
+// union-find over the core-core edges (row in [row0,row1), col > row): band pass first, then the full pass, which
+// skips every tile whose points already share a root
+static int union_rows(const double* Xc, long long n_core, const GroupTables& gt, double eps, long long row0,
+                      long long row1, int* parent, cudaStream_t st, PassTimer* pt) {
+    if (row1 <= row0) return 0;
+    TileArgs u = {};
+    u.Xr = u.Xc = Xc;
+    u.ldr = u.ldc = n_core;
+    u.r0 = row0;
+    u.r1 = row1;
+    u.c0 = 0;
+    u.c1 = n_core;
+    u.F = gt.F;
+    u.fw = gt.fw;
+    u.fend = gt.fend;
+    u.eps = eps;
+    u.symmetric = 1;
+    u.early_exit = gt.early_exit;
+    u.parent = parent;
+    u.sat_union = 1;
+    u.sat_seed = -1;
+    if ((row0 % TILE) == 0 && n_core > (2 * BAND_TILES + 1) * TILE * 4) {
+        u.band = BAND_TILES;
+        if (int rc = launch_tiles_rows<TM_UNION>(u, st)) return rc;
+        u.band = 0;
+    }
+    if (int rc = launch_tiles_rows<TM_UNION>(u, st)) return rc;
+    if (pt) pt->lap("pass 2 union");
+    return 0;
+}
+
 int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
                         const double* group_weight, double* D, cudaStream_t st) {
     GroupTables gt;
@@ -220,6 +378,7 @@ int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_
     a.fend = gt.fend;
     a.symmetric = 1;
     a.D = D;
+    a.sat_seed = -1;
     return launch_tiles_rows<TM_MATERIALIZE>(a, st);
 }
 
@@ -280,21 +439,16 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
         !tmp)
         MCBB_FAIL("dbscan: device scratch allocation failed");
 
-    // pass 1: neighbour counts (self counts: D_pp = 0 < eps)
-    k_fill_i32<<<nblk(n), 256, 0, st>>>(cnt, n, 1);
-    MCBB_LAUNCHED();
+    PassTimer pt(st);
+    // pass 1: neighbour counts (the diagonal pair, D_pp = 0 < eps, supplies the self count)
+    if (int rc = count_rows(X, n, gt, eps, minpts, 0, n, cnt, st, &pt)) return rc;
     TileArgs a = {};
-    a.Xr = a.Xc = X;
-    a.ldr = a.ldc = n;
-    a.r1 = a.c1 = n;
     a.F = F;
     a.fw = gt.fw;
     a.fend = gt.fend;
     a.eps = eps;
-    a.symmetric = 1;
     a.early_exit = gt.early_exit;
-    a.cnt = cnt;
-    if (int rc = launch_tiles_rows<TM_COUNT>(a, st)) return rc;
+    a.sat_seed = -1;
 
     // core flags and stable compaction
     k_core_flags<<<nblk(n), 256, 0, st>>>(cnt, n, minpts, core, noncore);
@@ -323,14 +477,7 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
         // pass 2: components of the core graph
         k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
         MCBB_LAUNCHED();
-        TileArgs u = a;
-        u.Xr = u.Xc = Xc;
-        u.ldr = u.ldc = n_core;
-        u.r0 = u.c0 = 0;
-        u.r1 = u.c1 = n_core;
-        u.cnt = nullptr;
-        u.parent = parent;
-        if (int rc = launch_tiles_rows<TM_UNION>(u, st)) return rc;
+        if (int rc = union_rows(Xc, n_core, gt, eps, 0, n_core, parent, st, &pt)) return rc;
         k_flatten_roots<<<nblk(n_core), 256, 0, st>>>(parent, n_core, core_idx, col_root);
         MCBB_LAUNCHED();
     }
@@ -354,7 +501,14 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
             b.cnt = nullptr;
             b.col_root = col_root;
             b.best = best;
+            {   // the globally smallest seed is the seed of the first core point (seeds are component minima)
+                int h_seed = -1;
+                MCBB_CUDA_OK(cudaMemcpyAsync(&h_seed, col_root, sizeof(int), cudaMemcpyDeviceToHost, st));
+                MCBB_CUDA_OK(cudaStreamSynchronize(st));
+                b.sat_seed = h_seed;
+            }
             if (int rc = launch_tiles_rows<TM_BORDER>(b, st)) return rc;
+            pt.lap("pass 3 border");
         }
     }
     k_root_labels<<<nblk(n), 256, 0, st>>>(n_core, core_idx, col_root, n_non, non_idx, best, root_label, is_seed);
@@ -410,29 +564,13 @@ __global__ void k_seed_flags(const int* root_label, long long n, int* is_seed) {
 }
 
 int rows_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
-                   double eps, long long row0, long long row1, int* count, cudaStream_t st) {
+                   double eps, int minpts, long long row0, long long row1, int* count, cudaStream_t st) {
     if (int rc = check_dbscan_args(n, eps, 1)) return rc;
     if (row0 < 0 || row1 > n || row0 > row1) MCBB_FAIL("dbscan rows: bad row range");
     GroupTables gt;
     if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
-    if (row1 == row0) return 0;
-    k_fill_i32<<<nblk(row1 - row0), 256, 0, st>>>(count, row1 - row0, 0);
-    MCBB_LAUNCHED();
-    TileArgs a = {};
-    a.Xr = a.Xc = X;
-    a.ldr = a.ldc = n;
-    a.r0 = row0;
-    a.r1 = row1;
-    a.c0 = 0;
-    a.c1 = n;
-    a.F = gt.F;
-    a.fw = gt.fw;
-    a.fend = gt.fend;
-    a.eps = eps;
-    a.symmetric = 0;  // full rows: the diagonal pair (d = 0 < eps) supplies the self count
-    a.early_exit = gt.early_exit;
-    a.cnt = count - row0;
-    return launch_tiles_rows<TM_COUNT>(a, st);
+    PassTimer pt(st);
+    return count_rows(X, n, gt, eps, minpts, row0, row1, count, st, &pt);
 }
 
 int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32_t* group_len,
@@ -444,22 +582,8 @@ int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32
     if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
     k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
     MCBB_LAUNCHED();
-    if (row1 == row0) return 0;
-    TileArgs a = {};
-    a.Xr = a.Xc = Xc;
-    a.ldr = a.ldc = n_core;
-    a.r0 = row0;
-    a.r1 = row1;
-    a.c0 = 0;
-    a.c1 = n_core;
-    a.F = gt.F;
-    a.fw = gt.fw;
-    a.fend = gt.fend;
-    a.eps = eps;
-    a.symmetric = 1;
-    a.early_exit = gt.early_exit;
-    a.parent = parent;
-    return launch_tiles_rows<TM_UNION>(a, st);
+    PassTimer pt(st);
+    return union_rows(Xc, n_core, gt, eps, row0, row1, parent, st, &pt);
 }
 
 int merge_parents_dev(int* parent, const int* other, long long n_core, cudaStream_t st) {
@@ -496,6 +620,12 @@ int rows_border_dev(const double* Xn, long long n_non, long long row0, long long
     a.early_exit = gt.early_exit;
     a.col_root = core_seed;
     a.best = best - row0;
+    {
+        int h_seed = -1;  // seed of the first core point = the globally smallest seed
+        MCBB_CUDA_OK(cudaMemcpyAsync(&h_seed, core_seed, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));
+        a.sat_seed = h_seed;
+    }
     return launch_tiles_rows<TM_BORDER>(a, st);
 }
 

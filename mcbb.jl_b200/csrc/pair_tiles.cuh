@@ -45,6 +45,18 @@ struct TileArgs {
     int* parent;     // TM_UNION
     const int* col_root;  // TM_BORDER: root (original index) of each core column
     int* best;            // TM_BORDER: per non-core row, min root seen (init INT_MAX)
+    // Saturation skips (exact: DBSCAN only needs core-ness, connectivity and the smallest adjacent seed, all of
+    // which are monotone).  A tile is skipped before any feature is loaded when nothing in it can still change:
+    int sat_count;        // TM_COUNT: every row (and column, if symmetric) already has >= sat_count neighbours
+    int sat_seed;         // TM_BORDER: every row already holds the globally smallest seed
+    int sat_union;        // TM_UNION: every row and column already shares one root
+    int col_mod, col_sel; // col_mod > 1: column tiles are split by (tile index % col_mod): col_sel 1 = only the
+                          // residue-0 tiles (an evenly spread sample of the columns; blockIdx.x counts sampled tiles),
+                          // col_sel 2 = all the others
+    int band;             // > 0: only column tiles within `band` tiles of the row tile are visited; blockIdx.x is
+                          // the offset (symmetric: 0..band, else -band..band).  Runs are sorted by parameter, so
+                          // index neighbours are the likely distance neighbours: a cheap first pass that saturates
+                          // most points before the exact passes.
 };
 
 __device__ __forceinline__ int uf_find(int* parent, int x) {
@@ -85,10 +97,55 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
     __shared__ unsigned char s_e[FC];
 
     const long long tr = a.r0 + (long long)blockIdx.y * TILE;
-    const long long tc = a.c0 + (long long)blockIdx.x * TILE;
+    long long tc = a.c0 + (long long)blockIdx.x * TILE;
+    if (a.col_mod > 1) {
+        if (a.col_sel == 1) {
+            tc = a.c0 + (long long)blockIdx.x * a.col_mod * TILE;
+            if (tc >= a.c1) return;
+        } else if ((blockIdx.x % a.col_mod) == 0) {
+            return;
+        }
+    }
+    if (a.band > 0) {  // band pass: column tile relative to the row tile (tile grids of rows and columns coincide)
+        tc = tr + ((long long)blockIdx.x - (a.symmetric ? 0 : a.band)) * TILE;
+        if (tc < a.c0 || tc >= a.c1) return;
+    }
     if (a.symmetric && tc + TILE <= tr) return;  // strictly below the diagonal
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;  // tx -> rows (contiguous in memory), ty -> columns
+
+    if (MODE == TM_COUNT && a.sat_count > 0) {
+        bool sat = true;
+        if (tid < TILE) {
+            const long long ri = tr + tid;
+            if (ri < a.r1) sat = __ldcg(a.cnt + ri) >= a.sat_count;
+        } else if (tid < 2 * TILE && a.symmetric) {
+            const long long cj = tc + (tid - TILE);
+            if (cj < a.c1) sat = __ldcg(a.cnt + cj) >= a.sat_count;
+        }
+        if (__syncthreads_and(sat)) return;
+    }
+    if (MODE == TM_UNION && a.sat_union) {
+        __shared__ int s_root0;
+        int root = -1;
+        if (tid < 2 * TILE) {
+            const long long id = (tid < TILE) ? tr + tid : tc + (tid - TILE);
+            const long long lim = (tid < TILE) ? a.r1 : a.c1;
+            if (id < lim) root = uf_find(a.parent, (int)id);
+        }
+        if (tid == 0) s_root0 = root;  // row tr always exists
+        __syncthreads();
+        const bool same = (root < 0) || (root == s_root0);
+        if (__syncthreads_and(same)) return;
+    }
+    if (MODE == TM_BORDER && a.sat_seed >= 0) {
+        bool sat = true;
+        if (tid < TILE) {
+            const long long ri = tr + tid;
+            if (ri < a.r1) sat = __ldcg(a.best + ri) == a.sat_seed;
+        }
+        if (__syncthreads_and(sat)) return;
+    }
 
     double acc[TT][TT], accg[TT][TT];
 #pragma unroll

@@ -100,7 +100,7 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
     dev = X_t.device
     # ---- stage 1: neighbour counts of the owned rows -------------------------------------------------------
     r0, r1 = shard_range(n, rank, world)
-    cnt_local = ops.rows_count(X_t, gl, gw, eps, r0, r1)
+    cnt_local = ops.rows_count(X_t, gl, gw, eps, minpts, r0, r1)
     cnt = _all_gather_rows(cnt_local, shard_sizes(n, world), dist_mod, group)
     core = cnt >= minpts
     core_idx = torch.nonzero(core).flatten().to(torch.int32)  # ascending = stable compaction
@@ -140,12 +140,12 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
 class _CudaStageOps:
     """Stage kernels through the C-ABI (device pointers of torch CUDA tensors)."""
 
-    def rows_count(self, X, gl, gw, eps, r0, r1):
+    def rows_count(self, X, gl, gw, eps, minpts, r0, r1):
         import torch
         out = torch.empty((r1 - r0,), dtype=torch.int32, device=X.device)
         check(lib().mcbb_dbscan_rows_count_dev(_ptr(X), X.shape[1], len(gl), gl.ctypes.data_as(abi.c_int32_p),
-                                               gw.ctypes.data_as(abi.c_double_p), float(eps), r0, r1, _ptr(out),
-                                               _stream()))
+                                               gw.ctypes.data_as(abi.c_double_p), float(eps), int(minpts), r0, r1,
+                                               _ptr(out), _stream()))
         return out
 
     def gather(self, X, idx):

@@ -180,7 +180,7 @@ class _CheckerOps:
             f += g
         return out
 
-    def rows_count(self, X, gl, gw, eps, r0, r1):
+    def rows_count(self, X, gl, gw, eps, minpts, r0, r1):
         Xn = X.numpy()
         return self.torch.from_numpy((self._d(Xn[:, r0:r1], Xn, gl, gw) < eps).sum(1).astype(np.int32))
 
