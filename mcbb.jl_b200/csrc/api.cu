@@ -169,6 +169,26 @@ static int julia_range(double start, double step, double stop, double* out, int 
     return len;
 }
 
+// incidence matrix of second_order_kuramoto by edge, compressed (layout: systems.cuh): the kernels never scan zeros
+void build_edge_csr(const mcbb_system_desc* sys, std::vector<double>* out) {
+    const int N = sys->n_osc, E = sys->n_edges;
+    std::vector<double> node, val;
+    out->assign(E + 1, 0.);
+    for (int e = 0; e < E; e++) {
+        (*out)[e] = (double)node.size();
+        for (int i = 0; i < N; i++) {
+            const double w = sys->mat_a[i + (size_t)N * e];
+            if (w != 0.) {
+                node.push_back((double)i);
+                val.push_back(w);
+            }
+        }
+    }
+    (*out)[E] = (double)node.size();
+    out->insert(out->end(), node.begin(), node.end());
+    out->insert(out->end(), val.begin(), val.end());
+}
+
 static int build_sysdev(const mcbb_system_desc* sys, SysDev* out, cudaStream_t st) {
     int len[5];
     if (int rc = table_lengths(sys, len)) return rc;
@@ -180,6 +200,12 @@ static int build_sysdev(const mcbb_system_desc* sys, SysDev* out, cudaStream_t s
     if (S.n_osc < 1 || S.n_dim < 1) MCBB_FAIL("system descriptor: N and n_dim must be positive");
     const double* src[5] = {sys->mat_a, sys->mat_b, sys->vec_a, sys->vec_b, sys->vec_c};
     const double* dst[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> edge_csr;
+    if (sys->system == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
+        build_edge_csr(sys, &edge_csr);
+        src[1] = edge_csr.data();
+        len[1] = (int)edge_csr.size();
+    }
     for (int k = 0; k < 5; k++) {
         if (len[k] == 0) continue;
         double* d = (double*)scratch_get(k, sizeof(double) * (size_t)len[k]);

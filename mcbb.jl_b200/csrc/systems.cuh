@@ -72,19 +72,22 @@ MCBB_HD void rhs_lane(const SysDev& S, const SysTabs& T, const double* sc, const
             du[i * bs] = fma(KN, cs[i * bs] * as - ss[i * bs] * ac, T.vec_a[i]);
         }
     } else if constexpr (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) {  // systems.jl:198-202
+        // mat_b holds the incidence matrix by edge in compressed form (built at upload, api.cu):
+        //   [0..E]          start of each edge's entries          (as doubles)
+        //   [E+1 .. E+nnz]  node index of each entry, ascending   (same order as the dense row scan)
+        //   [E+1+nnz ..]    incidence value of each entry
         const int E = S.n_edges;
+        const double* ptr = T.mat_b;
+        const int nnz = (int)ptr[E];
+        const double* node = T.mat_b + E + 1;
+        const double* val = node + nnz;
         for (int i = 0; i < N; i++) du[(N + i) * bs] = 0.;
         for (int e = 0; e < E; e++) {
+            const int p0 = (int)ptr[e], p1 = (int)ptr[e + 1];
             double arg = 0.;
-            for (int i = 0; i < N; i++) {
-                const double w = T.mat_a[i + N * e];
-                if (w != 0.) arg += w * u[i * bs];
-            }
-            const double s = sin(arg);
-            for (int i = 0; i < N; i++) {
-                const double w = T.mat_a[i + N * e];
-                if (w != 0.) du[(N + i) * bs] += w * s;
-            }
+            for (int q = p0; q < p1; q++) arg += val[q] * u[(int)node[q] * bs];  // incidence' * theta
+            const double sv = sin(arg);
+            for (int q = p0; q < p1; q++) du[(N + (int)node[q]) * bs] += val[q] * sv;  // incidence * sin(.)
         }
         for (int i = 0; i < N; i++) {
             const double om = u[(N + i) * bs];

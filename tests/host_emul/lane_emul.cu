@@ -8,6 +8,7 @@
 namespace mcbb {
 int table_lengths(const mcbb_system_desc* s, int len[5]);
 int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* out, std::vector<int>* filter_host);
+void build_edge_csr(const mcbb_system_desc* sys, std::vector<double>* out);
 }
 using namespace mcbb;
 
@@ -42,6 +43,11 @@ extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solve
     for (int i = 0; i < MCBB_N_SCALARS; i++) S.scalars[i] = sys->scalars[i];
     S.n_par = sys->n_par;
     for (int i = 0; i < MCBB_MAX_PAR; i++) S.par_slot[i] = sys->par_slot[i];
+    std::vector<double> csr;
+    if (S.system == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
+        build_edge_csr(sys, &csr);
+        S.mat_b = csr.data();
+    }
     FeatDev F;
     std::vector<int> filt;
     if (resolve_feat(sys, feat, &F, &filt)) return 1;
