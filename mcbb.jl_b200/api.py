@@ -535,6 +535,60 @@ def sort_(sol, prob, i=1):
 # ------------------------------------------------------------------------------------------------------------
 # distance_matrix / dbscan (src/eval_clustering.jl:164-241, 84)
 # ------------------------------------------------------------------------------------------------------------
+def _compute_hist_edges(data, N_dim, k_bin, nbin_default=50):
+    """_compute_hist_edges (eval_clustering.jl:607-642, automatic binning): common edges of one measure from the
+    Freedman-Draconis rule 0.5*k_bin*IQR/N_dim^(1/3); falls back to `nbin_default` equidistant edges over
+    [min-0.1min, max+0.1max] when the IQR is 0 or the rule yields more than nbin_default edges."""
+    data = np.asarray(data, dtype=np.float64)
+    minval, maxval = float(data.min()), float(data.max())
+    q75, q25 = np.percentile(data, [75, 25])  # type-7 quantiles, like StatsBase.iqr
+    bw = 0.5 * k_bin * float(q75 - q25) / N_dim ** (1 / 3.0)
+    if bw != 0:
+        edges = _julia_range(minval - bw, bw, maxval + bw)
+        if len(edges) <= nbin_default:
+            return edges, bw
+    import warnings
+    warnings.warn("Bin width from the IQR is 0 or gives too many bins; the number of bins is set to %d" % nbin_default)
+    a, b = np.longdouble(minval - 0.1 * minval), np.longdouble(maxval + 0.1 * maxval)
+    edges = np.array([float(a + (b - a) * np.longdouble(i) / np.longdouble(nbin_default - 1))
+                      for i in range(nbin_default)])
+    return edges, float(edges[1] - edges[0])
+
+
+def _compute_hist_weights(meas, edges, use_ecdf=True):
+    """_compute_hist_weights (eval_clustering.jl:587-598): per-run Float32 histogram of the N_dim values over the
+    common edges (closed=:left, out-of-range dropped), then ecdf_hist (:759-762) - Float32 like the reference."""
+    meas = np.asarray(meas, dtype=np.float64)
+    n_mc = meas.shape[0]
+    ne, nb = len(edges), len(edges) - 1
+    first, step = edges[0], edges[1] - edges[0]
+    with np.errstate(invalid="ignore"):
+        f = np.clip((meas - first) / step + 1.0, 1.0, float(ne))  # Base.searchsortedlast on a range
+        k = np.rint(np.where(np.isnan(f), 1.0, f)).astype(np.int64)
+        k -= (meas < edges[k - 1]).astype(np.int64)
+        ok = (k >= 1) & (k <= nb) & ~np.isnan(meas)
+    H = np.zeros((n_mc, nb), dtype=np.float32)
+    rows = np.broadcast_to(np.arange(n_mc)[:, None], meas.shape)
+    np.add.at(H, (rows[ok], k[ok] - 1), np.float32(1))
+    if use_ecdf:
+        H = np.cumsum(H, axis=1, dtype=np.float32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            H = H / H[:, -1:]
+    return H
+
+
+class DistanceMatrixHist:
+    """DistanceMatrixHist (eval_clustering.jl:62-73)."""
+
+    def __init__(self, data, weights, relative_parameter, hist_edges, bin_width, ecdf, k_bin):
+        self.data, self.weights, self.relative_parameter = data, list(weights), relative_parameter
+        self.hist_edges, self.bin_width, self.ecdf, self.k_bin = hist_edges, bin_width, ecdf, k_bin
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+
 class DistanceMatrix:
     """DistanceMatrix (eval_clustering.jl:32-38): `.data` is the dense N x N Float64 matrix."""
 
@@ -596,12 +650,48 @@ def feature_groups(sol, prob, weights, relative_parameter=False):
     return X, np.asarray(glen, dtype=np.int32), np.asarray(weights, dtype=np.float64)
 
 
-def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=False, materialize=True):
-    """distance_matrix(sol, prob, weights; relative_parameter) with the default L1 distance_func
-    (eval_clustering.jl:164-241).  materialize=False returns a B200FeatureMatrix for large N."""
+def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
+                    nbin_default=50, materialize=True):
+    """distance_matrix(sol, prob, weights; relative_parameter, histograms, use_ecdf, k_bin, nbin_default) with the
+    default L1 distance_func / wasserstein_histogram_distance (eval_clustering.jl:164-241).
+    materialize=False returns a B200FeatureMatrix (distances are then recomputed on the fly by dbscan)."""
+    hist_edges, bin_widths = [], []
     if histograms:
-        raise MCBBError("histograms=true is not implemented in the B200 back end yet")
-    X, glen, gw = feature_groups(sol, prob, weights, relative_parameter)
+        # per-dimension measures are replaced by per-run Float32 ECDF rows over common edges; the distance of two
+        # runs is sum|ECDF_i - ECDF_j| * bin_width (:261-268, 746-752) = an L1 group with weight w * bin_width
+        n_par = prob.par.shape[1]
+        if len(weights) != sol.N_meas + n_par:
+            raise MCBBError("Amount of weights not the same as Measures + Parameters")
+        cols, glen, gw = [], [], []
+        for mi in range(sol.N_meas_dim):
+            edges, bw = _compute_hist_edges(sol.feat[:, :, mi], sol.N_dim, k_bin, nbin_default)
+            H = _compute_hist_weights(sol.feat[:, :, mi], edges, use_ecdf)
+            hist_edges.append(edges)
+            bin_widths.append(bw)
+            cols.append(H.astype(np.float64))
+            glen.append(H.shape[1])
+            gw.append(weights[mi] * bw)
+        k = sol.N_meas_dim
+        if sol.matrix is not None:
+            cols.append(sol.matrix)
+            glen.append(sol.matrix.shape[1])
+            gw.append(weights[k])
+            k += 1
+        if sol.glob is not None:
+            for g in range(sol.glob.shape[1]):
+                cols.append(sol.glob[:, g:g + 1])
+                glen.append(1)
+                gw.append(weights[k])
+                k += 1
+        par = _relative_parameter(prob) if relative_parameter else prob.par
+        for p in range(n_par):
+            cols.append(np.asarray(par[:, p:p + 1], dtype=np.float64))
+            glen.append(1)
+            gw.append(weights[k + p])
+        X = np.asfortranarray(np.concatenate(cols, axis=1), dtype=np.float64)
+        glen, gw = np.asarray(glen, dtype=np.int32), np.asarray(gw, dtype=np.float64)
+    else:
+        X, glen, gw = feature_groups(sol, prob, weights, relative_parameter)
     if not materialize:
         return B200FeatureMatrix(X, glen, gw, weights, relative_parameter)
     n = X.shape[0]
@@ -615,6 +705,8 @@ def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=Fal
     if np.isinf(D).any():
         import warnings
         warnings.warn("There are some elements Inf in the distance matrix")
+    if histograms:
+        return DistanceMatrixHist(D, weights, relative_parameter, hist_edges, bin_widths, use_ecdf, k_bin)
     return DistanceMatrix(D, weights, relative_parameter)
 
 
@@ -631,7 +723,7 @@ def dbscan(D, eps, minpts):
     if isinstance(D, B200FeatureMatrix):
         n = D.X.shape[0]
     else:
-        data = D.data if isinstance(D, DistanceMatrix) else D
+        data = D.data if isinstance(D, (DistanceMatrix, DistanceMatrixHist)) else D
         data = np.asfortranarray(data, dtype=np.float64)
         n = data.shape[0]
         if data.shape[1] != n:
@@ -741,7 +833,7 @@ def cluster_membership(prob, clusters, window_size, window_offset, normalize=Tru
 # eps-selection helpers (src/eval_clustering.jl:1504-1553)
 # ------------------------------------------------------------------------------------------------------------
 def _knn(D, k, K):
-    data = D.data if isinstance(D, DistanceMatrix) else D
+    data = D.data if isinstance(D, (DistanceMatrix, DistanceMatrixHist)) else D
     data = np.asfortranarray(data, dtype=np.float64)
     n = data.shape[0]
     if data.shape[1] != n:

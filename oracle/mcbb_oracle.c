@@ -955,6 +955,108 @@ int orc_cluster_membership(const double* par, const int64_t* assignments, int64_
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------ */
+/* histogram-mode distance: distance_matrix(...; histograms=true), eval_clustering.jl:187-211, 261-268,     */
+/* 587-645, 746-762                                                                                         */
+/* ------------------------------------------------------------------------------------------------------ */
+static int cmp_double(const void* a, const void* b) {
+    const double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+/* StatsBase.iqr: type-7 quantiles (the Julia / numpy default) */
+static double quantile7(const double* sorted, int64_t n, double p) {
+    const double h = (double)(n - 1) * p;
+    const int64_t lo = (int64_t)floor(h);
+    const int64_t hi = lo + 1 < n ? lo + 1 : lo;
+    return sorted[lo] + (h - (double)lo) * (sorted[hi] - sorted[lo]);
+}
+/* _compute_hist_edges, eval_clustering.jl:607-642 (automatic binning branch).  Returns the number of edges. */
+int orc_hist_edges(const double* data, int64_t n_total, int32_t n_dim, double k_bin, int32_t nbin_default,
+                   double* edges_out /* >= nbin_default + 4 */, double* bin_width_out) {
+    double* srt = (double*)malloc(sizeof(double) * n_total);
+    memcpy(srt, data, sizeof(double) * n_total);
+    qsort(srt, n_total, sizeof(double), cmp_double);
+    const double minval = srt[0], maxval = srt[n_total - 1];
+    const double iqr = quantile7(srt, n_total, 0.75) - quantile7(srt, n_total, 0.25);
+    free(srt);
+    double bw = 0.5 * k_bin * iqr / pow((double)n_dim, 1. / 3.); /* freedman_draconis_bin_width, :644 */
+    int len = 0;
+    if (bw != 0) {
+        len = julia_range(minval - bw, bw, maxval + bw, NULL, 0);
+        if (len <= nbin_default) {
+            julia_range(minval - bw, bw, maxval + bw, edges_out, len);
+            *bin_width_out = bw;
+            return len;
+        }
+    }
+    /* fallback (:620-622, 626-628): range(minval - 0.1*minval, maxval + 0.1*maxval, length=nbin_default) */
+    const long double a = (long double)(minval - 0.1 * minval), b = (long double)(maxval + 0.1 * maxval);
+    len = nbin_default;
+    for (int i = 0; i < len; i++) edges_out[i] = (double)(a + (b - a) * (long double)i / (long double)(len - 1));
+    *bin_width_out = edges_out[1] - edges_out[0];
+    return len;
+}
+/* _compute_hist_weights for one run (eval_clustering.jl:587-598): Float32 histogram over the common edges
+ * (closed = :left, out-of-range values dropped), then ecdf_hist in Float32 (:759-762). */
+void orc_hist_ecdf(const double* x, int32_t n, const double* edges, int32_t n_edges, int32_t use_ecdf, float* out) {
+    const int nb = n_edges - 1;
+    const double first = edges[0], step = edges[1] - edges[0];
+    for (int b = 0; b < nb; b++) out[b] = 0.f;
+    for (int i = 0; i < n; i++) {
+        double f = (x[i] - first) / step + 1.; /* Base.searchsortedlast on a range */
+        if (f < 1.) f = 1.;
+        if (f > n_edges) f = n_edges;
+        int k = (int)nearbyint(f);
+        if (x[i] < edges[k - 1]) k -= 1;
+        if (x[i] != x[i]) continue;
+        if (k >= 1 && k <= nb) out[k - 1] += 1.f;
+    }
+    if (use_ecdf) {
+        float cum = 0.f;
+        for (int b = 0; b < nb; b++) {
+            cum += out[b];
+            out[b] = cum;
+        }
+        const float last = out[nb - 1];
+        for (int b = 0; b < nb; b++) out[b] = out[b] / last;
+    }
+}
+/* distance_matrix(sol, prob, weights; histograms=true, k_bin, nbin_default) for per-dimension measures plus the
+ * parameter term.  feat: [n_mc][n_dim][n_meas] column-major as produced by orc_solve_features. */
+int orc_distance_matrix_hist(const double* feat, int64_t n_mc, int32_t n_dim, int32_t n_meas, const double* par,
+                             int32_t n_par, const double* weights, double k_bin, int32_t nbin_default, double* D) {
+    for (int64_t q = 0; q < n_mc * n_mc; q++) D[q] = 0.;
+    double* edges = (double*)malloc(sizeof(double) * (nbin_default + 8));
+    double* xi = (double*)malloc(sizeof(double) * n_dim);
+    for (int m = 0; m < n_meas; m++) {
+        const double* data = feat + (size_t)m * n_dim * n_mc; /* n_mc x n_dim block */
+        double bw;
+        const int ne = orc_hist_edges(data, n_mc * n_dim, n_dim, k_bin, nbin_default, edges, &bw);
+        const int nb = ne - 1;
+        float* H = (float*)malloc(sizeof(float) * (size_t)n_mc * nb);
+        for (int64_t i = 0; i < n_mc; i++) {
+            for (int d = 0; d < n_dim; d++) xi[d] = data[i + n_mc * d];
+            orc_hist_ecdf(xi, n_dim, edges, ne, 1, H + (size_t)i * nb);
+        }
+        for (int64_t i = 0; i < n_mc; i++)
+            for (int64_t j = i + 1; j < n_mc; j++) { /* wasserstein_histogram_distance: Float32 sum times delta */
+                float s = 0.f;
+                for (int b = 0; b < nb; b++) s += fabsf(H[(size_t)i * nb + b] - H[(size_t)j * nb + b]);
+                D[i + n_mc * j] += weights[m] * ((double)s * bw);
+            }
+        free(H);
+    }
+    for (int p = 0; p < n_par; p++)
+        for (int64_t i = 0; i < n_mc; i++)
+            for (int64_t j = i + 1; j < n_mc; j++)
+                D[i + n_mc * j] += weights[n_meas + p] * fabs(par[i + n_mc * p] - par[j + n_mc * p]);
+    for (int64_t i = 0; i < n_mc; i++)
+        for (int64_t j = i + 1; j < n_mc; j++) D[j + n_mc * i] = D[i + n_mc * j];
+    free(xi);
+    free(edges);
+    return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

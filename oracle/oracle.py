@@ -60,6 +60,8 @@ def lib():
                                              dp, dp, ip]
         L.orc_kl_hist.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int]
         L.orc_kl_hist.restype = C.c_double
+        L.orc_distance_matrix_hist.argtypes = [dp, C.c_int64, C.c_int32, C.c_int32, dp, C.c_int32, dp, C.c_double, C.c_int32, dp]
+        L.orc_hist_edges.argtypes = [dp, C.c_int64, C.c_int32, C.c_double, C.c_int32, dp, dp]
         L.orc_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -171,3 +173,24 @@ def cluster_membership(par, assignments, k, window, offset, normalize=True):
 def kl_hist(u, mu, sig, hist_bins=31, n_stds=3.0, sig_tol=1e-4, force_len=0):
     u = np.ascontiguousarray(u, dtype=np.float64)
     return float(lib().orc_kl_hist(_dp(u), len(u), mu, sig, hist_bins, n_stds, sig_tol, force_len))
+
+
+def distance_matrix_hist(feat, par, weights, k_bin=1.0, nbin_default=50):
+    """distance_matrix(...; histograms=true) on per-dimension measures feat[n_mc, n_dim, n_meas] + parameters."""
+    feat = np.asfortranarray(feat, dtype=np.float64)
+    n_mc, n_dim, n_meas = feat.shape
+    par = np.asfortranarray(np.asarray(par, dtype=np.float64).reshape(n_mc, -1))
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    D = np.zeros((n_mc, n_mc), order="F")
+    lib().orc_distance_matrix_hist(_dp(feat), n_mc, n_dim, n_meas, _dp(par), par.shape[1], _dp(w), float(k_bin),
+                                   int(nbin_default), _dp(D))
+    return D
+
+
+def hist_edges(data, n_dim, k_bin=1.0, nbin_default=50):
+    data = np.ascontiguousarray(np.asarray(data, dtype=np.float64).ravel())
+    edges = np.zeros(nbin_default + 8)
+    bw = C.c_double(0)
+    ne = lib().orc_hist_edges(_dp(data), len(data), int(n_dim), float(k_bin), int(nbin_default), _dp(edges),
+                              C.cast(C.byref(bw), abi.c_double_p))
+    return edges[:ne].copy(), bw.value

@@ -458,3 +458,25 @@ def test_c4_stuart_landau_n100_global_state_path(gpu, orc):
     ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
     assert np.array_equal(sol.retcode, ref["retcode"])
     cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.5)
+
+
+def test_histogram_mode_distance_matrix(gpu, orc):
+    """distance_matrix(sol, prob, weights; histograms=true, k_bin) (eval_clustering.jl:187-211, 261-268): Float32
+    ECDF rows over common IQR-rule edges, L1 * bin_width.  The reference sums the |ECDF| differences in Float32,
+    the device in FP64 -> 1e-6 relative agreement."""
+    import warnings
+    m = gpu
+    prob, _ = cases.c1_problem(m, n_ics=40, seed=17, eval_funcs=(m.mean, m.std))
+    sol = m.solve(prob)
+    weights = [1.0, 0.5, 1.0]
+    for k_bin in (1.0, 0.25):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Dh = m.distance_matrix(sol, prob, weights, histograms=True, k_bin=k_bin)
+        assert isinstance(Dh, m.api.DistanceMatrixHist) and len(Dh.hist_edges) == 2
+        ref = orc.distance_matrix_hist(sol.feat, prob.par, weights, k_bin=k_bin, nbin_default=50)
+        assert np.array_equal(Dh.data, Dh.data.T) and np.all(np.diag(Dh.data) == 0)
+        assert np.allclose(Dh.data, ref, rtol=2e-6, atol=1e-9)
+        res = m.dbscan(Dh, float(np.median(np.sort(ref, axis=0)[5])), 4)
+        rdb = orc.dbscan(Dh.data, float(np.median(np.sort(ref, axis=0)[5])), 4)
+        assert np.array_equal(res.assignments, rdb["assignments"])

@@ -289,3 +289,31 @@ def test_sharded_dbscan_world2_gloo(mcbb, orc):
     a1, s1, c1 = mcbb.dist.dbscan_features_sharded(torch.from_numpy(X), gl, gw, eps, minpts, 0, 1, None,
                                                    backend_ops=_CheckerOps())
     assert np.array_equal(a1.numpy(), ref["assignments"])
+
+
+def test_hist_edges_and_ecdf_rows_match_oracle(mcbb, orc):
+    """Histogram-mode preprocessing (host side, like the reference): common edges (IQR rule + both fallbacks) and
+    the per-run Float32 ECDF rows — the product's vectorised numpy code against the oracle's scalar C loops."""
+    import ctypes as C
+    import warnings
+    rng = np.random.default_rng(0)
+    n, nd = 90, 12
+    cases_ = [rng.normal(0, 1, (n, nd)) * rng.uniform(0.2, 2, (n, 1)), np.abs(rng.normal(0, 0.3, (n, nd))),
+              np.full((n, nd), 0.25) + 1e-3 * (rng.random((n, nd)) < 0.05)]  # last: IQR == 0 -> fallback edges
+    L = orc.lib()
+    L.orc_hist_ecdf.argtypes = [orc.abi.c_double_p, C.c_int32, orc.abi.c_double_p, C.c_int32, C.c_int32,
+                                C.POINTER(C.c_float)]
+    for data in cases_:
+        for k_bin in (1.0, 0.25):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                e1, b1 = mcbb.api._compute_hist_edges(data, nd, k_bin, 50)
+            e2, b2 = orc.hist_edges(np.asfortranarray(data), nd, k_bin, 50)
+            assert np.array_equal(e1, e2) and b1 == b2
+            H = mcbb.api._compute_hist_weights(data, e1, True)
+            for i in (0, 7, n - 1):
+                row = np.ascontiguousarray(data[i])
+                out = np.zeros(len(e1) - 1, dtype=np.float32)
+                L.orc_hist_ecdf(row.ctypes.data_as(orc.abi.c_double_p), nd, e2.ctypes.data_as(orc.abi.c_double_p),
+                                len(e2), 1, out.ctypes.data_as(C.POINTER(C.c_float)))
+                assert np.array_equal(H[i], out, equal_nan=True)
