@@ -110,6 +110,8 @@ Base.@kwdef struct B200Eval
     measures::Vector{Symbol} = [:mean, :std, :kl_hist]
     state_filter::Union{Nothing,Vector{Int}} = nothing
     cyclic_setback::Bool = false
+    correlation_ecdf::Bool = false     # matrix_eval_funcs = [correlation_ecdf] (30 bins)
+    global_sum::Bool = false           # global_eval_funcs = [(x)->sum(x)]
 end
 const MEAS_ID = Dict(:mean => MEAS_MEAN, :std => MEAS_STD, :kl_hist => MEAS_KL_HIST)
 
@@ -131,21 +133,28 @@ function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eva
     nf = eval.state_filter === nothing ? size(prob.ic, 2) : length(filt)
     nm = length(eval.measures)
     fo = FeatOpts(nm, pad(Int32[MEAS_ID[m] for m in eval.measures], MAX_MEAS, Int32(0)), pad(Int32[], MAX_MEAS, Int32(0)),
-                  length(filt), isempty(filt) ? C_NULL : pointer(filt), eval.cyclic_setback, 0, 30, 0,
+                  length(filt), isempty(filt) ? C_NULL : pointer(filt), eval.cyclic_setback,
+                  eval.correlation_ecdf ? 1 : 0, 30, eval.global_sum ? 1 : 0,
                   pad(Int32[], MAX_GLOBAL, Int32(0)), 31, 3.0, 1e-4)
+    mat = eval.correlation_ecdf ? Matrix{Float64}(undef, prob.N_mc, 30) : Matrix{Float64}(undef, 0, 0)
+    glob = eval.global_sum ? Matrix{Float64}(undef, prob.N_mc, 1) : Matrix{Float64}(undef, 0, 0)
     ic = Matrix{Float64}(prob.ic)            # N_mc x N_dim, column-major: already struct-of-arrays over runs
     par = Matrix{Float64}(prob.par)
     ts = Vector{Float64}(t_save)
     feat = Array{Float64}(undef, prob.N_mc, nf, nm)
     retcode = Vector{Int32}(undef, prob.N_mc)
     nsteps = Matrix{Int64}(undef, prob.N_mc, 2)
-    GC.@preserve keep filt ic par ts feat retcode nsteps begin
+    GC.@preserve keep filt ic par ts feat mat glob retcode nsteps begin
         check(ccall((:mcbb_solve_features, LIB), Cint,
                     (Ref{SystemDesc}, Ref{SolverOpts}, Ref{FeatOpts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                      Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
-                    desc, opts, fo, prob.N_mc, ic, par, ts, length(ts), feat, C_NULL, C_NULL, retcode, nsteps))
+                    desc, opts, fo, prob.N_mc, ic, par, ts, length(ts), feat,
+                    eval.correlation_ecdf ? pointer(mat) : C_NULL, eval.global_sum ? pointer(glob) : C_NULL,
+                    retcode, nsteps))
     end
-    u = [ntuple(m -> feat[i, :, m], nm) for i in 1:prob.N_mc]
+    # tuple order of eval_ode_run: per-dimension measures, matrix measures, global measures (eval_mc_prob.jl:187)
+    u = [(ntuple(m -> feat[i, :, m], nm)..., (eval.correlation_ecdf ? (mat[i, :],) : ())...,
+          (eval.global_sum ? (glob[i, 1],) : ())...) for i in 1:prob.N_mc]
     DiffEqBase.EnsembleSolution(u, 0.0, true)
 end
 
@@ -180,8 +189,23 @@ function feature_groups(sol::MCBB.myMCSol, prob::MCBB.myMCProblem, weights::Abst
     hcat(cols...), glen, Vector{Float64}(weights)
 end
 
-function distance_matrix_b200(sol, prob, weights; relative_parameter::Bool=false)
+function distance_matrix_b200(sol, prob, weights; relative_parameter::Bool=false, histograms::Bool=false,
+                              k_bin::Number=1, nbin_default::Int=50)
     X, glen, gw = feature_groups(sol, prob, weights; relative_parameter=relative_parameter)
+    if histograms  # per-dimension measures -> Float32 ECDF rows over common edges; weight w * bin_width
+        cols = Matrix{Float64}[]; glen = Int32[]; gw = Float64[]
+        for k in 1:sol.N_meas_dim
+            edges, bw = MCBB._compute_hist_edges(k, sol, k_bin; nbin_default=nbin_default)
+            push!(cols, Float64.(MCBB._compute_hist_weights(k, sol, edges, true)))
+            push!(glen, length(edges) - 1); push!(gw, weights[k] * bw)
+        end
+        par = relative_parameter ? MCBB._relative_parameter(prob) : MCBB.parameter(prob)
+        par = ndims(par) == 1 ? reshape(Vector{Float64}(par), :, 1) : Matrix{Float64}(par)
+        for p in 1:size(par, 2)
+            push!(cols, par[:, p:p]); push!(glen, 1); push!(gw, weights[sol.N_meas + p])
+        end
+        X = hcat(cols...)
+    end
     n = size(X, 1)
     D = Matrix{Float64}(undef, n, n)
     check(ccall((:mcbb_distance_matrix, LIB), Cint, (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
@@ -221,5 +245,17 @@ function dbscan_b200(D::AbstractMatrix{Float64}, eps::Real, minpts::Int)
         Dd, n, Float64(eps), Int32(minpts), a, s, c, k))
 end
 dbscan_b200(D::MCBB.AbstractDistanceMatrix, eps::Real, minpts::Int) = dbscan_b200(D.data, eps, minpts)
+
+# ---- eps selection: k_dist / KNN_dist (src/eval_clustering.jl:1504-1553) ----------------------------------------
+function _knn(D::AbstractMatrix{Float64}, k::Int, K::Int)
+    n = size(D, 1)
+    kth = Vector{Float64}(undef, n); cum = Vector{Float64}(undef, n)
+    check(ccall((:mcbb_knn_dist_dense, LIB), Cint, (Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}),
+                Matrix{Float64}(D), n, k, K, kth, cum))
+    kth, cum
+end
+k_dist_b200(D::AbstractMatrix{Float64}, k::Int=4) = sort(_knn(D, k, 1)[1], rev=true)
+KNN_dist_b200(D::AbstractMatrix{Float64}, K::Int) = reshape(_knn(D, 1, K)[2], :, 1)
+KNN_dist_relative_b200(D::AbstractMatrix{Float64}, rel_K::Float64=0.005) = KNN_dist_b200(D, Int(round(size(D, 1) * rel_K)))
 
 end # module
