@@ -446,40 +446,57 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
             const int b = bg * TB + q;
             if (!ctl[b].accept) continue;
             const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
-            for (int k = ctl[b].s0; k < ctl[b].s1; k++) {
-                if (k < 1) continue;  // first saved sample dropped, eval_mc_prob.jl:152
-                const double ts = sm_ts[k];
-                double bth[7];
-                tsit5_btheta((ts - t_old) / dts, bth);
-                const double rk = 1. / (double)k;
+            const int ks0 = ctl[b].s0 < 1 ? 1 : ctl[b].s0, ks1 = ctl[b].s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
+            if (ks0 < ks1) {
+                // Welford state in registers across the samples of this step: one L2 round trip per accepted step
+                double am[TI], a2[TI], as[TI];
 #pragma unroll
                 for (int r = 0; r < TI; r++) {
                     const int e = r * TB + q;
-                    double lin = KS(1, e) * bth[0];
+                    am[r] = ACCS(0, e);
+                    a2[r] = ACCS(1, e);
+                    as[r] = ACCS(2, e);
+                }
+                for (int k = ks0; k < ks1; k++) {
+                    const double ts = sm_ts[k];
+                    double bth[7];
+                    tsit5_btheta((ts - t_old) / dts, bth);
+                    const double rk = 1. / (double)k;
 #pragma unroll
-                    for (int j = 1; j < 7; j++) lin = fma(KS(1 + j, e), bth[j], lin);
-                    double x = fma(dts, lin, KS(0, e));
-                    if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
-                        if (k == 1) {
-                            const double twopi = 6.283185307179586, pi = 3.141592653589793;
-                            double v = julia_mod_pos(x, twopi);
-                            if (v > pi) v -= twopi;
-                            ACCS(2, e) = x - v;
-                            x = v;
+                    for (int r = 0; r < TI; r++) {
+                        const int e = r * TB + q;
+                        double lin = KS(1, e) * bth[0];
+#pragma unroll
+                        for (int j = 1; j < 7; j++) lin = fma(KS(1 + j, e), bth[j], lin);
+                        double x = fma(dts, lin, KS(0, e));
+                        if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
+                            if (k == 1) {
+                                const double twopi = 6.283185307179586, pi = 3.141592653589793;
+                                double v = julia_mod_pos(x, twopi);
+                                if (v > pi) v -= twopi;
+                                as[r] = x - v;
+                                x = v;
+                            } else {
+                                x = x - as[r];
+                            }
+                        }
+                        const double delta = x - am[r];
+                        if (fabs(delta) <= 1.7976931348623157e308) {
+                            const double mnew = fma(delta, rk, am[r]);
+                            a2[r] = fma(delta, x - mnew, a2[r]);
+                            am[r] = mnew;
                         } else {
-                            x = x - ACCS(2, e);
+                            am[r] = nonfinite_mean(am[r], x);
+                            a2[r] = nan("");
                         }
                     }
-                    const double mean = ACCS(0, e);
-                    const double delta = x - mean;
-                    if (fabs(delta) <= 1.7976931348623157e308) {
-                        const double mnew = fma(delta, rk, mean);
-                        ACCS(0, e) = mnew;
-                        ACCS(1, e) = fma(delta, x - mnew, ACCS(1, e));
-                    } else {
-                        ACCS(0, e) = nonfinite_mean(mean, x);
-                        ACCS(1, e) = nan("");
-                    }
+                }
+#pragma unroll
+                for (int r = 0; r < TI; r++) {
+                    const int e = r * TB + q;
+                    ACCS(0, e) = am[r];
+                    ACCS(1, e) = a2[r];
+                    ACCS(2, e) = as[r];
                 }
             }
             bool bad = false;
