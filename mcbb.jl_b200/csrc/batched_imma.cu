@@ -297,7 +297,9 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
             }
             __syncthreads();
             // (b) seven s8 x u8 GEMM slices per column tile, (c) int64 recombination and k = a1 (c P - s Q) + w
-#pragma unroll 1
+            //     (specialised kernels unroll two column tiles: the second tile's IMMAs overlap the first one's
+            //     integer recombination)
+#pragma unroll(CT_T > 0 && CT_T <= 2 ? 2 : 1)
             for (int ct = part; ct < CT; ct += WS) {
                 int cacc[IM_NSLICE][4];
 #pragma unroll
@@ -471,70 +473,63 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
         }
         __syncthreads();
 
-        // ---- accepted steps: fused featurizer on the saved samples, then u <- u_new, k1 <- k7 ----------------
+        // ---- accepted steps: fused featurizer on the saved samples ---------------------------------------------
+        // Trajectories reach their tail at different times, so in a given round at most a few slots have samples.
+        // Work is therefore distributed per trajectory: one thread per oscillator (all warps), instead of every
+        // (warp, column tile) walking the samples of four unrelated trajectories.
+#pragma unroll 1
+        for (int b = 0; b < B; b++) {
+            if (!ctl[b].accept) continue;
+            const int ks0 = ctl[b].s0 < 1 ? 1 : ctl[b].s0, ks1 = ctl[b].s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
+            if (ks0 >= ks1) continue;
+            const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
+            for (int row = tid; row < N; row += (int)blockDim.x) {
+                const int idx = row * BP + b;
+                double am = ACCS(0, idx), a2 = ACCS(1, idx), as = ACCS(2, idx);  // one L2 round trip per step
+                double kk[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) kk[j] = KP(j, idx);
+                for (int k = ks0; k < ks1; k++) {
+                    double bth[7];
+                    tsit5_btheta((sm_ts[k] - t_old) / dts, bth);
+                    double lin = kk[1] * bth[0];
+#pragma unroll
+                    for (int j = 1; j < 7; j++) lin = fma(kk[1 + j], bth[j], lin);
+                    double x = fma(dts, lin, kk[0]);
+                    if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
+                        if (k == 1) {
+                            const double twopi = 6.283185307179586, pi = 3.141592653589793;
+                            double vv = julia_mod_pos(x, twopi);
+                            if (vv > pi) vv -= twopi;
+                            as = x - vv;
+                            x = vv;
+                        } else {
+                            x = x - as;
+                        }
+                    }
+                    const double delta = x - am;
+                    if (fabs(delta) <= 1.7976931348623157e308) {
+                        const double mnew = fma(delta, 1. / (double)k, am);
+                        a2 = fma(delta, x - mnew, a2);
+                        am = mnew;
+                    } else {
+                        am = nonfinite_mean(am, x);
+                        a2 = nan("");
+                    }
+                }
+                ACCS(0, idx) = am;
+                ACCS(1, idx) = a2;
+                ACCS(2, idx) = as;
+            }
+        }
+        __syncthreads();  // the samples read u and k1..k7 of every oscillator: only now may the owners overwrite them
+
+        // ---- u <- u_new, k1 <- k7 (FSAL) by the fragment owners ---------------------------------------------------
 #pragma unroll 1
         for (int ct = part; ct < CT; ct += WS) {
             const int b = ct * 4 + t4;
             if (!ctl[b].accept) continue;
-            const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
-            const int ks0 = ctl[b].s0 < 1 ? 1 : ctl[b].s0, ks1 = ctl[b].s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
-            if (ks0 < ks1) {
-                // Welford state of the two owned elements: one global (L2) round trip per accepted step, the
-                // per-sample updates stay in registers
-                const int idx0 = (v0 ? row0 : 0) * BP + b, idx1 = (v1 ? row1 : 0) * BP + b;
-                double am[2] = {ACCS(0, idx0), ACCS(0, idx1)};
-                double a2[2] = {ACCS(1, idx0), ACCS(1, idx1)};
-                double as[2] = {ACCS(2, idx0), ACCS(2, idx1)};
-                double kk[2][8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    kk[0][j] = KP(j, idx0);
-                    kk[1][j] = KP(j, idx1);
-                }
-                for (int k = ks0; k < ks1; k++) {
-                    const double ts = sm_ts[k];
-                    double bth[7];
-                    tsit5_btheta((ts - t_old) / dts, bth);
-                    const double rk = 1. / (double)k;
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        double lin = kk[h][1] * bth[0];
-#pragma unroll
-                        for (int j = 1; j < 7; j++) lin = fma(kk[h][1 + j], bth[j], lin);
-                        double x = fma(dts, lin, kk[h][0]);
-                        if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
-                            if (k == 1) {
-                                const double twopi = 6.283185307179586, pi = 3.141592653589793;
-                                double vv = julia_mod_pos(x, twopi);
-                                if (vv > pi) vv -= twopi;
-                                as[h] = x - vv;
-                                x = vv;
-                            } else {
-                                x = x - as[h];
-                            }
-                        }
-                        const double delta = x - am[h];
-                        if (fabs(delta) <= 1.7976931348623157e308) {
-                            const double mnew = fma(delta, rk, am[h]);
-                            a2[h] = fma(delta, x - mnew, a2[h]);
-                            am[h] = mnew;
-                        } else {
-                            am[h] = nonfinite_mean(am[h], x);
-                            a2[h] = nan("");
-                        }
-                    }
-                }
-                if (v0) {
-                    ACCS(0, idx0) = am[0];
-                    ACCS(1, idx0) = a2[0];
-                    ACCS(2, idx0) = as[0];
-                }
-                if (v1) {
-                    ACCS(0, idx1) = am[1];
-                    ACCS(1, idx1) = a2[1];
-                    ACCS(2, idx1) = as[1];
-                }
-            }
+            const double dts = ctl[b].dts_old;
             bool bad = false;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
