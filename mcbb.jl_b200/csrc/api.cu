@@ -189,6 +189,19 @@ void build_edge_csr(const mcbb_system_desc* sys, std::vector<double>* out) {
     out->insert(out->end(), val.begin(), val.end());
 }
 
+// 0/1 adjacency (non-zero = true) as compressed rows: [0..N] row starts, then ascending column indices (doubles)
+void build_adj_csr(const double* A, int N, std::vector<double>* out) {
+    std::vector<double> cols;
+    out->assign(N + 1, 0.);
+    for (int i = 0; i < N; i++) {
+        (*out)[i] = (double)cols.size();
+        for (int j = 0; j < N; j++)
+            if (A[i + (size_t)N * j] != 0.) cols.push_back((double)j);
+    }
+    (*out)[N] = (double)cols.size();
+    out->insert(out->end(), cols.begin(), cols.end());
+}
+
 static int build_sysdev(const mcbb_system_desc* sys, SysDev* out, cudaStream_t st) {
     int len[5];
     if (int rc = table_lengths(sys, len)) return rc;
@@ -200,11 +213,19 @@ static int build_sysdev(const mcbb_system_desc* sys, SysDev* out, cudaStream_t s
     if (S.n_osc < 1 || S.n_dim < 1) MCBB_FAIL("system descriptor: N and n_dim must be positive");
     const double* src[5] = {sys->mat_a, sys->mat_b, sys->vec_a, sys->vec_b, sys->vec_c};
     const double* dst[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    std::vector<double> edge_csr;
+    std::vector<double> edge_csr, adj1, adj2;
     if (sys->system == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
         build_edge_csr(sys, &edge_csr);
         src[1] = edge_csr.data();
         len[1] = (int)edge_csr.size();
+    }
+    if (sys->system == MCBB_SYS_STUART_LANDAU) {
+        build_adj_csr(sys->mat_a, sys->n_osc, &adj1);
+        build_adj_csr(sys->mat_b, sys->n_osc, &adj2);
+        src[0] = adj1.data();
+        len[0] = (int)adj1.size();
+        src[1] = adj2.data();
+        len[1] = (int)adj2.size();
     }
     for (int k = 0; k < 5; k++) {
         if (len[k] == 0) continue;

@@ -242,12 +242,13 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
         }
     }
     if (bs == 0) {
-        // state in global memory: at most ~64 MB of stage vectors in flight so that they stay L2-resident
+        // state in global memory.  The kernel is latency bound (dependent loads of the stage vectors), so fill the
+        // machine: 8 CTAs of 64 lanes per SM (~76 k lanes; at most 8 GB of stage vectors, HBM-resident)
         int dev = 0, sms = 148;
         MCBB_CUDA_OK(cudaGetDevice(&dev));
         MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int block = 64;
-        long long lanes = std::min<long long>((long long)sms * 8 * block, std::max<long long>(block, (64LL << 20) / (long long)per_lane));
+        long long lanes = std::min<long long>((long long)sms * 8 * block, std::max<long long>(block, (8LL << 30) / (long long)per_lane));
         lanes = std::min<long long>(lanes, (io.n_mc + block - 1) / block * block);
         lanes = std::max<long long>(block, lanes / block * block);
         const int grid = (int)(lanes / block);

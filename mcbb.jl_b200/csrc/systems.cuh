@@ -118,16 +118,20 @@ MCBB_HD void rhs_lane(const SysDev& S, const SysTabs& T, const double* sc, const
             du[k * bs] = -(sk * gc - ck * gs) / fak + omega0;
         }
     } else if constexpr (SYS == MCBB_SYS_STUART_LANDAU) {  // SL notebook cell 1
+        // mat_a / mat_b hold A_1 / A_2 as compressed rows (built at upload, api.cu): [0..N] row starts,
+        // then the column indices in ascending order (= the summation order of the reference's dense scan)
         const double eps = sc[0], lambda = sc[1], omega = sc[2];
         const double epsP1 = eps / (2. * sc[3]);
         const double epsP2 = eps / (2. * sc[4]);
+        const double* p1 = T.mat_a;
+        const double* c1 = T.mat_a + N + 1;
+        const double* p2 = T.mat_b;
+        const double* c2 = T.mat_b + N + 1;
         for (int i = 0; i < N; i++) {
             const double x = u[(2 * i) * bs], y = u[(2 * i + 1) * bs];
             double attr = 0., rep = 0.;
-            for (int j = 0; j < N; j++) {
-                if (T.mat_a[i + N * j] != 0.) attr += u[(2 * j) * bs] - x;
-                if (T.mat_b[i + N * j] != 0.) rep += u[(2 * j + 1) * bs] - y;
-            }
+            for (int q = (int)p1[i]; q < (int)p1[i + 1]; q++) attr += u[(2 * (int)c1[q]) * bs] - x;
+            for (int q = (int)p2[i]; q < (int)p2[i + 1]; q++) rep += u[(2 * (int)c2[q] + 1) * bs] - y;
             attr *= epsP1;
             rep *= epsP2;
             const double cr = lambda - (x * x + y * y);

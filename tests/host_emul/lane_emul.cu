@@ -9,6 +9,7 @@ namespace mcbb {
 int table_lengths(const mcbb_system_desc* s, int len[5]);
 int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* out, std::vector<int>* filter_host);
 void build_edge_csr(const mcbb_system_desc* sys, std::vector<double>* out);
+void build_adj_csr(const double* A, int N, std::vector<double>* out);
 }
 using namespace mcbb;
 
@@ -47,6 +48,13 @@ extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solve
     if (S.system == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
         build_edge_csr(sys, &csr);
         S.mat_b = csr.data();
+    }
+    std::vector<double> adj1, adj2;
+    if (S.system == MCBB_SYS_STUART_LANDAU) {
+        build_adj_csr(sys->mat_a, sys->n_osc, &adj1);
+        build_adj_csr(sys->mat_b, sys->n_osc, &adj2);
+        S.mat_a = adj1.data();
+        S.mat_b = adj2.data();
     }
     FeatDev F;
     std::vector<int> filt;
