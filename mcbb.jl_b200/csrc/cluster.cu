@@ -194,6 +194,7 @@ static inline unsigned nblk(long long n, int b = 256) { return (unsigned)((n + b
 struct GroupTables {
     double* fw;
     unsigned char* fend;
+    unsigned short* fmask;
     int F;
     int early_exit;
 };
@@ -216,11 +217,16 @@ static int upload_groups(int n_groups, const int32_t* group_len, const double* g
             fe[f] = (q == group_len[g] - 1);
         }
     }
+    std::vector<unsigned short> fm((F + FC - 1) / FC, 0);
+    for (int q = 0; q < F; q++)
+        if (fe[q]) fm[q / FC] |= (unsigned short)(1u << (q % FC));
     gt->fw = (double*)scratch_get(10, sizeof(double) * F);
     gt->fend = (unsigned char*)scratch_get(11, F);
-    if (!gt->fw || !gt->fend) MCBB_FAIL("distance: device scratch allocation failed");
+    gt->fmask = (unsigned short*)scratch_get(58, sizeof(unsigned short) * fm.size());
+    if (!gt->fw || !gt->fend || !gt->fmask) MCBB_FAIL("distance: device scratch allocation failed");
     MCBB_CUDA_OK(cudaMemcpyAsync(gt->fw, fw.data(), sizeof(double) * F, cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(gt->fend, fe.data(), F, cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(gt->fmask, fm.data(), sizeof(unsigned short) * fm.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));  // fw / fe are stack-owned
     gt->F = F;
     gt->early_exit = ee;
@@ -278,6 +284,7 @@ static int count_rows(const double* X, long long n, const GroupTables& gt, doubl
     a.F = gt.F;
     a.fw = gt.fw;
     a.fend = gt.fend;
+    a.fmask = gt.fmask;
     a.eps = eps;
     a.symmetric = 0;  // full rows: the diagonal pair (d = 0 < eps) supplies the self count
     a.early_exit = gt.early_exit;
@@ -348,6 +355,7 @@ static int union_rows(const double* Xc, long long n_core, const GroupTables& gt,
     u.F = gt.F;
     u.fw = gt.fw;
     u.fend = gt.fend;
+    u.fmask = gt.fmask;
     u.eps = eps;
     u.symmetric = 1;
     u.early_exit = gt.early_exit;
@@ -376,6 +384,7 @@ int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_
     a.F = gt.F;
     a.fw = gt.fw;
     a.fend = gt.fend;
+    a.fmask = gt.fmask;
     a.symmetric = 1;
     a.D = D;
     a.sat_seed = -1;
@@ -446,6 +455,7 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
     a.F = F;
     a.fw = gt.fw;
     a.fend = gt.fend;
+    a.fmask = gt.fmask;
     a.eps = eps;
     a.early_exit = gt.early_exit;
     a.sat_seed = -1;
@@ -615,6 +625,7 @@ int rows_border_dev(const double* Xn, long long n_non, long long row0, long long
     a.F = gt.F;
     a.fw = gt.fw;
     a.fend = gt.fend;
+    a.fmask = gt.fmask;
     a.eps = eps;
     a.symmetric = 0;
     a.early_exit = gt.early_exit;

@@ -37,6 +37,7 @@ struct TileArgs {
     int F;
     const double* fw;          // [F] weight of the feature's group
     const unsigned char* fend; // [F] 1 when the feature closes its group
+    const unsigned short* fmask;  // [ceil(F/16)] bit f%16 set when feature f closes its group (one load per slab)
     double eps;
     int symmetric;   // Xr == Xc: only pairs col > row are visited, results applied to both sides
     int early_exit;  // all weights >= 0
@@ -89,12 +90,9 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
-    __shared__ double s_slab[2][FC][TILE];  // row-side and column-side feature slabs (contiguous: reused as the
-                                            // 32 x 64 staging buffer of the materialising store)
-    double (*s_r)[TILE] = s_slab[0];
-    double (*s_c)[TILE] = s_slab[1];
-    __shared__ double s_w[FC];
-    __shared__ unsigned char s_e[FC];
+    __shared__ __align__(16) double s_slab[2][2][FC][TILE];  // [buffer][row side / column side][feature][point]; a
+                                                             // buffer doubles as the 32 x 64 staging tile of the
+                                                             // materialising store
 
     const long long tr = a.r0 + (long long)blockIdx.y * TILE;
     long long tc = a.c0 + (long long)blockIdx.x * TILE;
@@ -153,25 +151,33 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
 #pragma unroll
         for (int j = 0; j < TT; j++) acc[i][j] = accg[i][j] = 0.;
 
-    for (int f0 = 0; f0 < a.F; f0 += FC) {
+    // Feature slabs are double buffered with cp.async (LDGSTS): slab k+1 streams into the other buffer while slab k
+    // is being accumulated; out-of-range rows / columns / features are zero-filled (src-size 0).
+    auto issue_slab = [&](const int f0, const int buf) {
         const int fc = min(FC, a.F - f0);
-        __syncthreads();
         for (int q = tid; q < FC * TILE; q += 256) {
             const int f = q / TILE, k = q - f * TILE;
-            double vr = 0., vc = 0.;
-            if (f < fc) {
-                const long long ir = tr + k, ic = tc + k;
-                if (ir < a.r1) vr = __ldg(a.Xr + (long long)(f0 + f) * a.ldr + ir);
-                if (ic < a.c1) vc = __ldg(a.Xc + (long long)(f0 + f) * a.ldc + ic);
-            }
-            s_r[f][k] = vr;
-            s_c[f][k] = vc;
+            const long long ir = tr + k, ic = tc + k;
+            const bool fr = (f < fc) && (ir < a.r1), fcn = (f < fc) && (ic < a.c1);
+            const double* gr = a.Xr + (long long)(f0 + (f < fc ? f : 0)) * a.ldr + (fr ? ir : a.r0);
+            const double* gc = a.Xc + (long long)(f0 + (f < fc ? f : 0)) * a.ldc + (fcn ? ic : a.c0);
+            const unsigned dr = (unsigned)__cvta_generic_to_shared(&s_slab[buf][0][f][k]);
+            const unsigned dc = (unsigned)__cvta_generic_to_shared(&s_slab[buf][1][f][k]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dr), "l"(gr), "r"(fr ? 8 : 0));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dc), "l"(gc), "r"(fcn ? 8 : 0));
         }
-        if (tid < FC) {
-            s_w[tid] = tid < fc ? __ldg(a.fw + f0 + tid) : 0.;
-            s_e[tid] = tid < fc ? a.fend[f0 + tid] : 0;
-        }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;");
+    };
+    issue_slab(0, 0);
+    int buf = 0;
+    for (int f0 = 0; f0 < a.F; f0 += FC, buf ^= 1) {
+        const int fc = min(FC, a.F - f0);
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();  // slab `buf` complete for everyone; everyone is also done reading slab `buf^1`
+        if (f0 + FC < a.F) issue_slab(f0 + FC, buf ^ 1);
+        const unsigned emask = a.fmask[f0 / FC];
+        const double (*s_r)[TILE] = s_slab[buf][0];
+        const double (*s_c)[TILE] = s_slab[buf][1];
 #pragma unroll 4
         for (int f = 0; f < fc; f++) {
             double xr[TT], xc[TT];
@@ -183,8 +189,8 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
             for (int i = 0; i < TT; i++)
 #pragma unroll
                 for (int j = 0; j < TT; j++) accg[i][j] += fabs(xr[i] - xc[j]);
-            if (s_e[f]) {  // group closes: mat_elements += weight * distance_func(...)
-                const double w = s_w[f];
+            if ((emask >> f) & 1u) {  // group closes: mat_elements += weight * distance_func(...)
+                const double w = __ldg(a.fw + f0 + f);
 #pragma unroll
                 for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -196,12 +202,15 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
         }
         if (MODE != TM_MATERIALIZE && a.early_exit && f0 + FC < a.F) {
             bool alive = false;
-            const double w = s_w[fc - 1];  // weight of the group still open (if any)
+            const double w = __ldg(a.fw + f0 + fc - 1);  // weight of the group still open (if any)
 #pragma unroll
             for (int i = 0; i < TT; i++)
 #pragma unroll
                 for (int j = 0; j < TT; j++) alive |= (fma(w, accg[i][j], acc[i][j]) < a.eps);
-            if (!__syncthreads_or(alive)) return;  // no pair of this tile can still fall below eps
+            if (!__syncthreads_or(alive)) {  // no pair of this tile can still fall below eps
+                asm volatile("cp.async.wait_group 0;");  // do not leave the prefetch in flight
+                return;
+            }
         }
     }
 
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
     if (MODE == TM_MATERIALIZE) {
         // Stage the tile in shared memory (reusing the feature slabs: 2 x 16 x 64 doubles = one 64 x 32 half
         // at a time) so that BOTH D[tile] and its mirror D[tile]^T leave as 512-byte coalesced rows.
-        double* s_t = &s_r[0][0];  // 32 x 64 doubles = 16 KB (s_r and s_c are contiguous)
+        double* s_t = &s_slab[0][0][0][0];  // 32 x 64 doubles = 16 KB (one buffer: both sides are contiguous)
         static_assert(2 * FC == 32, "staging buffer is 32 x 64 doubles");
         const bool diag = a.symmetric && (tc == tr);
 #pragma unroll
