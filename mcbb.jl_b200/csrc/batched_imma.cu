@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "fixedpoint.cuh"
 #include "lane_core.cuh"
 
 namespace mcbb {
@@ -44,32 +45,6 @@ struct ImmaArgs {
     SolveIO io;
     double* acc;  // [grid][3][N][B]  mean, M2, cyclic offset (L2-resident scratch)
 };
-
-__device__ __forceinline__ void sincos_fast2(const double x, double* s, double* c) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    const double qd = fma(x, 0.6366197723675814, magic);
-    const int q = __double2loint(qd);
-    const double qf = qd - magic;
-    double r = fma(-qf, 1.5707963267948966, x);
-    r = fma(-qf, 6.123233995736766e-17, r);
-    const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    const double sr = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-    const double a = (q & 1) ? cr : sr;
-    const double b = (q & 1) ? sr : cr;
-    *s = (q & 2) ? -a : a;
-    *c = ((q + 1) & 2) ? -b : b;
-}
 
 struct ImSlotCtl {
     long long run, iter, nrej, natt;
@@ -222,6 +197,7 @@ __device__ __forceinline__ void solve_batched_imma_body(const ImmaArgs& a) {
                     c.nrej = 0;
                     c.natt = 0;
                     c.qold = o.qoldinit;
+                    c.dt0 = 0.;  // multiplies a zero stage sum in the first evaluation: must be finite
                     c.isave = 0;
                     c.ret = 0;
                     c.mode = MODE_INIT;

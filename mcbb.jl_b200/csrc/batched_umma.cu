@@ -1,0 +1,691 @@
+// batched_umma.cu — ensemble Tsit5 for kuramoto_network (src/systems.jl:119-130) with a unit-weight adjacency,
+// coupling sums on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in tensor memory),
+// statistics of eval_ode_run (mean / std, eval_mc_prob.jl:191-198) fused into the step.
+//
+// Same exact fixed-point algorithm as batched_imma.cu (see fixedpoint.cuh): per right-hand-side evaluation
+//        P = A sin(Y),  Q = A cos(Y)          A: N x N in {0,1},  sin/cos(Y): N x JB
+// with sin/cos written as u = round(x 2^50) + 2^51 and split into radix-256 digits.  What changes is the
+// machine mapping, which is built around tcgen05 instead of mma.sync:
+//
+//   * D[128 x 16 JB] (s32, TMEM) = A[128 x 128] (u8, K-major) * B[128 x 16 JB] (u8, MN-major, no swizzle).
+//     In the MN-major canonical layout the 16 columns of one trajectory are 16 CONTIGUOUS bytes per oscillator
+//     row, and the digits of (sin, cos) are simply the little-endian bytes of the two 64-bit integers
+//     {u_sin, u_cos}: the producer writes its element with ONE 16-byte shared-memory store, no byte shuffles.
+//   * one thread per oscillator row (thread r <-> TMEM lane r, tcgen05.ld 32x32b): the thread that produced
+//     sin/cos of element (r, j) is the one that reads row r of P, Q back, so sin/cos and the Welford state stay
+//     in registers and every Runge-Kutta stage vector is thread-private shared memory.  Element ownership
+//     never changes => 8 CTA barriers per step (6 stage hand-offs to the MMA, 2 around the step controller)
+//     instead of 19 in the mma.sync kernel.
+//   * the MMA is asynchronous (one elected thread issues, completion arrives on an mbarrier); several CTAs per
+//     SM keep the FP64 pipe busy while another CTA's MMA round trip (~450 clocks measured,
+//     profiles/microbench/umma_probe.cu) is in flight.
+//
+// Descriptor encodings were pinned bit-exactly on hardware with profiles/microbench/umma_probe.cu.
+#include <algorithm>
+#include <vector>
+
+#include "fixedpoint.cuh"
+#include "lane_core.cuh"
+
+namespace mcbb {
+
+constexpr int UM_NSLOT = 8;  // u, k1..k7
+constexpr int UM_MAXS = 2;   // save times per accepted step whose interpolation weights the controller precomputes
+constexpr int UM_A_BYTES = 128 * 128;
+
+struct UmmaArgs {
+    int N, KS, n_sms;
+    const unsigned char* a_img;  // [16384] A in its shared-memory (canonical K-major, no swizzle) layout
+    const int* deg;              // [128] number of non-zero couplings per row
+    const double* bias;          // [128]
+    const int* filter_pos;       // [128]
+    double unit_weight;
+    double scalars[MCBB_N_SCALARS];
+    int n_par;
+    int par_slot[MCBB_MAX_PAR];
+    SolverDev o;
+    int n_meas, meas[MCBB_MAX_MEAS], n_filter, cyclic;
+    SolveIO io;
+};
+
+struct UmSlotCtl {
+    long long run, fin_run, iter, nrej, natt;
+    double t, dt, dts, qold, al1s, d0, d1, dt0, t_old, dts_old;
+    double hstep;  // step of the stage inputs: dts while running, the probe step dt0 while measuring the initial dt
+    double bth[UM_MAXS][7];
+    int mode, isave, ret, clipped, accept, fresh, fin, fin_ok, s0, s1;
+};
+
+// ---- tcgen05 / mbarrier plumbing (PTX ISA 8.7, sm_100a) ------------------------------------------------------
+__device__ __forceinline__ unsigned um_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets in 16-byte units
+__device__ __forceinline__ unsigned long long um_desc(const unsigned addr, const unsigned lbo, const unsigned sbo) {
+    return (unsigned long long)((addr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void um_mma_i8(const unsigned d_tmem, const unsigned long long da, const unsigned long long db,
+                                          const unsigned idesc, const unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void um_commit(const unsigned mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void um_mbar_wait(const unsigned mbar, const unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ void um_tmem_ld16(const unsigned taddr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"  // same statement: the registers are valid when it retires
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+// tensor-memory allocation: power of two >= 32 columns
+template <int JB>
+struct UmCols {
+    static constexpr unsigned value = 16 * JB <= 32 ? 32u : 16 * JB <= 64 ? 64u : 16 * JB <= 128 ? 128u : 256u;
+};
+
+// warp-level sum with a fixed tree (deterministic)
+__device__ __forceinline__ double um_warp_sum(double p) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+    return p;
+}
+
+// G independent sincos chains written side by side so that the scheduler interleaves them (one basic block)
+template <int G>
+__device__ __forceinline__ void um_sincos_vec(const double (&x)[G], double* s, double* c) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+        const double qd = fma(x[i], 0.6366197723675814, magic);
+        const int q = __double2loint(qd);
+        const double qf = qd - magic;
+        double r = fma(-qf, 1.5707963267948966, x[i]);
+        r = fma(-qf, 6.123233995736766e-17, r);
+        const double z = r * r;
+        double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+        ps = fma(z, ps, 2.75573137070700676789e-06);
+        ps = fma(z, ps, -1.98412698298579493134e-04);
+        ps = fma(z, ps, 8.33333333332248946124e-03);
+        ps = fma(z, ps, -1.66666666666666324348e-01);
+        const double sr = fma(z * r, ps, r);
+        double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+        pc = fma(z, pc, -2.75573143513906633035e-07);
+        pc = fma(z, pc, 2.48015872894767294178e-05);
+        pc = fma(z, pc, -1.38888888888741095749e-03);
+        pc = fma(z, pc, 4.16666666666666019037e-02);
+        const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+        const double a = (q & 1) ? cr : sr;
+        const double b = (q & 1) ? sr : cr;
+        // quadrant signs on the integer pipe (the FP64 pipe is the scarce one)
+        s[i] = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
+        c[i] = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
+    }
+}
+
+// a / b for normal, well-scaled b without the compiler's slow-path branch: reciprocal seed, two Newton steps,
+// one residual correction (used only inside the step-size error norm)
+__device__ __forceinline__ double um_div(const double a, const double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+
+template <int JB, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int N = a.N;
+    const int row = tid;
+    const bool valid = row < N;
+    const int rr = valid ? row : N - 1;  // clamped: idle rows read (never write) the last oscillator's data
+    const SolverDev& o = a.o;
+    const int n_t = a.io.n_t;
+    const long long n_mc = a.io.n_mc;
+    constexpr unsigned NCOL = 16 * JB;            // MMA N: 16 accumulator columns per trajectory (7 + 7 digits, 2 zero)
+    constexpr int G = JB <= 4 ? JB : (JB % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved
+    constexpr int RS = UM_NSLOT * JB + 1;         // odd row stride (doubles): conflict-free thread-private blocks
+    static_assert(JB % G == 0, "batch must be a multiple of the interleave group");
+
+    unsigned char* sA = smem;                                   // [16384]
+    unsigned char* sB = smem + UM_A_BYTES;                      // [JB][128][16]
+    double* sm_k = (double*)(sB + JB * 2048);                   // [N][8 JB + 1]  u, k1..k7 of the row's JB elements
+    double* sm_ts = sm_k + (((size_t)N * RS + 1) & ~(size_t)1);               // [n_t]
+    double* sm_red0 = sm_ts + ((n_t + 1) & ~1);                 // [4][JB]
+    double* sm_red1 = sm_red0 + 4 * JB;                         // [4][JB]
+    UmSlotCtl* ctl = (UmSlotCtl*)(sm_red1 + 4 * JB);            // [JB]
+    unsigned long long* mbar_p = (unsigned long long*)(ctl + JB);
+    unsigned* tmem_slot = (unsigned*)(mbar_p + 1);
+    const unsigned mbar = um_smem_u32(mbar_p);
+    double* const kb = sm_k + (size_t)rr * RS;
+
+#define KP(slot, j) kb[(slot)*JB + (j)]
+
+    for (int i = tid; i < UM_A_BYTES / 16; i += 128) ((uint4*)sA)[i] = ((const uint4*)a.a_img)[i];
+    for (int i = tid; i < JB * 2048 / 16; i += 128) ((uint4*)sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < N * RS; i += 128) sm_k[i] = 0.;  // stage slots are read before written (x 0)
+    for (int i = tid; i < n_t; i += 128) sm_ts[i] = a.io.t_save[i];
+    // the controller lanes sit in a different warp (scheduler partition) for each CTA resident on an SM
+    const int cw = (blockIdx.x / a.n_sms) & 3;
+    const bool is_ctl = (wid == cw) && lane < JB;
+    if (is_ctl) {
+        UmSlotCtl& c = ctl[lane];
+        c.mode = MODE_FETCH;
+        c.accept = c.fresh = c.fin = 0;
+        c.hstep = 0.;
+        c.dts = 0.;
+        c.al1s = 0.;
+    }
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)),
+                     "n"(UmCols<JB>::value));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A image and zeros -> visible to the MMA's proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+    const unsigned tmem_row = tmem_base + ((unsigned)(32 * wid) << 16);  // this warp's 32 TMEM lanes
+
+    // MMA operands: A K-major (8-row groups 1024 B apart, the two 16-byte K chunks of an MMA 128 B apart, next
+    // K step + 256 B); B MN-major (16-column chunks 2048 B apart, 8-deep K groups 128 B apart, next K step + 512 B)
+    const unsigned idesc = (2u << 4) /* D s32 */ | (0u << 7) /* A u8 */ | (0u << 10) /* B u8 */ | (0u << 15) /* A K-major */ |
+                           (1u << 16) /* B MN-major */ | ((NCOL >> 3) << 17) | ((128u >> 4) << 24);
+    const unsigned sA_addr = um_smem_u32(sA), sB_addr = um_smem_u32(sB);
+    const int KSTEPS = a.KS;
+    unsigned char* const sB_row = sB + row * 16;
+
+    const double bias = a.bias[row];
+    const long long deg51 = (long long)a.deg[row] << 51;
+    const int fpos = a.filter_pos[row];
+    unsigned phase = 0;
+
+    // thread-private state of the JB elements of this oscillator row
+    double sv[JB], cv[JB], un[JB], am[JB], a2[JB], as[JB];
+#pragma unroll
+    for (int j = 0; j < JB; j++) sv[j] = cv[j] = un[j] = am[j] = a2[j] = as[j] = 0.;
+
+    auto begin_attempt = [&](UmSlotCtl& c) -> bool {
+        if (++c.iter > o.maxiters) {
+            c.ret = MCBB_RET_MAXITERS;
+            return false;
+        }
+        c.dts = c.dt;
+        c.clipped = 0;
+        if (c.dts >= o.t1 - c.t) {
+            c.dts = o.t1 - c.t;
+            c.clipped = 1;
+        }
+        if (!c.clipped && c.dts <= o.dtmin) {
+            c.ret = MCBB_RET_DTLESSTHANMIN;
+            return false;
+        }
+        c.hstep = c.dts;
+        return true;
+    };
+
+    for (;;) {
+        // ---- per-trajectory control: PI controller, accept / reject, save window, finish, refill -----------------
+        if (is_ctl) {
+            UmSlotCtl& c = ctl[lane];
+            c.accept = 0;
+            c.fin = 0;
+            c.fresh = 0;
+            int finished = 0;
+            if (c.mode == MODE_INIT) {
+                c.mode = MODE_RUN;
+                if (!begin_attempt(c)) finished = 1;
+            } else if (c.mode == MODE_RUN) {
+                c.natt++;
+                double e2 = 0., nb = 0.;
+                for (int w = 0; w < 4; w++) {
+                    e2 += sm_red0[w * JB + lane];
+                    nb += sm_red1[w * JB + lane];
+                }
+                const double EEst = sqrt(e2 / N);
+                double q, q11 = 0.;
+                if (EEst == 0.) {
+                    q = 1. / o.qmax;
+                } else {
+                    q11 = pow(EEst, o.beta1);
+                    q = q11 / pow(c.qold, o.beta2);
+                    q = fmax(1. / o.qmax, fmin(1. / o.qmin, q / o.gamma));
+                }
+                if (!(EEst > 1.)) {
+                    c.qold = fmax(EEst, o.qoldinit);
+                    const double tnew = c.clipped ? o.t1 : c.t + c.dts;
+                    int k1 = c.isave;
+                    while (k1 < n_t && sm_ts[k1] <= tnew) k1++;
+                    c.s0 = c.isave;
+                    c.s1 = k1;
+                    c.isave = k1;
+                    c.t_old = c.t;
+                    c.dts_old = c.dts;
+                    {  // dense-output weights of the first save times in the window (shared by all 128 rows)
+                        const int ks0 = c.s0 < 1 ? 1 : c.s0;
+                        for (int q2 = 0; q2 < UM_MAXS && ks0 + q2 < k1; q2++)
+                            tsit5_btheta((sm_ts[ks0 + q2] - c.t) / c.dts, c.bth[q2]);
+                    }
+                    c.t = tnew;
+                    c.dt = fmin(o.dtmax, fmax(o.dtmin, c.dts / q));
+                    c.accept = 1;
+                    if (nb > 0.) c.ret = MCBB_RET_UNSTABLE;  // NaN in the new state
+                } else {
+                    c.nrej++;
+                    c.dt = c.dts / fmin(1. / o.qmin, q11 / o.gamma);
+                }
+                if (c.ret != 0 || (c.accept && !(c.t < o.t1)))
+                    finished = 1;
+                else if (!begin_attempt(c))
+                    finished = 1;
+            }
+            if (finished) {
+                c.fin = 1;
+                c.fin_run = c.run;
+                c.fin_ok = (c.ret == 0) && c.isave >= n_t;
+                if (a.io.retcode) a.io.retcode[c.run] = c.ret;
+                if (a.io.nsteps) {
+                    a.io.nsteps[c.run] = c.natt;
+                    a.io.nsteps[n_mc + c.run] = c.nrej;
+                }
+                c.mode = MODE_FETCH;
+            }
+            if (c.mode == MODE_FETCH) {
+                const long long run = (long long)atomicAdd(a.io.work_counter, 1ULL);
+                if (run >= n_mc) {
+                    c.mode = MODE_DONE;
+                } else {
+                    double sc[MCBB_N_SCALARS];
+                    for (int q = 0; q < MCBB_N_SCALARS; q++) sc[q] = a.scalars[q];
+                    for (int p = 0; p < a.n_par; p++) sc[a.par_slot[p]] = a.io.par[(long long)p * n_mc + run];
+                    // K/N (systems.jl:128) times the coupling value, times the 2^-50 of the fixed-point sums
+                    c.al1s = ((sc[0] / (double)N) * a.unit_weight) * 8.881784197001252e-16;
+                    c.run = run;
+                    c.t = o.t0;
+                    c.iter = 0;
+                    c.nrej = 0;
+                    c.natt = 0;
+                    c.qold = o.qoldinit;
+                    c.hstep = 0.;
+                    c.isave = 0;
+                    c.ret = 0;
+                    c.mode = MODE_INIT;
+                    c.fresh = 1;
+                }
+            }
+        }
+        const bool all_done = __syncthreads_and(!is_ctl || ctl[lane].mode == MODE_DONE);
+
+        // ---- row owners: samples of the accepted step, u <- u_new, results of finished runs, new initial state ----
+        bool any_init = false;
+#pragma unroll
+        for (int j = 0; j < JB; j++) {
+            const UmSlotCtl& c = ctl[j];
+            if (c.accept) {
+                const int ks0 = c.s0 < 1 ? 1 : c.s0, ks1 = c.s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
+                if (valid) {
+                    if (ks0 < ks1) {
+                        const double dts = c.dts_old, t_old = c.t_old;
+                        double kk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) kk[q] = KP(q, j);
+                        for (int k = ks0; k < ks1; k++) {
+                            double bth[7];
+                            if (k - ks0 < UM_MAXS) {
+#pragma unroll
+                                for (int q = 0; q < 7; q++) bth[q] = c.bth[k - ks0][q];
+                            } else {
+                                tsit5_btheta((sm_ts[k] - t_old) / dts, bth);
+                            }
+                            double lin = kk[1] * bth[0];
+#pragma unroll
+                            for (int q = 1; q < 7; q++) lin = fma(kk[1 + q], bth[q], lin);
+                            double x = fma(dts, lin, kk[0]);
+                            if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
+                                if (k == 1) {
+                                    const double twopi = 6.283185307179586, pi = 3.141592653589793;
+                                    double vv = julia_mod_pos(x, twopi);
+                                    if (vv > pi) vv -= twopi;
+                                    as[j] = x - vv;
+                                    x = vv;
+                                } else {
+                                    x = x - as[j];
+                                }
+                            }
+                            const double delta = x - am[j];
+                            if (fabs(delta) <= 1.7976931348623157e308) {
+                                const double mnew = fma(delta, 1. / (double)k, am[j]);
+                                a2[j] = fma(delta, x - mnew, a2[j]);
+                                am[j] = mnew;
+                            } else {
+                                am[j] = nonfinite_mean(am[j], x);
+                                a2[j] = nan("");
+                            }
+                        }
+                    }
+                    KP(0, j) = un[j];
+                    KP(1, j) = KP(7, j);  // FSAL
+                }
+            }
+            if (c.fin && valid && fpos >= 0) {
+                const bool ok = c.fin_ok != 0;
+                const double mean = ok ? am[j] : nan("");
+                const double sd = ok ? sqrt((a2[j] < 0. ? 0. : a2[j]) / (double)(n_t - 2)) : nan("");
+                for (int m = 0; m < a.n_meas; m++)
+                    a.io.feat[((long long)m * a.n_filter + fpos) * n_mc + c.fin_run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
+            }
+            if (c.fresh) {
+                if (valid) {
+                    KP(0, j) = a.io.ic[(long long)row * n_mc + c.run];
+#pragma unroll
+                    for (int q = 1; q < UM_NSLOT; q++) KP(q, j) = 0.;  // no stale values from the slot's previous run
+                }
+                am[j] = a2[j] = as[j] = 0.;
+            }
+            any_init |= (c.mode == MODE_INIT);
+        }
+        if (all_done) break;
+
+        // ---- one round: 6 right-hand-side evaluations of the whole batch -----------------------------------------
+        // Everything below is written without per-trajectory branches: slots that are idle or still measuring their
+        // initial step compute harmlessly on their own columns (their stage slots k2..k7 are zero), so that the G
+        // dependent chains of a group sit in one basic block and hide each other's latency.
+#pragma unroll 1
+        for (int s = 0; s < 6; s++) {
+            double cs[6];  // stage coefficients with zeros beyond the current stage
+#pragma unroll
+            for (int q = 0; q < 6; q++) cs[q] = (q <= s) ? TS_A(s, q) : 0.;
+            const double ci0 = (s == 1) ? 1. : 0.;  // initial-dt probe: u0 + dt0 f(u0) in the second evaluation
+            // (a) stage input Y -> sin, cos -> the 16 digit bytes of this (row, trajectory) element
+#pragma unroll
+            for (int g0 = 0; g0 < JB; g0 += G) {
+                double y[G];
+#pragma unroll
+                for (int i = 0; i < G; i++) {
+                    const int j = g0 + i;
+                    const double c0 = (ctl[j].mode == MODE_RUN) ? cs[0] : ci0;
+                    double lin = c0 * KP(1, j);
+#pragma unroll
+                    for (int q = 1; q < 6; q++) lin = fma(cs[q], KP(1 + q, j), lin);
+                    y[i] = fma(ctl[j].hstep, lin, KP(0, j));
+                }
+                um_sincos_vec<G>(y, &sv[g0], &cv[g0]);
+#pragma unroll
+                for (int i = 0; i < G; i++) {
+                    uint4 dg;
+                    fixed52(sv[g0 + i], dg.x, dg.y);
+                    fixed52(cv[g0 + i], dg.z, dg.w);
+                    if (valid) *reinterpret_cast<uint4*>(sB_row + (g0 + i) * 2048) = dg;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            // (b) D = A * digits on the tensor core; one thread issues, completion arrives on the mbarrier
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int ks = 0; ks < KSTEPS; ks++)
+                    um_mma_i8(tmem_base, um_desc(sA_addr + ks * 256, 128, 1024), um_desc(sB_addr + ks * 512, 128, 2048), idesc,
+                              ks > 0 ? 1u : 0u);
+                um_commit(mbar);
+            }
+            um_mbar_wait(mbar, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // (c) row r of P, Q from tensor memory, int64 recombination, k = a1 (c P - s Q) + w
+            double kv[JB];
+            double* const kst = kb + (2 + s) * JB;
+#pragma unroll
+            for (int j = 0; j < JB; j++) {
+                unsigned v[16];
+                um_tmem_ld16(tmem_row + 16u * j, v);
+                const double P = (double)(recombine7(v[0], v[1], v[2], v[3], v[4], v[5], v[6]) - deg51);
+                const double Q = (double)(recombine7(v[8], v[9], v[10], v[11], v[12], v[13], v[14]) - deg51);
+                kv[j] = fma(ctl[j].al1s, cv[j] * P - sv[j] * Q, bias);
+                if (valid && ctl[j].mode == MODE_RUN) kst[j] = kv[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads done before the next MMA
+            if (any_init && s < 2) {  // initial step size (OrdinaryDiffEq initdt.jl), only in rounds that start a run
+#pragma unroll
+                for (int j = 0; j < JB; j++) {
+                    if (ctl[j].mode == MODE_INIT) {
+                        double p0 = 0., p1 = 0.;
+                        if (valid) {
+                            const double u0 = KP(0, j);
+                            const double sk = o.abstol + fabs(u0) * o.reltol;
+                            if (s == 0) {
+                                KP(1, j) = kv[j];
+                                const double w0 = u0 / sk, w1 = kv[j] / sk;
+                                p0 = w0 * w0;
+                                p1 = w1 * w1;
+                            } else {
+                                const double vv = (kv[j] - KP(1, j)) / sk;
+                                p0 = vv * vv;
+                            }
+                        }
+                        p0 = um_warp_sum(p0);
+                        p1 = um_warp_sum(p1);
+                        if (lane == 0) {
+                            sm_red0[wid * JB + j] = p0;
+                            sm_red1[wid * JB + j] = p1;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (is_ctl && ctl[lane].mode == MODE_INIT) {
+                    UmSlotCtl& c = ctl[lane];
+                    double r0 = 0., r1 = 0.;
+                    for (int w = 0; w < 4; w++) {
+                        r0 += sm_red0[w * JB + lane];
+                        r1 += sm_red1[w * JB + lane];
+                    }
+                    if (o.dt_user > 0) {
+                        c.dt = o.dt_user;
+                        c.dt0 = 0.;
+                    } else if (s == 0) {
+                        c.d0 = sqrt(r0 / N);
+                        c.d1 = sqrt(r1 / N);
+                        const double dt0 = (c.d0 < 1e-5 || c.d1 < 1e-5) ? 1e-6 : 0.01 * (c.d0 / c.d1);
+                        c.dt0 = fmin(dt0, o.dtmax);
+                    } else {
+                        const double d2 = sqrt(r0 / N) / c.dt0;
+                        const double dm = fmax(c.d1, d2);
+                        const double dt1 = (dm <= 1e-15) ? fmax(1e-6, c.dt0 * 1e-3) : pow(10., -(2. + log10(dm)) / 5.);
+                        c.dt = fmin(fmin(100. * c.dt0, dt1), o.dtmax);
+                    }
+                    c.hstep = c.dt0;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- error estimate partials and the candidate new state (branch-free; the controller ignores idle slots) ---
+        {
+            double pe[JB];
+            bool bad[JB];
+#pragma unroll
+            for (int j = 0; j < JB; j++) {
+                const double dts = ctl[j].dts;
+                const double k1 = KP(1, j);
+                double lin = TS_BT(0) * k1;
+                double lu = TS_A(5, 0) * k1;
+#pragma unroll
+                for (int q = 1; q < 7; q++) {
+                    const double kq = KP(1 + q, j);
+                    lin = fma(TS_BT(q), kq, lin);
+                    if (q < 6) lu = fma(TS_A(5, q), kq, lu);
+                }
+                const double u0 = KP(0, j);
+                const double u1 = fma(dts, lu, u0);
+                const double r = um_div(dts * lin, o.abstol + fmax(fabs(u0), fabs(u1)) * o.reltol);
+                pe[j] = valid ? r * r : 0.;
+                un[j] = u1;
+                bad[j] = valid && (u1 != u1);
+            }
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1)
+#pragma unroll
+                for (int j = 0; j < JB; j++) pe[j] += __shfl_xor_sync(0xffffffffu, pe[j], off);
+#pragma unroll
+            for (int j = 0; j < JB; j++) {
+                const bool anybad = __any_sync(0xffffffffu, bad[j]);
+                if (lane == 0) {
+                    sm_red0[wid * JB + j] = pe[j];
+                    sm_red1[wid * JB + j] = anybad ? 1. : 0.;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#undef KP
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
+}
+
+template <int JB, int MINB>
+static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_umma<JB, MINB><<<grid, 128, smem, st>>>(a);
+    MCBB_LAUNCHED();
+    return 0;
+}
+
+static size_t umma_smem_bytes(int JB, int N, int n_t) {
+    return (size_t)UM_A_BYTES + (size_t)JB * 2048 + sizeof(double) * ((size_t)N * (UM_NSLOT * JB + 1) + 1 + ((n_t + 1) & ~1) + 8 * (size_t)JB) +
+           sizeof(UmSlotCtl) * (size_t)JB + 16 + 128;
+}
+
+// Returns handled = true when the problem was run on the tcgen05 path.
+int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                        const SolveIO& io, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const int N = S.n_osc;
+    if (S.system != MCBB_SYS_KURAMOTO_NETWORK || hs == nullptr) return 0;
+    if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1 || F.matrix_meas) return 0;
+    if (N < 33 || N > 128) return 0;  // one 128-row MMA tile; small networks stay on the mma.sync kernel
+    if (getenv("MCBB_NO_IMMA") || getenv("MCBB_NO_UMMA")) return 0;
+    for (int m = 0; m < F.n_meas; m++)
+        if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
+    double uw = 0.;  // unit-weight adjacency?
+    for (size_t q = 0; q < (size_t)N * N; q++) {
+        const double v = hs->mat_a[q];
+        if (v != 0.) {
+            if (uw == 0.) uw = v;
+            if (v != uw) return 0;  // weighted couplings: the FP64 kernel (batched.cu) handles them
+        }
+    }
+    if (uw == 0.) uw = 1.;
+
+    UmmaArgs a = {};
+    a.N = N;
+    a.KS = (N + 31) / 32;
+    a.unit_weight = uw;
+    std::vector<unsigned char> img(UM_A_BYTES, 0);
+    std::vector<int> deg(128, 0);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+            if (hs->mat_a[i + (size_t)N * j] != 0.) {
+                img[(i >> 3) * 1024 + (j >> 4) * 128 + (i & 7) * 16 + (j & 15)] = 1;
+                deg[i]++;
+            }
+    std::vector<double> bias(128, 0.);
+    for (int i = 0; i < N; i++) bias[i] = hs->vec_a[i];
+    std::vector<int> fpos(128, -1);
+    if (F.filter) {
+        std::vector<int> fh(F.n_filter);
+        MCBB_CUDA_OK(cudaMemcpyAsync(fh.data(), F.filter, sizeof(int) * F.n_filter, cudaMemcpyDeviceToHost, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));
+        for (int ii = 0; ii < F.n_filter; ii++) fpos[fh[ii] - 1] = ii;
+    } else {
+        for (int i = 0; i < N; i++) fpos[i] = i;
+    }
+    unsigned char* d_img = (unsigned char*)scratch_get(59, img.size());
+    int* d_deg = (int*)scratch_get(60, sizeof(int) * deg.size());
+    double* d_bias = (double*)scratch_get(61, sizeof(double) * bias.size());
+    int* d_fpos = (int*)scratch_get(62, sizeof(int) * fpos.size());
+    if (!d_img || !d_deg || !d_bias || !d_fpos) MCBB_FAIL("solve: device allocation failed");
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_img, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_deg, deg.data(), sizeof(int) * deg.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_bias, bias.data(), sizeof(double) * bias.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_fpos, fpos.data(), sizeof(int) * fpos.size(), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    a.a_img = d_img;
+    a.deg = d_deg;
+    a.bias = d_bias;
+    a.filter_pos = d_fpos;
+    for (int q = 0; q < MCBB_N_SCALARS; q++) a.scalars[q] = S.scalars[q];
+    a.n_par = S.n_par;
+    for (int p = 0; p < MCBB_MAX_PAR; p++) a.par_slot[p] = S.par_slot[p];
+    a.o = o;
+    a.n_meas = F.n_meas;
+    for (int m = 0; m < F.n_meas; m++) a.meas[m] = F.meas[m];
+    a.n_filter = F.n_filter;
+    a.cyclic = F.cyclic;
+    a.io = io;
+
+    // configurations (trajectories per CTA, CTAs per SM): TMEM columns and shared memory both have to fit
+    struct Cfg { int jb, per_sm; };
+    static const Cfg cfgs[] = {{4, 4}, {6, 3}, {8, 2}, {4, 3}, {4, 2}, {2, 2}, {2, 1}};  // measured on C5: 372k, 360k, 307k traj/s
+    int want_jb = getenv("MCBB_UMMA_JB") ? atoi(getenv("MCBB_UMMA_JB")) : 0;
+    int want_per = getenv("MCBB_UMMA_PER_SM") ? atoi(getenv("MCBB_UMMA_PER_SM")) : 0;
+    const Cfg* pick = nullptr;
+    for (const Cfg& c : cfgs) {
+        if (want_jb && c.jb != want_jb) continue;
+        if (want_per && c.per_sm != want_per) continue;
+        const size_t need = umma_smem_bytes(c.jb, N, io.n_t);
+        if ((need + 1024) * c.per_sm <= (size_t)227 * 1024 && need <= (size_t)226 * 1024) {
+            pick = &c;
+            break;
+        }
+    }
+    if (!pick) return 0;
+    const size_t smem = umma_smem_bytes(pick->jb, N, io.n_t);
+    int dev = 0, sms = 148;
+    MCBB_CUDA_OK(cudaGetDevice(&dev));
+    MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    a.n_sms = sms;
+    const long long want = (io.n_mc + pick->jb - 1) / pick->jb;
+    const int grid = (int)std::min<long long>(want, (long long)sms * pick->per_sm);
+    MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
+    int rc = 1;
+    if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3>(a, smem, grid, st);
+    else if (pick->jb == 4 && pick->per_sm == 4) rc = launch_umma_spec<4, 4>(a, smem, grid, st);
+    else if (pick->jb == 8 && pick->per_sm == 2) rc = launch_umma_spec<8, 2>(a, smem, grid, st);
+    else if (pick->jb == 4 && pick->per_sm == 3) rc = launch_umma_spec<4, 3>(a, smem, grid, st);
+    else if (pick->jb == 4 && pick->per_sm == 2) rc = launch_umma_spec<4, 2>(a, smem, grid, st);
+    else if (pick->jb == 2 && pick->per_sm == 2) rc = launch_umma_spec<2, 2>(a, smem, grid, st);
+    else if (pick->jb == 2 && pick->per_sm == 1) rc = launch_umma_spec<2, 1>(a, smem, grid, st);
+    if (rc) return rc;
+    *handled = true;
+    return 0;
+}
+
+}  // namespace mcbb

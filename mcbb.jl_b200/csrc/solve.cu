@@ -297,6 +297,8 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
     return 0;
 }
 
+int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                        const SolveIO& io, cudaStream_t st, bool* handled);
 int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
                         const SolveIO& io, cudaStream_t st, bool* handled);
 int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
@@ -314,6 +316,8 @@ int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const Sol
     if (!(o.t1 > o.t0)) MCBB_FAIL("tspan must be increasing");
     if (io.n_t < 2) MCBB_FAIL("need at least two save times (the first saved sample is dropped)");
     bool handled = false;
+    if (int rc = launch_batched_umma(hs, S, o, F, io, st, &handled)) return rc;  // tcgen05 + tensor memory
+    if (handled) return 0;
     if (int rc = launch_batched_imma(hs, S, o, F, io, st, &handled)) return rc;
     if (handled) return 0;
     if (int rc = launch_batched_kuramoto(hs, S, o, F, io, st, &handled)) return rc;
