@@ -22,6 +22,7 @@
 //
 // Descriptor encodings were pinned bit-exactly on hardware with profiles/microbench/umma_probe.cu.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "fixedpoint.cuh"
@@ -30,11 +31,11 @@
 namespace mcbb {
 
 constexpr int UM_NSLOT = 8;  // u, k1..k7
-constexpr int UM_MAXS = 2;   // save times per accepted step whose interpolation weights the controller precomputes
 constexpr int UM_A_BYTES = 128 * 128;
 
 struct UmmaArgs {
     int N, KS, n_sms;
+    double inv_n, ln_qoldinit;
     const unsigned char* a_img;  // [16384] A in its shared-memory (canonical K-major, no swizzle) layout
     const int* deg;              // [128] number of non-zero couplings per row
     const double* bias;          // [128]
@@ -50,9 +51,8 @@ struct UmmaArgs {
 
 struct UmSlotCtl {
     long long run, fin_run, iter, nrej, natt;
-    double t, dt, dts, qold, al1s, d0, d1, dt0, t_old, dts_old;
+    double t, dt, dts, lq, al1s, d0, d1, dt0, t_old, dts_old;  // lq = ln(qold) of the PI controller
     double hstep;  // step of the stage inputs: dts while running, the probe step dt0 while measuring the initial dt
-    double bth[UM_MAXS][7];
     int mode, isave, ret, clipped, accept, fresh, fin, fin_ok, s0, s1;
 };
 
@@ -82,9 +82,9 @@ __device__ __forceinline__ void um_mbar_wait(const unsigned mbar, const unsigned
     unsigned done = 0;
     while (!done) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(mbar), "r"(parity)
+            : "r"(mbar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware until the phase flips
             : "memory");
     }
 }
@@ -111,29 +111,43 @@ __device__ __forceinline__ double um_warp_sum(double p) {
     return p;
 }
 
-// G independent sincos chains written side by side so that the scheduler interleaves them (one basic block)
+// sincos / fixed-point constants live in the constant bank: DFMA takes them as c[bank][offset] operands, no
+// per-use immediate moves
+static __constant__ double c_um[20] = {
+    0.6366197723675814,       // 0  2/pi
+    6755399441055744.0,       // 1  1.5 * 2^52
+    1.5707963267948966,       // 2  pi/2 high
+    6.123233995736766e-17,    // 3  pi/2 low
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,                                       // 4..9  sin kernel
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02,                                       // 10..15 cos kernel
+    1125899906842624.0,       // 16 2^50
+    0., 0., 0.};
+
+// G independent sincos chains written side by side so that the scheduler interleaves them (one basic block);
+// same arithmetic as sincos_fast2 (fixedpoint.cuh)
 template <int G>
 __device__ __forceinline__ void um_sincos_vec(const double (&x)[G], double* s, double* c) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
 #pragma unroll
     for (int i = 0; i < G; i++) {
-        const double qd = fma(x[i], 0.6366197723675814, magic);
+        const double qd = fma(x[i], c_um[0], c_um[1]);
         const int q = __double2loint(qd);
-        const double qf = qd - magic;
-        double r = fma(-qf, 1.5707963267948966, x[i]);
-        r = fma(-qf, 6.123233995736766e-17, r);
+        const double qf = qd - c_um[1];
+        double r = fma(-qf, c_um[2], x[i]);
+        r = fma(-qf, c_um[3], r);
         const double z = r * r;
-        double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-        ps = fma(z, ps, 2.75573137070700676789e-06);
-        ps = fma(z, ps, -1.98412698298579493134e-04);
-        ps = fma(z, ps, 8.33333333332248946124e-03);
-        ps = fma(z, ps, -1.66666666666666324348e-01);
+        double ps = fma(z, c_um[4], c_um[5]);
+        ps = fma(z, ps, c_um[6]);
+        ps = fma(z, ps, c_um[7]);
+        ps = fma(z, ps, c_um[8]);
+        ps = fma(z, ps, c_um[9]);
         const double sr = fma(z * r, ps, r);
-        double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-        pc = fma(z, pc, -2.75573143513906633035e-07);
-        pc = fma(z, pc, 2.48015872894767294178e-05);
-        pc = fma(z, pc, -1.38888888888741095749e-03);
-        pc = fma(z, pc, 4.16666666666666019037e-02);
+        double pc = fma(z, c_um[10], c_um[11]);
+        pc = fma(z, pc, c_um[12]);
+        pc = fma(z, pc, c_um[13]);
+        pc = fma(z, pc, c_um[14]);
+        pc = fma(z, pc, c_um[15]);
         const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
         const double a = (q & 1) ? cr : sr;
         const double b = (q & 1) ? sr : cr;
@@ -141,6 +155,36 @@ __device__ __forceinline__ void um_sincos_vec(const double (&x)[G], double* s, d
         s[i] = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
         c[i] = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
     }
+}
+
+// Tsit5 dense-output weights b_q(theta) (OrdinaryDiffEq tsit_interpolants): b_0 = th (1 + th (A + th (B + th C))),
+// b_q = th^2 (A + th (B + th C)) for q = 1..6; lane q of a warp evaluates polynomial q
+static __constant__ double c_um_bth[7][3] = {
+    {-2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+    {0.13169999999999998, -0.2234, 0.1017},
+    {3.9302962368947516, -5.941033872131505, 2.490627285651253},
+    {-12.411077166933676, 30.33818863028232, -16.548102889244902},
+    {37.50931341651104, -88.1789048947664, 47.37952196281928},
+    {-27.896526289197286, 65.09189467479366, -34.87065786149661},
+    {1.5, -4., 2.5}};
+
+// x in [-1, 1] -> (low 32 bits, high 20 bits) of round(x 2^50) + 2^51, constants from the constant bank
+__device__ __forceinline__ void um_fixed52(const double x, unsigned& lo, unsigned& hi) {
+    const double t = fma(x, c_um[16], c_um[1]);
+    lo = (unsigned)__double2loint(t);
+    hi = (unsigned)__double2hiint(t) & 0xFFFFFu;
+}
+
+// sum_k v[k] 2^(8k) - deg 2^51 as a double (one rounding).  Digit sums are < 2^15 (<= 128 couplings of <= 255), so
+// three of them pack into 31 bits; one wide multiply-add joins the two packs, v6 and the degree only touch the
+// high word.  degh = deg << 19.
+__device__ __forceinline__ double um_recombine(const unsigned v0, const unsigned v1, const unsigned v2, const unsigned v3,
+                                               const unsigned v4, const unsigned v5, const unsigned v6, const int degh) {
+    const unsigned lo3 = v0 + (v1 << 8) + (v2 << 16);
+    const unsigned mid3 = v3 + (v4 << 8) + (v5 << 16);
+    const unsigned long long w = (unsigned long long)mid3 * 16777216ull + lo3;
+    const int hi = (int)(unsigned)(w >> 32) + ((int)(v6 << 16) - degh);
+    return (double)(long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)w);
 }
 
 // a / b for normal, well-scaled b without the compiler's slow-path branch: reciprocal seed, two Newton steps,
@@ -163,32 +207,34 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     const int N = a.N;
     const int row = tid;
     const bool valid = row < N;
-    const int rr = valid ? row : N - 1;  // clamped: idle rows read (never write) the last oscillator's data
+    const int rr = valid ? row : N;  // idle lanes (rows >= N of the MMA tile) work on a dummy row: no branches
     const SolverDev& o = a.o;
     const int n_t = a.io.n_t;
     const long long n_mc = a.io.n_mc;
     constexpr unsigned NCOL = 16 * JB;            // MMA N: 16 accumulator columns per trajectory (7 + 7 digits, 2 zero)
     constexpr int G = JB <= 4 ? JB : (JB % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved
-    constexpr int RS = UM_NSLOT * JB + 1;         // odd row stride (doubles): conflict-free thread-private blocks
+    constexpr int RS = UM_NSLOT * JB + 2;         // row stride (doubles) = 2 (mod 4): 16-byte aligned thread-private
+                                                  // blocks whose 128-bit accesses are bank-conflict free
     static_assert(JB % G == 0, "batch must be a multiple of the interleave group");
 
     unsigned char* sA = smem;                                   // [16384]
     unsigned char* sB = smem + UM_A_BYTES;                      // [JB][128][16]
-    double* sm_k = (double*)(sB + JB * 2048);                   // [N][8 JB + 1]  u, k1..k7 of the row's JB elements
-    double* sm_ts = sm_k + (((size_t)N * RS + 1) & ~(size_t)1);               // [n_t]
+    double* sm_k = (double*)(sB + JB * 2048);                   // [N + 1][JB][8] (+2 pad)  u, k1..k7 per element
+    double* sm_ts = sm_k + (size_t)(N + 1) * RS;               // [n_t]
     double* sm_red0 = sm_ts + ((n_t + 1) & ~1);                 // [4][JB]
     double* sm_red1 = sm_red0 + 4 * JB;                         // [4][JB]
     UmSlotCtl* ctl = (UmSlotCtl*)(sm_red1 + 4 * JB);            // [JB]
     unsigned long long* mbar_p = (unsigned long long*)(ctl + JB);
     unsigned* tmem_slot = (unsigned*)(mbar_p + 1);
+    unsigned* arrive_cnt = tmem_slot + 1;  // warps that have published their digits of the current evaluation
     const unsigned mbar = um_smem_u32(mbar_p);
     double* const kb = sm_k + (size_t)rr * RS;
 
-#define KP(slot, j) kb[(slot)*JB + (j)]
+#define KP(slot, j) kb[(j)*UM_NSLOT + (slot)]
 
     for (int i = tid; i < UM_A_BYTES / 16; i += 128) ((uint4*)sA)[i] = ((const uint4*)a.a_img)[i];
     for (int i = tid; i < JB * 2048 / 16; i += 128) ((uint4*)sB)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < N * RS; i += 128) sm_k[i] = 0.;  // stage slots are read before written (x 0)
+    for (int i = tid; i < (N + 1) * RS; i += 128) sm_k[i] = 0.;  // stage slots are read before written (x 0)
     for (int i = tid; i < n_t; i += 128) sm_ts[i] = a.io.t_save[i];
     // the controller lanes sit in a different warp (scheduler partition) for each CTA resident on an SM
     const int cw = (blockIdx.x / a.n_sms) & 3;
@@ -201,7 +247,10 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
         c.dts = 0.;
         c.al1s = 0.;
     }
-    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        *arrive_cnt = 0u;
+    }
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)),
                      "n"(UmCols<JB>::value));
@@ -223,7 +272,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     unsigned char* const sB_row = sB + row * 16;
 
     const double bias = a.bias[row];
-    const long long deg51 = (long long)a.deg[row] << 51;
+    const int degh = a.deg[row] << 19;  // deg 2^51 in units of the high word
     const int fpos = a.filter_pos[row];
     unsigned phase = 0;
 
@@ -269,17 +318,15 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     e2 += sm_red0[w * JB + lane];
                     nb += sm_red1[w * JB + lane];
                 }
-                const double EEst = sqrt(e2 / N);
-                double q, q11 = 0.;
-                if (EEst == 0.) {
-                    q = 1. / o.qmax;
-                } else {
-                    q11 = pow(EEst, o.beta1);
-                    q = q11 / pow(c.qold, o.beta2);
-                    q = fmax(1. / o.qmax, fmin(1. / o.qmin, q / o.gamma));
-                }
-                if (!(EEst > 1.)) {
-                    c.qold = fmax(EEst, o.qoldinit);
+                // PI controller (OrdinaryDiffEq stepsize_controller!/step_accept_controller! for PIController):
+                //   q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin], dt <- dt / q
+                // evaluated as dt * clamp(gamma exp(beta2 ln qold - beta1 ln EEst), qmin, qmax) with
+                // ln EEst = ln(e2 / N) / 2: one log and one exp on the critical path, no sqrt / pow / division.
+                const double m2 = e2 * a.inv_n;  // EEst^2
+                const double L = 0.5 * log(m2);
+                if (!(m2 > 1.)) {
+                    const double r = (m2 == 0.) ? o.qmax : fmin(o.qmax, fmax(o.qmin, o.gamma * exp(fma(o.beta2, c.lq, -o.beta1 * L))));
+                    c.lq = fmax(L, a.ln_qoldinit);
                     const double tnew = c.clipped ? o.t1 : c.t + c.dts;
                     int k1 = c.isave;
                     while (k1 < n_t && sm_ts[k1] <= tnew) k1++;
@@ -288,18 +335,13 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     c.isave = k1;
                     c.t_old = c.t;
                     c.dts_old = c.dts;
-                    {  // dense-output weights of the first save times in the window (shared by all 128 rows)
-                        const int ks0 = c.s0 < 1 ? 1 : c.s0;
-                        for (int q2 = 0; q2 < UM_MAXS && ks0 + q2 < k1; q2++)
-                            tsit5_btheta((sm_ts[ks0 + q2] - c.t) / c.dts, c.bth[q2]);
-                    }
                     c.t = tnew;
-                    c.dt = fmin(o.dtmax, fmax(o.dtmin, c.dts / q));
+                    c.dt = fmin(o.dtmax, fmax(o.dtmin, c.dts * r));
                     c.accept = 1;
                     if (nb > 0.) c.ret = MCBB_RET_UNSTABLE;  // NaN in the new state
                 } else {
                     c.nrej++;
-                    c.dt = c.dts / fmin(1. / o.qmin, q11 / o.gamma);
+                    c.dt = c.dts * fmax(o.qmin, o.gamma * exp(-o.beta1 * L));
                 }
                 if (c.ret != 0 || (c.accept && !(c.t < o.t1)))
                     finished = 1;
@@ -332,7 +374,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     c.iter = 0;
                     c.nrej = 0;
                     c.natt = 0;
-                    c.qold = o.qoldinit;
+                    c.lq = a.ln_qoldinit;
                     c.hstep = 0.;
                     c.isave = 0;
                     c.ret = 0;
@@ -345,54 +387,56 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 
         // ---- row owners: samples of the accepted step, u <- u_new, results of finished runs, new initial state ----
         bool any_init = false;
+        unsigned runmask = 0u;  // bit j: slot j integrates (its stage slots are live)
 #pragma unroll
         for (int j = 0; j < JB; j++) {
             const UmSlotCtl& c = ctl[j];
-            if (c.accept) {
+            if (c.accept) {  // uniform over the CTA; idle lanes run along on the dummy row
                 const int ks0 = c.s0 < 1 ? 1 : c.s0, ks1 = c.s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
-                if (valid) {
-                    if (ks0 < ks1) {
-                        const double dts = c.dts_old, t_old = c.t_old;
-                        double kk[8];
+                if (ks0 < ks1) {
+                    const double dts = c.dts_old, t_old = c.t_old;
+                    double kk[8];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) kk[q] = KP(q, j);
-                        for (int k = ks0; k < ks1; k++) {
-                            double bth[7];
-                            if (k - ks0 < UM_MAXS) {
+                    for (int q = 0; q < 4; q++) {
+                        const double2 t2 = reinterpret_cast<const double2*>(kb + j * UM_NSLOT)[q];
+                        kk[2 * q] = t2.x;
+                        kk[2 * q + 1] = t2.y;
+                    }
+                    const int lq = lane < 7 ? lane : 0;
+                    const double pa = c_um_bth[lq][0], pb = c_um_bth[lq][1], pc = c_um_bth[lq][2];
+                    for (int k = ks0; k < ks1; k++) {
+                        // dense-output weights: lane q evaluates b_q(theta), a shuffle hands all seven to every row
+                        const double th = um_div(sm_ts[k] - t_old, dts);
+                        const double inner = fma(th, fma(th, pc, pb), pa);
+                        const double bq = (lq == 0) ? th * fma(th, inner, 1.) : (th * th) * inner;
+                        double lin = kk[1] * __shfl_sync(0xffffffffu, bq, 0);
 #pragma unroll
-                                for (int q = 0; q < 7; q++) bth[q] = c.bth[k - ks0][q];
+                        for (int q = 1; q < 7; q++) lin = fma(kk[1 + q], __shfl_sync(0xffffffffu, bq, q), lin);
+                        double x = fma(dts, lin, kk[0]);
+                        if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
+                            if (k == 1) {
+                                const double twopi = 6.283185307179586, pi = 3.141592653589793;
+                                double vv = julia_mod_pos(x, twopi);
+                                if (vv > pi) vv -= twopi;
+                                as[j] = x - vv;
+                                x = vv;
                             } else {
-                                tsit5_btheta((sm_ts[k] - t_old) / dts, bth);
-                            }
-                            double lin = kk[1] * bth[0];
-#pragma unroll
-                            for (int q = 1; q < 7; q++) lin = fma(kk[1 + q], bth[q], lin);
-                            double x = fma(dts, lin, kk[0]);
-                            if (a.cyclic) {  // _cyclic_setback!, eval_mc_prob.jl:286-296
-                                if (k == 1) {
-                                    const double twopi = 6.283185307179586, pi = 3.141592653589793;
-                                    double vv = julia_mod_pos(x, twopi);
-                                    if (vv > pi) vv -= twopi;
-                                    as[j] = x - vv;
-                                    x = vv;
-                                } else {
-                                    x = x - as[j];
-                                }
-                            }
-                            const double delta = x - am[j];
-                            if (fabs(delta) <= 1.7976931348623157e308) {
-                                const double mnew = fma(delta, 1. / (double)k, am[j]);
-                                a2[j] = fma(delta, x - mnew, a2[j]);
-                                am[j] = mnew;
-                            } else {
-                                am[j] = nonfinite_mean(am[j], x);
-                                a2[j] = nan("");
+                                x = x - as[j];
                             }
                         }
+                        const double delta = x - am[j];
+                        if (fabs(delta) <= 1.7976931348623157e308) {
+                            const double mnew = fma(delta, um_div(1., (double)k), am[j]);
+                            a2[j] = fma(delta, x - mnew, a2[j]);
+                            am[j] = mnew;
+                        } else {
+                            am[j] = nonfinite_mean(am[j], x);
+                            a2[j] = nan("");
+                        }
                     }
-                    KP(0, j) = un[j];
-                    KP(1, j) = KP(7, j);  // FSAL
                 }
+                KP(0, j) = un[j];
+                KP(1, j) = KP(7, j);  // FSAL
             }
             if (c.fin && valid && fpos >= 0) {
                 const bool ok = c.fin_ok != 0;
@@ -410,6 +454,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                 am[j] = a2[j] = as[j] = 0.;
             }
             any_init |= (c.mode == MODE_INIT);
+            runmask |= (c.mode == MODE_RUN ? 1u : 0u) << j;
         }
         if (all_done) break;
 
@@ -430,45 +475,60 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 #pragma unroll
                 for (int i = 0; i < G; i++) {
                     const int j = g0 + i;
-                    const double c0 = (ctl[j].mode == MODE_RUN) ? cs[0] : ci0;
-                    double lin = c0 * KP(1, j);
-#pragma unroll
-                    for (int q = 1; q < 6; q++) lin = fma(cs[q], KP(1 + q, j), lin);
-                    y[i] = fma(ctl[j].hstep, lin, KP(0, j));
+                    const double2* kq = reinterpret_cast<const double2*>(kb + j * UM_NSLOT);
+                    const double2 k01 = kq[0], k23 = kq[1], k45 = kq[2];  // (u, k1) (k2, k3) (k4, k5)
+                    const double k6 = kb[j * UM_NSLOT + 6];
+                    const double c0 = ((runmask >> j) & 1u) ? cs[0] : ci0;
+                    double lin = c0 * k01.y;
+                    lin = fma(cs[1], k23.x, lin);
+                    lin = fma(cs[2], k23.y, lin);
+                    lin = fma(cs[3], k45.x, lin);
+                    lin = fma(cs[4], k45.y, lin);
+                    lin = fma(cs[5], k6, lin);
+                    y[i] = fma(ctl[j].hstep, lin, k01.x);
                 }
                 um_sincos_vec<G>(y, &sv[g0], &cv[g0]);
 #pragma unroll
                 for (int i = 0; i < G; i++) {
                     uint4 dg;
-                    fixed52(sv[g0 + i], dg.x, dg.y);
-                    fixed52(cv[g0 + i], dg.z, dg.w);
-                    if (valid) *reinterpret_cast<uint4*>(sB_row + (g0 + i) * 2048) = dg;
+                    um_fixed52(sv[g0 + i], dg.x, dg.y);
+                    um_fixed52(cv[g0 + i], dg.z, dg.w);
+                    *reinterpret_cast<uint4*>(sB_row + (g0 + i) * 2048) = dg;  // rows >= N meet zero columns of A
                 }
             }
+            // (b) D = A * digits on the tensor core.  No CTA barrier: every warp publishes its rows (generic -> async
+            //     proxy fence, then a release on a shared counter); the lane that sees the fourth arrival issues the
+            //     MMAs, completion arrives on the mbarrier everybody waits on.
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            // (b) D = A * digits on the tensor core; one thread issues, completion arrives on the mbarrier
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int ks = 0; ks < KSTEPS; ks++)
-                    um_mma_i8(tmem_base, um_desc(sA_addr + ks * 256, 128, 1024), um_desc(sB_addr + ks * 512, 128, 2048), idesc,
-                              ks > 0 ? 1u : 0u);
-                um_commit(mbar);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // this thread's TMEM reads of the last stage
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                const unsigned old = atomicAdd(arrive_cnt, 1u);
+                if ((old & 3u) == 3u) {
+                    __threadfence_block();
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int ks = 0; ks < KSTEPS; ks++)
+                        um_mma_i8(tmem_base, um_desc(sA_addr + ks * 256, 128, 1024), um_desc(sB_addr + ks * 512, 128, 2048),
+                                  idesc, ks > 0 ? 1u : 0u);
+                    um_commit(mbar);
+                }
             }
+            __syncwarp();
             um_mbar_wait(mbar, phase);
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // (c) row r of P, Q from tensor memory, int64 recombination, k = a1 (c P - s Q) + w
             double kv[JB];
-            double* const kst = kb + (2 + s) * JB;
+            double* const kst = kb + 2 + s;
 #pragma unroll
             for (int j = 0; j < JB; j++) {
                 unsigned v[16];
                 um_tmem_ld16(tmem_row + 16u * j, v);
-                const double P = (double)(recombine7(v[0], v[1], v[2], v[3], v[4], v[5], v[6]) - deg51);
-                const double Q = (double)(recombine7(v[8], v[9], v[10], v[11], v[12], v[13], v[14]) - deg51);
+                const double P = um_recombine(v[0], v[1], v[2], v[3], v[4], v[5], v[6], degh);
+                const double Q = um_recombine(v[8], v[9], v[10], v[11], v[12], v[13], v[14], degh);
                 kv[j] = fma(ctl[j].al1s, cv[j] * P - sv[j] * Q, bias);
-                if (valid && ctl[j].mode == MODE_RUN) kst[j] = kv[j];
+                kst[j * UM_NSLOT] = ((runmask >> j) & 1u) ? kv[j] : 0.;  // slots that do not integrate keep zeros
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads done before the next MMA
             if (any_init && s < 2) {  // initial step size (OrdinaryDiffEq initdt.jl), only in rounds that start a run
@@ -532,16 +592,21 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 #pragma unroll
             for (int j = 0; j < JB; j++) {
                 const double dts = ctl[j].dts;
-                const double k1 = KP(1, j);
-                double lin = TS_BT(0) * k1;
-                double lu = TS_A(5, 0) * k1;
+                double kk[8];  // u, k1..k7: four 128-bit loads
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double2 t2 = reinterpret_cast<const double2*>(kb + j * UM_NSLOT)[q];
+                    kk[2 * q] = t2.x;
+                    kk[2 * q + 1] = t2.y;
+                }
+                double lin = TS_BT(0) * kk[1];
+                double lu = TS_A(5, 0) * kk[1];
 #pragma unroll
                 for (int q = 1; q < 7; q++) {
-                    const double kq = KP(1 + q, j);
-                    lin = fma(TS_BT(q), kq, lin);
-                    if (q < 6) lu = fma(TS_A(5, q), kq, lu);
+                    lin = fma(TS_BT(q), kk[1 + q], lin);
+                    if (q < 6) lu = fma(TS_A(5, q), kk[1 + q], lu);
                 }
-                const double u0 = KP(0, j);
+                const double u0 = kk[0];
                 const double u1 = fma(dts, lu, u0);
                 const double r = um_div(dts * lin, o.abstol + fmax(fabs(u0), fabs(u1)) * o.reltol);
                 pe[j] = valid ? r * r : 0.;
@@ -579,7 +644,7 @@ static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream
 }
 
 static size_t umma_smem_bytes(int JB, int N, int n_t) {
-    return (size_t)UM_A_BYTES + (size_t)JB * 2048 + sizeof(double) * ((size_t)N * (UM_NSLOT * JB + 1) + 1 + ((n_t + 1) & ~1) + 8 * (size_t)JB) +
+    return (size_t)UM_A_BYTES + (size_t)JB * 2048 + sizeof(double) * ((size_t)(N + 1) * (UM_NSLOT * JB + 2) + ((n_t + 1) & ~1) + 8 * (size_t)JB) +
            sizeof(UmSlotCtl) * (size_t)JB + 16 + 128;
 }
 
@@ -608,6 +673,8 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.N = N;
     a.KS = (N + 31) / 32;
     a.unit_weight = uw;
+    a.inv_n = 1. / (double)N;
+    a.ln_qoldinit = std::log(o.qoldinit);
     std::vector<unsigned char> img(UM_A_BYTES, 0);
     std::vector<int> deg(128, 0);
     for (int i = 0; i < N; i++)
