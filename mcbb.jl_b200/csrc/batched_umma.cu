@@ -47,6 +47,7 @@ struct UmmaArgs {
     SolverDev o;
     int n_meas, meas[MCBB_MAX_MEAS], n_filter, cyclic;
     SolveIO io;
+    unsigned long long* timing;  // [8] phase clocks (TIMING builds only)
 };
 
 struct UmSlotCtl {
@@ -95,6 +96,19 @@ __device__ __forceinline__ void um_tmem_ld16(const unsigned taddr, unsigned (&v)
         "tcgen05.wait::ld.sync.aligned;"  // same statement: the registers are valid when it retires
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+// 32 lanes x 32 columns (two trajectories), load and wait in one statement
+__device__ __forceinline__ void um_tmem_ld32(const unsigned taddr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
 
@@ -200,7 +214,9 @@ __device__ __forceinline__ double um_div(const double a, const double b) {
     return fma(fma(-b, q, a), y, q);
 }
 
-template <int JB, int MINB>
+// TIMING = true: thread 0 of every CTA accumulates clock64() per phase into a.timing (development aid,
+// MCBB_UMMA_TIMING=1; the compiler may move arithmetic across the ticks, so treat the split as approximate)
+template <int JB, int MINB, bool TIMING = false>
 __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     constexpr int G = JB <= 4 ? JB : (JB % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved
     constexpr int RS = UM_NSLOT * JB + 2;         // row stride (doubles) = 2 (mod 4): 16-byte aligned thread-private
                                                   // blocks whose 128-bit accesses are bank-conflict free
-    static_assert(JB % G == 0, "batch must be a multiple of the interleave group");
+    static_assert(JB % G == 0 && JB % 2 == 0, "batch must be a multiple of the interleave group and even");
 
     unsigned char* sA = smem;                                   // [16384]
     unsigned char* sB = smem + UM_A_BYTES;                      // [JB][128][16]
@@ -225,8 +241,9 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     double* sm_red1 = sm_red0 + 4 * JB;                         // [4][JB]
     UmSlotCtl* ctl = (UmSlotCtl*)(sm_red1 + 4 * JB);            // [JB]
     unsigned long long* mbar_p = (unsigned long long*)(ctl + JB);
-    unsigned* tmem_slot = (unsigned*)(mbar_p + 1);
-    unsigned* arrive_cnt = tmem_slot + 1;  // warps that have published their digits of the current evaluation
+    unsigned* tmem_slot = (unsigned*)(mbar_p + 2);
+    unsigned long long* full_p = mbar_p + 1;  // "digits published": one arrival per row warp
+    const unsigned mbar_full = um_smem_u32(full_p);
     const unsigned mbar = um_smem_u32(mbar_p);
     double* const kb = sm_k + (size_t)rr * RS;
 
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-        *arrive_cnt = 0u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(mbar_full));
     }
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)),
@@ -300,6 +317,14 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
         return true;
     };
 
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+    if (TIMING) tprev = clock64();
+#define UM_TICK(k)                              \
+    if (TIMING && tid == 0) {                   \
+        const long long tn_ = clock64();        \
+        tph[k] += tn_ - tprev;                  \
+        tprev = tn_;                            \
+    }
     for (;;) {
         // ---- per-trajectory control: PI controller, accept / reject, save window, finish, refill -----------------
         if (is_ctl) {
@@ -384,6 +409,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             }
         }
         const bool all_done = __syncthreads_and(!is_ctl || ctl[lane].mode == MODE_DONE);
+        UM_TICK(0)  // error partials + controller + barriers
 
         // ---- row owners: samples of the accepted step, u <- u_new, results of finished runs, new initial state ----
         bool any_init = false;
@@ -457,6 +483,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             runmask |= (c.mode == MODE_RUN ? 1u : 0u) << j;
         }
         if (all_done) break;
+        UM_TICK(1)  // samples, update, results, refill
 
         // ---- one round: 6 right-hand-side evaluations of the whole batch -----------------------------------------
         // Everything below is written without per-trajectory branches: slots that are idle or still measuring their
@@ -496,17 +523,23 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     *reinterpret_cast<uint4*>(sB_row + (g0 + i) * 2048) = dg;  // rows >= N meet zero columns of A
                 }
             }
+            UM_TICK(2)  // stage input, sincos, digits
             // (b) D = A * digits on the tensor core.  No CTA barrier: every warp publishes its rows (generic -> async
-            //     proxy fence, then a release on a shared counter); the lane that sees the fourth arrival issues the
-            //     MMAs, completion arrives on the mbarrier everybody waits on.
+            //     proxy fence, then a release-arrive on a 4-count mbarrier); the lane whose arrival completes the phase
+            //     (pending count 1, profiles/microbench/mbar_probe.cu) issues the MMAs; their completion arrives on
+            //     the second mbarrier, the one everybody waits on.
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // this thread's TMEM reads of the last stage
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                const unsigned old = atomicAdd(arrive_cnt, 1u);
-                if ((old & 3u) == 3u) {
-                    __threadfence_block();
+                unsigned long long st;
+                unsigned pend;
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(mbar_full) : "memory");
+                asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pend) : "l"(st));
+                if (pend == 1u) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t}" ::"r"(mbar_full),
+                                 "r"(phase)
+                                 : "memory");  // acquire the other warps' releases (the phase is complete)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (int ks = 0; ks < KSTEPS; ks++)
                         um_mma_i8(tmem_base, um_desc(sA_addr + ks * 256, 128, 1024), um_desc(sB_addr + ks * 512, 128, 2048),
@@ -515,22 +548,30 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                 }
             }
             __syncwarp();
+            UM_TICK(3)  // publish (+ issue)
             um_mbar_wait(mbar, phase);
+            UM_TICK(4)  // MMA wait
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // (c) row r of P, Q from tensor memory, int64 recombination, k = a1 (c P - s Q) + w
             double kv[JB];
             double* const kst = kb + 2 + s;
 #pragma unroll
-            for (int j = 0; j < JB; j++) {
-                unsigned v[16];
-                um_tmem_ld16(tmem_row + 16u * j, v);
-                const double P = um_recombine(v[0], v[1], v[2], v[3], v[4], v[5], v[6], degh);
-                const double Q = um_recombine(v[8], v[9], v[10], v[11], v[12], v[13], v[14], degh);
-                kv[j] = fma(ctl[j].al1s, cv[j] * P - sv[j] * Q, bias);
-                kst[j * UM_NSLOT] = ((runmask >> j) & 1u) ? kv[j] : 0.;  // slots that do not integrate keep zeros
+            for (int g0 = 0; g0 < JB; g0 += 2) {  // two trajectories per tensor-memory load
+                unsigned v[32];
+                um_tmem_ld32(tmem_row + 16u * g0, v);
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int j = g0 + i;
+                    const unsigned* w = v + 16 * i;
+                    const double P = um_recombine(w[0], w[1], w[2], w[3], w[4], w[5], w[6], degh);
+                    const double Q = um_recombine(w[8], w[9], w[10], w[11], w[12], w[13], w[14], degh);
+                    kv[j] = fma(ctl[j].al1s, cv[j] * P - sv[j] * Q, bias);
+                    kst[j * UM_NSLOT] = ((runmask >> j) & 1u) ? kv[j] : 0.;  // slots that do not integrate keep zeros
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads done before the next MMA
+            UM_TICK(5)  // accumulators -> k
             if (any_init && s < 2) {  // initial step size (OrdinaryDiffEq initdt.jl), only in rounds that start a run
 #pragma unroll
                 for (int j = 0; j < JB; j++) {
@@ -629,23 +670,27 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
         __syncthreads();
     }
 #undef KP
+    if (TIMING && tid == 0) {
+        for (int k = 0; k < 8; k++) atomicAdd(a.timing + k, (unsigned long long)tph[k]);
+    }
+#undef UM_TICK
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (wid == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
 }
 
-template <int JB, int MINB>
+template <int JB, int MINB, bool TIMING = false>
 static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_batched_umma<JB, MINB><<<grid, 128, smem, st>>>(a);
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_umma<JB, MINB, TIMING><<<grid, 128, smem, st>>>(a);
     MCBB_LAUNCHED();
     return 0;
 }
 
 static size_t umma_smem_bytes(int JB, int N, int n_t) {
     return (size_t)UM_A_BYTES + (size_t)JB * 2048 + sizeof(double) * ((size_t)(N + 1) * (UM_NSLOT * JB + 2) + ((n_t + 1) & ~1) + 8 * (size_t)JB) +
-           sizeof(UmSlotCtl) * (size_t)JB + 16 + 128;
+           sizeof(UmSlotCtl) * (size_t)JB + 24 + 128;
 }
 
 // Returns handled = true when the problem was run on the tcgen05 path.
@@ -743,6 +788,24 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     const int grid = (int)std::min<long long>(want, (long long)sms * pick->per_sm);
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     int rc = 1;
+    if (getenv("MCBB_UMMA_TIMING") && pick->jb == 4 && (pick->per_sm == 4 || pick->per_sm == 2)) {  // development aid
+        a.timing = (unsigned long long*)scratch_get(63, 64);
+        if (!a.timing) MCBB_FAIL("solve: device allocation failed");
+        MCBB_CUDA_OK(cudaMemsetAsync(a.timing, 0, 64, st));
+        rc = pick->per_sm == 4 ? launch_umma_spec<4, 4, true>(a, smem, grid, st) : launch_umma_spec<4, 2, true>(a, smem, grid, st);
+        if (rc) return rc;
+        unsigned long long h[8];
+        MCBB_CUDA_OK(cudaMemcpyAsync(h, a.timing, 64, cudaMemcpyDeviceToHost, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));
+        static const char* nm[8] = {"error+control+barrier", "samples/update", "stage input+sincos", "publish/issue", "MMA wait", "TMEM->k",
+                                    "-", "-"};
+        double tot = 0;
+        for (int k = 0; k < 8; k++) tot += (double)h[k];
+        for (int k = 0; k < 8; k++)
+            fprintf(stderr, "[umma timing] %-24s %6.2f %%  %10.0f clk per CTA\n", nm[k], 100. * h[k] / tot, (double)h[k] / grid);
+        *handled = true;
+        return 0;
+    }
     if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 4) rc = launch_umma_spec<4, 4>(a, smem, grid, st);
     else if (pick->jb == 8 && pick->per_sm == 2) rc = launch_umma_spec<8, 2>(a, smem, grid, st);
