@@ -269,20 +269,24 @@ def main():
     m.check(m.lib().mcbb_measure_fp64_fma_peak(C.byref(peak), C.byref(mhz)))
     fl_alg, fl_dense = algorithmic_flops(A, float(nst.item()) * args.steps)
     traffic_ncu = None
-    try:  # DRAM traffic of the same kernel from the committed ncu --set full capture (a smaller launch: 7104 runs)
+    traffic = None
+    try:  # DRAM traffic of the same kernel from the committed ncu --set full capture (one launch of 125 000 runs)
         import csv
-        rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_k_solve_batched_imma_x2s.csv")))}
+        rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_k_solve_batched_umma.csv")))}
         unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
-        traffic_ncu = {"runs_per_launch": 7104, "dram_bytes": float(rd[2]) * unit[rd[1]] + float(wr[2]) * unit[wr[1]],
-                       "algorithmic_bytes": 7104 * (N_OSC * 8 + 8 + 2 * N_OSC * 8 + 4 + 16)}
+        ncu_runs = 125000
+        traffic_ncu = {"runs_per_launch": ncu_runs, "dram_bytes": float(rd[2]) * unit[rd[1]] + float(wr[2]) * unit[wr[1]],
+                       "algorithmic_bytes": ncu_runs * (N_OSC * 8 + 8 + 2 * N_OSC * 8 + 4 + 16)}
+        if R == ncu_runs:
+            traffic = traffic_ncu["dram_bytes"]
     except Exception:
         pass
     achieved = fl_alg / (ms_total * 1e-3) / world / 1e12
     roofline = {
         "bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-        "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
-        "kernel": "k_solve_batched_imma_x2s<2,4>", "traffic_ncu": traffic_ncu,
+        "frac": achieved / peak.value if peak.value > 0 else None, "traffic": traffic,
+        "kernel": "k_solve_batched_umma<4,4> (tcgen05.mma kind::i8 + TMEM)", "traffic_ncu": traffic_ncu,
         "peak_source": "measured in this run by the library's DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 "
                        "entry; nominal B200 ~37 TFLOP/s)",
         "achieved_dense_equiv": fl_dense / (ms_total * 1e-3) / world / 1e12,

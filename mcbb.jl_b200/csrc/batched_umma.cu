@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     const int j = g0 + i;
                     const double2* kq = reinterpret_cast<const double2*>(kb + j * UM_NSLOT);
                     const double2 k01 = kq[0], k23 = kq[1], k45 = kq[2];  // (u, k1) (k2, k3) (k4, k5)
-                    const double k6 = kb[j * UM_NSLOT + 6];
+                    const double k6 = kq[3].x;  // 128-bit like the others: 64-bit accesses at this row stride conflict 2-way
                     const double c0 = ((runmask >> j) & 1u) ? cs[0] : ci0;
                     double lin = c0 * k01.y;
                     lin = fma(cs[1], k23.x, lin);
