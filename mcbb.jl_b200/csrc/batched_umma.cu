@@ -7,7 +7,9 @@
 // with sin/cos written as u = round(x 2^50) + 2^51 and split into radix-256 digits.  What changes is the
 // machine mapping, which is built around tcgen05 instead of mma.sync:
 //
-//   * D[128 x 16 JB] (s32, TMEM) = A[128 x 128] (u8, K-major) * B[128 x 16 JB] (u8, MN-major, no swizzle).
+//   * D[128 x 16 JB] (s32, TMEM) = A[128 x 128] (u8, resident in TMEM: row r in lane r, four K bytes per 32-bit
+//     column) * B[128 x 16 JB] (u8, shared memory, MN-major, no swizzle).  A in tensor memory instead of shared
+//     memory frees 16 KB per CTA: 24 instead of 16 resident trajectories per SM.
 //     In the MN-major canonical layout the 16 columns of one trajectory are 16 CONTIGUOUS bytes per oscillator
 //     row, and the digits of (sin, cos) are simply the little-endian bytes of the two 64-bit integers
 //     {u_sin, u_cos}: the producer writes its element with ONE 16-byte shared-memory store, no byte shuffles.
@@ -36,7 +38,7 @@ constexpr int UM_A_BYTES = 128 * 128;
 struct UmmaArgs {
     int N, KS, n_sms;
     double inv_n, ln_qoldinit;
-    const unsigned char* a_img;  // [16384] A in its shared-memory (canonical K-major, no swizzle) layout
+    const unsigned char* a_img;  // [128][128] A, row-major bytes (row r goes to TMEM lane r)
     const int* deg;              // [128] number of non-zero couplings per row
     const double* bias;          // [128]
     const int* filter_pos;       // [128]
@@ -72,6 +74,28 @@ __device__ __forceinline__ void um_mma_i8(const unsigned d_tmem, const unsigned 
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// A operand from tensor memory (lane = row, 32-bit column = four consecutive K bytes)
+__device__ __forceinline__ void um_mma_i8_ts(const unsigned d_tmem, const unsigned a_tmem, const unsigned long long db,
+                                             const unsigned idesc, const unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void um_tmem_st32(const unsigned taddr, const unsigned (&w)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n\t"
+        "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
+        "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]),
+        "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]),
+        "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]),
+        "r"(w[31])
         : "memory");
 }
 
@@ -115,7 +139,8 @@ __device__ __forceinline__ void um_tmem_ld32(const unsigned taddr, unsigned (&v)
 // tensor-memory allocation: power of two >= 32 columns
 template <int JB>
 struct UmCols {
-    static constexpr unsigned value = 16 * JB <= 32 ? 32u : 16 * JB <= 64 ? 64u : 16 * JB <= 128 ? 128u : 256u;
+    static constexpr unsigned need = 16 * JB + 32;  // accumulators + the A operand
+    static constexpr unsigned value = need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
 };
 
 // warp-level sum with a fixed tree (deterministic)
@@ -124,6 +149,11 @@ __device__ __forceinline__ double um_warp_sum(double p) {
     for (int off = 1; off < 32; off <<= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
     return p;
 }
+
+// save times t_save (eval_ode_run's saveat grid), read with uniform or near-uniform indices: constant bank instead of
+// 8 n_t bytes of every CTA's shared memory
+constexpr int UM_MAX_NT = 4096;
+static __constant__ double c_um_ts[UM_MAX_NT];
 
 // sincos / fixed-point constants live in the constant bank: DFMA takes them as c[bank][offset] operands, no
 // per-use immediate moves
@@ -233,11 +263,10 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                                                   // blocks whose 128-bit accesses are bank-conflict free
     static_assert(JB % G == 0 && JB % 2 == 0, "batch must be a multiple of the interleave group and even");
 
-    unsigned char* sA = smem;                                   // [16384]
-    unsigned char* sB = smem + UM_A_BYTES;                      // [JB][128][16]
+    unsigned char* sB = smem;                                   // [JB][128][16]
     double* sm_k = (double*)(sB + JB * 2048);                   // [N + 1][JB][8] (+2 pad)  u, k1..k7 per element
-    double* sm_ts = sm_k + (size_t)(N + 1) * RS;               // [n_t]
-    double* sm_red0 = sm_ts + ((n_t + 1) & ~1);                 // [4][JB]
+    const double* const sm_ts = c_um_ts;                        // [n_t] (constant bank)
+    double* sm_red0 = sm_k + (size_t)(N + 1) * RS;              // [4][JB]
     double* sm_red1 = sm_red0 + 4 * JB;                         // [4][JB]
     UmSlotCtl* ctl = (UmSlotCtl*)(sm_red1 + 4 * JB);            // [JB]
     unsigned long long* mbar_p = (unsigned long long*)(ctl + JB);
@@ -249,10 +278,8 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 
 #define KP(slot, j) kb[(j)*UM_NSLOT + (slot)]
 
-    for (int i = tid; i < UM_A_BYTES / 16; i += 128) ((uint4*)sA)[i] = ((const uint4*)a.a_img)[i];
     for (int i = tid; i < JB * 2048 / 16; i += 128) ((uint4*)sB)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < (N + 1) * RS; i += 128) sm_k[i] = 0.;  // stage slots are read before written (x 0)
-    for (int i = tid; i < n_t; i += 128) sm_ts[i] = a.io.t_save[i];
     // the controller lanes sit in a different warp (scheduler partition) for each CTA resident on an SM
     const int cw = (blockIdx.x / a.n_sms) & 3;
     const bool is_ctl = (wid == cw) && lane < JB;
@@ -279,12 +306,27 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
     const unsigned tmem_row = tmem_base + ((unsigned)(32 * wid) << 16);  // this warp's 32 TMEM lanes
+    const unsigned tmem_a = tmem_base + NCOL;                            // A operand: 32 columns behind the accumulators
+    {  // row r of A -> lane r: 128 K bytes = 32 columns
+        unsigned w[32];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint4 t4 = reinterpret_cast<const uint4*>(a.a_img + (size_t)row * 128)[q];
+            w[4 * q] = t4.x;
+            w[4 * q + 1] = t4.y;
+            w[4 * q + 2] = t4.z;
+            w[4 * q + 3] = t4.w;
+        }
+        um_tmem_st32(tmem_row + NCOL, w);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
 
-    // MMA operands: A K-major (8-row groups 1024 B apart, the two 16-byte K chunks of an MMA 128 B apart, next
-    // K step + 256 B); B MN-major (16-column chunks 2048 B apart, 8-deep K groups 128 B apart, next K step + 512 B)
+    // MMA operands: A from tensor memory (next K step + 8 columns); B MN-major (16-column chunks 2048 B apart, 8-deep K groups 128 B apart, next K step + 512 B)
     const unsigned idesc = (2u << 4) /* D s32 */ | (0u << 7) /* A u8 */ | (0u << 10) /* B u8 */ | (0u << 15) /* A K-major */ |
                            (1u << 16) /* B MN-major */ | ((NCOL >> 3) << 17) | ((128u >> 4) << 24);
-    const unsigned sA_addr = um_smem_u32(sA), sB_addr = um_smem_u32(sB);
+    const unsigned sB_addr = um_smem_u32(sB);
     const int KSTEPS = a.KS;
     unsigned char* const sB_row = sB + row * 16;
 
@@ -542,8 +584,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                                  : "memory");  // acquire the other warps' releases (the phase is complete)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (int ks = 0; ks < KSTEPS; ks++)
-                        um_mma_i8(tmem_base, um_desc(sA_addr + ks * 256, 128, 1024), um_desc(sB_addr + ks * 512, 128, 2048),
-                                  idesc, ks > 0 ? 1u : 0u);
+                        um_mma_i8_ts(tmem_base, tmem_a + 8u * ks, um_desc(sB_addr + ks * 512, 128, 2048), idesc, ks > 0 ? 1u : 0u);
                     um_commit(mbar);
                 }
             }
@@ -689,7 +730,8 @@ static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream
 }
 
 static size_t umma_smem_bytes(int JB, int N, int n_t) {
-    return (size_t)UM_A_BYTES + (size_t)JB * 2048 + sizeof(double) * ((size_t)(N + 1) * (UM_NSLOT * JB + 2) + ((n_t + 1) & ~1) + 8 * (size_t)JB) +
+    (void)n_t;  // the save times live in the constant bank
+    return (size_t)JB * 2048 + sizeof(double) * ((size_t)(N + 1) * (UM_NSLOT * JB + 2) + 8 * (size_t)JB) +
            sizeof(UmSlotCtl) * (size_t)JB + 24 + 128;
 }
 
@@ -701,6 +743,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     if (S.system != MCBB_SYS_KURAMOTO_NETWORK || hs == nullptr) return 0;
     if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1 || F.matrix_meas) return 0;
     if (N < 33 || N > 128) return 0;  // one 128-row MMA tile; small networks stay on the mma.sync kernel
+    if (io.n_t > UM_MAX_NT) return 0;  // save times are kept in the constant bank
     if (getenv("MCBB_NO_IMMA") || getenv("MCBB_NO_UMMA")) return 0;
     for (int m = 0; m < F.n_meas; m++)
         if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
@@ -725,7 +768,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     for (int i = 0; i < N; i++)
         for (int j = 0; j < N; j++)
             if (hs->mat_a[i + (size_t)N * j] != 0.) {
-                img[(i >> 3) * 1024 + (j >> 4) * 128 + (i & 7) * 16 + (j & 15)] = 1;
+                img[(size_t)i * 128 + j] = 1;
                 deg[i]++;
             }
     std::vector<double> bias(128, 0.);
@@ -765,7 +808,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
 
     // configurations (trajectories per CTA, CTAs per SM): TMEM columns and shared memory both have to fit
     struct Cfg { int jb, per_sm; };
-    static const Cfg cfgs[] = {{4, 4}, {6, 3}, {8, 2}, {4, 3}, {4, 2}, {2, 2}, {2, 1}};  // measured on C5: 372k, 360k, 307k traj/s
+    static const Cfg cfgs[] = {{6, 4}, {4, 4}, {6, 3}, {8, 2}, {4, 3}, {4, 2}, {2, 2}, {2, 1}};
     int want_jb = getenv("MCBB_UMMA_JB") ? atoi(getenv("MCBB_UMMA_JB")) : 0;
     int want_per = getenv("MCBB_UMMA_PER_SM") ? atoi(getenv("MCBB_UMMA_PER_SM")) : 0;
     const Cfg* pick = nullptr;
@@ -787,6 +830,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     const long long want = (io.n_mc + pick->jb - 1) / pick->jb;
     const int grid = (int)std::min<long long>(want, (long long)sms * pick->per_sm);
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
+    MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     int rc = 1;
     if (getenv("MCBB_UMMA_TIMING") && pick->jb == 4 && (pick->per_sm == 4 || pick->per_sm == 2)) {  // development aid
         a.timing = (unsigned long long*)scratch_get(63, 64);
@@ -806,7 +850,8 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
         *handled = true;
         return 0;
     }
-    if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3>(a, smem, grid, st);
+    if (pick->jb == 6 && pick->per_sm == 4) rc = launch_umma_spec<6, 4>(a, smem, grid, st);
+    else if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 4) rc = launch_umma_spec<4, 4>(a, smem, grid, st);
     else if (pick->jb == 8 && pick->per_sm == 2) rc = launch_umma_spec<8, 2>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 3) rc = launch_umma_spec<4, 3>(a, smem, grid, st);

@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_probe umma_probe.cu
 // Run:   umma_probe <amode> <bmode> <N> [reps]     exit 0 = D matches the CPU product bit for bit
 //   amode 0: LBO = 128 (between the two 16-byte K chunks), SBO = 1024 (between 8-row groups); 1: swapped
+//         2: A from tensor memory (row r in lane r, 4 K bytes per 32-bit column, written with tcgen05.st)
 //   bmode 0: MN-major, LBO = 128 (between 8-deep K groups), SBO = 2048 (between 16-column chunks); 1: swapped
 //         2: K-major,  LBO = 128, SBO = 1024; 3: swapped
 #include <cstdint>
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint8_t* A, const uint8_
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
     }
     if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -71,6 +72,26 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint8_t* A, const uint8_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tb = tmem_base;
+    const uint32_t ta = tb + 256u;  // A operand: columns 256..287 (allocation below covers 512 columns)
+    if (p.amode == 2) {
+        uint32_t w[32];
+        for (int c = 0; c < 32; c++) {
+            const uint8_t* q = A + tid * 128 + 4 * c;
+            w[c] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        }
+        const uint32_t taddr = ta + ((uint32_t)(32 * wid) << 16);
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+            "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+            ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
+            "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]),
+            "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]),
+            "r"(w[30]), "r"(w[31]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
 
     const uint32_t a_lbo = p.amode == 0 ? 128 : 1024, a_sbo = p.amode == 0 ? 1024 : 128;
     uint32_t b_lbo, b_sbo;
@@ -93,6 +114,13 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint8_t* A, const uint8_
                 // 32 k rows further: MN-major 32 * 16 bytes; K-major two 16-byte chunks = 2 * 128
                 const uint64_t db = make_desc(smem_u32(sB) + (p.bmode < 2 ? ks * 512 : ks * 256), b_lbo, b_sbo);
                 const uint32_t accum = ks > 0 ? 1u : 0u;
+                if (p.amode == 2) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                        ::"r"(tb), "r"(ta + 8u * ks), "l"(db), "r"(idesc), "r"(accum) : "memory");
+                    continue;
+                }
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint8_t* A, const uint8_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tb));
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb));
 }
 
 int main(int argc, char** argv) {
