@@ -573,12 +573,14 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // this thread's TMEM reads of the last stage
             __syncwarp();
+            int issuer = 0;
             if (lane == 0) {
                 unsigned long long st;
                 unsigned pend;
                 asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(mbar_full) : "memory");
                 asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pend) : "l"(st));
                 if (pend == 1u) {
+                    issuer = 1;
                     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t}" ::"r"(mbar_full),
                                  "r"(phase)
                                  : "memory");  // acquire the other warps' releases (the phase is complete)
@@ -588,9 +590,15 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     um_commit(mbar);
                 }
             }
-            __syncwarp();
+            // Only the issuing warp polls the completion mbarrier (a polling warp burns issue slots: ~10 % of all
+            // issued instructions when all four polled); the other three sleep on hardware barrier 1 until it joins.
+            issuer = __shfl_sync(0xffffffffu, issuer, 0);
             UM_TICK(3)  // publish (+ issue)
-            um_mbar_wait(mbar, phase);
+            if (issuer) {
+                um_mbar_wait(mbar, phase);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             UM_TICK(4)  // MMA wait
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
