@@ -239,7 +239,7 @@ static int launch_tiles(const TileArgs& a, cudaStream_t st) {
     if (nr <= 0 || nc <= 0) return 0;
     dim3 grid((unsigned)((nc + TILE - 1) / TILE), (unsigned)((nr + TILE - 1) / TILE));
     if (a.band > 0) grid.x = a.symmetric ? (unsigned)(a.band + 1) : (unsigned)(2 * a.band + 1);
-    if (a.col_mod > 1 && a.col_sel == 1) grid.x = (grid.x + a.col_mod - 1) / a.col_mod;
+    if (a.col_mod > 1) grid.x = ((grid.x + a.col_mod - 1) / a.col_mod) * (unsigned)(a.col_hi - a.col_lo);
     if (grid.y > 65535u) MCBB_FAIL("pair tiles: more than 65535 row tiles in one launch; shard the rows");
     k_pair_tiles<MODE><<<grid, 256, 0, st>>>(a);
     MCBB_LAUNCHED();
@@ -264,10 +264,12 @@ constexpr int BAND_TILES = 4;
 constexpr int COL_SAMPLE = 32;
 
 // eps-neighbour counts of rows [row0,row1) against all n columns, exact below minpts and >= minpts otherwise.
-// Proving a point NON-core needs its whole row; proving it core needs only minpts hits.  So:
-//   (a) every row against an evenly spread 1/32 sample of the column tiles — dense (core) points saturate here;
-//   (b) the rows still below minpts are compacted and finish against the remaining 31/32 of the column tiles.
-// Work ~ n^2/32 + |unsaturated| n instead of n^2/2; counts add up exactly (disjoint column sets).
+// Proving a point NON-core needs its whole row; proving it core needs only minpts hits.  The column tiles are
+// therefore visited in four disjoint, evenly spread samples (residues of the tile index mod 32: [0,1) [1,5) [5,16)
+// [16,32), i.e. cumulative 1/32, 5/32, 1/2, 1); after each sample the rows that already reached minpts drop out and
+// the rest are compacted.  A point with m neighbours leaves after the first sample if m >~ 32 minpts, after the second
+// if m >~ 6.4 minpts, ...: work ~ n^2 (1/32 + 4/32 u1 + 11/32 u2 + 16/32 u3) with u_k the still-unsaturated fractions,
+// instead of n^2/2.  Counts add up exactly (disjoint column sets).
 static int count_rows(const double* X, long long n, const GroupTables& gt, double eps, int minpts, long long row0,
                       long long row1, int* cnt /* row1-row0 */, cudaStream_t st, PassTimer* pt) {
     const long long m = row1 - row0;
@@ -292,10 +294,12 @@ static int count_rows(const double* X, long long n, const GroupTables& gt, doubl
     a.sat_count = minpts;
     a.sat_seed = -1;
     if (n >= (long long)COL_SAMPLE * TILE * 8) {
+        static const int bounds[5] = {0, 1, 5, 16, COL_SAMPLE};
         a.col_mod = COL_SAMPLE;
-        a.col_sel = 1;
+        a.col_lo = bounds[0];
+        a.col_hi = bounds[1];
         if (int rc = launch_tiles_rows<TM_COUNT>(a, st)) return rc;
-        if (pt) pt->lap("pass 1a sampled columns");
+        if (pt) pt->lap("pass 1 sample 1/32");
         int* flag = (int*)scratch_get(13, sizeof(int) * m);
         int* pos = (int*)scratch_get(15, sizeof(int) * m);
         int* uidx = (int*)scratch_get(17, sizeof(int) * m);
@@ -303,36 +307,39 @@ static int count_rows(const double* X, long long n, const GroupTables& gt, doubl
         cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)m, st);
         void* tmp = scratch_get(21, tb);
         if (!flag || !pos || !uidx || !tmp) MCBB_FAIL("dbscan: device scratch allocation failed");
-        k_flag_below<<<nblk(m), 256, 0, st>>>(cnt, m, minpts, flag);
-        MCBB_LAUNCHED();
-        MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, pos, (int)m, st));
-        g_launch_count.fetch_add(1);
-        int h_pos = 0, h_flag = 0;
-        MCBB_CUDA_OK(cudaMemcpyAsync(&h_pos, pos + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-        MCBB_CUDA_OK(cudaMemcpyAsync(&h_flag, flag + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-        MCBB_CUDA_OK(cudaStreamSynchronize(st));
-        const long long nu = (long long)h_pos + h_flag;
-        if (nu == 0) return 0;
-        k_compact_flagged<<<nblk(m), 256, 0, st>>>(flag, pos, m, uidx);  // indices relative to row0
-        MCBB_LAUNCHED();
-        double* Xu = (double*)scratch_get(24, sizeof(double) * (size_t)gt.F * (size_t)nu);
-        int* cu = (int*)scratch_get(16, sizeof(int) * (size_t)nu);
-        if (!Xu || !cu) MCBB_FAIL("dbscan: device scratch allocation failed");
-        k_gather_cols<<<dim3(nblk(nu), gt.F), 256, 0, st>>>(X + row0, n, uidx, nu, gt.F, Xu);
-        MCBB_LAUNCHED();
-        k_gather_i32<<<nblk(nu), 256, 0, st>>>(cnt, uidx, nu, cu);  // carry the sampled-column counts over
-        MCBB_LAUNCHED();
-        TileArgs b = a;
-        b.Xr = Xu;
-        b.ldr = nu;
-        b.r0 = 0;
-        b.r1 = nu;
-        b.cnt = cu;
-        b.col_sel = 2;
-        if (int rc = launch_tiles_rows<TM_COUNT>(b, st)) return rc;
-        k_scatter_i32<<<nblk(nu), 256, 0, st>>>(cu, uidx, nu, cnt);
-        MCBB_LAUNCHED();
-        if (pt) pt->lap("pass 1b unsaturated rows");
+        for (int stage = 1; stage < 4; stage++) {
+            k_flag_below<<<nblk(m), 256, 0, st>>>(cnt, m, minpts, flag);
+            MCBB_LAUNCHED();
+            MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, pos, (int)m, st));
+            g_launch_count.fetch_add(1);
+            int h_pos = 0, h_flag = 0;
+            MCBB_CUDA_OK(cudaMemcpyAsync(&h_pos, pos + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+            MCBB_CUDA_OK(cudaMemcpyAsync(&h_flag, flag + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+            MCBB_CUDA_OK(cudaStreamSynchronize(st));
+            const long long nu = (long long)h_pos + h_flag;
+            if (nu == 0) return 0;
+            k_compact_flagged<<<nblk(m), 256, 0, st>>>(flag, pos, m, uidx);  // indices relative to row0
+            MCBB_LAUNCHED();
+            double* Xu = (double*)scratch_get(24, sizeof(double) * (size_t)gt.F * (size_t)nu);
+            int* cu = (int*)scratch_get(16, sizeof(int) * (size_t)nu);
+            if (!Xu || !cu) MCBB_FAIL("dbscan: device scratch allocation failed");
+            k_gather_cols<<<dim3(nblk(nu), gt.F), 256, 0, st>>>(X + row0, n, uidx, nu, gt.F, Xu);
+            MCBB_LAUNCHED();
+            k_gather_i32<<<nblk(nu), 256, 0, st>>>(cnt, uidx, nu, cu);  // carry the counts so far over
+            MCBB_LAUNCHED();
+            TileArgs b = a;
+            b.Xr = Xu;
+            b.ldr = nu;
+            b.r0 = 0;
+            b.r1 = nu;
+            b.cnt = cu;
+            b.col_lo = bounds[stage];
+            b.col_hi = bounds[stage + 1];
+            if (int rc = launch_tiles_rows<TM_COUNT>(b, st)) return rc;
+            k_scatter_i32<<<nblk(nu), 256, 0, st>>>(cu, uidx, nu, cnt);
+            MCBB_LAUNCHED();
+            if (pt) pt->lap(stage == 1 ? "pass 1 sample 5/32" : stage == 2 ? "pass 1 sample 1/2" : "pass 1 rest");
+        }
         return 0;
     }
     if (int rc = launch_tiles_rows<TM_COUNT>(a, st)) return rc;

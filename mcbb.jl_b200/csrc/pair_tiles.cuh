@@ -51,9 +51,8 @@ struct TileArgs {
     int sat_count;        // TM_COUNT: every row (and column, if symmetric) already has >= sat_count neighbours
     int sat_seed;         // TM_BORDER: every row already holds the globally smallest seed
     int sat_union;        // TM_UNION: every row and column already shares one root
-    int col_mod, col_sel; // col_mod > 1: column tiles are split by (tile index % col_mod): col_sel 1 = only the
-                          // residue-0 tiles (an evenly spread sample of the columns; blockIdx.x counts sampled tiles),
-                          // col_sel 2 = all the others
+    int col_mod, col_lo, col_hi;  // col_mod > 1: only column tiles with (tile index % col_mod) in [col_lo, col_hi) are
+                                  // visited: evenly spread, disjoint samples of the columns (progressive counting)
     int band;             // > 0: only column tiles within `band` tiles of the row tile are visited; blockIdx.x is
                           // the offset (symmetric: 0..band, else -band..band).  Runs are sorted by parameter, so
                           // index neighbours are the likely distance neighbours: a cheap first pass that saturates
@@ -96,13 +95,12 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
 
     const long long tr = a.r0 + (long long)blockIdx.y * TILE;
     long long tc = a.c0 + (long long)blockIdx.x * TILE;
-    if (a.col_mod > 1) {
-        if (a.col_sel == 1) {
-            tc = a.c0 + (long long)blockIdx.x * a.col_mod * TILE;
-            if (tc >= a.c1) return;
-        } else if ((blockIdx.x % a.col_mod) == 0) {
-            return;
-        }
+    if (a.col_mod > 1) {  // blockIdx.x enumerates the sampled tiles: period index * width + offset inside the residue range
+        const int wdt = a.col_hi - a.col_lo;
+        const long long per = blockIdx.x / wdt;
+        const int off = blockIdx.x - (int)per * wdt;
+        tc = a.c0 + (per * a.col_mod + a.col_lo + off) * TILE;
+        if (tc >= a.c1) return;
     }
     if (a.band > 0) {  // band pass: column tile relative to the row tile (tile grids of rows and columns coincide)
         tc = tr + ((long long)blockIdx.x - (a.symmetric ? 0 : a.band)) * TILE;
