@@ -84,10 +84,39 @@ def dbscan_features_device(X_t, group_len, group_weight, eps, minpts):
     return a, s[: k[0]], c[: k[0]]
 
 
+_TILE = 64  # pair-tile edge of the stage kernels (csrc/pair_tiles.cuh)
+
+
+def cyclic_order(m, world, device=None):
+    """Permutation of range(m) that lists the 64-point tiles owned by rank 0, then rank 1, ... where tile t belongs
+    to rank t % world.  Runs arrive sorted by parameter, and the cost of a row (how early it saturates, how many of
+    its tiles exit early) varies strongly along that order: contiguous shards of the permuted order are balanced."""
+    import torch
+    idx = torch.arange(m, device=device)
+    owner = (idx // _TILE) % world
+    return torch.sort(owner, stable=True).indices
+
+
+def triangle_range(m, rank, world):
+    """Row block [lo, hi) (tile aligned) of the pair triangle {col > row} holding ~1/world of its pairs."""
+    def edge(k):
+        if k >= world:
+            return m
+        b = int(m * (1.0 - (1.0 - k / world) ** 0.5))
+        return min(m, (b // _TILE) * _TILE)
+    return edge(rank), edge(rank + 1)
+
+
 def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, world, dist_mod=None, group=None,
                             backend_ops=None):
     """Row-sharded DBSCAN over `world` ranks; every rank holds the full feature matrix X_t [F, n] (after the
     feature all-gather) and returns identical (assignments, seeds, counts) tensors.
+
+    Balance: every stage runs on a tile-cyclic permutation of its rows (`cyclic_order`); counts and border labels are
+    order independent and are scattered back, the union stage only yields the COMPONENTS of the core graph in the
+    permuted index space (which pairs a rank visits does not matter) and the seed of a component is then taken as the
+    smallest ORIGINAL index among its members, as the sequential algorithm would.  The union stage's pair triangle is
+    cut into equal-area row blocks (`triangle_range`).
 
     `backend_ops` lets the CPU gloo tests substitute the stage kernels with a checker implementation while the
     collectives / index bookkeeping under test stay the same code.
@@ -98,20 +127,27 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
     gl = np.ascontiguousarray(group_len, dtype=np.int32)
     gw = np.ascontiguousarray(group_weight, dtype=np.float64)
     dev = X_t.device
+    i32max = torch.iinfo(torch.int32).max
     # ---- stage 1: neighbour counts of the owned rows -------------------------------------------------------
+    perm = cyclic_order(n, world, dev)
+    Xp = ops.gather(X_t, perm.to(torch.int32))
     r0, r1 = shard_range(n, rank, world)
-    cnt_local = ops.rows_count(X_t, gl, gw, eps, minpts, r0, r1)
-    cnt = _all_gather_rows(cnt_local, shard_sizes(n, world), dist_mod, group)
+    cnt_local = ops.rows_count(Xp, gl, gw, eps, minpts, r0, r1)
+    cnt_perm = _all_gather_rows(cnt_local, shard_sizes(n, world), dist_mod, group)
+    cnt = torch.empty_like(cnt_perm)
+    cnt[perm] = cnt_perm
+    del Xp
     core = cnt >= minpts
     core_idx = torch.nonzero(core).flatten().to(torch.int32)  # ascending = stable compaction
     non_idx = torch.nonzero(~core).flatten().to(torch.int32)
     n_core, n_non = core_idx.numel(), non_idx.numel()
-    Xc = ops.gather(X_t, core_idx)
-    Xn = ops.gather(X_t, non_idx)
     # ---- stage 2: components of the core graph, union-find merge across ranks -------------------------------
     root_label = torch.full((n,), -1, dtype=torch.int32, device=dev)
     if n_core > 0:
-        c0, c1 = shard_range(n_core, rank, world)
+        cp = cyclic_order(n_core, world, dev)
+        core_orig = core_idx[cp].contiguous()  # original index of every permuted core position
+        Xc = ops.gather(X_t, core_orig)
+        c0, c1 = triangle_range(n_core, rank, world)
         parent = ops.rows_union(Xc, gl, gw, eps, c0, c1)
         if world > 1:
             others = [torch.empty_like(parent) for _ in range(world)]
@@ -120,20 +156,26 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
                 if r != rank:
                     ops.merge_parents(parent, others[r])
         root = parent.to(torch.int64)
-        while True:  # pointer jumping to the roots (roots are the smallest member = the seed)
+        while True:  # pointer jumping to the component representatives
             nxt = root[root]
             if torch.equal(nxt, root):
                 break
             root = nxt
-        core_seed = core_idx[root].contiguous()  # original index of each core's seed
-        root_label[core_idx.long()] = core_seed
+        # seed of a component = its smallest original index (sparse_clustering.jl:149-157 visits points in order)
+        seed_of = torch.full((n_core,), i32max, dtype=torch.int32, device=dev)
+        seed_of.scatter_reduce_(0, root, core_orig, reduce="amin", include_self=True)
+        core_seed = seed_of[root].contiguous()  # per permuted core position
+        root_label[core_orig.long()] = core_seed
         # ---- stage 3: border points ----------------------------------------------------------------------
         if n_non > 0:
+            bp = cyclic_order(n_non, world, dev)
+            non_orig = non_idx[bp].contiguous()
+            Xn = ops.gather(X_t, non_orig)
             b0, b1 = shard_range(n_non, rank, world)
             best_local = ops.rows_border(Xn, b0, b1, Xc, core_seed, gl, gw, eps)
             best = _all_gather_rows(best_local, shard_sizes(n_non, world), dist_mod, group)
-            lab = torch.where(best == torch.iinfo(torch.int32).max, torch.full_like(best, -1), best)
-            root_label[non_idx.long()] = lab
+            lab = torch.where(best == i32max, torch.full_like(best, -1), best)
+            root_label[non_orig.long()] = lab
     return ops.labels(root_label)
 
 
