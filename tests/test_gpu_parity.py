@@ -328,6 +328,24 @@ def test_c5_batched_converged(gpu, orc):
     print("c5 converged parity", stats)
 
 
+@pytest.mark.parametrize("N,filt", [(40, None), (64, None), (97, [0, 5, 63, 64, 95, 96]), (128, None)])
+def test_tensor_core_kernel_network_sizes(gpu, orc, N, filt):
+    """The tcgen05 integrator maps oscillator r to row r of a 128-row MMA tile: sizes that leave whole warps idle
+    (N = 40, 64), a size with a one-row last warp plus a state_filter straddling the warp edges (N = 97), and the full
+    tile (N = 128) — converged tolerances, every run must match the oracle to 1e-6."""
+    m = gpu
+    prob, _ = cases.c5_problem(m, 48, N=N, seed=20 + N, tspan=(0.0, 60.0))
+    if filt is not None:
+        prob.eval_ode_func = m.EvalOdeRun(state_filter=[f + 1 for f in filt], eval_funcs=(m.mean, m.std), cyclic_setback=True)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10**7)
+    sol = m.solve(prob, **kw)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
+    assert np.array_equal(sol.retcode, ref["retcode"])
+    assert sol.feat.shape[1] == (N if filt is None else len(filt))
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.9)
+
+
 def test_batched_ring_and_filter(gpu, orc):
     """non_local_kuramoto_ring N=40 (phase_delay swept) and a state_filter subset on the batched kernel."""
     m = gpu
