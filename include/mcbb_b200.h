@@ -213,6 +213,41 @@ int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double
 int mcbb_knn_dist_dense_dev(const double* D_dev, int64_t n, int32_t k, int32_t K, double* kth_dev,
                             double* cum_dev, void* stream);
 
+/* ---- sparse interchange ------------------------------------------------------------
+ * Replace the NonzeroSparseMatrix branch of distance_matrix (src/eval_clustering.jl:541-550 builds it column by
+ * column from a dense row; src/sparse_clustering.jl:37-110 is the type): only entries with d < sparse_threshold are
+ * stored, as d - sparse_threshold, in compressed columns; unstored entries read as the threshold.  Here the columns
+ * are produced from the feature matrix without ever materialising D:
+ *   1  mcbb_distance_sparse_count   count_out[c] = stored entries of column c (the diagonal, d = 0, included)
+ *      -- caller forms colptr (exclusive prefix sum, 0-based, n+1 entries) and allocates rowval / nzval
+ *   2  mcbb_distance_sparse_fill    rowval (0-based, ascending within a column) and nzval = d - sparse_threshold
+ * mcbb_dbscan_sparse replaces dbscan(::AbstractNonzeroSparseMatrix, eps, minpts) (src/sparse_clustering.jl:126-215):
+ * same labels as the sequential algorithm on the matrix whose unstored entries equal `value`. */
+int mcbb_distance_sparse_count(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, double sparse_threshold, int32_t* count_out);
+/* rows [row0,row1) of D as contiguous n-vectors (rows_out[(i-row0)*n + j] = D[i,j]): the unit that
+ * distance_matrix_mmap (src/eval_clustering.jl:317-406) appends to its file, so that D never has to fit in memory */
+int mcbb_distance_matrix_rows(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                              const double* group_weight, int64_t row0, int64_t row1, double* rows_out);
+int mcbb_distance_matrix_rows_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                  const double* group_weight, int64_t row0, int64_t row1, double* rows_dev,
+                                  void* stream);
+int mcbb_distance_sparse_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                   const double* group_weight, double sparse_threshold, int32_t* count_dev,
+                                   void* stream);
+int mcbb_distance_sparse_fill(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                              const double* group_weight, double sparse_threshold, const int64_t* colptr,
+                              int32_t* rowval_out, double* nzval_out);
+int mcbb_distance_sparse_fill_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                  const double* group_weight, double sparse_threshold, const int64_t* colptr_dev,
+                                  int64_t nnz, int32_t* rowval_dev, double* nzval_dev, void* stream);
+int mcbb_dbscan_sparse(int64_t n, const int64_t* colptr, const int32_t* rowval, const double* nzval, double value,
+                       double eps, int32_t minpts, int64_t* assignments, int64_t* seeds, int64_t* counts,
+                       int64_t* n_clusters);
+int mcbb_dbscan_sparse_dev(int64_t n, const int64_t* colptr_dev, const int32_t* rowval_dev, const double* nzval_dev,
+                           double value, double eps, int32_t minpts, int64_t* assignments_dev, int64_t* seeds_dev,
+                           int64_t* counts_dev, int64_t* n_clusters_host, void* stream);
+
 /* ---- rank-sharded DBSCAN stages (one process per GPU; the collectives stay with the caller) --------------
  * The pair space shards by point rows; rank r owns rows [row0,row1).  All pointers are device pointers.
  *   1  mcbb_dbscan_rows_count_dev    neighbour counts (self included) of the owned rows against all n columns

@@ -650,11 +650,9 @@ def feature_groups(sol, prob, weights, relative_parameter=False):
     return X, np.asarray(glen, dtype=np.int32), np.asarray(weights, dtype=np.float64)
 
 
-def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
-                    nbin_default=50, materialize=True):
-    """distance_matrix(sol, prob, weights; relative_parameter, histograms, use_ecdf, k_bin, nbin_default) with the
-    default L1 distance_func / wasserstein_histogram_distance (eval_clustering.jl:164-241).
-    materialize=False returns a B200FeatureMatrix (distances are then recomputed on the fly by dbscan)."""
+def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_ecdf, k_bin, nbin_default):
+    """Feature matrix X [N_mc, F] + L1 groups (lengths, weights) whose weighted group sums are the reference distance
+    (eval_clustering.jl:164-241), for the plain and the histogram variant; also the histogram edges / bin widths."""
     hist_edges, bin_widths = [], []
     if histograms:
         # per-dimension measures are replaced by per-run Float32 ECDF rows over common edges; the distance of two
@@ -692,6 +690,16 @@ def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=Fal
         glen, gw = np.asarray(glen, dtype=np.int32), np.asarray(gw, dtype=np.float64)
     else:
         X, glen, gw = feature_groups(sol, prob, weights, relative_parameter)
+    return X, glen, gw, hist_edges, bin_widths
+
+
+def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
+                    nbin_default=50, materialize=True):
+    """distance_matrix(sol, prob, weights; relative_parameter, histograms, use_ecdf, k_bin, nbin_default) with the
+    default L1 distance_func / wasserstein_histogram_distance (eval_clustering.jl:164-241).
+    materialize=False returns a B200FeatureMatrix (distances are then recomputed on the fly by dbscan)."""
+    X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
+                                                             use_ecdf, k_bin, nbin_default)
     if not materialize:
         return B200FeatureMatrix(X, glen, gw, weights, relative_parameter)
     n = X.shape[0]
@@ -710,6 +718,105 @@ def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=Fal
     return DistanceMatrix(D, weights, relative_parameter)
 
 
+class NonzeroSparseMatrix:
+    """NonzeroSparseMatrix (src/sparse_clustering.jl:37-110): compressed columns holding d - value for the stored
+    entries; every unstored entry reads as `value`.  colptr / rowval are 0-based here (Julia's are 1-based)."""
+
+    def __init__(self, colptr, rowval, nzval, value, n):
+        self.colptr, self.rowval, self.nzval, self.value, self.n = colptr, rowval, nzval, value, int(n)
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def __getitem__(self, ij):
+        i, j = ij
+        lo, hi = self.colptr[j], self.colptr[j + 1]
+        k = lo + np.searchsorted(self.rowval[lo:hi], i)
+        if k < hi and self.rowval[k] == i:
+            return self.nzval[k] + self.value
+        return self.value
+
+    def toarray(self):
+        D = np.full((self.n, self.n), self.value, dtype=self.nzval.dtype, order="F")
+        cols = np.repeat(np.arange(self.n), np.diff(self.colptr))
+        D[self.rowval, cols] = self.nzval + self.value
+        return D
+
+
+def distance_matrix_sparse(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
+                           nbin_default=50, sparse_threshold=np.inf, el_type=np.float32):
+    """distance_matrix_sparse (eval_clustering.jl:451-559): only distances below `sparse_threshold` are kept, as a
+    NonzeroSparseMatrix.  The columns come straight from the feature matrix (two passes over the pair tiles on the
+    GPU), D is never materialised.  Distances are accumulated in Float64 and rounded to `el_type` once (the reference
+    accumulates in `el_type`)."""
+    if not np.isfinite(sparse_threshold) or not sparse_threshold > 0:
+        raise MCBBError("sparse_threshold must be a finite positive number")
+    X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
+                                                             use_ecdf, k_bin, nbin_default)
+    n = X.shape[0]
+    thr = float(el_type(sparse_threshold))
+    ip, dp, lp = abi.c_int32_p, abi.c_double_p, abi.c_int64_p
+    cnt = np.zeros(n, dtype=np.int32)
+    check(lib().mcbb_distance_sparse_count(X.ctypes.data_as(dp), n, len(glen), glen.ctypes.data_as(ip),
+                                           gw.ctypes.data_as(dp), thr, cnt.ctypes.data_as(ip)))
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cnt, out=colptr[1:])
+    rowval = np.zeros(int(colptr[-1]), dtype=np.int32)
+    nzval = np.zeros(int(colptr[-1]), dtype=np.float64)
+    check(lib().mcbb_distance_sparse_fill(X.ctypes.data_as(dp), n, len(glen), glen.ctypes.data_as(ip),
+                                          gw.ctypes.data_as(dp), thr, colptr.ctypes.data_as(lp),
+                                          rowval.ctypes.data_as(ip), nzval.ctypes.data_as(dp)))
+    S = NonzeroSparseMatrix(colptr, rowval, nzval.astype(el_type), el_type(thr), n)
+    if histograms:
+        return DistanceMatrixHist(S, weights, relative_parameter, hist_edges, bin_widths, use_ecdf, k_bin)
+    return DistanceMatrix(S, weights, relative_parameter)
+
+
+def distance_matrix_mmap(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
+                         nbin_default=50, el_type=np.float32, save_name="mmap-distance-matrix.bin", block_rows=None):
+    """distance_matrix_mmap (eval_clustering.jl:317-406): the matrix goes to `save_name` — two Int64 (N_mc, N_mc)
+    followed by the rows in `el_type` — block of rows by block of rows from the GPU, and is returned memory-mapped
+    (column-major (m, n) view of the file like Mmap.mmap(f, Matrix{el_type}, (m, n)); D is symmetric)."""
+    X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
+                                                             use_ecdf, k_bin, nbin_default)
+    n = X.shape[0]
+    ip, dp = abi.c_int32_p, abi.c_double_p
+    if block_rows is None:
+        block_rows = max(1, min(n, (256 << 20) // (8 * n)))
+    buf = np.zeros((block_rows, n), dtype=np.float64)
+    with open(save_name, "wb") as f:
+        np.array([n, n], dtype=np.int64).tofile(f)
+        for r0 in range(0, n, block_rows):
+            r1 = min(n, r0 + block_rows)
+            check(lib().mcbb_distance_matrix_rows(X.ctypes.data_as(dp), n, len(glen), glen.ctypes.data_as(ip),
+                                                  gw.ctypes.data_as(dp), r0, r1, buf.ctypes.data_as(dp)))
+            blk = buf[: r1 - r0]
+            if np.isnan(blk).any():
+                import warnings
+                warnings.warn("There are some elements NaN in the distance matrix")
+            if np.isinf(blk).any():
+                import warnings
+                warnings.warn("There are some elements Inf in the distance matrix")
+            blk.astype(el_type).tofile(f)
+    D = reload_mmap_distance_matrix(None, save_name, el_type=el_type).data
+    if histograms:
+        return DistanceMatrixHist(D, weights, relative_parameter, hist_edges, bin_widths, use_ecdf, k_bin)
+    return DistanceMatrix(D, weights, relative_parameter)
+
+
+def reload_mmap_distance_matrix(old_instance, binary_file, el_type=np.float32):
+    """reload_mmap_distance_matrix (eval_clustering.jl:411-433): re-attach a distance-matrix file to an instance."""
+    m, n = (int(v) for v in np.fromfile(binary_file, dtype=np.int64, count=2))
+    data = np.memmap(binary_file, dtype=el_type, mode="r", offset=16, shape=(m, n), order="F")
+    if old_instance is None:
+        return DistanceMatrix(data, [], False)
+    if isinstance(old_instance, DistanceMatrixHist):
+        return DistanceMatrixHist(data, old_instance.weights, old_instance.relative_parameter, old_instance.hist_edges,
+                                  old_instance.bin_width, old_instance.ecdf, old_instance.k_bin)
+    return DistanceMatrix(data, old_instance.weights, old_instance.relative_parameter)
+
+
 class DbscanResult:
     """Clustering.DbscanResult: seeds (1-based), assignments (0 = noise), counts."""
 
@@ -720,6 +827,19 @@ class DbscanResult:
 def dbscan(D, eps, minpts):
     """Clustering.dbscan(D, eps, minpts) (eval_clustering.jl:84; algorithm src/sparse_clustering.jl:126-209)."""
     lp = abi.c_int64_p
+    S = D.data if isinstance(D, (DistanceMatrix, DistanceMatrixHist)) else D
+    if isinstance(S, NonzeroSparseMatrix):  # dbscan(::AbstractNonzeroSparseMatrix, ...), sparse_clustering.jl:126-215
+        n = S.n
+        a, s, c = (np.zeros(n, dtype=np.int64) for _ in range(3))
+        k = np.zeros(1, dtype=np.int64)
+        colptr = np.ascontiguousarray(S.colptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(S.rowval, dtype=np.int32)
+        nzval = np.ascontiguousarray(S.nzval, dtype=np.float64)
+        check(lib().mcbb_dbscan_sparse(n, colptr.ctypes.data_as(lp), rowval.ctypes.data_as(abi.c_int32_p),
+                                       nzval.ctypes.data_as(abi.c_double_p), float(S.value), float(eps), int(minpts),
+                                       a.ctypes.data_as(lp), s.ctypes.data_as(lp), c.ctypes.data_as(lp),
+                                       k.ctypes.data_as(lp)))
+        return DbscanResult(s[:k[0]].copy(), a, c[:k[0]].copy())
     if isinstance(D, B200FeatureMatrix):
         n = D.X.shape[0]
     else:

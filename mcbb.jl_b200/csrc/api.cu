@@ -86,6 +86,16 @@ int labels_dev(const int* root_label, long long n, long long* assignments, long 
 int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
                        cudaStream_t st);
 int knn_dist_dense_dev(const double* D, long long n, int k, int K, double* kth, double* cum, cudaStream_t st);
+int distance_rows_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
+                      long long row0, long long row1, double* out, cudaStream_t st);
+int distance_sparse_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                              const double* group_weight, double thr, int* count, cudaStream_t st);
+int distance_sparse_fill_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                             const double* group_weight, double thr, const long long* colptr, long long nnz,
+                             int* rowval, double* nzval, cudaStream_t st);
+int dbscan_sparse_dev(long long n, const long long* colptr, const int* rowval, const double* nzval, double value,
+                      double eps, int minpts, long long* assignments, long long* seeds, long long* counts,
+                      long long* n_clusters_host, cudaStream_t st);
 
 
 // Julia Base (:)(start, step, stop) for Float64 (base/twiceprecision.jl): length and elements.  First the
@@ -553,6 +563,125 @@ int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double
     if (cum_out) MCBB_CUDA_OK(cudaMemcpyAsync(cum_out, d_c, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
+}
+
+int mcbb_distance_sparse_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                   const double* group_weight, double sparse_threshold, int32_t* count_dev,
+                                   void* stream) {
+    if (!X_dev || !count_dev || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    return distance_sparse_count_dev(X_dev, n, n_groups, group_len, group_weight, sparse_threshold, count_dev,
+                                     (cudaStream_t)stream);
+}
+int mcbb_distance_sparse_fill_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                  const double* group_weight, double sparse_threshold, const int64_t* colptr_dev,
+                                  int64_t nnz, int32_t* rowval_dev, double* nzval_dev, void* stream) {
+    if (!X_dev || !colptr_dev || !rowval_dev || !nzval_dev || !group_len || !group_weight)
+        MCBB_FAIL("distance_matrix: NULL argument");
+    return distance_sparse_fill_dev(X_dev, n, n_groups, group_len, group_weight, sparse_threshold,
+                                    (const long long*)colptr_dev, nnz, rowval_dev, nzval_dev, (cudaStream_t)stream);
+}
+int mcbb_dbscan_sparse_dev(int64_t n, const int64_t* colptr_dev, const int32_t* rowval_dev, const double* nzval_dev,
+                           double value, double eps, int32_t minpts, int64_t* assignments_dev, int64_t* seeds_dev,
+                           int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    if (!colptr_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host) MCBB_FAIL("dbscan: NULL argument");
+    return dbscan_sparse_dev(n, (const long long*)colptr_dev, rowval_dev, nzval_dev, value, eps, minpts,
+                             (long long*)assignments_dev, (long long*)seeds_dev, (long long*)counts_dev,
+                             (long long*)n_clusters_host, (cudaStream_t)stream);
+}
+
+static size_t total_features(int32_t n_groups, const int32_t* group_len) {
+    size_t F = 0;
+    for (int g = 0; g < n_groups; g++) F += group_len[g] > 0 ? group_len[g] : 0;
+    return F;
+}
+
+int mcbb_distance_matrix_rows_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                  const double* group_weight, int64_t row0, int64_t row1, double* rows_dev, void* stream) {
+    if (!X_dev || !rows_dev || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    return distance_rows_dev(X_dev, n, n_groups, group_len, group_weight, row0, row1, rows_dev, (cudaStream_t)stream);
+}
+int mcbb_distance_matrix_rows(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                              const double* group_weight, int64_t row0, int64_t row1, double* rows_out) {
+    if (!X || !rows_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
+    if (row0 < 0 || row1 > n || row0 > row1) MCBB_FAIL("distance_matrix: bad row range");
+    const size_t F = total_features(n_groups, group_len);
+    const size_t nb = (size_t)(row1 - row0) * (size_t)n;
+    double* d_X = (double*)scratch_get(40, sizeof(double) * F * (size_t)n);
+    double* d_D = (double*)scratch_get(41, sizeof(double) * (nb > 0 ? nb : 1));
+    if (!d_X || !d_D) MCBB_FAIL("distance_matrix: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_X, X, sizeof(double) * F * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (int rc = distance_rows_dev(d_X, n, n_groups, group_len, group_weight, row0, row1, d_D, st)) return rc;
+    MCBB_CUDA_OK(cudaMemcpyAsync(rows_out, d_D, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_distance_sparse_count(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, double sparse_threshold, int32_t* count_out) {
+    if (!X || !count_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
+    const size_t F = total_features(n_groups, group_len);
+    double* d_X = (double*)scratch_get(40, sizeof(double) * F * (size_t)n);
+    int* d_c = (int*)scratch_get(30, sizeof(int) * (size_t)n);
+    if (!d_X || !d_c) MCBB_FAIL("distance_matrix: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_X, X, sizeof(double) * F * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (int rc = distance_sparse_count_dev(d_X, n, n_groups, group_len, group_weight, sparse_threshold, d_c, st)) return rc;
+    MCBB_CUDA_OK(cudaMemcpyAsync(count_out, d_c, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_distance_sparse_fill(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                              const double* group_weight, double sparse_threshold, const int64_t* colptr,
+                              int32_t* rowval_out, double* nzval_out) {
+    if (!X || !colptr || !rowval_out || !nzval_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
+    if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
+    const long long nnz = colptr[n];
+    if (colptr[0] != 0 || nnz < n) MCBB_FAIL("sparse distance matrix: colptr must start at 0 and hold the diagonal");
+    const size_t F = total_features(n_groups, group_len);
+    double* d_X = (double*)scratch_get(40, sizeof(double) * F * (size_t)n);
+    long long* d_p = (long long*)scratch_get(31, sizeof(long long) * (size_t)(n + 1));
+    int* d_r = (int*)scratch_get(32, sizeof(int) * (size_t)nnz);
+    double* d_v = (double*)scratch_get(33, sizeof(double) * (size_t)nnz);
+    if (!d_X || !d_p || !d_r || !d_v) MCBB_FAIL("distance_matrix: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_X, X, sizeof(double) * F * (size_t)n, cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_p, colptr, sizeof(long long) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if (int rc = distance_sparse_fill_dev(d_X, n, n_groups, group_len, group_weight, sparse_threshold, d_p, nnz, d_r, d_v, st))
+        return rc;
+    MCBB_CUDA_OK(cudaMemcpyAsync(rowval_out, d_r, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(nzval_out, d_v, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_dbscan_sparse(int64_t n, const int64_t* colptr, const int32_t* rowval, const double* nzval, double value,
+                       double eps, int32_t minpts, int64_t* assignments, int64_t* seeds, int64_t* counts,
+                       int64_t* n_clusters) {
+    if (!colptr || !assignments || !seeds || !counts || !n_clusters) MCBB_FAIL("dbscan: NULL argument");
+    if (n < 2) MCBB_FAIL("At least two data points are required.");
+    const long long nnz = colptr[n];
+    if (nnz > 0 && (!rowval || !nzval)) MCBB_FAIL("dbscan: NULL argument");
+    long long* d_p = (long long*)scratch_get(31, sizeof(long long) * (size_t)(n + 1));
+    int* d_r = (int*)scratch_get(32, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1));
+    double* d_v = (double*)scratch_get(33, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+    long long* d_a = (long long*)scratch_get(42, sizeof(long long) * (size_t)n);
+    long long* d_s = (long long*)scratch_get(43, sizeof(long long) * (size_t)n);
+    long long* d_c = (long long*)scratch_get(44, sizeof(long long) * (size_t)n);
+    if (!d_p || !d_r || !d_v || !d_a || !d_s || !d_c) MCBB_FAIL("dbscan: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_p, colptr, sizeof(long long) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        MCBB_CUDA_OK(cudaMemcpyAsync(d_r, rowval, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        MCBB_CUDA_OK(cudaMemcpyAsync(d_v, nzval, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+    long long k = 0;
+    if (int rc = dbscan_sparse_dev(n, d_p, d_r, d_v, value, eps, minpts, d_a, d_s, d_c, &k, st)) return rc;
+    *n_clusters = k;
+    return dbscan_copy_back(n, d_a, d_s, d_c, assignments, seeds, counts, st);
 }
 
 }  // extern "C"

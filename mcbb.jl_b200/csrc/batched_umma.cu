@@ -791,7 +791,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
         for (int i = 0; i < N; i++) fpos[i] = i;
     }
     unsigned char* d_img = (unsigned char*)scratch_get(59, img.size());
-    int* d_deg = (int*)scratch_get(60, sizeof(int) * deg.size());
+    int* d_deg = (int*)scratch_get(38, sizeof(int) * deg.size());
     double* d_bias = (double*)scratch_get(61, sizeof(double) * bias.size());
     int* d_fpos = (int*)scratch_get(62, sizeof(int) * fpos.size());
     if (!d_img || !d_deg || !d_bias || !d_fpos) MCBB_FAIL("solve: device allocation failed");

@@ -398,6 +398,32 @@ int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_
     return launch_tiles_rows<TM_MATERIALIZE>(a, st);
 }
 
+// rows [row0,row1) of D as (row1-row0) contiguous n-vectors: the unit distance_matrix_mmap writes to its file
+// (src/eval_clustering.jl:351-394).  D is symmetric, so the block is produced as columns of the column-major tile
+// kernel: out[(c - row0) * n + r] = d(r, c).
+int distance_rows_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
+                      long long row0, long long row1, double* out, cudaStream_t st) {
+    if (row0 < 0 || row1 > n || row0 > row1) MCBB_FAIL("distance_matrix: bad row range");
+    if (row0 == row1) return 0;
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    TileArgs a = {};
+    a.Xr = a.Xc = X;
+    a.ldr = a.ldc = n;
+    a.r0 = 0;
+    a.r1 = n;
+    a.c0 = row0;
+    a.c1 = row1;
+    a.F = gt.F;
+    a.fw = gt.fw;
+    a.fend = gt.fend;
+    a.fmask = gt.fmask;
+    a.symmetric = 0;
+    a.D = out - n * row0;
+    a.sat_seed = -1;
+    return launch_tiles_rows<TM_MATERIALIZE>(a, st);
+}
+
 // seeds / assignments / counts from root labels (shared by the dense and the feature path)
 static int finalize_labels(const int* root_label, const int* is_seed, long long n, long long* assignments,
                            long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st) {
@@ -663,6 +689,182 @@ int gather_columns_dev(const double* X, long long ld, const int* idx, long long 
     k_gather_cols<<<dim3(nblk(m), F), 256, 0, st>>>(X, ld, idx, m, F, Xout);
     MCBB_LAUNCHED();
     return 0;
+}
+
+// ---- sparse interchange: NonzeroSparseMatrix (src/sparse_clustering.jl:37-110, built column by column in
+// src/eval_clustering.jl:541-550): entries with d < threshold stored as d - threshold in compressed columns ----------
+__global__ void k_add_i32(int* p, long long n, int v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += v;
+}
+__global__ void k_sparse_diag(const long long* colptr, int* fill, int* row, double* val, long long n, double thr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {  // D_ii = 0 < threshold: stored as -threshold
+        const int s = atomicAdd(&fill[i], 1);
+        row[colptr[i] + s] = (int)i;
+        val[colptr[i] + s] = 0. - thr;
+    }
+}
+
+static int sparse_tile_args(TileArgs* a, const double* X, long long n, const GroupTables& gt, double thr) {
+    *a = TileArgs{};
+    a->Xr = a->Xc = X;
+    a->ldr = a->ldc = n;
+    a->r0 = a->c0 = 0;
+    a->r1 = a->c1 = n;
+    a->F = gt.F;
+    a->fw = gt.fw;
+    a->fend = gt.fend;
+    a->fmask = gt.fmask;
+    a->eps = thr;
+    a->symmetric = 1;
+    a->early_exit = gt.early_exit;
+    a->sat_seed = -1;
+    return 0;
+}
+
+// count[c] = number of rows r with D[r,c] < threshold (diagonal included)
+int distance_sparse_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                              const double* group_weight, double thr, int* count, cudaStream_t st) {
+    if (n < 1) MCBB_FAIL("distance_matrix: empty input");
+    if (!(thr > 0)) MCBB_FAIL("sparse_threshold must be positive");
+    if (n > 2147483647LL - 1) MCBB_FAIL("distance_matrix: n exceeds int32 index range");
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(count, n, 1);  // the diagonal
+    MCBB_LAUNCHED();
+    TileArgs a;
+    sparse_tile_args(&a, X, n, gt, thr);
+    a.cnt = count;
+    return launch_tiles_rows<TM_COUNT>(a, st);
+}
+
+// fills rowval (0-based, ascending within each column) and nzval = d - threshold for the layout given by colptr
+int distance_sparse_fill_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                             const double* group_weight, double thr, const long long* colptr, long long nnz,
+                             int* rowval, double* nzval, cudaStream_t st) {
+    if (n < 1) MCBB_FAIL("distance_matrix: empty input");
+    if (!(thr > 0)) MCBB_FAIL("sparse_threshold must be positive");
+    if (nnz > 2147483647LL - 1) MCBB_FAIL("sparse distance matrix: more than 2^31 stored entries");
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    int* fill = (int*)scratch_get(12, sizeof(int) * n);
+    int* row_u = (int*)scratch_get(28, sizeof(int) * (size_t)nnz);
+    double* val_u = (double*)scratch_get(29, sizeof(double) * (size_t)nnz);
+    if (!fill || !row_u || !val_u) MCBB_FAIL("sparse distance matrix: device scratch allocation failed");
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(fill, n, 0);
+    MCBB_LAUNCHED();
+    k_sparse_diag<<<nblk(n), 256, 0, st>>>(colptr, fill, row_u, val_u, n, thr);
+    MCBB_LAUNCHED();
+    TileArgs a;
+    sparse_tile_args(&a, X, n, gt, thr);
+    a.sp_colptr = colptr;
+    a.sp_fill = fill;
+    a.sp_row = row_u;
+    a.sp_val = val_u;
+    if (int rc = launch_tiles_rows<TM_SPARSE>(a, st)) return rc;
+    // rows ascending within every column, like SparseMatrixCSC
+    size_t tb = 0;
+    cub::DeviceSegmentedSort::SortPairs(nullptr, tb, row_u, rowval, val_u, nzval, (int)nnz, (int)n, colptr, colptr + 1, st);
+    void* tmp = scratch_get(47, tb);
+    if (!tmp) MCBB_FAIL("sparse distance matrix: device scratch allocation failed");
+    MCBB_CUDA_OK(cub::DeviceSegmentedSort::SortPairs(tmp, tb, row_u, rowval, val_u, nzval, (int)nnz, (int)n, colptr,
+                                                     colptr + 1, st));
+    g_launch_count.fetch_add(1);
+    return 0;
+}
+
+// DBSCAN on a NonzeroSparseMatrix (src/sparse_clustering.jl:126-215): unstored entries read as `value`
+__global__ void k_sp_count(const long long* colptr, const double* val, long long n, double value, double eps, int* cnt) {
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n) return;
+    int k = 0;
+    for (long long e = colptr[c] + lane; e < colptr[c + 1]; e += 32) k += (val[e] + value < eps);
+    for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    if (lane == 0) cnt[c] = k;
+}
+template <int PASS>  // 0: union over core-core edges, 1: smallest adjacent seed of the non-core columns
+__global__ void k_sp_edges(const long long* colptr, const int* row, const double* val, long long n, double value,
+                           double eps, const int* core, int* parent, int* best) {
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n) return;
+    if (PASS == 0 && !core[c]) return;
+    if (PASS == 1 && core[c]) return;
+    for (long long e = colptr[c] + lane; e < colptr[c + 1]; e += 32) {
+        const int r = row[e];
+        if (!(val[e] + value < eps) || !core[r]) continue;
+        if (PASS == 0) {
+            if (r < (int)c) uf_union(parent, r, (int)c);
+        } else {
+            atomicMin(&best[c], uf_find(parent, r));
+        }
+    }
+}
+__global__ void k_sp_labels(const int* core, int* parent, const int* best, long long n, int* root_label, int* is_seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        if (core[i]) {
+            const int r = uf_find(parent, (int)i);
+            root_label[i] = r;
+            is_seed[i] = (r == (int)i);
+        } else {
+            root_label[i] = best[i] == INT_MAX ? -1 : best[i];
+            is_seed[i] = 0;
+        }
+    }
+}
+__global__ void k_all_one_cluster(long long n, int* root_label, int* is_seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        root_label[i] = 0;
+        is_seed[i] = (i == 0);
+    }
+}
+
+int dbscan_sparse_dev(long long n, const long long* colptr, const int* rowval, const double* nzval, double value,
+                      double eps, int minpts, long long* assignments, long long* seeds, long long* counts,
+                      long long* n_clusters_host, cudaStream_t st) {
+    if (int rc = check_dbscan_args(n, eps, minpts)) return rc;
+    int* cnt = (int*)scratch_get(12, sizeof(int) * n);
+    int* core = (int*)scratch_get(13, sizeof(int) * n);
+    int* noncore = (int*)scratch_get(14, sizeof(int) * n);
+    int* root_label = (int*)scratch_get(19, sizeof(int) * n);
+    int* is_seed = (int*)scratch_get(22, sizeof(int) * n);
+    int* parent = (int*)scratch_get(25, sizeof(int) * n);
+    int* best = (int*)scratch_get(27, sizeof(int) * n);
+    if (!cnt || !core || !noncore || !root_label || !is_seed || !parent || !best)
+        MCBB_FAIL("dbscan: device scratch allocation failed");
+    if (value < eps) {
+        // every unstored pair reads as `value` < eps and every stored one is below `value`: all points are mutual
+        // neighbours, exactly what the reference's region query returns
+        if (n >= minpts) {
+            k_all_one_cluster<<<nblk(n), 256, 0, st>>>(n, root_label, is_seed);
+        } else {
+            k_fill_i32<<<nblk(n), 256, 0, st>>>(root_label, n, -1);
+            MCBB_LAUNCHED();
+            k_fill_i32<<<nblk(n), 256, 0, st>>>(is_seed, n, 0);
+        }
+        MCBB_LAUNCHED();
+        return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
+    }
+    const unsigned wb = nblk(n * 32);
+    k_sp_count<<<wb, 256, 0, st>>>(colptr, nzval, n, value, eps, cnt);
+    MCBB_LAUNCHED();
+    k_core_flags<<<nblk(n), 256, 0, st>>>(cnt, n, minpts, core, noncore);
+    MCBB_LAUNCHED();
+    k_iota_i32<<<nblk(n), 256, 0, st>>>(parent, n);
+    MCBB_LAUNCHED();
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(best, n, INT_MAX);
+    MCBB_LAUNCHED();
+    k_sp_edges<0><<<wb, 256, 0, st>>>(colptr, rowval, nzval, n, value, eps, core, parent, best);
+    MCBB_LAUNCHED();
+    k_sp_edges<1><<<wb, 256, 0, st>>>(colptr, rowval, nzval, n, value, eps, core, parent, best);
+    MCBB_LAUNCHED();
+    k_sp_labels<<<nblk(n), 256, 0, st>>>(core, parent, best, n, root_label, is_seed);
+    MCBB_LAUNCHED();
+    return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
 }
 
 // ---- k_dist / KNN_dist (src/eval_clustering.jl:1504-1553): every row of D sorted ascending -----------------------

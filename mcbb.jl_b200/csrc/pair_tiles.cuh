@@ -14,6 +14,8 @@
 //             TM_COUNT        eps-neighbour counts (DBSCAN pass 1)
 //             TM_UNION        union-find over core-core edges (pass 2)
 //             TM_BORDER       smallest adjacent core root per non-core point (pass 3)
+//             TM_SPARSE       compressed-column fill of the entries below a threshold, stored as d - threshold
+//                             (NonzeroSparseMatrix, src/sparse_clustering.jl:37-110)
 // All three DBSCAN passes stop accumulating a tile as soon as every pair in it is provably >= eps
 // (terms are non-negative, floating-point addition of non-negatives is monotone, so the test is exact).
 #pragma once
@@ -21,7 +23,7 @@
 
 namespace mcbb {
 
-enum TileMode { TM_MATERIALIZE = 0, TM_COUNT = 1, TM_UNION = 2, TM_BORDER = 3 };
+enum TileMode { TM_MATERIALIZE = 0, TM_COUNT = 1, TM_UNION = 2, TM_BORDER = 3, TM_SPARSE = 4 };
 
 constexpr int TILE = 64;   // tile edge
 constexpr int TT = 4;      // register block edge
@@ -46,6 +48,10 @@ struct TileArgs {
     int* parent;     // TM_UNION
     const int* col_root;  // TM_BORDER: root (original index) of each core column
     int* best;            // TM_BORDER: per non-core row, min root seen (init INT_MAX)
+    const long long* sp_colptr;  // TM_SPARSE: [n+1] start of every column (0-based)
+    int* sp_fill;                // TM_SPARSE: [n] entries written so far per column
+    int* sp_row;                 // TM_SPARSE: row index of every stored entry (unordered within a column)
+    double* sp_val;              // TM_SPARSE: d - threshold
     // Saturation skips (exact: DBSCAN only needs core-ness, connectivity and the smallest adjacent seed, all of
     // which are monotone).  A tile is skipped before any feature is loaded when nothing in it can still change:
     int sat_count;        // TM_COUNT: every row (and column, if symmetric) already has >= sat_count neighbours
@@ -301,6 +307,12 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
             if (!(d < a.eps)) continue;  // strict, sparse_clustering.jl:173
             if (MODE == TM_UNION) {
                 uf_union(a.parent, (int)ri, (int)cj);
+            } else if (MODE == TM_SPARSE) {  // symmetric launch: the pair lands in both columns
+                const int s0 = atomicAdd(&a.sp_fill[cj], 1), s1 = atomicAdd(&a.sp_fill[ri], 1);
+                a.sp_row[a.sp_colptr[cj] + s0] = (int)ri;
+                a.sp_val[a.sp_colptr[cj] + s0] = d - a.eps;
+                a.sp_row[a.sp_colptr[ri] + s1] = (int)cj;
+                a.sp_val[a.sp_colptr[ri] + s1] = d - a.eps;
             } else if (MODE == TM_BORDER) {
                 atomicMin(&a.best[ri], a.col_root[cj]);
             }

@@ -16,7 +16,7 @@
 module MCBBB200
 
 using MCBB
-using DiffEqBase, Clustering
+using DiffEqBase, Clustering, SparseArrays, Mmap
 import Clustering: dbscan
 
 const LIB = get(ENV, "MCBB_B200_LIB", "libmcbb_b200.so")
@@ -211,6 +211,53 @@ function distance_matrix_b200(sol, prob, weights; relative_parameter::Bool=false
     check(ccall((:mcbb_distance_matrix, LIB), Cint, (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
                 X, n, length(glen), glen, gw, D))
     MCBB.DistanceMatrix(D, weights, (x, y) -> sum(abs.(x .- y)), nothing, relative_parameter)
+end
+
+"""
+    distance_matrix_sparse_b200(sol, prob, weights; sparse_threshold, el_type=Float32, relative_parameter=false)
+
+`distance_matrix_sparse` (src/eval_clustering.jl:451-559) without the dense rows: the library counts the entries below
+the threshold per column, Julia forms `colptr`, the library fills `rowval` / `nzval = d - threshold`; the result is the
+reference's own `NonzeroSparseMatrix`, so `dbscan(::NonzeroSparseMatrix, ...)` and the cluster analysis run unchanged.
+"""
+function distance_matrix_sparse_b200(sol, prob, weights; sparse_threshold::Number, el_type=Float32, relative_parameter::Bool=false)
+    X, glen, gw = feature_groups(sol, prob, weights; relative_parameter=relative_parameter)
+    n = size(X, 1); thr = Float64(el_type(sparse_threshold))
+    cnt = Vector{Int32}(undef, n)
+    check(ccall((:mcbb_distance_sparse_count, LIB), Cint, (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Float64, Ptr{Int32}),
+                X, n, length(glen), glen, gw, thr, cnt))
+    colptr0 = vcat(Int64(0), cumsum(Int64.(cnt)))                      # 0-based for the library
+    rowval0 = Vector{Int32}(undef, colptr0[end]); nzval = Vector{Float64}(undef, colptr0[end])
+    check(ccall((:mcbb_distance_sparse_fill, LIB), Cint,
+                (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Float64, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}),
+                X, n, length(glen), glen, gw, thr, colptr0, rowval0, nzval))
+    sp = SparseArrays.SparseMatrixCSC(n, n, colptr0 .+ 1, Int64.(rowval0) .+ 1, el_type.(nzval))
+    MCBB.DistanceMatrix(MCBB.NonzeroSparseMatrix(sp, el_type(thr)), weights, (x, y) -> sum(abs.(x .- y)), nothing, relative_parameter)
+end
+
+"""
+    distance_matrix_mmap_b200(sol, prob, weights; el_type=Float32, save_name="mmap-distance-matrix.bin", block_rows=4096)
+
+`distance_matrix_mmap` (src/eval_clustering.jl:317-406): same file (two `Int64`, then the rows in `el_type`), the rows
+come from the device in blocks.
+"""
+function distance_matrix_mmap_b200(sol, prob, weights; el_type=Float32, save_name="mmap-distance-matrix.bin",
+                                   block_rows::Int=4096, relative_parameter::Bool=false)
+    X, glen, gw = feature_groups(sol, prob, weights; relative_parameter=relative_parameter)
+    n = size(X, 1)
+    buf = Matrix{Float64}(undef, n, min(block_rows, n))                # column k = row (r0 + k) of D
+    open(save_name, "w+") do f
+        write(f, Int64(n)); write(f, Int64(n))
+        for r0 in 0:size(buf, 2):(n - 1)
+            r1 = min(n, r0 + size(buf, 2))
+            check(ccall((:mcbb_distance_matrix_rows, LIB), Cint,
+                        (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Int64, Int64, Ptr{Float64}),
+                        X, n, length(glen), glen, gw, r0, r1, buf))
+            write(f, el_type.(view(buf, :, 1:(r1 - r0))))
+        end
+    end
+    f = open(save_name); m = read(f, Int); n2 = read(f, Int)
+    MCBB.DistanceMatrix(Mmap.mmap(f, Matrix{el_type}, (m, n2)), weights, (x, y) -> sum(abs.(x .- y)), nothing, relative_parameter)
 end
 
 "Holds the featurized runs instead of the N x N matrix; `dbscan` recomputes distances tile by tile on the device."

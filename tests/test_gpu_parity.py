@@ -2,6 +2,7 @@
 seeded inputs.  Bit-exact for integer work (DBSCAN labels / seeds / counts), 1e-6 for FP64 features
 (north_star), 1e-12 for distances."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -498,3 +499,50 @@ def test_histogram_mode_distance_matrix(gpu, orc):
         res = m.dbscan(Dh, float(np.median(np.sort(ref, axis=0)[5])), 4)
         rdb = orc.dbscan(Dh.data, float(np.median(np.sort(ref, axis=0)[5])), 4)
         assert np.array_equal(res.assignments, rdb["assignments"])
+
+
+def test_sparse_and_mmap_distance_matrices(gpu, orc, tmp_path):
+    """distance_matrix_sparse -> NonzeroSparseMatrix (entries d < threshold stored as
+    d - threshold, compressed columns with ascending rows) and distance_matrix_mmap (2 x Int64 header + rows of
+    el_type), both against the oracle's dense matrix; dbscan on the sparse matrix == the sequential algorithm on the
+    matrix whose unstored entries read as the threshold (sparse_clustering.jl:126-215), including eps > threshold."""
+    m = gpu
+    prob, weights = cases.c1_problem(m, n_ics=60, seed=21)
+    sol = m.solve(prob)
+    X, gl, gw = m.feature_groups(sol, prob, weights)
+    Dref = orc.distance_matrix(X, gl, gw)
+    n = Dref.shape[0]
+    thr = float(np.quantile(Dref, 0.15))
+    # ---- sparse, Float64 elements: exact
+    S = m.distance_matrix_sparse(sol, prob, weights, sparse_threshold=thr, el_type=np.float64).data
+    keep = Dref < thr
+    assert np.array_equal(np.diff(S.colptr), keep.sum(axis=0))
+    dense = S.toarray()
+    assert np.allclose(dense[keep], Dref[keep], rtol=1e-12, atol=1e-12) and np.all(dense[~keep] == thr)
+    for c in range(0, n, 97):
+        rows = S.rowval[S.colptr[c]:S.colptr[c + 1]]
+        assert np.all(np.diff(rows) > 0) and np.array_equal(rows, np.nonzero(keep[:, c])[0])
+    assert S[3, 3] == 0.0 and S[0, int(np.argmax(Dref[0]))] == thr
+    # ---- DBSCAN on the sparse matrix
+    for eps, minpts in ((0.6 * thr, 5), (thr, 8), (1.5 * thr, 3)):
+        ref = orc.dbscan(np.asfortranarray(dense), eps, minpts)
+        res = m.dbscan(S, eps, minpts)
+        assert np.array_equal(res.assignments, ref["assignments"]), (eps, minpts)
+        assert np.array_equal(res.seeds, ref["seeds"]) and np.array_equal(res.counts, ref["counts"])
+    # ---- sparse, default Float32 elements
+    S32 = m.distance_matrix_sparse(sol, prob, weights, sparse_threshold=thr).data
+    assert S32.nzval.dtype == np.float32 and np.allclose(S32.toarray()[keep], Dref[keep], rtol=1e-6, atol=1e-6 * thr)
+    with pytest.raises(m.MCBBError):
+        m.distance_matrix_sparse(sol, prob, weights)  # the reference's default threshold Inf stores d - Inf
+    # ---- mmap file
+    name = str(tmp_path / "mmap-distance-matrix.bin")
+    Dm = m.distance_matrix_mmap(sol, prob, weights, save_name=name, block_rows=77)
+    raw = np.fromfile(name, dtype=np.int64, count=2)
+    assert list(raw) == [n, n] and os.path.getsize(name) == 16 + 4 * n * n
+    assert Dm.data.dtype == np.float32 and np.allclose(np.asarray(Dm.data), Dref, rtol=1e-6, atol=1e-6)
+    D64 = m.distance_matrix_mmap(sol, prob, weights, save_name=name, el_type=np.float64)
+    assert np.allclose(np.asarray(D64.data), Dref, rtol=1e-12, atol=1e-12)
+    again = m.reload_mmap_distance_matrix(D64, name, el_type=np.float64)
+    assert np.array_equal(np.asarray(again.data), np.asarray(D64.data)) and again.weights == D64.weights
+    res = m.dbscan(np.asarray(D64.data, dtype=np.float64), 0.6 * thr, 5)
+    assert np.array_equal(res.assignments, orc.dbscan(Dref, 0.6 * thr, 5)["assignments"])
