@@ -34,6 +34,7 @@ namespace mcbb {
 
 constexpr int UM_NSLOT = 8;  // u, k1..k7
 constexpr int UM_A_BYTES = 128 * 128;
+constexpr int UM_MAX_KL_BINS = 64;
 
 struct UmmaArgs {
     int N, KS, n_sms;
@@ -50,6 +51,11 @@ struct UmmaArgs {
     int n_meas, meas[MCBB_MAX_MEAS], n_filter, cyclic;
     SolveIO io;
     unsigned long long* timing;  // [8] phase clocks (TIMING builds only)
+    // empirical_1D_KL_divergence_hist (eval_mc_prob.jl:312-330): the saved samples of the runs in flight are kept in
+    // a global scratch [slot][n_t][N] and binned once mean and std are final
+    int need_kl, kl_bins;
+    double kl_nstd, kl_tol;
+    double* smp;
 };
 
 struct UmSlotCtl {
@@ -242,6 +248,78 @@ __device__ __forceinline__ double um_div(const double a, const double b) {
     y = fma(y, e, y);
     const double q = a * y;
     return fma(fma(-b, q, a), y, q);
+}
+
+// KL divergence of the saved samples of one state dimension to the normal distribution with their mean and standard
+// deviation, on the histogram of empirical_1D_KL_divergence_hist (eval_mc_prob.jl:312-330; same arithmetic as the lane
+// kernel, lane_core.cuh).  Sample k of the dimension is smp[k * stride], k = 1 .. n_t - 1.
+// The per-thread histogram lives in shared memory when the caller can lend some (hs[bin * 128 + thread]): a local
+// array indexed by a data-dependent bin scatters over 32 cache lines per warp access.
+__device__ double um_kl_hist(const double* smp, const long long stride, const int n_t, const double mu, const double sig,
+                             const int nb, const double nstd, const double tol, unsigned short* hs) {
+    const double NaN = nan("");
+    const double kq = (nb - 1) / 2.;
+    const double bw = (nstd * sig) / kq;
+    const double start = mu - kq * bw, stop = mu + kq * bw;
+    int nc = 0;
+    if (sig >= tol) nc = julia_range_len(start, bw, stop);
+    if (nc > nb) nc = nb;
+    if (sig != sig) return NaN;  // NaN std (non-finite samples): the reference's KL is NaN
+    if (nc <= 0) return 0.;      // sig < sig_tol
+    int hist[UM_MAX_KL_BINS];
+    if (hs) {
+        for (int b = 0; b < nc; b++) hs[b * 128] = 0;
+    } else {
+        for (int b = 0; b < nc; b++) hist[b] = 0;
+    }
+    const double hb = bw / 2.;
+    const double last_edge = kq * bw + hb;  // `mu` missing: eval_mc_prob.jl:328
+    const double e1 = start - hb, ibw = 1. / bw;
+    auto edge = [&](const int m) { return fma((double)(m - 1), bw, start) - hb; };  // edges 1..nc (ascending)
+    // fit(Histogram, u, edges; closed=:left) = searchsortedlast on the vector [edge(1..nc), last_edge].  Its bisection
+    // probes last_edge only after x >= edge(nc) (everything before it is ascending), so the result is: r = position
+    // among the ascending edges — taken directly and corrected against the very same edge expression — and, when
+    // r == nc, bin nc if x < last_edge, else outside.  Eight samples are fetched at a time (the scratch lives in
+    // L2 / HBM: keep the loads in flight).
+    for (int k0 = 1; k0 < n_t; k0 += 8) {
+        double xs[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) xs[q] = (k0 + q < n_t) ? __ldcg(smp + (long long)(k0 + q) * stride) : nan("");
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const double x = xs[q];
+            if (!(x == x)) continue;  // NaN compares false everywhere: the bisection runs off the right end
+            const double f = floor((x - e1) * ibw) + 1.;
+            int r = f < 0. ? 0 : (f > (double)nc ? nc : (int)f);
+            while (r >= 1 && x < edge(r)) r--;
+            while (r < nc && x >= edge(r + 1)) r++;
+            if (r >= 1 && (r < nc || x < last_edge)) {
+                if (hs)
+                    hs[(r - 1) * 128] += 1;
+                else
+                    hist[r - 1] += 1;
+            }
+        }
+    }
+    double tot = 0., rs = 0.;
+    double qn[UM_MAX_KL_BINS];  // unnormalised normal weights of the bin centres
+    for (int b = 0; b < nc; b++) {
+        if (hs) hist[b] = hs[b * 128];
+        tot += (double)hist[b];
+        const double z = (fma((double)b, bw, start) - mu) / sig;
+        qn[b] = exp(-(z * z) / 2.);
+        rs += qn[b];
+    }
+    if (tot == 0.) return NaN;  // 0/0 weights -> NaN, as StatsBase would give
+    double kl = 0.;
+    for (int b = 0; b < nc; b++) {
+        const double p = (double)hist[b] / tot;
+        if (p > 0.) {
+            const double q = qn[b] / rs;
+            kl += p * log(p / q);
+        }
+    }
+    return kl;
 }
 
 // TIMING = true: thread 0 of every CTA accumulates clock64() per phase into a.timing (development aid,
@@ -454,7 +532,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
         UM_TICK(0)  // error partials + controller + barriers
 
         // ---- row owners: samples of the accepted step, u <- u_new, results of finished runs, new initial state ----
-        bool any_init = false;
+        bool any_init = false, any_fin = false;
         unsigned runmask = 0u;  // bit j: slot j integrates (its stage slots are live)
 #pragma unroll
         for (int j = 0; j < JB; j++) {
@@ -492,6 +570,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                                 x = x - as[j];
                             }
                         }
+                        if (a.smp && valid) a.smp[(((size_t)blockIdx.x * JB + j) * n_t + k) * N + row] = x;
                         const double delta = x - am[j];
                         if (fabs(delta) <= 1.7976931348623157e308) {
                             const double mnew = fma(delta, um_div(1., (double)k), am[j]);
@@ -510,8 +589,15 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                 const bool ok = c.fin_ok != 0;
                 const double mean = ok ? am[j] : nan("");
                 const double sd = ok ? sqrt((a2[j] < 0. ? 0. : a2[j]) / (double)(n_t - 2)) : nan("");
+                double kl = nan("");
+                if (a.need_kl && ok)
+                    kl = um_kl_hist(a.smp + ((size_t)blockIdx.x * JB + j) * n_t * N + row, N, n_t, mean, sd, a.kl_bins, a.kl_nstd,
+                                    a.kl_tol,
+                                    // the digit panel is dead between two rounds: lend it as histogram scratch
+                                    (JB * 2048 >= a.kl_bins * 256) ? reinterpret_cast<unsigned short*>(sB) + tid : nullptr);
                 for (int m = 0; m < a.n_meas; m++)
-                    a.io.feat[((long long)m * a.n_filter + fpos) * n_mc + c.fin_run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
+                    a.io.feat[((long long)m * a.n_filter + fpos) * n_mc + c.fin_run] =
+                        (a.meas[m] == MCBB_MEAS_MEAN) ? mean : (a.meas[m] == MCBB_MEAS_STD) ? sd : kl;
             }
             if (c.fresh) {
                 if (valid) {
@@ -523,7 +609,9 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             }
             any_init |= (c.mode == MODE_INIT);
             runmask |= (c.mode == MODE_RUN ? 1u : 0u) << j;
+            any_fin |= (c.fin != 0);
         }
+        if (any_fin && a.need_kl) __syncthreads();  // the digit panel served as histogram scratch: all done before it is rewritten
         if (all_done) break;
         UM_TICK(1)  // samples, update, results, refill
 
@@ -749,12 +837,13 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     *handled = false;
     const int N = S.n_osc;
     if (S.system != MCBB_SYS_KURAMOTO_NETWORK || hs == nullptr) return 0;
-    if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1 || F.matrix_meas) return 0;
+    if (o.alg != MCBB_ALG_TSIT5 || F.n_global > 0 || F.n_comp != 1 || F.matrix_meas) return 0;
+    if (F.need_kl && (F.kl_bins > UM_MAX_KL_BINS || F.kl_bins < 3)) return 0;
     if (N < 33 || N > 128) return 0;  // one 128-row MMA tile; small networks stay on the mma.sync kernel
     if (io.n_t > UM_MAX_NT) return 0;  // save times are kept in the constant bank
     if (getenv("MCBB_NO_IMMA") || getenv("MCBB_NO_UMMA")) return 0;
     for (int m = 0; m < F.n_meas; m++)
-        if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
+        if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD && F.meas[m] != MCBB_MEAS_KL_HIST) return 0;
     double uw = 0.;  // unit-weight adjacency?
     for (size_t q = 0; q < (size_t)N * N; q++) {
         const double v = hs->mat_a[q];
@@ -837,6 +926,15 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.n_sms = sms;
     const long long want = (io.n_mc + pick->jb - 1) / pick->jb;
     const int grid = (int)std::min<long long>(want, (long long)sms * pick->per_sm);
+    a.need_kl = F.need_kl;
+    a.kl_bins = F.kl_bins;
+    a.kl_nstd = F.kl_nstd;
+    a.kl_tol = F.kl_tol;
+    a.smp = nullptr;
+    if (a.need_kl) {
+        a.smp = (double*)scratch_get(39, sizeof(double) * (size_t)grid * pick->jb * (size_t)io.n_t * (size_t)N);
+        if (!a.smp) MCBB_FAIL("solve: device allocation failed");
+    }
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     int rc = 1;

@@ -546,3 +546,23 @@ def test_sparse_and_mmap_distance_matrices(gpu, orc, tmp_path):
     assert np.array_equal(np.asarray(again.data), np.asarray(D64.data)) and again.weights == D64.weights
     res = m.dbscan(np.asarray(D64.data, dtype=np.float64), 0.6 * thr, 5)
     assert np.array_equal(res.assignments, orc.dbscan(Dref, 0.6 * thr, 5)["assignments"])
+
+
+def test_tensor_core_kernel_default_measures_with_kl(gpu, orc):
+    """The reference's default eval_ode_run measures (mean, std, empirical_1D_KL_divergence_hist) on a unit-weight
+    Kuramoto network go through the tcgen05 integrator too: the saved samples of the runs in flight are kept in a
+    device scratch and binned once mean / std are final.  Converged tolerances; KL compared with its 1-ulp bin-count
+    quirk handled by compare_features."""
+    m = gpu
+    prob, _ = cases.c5_problem(m, 60, N=48, seed=31, tspan=(0.0, 80.0))
+    prob.eval_ode_func = m.EvalOdeRun(eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist), cyclic_setback=True)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10**7)
+    before = m.kernel_launch_count()
+    sol = m.solve(prob, **kw)
+    assert m.kernel_launch_count() - before <= 3  # one integrator launch: no second (replay) pass of the lane kernels
+    assert sol.feat.shape == (60, 48, 3)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
+    assert np.array_equal(sol.retcode, ref["retcode"])
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.8)
+    assert np.isfinite(sol.feat[:, :, 2]).mean() > 0.9
