@@ -286,7 +286,7 @@ def main():
     roofline = {
         "bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value > 0 else None, "traffic": traffic,
-        "kernel": "k_solve_batched_umma<4,4> (tcgen05.mma kind::i8 + TMEM)", "traffic_ncu": traffic_ncu,
+        "kernel": "k_solve_batched_umma<6,4> (tcgen05.mma kind::i8, A and accumulators in TMEM)", "traffic_ncu": traffic_ncu,
         "peak_source": "measured in this run by the library's DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 "
                        "entry; nominal B200 ~37 TFLOP/s)",
         "achieved_dense_equiv": fl_dense / (ms_total * 1e-3) / world / 1e12,

@@ -273,6 +273,14 @@ const char* mcbb_version(void) { return "mcbb_b200 0.1.0 (sm_100a)"; }
 int mcbb_init(int device) {
     MCBB_CUDA_OK(cudaSetDevice(device));
     MCBB_CUDA_OK(cudaFree(0));
+    // The library is compiled for sm_100a only (tcgen05 / tensor memory have no forward-compatible PTX): fail here,
+    // with a readable message, rather than with "no kernel image" at the first launch.
+    int major = 0, minor = 0;
+    MCBB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    MCBB_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10 || minor != 0)
+        MCBB_FAIL("mcbb_init: device " + std::to_string(device) + " has compute capability " + std::to_string(major) + "." +
+                  std::to_string(minor) + "; this library is built for sm_100a (B200) only");
     return 0;
 }
 

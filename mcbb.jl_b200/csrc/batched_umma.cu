@@ -255,7 +255,7 @@ __device__ __forceinline__ double um_div(const double a, const double b) {
 // kernel, lane_core.cuh).  Sample k of the dimension is smp[k * stride], k = 1 .. n_t - 1.
 // The per-thread histogram lives in shared memory when the caller can lend some (hs[bin * 128 + thread]): a local
 // array indexed by a data-dependent bin scatters over 32 cache lines per warp access.
-__device__ double um_kl_hist(const double* smp, const long long stride, const int n_t, const double mu, const double sig,
+__device__ __noinline__ double um_kl_hist(const double* smp, const long long stride, const int n_t, const double mu, const double sig,
                              const int nb, const double nstd, const double tol, unsigned short* hs) {
     const double NaN = nan("");
     const double kq = (nb - 1) / 2.;
@@ -324,7 +324,9 @@ __device__ double um_kl_hist(const double* smp, const long long stride, const in
 
 // TIMING = true: thread 0 of every CTA accumulates clock64() per phase into a.timing (development aid,
 // MCBB_UMMA_TIMING=1; the compiler may move arithmetic across the ticks, so treat the split as approximate)
-template <int JB, int MINB, bool TIMING = false>
+// KL = true: the instantiation that keeps the saved samples and evaluates the KL-histogram measure (a separate
+// instantiation: the call and the sample stores cost the plain mean / std kernel ~5 % through register allocation)
+template <int JB, int MINB, bool TIMING = false, bool KL = false>
 __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                                 x = x - as[j];
                             }
                         }
-                        if (a.smp && valid) a.smp[(((size_t)blockIdx.x * JB + j) * n_t + k) * N + row] = x;
+                        if (KL && valid) a.smp[(((size_t)blockIdx.x * JB + j) * n_t + k) * N + row] = x;
                         const double delta = x - am[j];
                         if (fabs(delta) <= 1.7976931348623157e308) {
                             const double mnew = fma(delta, um_div(1., (double)k), am[j]);
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                 const double mean = ok ? am[j] : nan("");
                 const double sd = ok ? sqrt((a2[j] < 0. ? 0. : a2[j]) / (double)(n_t - 2)) : nan("");
                 double kl = nan("");
-                if (a.need_kl && ok)
+                if (KL && ok)
                     kl = um_kl_hist(a.smp + ((size_t)blockIdx.x * JB + j) * n_t * N + row, N, n_t, mean, sd, a.kl_bins, a.kl_nstd,
                                     a.kl_tol,
                                     // the digit panel is dead between two rounds: lend it as histogram scratch
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             runmask |= (c.mode == MODE_RUN ? 1u : 0u) << j;
             any_fin |= (c.fin != 0);
         }
-        if (any_fin && a.need_kl) __syncthreads();  // the digit panel served as histogram scratch: all done before it is rewritten
+        if (KL && any_fin) __syncthreads();  // the digit panel served as histogram scratch: all done before it is rewritten
         if (all_done) break;
         UM_TICK(1)  // samples, update, results, refill
 
@@ -817,12 +819,16 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
 }
 
-template <int JB, int MINB, bool TIMING = false>
-static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_batched_umma<JB, MINB, TIMING><<<grid, 128, smem, st>>>(a);
+template <int JB, int MINB, bool TIMING = false, bool KL = false>
+static int launch_umma_one(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_umma<JB, MINB, TIMING, KL><<<grid, 128, smem, st>>>(a);
     MCBB_LAUNCHED();
     return 0;
+}
+template <int JB, int MINB, bool TIMING = false>
+static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
+    return a.need_kl ? launch_umma_one<JB, MINB, false, true>(a, smem, grid, st) : launch_umma_one<JB, MINB, TIMING, false>(a, smem, grid, st);
 }
 
 static size_t umma_smem_bytes(int JB, int N, int n_t) {
