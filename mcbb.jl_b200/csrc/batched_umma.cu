@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     const int n_t = a.io.n_t;
     const long long n_mc = a.io.n_mc;
     constexpr unsigned NCOL = 16 * JB;            // MMA N: 16 accumulator columns per trajectory (7 + 7 digits, 2 zero)
-    constexpr int G = JB <= 4 ? JB : (JB % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved
+    constexpr int G = JB <= 4 ? JB : (JB % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved (2 measures the same)
     constexpr int RS = UM_NSLOT * JB + 2;         // row stride (doubles) = 2 (mod 4): 16-byte aligned thread-private
                                                   // blocks whose 128-bit accesses are bank-conflict free
     static_assert(JB % G == 0 && JB % 2 == 0, "batch must be a multiple of the interleave group and even");
