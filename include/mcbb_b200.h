@@ -264,9 +264,21 @@ int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups,
                                int64_t row1, int32_t* count_dev /* row1-row0, exact below minpts and a lower
                                bound >= minpts above it: counting stops once core-ness is decided */,
                                void* stream);
+/* Same counts, plus the first `minpts` neighbours found for every owned row (column indices, unordered):
+ * nbr_dev[(i - row0) * minpts + s], s < min(nfill_dev[i - row0], minpts).  A row that ends below minpts has all its
+ * neighbours in the list, so the border stage (3) can be replaced by a lookup of their seeds. */
+int mcbb_dbscan_rows_count_lists_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                     const double* group_weight, double eps, int32_t minpts, int64_t row0,
+                                     int64_t row1, int32_t* count_dev, int32_t* nbr_dev, int32_t* nfill_dev,
+                                     void* stream);
 int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups,
                                const int32_t* group_len, const double* group_weight, double eps, int64_t row0,
                                int64_t row1, int32_t* parent_dev /* n_core */, void* stream);
+/* adds the edges seen from a further row block to a parent array that already holds some (no reset): lets a rank own
+ * several blocks of the pair triangle, interleaved with the other ranks' */
+int mcbb_dbscan_rows_union_more_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups,
+                                    const int32_t* group_len, const double* group_weight, double eps, int64_t row0,
+                                    int64_t row1, int32_t* parent_dev, void* stream);
 int mcbb_dbscan_merge_parents_dev(int32_t* parent_dev, const int32_t* other_parent_dev, int64_t n_core,
                                   void* stream);
 int mcbb_dbscan_rows_border_dev(const double* Xnon_dev, int64_t n_non, int64_t row0, int64_t row1,

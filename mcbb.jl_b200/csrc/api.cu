@@ -73,9 +73,10 @@ int dbscan_dense_dev(const double* D, long long n, double eps, int minpts, long 
                      long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st);
 
 int rows_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
-                   double eps, int minpts, long long row0, long long row1, int* count, cudaStream_t st);
+                   double eps, int minpts, long long row0, long long row1, int* count, int* nbr, int* nfill,
+                   cudaStream_t st);
 int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32_t* group_len,
-                   const double* group_weight, double eps, long long row0, long long row1, int* parent,
+                   const double* group_weight, double eps, long long row0, long long row1, int* parent, int reset,
                    cudaStream_t st);
 int merge_parents_dev(int* parent, const int* other, long long n_core, cudaStream_t st);
 int rows_border_dev(const double* Xn, long long n_non, long long row0, long long row1, const double* Xc,
@@ -517,14 +518,28 @@ int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups,
                                const double* group_weight, double eps, int32_t minpts, int64_t row0, int64_t row1,
                                int32_t* count_dev, void* stream) {
     if (!X_dev || !count_dev || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
-    return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, row0, row1, count_dev,
-                          (cudaStream_t)stream);
+    return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, row0, row1, count_dev, nullptr,
+                          nullptr, (cudaStream_t)stream);
+}
+int mcbb_dbscan_rows_count_lists_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                                     const double* group_weight, double eps, int32_t minpts, int64_t row0, int64_t row1,
+                                     int32_t* count_dev, int32_t* nbr_dev, int32_t* nfill_dev, void* stream) {
+    if (!X_dev || !count_dev || !nbr_dev || !nfill_dev || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
+    return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, row0, row1, count_dev, nbr_dev,
+                          nfill_dev, (cudaStream_t)stream);
 }
 int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups, const int32_t* group_len,
                                const double* group_weight, double eps, int64_t row0, int64_t row1,
                                int32_t* parent_dev, void* stream) {
     if ((n_core > 0 && (!Xcore_dev || !parent_dev)) || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
-    return rows_union_dev(Xcore_dev, n_core, n_groups, group_len, group_weight, eps, row0, row1, parent_dev,
+    return rows_union_dev(Xcore_dev, n_core, n_groups, group_len, group_weight, eps, row0, row1, parent_dev, 1,
+                          (cudaStream_t)stream);
+}
+int mcbb_dbscan_rows_union_more_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups, const int32_t* group_len,
+                                    const double* group_weight, double eps, int64_t row0, int64_t row1,
+                                    int32_t* parent_dev, void* stream) {
+    if ((n_core > 0 && (!Xcore_dev || !parent_dev)) || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
+    return rows_union_dev(Xcore_dev, n_core, n_groups, group_len, group_weight, eps, row0, row1, parent_dev, 0,
                           (cudaStream_t)stream);
 }
 int mcbb_dbscan_merge_parents_dev(int32_t* parent_dev, const int32_t* other_parent_dev, int64_t n_core, void* stream) {

@@ -271,7 +271,8 @@ constexpr int COL_SAMPLE = 32;
 // if m >~ 6.4 minpts, ...: work ~ n^2 (1/32 + 4/32 u1 + 11/32 u2 + 16/32 u3) with u_k the still-unsaturated fractions,
 // instead of n^2/2.  Counts add up exactly (disjoint column sets).
 static int count_rows(const double* X, long long n, const GroupTables& gt, double eps, int minpts, long long row0,
-                      long long row1, int* cnt /* row1-row0 */, cudaStream_t st, PassTimer* pt) {
+                      long long row1, int* cnt /* row1-row0 */, cudaStream_t st, PassTimer* pt, int* nbr = nullptr,
+                      int* nfill = nullptr, int nbr_cap = 0) {
     const long long m = row1 - row0;
     if (m <= 0) return 0;
     k_fill_i32<<<nblk(m), 256, 0, st>>>(cnt, m, 0);
@@ -293,6 +294,14 @@ static int count_rows(const double* X, long long n, const GroupTables& gt, doubl
     a.cnt = cnt - row0;
     a.sat_count = minpts;
     a.sat_seed = -1;
+    a.nbr = nbr;
+    a.nfill = nfill;
+    a.nbr_cap = nbr_cap;
+    a.nbr_row0 = row0;
+    if (nbr) {
+        k_fill_i32<<<nblk(m), 256, 0, st>>>(nfill, m, 0);
+        MCBB_LAUNCHED();
+    }
     if (n >= (long long)COL_SAMPLE * TILE * 8) {
         static const int bounds[5] = {0, 1, 5, 16, COL_SAMPLE};
         a.col_mod = COL_SAMPLE;
@@ -333,6 +342,7 @@ static int count_rows(const double* X, long long n, const GroupTables& gt, doubl
             b.r0 = 0;
             b.r1 = nu;
             b.cnt = cu;
+            b.rid = uidx;  // neighbour lists stay indexed by the original (row0-relative) row
             b.col_lo = bounds[stage];
             b.col_hi = bounds[stage + 1];
             if (int rc = launch_tiles_rows<TM_COUNT>(b, st)) return rc;
@@ -377,6 +387,21 @@ static int union_rows(const double* Xc, long long n_core, const GroupTables& gt,
     if (int rc = launch_tiles_rows<TM_UNION>(u, st)) return rc;
     if (pt) pt->lap("pass 2 union");
     return 0;
+}
+
+// border points from the neighbour lists recorded in pass 1: smallest seed among the adjacent core points
+__global__ void k_border_from_lists(const int* non_idx, long long n_non, const int* nbr, const int* nfill, int cap,
+                                    const int* core, const int* core_pos, const int* col_root, int* best) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_non) return;
+    const int o = non_idx[k];
+    const int m = min(nfill[o], cap);
+    int b = INT_MAX;
+    for (int s = 0; s < m; s++) {
+        const int q = nbr[(long long)o * cap + s];
+        if (core[q]) b = min(b, col_root[core_pos[q]]);
+    }
+    best[k] = b;
 }
 
 int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
@@ -483,7 +508,14 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
 
     PassTimer pt(st);
     // pass 1: neighbour counts (the diagonal pair, D_pp = 0 < eps, supplies the self count)
-    if (int rc = count_rows(X, n, gt, eps, minpts, 0, n, cnt, st, &pt)) return rc;
+    // neighbour lists of the (eventual) non-core points: minpts entries per point are enough
+    int *nbr = nullptr, *nfill = nullptr;
+    if ((size_t)n * (size_t)minpts * sizeof(int) <= ((size_t)512 << 20) && !getenv("MCBB_DBSCAN_NO_LISTS")) {
+        nbr = (int*)scratch_get(34, sizeof(int) * (size_t)n * (size_t)minpts);
+        nfill = (int*)scratch_get(35, sizeof(int) * (size_t)n);
+        if (!nbr || !nfill) MCBB_FAIL("dbscan: device scratch allocation failed");
+    }
+    if (int rc = count_rows(X, n, gt, eps, minpts, 0, n, cnt, st, &pt, nbr, nfill, minpts)) return rc;
     TileArgs a = {};
     a.F = F;
     a.fw = gt.fw;
@@ -527,7 +559,11 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
     if (n_non > 0) {
         k_fill_i32<<<nblk(n_non), 256, 0, st>>>(best, n_non, INT_MAX);
         MCBB_LAUNCHED();
-        if (n_core > 0) {
+        if (n_core > 0 && nbr) {
+            k_border_from_lists<<<nblk(n_non), 256, 0, st>>>(non_idx, n_non, nbr, nfill, minpts, core, core_pos, col_root, best);
+            MCBB_LAUNCHED();
+            pt.lap("border from the recorded neighbour lists");
+        } else if (n_core > 0) {
             k_gather_cols<<<dim3(nblk(n_non), F), 256, 0, st>>>(X, n, non_idx, n_non, F, Xn);
             MCBB_LAUNCHED();
             // pass 3: border points
@@ -607,24 +643,28 @@ __global__ void k_seed_flags(const int* root_label, long long n, int* is_seed) {
 }
 
 int rows_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
-                   double eps, int minpts, long long row0, long long row1, int* count, cudaStream_t st) {
+                   double eps, int minpts, long long row0, long long row1, int* count, int* nbr, int* nfill,
+                   cudaStream_t st) {
     if (int rc = check_dbscan_args(n, eps, 1)) return rc;
     if (row0 < 0 || row1 > n || row0 > row1) MCBB_FAIL("dbscan rows: bad row range");
+    if ((nbr == nullptr) != (nfill == nullptr)) MCBB_FAIL("dbscan rows: neighbour lists need both arrays");
     GroupTables gt;
     if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
     PassTimer pt(st);
-    return count_rows(X, n, gt, eps, minpts, row0, row1, count, st, &pt);
+    return count_rows(X, n, gt, eps, minpts, row0, row1, count, st, &pt, nbr, nfill, minpts);
 }
 
 int rows_union_dev(const double* Xc, long long n_core, int n_groups, const int32_t* group_len,
-                   const double* group_weight, double eps, long long row0, long long row1, int* parent,
+                   const double* group_weight, double eps, long long row0, long long row1, int* parent, int reset,
                    cudaStream_t st) {
     if (n_core <= 0) return 0;
     if (row0 < 0 || row1 > n_core || row0 > row1) MCBB_FAIL("dbscan rows: bad row range");
     GroupTables gt;
     if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
-    k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
-    MCBB_LAUNCHED();
+    if (reset) {
+        k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
+        MCBB_LAUNCHED();
+    }
     PassTimer pt(st);
     return union_rows(Xc, n_core, gt, eps, row0, row1, parent, st, &pt);
 }

@@ -48,6 +48,14 @@ struct TileArgs {
     int* parent;     // TM_UNION
     const int* col_root;  // TM_BORDER: root (original index) of each core column
     int* best;            // TM_BORDER: per non-core row, min root seen (init INT_MAX)
+    // TM_COUNT, optional: the first nbr_cap neighbours found for every row are recorded (row-local index = rid[ri] or
+    // ri - nbr_row0).  A point that ends below minpts has ALL its neighbours in the list, which is what the border
+    // assignment needs: the third pass over the pair space disappears.
+    int* nbr;
+    int* nfill;
+    int nbr_cap;
+    const int* rid;
+    long long nbr_row0;
     const long long* sp_colptr;  // TM_SPARSE: [n+1] start of every column (0-based)
     int* sp_fill;                // TM_SPARSE: [n] entries written so far per column
     int* sp_row;                 // TM_SPARSE: row index of every stored entry (unordered within a column)
@@ -281,6 +289,11 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
                 if (!(acc[i][j] < a.eps)) continue;  // strict, sparse_clustering.jl:173
                 local++;
                 if (a.symmetric) atomicAdd(&s_cnt[TILE + ty * TT + j], 1);
+                if (a.nbr) {
+                    const long long lr = a.rid ? (long long)a.rid[ri] : ri - a.nbr_row0;
+                    const int slot = atomicAdd(&a.nfill[lr], 1);
+                    if (slot < a.nbr_cap) a.nbr[lr * a.nbr_cap + slot] = (int)cj;
+                }
             }
             if (local) atomicAdd(&s_cnt[tx * TT + i], local);
         }

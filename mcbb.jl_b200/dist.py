@@ -128,12 +128,30 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
     gw = np.ascontiguousarray(group_weight, dtype=np.float64)
     dev = X_t.device
     i32max = torch.iinfo(torch.int32).max
+    import os
+    import time
+    trace = bool(os.environ.get("MCBB_TRACE")) and X_t.is_cuda
+    t_last = [time.perf_counter()]
+
+    def lap(what):
+        if trace:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            print("[mcbb trace] rank %d sharded dbscan: %-28s %9.3f ms" % (rank, what, 1e3 * (now - t_last[0])),
+                  file=__import__("sys").stderr, flush=True)
+            t_last[0] = now
     # ---- stage 1: neighbour counts of the owned rows -------------------------------------------------------
     perm = cyclic_order(n, world, dev)
     Xp = ops.gather(X_t, perm.to(torch.int32))
     r0, r1 = shard_range(n, rank, world)
-    cnt_local = ops.rows_count(Xp, gl, gw, eps, minpts, r0, r1)
+    lists = hasattr(ops, "rows_count_lists") and (r1 - r0) * minpts * 4 <= (512 << 20)
+    if lists:  # also the first minpts neighbours of every owned row: the border stage becomes a lookup
+        cnt_local, nbr_local, nfill_local = ops.rows_count_lists(Xp, gl, gw, eps, minpts, r0, r1)
+    else:
+        cnt_local = ops.rows_count(Xp, gl, gw, eps, minpts, r0, r1)
+    lap("permute + count rows")
     cnt_perm = _all_gather_rows(cnt_local, shard_sizes(n, world), dist_mod, group)
+    lap("all-gather counts")
     cnt = torch.empty_like(cnt_perm)
     cnt[perm] = cnt_perm
     del Xp
@@ -144,17 +162,27 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
     # ---- stage 2: components of the core graph, union-find merge across ranks -------------------------------
     root_label = torch.full((n,), -1, dtype=torch.int32, device=dev)
     if n_core > 0:
+        lap("core flags, index lists")
         cp = cyclic_order(n_core, world, dev)
         core_orig = core_idx[cp].contiguous()  # original index of every permuted core position
         Xc = ops.gather(X_t, core_orig)
-        c0, c1 = triangle_range(n_core, rank, world)
+        lap("core flags + gathers")
+        # the pair triangle {col > row} is cut into 4 * world equal-area row blocks, dealt out cyclically: how many
+        # tiles a block can skip (points that already share a root) varies along the triangle
+        parts = 4 if hasattr(ops, "rows_union_more") else 1
+        c0, c1 = triangle_range(n_core, rank, world * parts)
         parent = ops.rows_union(Xc, gl, gw, eps, c0, c1)
+        for k in range(1, parts):
+            c0, c1 = triangle_range(n_core, rank + k * world, world * parts)
+            ops.rows_union_more(Xc, gl, gw, eps, c0, c1, parent)
+        lap("union rows")
         if world > 1:
             others = [torch.empty_like(parent) for _ in range(world)]
             dist_mod.all_gather(others, parent, group=group)
             for r in range(world):
                 if r != rank:
                     ops.merge_parents(parent, others[r])
+        lap("all-gather + merge parents")
         root = parent.to(torch.int64)
         while True:  # pointer jumping to the component representatives
             nxt = root[root]
@@ -166,8 +194,22 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
         seed_of.scatter_reduce_(0, root, core_orig, reduce="amin", include_self=True)
         core_seed = seed_of[root].contiguous()  # per permuted core position
         root_label[core_orig.long()] = core_seed
+        lap("roots + seeds")
         # ---- stage 3: border points ----------------------------------------------------------------------
-        if n_non > 0:
+        if n_non > 0 and lists:
+            # a non-core point has fewer than minpts neighbours, all of them recorded (as permuted column indices)
+            # by the rank that owned its row in stage 1: its label is the smallest seed among the core ones
+            seed_of_point = torch.full((n,), i32max, dtype=torch.int32, device=dev)
+            seed_of_point[core_orig.long()] = core_seed
+            valid = torch.arange(minpts, device=dev)[None, :] < nfill_local[:, None]
+            q = perm[nbr_local.long().clamp_(0, n - 1)]  # original index of every recorded neighbour
+            best_local = torch.where(valid, seed_of_point[q], torch.full_like(nbr_local, i32max)).amin(dim=1)
+            best_perm = _all_gather_rows(best_local, shard_sizes(n, world), dist_mod, group)
+            best = torch.empty_like(best_perm)
+            best[perm] = best_perm  # by original point index
+            lab = torch.where(best == i32max, torch.full_like(best, -1), best)
+            root_label[non_idx.long()] = lab[non_idx.long()]
+        elif n_non > 0:
             bp = cyclic_order(n_non, world, dev)
             non_orig = non_idx[bp].contiguous()
             Xn = ops.gather(X_t, non_orig)
@@ -176,7 +218,10 @@ def dbscan_features_sharded(X_t, group_len, group_weight, eps, minpts, rank, wor
             best = _all_gather_rows(best_local, shard_sizes(n_non, world), dist_mod, group)
             lab = torch.where(best == i32max, torch.full_like(best, -1), best)
             root_label[non_orig.long()] = lab
-    return ops.labels(root_label)
+    lap("border")
+    out = ops.labels(root_label)
+    lap("labels")
+    return out
 
 
 class _CudaStageOps:
@@ -189,6 +234,16 @@ class _CudaStageOps:
                                                gw.ctypes.data_as(abi.c_double_p), float(eps), int(minpts), r0, r1,
                                                _ptr(out), _stream()))
         return out
+
+    def rows_count_lists(self, X, gl, gw, eps, minpts, r0, r1):
+        import torch
+        out = torch.empty((r1 - r0,), dtype=torch.int32, device=X.device)
+        nbr = torch.zeros((r1 - r0, minpts), dtype=torch.int32, device=X.device)
+        nfill = torch.empty((r1 - r0,), dtype=torch.int32, device=X.device)
+        check(lib().mcbb_dbscan_rows_count_lists_dev(_ptr(X), X.shape[1], len(gl), gl.ctypes.data_as(abi.c_int32_p),
+                                                     gw.ctypes.data_as(abi.c_double_p), float(eps), int(minpts), r0, r1,
+                                                     _ptr(out), _ptr(nbr), _ptr(nfill), _stream()))
+        return out, nbr, nfill
 
     def gather(self, X, idx):
         import torch
@@ -204,6 +259,11 @@ class _CudaStageOps:
                                                gw.ctypes.data_as(abi.c_double_p), float(eps), c0, c1, _ptr(parent),
                                                _stream()))
         return parent
+
+    def rows_union_more(self, Xc, gl, gw, eps, c0, c1, parent):
+        check(lib().mcbb_dbscan_rows_union_more_dev(_ptr(Xc), Xc.shape[1], len(gl), gl.ctypes.data_as(abi.c_int32_p),
+                                                    gw.ctypes.data_as(abi.c_double_p), float(eps), c0, c1, _ptr(parent),
+                                                    _stream()))
 
     def merge_parents(self, parent, other):
         check(lib().mcbb_dbscan_merge_parents_dev(_ptr(parent), _ptr(other), parent.numel(), _stream()))

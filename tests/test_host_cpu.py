@@ -168,9 +168,11 @@ class _CheckerOps:
     """CPU stand-in for the stage kernels (numpy, same contracts as the C-ABI stage entry points), so the
     collectives and index bookkeeping of dist.dbscan_features_sharded can be exercised under gloo."""
 
-    def __init__(self):
+    def __init__(self, lists=True):
         import torch
         self.torch = torch
+        if lists:  # without it dist.dbscan_features_sharded falls back to the pair-space border stage
+            self.rows_count_lists = self._rows_count_lists
 
     def _d(self, Xa, Xb, gl, gw):
         out = np.zeros((Xa.shape[1], Xb.shape[1]))
@@ -183,6 +185,16 @@ class _CheckerOps:
     def rows_count(self, X, gl, gw, eps, minpts, r0, r1):
         Xn = X.numpy()
         return self.torch.from_numpy((self._d(Xn[:, r0:r1], Xn, gl, gw) < eps).sum(1).astype(np.int32))
+
+    def _rows_count_lists(self, X, gl, gw, eps, minpts, r0, r1):
+        Xn = X.numpy()
+        near = self._d(Xn[:, r0:r1], Xn, gl, gw) < eps
+        nbr = np.zeros((r1 - r0, minpts), dtype=np.int32)
+        for i in range(r1 - r0):
+            idx = np.nonzero(near[i])[0][::-1][:minpts]  # any order, only the first minpts
+            nbr[i, :len(idx)] = idx
+        cnt = near.sum(1).astype(np.int32)
+        return self.torch.from_numpy(cnt), self.torch.from_numpy(nbr), self.torch.from_numpy(cnt.copy())
 
     def gather(self, X, idx):
         return X[:, idx.long()].contiguous()
@@ -204,6 +216,10 @@ class _CheckerOps:
                     if a != b:
                         parent[max(a, b)] = min(a, b)
         return self.torch.from_numpy(parent)
+
+    def rows_union_more(self, Xc, gl, gw, eps, c0, c1, parent):
+        extra = self.rows_union(Xc, gl, gw, eps, c0, c1)
+        self.merge_parents(parent, extra)
 
     def merge_parents(self, parent, other):
         p, o = parent.numpy(), other.numpy()
@@ -289,6 +305,9 @@ def test_sharded_dbscan_world2_gloo(mcbb, orc):
     a1, s1, c1 = mcbb.dist.dbscan_features_sharded(torch.from_numpy(X), gl, gw, eps, minpts, 0, 1, None,
                                                    backend_ops=_CheckerOps())
     assert np.array_equal(a1.numpy(), ref["assignments"])
+    a2, s2, c2 = mcbb.dist.dbscan_features_sharded(torch.from_numpy(X), gl, gw, eps, minpts, 0, 1, None,
+                                                   backend_ops=_CheckerOps(lists=False))
+    assert np.array_equal(a2.numpy(), ref["assignments"]) and np.array_equal(s2.numpy(), ref["seeds"])
 
 
 def test_hist_edges_and_ecdf_rows_match_oracle(mcbb, orc):
