@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
     };
     issue_slab(0, 0);
     int buf = 0;
+    bool warp_alive = true;
     for (int f0 = 0; f0 < a.F; f0 += FC, buf ^= 1) {
         const int fc = min(FC, a.F - f0);
         asm volatile("cp.async.wait_group 0;");
@@ -190,8 +191,11 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
         const unsigned emask = a.fmask[f0 / FC];
         const double (*s_r)[TILE] = s_slab[buf][0];
         const double (*s_c)[TILE] = s_slab[buf][1];
+        // warp_alive: some pair of this warp's 64 x 8 block can still fall below eps.  A warp whose pairs are all
+        // provably >= eps (monotone partial sums) stops accumulating — its values no longer matter to any consumer
+        // but the materialising one — while the rest of the tile goes on.
 #pragma unroll 4
-        for (int f = 0; f < fc; f++) {
+        for (int f = 0; f < (warp_alive ? fc : 0); f++) {
             double xr[TT], xc[TT];
 #pragma unroll
             for (int i = 0; i < TT; i++) xr[i] = s_r[f][tx * TT + i];
@@ -214,11 +218,20 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
         }
         if (MODE != TM_MATERIALIZE && a.early_exit && f0 + FC < a.F) {
             bool alive = false;
-            const double w = __ldg(a.fw + f0 + fc - 1);  // weight of the group still open (if any)
+            if (warp_alive) {
+                const double w = __ldg(a.fw + f0 + fc - 1);  // weight of the group still open (if any)
 #pragma unroll
-            for (int i = 0; i < TT; i++)
+                for (int i = 0; i < TT; i++)
 #pragma unroll
-                for (int j = 0; j < TT; j++) alive |= (fma(w, accg[i][j], acc[i][j]) < a.eps);
+                    for (int j = 0; j < TT; j++) alive |= (fma(w, accg[i][j], acc[i][j]) < a.eps);
+                warp_alive = __any_sync(0xffffffffu, alive);
+                if (!warp_alive) {  // freeze the bound (>= eps) as the value the consumers will see
+#pragma unroll
+                    for (int i = 0; i < TT; i++)
+#pragma unroll
+                        for (int j = 0; j < TT; j++) acc[i][j] = fma(w, accg[i][j], acc[i][j]);
+                }
+            }
             if (!__syncthreads_or(alive)) {  // no pair of this tile can still fall below eps
                 asm volatile("cp.async.wait_group 0;");  // do not leave the prefetch in flight
                 return;
