@@ -1,6 +1,6 @@
 // batched_umma.cu — ensemble Tsit5 for kuramoto_network (src/systems.jl:119-130) with a unit-weight adjacency,
-// coupling sums on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in tensor memory),
-// statistics of eval_ode_run (mean / std, eval_mc_prob.jl:191-198) fused into the step.
+// coupling sums on the 5th-generation tensor cores (tcgen05.mma kind::i8, A operand and accumulators in tensor
+// memory), statistics of eval_ode_run (mean / std / KL-hist, eval_mc_prob.jl:191-198, 312-330) fused into the step.
 //
 // Same exact fixed-point algorithm as batched_imma.cu (see fixedpoint.cuh): per right-hand-side evaluation
 //        P = A sin(Y),  Q = A cos(Y)          A: N x N in {0,1},  sin/cos(Y): N x JB
@@ -16,13 +16,15 @@
 //   * one thread per oscillator row (thread r <-> TMEM lane r, tcgen05.ld 32x32b): the thread that produced
 //     sin/cos of element (r, j) is the one that reads row r of P, Q back, so sin/cos and the Welford state stay
 //     in registers and every Runge-Kutta stage vector is thread-private shared memory.  Element ownership
-//     never changes => 8 CTA barriers per step (6 stage hand-offs to the MMA, 2 around the step controller)
-//     instead of 19 in the mma.sync kernel.
-//   * the MMA is asynchronous (one elected thread issues, completion arrives on an mbarrier); several CTAs per
-//     SM keep the FP64 pipe busy while another CTA's MMA round trip (~450 clocks measured,
-//     profiles/microbench/umma_probe.cu) is in flight.
+//     never changes => the stage loop needs no CTA-wide barrier (warps publish their digits on a 4-count
+//     mbarrier, the last one to arrive issues the MMA, the others sleep on a named barrier until its completion
+//     mbarrier flips); 2 CTA barriers per step remain, around the step controller (19 in the mma.sync kernel).
+//   * the MMA is asynchronous; four CTAs per SM keep the FP64 pipe busy while another CTA's MMA round trip
+//     (~450 clocks measured, profiles/microbench/umma_probe.cu) is in flight.
 //
-// Descriptor encodings were pinned bit-exactly on hardware with profiles/microbench/umma_probe.cu.
+// Operand encodings were pinned bit-exactly on hardware with profiles/microbench/umma_probe.cu (shared-memory
+// descriptors, instruction descriptor, A from tensor memory), mbarrier.arrive / pending_count semantics with
+// mbar_probe.cu, FP64 latency / issue numbers with dfma_latency.cu.
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -74,15 +76,6 @@ __device__ __forceinline__ unsigned long long um_desc(const unsigned addr, const
            ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-__device__ __forceinline__ void um_mma_i8(const unsigned d_tmem, const unsigned long long da, const unsigned long long db,
-                                          const unsigned idesc, const unsigned accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // A operand from tensor memory (lane = row, 32-bit column = four consecutive K bytes)
 __device__ __forceinline__ void um_mma_i8_ts(const unsigned d_tmem, const unsigned a_tmem, const unsigned long long db,
                                              const unsigned idesc, const unsigned accumulate) {
@@ -118,15 +111,6 @@ __device__ __forceinline__ void um_mbar_wait(const unsigned mbar, const unsigned
             : "r"(mbar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware until the phase flips
             : "memory");
     }
-}
-
-__device__ __forceinline__ void um_tmem_ld16(const unsigned taddr, unsigned (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"  // same statement: the registers are valid when it retires
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
 }
 
 // 32 lanes x 32 columns (two trajectories), load and wait in one statement
