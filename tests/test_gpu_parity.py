@@ -566,3 +566,28 @@ def test_tensor_core_kernel_default_measures_with_kl(gpu, orc):
     assert np.array_equal(sol.retcode, ref["retcode"])
     cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.8)
     assert np.isfinite(sol.feat[:, :, 2]).mean() > 0.9
+
+
+def test_tensor_core_kernel_retcodes_and_fixed_dt(gpu, orc):
+    """Failure and option paths of the tcgen05 integrator against the oracle: MaxIters at the exact attempt count
+    (a mix of finished and truncated runs), NaN measures for truncated runs, and a user-given initial dt."""
+    m = gpu
+    prob, _ = cases.c5_problem(m, 40, N=40, seed=41, tspan=(0.0, 30.0))
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    full = m.solve(prob, flag_check_inf_nan=False, sort_results=False)
+    limit = int(np.median(full.nsteps[:, 0]))  # about half of the runs need more attempts than this
+    sol = m.solve(prob, maxiters=limit, flag_check_inf_nan=False)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, maxiters=limit)
+    assert np.array_equal(sol.retcode, ref["retcode"])
+    bad = sol.retcode == m.abi.RET_MAXITERS
+    assert 0 < bad.sum() < len(bad)
+    assert np.isnan(sol.feat[bad]).all() and np.isfinite(sol.feat[~bad]).all()
+    assert np.array_equal(sol.nsteps[bad, 0], ref["nsteps"][bad, 0])
+    # user-given initial step (no Hairer-Wanner probe): converged run must still match
+    prob2, _ = cases.c5_problem(m, 24, N=40, seed=43, tspan=(0.0, 30.0))
+    ic0, par0 = prob2.ic.copy(), prob2.par.copy()
+    kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10**7, dt=1e-3)
+    sol2 = m.solve(prob2, **kw)
+    ref2, ctx2 = _oracle_ref(m, orc, prob2, ic0, par0, **kw)
+    assert np.array_equal(sol2.retcode, ref2["retcode"])
+    cases.compare_features(sol2.feat, ref2, orc, *ctx2, min_checked=0.9)
