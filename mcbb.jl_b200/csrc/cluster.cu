@@ -234,10 +234,14 @@ static int upload_groups(int n_groups, const int32_t* group_len, const double* g
 }
 
 template <int MODE>
-static int launch_tiles(const TileArgs& a, cudaStream_t st) {
+static int launch_tiles(const TileArgs& a_in, cudaStream_t st) {
+    TileArgs a = a_in;
     const long long nr = a.r1 - a.r0, nc = a.c1 - a.c0;
     if (nr <= 0 || nc <= 0) return 0;
     dim3 grid((unsigned)((nc + TILE - 1) / TILE), (unsigned)((nr + TILE - 1) / TILE));
+    // symmetric launch over the whole square: fold the lower triangle away instead of launching blocks that return
+    a.fold = (a.symmetric && a.band == 0 && a.col_mod <= 1 && a.r0 == a.c0 && a.r1 == a.c1) ? 1 : 0;
+    if (a.fold) grid.y = grid.x / 2 + 1;
     if (a.band > 0) grid.x = a.symmetric ? (unsigned)(a.band + 1) : (unsigned)(2 * a.band + 1);
     if (a.col_mod > 1) grid.x = ((grid.x + a.col_mod - 1) / a.col_mod) * (unsigned)(a.col_hi - a.col_lo);
     if (grid.y > 65535u) MCBB_FAIL("pair tiles: more than 65535 row tiles in one launch; shard the rows");

@@ -67,6 +67,9 @@ struct TileArgs {
     int sat_union;        // TM_UNION: every row and column already shares one root
     int col_mod, col_lo, col_hi;  // col_mod > 1: only column tiles with (tile index % col_mod) in [col_lo, col_hi) are
                                   // visited: evenly spread, disjoint samples of the columns (progressive counting)
+    int fold;             // symmetric full launch: the grid is nt x (nt/2 + 1); block (x, y) owns tile (y, x) if x >= y,
+                          // else tile (nt - y, nt - 1 - x): every block lands on or above the diagonal, none is launched
+                          // only to return
     int band;             // > 0: only column tiles within `band` tiles of the row tile are visited; blockIdx.x is
                           // the offset (symmetric: 0..band, else -band..band).  Runs are sorted by parameter, so
                           // index neighbours are the likely distance neighbours: a cheap first pass that saturates
@@ -107,8 +110,14 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
                                                              // buffer doubles as the 32 x 64 staging tile of the
                                                              // materialising store
 
-    const long long tr = a.r0 + (long long)blockIdx.y * TILE;
+    long long tr = a.r0 + (long long)blockIdx.y * TILE;
     long long tc = a.c0 + (long long)blockIdx.x * TILE;
+    if (a.fold && blockIdx.x < blockIdx.y) {
+        const long long nt = gridDim.x;
+        if (2 * (long long)blockIdx.y == nt) return;  // the middle row of an even grid is already complete
+        tr = a.r0 + (nt - blockIdx.y) * TILE;
+        tc = a.c0 + (nt - 1 - blockIdx.x) * TILE;
+    }
     if (a.col_mod > 1) {  // blockIdx.x enumerates the sampled tiles: period index * width + offset inside the residue range
         const int wdt = a.col_hi - a.col_lo;
         const long long per = blockIdx.x / wdt;
@@ -259,25 +268,52 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
                     }
             }
             __syncthreads();
+            // Streaming (evict-first) stores: D is written once and is far larger than L2.  Off the diagonal and with
+            // an even leading dimension two neighbouring elements leave as one 16-byte store.
+            const bool vec_ok = ((a.ldr & 1) == 0) && !diag && ((reinterpret_cast<size_t>(a.D) & 15) == 0);
             // direct orientation: for each of the 32 columns, 64 contiguous rows
-            for (int q = tid; q < 32 * TILE; q += 256) {
-                const int cl = q >> 6, rl = q & 63;
-                const long long ri = tr + rl, cj = tc + 32 * half + cl;
-                if (ri < a.r1 && cj < a.c1) {
-                    double d = s_t[cl * TILE + (rl ^ cl)];
-                    if (a.symmetric) {
-                        if (cj < ri && diag) continue;      // lower part of a diagonal tile comes from the mirror
-                        if (cj == ri) d = 0.;
+            if (vec_ok) {
+                for (int q = tid; q < 32 * (TILE / 2); q += 256) {
+                    const int cl = q >> 5, rl = (q & 31) * 2;
+                    const long long ri = tr + rl, cj = tc + 32 * half + cl;
+                    if (cj >= a.c1 || ri >= a.r1) continue;
+                    const double d0 = s_t[cl * TILE + (rl ^ cl)], d1 = s_t[cl * TILE + ((rl + 1) ^ cl)];
+                    if (ri + 1 < a.r1)
+                        __stcs(reinterpret_cast<double2*>(a.D + ri + a.ldr * cj), make_double2(d0, d1));
+                    else
+                        __stcs(a.D + ri + a.ldr * cj, d0);
+                }
+            } else {
+                for (int q = tid; q < 32 * TILE; q += 256) {
+                    const int cl = q >> 6, rl = q & 63;
+                    const long long ri = tr + rl, cj = tc + 32 * half + cl;
+                    if (ri < a.r1 && cj < a.c1) {
+                        double d = s_t[cl * TILE + (rl ^ cl)];
+                        if (a.symmetric) {
+                            if (cj < ri && diag) continue;      // lower part of a diagonal tile comes from the mirror
+                            if (cj == ri) d = 0.;
+                        }
+                        __stcs(a.D + ri + a.ldr * cj, d);
                     }
-                    a.D[ri + a.ldr * cj] = d;
                 }
             }
             // mirrored orientation (symmetric only): D[cj, ri] — contiguous in cj for fixed ri
-            if (a.symmetric) {
+            if (a.symmetric && vec_ok) {
+                for (int q = tid; q < TILE * 16; q += 256) {
+                    const int rl = q >> 4, cl = (q & 15) * 2;
+                    const long long ri = tr + rl, cj = tc + 32 * half + cl;
+                    if (ri >= a.r1 || cj >= a.c1) continue;
+                    const double d0 = s_t[cl * TILE + (rl ^ cl)], d1 = s_t[(cl + 1) * TILE + (rl ^ (cl + 1))];
+                    if (cj + 1 < a.c1)
+                        __stcs(reinterpret_cast<double2*>(a.D + cj + a.ldr * ri), make_double2(d0, d1));
+                    else
+                        __stcs(a.D + cj + a.ldr * ri, d0);
+                }
+            } else if (a.symmetric) {
                 for (int q = tid; q < 32 * TILE; q += 256) {
                     const int rl = q >> 5, cl = q & 31;
                     const long long ri = tr + rl, cj = tc + 32 * half + cl;
-                    if (ri < a.r1 && cj < a.c1 && cj > ri) a.D[cj + a.ldr * ri] = s_t[cl * TILE + (rl ^ cl)];
+                    if (ri < a.r1 && cj < a.c1 && cj > ri) __stcs(a.D + cj + a.ldr * ri, s_t[cl * TILE + (rl ^ cl)]);
                 }
             }
         }
