@@ -336,3 +336,51 @@ def test_hist_edges_and_ecdf_rows_match_oracle(mcbb, orc):
                 L.orc_hist_ecdf(row.ctypes.data_as(orc.abi.c_double_p), nd, e2.ctypes.data_as(orc.abi.c_double_p),
                                 len(e2), 1, out.ctypes.data_as(C.POINTER(C.c_float)))
                 assert np.array_equal(H[i], out, equal_nan=True)
+
+
+def test_sharding_helpers_partition_exactly(mcbb):
+    """dist.cyclic_order is a permutation that groups the 64-point tiles by owner (tile t -> rank t % world) in
+    ascending order inside each group; dist.triangle_range blocks are tile aligned, contiguous, cover [0, m) and hold
+    roughly equal shares of the pair triangle {col > row}."""
+    import torch
+    d = mcbb.dist
+    for m_, world in ((1, 1), (63, 2), (64, 2), (1000, 3), (12345, 8)):
+        perm = d.cyclic_order(m_, world)
+        assert torch.equal(torch.sort(perm).values, torch.arange(m_))
+        owner = (perm // 64) % world
+        assert torch.all(owner[1:] >= owner[:-1])  # grouped by owner, rank 0 first
+        for r in range(world):
+            mine = perm[owner == r]
+            assert torch.all(mine[1:] > mine[:-1])  # original order kept inside a group
+        # contiguous shards of the permuted order are what the ranks own
+        sizes = d.shard_sizes(m_, world)
+        assert sum(sizes) == m_ and max(sizes) - min(sizes) <= 1
+    for m_, parts in ((100000, 8), (100000, 32), (5000, 3), (70, 4)):
+        edges = [d.triangle_range(m_, k, parts) for k in range(parts)]
+        assert edges[0][0] == 0 and edges[-1][1] == m_
+        for (a0, a1), (b0, b1) in zip(edges[:-1], edges[1:]):
+            assert a1 == b0 and a0 % 64 == 0 and a0 <= a1
+        if m_ >= 100000:
+            area = [sum(m_ - r for r in (lo, hi - 1)) * (hi - lo) / 2 for lo, hi in edges if hi > lo]
+            assert max(area) / min(area) < 1.25
+
+
+def test_nonzero_sparse_matrix_semantics(mcbb):
+    """NonzeroSparseMatrix (src/sparse_clustering.jl:37-110): stored entries are value-shifted, everything else reads
+    as `value`; host-side container only (the device fills it)."""
+    rng = np.random.default_rng(4)
+    n, thr = 37, 0.35
+    pts = rng.random((n, 3))
+    D = np.abs(pts[:, None, :] - pts[None, :, :]).sum(-1)
+    keep = D < thr
+    colptr = np.concatenate([[0], np.cumsum(keep.sum(0))]).astype(np.int64)
+    rowval = np.concatenate([np.nonzero(keep[:, c])[0] for c in range(n)]).astype(np.int32)
+    nzval = np.concatenate([D[keep[:, c], c] - thr for c in range(n)])
+    S = mcbb.NonzeroSparseMatrix(colptr, rowval, nzval, thr, n)
+    assert S.shape == (n, n)
+    dense = S.toarray()
+    assert np.allclose(dense[keep], D[keep]) and np.all(dense[~keep] == thr)
+    for i, j in ((0, 0), (3, 17), (n - 1, 2), (5, 5)):
+        assert np.isclose(S[i, j], D[i, j] if keep[i, j] else thr)
+    with pytest.raises(mcbb.MCBBError, match="sparse_threshold"):
+        mcbb.distance_matrix_sparse(None, None, [1.0])  # the default threshold (Inf) is rejected before any work
