@@ -295,6 +295,17 @@ def main():
                 "(arithmetic intensity > 1e4 flop/B)",
     }
 
+    # tensor-pipe view of the same kernel: every right-hand-side evaluation of a CTA (6 trajectories) is one
+    # D[128 x 96] += A[128 x 128] B[128 x 96] int8 GEMM (zero padding of rows / K / the two pad columns included)
+    evals = 6.0 * float(nst.item()) * args.steps / world  # per GPU in the timed region
+    int8_ops = evals * (2.0 * 128 * 128 * 16)             # 16 accumulator columns per trajectory
+    roofline["tensor"] = {
+        "bound": "tensor", "achieved": int8_ops / (ms_total * 1e-3) / 1e12, "peak": 8192 * 2 * 148 * 1.965e9 / 1e12,
+        "unit": "TOP/s (int8)", "frac": int8_ops / (ms_total * 1e-3) / (8192 * 2 * 148 * 1.965e9),
+        "peak_source": "tcgen05.mma kind::i8 M=128: 8192 MAC/clk/SM measured by profiles/microbench/umma_probe.cu, x 148 SMs x 1.965 GHz",
+        "note": "the tensor cores replace 54 % of the algorithmic FP64 flops; they are not the bound of the kernel",
+    }
+
     # ---- cluster time at N runs (fused row-sharded DBSCAN on the all-gathered features) -----------------------
     cluster = None
     if not args.no_cluster:
