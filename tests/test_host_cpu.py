@@ -384,3 +384,46 @@ def test_nonzero_sparse_matrix_semantics(mcbb):
         assert np.isclose(S[i, j], D[i, j] if keep[i, j] else thr)
     with pytest.raises(mcbb.MCBBError, match="sparse_threshold"):
         mcbb.distance_matrix_sparse(None, None, [1.0])  # the default threshold (Inf) is rejected before any work
+
+
+def test_fixed_point_coupling_sum_identities():
+    """The arithmetic claims behind the tensor-core coupling sums (csrc/fixedpoint.cuh, batched_umma.cu), restated in
+    numpy / Python integers: the magic-number split gives u = round(x 2^50) + 2^51 and its radix-256 digits; digit sums
+    over up to 128 unit couplings recombine EXACTLY with the 31-bit packing used on the device (three sums per 32-bit
+    word, one 64-bit multiply-add, degree correction in the high word), and the single conversion to double is the
+    correctly rounded sum — i.e. more accurate than any FP64 summation order."""
+    from fractions import Fraction
+    rng = np.random.default_rng(123)
+    magic = 6755399441055744.0  # 1.5 * 2^52
+    for deg in (1, 7, 20, 100, 128):
+        x = rng.uniform(-1.0, 1.0, size=deg)
+        x[0] = 1.0 if deg > 1 else x[0]   # extremes of the range
+        x[-1] = -1.0
+        t = x * 1125899906842624.0 + magic                       # one FMA on the device; exact here as well
+        bits = t.view(np.uint64)
+        lo = (bits & 0xFFFFFFFF).astype(np.uint64)
+        hi = ((bits >> 32) & 0xFFFFF).astype(np.uint64)
+        u = (hi << 32) | lo
+        expect_u = np.array([int(np.rint(v * 2.0 ** 50)) + 2 ** 51 for v in x], dtype=object)
+        assert all(int(a) == int(b) for a, b in zip(u, expect_u))
+        digits = np.array([[(int(ui) >> (8 * k)) & 0xFF for k in range(8)] for ui in u])
+        assert np.all(digits[:, 7] == 0) and np.all(digits[:, 6] <= 15)
+        v = digits.sum(axis=0)                                   # what the int8 GEMM accumulates per digit column
+        assert v.max() <= 128 * 255 < 2 ** 15
+        # device recombination (32-bit wrap-around arithmetic made explicit)
+        m32 = 0xFFFFFFFF
+        lo3 = (int(v[0]) + (int(v[1]) << 8) + (int(v[2]) << 16)) & m32
+        mid3 = (int(v[3]) + (int(v[4]) << 8) + (int(v[5]) << 16)) & m32
+        assert lo3 == int(v[0]) + (int(v[1]) << 8) + (int(v[2]) << 16) < 2 ** 31   # no wrap: the packing is lossless
+        w = mid3 * 16777216 + lo3
+        degh = deg << 19
+        hi_word = ((w >> 32) + ((int(v[6]) << 16) - degh))
+        val = (hi_word << 32) | (w & m32)
+        exact = sum(int(ui) for ui in u) - deg * 2 ** 51
+        assert val == exact
+        # one rounding: double(val) * 2^-50 against the exact rational sum of the rounded terms
+        got = float(val) * 2.0 ** -50
+        want = Fraction(exact, 2 ** 50)
+        assert abs(Fraction(got) - want) <= Fraction(abs(exact), 2 ** 50) * Fraction(1, 2 ** 53) + 0
+        # and the fixed-point terms are within 2^-51 of the true values
+        assert np.max(np.abs(np.array([float(Fraction(int(ui) - 2 ** 51, 2 ** 50)) for ui in u]) - x)) <= 2.0 ** -51
