@@ -329,11 +329,12 @@ def test_c5_batched_converged(gpu, orc):
     print("c5 converged parity", stats)
 
 
-@pytest.mark.parametrize("N,filt", [(40, None), (64, None), (97, [0, 5, 63, 64, 95, 96]), (128, None)])
+@pytest.mark.parametrize("N,filt", [(30, None), (40, None), (64, None), (97, [0, 5, 63, 64, 95, 96]), (128, None)])
 def test_tensor_core_kernel_network_sizes(gpu, orc, N, filt):
     """The tcgen05 integrator maps oscillator r to row r of a 128-row MMA tile: sizes that leave whole warps idle
     (N = 40, 64), a size with a one-row last warp plus a state_filter straddling the warp edges (N = 97), and the full
-    tile (N = 128) — converged tolerances, every run must match the oracle to 1e-6."""
+    tile (N = 128) — converged tolerances, every run must match the oracle to 1e-6.  N = 30 is below the tcgen05
+    kernel's range and exercises its mma.sync predecessor (csrc/batched_imma.cu)."""
     m = gpu
     prob, _ = cases.c5_problem(m, 48, N=N, seed=20 + N, tspan=(0.0, 60.0))
     if filt is not None:
