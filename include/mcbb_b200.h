@@ -101,7 +101,8 @@ enum mcbb_measure {
 };
 enum mcbb_matrix_measure {
     MCBB_MAT_NONE = 0,
-    MCBB_MAT_CORR_ECDF = 1     /* correlation_ecdf(sol, nbins)                         eval_mc_prob.jl:462-488 */
+    MCBB_MAT_CORR_ECDF = 1,    /* correlation_ecdf(sol, nbins)                         eval_mc_prob.jl:462-488 */
+    MCBB_MAT_CORR_HIST = 2     /* correlation_hist(sol, nbins): the raw bin weights    eval_mc_prob.jl:472-481 */
 };
 enum mcbb_global_measure {
     MCBB_GLOB_SUM = 0          /* (x)->sum(x) over sol[state_filter, 2:end]     test/ode_prob_example.jl:54   */

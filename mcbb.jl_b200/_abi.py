@@ -38,6 +38,7 @@ MEAS_STD = 1
 MEAS_KL_HIST = 2
 MAT_NONE = 0
 MAT_CORR_ECDF = 1
+MAT_CORR_HIST = 2
 GLOB_SUM = 0
 
 c_double_p = C.POINTER(C.c_double)

@@ -233,6 +233,8 @@ mean = "mean"
 std = "std"
 empirical_1D_KL_divergence_hist = "kl_hist"
 correlation_ecdf = "correlation_ecdf"
+correlation_hist = "correlation_hist"  # the raw bin weights, eval_mc_prob.jl:472-481
+_MAT = {"correlation_ecdf": abi.MAT_CORR_ECDF, "correlation_hist": abi.MAT_CORR_HIST}
 _MEAS = {"mean": abi.MEAS_MEAN, "std": abi.MEAS_STD, "kl_hist": abi.MEAS_KL_HIST, "mean_real": abi.MEAS_MEAN,
          "std_real": abi.MEAS_STD, "kl_real": abi.MEAS_KL_HIST, "mean_imag": abi.MEAS_MEAN,
          "std_imag": abi.MEAS_STD, "kl_imag": abi.MEAS_KL_HIST}
@@ -258,7 +260,11 @@ class EvalOdeRun:
     def pack(self):
         meas = [_MEAS[f] for f in self.eval_funcs]
         comp = [1 if f.endswith("_imag") else 0 for f in self.eval_funcs]
-        mat = abi.MAT_CORR_ECDF if self.matrix_eval_funcs else abi.MAT_NONE
+        if len(self.matrix_eval_funcs) > 1:
+            raise MCBBError("one matrix measure per problem (correlation_ecdf or correlation_hist)")
+        if self.matrix_eval_funcs and self.matrix_eval_funcs[0] not in _MAT:
+            raise MCBBError("matrix measure not known: %r" % (self.matrix_eval_funcs[0],))
+        mat = _MAT[self.matrix_eval_funcs[0]] if self.matrix_eval_funcs else abi.MAT_NONE
         glob = [abi.GLOB_SUM for _ in self.global_eval_funcs]
         return abi.PackedFeat(meas, comp, self.state_filter, self.cyclic_setback, mat, 30, glob)
 

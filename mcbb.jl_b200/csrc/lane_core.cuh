@@ -110,7 +110,7 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
 #define A(slot, ch) acc[((size_t)(slot)*n_ch + (ch)) * bs]
 #define B(ch, b) bins[((size_t)(ch)*nb + (b)) * bs]
 #define CM(p) como[(size_t)(p)*bs]  /* co-moments of channel pairs (i > j), p = i(i-1)/2 + j */
-    const bool corr = F.matrix_meas == MCBB_MAT_CORR_ECDF;
+    const bool corr = F.matrix_meas != MCBB_MAT_NONE;  // correlation_ecdf or correlation_hist
 
     int mode = MODE_FETCH;
     long long run = -1;
@@ -333,10 +333,13 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                         }
                     double cum = 0., tot = 0.;
                     for (int b = 0; b < nbn; b++) tot += (double)h[b];
-                    for (int b = 0; b < nbn; b++) {  // ecdf_hist, eval_clustering.jl:759-762
-                        cum += (double)h[b];
-                        io.matrix[(long long)b * io.n_mc + run] = cum / tot;
-                    }
+                    if (F.matrix_meas == MCBB_MAT_CORR_HIST)  // the weights themselves, eval_mc_prob.jl:472-481
+                        for (int b = 0; b < nbn; b++) io.matrix[(long long)b * io.n_mc + run] = (double)h[b];
+                    else
+                        for (int b = 0; b < nbn; b++) {  // ecdf_hist, eval_clustering.jl:759-762
+                            cum += (double)h[b];
+                            io.matrix[(long long)b * io.n_mc + run] = cum / tot;
+                        }
                 }
                 for (int ch = 0; ch < n_ch; ch++)  // std(u; mean, corrected=true)
                     {

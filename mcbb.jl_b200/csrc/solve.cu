@@ -197,8 +197,9 @@ int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* 
     F.cyclic = f->cyclic_setback != 0;
     F.matrix_meas = f->matrix_meas;
     F.corr_nbins = f->corr_nbins > 0 ? f->corr_nbins : 30;
-    if (F.matrix_meas != MCBB_MAT_NONE && F.matrix_meas != MCBB_MAT_CORR_ECDF) MCBB_FAIL("unknown matrix measure id");
-    if (F.matrix_meas == MCBB_MAT_CORR_ECDF) {
+    if (F.matrix_meas != MCBB_MAT_NONE && F.matrix_meas != MCBB_MAT_CORR_ECDF && F.matrix_meas != MCBB_MAT_CORR_HIST)
+        MCBB_FAIL("unknown matrix measure id");
+    if (F.matrix_meas != MCBB_MAT_NONE) {
         if (cplx) MCBB_FAIL("correlation_ecdf of complex states is not implemented on the device yet");
         if (F.corr_nbins > 64) MCBB_FAIL("correlation_ecdf: at most 64 bins");
     }
@@ -222,7 +223,7 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
     const int n = S.n_dim;
     LaneLayout lay = {};
     lay.n_slots = 9 + n_scratch_for(SYS);
-    const bool corr = F.matrix_meas == MCBB_MAT_CORR_ECDF;
+    const bool corr = F.matrix_meas != MCBB_MAT_NONE;
     const int n_pairs = corr ? F.n_ch * (F.n_ch - 1) / 2 : 0;
     lay.n_acc = corr ? ACC_SLOTS_CORR : (F.need_kl ? ACC_SLOTS_KL : ACC_SLOTS);
     const int lens[5] = {S.len_mat_a, S.len_mat_b, S.len_vec_a, S.len_vec_b, S.len_vec_c};

@@ -111,6 +111,7 @@ Base.@kwdef struct B200Eval
     state_filter::Union{Nothing,Vector{Int}} = nothing
     cyclic_setback::Bool = false
     correlation_ecdf::Bool = false     # matrix_eval_funcs = [correlation_ecdf] (30 bins)
+    correlation_hist::Bool = false     # matrix_eval_funcs = [correlation_hist] (30 bins, raw weights)
     global_sum::Bool = false           # global_eval_funcs = [(x)->sum(x)]
 end
 const MEAS_ID = Dict(:mean => MEAS_MEAN, :std => MEAS_STD, :kl_hist => MEAS_KL_HIST)
@@ -132,11 +133,13 @@ function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eva
     filt = eval.state_filter === nothing ? Int32[] : Int32.(eval.state_filter)
     nf = eval.state_filter === nothing ? size(prob.ic, 2) : length(filt)
     nm = length(eval.measures)
+    eval.correlation_ecdf && eval.correlation_hist && error("one matrix measure per problem")
+    has_mat = eval.correlation_ecdf || eval.correlation_hist
     fo = FeatOpts(nm, pad(Int32[MEAS_ID[m] for m in eval.measures], MAX_MEAS, Int32(0)), pad(Int32[], MAX_MEAS, Int32(0)),
                   length(filt), isempty(filt) ? C_NULL : pointer(filt), eval.cyclic_setback,
-                  eval.correlation_ecdf ? 1 : 0, 30, eval.global_sum ? 1 : 0,
+                  eval.correlation_ecdf ? 1 : (eval.correlation_hist ? 2 : 0), 30, eval.global_sum ? 1 : 0,
                   pad(Int32[], MAX_GLOBAL, Int32(0)), 31, 3.0, 1e-4)
-    mat = eval.correlation_ecdf ? Matrix{Float64}(undef, prob.N_mc, 30) : Matrix{Float64}(undef, 0, 0)
+    mat = has_mat ? Matrix{Float64}(undef, prob.N_mc, 30) : Matrix{Float64}(undef, 0, 0)
     glob = eval.global_sum ? Matrix{Float64}(undef, prob.N_mc, 1) : Matrix{Float64}(undef, 0, 0)
     ic = Matrix{Float64}(prob.ic)            # N_mc x N_dim, column-major: already struct-of-arrays over runs
     par = Matrix{Float64}(prob.par)
@@ -149,11 +152,11 @@ function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eva
                     (Ref{SystemDesc}, Ref{SolverOpts}, Ref{FeatOpts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                      Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
                     desc, opts, fo, prob.N_mc, ic, par, ts, length(ts), feat,
-                    eval.correlation_ecdf ? pointer(mat) : C_NULL, eval.global_sum ? pointer(glob) : C_NULL,
+                    has_mat ? pointer(mat) : C_NULL, eval.global_sum ? pointer(glob) : C_NULL,
                     retcode, nsteps))
     end
     # tuple order of eval_ode_run: per-dimension measures, matrix measures, global measures (eval_mc_prob.jl:187)
-    u = [(ntuple(m -> feat[i, :, m], nm)..., (eval.correlation_ecdf ? (mat[i, :],) : ())...,
+    u = [(ntuple(m -> feat[i, :, m], nm)..., (has_mat ? (mat[i, :],) : ())...,
           (eval.global_sum ? (glob[i, 1],) : ())...) for i in 1:prob.N_mc]
     DiffEqBase.EnsembleSolution(u, 0.0, true)
 end

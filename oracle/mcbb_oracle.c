@@ -602,7 +602,7 @@ static int searchsortedlast_range(double first, double step, int len, double x) 
 }
 
 /* correlation_ecdf, eval_mc_prob.jl:462-488 (real states).  X is nf x ns (sample index slowest). */
-static void corr_ecdf(const double* X, int nf, int ns, int nbins, double* out) {
+static void corr_ecdf(const double* X, int nf, int ns, int nbins, int raw_weights, double* out) {
     double* mean = (double*)malloc(sizeof(double) * nf);
     double* C = (double*)malloc(sizeof(double) * nf * nf);
     for (int i = 0; i < nf; i++) {
@@ -633,6 +633,13 @@ static void corr_ecdf(const double* X, int nf, int ns, int nbins, double* out) {
             const int idx = searchsortedlast_range(0., step, nbins + 1, c);
             if (idx >= 1 && idx <= nbins) h[idx - 1]++;
         }
+    if (raw_weights) { /* correlation_hist returns hist.weights, eval_mc_prob.jl:472-481 */
+        for (int b = 0; b < nbins; b++) out[b] = (double)h[b];
+        free(h);
+        free(C);
+        free(mean);
+        return;
+    }
     double cum = 0.;
     for (int b = 0; b < nbins; b++) { /* ecdf_hist, eval_clustering.jl:759-762 */
         cum += (double)h[b];
@@ -703,7 +710,7 @@ static void featurize(const mcbb_system_desc* sys, const mcbb_feat_opts* fo, con
             glob[(size_t)g * stride + off] = s;
         }
     }
-    if (fo->matrix_meas == MCBB_MAT_CORR_ECDF && mat && !cplx) {
+    if (fo->matrix_meas != MCBB_MAT_NONE && mat && !cplx) {
         const int nb = fo->corr_nbins > 0 ? fo->corr_nbins : 30;
         double* X = (double*)malloc(sizeof(double) * nf * ns);
         double* e = (double*)malloc(sizeof(double) * nb);
@@ -712,7 +719,7 @@ static void featurize(const mcbb_system_desc* sys, const mcbb_feat_opts* fo, con
                 const int sidx = fo->n_filter > 0 ? fo->state_filter[ii] - 1 : ii;
                 X[ii + (size_t)nf * t] = saved[sidx + (size_t)n_dim * (t + 1)];
             }
-        corr_ecdf(X, nf, ns, nb, e);
+        corr_ecdf(X, nf, ns, nb, fo->matrix_meas == MCBB_MAT_CORR_HIST, e);
         for (int b = 0; b < nb; b++) mat[(size_t)b * stride + off] = e[b];
         free(e);
         free(X);

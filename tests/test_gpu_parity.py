@@ -406,6 +406,31 @@ def test_all_measures_correlation_ecdf_and_sum(gpu, orc):
     assert np.allclose(D.data, orc.distance_matrix(X, gl, gw), rtol=1e-12, atol=1e-13, equal_nan=True)
 
 
+def test_correlation_hist_and_ecdf_on_power_grid_frequencies(gpu, orc):
+    """correlation_hist / correlation_ecdf (eval_mc_prob.jl:462-488) where the |cor| values actually spread over the
+    bins: the ten frequencies of the second-order Kuramoto grid during their transient (90 off-diagonal pairs)."""
+    m = gpu
+    out = {}
+    for f in (m.correlation_hist, m.correlation_ecdf):
+        prob, _ = cases.c3_problem(m, n_mc=60, seed=5, N=10, tspan=(0.0, 60.0), tail=0.5)
+        prob.eval_ode_func = m.EvalOdeRun(state_filter=list(range(11, 21)), eval_funcs=(m.mean, m.std),
+                                          matrix_eval_funcs=[f])
+        ic0, par0 = prob.ic.copy(), prob.par.copy()
+        sol = m.solve(prob, reltol=1e-9, abstol=1e-9)
+        ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, reltol=1e-9, abstol=1e-9)
+        cases.compare_features(sol.feat, ref, orc, *ctx)
+        out[f] = (sol.matrix, ref["matrix"])
+    w, w_ref = out[m.correlation_hist]
+    e, e_ref = out[m.correlation_ecdf]
+    assert np.all(w == np.rint(w)) and np.all(w.sum(axis=1) == 90) and np.all(w >= 0)
+    assert (w[:, :-1].sum(axis=1) > 0).sum() >= 40  # not just the last bin
+    # a |cor| within rounding of a bin edge may land on either side: exact for (nearly) every run
+    assert np.all(w == w_ref, axis=1).mean() >= 0.95, np.all(w == w_ref, axis=1).mean()
+    assert np.abs(w - w_ref).sum(axis=1).max() <= 4
+    assert np.all(np.abs(e - e_ref) < 1e-15, axis=1).mean() >= 0.95
+    assert np.array_equal(e, np.cumsum(w, axis=1) / 90.0)  # ecdf_hist of the weights, eval_clustering.jl:759-762
+
+
 def test_k_dist_and_knn_helpers(gpu):
     """k_dist / KNN_dist / KNN_dist_relative (eval_clustering.jl:1504-1553) against numpy on the same matrix."""
     m = gpu

@@ -137,6 +137,29 @@ def test_kl_hist_against_numpy_restatement(orc):
     assert orc.kl_hist(np.ones(10), 1.0, 1e-5) == 0.0
 
 
+def test_correlation_hist_and_ecdf_against_numpy(orc):
+    """correlation_hist / correlation_ecdf (eval_mc_prob.jl:462-488) against numpy corrcoef + histogram: the weights
+    of |cor| over 0:1/30:1 (left-closed bins, so the unit diagonal falls outside), and ecdf_hist of them.  The first
+    saved sample is dropped before measuring (eval_mc_prob.jl:95)."""
+    abi = orc.abi
+    rng = np.random.default_rng(3)
+    N, n_t, n_mc = 7, 120, 12
+    psys, _, _ = _kur(abi, N=N)
+    mix = rng.normal(size=(n_mc, N, N))
+    saved = np.einsum("rij,rjt->rit", mix, rng.normal(size=(n_mc, N, n_t)))
+    out = {}
+    for kind in (abi.MAT_CORR_HIST, abi.MAT_CORR_ECDF):
+        pfeat = abi.PackedFeat([abi.MEAS_MEAN, abi.MEAS_STD], matrix_meas=kind, corr_nbins=30)
+        out[kind] = orc.featurize_saved(psys, pfeat, saved)["matrix"]
+    for r in range(n_mc):
+        c = np.abs(np.corrcoef(saved[r][:, 1:]))
+        # numpy's last bin is closed on the right, Julia's is not: the unit diagonal is dropped by hand
+        w = np.histogram(c[~np.eye(N, dtype=bool)], bins=np.arange(31) / 30.0)[0]
+        assert w.sum() == N * (N - 1)
+        assert np.array_equal(out[abi.MAT_CORR_HIST][r], w.astype(float))
+        assert np.allclose(out[abi.MAT_CORR_ECDF][r], np.cumsum(w) / w.sum(), rtol=0, atol=1e-15)
+
+
 def _ssl(v, x):  # Base.searchsortedlast on a Vector, binary search as in sort.jl
     lo, hi = 0, len(v) + 1
     while lo < hi - 1:
