@@ -319,12 +319,22 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
                     int h[64];
                     for (int b = 0; b < nbn; b++) h[b] = 0;
                     const double step = 1. / (double)nbn;
-                    int p = 0;
-                    for (int i = 1; i < n_ch; i++)
-                        for (int j = 0; j < i; j++, p++) {
-                            double c = CM(p) / (sqrt(A(ACC_M2, i)) * sqrt(A(ACC_M2, j)));
-                            c = fabs(fmin(1., fmax(-1., c)));  // clampcor, then abs
-                            if (c != c) continue;              // zero-variance dimension: dropped
+                    const int n_st = F.n_filter;  // states: real, or complex as (re, im) channel pairs
+                    for (int i = 1; i < n_st; i++)
+                        for (int j = 0; j < i; j++) {
+                            double c;
+                            if (F.n_comp == 1) {
+                                c = CM(i * (i - 1) / 2 + j) / (sqrt(A(ACC_M2, i)) * sqrt(A(ACC_M2, j)));
+                                c = fabs(fmin(1., fmax(-1., c)));  // clampcor, then abs
+                            } else {
+                                // cor of complex series: sum (z_i - m_i) conj(z_j - m_j) over the samples, from the
+                                // real co-moments of the (re, im) channels; clampcor leaves complex values alone
+                                const int ai = 2 * i, bi = 2 * i + 1, aj = 2 * j, bj = 2 * j + 1;
+                                const double re = CM(ai * (ai - 1) / 2 + aj) + CM(bi * (bi - 1) / 2 + bj);
+                                const double im = CM(bi * (bi - 1) / 2 + aj) - CM(ai * (ai - 1) / 2 + bj);
+                                c = hypot(re, im) / (sqrt(A(ACC_M2, ai) + A(ACC_M2, bi)) * sqrt(A(ACC_M2, aj) + A(ACC_M2, bj)));
+                            }
+                            if (c != c) continue;  // zero-variance dimension: dropped
                             double f = c / step + 1.;          // Base.searchsortedlast on the range 0:1/nbins:1
                             f = fmin(fmax(f, 1.), (double)(nbn + 1));
                             const int n0 = (int)rint(f);

@@ -200,7 +200,6 @@ int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* 
     if (F.matrix_meas != MCBB_MAT_NONE && F.matrix_meas != MCBB_MAT_CORR_ECDF && F.matrix_meas != MCBB_MAT_CORR_HIST)
         MCBB_FAIL("unknown matrix measure id");
     if (F.matrix_meas != MCBB_MAT_NONE) {
-        if (cplx) MCBB_FAIL("correlation_ecdf of complex states is not implemented on the device yet");
         if (F.corr_nbins > 64) MCBB_FAIL("correlation_ecdf: at most 64 bins");
     }
     F.n_global = f->n_global;

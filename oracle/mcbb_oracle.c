@@ -652,6 +652,58 @@ static void corr_ecdf(const double* X, int nf, int ns, int nbins, int raw_weight
     free(mean);
 }
 
+/* correlation_hist / correlation_ecdf of COMPLEX states (the Stuart-Landau configuration): Statistics.cor(x, dims=2)
+ * centres each row, forms x*x' (second factor conjugated) and divides by the root of the diagonal; clampcor is the
+ * identity for complex values; then abs, the same histogram and ecdf_hist.  Z holds interleaved (re, im), nf x ns. */
+static void corr_ecdf_complex(const double* Z, int nf, int ns, int nbins, int raw_weights, double* out) {
+    double* mre = (double*)calloc(nf, sizeof(double));
+    double* mim = (double*)calloc(nf, sizeof(double));
+    double* var = (double*)calloc(nf, sizeof(double));
+    for (int i = 0; i < nf; i++) {
+        double sr = 0., si = 0.;
+        for (int t = 0; t < ns; t++) {
+            sr += Z[2 * i + (size_t)2 * nf * t];
+            si += Z[2 * i + 1 + (size_t)2 * nf * t];
+        }
+        mre[i] = sr / ns;
+        mim[i] = si / ns;
+        double v = 0.;
+        for (int t = 0; t < ns; t++) {
+            const double a = Z[2 * i + (size_t)2 * nf * t] - mre[i], b = Z[2 * i + 1 + (size_t)2 * nf * t] - mim[i];
+            v += a * a + b * b;
+        }
+        var[i] = v;
+    }
+    int64_t* h = (int64_t*)calloc(nbins, sizeof(int64_t));
+    const double step = 1. / nbins;
+    for (int j = 0; j < nf; j++)
+        for (int i = 0; i < nf; i++) {
+            if (i == j) continue; /* the unit diagonal lies outside [0, 1) */
+            double re = 0., im = 0.;
+            for (int t = 0; t < ns; t++) {
+                const double a = Z[2 * i + (size_t)2 * nf * t] - mre[i], b = Z[2 * i + 1 + (size_t)2 * nf * t] - mim[i];
+                const double c = Z[2 * j + (size_t)2 * nf * t] - mre[j], d = Z[2 * j + 1 + (size_t)2 * nf * t] - mim[j];
+                re += a * c + b * d; /* (a + ib)(c - id) */
+                im += b * c - a * d;
+            }
+            const double den = sqrt(var[i]) * sqrt(var[j]);
+            const double c = hypot(re / den, im / den);
+            if (isnan(c)) continue;
+            const int idx = searchsortedlast_range(0., step, nbins + 1, c);
+            if (idx >= 1 && idx <= nbins) h[idx - 1]++;
+        }
+    double cum = 0., tot = 0.;
+    for (int b = 0; b < nbins; b++) tot += (double)h[b];
+    for (int b = 0; b < nbins; b++) {
+        cum += (double)h[b];
+        out[b] = raw_weights ? (double)h[b] : cum / tot;
+    }
+    free(h);
+    free(var);
+    free(mim);
+    free(mre);
+}
+
 /* eval_ode_run, eval_mc_prob.jl:75-188, on a saved array (n_dim x nt).  Output strides: per-run values are
  * written at feat[(m*nf + d)*stride + off] so the caller can lay runs out column-major. */
 static void featurize(const mcbb_system_desc* sys, const mcbb_feat_opts* fo, const double* saved, int n_dim,
@@ -709,6 +761,21 @@ static void featurize(const mcbb_system_desc* sys, const mcbb_feat_opts* fo, con
                 }
             glob[(size_t)g * stride + off] = s;
         }
+    }
+    if (fo->matrix_meas != MCBB_MAT_NONE && mat && cplx) {
+        const int nb = fo->corr_nbins > 0 ? fo->corr_nbins : 30;
+        double* Z = (double*)malloc(sizeof(double) * 2 * nf * ns);
+        double* e = (double*)malloc(sizeof(double) * nb);
+        for (int t = 0; t < ns; t++)
+            for (int ii = 0; ii < nf; ii++) {
+                const int sidx = fo->n_filter > 0 ? fo->state_filter[ii] - 1 : ii;
+                Z[2 * ii + (size_t)2 * nf * t] = saved[2 * sidx + (size_t)n_dim * (t + 1)];
+                Z[2 * ii + 1 + (size_t)2 * nf * t] = saved[2 * sidx + 1 + (size_t)n_dim * (t + 1)];
+            }
+        corr_ecdf_complex(Z, nf, ns, nb, fo->matrix_meas == MCBB_MAT_CORR_HIST, e);
+        for (int b = 0; b < nb; b++) mat[(size_t)b * stride + off] = e[b];
+        free(e);
+        free(Z);
     }
     if (fo->matrix_meas != MCBB_MAT_NONE && mat && !cplx) {
         const int nb = fo->corr_nbins > 0 ? fo->corr_nbins : 30;

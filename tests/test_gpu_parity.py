@@ -431,6 +431,45 @@ def test_correlation_hist_and_ecdf_on_power_grid_frequencies(gpu, orc):
     assert np.array_equal(e, np.cumsum(w, axis=1) / 90.0)  # ecdf_hist of the weights, eval_clustering.jl:759-762
 
 
+def test_complex_state_correlation_measures(gpu, orc):
+    """correlation_hist / correlation_ecdf of COMPLEX states (the Stuart-Landau configuration of the paper notebooks):
+    |cor| of the complex series, from the device's online co-moments of the (re, im) channels.  Measured over the
+    transient (T = 10, nothing discarded): once the amplitudes synchronise every |cor| sits within rounding of 1, the
+    open end of the last bin, and the oracle itself flips bins under 1e-12 perturbations of the initial condition."""
+    m = gpu
+    Ns = 8
+    A1 = np.roll(np.eye(Ns), 1, 0) + np.roll(np.eye(Ns), -1, 0)
+    A2 = A1 + np.roll(np.eye(Ns), 2, 0) + np.roll(np.eye(Ns), -2, 0)
+    kw = dict(reltol=1e-9, abstol=1e-9)
+    out = {}
+    for f, filt in ((m.correlation_hist, None), (m.correlation_ecdf, None), (m.correlation_hist, [1, 3, 4, 8])):
+        rng, prng = np.random.default_rng(31), np.random.default_rng(32)
+        pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.9, Ns, 1, 2, A1, A2)
+        ev = m.EvalOdeRun(state_filter=filt, eval_funcs=("mean_real", "std_real", "mean_imag", "std_imag"),
+                          matrix_eval_funcs=[f])
+        rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(Ns, dtype=complex), (0.0, 10.0), pars)
+        prob = m.DEMCBBProblem(rp, lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1)), 64, pars,
+                               ("eps", lambda: prng.uniform(1.8, 2.1)), ev, 0.0)
+        ic0, par0 = prob.ic.copy(), prob.par.copy()
+        sol = m.solve(prob, **kw)
+        ic0 = np.stack([ic0.real, ic0.imag], axis=2).reshape(ic0.shape[0], -1)
+        ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
+        assert np.array_equal(sol.retcode, ref["retcode"])
+        cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.8)
+        out[(f, filt is None)] = (sol.matrix, ref["matrix"])
+    for key, npairs in (((m.correlation_hist, True), 56), ((m.correlation_hist, False), 12)):
+        w, w_ref = out[key]
+        assert np.all(w == np.rint(w)) and np.all(w >= 0) and np.all(w.sum(axis=1) == npairs)
+        same = np.all(w == w_ref, axis=1)
+        assert same.mean() >= 0.95, (same.mean(), w[~same][:2], w_ref[~same][:2])
+        assert np.abs(w - w_ref).sum(axis=1).max() <= 4
+    w = out[(m.correlation_hist, True)][0]
+    assert (w[:, :-1].sum(axis=1) > 0).all()  # spread over the bins, not just the last one
+    e, e_ref = out[(m.correlation_ecdf, True)]
+    assert np.array_equal(e, np.cumsum(w, axis=1) / 56.0)
+    assert np.all(np.abs(e - e_ref) < 1e-15, axis=1).mean() >= 0.95
+
+
 def test_k_dist_and_knn_helpers(gpu):
     """k_dist / KNN_dist / KNN_dist_relative (eval_clustering.jl:1504-1553) against numpy on the same matrix."""
     m = gpu
@@ -490,7 +529,8 @@ def test_c4_stuart_landau_n100_global_state_path(gpu, orc):
             A += np.roll(np.eye(N), d, 0) + np.roll(np.eye(N), -d, 0)
         return A
     pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.925, N, 1, 22, ring_adj(1), ring_adj(22))
-    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"))
+    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"),
+                      matrix_eval_funcs=[m.correlation_ecdf])  # the notebook's full measure set
     rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(N, dtype=complex), (0.0, 20.0), pars)
     prng = np.random.default_rng(8)
     prob = m.DEMCBBProblem(rp, lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1)), 48, pars,
@@ -503,6 +543,9 @@ def test_c4_stuart_landau_n100_global_state_path(gpu, orc):
     ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
     assert np.array_equal(sol.retcode, ref["retcode"])
     cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.5)
+    e, e_ref = sol.matrix, ref["matrix"]  # ECDF of 9900 |cor| values over 30 bins
+    assert e.shape == (48, 30) and np.allclose(e[:, -1], 1.0) and np.all(np.diff(e, axis=1) >= 0)
+    assert np.abs(e - e_ref).max() <= 4 / 9900 + 1e-15 and (np.abs(e - e_ref).max(axis=1) < 1e-15).mean() >= 0.8
 
 
 def test_histogram_mode_distance_matrix(gpu, orc):

@@ -160,6 +160,33 @@ def test_correlation_hist_and_ecdf_against_numpy(orc):
         assert np.allclose(out[abi.MAT_CORR_ECDF][r], np.cumsum(w) / w.sum(), rtol=0, atol=1e-15)
 
 
+def test_complex_state_correlation_against_numpy(mcbb, orc):
+    """|cor| of complex series (Stuart-Landau states, interleaved re/im): Statistics.cor conjugates the second factor,
+    clampcor leaves complex values alone, abs gives the magnitude — the same as numpy's complex corrcoef."""
+    abi = orc.abi
+    rng = np.random.default_rng(4)
+    N, n_t, n_mc = 6, 90, 10
+    ring = np.roll(np.eye(N), 1, 0) + np.roll(np.eye(N), -1, 0)
+    psys = mcbb.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.9, N, 1, 1, ring, ring).pack(["eps"])
+    mix = rng.normal(size=(n_mc, N, N)) + 1j * rng.normal(size=(n_mc, N, N))
+    z = np.einsum("rij,rjt->rit", mix, rng.normal(size=(n_mc, N, n_t)) + 1j * rng.normal(size=(n_mc, N, n_t)))
+    saved = np.stack([z.real, z.imag], axis=2).reshape(n_mc, 2 * N, n_t)  # dimension index: re_0, im_0, re_1, ...
+    filt = [2, 3, 5, 6]
+    for state_filter in (None, filt):
+        sel = np.arange(N) if state_filter is None else np.array(filt) - 1
+        out = {}
+        for kind in (abi.MAT_CORR_HIST, abi.MAT_CORR_ECDF):
+            pfeat = abi.PackedFeat([abi.MEAS_MEAN, abi.MEAS_STD], meas_comp=[0, 1], state_filter=state_filter,
+                                   matrix_meas=kind, corr_nbins=30)
+            out[kind] = orc.featurize_saved(psys, pfeat, saved)["matrix"]
+        for r in range(n_mc):
+            c = np.abs(np.corrcoef(z[r][sel][:, 1:]))
+            w = np.histogram(c[~np.eye(len(sel), dtype=bool)], bins=np.arange(31) / 30.0)[0]
+            assert w.sum() == len(sel) * (len(sel) - 1)
+            assert np.array_equal(out[abi.MAT_CORR_HIST][r], w.astype(float))
+            assert np.allclose(out[abi.MAT_CORR_ECDF][r], np.cumsum(w) / w.sum(), rtol=0, atol=1e-15)
+
+
 def _ssl(v, x):  # Base.searchsortedlast on a Vector, binary search as in sort.jl
     lo, hi = 0, len(v) + 1
     while lo < hi - 1:
