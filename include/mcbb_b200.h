@@ -169,6 +169,26 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
                             double* matrix_dev, double* global_dev, int32_t* retcode_dev,
                             int64_t* nsteps_dev, void* stream);
 
+/* The same solve, additionally exporting the saved samples themselves — what `sol.solve_command(prob_i)` returns to
+ * get_trajectory (src/eval_clustering.jl:1484-1492; setup_mc_prob.jl:1108-1110: saveat = t_save, savestart = false,
+ * save_everystep = false), and the end state `sol[end]` the continuation / response analysis restarts its three
+ * short runs from (src/eval_mc_prob.jl:210-216).
+ *   MCBB_SAVE_ALL   saved_out = N_mc blocks of n_dim x n_t, column-major: saved_out[(i*n_t + k)*n_dim + d]
+ *   MCBB_SAVE_LAST  saved_out = N_mc x n_dim column-major, the ic layout: saved_out[d*N_mc + i] = sol_i[end][d]
+ * Samples a failed run never reached are NaN.  Complex states are interleaved (re, im) like `ic`.  The export runs
+ * the one-trajectory-per-lane kernels (the batched tensor-core kernels keep no per-sample state). */
+enum mcbb_save_mode { MCBB_SAVE_NONE = 0, MCBB_SAVE_ALL = 1, MCBB_SAVE_LAST = 2 };
+int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opts* opts,
+                              const mcbb_feat_opts* feat, int64_t n_mc, const double* ic, const double* par,
+                              const double* t_save, int32_t n_t, double* feat_out, double* matrix_out,
+                              double* global_out, int32_t* retcode_out, int64_t* nsteps_out, int32_t save_mode,
+                              double* saved_out);
+int mcbb_solve_features_saved_dev(const mcbb_system_desc* sys, const mcbb_solver_opts* opts,
+                                  const mcbb_feat_opts* feat, int64_t n_mc, const double* ic_dev,
+                                  const double* par_dev, const double* t_save_dev, int32_t n_t, double* feat_dev,
+                                  double* matrix_dev, double* global_dev, int32_t* retcode_dev,
+                                  int64_t* nsteps_dev, int32_t save_mode, double* saved_dev, void* stream);
+
 /* ---- hot entry 2: distance matrix ----------------------------------------------------------------------
  * Replaces distance_matrix(sol, prob, weights) with the default L1 distance_func
  * (src/eval_clustering.jl:164-254):

@@ -39,6 +39,7 @@ MEAS_KL_HIST = 2
 MAT_NONE = 0
 MAT_CORR_ECDF = 1
 MAT_CORR_HIST = 2
+SAVE_NONE, SAVE_ALL, SAVE_LAST = 0, 1, 2
 GLOB_SUM = 0
 
 c_double_p = C.POINTER(C.c_double)

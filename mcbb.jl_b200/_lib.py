@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmcbb_b200.so")
 EXPORTS = [
     "mcbb_version", "mcbb_init", "mcbb_finalize", "mcbb_last_error", "mcbb_device_info",
     "mcbb_kernel_launch_count", "mcbb_tsave_array", "mcbb_solve_features", "mcbb_solve_features_dev",
+    "mcbb_solve_features_saved", "mcbb_solve_features_saved_dev",
     "mcbb_distance_matrix", "mcbb_distance_matrix_dev", "mcbb_dbscan_dense", "mcbb_dbscan_dense_dev",
     "mcbb_dbscan_features", "mcbb_dbscan_features_dev", "mcbb_dbscan_rows_count_dev",
     "mcbb_dbscan_rows_union_dev", "mcbb_dbscan_merge_parents_dev", "mcbb_dbscan_rows_border_dev",
@@ -49,6 +50,10 @@ def lib():
     L.mcbb_solve_features.argtypes = [SD, SO, FO, C.c_int64, dp, dp, dp, C.c_int32, dp, dp, dp, ip, lp]
     # device entry points take raw addresses
     L.mcbb_solve_features_dev.argtypes = [SD, SO, FO, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.mcbb_solve_features_saved.argtypes = [SD, SO, FO, C.c_int64, dp, dp, dp, C.c_int32, dp, dp, dp, ip, lp,
+                                            C.c_int32, dp]
+    L.mcbb_solve_features_saved_dev.argtypes = [SD, SO, FO, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp,
+                                                C.c_int32, vp, vp]
     L.mcbb_distance_matrix.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, dp]
     L.mcbb_distance_matrix_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, vp, vp]
     L.mcbb_dbscan_dense.argtypes = [dp, C.c_int64, C.c_double, C.c_int32, lp, lp, lp, lp]

@@ -245,7 +245,7 @@ class EvalOdeRun:
 
     def __init__(self, state_filter=None, eval_funcs=(mean, std, empirical_1D_KL_divergence_hist),
                  matrix_eval_funcs=None, global_eval_funcs=None, failure_handling="None", cyclic_setback=False,
-                 flag_past_measures=True):
+                 flag_past_measures=True, continuation=None):
         if len(eval_funcs) < 1:
             raise MCBBError("No per dimension measures")  # eval_mc_prob.jl:79-81
         if failure_handling not in ("None", "Inf", "Repeat"):
@@ -256,6 +256,7 @@ class EvalOdeRun:
         self.global_eval_funcs = list(global_eval_funcs or [])
         self.failure_handling = failure_handling
         self.cyclic_setback = bool(cyclic_setback)
+        self.continuation = continuation  # ContinuationResponse or None
 
     def pack(self):
         meas = [_MEAS[f] for f in self.eval_funcs]
@@ -267,6 +268,28 @@ class EvalOdeRun:
         mat = _MAT[self.matrix_eval_funcs[0]] if self.matrix_eval_funcs else abi.MAT_NONE
         glob = [abi.GLOB_SUM for _ in self.global_eval_funcs]
         return abi.PackedFeat(meas, comp, self.state_filter, self.cyclic_setback, mat, 30, glob)
+
+
+class ContinuationResponse:
+    """The extra arguments of the response-analysis method of eval_ode_run (eval_mc_prob.jl:202-257):
+    `eval_ode_run(sol, i, state_filter, eval_funcs, global_eval_funcs, matrix_eval_funcs, par_var, eps, par_bounds,
+    distance_matrix_func; N_t=200, alg=nothing, return_pm=true, new_tspan=nothing, kwargs...)`.
+
+    After the main run, three short runs restart from its end state `sol[end]` at p - eps, p, p + eps (clipped to
+    par_bounds) over `new_tspan` (default: the first 15 % of the main time span) with rel_transient_time 0.1; the
+    distances D[1,2] and D[2,3] between their measures (or their mean when return_pm is false) are appended to the
+    measures as scalars.  `distance_matrix_func` is fixed to the default L1 `distance_matrix(sol, prob, weights)`;
+    it crosses the ABI as its `weights`.  `solve_kwargs` are the kwargs the reference hands to the inner solve."""
+
+    def __init__(self, eps, par_bounds, weights, N_t=200, return_pm=True, new_tspan=None, alg=None, **solve_kwargs):
+        self.eps = float(eps)
+        self.par_bounds = (float(par_bounds[0]), float(par_bounds[1]))
+        self.weights = [float(w) for w in weights]
+        self.N_t = int(N_t)
+        self.return_pm = bool(return_pm)
+        self.new_tspan = None if new_tspan is None else (float(new_tspan[0]), float(new_tspan[1]))
+        self.alg = alg
+        self.solve_kwargs = solve_kwargs
 
 
 eval_ode_run = EvalOdeRun()  # default: mean, std (corrected, given mean), KL-hist — eval_mc_prob.jl:191-198
@@ -441,6 +464,13 @@ def _solver_opts(prob, alg, kwargs):
 def custom_solve_b200(prob, t_save, alg=None, **kwargs):
     """The `custom_solve(prob, t_save)` plug-in (setup_mc_prob.jl:1102-1104): integrates and featurizes the
     whole ensemble on the GPU and returns the per-run measures in the caller's run order."""
+    return _solve_b200(prob, t_save, alg, abi.SAVE_NONE, kwargs)[:5]
+
+
+def _solve_b200(prob, t_save, alg, save_mode, kwargs):
+    """custom_solve_b200 plus the optional sample export of mcbb_solve_features_saved: returns
+    (feat, mat, glob, retcode, nsteps, saved) with saved = None, [N_mc, n_dim, n_t] (SAVE_ALL) or the end states
+    [N_mc, n_dim] (SAVE_LAST); complex systems come back as complex arrays."""
     names = prob.par_names
     psys = prob.pars.pack(names)
     pfeat = prob.eval_ode_func.pack()
@@ -461,11 +491,22 @@ def custom_solve_b200(prob, t_save, alg=None, **kwargs):
     ret = np.zeros(n_mc, dtype=np.int32)
     nsteps = np.zeros((n_mc, 2), dtype=np.int64, order="F")
     dp = abi.c_double_p
-    check(lib().mcbb_solve_features(
+    saved = None
+    if save_mode == abi.SAVE_ALL:
+        saved = np.empty((n_mc, len(t_save), psys.n_dim))  # per run: n_dim x n_t column-major
+    elif save_mode == abi.SAVE_LAST:
+        saved = np.empty((n_mc, psys.n_dim), order="F")
+    check(lib().mcbb_solve_features_saved(
         C.byref(psys.desc), C.byref(o), C.byref(pfeat.opts), n_mc, ic.ctypes.data_as(dp), par.ctypes.data_as(dp),
         t_save.ctypes.data_as(dp), len(t_save), feat.ctypes.data_as(dp),
         mat.ctypes.data_as(dp) if mat is not None else dp(), glob.ctypes.data_as(dp) if glob is not None else dp(),
-        ret.ctypes.data_as(abi.c_int32_p), nsteps.ctypes.data_as(abi.c_int64_p)))
+        ret.ctypes.data_as(abi.c_int32_p), nsteps.ctypes.data_as(abi.c_int64_p), int(save_mode),
+        saved.ctypes.data_as(dp) if saved is not None else dp()))
+    if saved is not None:
+        if save_mode == abi.SAVE_ALL:
+            saved = np.transpose(saved, (0, 2, 1))  # [run, dim, sample]
+        if np.iscomplexobj(prob.ic):
+            saved = saved[:, 0::2] + 1j * saved[:, 1::2]
     if prob.eval_ode_func.failure_handling == "Inf":  # eval_mc_prob.jl:97-119
         bad = (ret == abi.RET_DTLESSTHANMIN) | (ret == abi.RET_UNSTABLE)
         feat[bad] = np.inf
@@ -473,7 +514,7 @@ def custom_solve_b200(prob, t_save, alg=None, **kwargs):
             mat[bad] = np.inf
         if glob is not None:
             glob[bad] = np.inf
-    return feat, mat, glob, ret, nsteps
+    return feat, mat, glob, ret, nsteps, saved
 
 
 def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, custom_solve=None,
@@ -483,9 +524,23 @@ def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, 
     Integrates N_mc trajectories, keeps only the post-transient statistics and sorts by parameter value.
     """
     t_save = tsave_array(prob.p, N_t, prob.rel_transient_time)
+    cont = getattr(prob.eval_ode_func, "continuation", None)
+    end = None
+    if cont is not None:
+        if custom_solve is not None:
+            raise MCBBError("the continuation / response analysis needs the end states: not available with a "
+                            "user custom_solve")
+
+        def custom_solve(sub, ts, alg=None, **kw):  # keeps the end states of the runs it solved last
+            nonlocal last_end
+            *out, last_end = _solve_b200(sub, ts, alg, abi.SAVE_LAST, kw)
+            return tuple(out)
+        last_end = None
     if custom_solve is None:
         custom_solve = custom_solve_b200
     feat, mat, glob, ret, nsteps = custom_solve(prob, t_save, alg=alg, **kwargs)
+    if cont is not None:
+        end = last_end
     if prob.eval_ode_func.failure_handling == "Repeat":
         # eval_ode_run returns ((), true) for a failed run and the ensemble loop redraws its initial condition,
         # at most 10 times (eval_mc_prob.jl:120-123, setup_mc_prob.jl:790-813)
@@ -500,6 +555,8 @@ def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, 
             f2, m2, g2, r2, n2 = custom_solve(sub, t_save, alg=alg, **kwargs)
             prob.ic[bad] = sub.ic
             feat[bad], ret[bad], nsteps[bad] = f2, r2, n2
+            if end is not None:
+                end[bad] = last_end
             if mat is not None:
                 mat[bad] = m2
             if glob is not None:
@@ -508,6 +565,9 @@ def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, 
             if np.any(ret != abi.RET_SUCCESS):
                 raise MCBBError("More than 10 Repeats of a Problem in the Monte Carlo Run, there might me something "
                                 "wrong here!")
+    if cont is not None:  # (meas_1..., dD...): the responses follow the global measures, eval_mc_prob.jl:253-256
+        dD = _continuation_response(prob, end, cont, alg, kwargs)
+        glob = dD if glob is None else np.asfortranarray(np.hstack([glob, dD]))
     sol = DEMCBBSol(feat, mat, glob, ret, nsteps, N_t, custom_solve)
     if flag_check_inf_nan:
         inf_nan = check_inf_nan(sol)
@@ -518,6 +578,86 @@ def solve(prob, alg=None, N_t=400, parallel_type=None, flag_check_inf_nan=True, 
     if sort_results:
         sort_(sol, prob)
     return sol
+
+
+def _continuation_response(prob, end, cont, alg, kwargs):
+    """The three restarted runs per trajectory of eval_mc_prob.jl:209-244, for all N_mc trajectories in ONE
+    ensemble of 3 N_mc runs, and their distances D[1,2], D[2,3] (eval_mc_prob.jl:246-251)."""
+    import copy
+    n = prob.N_mc
+    p0 = prob.par[:, 0]
+    par3 = np.stack([p0 - cont.eps, p0, p0 + cont.eps], axis=1)
+    par3[par3[:, 0] < cont.par_bounds[0], 0] = cont.par_bounds[0]
+    par3[par3[:, 2] > cont.par_bounds[1], 2] = cont.par_bounds[1]
+    t0, t1 = prob.p.tspan
+    tspan = cont.new_tspan if cont.new_tspan is not None else (t0, t0 + 0.15 * (t1 - t0))
+    sub = copy.copy(prob)
+    sub.p = copy.copy(prob.p)
+    sub.p.tspan = (float(tspan[0]), float(tspan[1]))
+    sub.ic = np.asfortranarray(np.repeat(end, 3, axis=0))  # runs 3i, 3i+1, 3i+2 restart from sol_i[end]
+    sub.par = np.asfortranarray(par3.reshape(-1, 1))
+    sub.N_mc = 3 * n
+    sub.rel_transient_time = 0.1  # DEMCBBProblem(mcp, 3, 0.1, ic, par, par_var), :239
+    sub.eval_ode_func = copy.copy(prob.eval_ode_func)
+    sub.eval_ode_func.continuation = None
+    ts = tsave_array(sub.p, cont.N_t, sub.rel_transient_time)
+    kw = cont.solve_kwargs if cont.solve_kwargs else kwargs
+    f, mt, g, r, ns = custom_solve_b200(sub, ts, alg=cont.alg if cont.alg is not None else alg, **kw)
+    sol3 = DEMCBBSol(f, mt, g, r, ns, cont.N_t, custom_solve_b200)
+    # the inner solve's sort by parameter keeps (p - eps, p, p + eps) in place: ascending, ties stable
+    X, glen, gw = feature_groups(sol3, sub, cont.weights)
+    d12, d23 = np.zeros(n), np.zeros(n)
+    c = 0
+    for L, w in zip(glen, gw):  # distance_matrix: per-group L1 sums, weighted, accumulated in group order
+        blk = X[:, c:c + L]
+        d12 += w * np.abs(blk[0::3] - blk[1::3]).sum(axis=1)
+        d23 += w * np.abs(blk[1::3] - blk[2::3]).sum(axis=1)
+        c += L
+    if cont.return_pm:
+        return np.asfortranarray(np.stack([d12, d23], axis=1))
+    return np.asfortranarray(((d12 + d23) / 2.0)[:, None])
+
+
+class Trajectory:
+    """What `sol.solve_command(prob_i)` returns to get_trajectory: the samples at t_save (savestart = false,
+    save_everystep = false; setup_mc_prob.jl:1108-1110).  `np.asarray(tr)` is the N_dim x N_t matrix."""
+
+    def __init__(self, t, u, retcode, i_run):
+        self.t, self.u, self.retcode, self.i_run = t, u, int(retcode), int(i_run)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.u, dtype=dtype)
+
+    def __getitem__(self, k):
+        return self.u[:, k]
+
+    def __len__(self):
+        return self.u.shape[1]
+
+
+def get_trajectory(prob, sol, clusters_or_i, i=None, only_sol=True, alg=None, rng=None, **kwargs):
+    """get_trajectory(prob, sol, clusters, i; only_sol) / get_trajectory(prob, sol, i_run; only_sol)
+    (eval_clustering.jl:1484-1500): re-solves ONE run and returns its saved trajectory.  With a clustering result a
+    random member of cluster `i` (1-based, 1 = the noise "cluster", as in the reference) is picked; `i_run` is
+    0-based like `sol[i_run]`.  `rng` (numpy Generator) makes the pick reproducible."""
+    import copy
+    if i is not None:
+        members = np.nonzero(np.asarray(clusters_or_i.assignments) == (int(i) - 1))[0]
+        if len(members) == 0:
+            raise MCBBError("cluster %d has no members" % int(i))
+        i_run = int((rng or np.random.default_rng()).choice(members))
+    else:
+        i_run = int(clusters_or_i)
+    if not 0 <= i_run < prob.N_mc:
+        raise MCBBError("run index out of range")
+    sub = copy.copy(prob)
+    sub.ic = np.asfortranarray(prob.ic[i_run:i_run + 1])
+    sub.par = np.asfortranarray(prob.par[i_run:i_run + 1])
+    sub.N_mc = 1
+    t_save = tsave_array(prob.p, sol.N_t, prob.rel_transient_time)
+    *_, ret, _ns, saved = _solve_b200(sub, t_save, alg, abi.SAVE_ALL, kwargs)
+    tr = Trajectory(t_save, saved[0], ret[0], i_run)
+    return tr if only_sol else (tr, sub, i_run)
 
 
 def sort_(sol, prob, i=1):

@@ -20,7 +20,7 @@ struct ScratchSlot {
     size_t cap = 0;
     int dev = -1;
 };
-static ScratchSlot g_scratch[64];
+static ScratchSlot g_scratch[72];
 static std::mutex g_scratch_mu;
 
 void* scratch_get(int slot, size_t bytes) {
@@ -335,7 +335,19 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
                             int64_t n_mc, const double* ic_dev, const double* par_dev, const double* t_save_dev,
                             int32_t n_t, double* feat_dev, double* matrix_dev, double* global_dev,
                             int32_t* retcode_dev, int64_t* nsteps_dev, void* stream) {
+    return mcbb_solve_features_saved_dev(sys, opts, feat, n_mc, ic_dev, par_dev, t_save_dev, n_t, feat_dev, matrix_dev,
+                                         global_dev, retcode_dev, nsteps_dev, MCBB_SAVE_NONE, nullptr, stream);
+}
+
+int mcbb_solve_features_saved_dev(const mcbb_system_desc* sys, const mcbb_solver_opts* opts,
+                                  const mcbb_feat_opts* feat, int64_t n_mc, const double* ic_dev,
+                                  const double* par_dev, const double* t_save_dev, int32_t n_t, double* feat_dev,
+                                  double* matrix_dev, double* global_dev, int32_t* retcode_dev, int64_t* nsteps_dev,
+                                  int32_t save_mode, double* saved_dev, void* stream) {
     if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
+    if (save_mode != MCBB_SAVE_NONE && save_mode != MCBB_SAVE_ALL && save_mode != MCBB_SAVE_LAST)
+        MCBB_FAIL("solve: unknown save mode");
+    if (save_mode != MCBB_SAVE_NONE && !saved_dev) MCBB_FAIL("solve: sample export requested but saved_out is NULL");
     if (n_mc < 1) MCBB_FAIL("solve: N_mc must be positive");
     if (!ic_dev || !t_save_dev || !feat_dev) MCBB_FAIL("solve: NULL ic / t_save / feat_out");
     if (sys->n_par > 0 && !par_dev) MCBB_FAIL("solve: NULL par with n_par > 0");
@@ -372,6 +384,13 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
         io.ckpt = (double*)scratch_get(7, sizeof(double) * (size_t)(2 * S.n_dim + 4) * (size_t)n_mc);
         if (!io.ckpt) MCBB_FAIL("solve: device allocation of the KL checkpoint buffer failed");
     }
+    if (save_mode != MCBB_SAVE_NONE) {
+        io.saved = saved_dev;
+        io.save_mode = save_mode;
+        // samples a failed run never reached read as NaN (all-ones bytes are a quiet NaN)
+        const size_t cnt = (size_t)n_mc * S.n_dim * (save_mode == MCBB_SAVE_ALL ? (size_t)n_t : 1);
+        MCBB_CUDA_OK(cudaMemsetAsync(saved_dev, 0xFF, sizeof(double) * cnt, st));
+    }
     return solve_features_launch(sys, S, o, F, io, st);
 }
 
@@ -379,7 +398,17 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
                         int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
                         double* feat_out, double* matrix_out, double* global_out, int32_t* retcode_out,
                         int64_t* nsteps_out) {
+    return mcbb_solve_features_saved(sys, opts, feat, n_mc, ic, par, t_save, n_t, feat_out, matrix_out, global_out,
+                                     retcode_out, nsteps_out, MCBB_SAVE_NONE, nullptr);
+}
+
+int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
+                              int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
+                              double* feat_out, double* matrix_out, double* global_out, int32_t* retcode_out,
+                              int64_t* nsteps_out, int32_t save_mode, double* saved_out) {
     if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
+    if (save_mode != MCBB_SAVE_NONE && !saved_out) MCBB_FAIL("solve: sample export requested but saved_out is NULL");
+    if (save_mode < MCBB_SAVE_NONE || save_mode > MCBB_SAVE_LAST) MCBB_FAIL("solve: unknown save mode");
     if (n_mc < 1) MCBB_FAIL("solve: N_mc must be positive");
     if (!ic || !t_save || !feat_out) MCBB_FAIL("solve: NULL ic / t_save / feat_out");
     const bool cplx = sys->system == MCBB_SYS_STUART_LANDAU;
@@ -402,6 +431,14 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
     int* d_ret = (int*)scratch_get(35, sizeof(int) * (size_t)n_mc);
     long long* d_ns = (long long*)scratch_get(36, sizeof(long long) * 2 * (size_t)n_mc);
     if (!d_ic || !d_par || !d_ts || !d_feat || !d_glob || !d_ret || !d_ns) MCBB_FAIL("solve: device allocation failed");
+    const size_t b_saved = save_mode == MCBB_SAVE_NONE
+                               ? 0
+                               : sizeof(double) * (size_t)n_mc * sys->n_dim * (save_mode == MCBB_SAVE_ALL ? (size_t)n_t : 1);
+    double* d_saved = nullptr;
+    if (b_saved) {
+        d_saved = (double*)scratch_get(64, b_saved);
+        if (!d_saved) MCBB_FAIL("solve: device allocation of the sample export buffer failed");
+    }
     cudaStream_t st = 0;
     MCBB_CUDA_OK(cudaMemcpyAsync(d_ic, ic, b_ic, cudaMemcpyHostToDevice, st));
     if (sys->n_par > 0) {
@@ -409,10 +446,12 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
         MCBB_CUDA_OK(cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, st));
     }
     MCBB_CUDA_OK(cudaMemcpyAsync(d_ts, t_save, b_ts, cudaMemcpyHostToDevice, st));
-    if (int rc = mcbb_solve_features_dev(sys, opts, feat, n_mc, d_ic, d_par, d_ts, n_t, d_feat,
-                                         feat->matrix_meas != MCBB_MAT_NONE ? d_mat : nullptr,
-                                         feat->n_global > 0 ? d_glob : nullptr, d_ret, (int64_t*)d_ns, (void*)st))
+    if (int rc = mcbb_solve_features_saved_dev(sys, opts, feat, n_mc, d_ic, d_par, d_ts, n_t, d_feat,
+                                               feat->matrix_meas != MCBB_MAT_NONE ? d_mat : nullptr,
+                                               feat->n_global > 0 ? d_glob : nullptr, d_ret, (int64_t*)d_ns,
+                                               save_mode, d_saved, (void*)st))
         return rc;
+    if (b_saved) MCBB_CUDA_OK(cudaMemcpyAsync(saved_out, d_saved, b_saved, cudaMemcpyDeviceToHost, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(feat_out, d_feat, b_feat, cudaMemcpyDeviceToHost, st));
     if (global_out && feat->n_global > 0)
         MCBB_CUDA_OK(cudaMemcpyAsync(global_out, d_glob, b_glob, cudaMemcpyDeviceToHost, st));

@@ -86,6 +86,10 @@ struct SolveIO {
     long long* nsteps;     // [2][n_mc] or null
     double* ckpt;          // [2*n_dim + 4][n_mc] checkpoint scratch for the KL pass, or null
     unsigned long long* work_counter;  // dynamic trajectory queue
+    // optional export of the saved samples themselves (get_trajectory, eval_clustering.jl:1484-1492; the end state
+    // the continuation analysis restarts from, eval_mc_prob.jl:210-216).  Lane kernels only.
+    double* saved;   // save_mode 1: [n_mc][n_t][n_dim]; save_mode 2: the last sample, [n_dim][n_mc] (the ic layout)
+    int save_mode;   // 0 = none
 };
 
 SolverDev resolve_solver(const mcbb_solver_opts* o);

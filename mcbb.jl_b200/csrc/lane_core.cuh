@@ -233,6 +233,14 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
 
     // one saved sample (index isave in t_save; value of state dim d given by val(d))
     auto consume = [&](auto&& val) {
+        if (io.saved && pass == 0) {  // sample export: every sample, or only sol[end]
+            if (io.save_mode == 1) {
+                double* dst = io.saved + ((size_t)run * n_t + isave) * n;
+                for (int d = 0; d < n; d++) dst[d] = val(d);
+            } else if (isave == n_t - 1) {
+                for (int d = 0; d < n; d++) io.saved[(size_t)d * io.n_mc + run] = val(d);
+            }
+        }
         if (isave >= 1) {  // the first saved sample is dropped, eval_mc_prob.jl:152
             ckpt_done = true;
             const double rk = 1. / (double)isave;

@@ -316,12 +316,14 @@ int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const Sol
     if (!(o.t1 > o.t0)) MCBB_FAIL("tspan must be increasing");
     if (io.n_t < 2) MCBB_FAIL("need at least two save times (the first saved sample is dropped)");
     bool handled = false;
-    if (int rc = launch_batched_umma(hs, S, o, F, io, st, &handled)) return rc;  // tcgen05 + tensor memory
-    if (handled) return 0;
-    if (int rc = launch_batched_imma(hs, S, o, F, io, st, &handled)) return rc;
-    if (handled) return 0;
-    if (int rc = launch_batched_kuramoto(hs, S, o, F, io, st, &handled)) return rc;
-    if (handled) return 0;
+    if (!io.saved) {  // the batched kernels keep no per-sample state to export: sample export runs the lane kernels
+        if (int rc = launch_batched_umma(hs, S, o, F, io, st, &handled)) return rc;  // tcgen05 + tensor memory
+        if (handled) return 0;
+        if (int rc = launch_batched_imma(hs, S, o, F, io, st, &handled)) return rc;
+        if (handled) return 0;
+        if (int rc = launch_batched_kuramoto(hs, S, o, F, io, st, &handled)) return rc;
+        if (handled) return 0;
+    }
     switch (S.system) {
     case MCBB_SYS_LOGISTIC:
         return launch_lane<MCBB_SYS_LOGISTIC>(S, o, F, io, st);

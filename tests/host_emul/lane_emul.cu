@@ -35,7 +35,7 @@ static void run_host(const SysDev& S, const SolverDev& o, const FeatDev& F, cons
 extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
                                    int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
                                    double* feat_out, double* global_out, int32_t* retcode_out, int64_t* nsteps_out,
-                                   double* matrix_out) {
+                                   double* matrix_out, int32_t save_mode, double* saved_out) {
     int len[5];
     if (table_lengths(sys, len)) return 1;
     SysDev S = {};
@@ -65,6 +65,8 @@ extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solve
     SolveIO io = {};
     io.n_mc = n_mc; io.ic = ic; io.par = par; io.t_save = t_save; io.n_t = n_t; io.feat = feat_out;
     io.glob = global_out; io.matrix = matrix_out; io.retcode = retcode_out; io.nsteps = (long long*)nsteps_out; io.ckpt = ckpt.data();
+    io.saved = save_mode ? saved_out : nullptr;
+    io.save_mode = save_mode;
     switch (S.system) {
     case MCBB_SYS_LOGISTIC: run_host<MCBB_SYS_LOGISTIC>(S, o, F, io); break;
     case MCBB_SYS_KURAMOTO: run_host<MCBB_SYS_KURAMOTO>(S, o, F, io); break;

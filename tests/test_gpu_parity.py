@@ -470,6 +470,102 @@ def test_complex_state_correlation_measures(gpu, orc):
     assert np.all(np.abs(e - e_ref) < 1e-15, axis=1).mean() >= 0.95
 
 
+def test_get_trajectory_and_end_state_export(gpu, orc):
+    """get_trajectory (eval_clustering.jl:1484-1500): the samples `sol.solve_command(prob_i)` saves at t_save, for a
+    given run and for a random member of a cluster; plus the end-state export (sol[end]) of a whole ensemble."""
+    m = gpu
+    prob, weights = cases.c1_problem(m, n_ics=40, seed=23)
+    sol = m.solve(prob)  # sorted: prob.ic / prob.par now follow the sorted order
+    psys = prob.pars.pack(prob.par_names)
+    o = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan)
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    for i_run in (0, 57, prob.N_mc - 1):
+        tr = m.get_trajectory(prob, sol, i_run)
+        ref, ret, _, nsv = orc.trajectory(psys, o, prob.ic[i_run], prob.par[i_run], ts)
+        assert tr.retcode == ret == 0 and nsv == 400 and np.array_equal(tr.t, ts)
+        assert np.asarray(tr).shape == (6, 400) and len(tr) == 400
+        assert np.allclose(np.asarray(tr), ref, rtol=1e-9, atol=1e-9)
+        # the measures of the run are the statistics of exactly these samples (first one dropped)
+        assert np.allclose(sol.feat[i_run, :, 0], np.asarray(tr)[:, 1:].mean(axis=1), rtol=1e-12, atol=1e-12)
+    D = m.distance_matrix(sol, prob, weights)
+    db = m.dbscan(D, 0.5, 4)
+    k = 2 if len(db.counts) >= 1 else 1
+    tr, sub, i_run = m.get_trajectory(prob, sol, db, k, only_sol=False, rng=np.random.default_rng(0))
+    assert db.assignments[i_run] == k - 1 and sub.N_mc == 1 and np.array_equal(sub.ic[0], prob.ic[i_run])
+    with pytest.raises(m.MCBBError):
+        m.get_trajectory(prob, sol, db, len(db.counts) + 5)
+    # whole-ensemble exports through the C-ABI: every sample, and only the last one (the ic layout)
+    ts20 = ts[:20]
+    *_, ret_a, _, all_s = m.api._solve_b200(prob, ts20, None, m.abi.SAVE_ALL, {})
+    *_, ret_l, _, last = m.api._solve_b200(prob, ts20, None, m.abi.SAVE_LAST, {})
+    assert all_s.shape == (prob.N_mc, 6, 20) and last.shape == (prob.N_mc, 6)
+    assert np.array_equal(all_s[:, :, -1], last) and np.all(ret_a == 0) and np.all(ret_l == 0)
+    # a failed run exports NaN for the samples it never reached
+    *_, ret_f, _, cut = m.api._solve_b200(prob, ts, None, m.abi.SAVE_ALL, dict(maxiters=8))
+    assert np.all(ret_f == m.abi.RET_MAXITERS) and np.isnan(cut[:, :, -1]).all()
+    # complex states come back complex
+    Ns = 8
+    A1 = np.roll(np.eye(Ns), 1, 0) + np.roll(np.eye(Ns), -1, 0)
+    pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.9, Ns, 1, 1, A1, A1)
+    rng, prng = np.random.default_rng(3), np.random.default_rng(4)
+    rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(Ns, dtype=complex), (0.0, 10.0), pars)
+    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_imag"))
+    probc = m.DEMCBBProblem(rp, lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1)), 8, pars,
+                            ("eps", lambda: prng.uniform(1.8, 2.1)), ev, 0.5)
+    solc = m.solve(probc)
+    trc = m.get_trajectory(probc, solc, 5)
+    ic = np.stack([probc.ic[5].real, probc.ic[5].imag], axis=1).reshape(-1)
+    oc = m.abi.solver_opts(m.abi.ALG_TSIT5, probc.p.tspan)
+    refc, _, _, _ = orc.trajectory(probc.pars.pack(probc.par_names), oc, ic, probc.par[5],
+                                   m.tsave_array(probc.p, 400, 0.5))
+    assert np.iscomplexobj(trc.u) and trc.u.shape == (Ns, 400)
+    assert np.allclose(trc.u, refc[0::2] + 1j * refc[1::2], rtol=1e-9, atol=1e-9)
+
+
+def test_continuation_response_analysis(gpu, orc):
+    """eval_ode_run with the response analysis (eval_mc_prob.jl:202-257): after each run, three short runs restart
+    from its end state at p - eps, p, p + eps; D[1,2] and D[2,3] of their measures are appended as scalars.  The
+    oracle side is composed from its single-trajectory, featurize and distance functions."""
+    m = gpu
+    eps, bounds, w_inner = 0.25, (1.0, 3.0), [1.0, 0.5, 1.0]
+    for return_pm in (True, False):
+        prob, _ = cases.c1_problem(m, n_ics=12, seed=29, eval_funcs=(m.mean, m.std))
+        prob.eval_ode_func = m.EvalOdeRun(eval_funcs=(m.mean, m.std),
+                                          continuation=m.ContinuationResponse(eps, bounds, w_inner, N_t=200,
+                                                                              return_pm=return_pm))
+        sol = m.solve(prob)
+        n_resp = 2 if return_pm else 1
+        assert (sol.N_meas_dim, sol.N_meas_global, sol.N_meas) == (2, n_resp, 2 + n_resp)
+        assert sol.glob.shape == (prob.N_mc, n_resp) and len(sol[0]) == 2 + n_resp
+        # oracle composition, in the sorted run order solve() leaves behind
+        psys, pfeat = prob.pars.pack(prob.par_names), m.EvalOdeRun(eval_funcs=(m.mean, m.std)).pack()
+        o = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan)
+        ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+        n = prob.N_mc
+        end = np.stack([orc.trajectory(psys, o, prob.ic[i], prob.par[i], ts)[0][:, -1] for i in range(n)])
+        p0 = prob.par[:, 0]
+        par3 = np.stack([np.maximum(p0 - eps, bounds[0]), p0, np.minimum(p0 + eps, bounds[1])], axis=1)
+        assert (par3[:, 0] == p0).any() and (par3[:, 2] == p0).any()  # both bounds clip somewhere
+        t0, t1 = prob.p.tspan
+        o2 = m.abi.solver_opts(m.abi.ALG_TSIT5, (t0, t0 + 0.15 * (t1 - t0)))
+        rp2 = m.ODEProblem(m.kuramoto_network, np.zeros(6), (t0, t0 + 0.15 * (t1 - t0)), prob.pars)
+        ts2 = m.tsave_array(rp2, 200, 0.1)
+        ref3 = orc.solve_features(psys, o2, pfeat, np.repeat(end, 3, axis=0), par3.reshape(-1, 1), ts2)["feat"]
+        X = np.concatenate([ref3[:, :, 0], ref3[:, :, 1], par3.reshape(-1, 1)], axis=1)
+        d = np.zeros((n, 2))
+        for i in range(n):
+            D3 = orc.distance_matrix(X[3 * i:3 * i + 3], [6, 6, 1], w_inner)
+            d[i] = D3[0, 1], D3[1, 2]
+        want = d if return_pm else d.mean(axis=1, keepdims=True)
+        assert np.allclose(sol.glob, want, rtol=1e-6, atol=1e-9), np.abs(sol.glob - want).max()
+        # the response vanishes only where the bound clipped the parameter onto p itself ... and not elsewhere
+        if return_pm:
+            assert np.all(sol.glob[par3[:, 0] != p0, 0] > 0)
+    # the responses enter distance_matrix as global measures
+    D = m.distance_matrix(sol, prob, [1.0, 0.5, 0.25, 1.0])
+    assert D.data.shape == (prob.N_mc, prob.N_mc) and np.isfinite(D.data).all()
+
+
 def test_k_dist_and_knn_helpers(gpu):
     """k_dist / KNN_dist / KNN_dist_relative (eval_clustering.jl:1504-1553) against numpy on the same matrix."""
     m = gpu

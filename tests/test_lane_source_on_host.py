@@ -1,0 +1,139 @@
+"""CPU test (-m "not gpu") of the PRODUCT's per-lane integrator source: tests/host_emul/lane_emul.cu compiles
+csrc/lane_core.cuh (the code every `k_solve_lane<SYS>` instantiates) for the host and runs it one lane at a time, so
+the state machine, the fused statistics, the correlation measures and the sample export are compared with the oracle
+in the CPU-only container as well.  The harness is test infrastructure: the product never loads it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "host_emul", "lane_emul.cu")
+OUT = os.path.join(HERE, "host_emul", "_build", "liblane_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul(mcbb):
+    deps = [SRC, mcbb.LIB_PATH] + [os.path.join(ROOT, "mcbb.jl_b200", "csrc", f)
+                                   for f in ("lane_core.cuh", "systems.cuh", "common.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        libdir = os.path.dirname(mcbb.LIB_PATH)
+        cmd = ["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler",
+               "-fPIC", "-I" + os.path.join(ROOT, "include"), "-o", OUT, SRC, "-L" + libdir,
+               "-l:" + os.path.basename(mcbb.LIB_PATH), "-Xlinker", "-rpath", "-Xlinker", libdir]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+    L = C.CDLL(OUT)
+    abi = mcbb.abi
+    dp = abi.c_double_p
+    L.emul_solve_features.argtypes = [C.POINTER(abi.SystemDesc), C.POINTER(abi.SolverOpts), C.POINTER(abi.FeatOpts),
+                                      C.c_int64, dp, dp, dp, C.c_int32, dp, dp, abi.c_int32_p, abi.c_int64_p, dp,
+                                      C.c_int32, dp]
+
+    def solve(psys, opts, pfeat, ic, par, t_save, save_mode=0):
+        ic = np.asfortranarray(ic, dtype=np.float64)
+        par = np.asfortranarray(np.asarray(par, dtype=np.float64).reshape(ic.shape[0], -1))
+        t_save = np.ascontiguousarray(t_save, dtype=np.float64)
+        n_mc, nf = ic.shape[0], pfeat.n_filter(psys)
+        feat = np.full((n_mc, nf, pfeat.n_meas), np.nan, order="F")
+        mat = np.full((n_mc, pfeat.corr_nbins), np.nan, order="F")
+        glob = np.full((n_mc, max(1, pfeat.n_global)), np.nan, order="F")
+        ret = np.zeros(n_mc, dtype=np.int32)
+        ns = np.zeros((n_mc, 2), dtype=np.int64, order="F")
+        saved = None
+        if save_mode == abi.SAVE_ALL:
+            saved = np.full((n_mc, len(t_save), psys.n_dim), np.nan)
+        elif save_mode == abi.SAVE_LAST:
+            saved = np.full((n_mc, psys.n_dim), np.nan, order="F")
+        rc = L.emul_solve_features(C.byref(psys.desc), C.byref(opts), C.byref(pfeat.opts), n_mc, ic.ctypes.data_as(dp),
+                                   par.ctypes.data_as(dp), t_save.ctypes.data_as(dp), len(t_save),
+                                   feat.ctypes.data_as(dp), glob.ctypes.data_as(dp), ret.ctypes.data_as(abi.c_int32_p),
+                                   ns.ctypes.data_as(abi.c_int64_p), mat.ctypes.data_as(dp), int(save_mode),
+                                   saved.ctypes.data_as(dp) if saved is not None else dp())
+        assert rc == 0
+        if save_mode == abi.SAVE_ALL:
+            saved = np.transpose(saved, (0, 2, 1))
+        return dict(feat=feat, matrix=mat, glob=glob, retcode=ret, nsteps=ns, saved=saved)
+    return solve
+
+
+def _setup(m, prob, **kw):
+    psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+    a = m.abi.ALG_FUNCTIONMAP if prob.p.discrete else m.abi.ALG_TSIT5
+    o = m.abi.solver_opts(a, prob.p.tspan, **kw)
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    ic = prob.ic
+    if np.iscomplexobj(ic):
+        ic = np.stack([ic.real, ic.imag], axis=2).reshape(ic.shape[0], -1)
+    return psys, o, pfeat, ic, prob.par, ts
+
+
+def test_lane_source_default_measures_match_oracle(mcbb, orc, emul):
+    prob, _ = cases.c1_problem(mcbb, n_ics=12, seed=41)
+    ctx = _setup(mcbb, prob)
+    got, ref = emul(*ctx), orc.solve_features(*ctx)
+    assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["nsteps"], ref["nsteps"])
+    cases.compare_features(got["feat"], ref, orc, *ctx)
+    prob, _ = cases.c2_problem(mcbb, n_mc=64)
+    ctx = _setup(mcbb, prob)
+    got, ref = emul(*ctx), orc.solve_features(*ctx)
+    cases.compare_features(got["feat"], ref, orc, *ctx)
+
+
+def test_lane_source_sample_export_matches_oracle_trajectories(mcbb, orc, emul):
+    abi = mcbb.abi
+    prob, _ = cases.c1_problem(mcbb, n_ics=6, seed=42, eval_funcs=(mcbb.mean, mcbb.std))
+    ctx = _setup(mcbb, prob)
+    psys, o, pfeat, ic, par, ts = ctx
+    plain = emul(*ctx)
+    all_s = emul(*ctx, save_mode=abi.SAVE_ALL)
+    last = emul(*ctx, save_mode=abi.SAVE_LAST)
+    assert np.array_equal(all_s["feat"], plain["feat"]) and np.array_equal(last["feat"], plain["feat"])
+    assert np.array_equal(all_s["saved"][:, :, -1], last["saved"])
+    for i in range(prob.N_mc):
+        ref, ret, _, nsv = orc.trajectory(psys, o, ic[i], par[i], ts)
+        assert ret == 0 and nsv == len(ts)
+        assert np.allclose(all_s["saved"][i], ref, rtol=1e-10, atol=1e-10)
+    # the measures are the statistics of these samples, first one dropped
+    assert np.allclose(plain["feat"][:, :, 0], all_s["saved"][:, :, 1:].mean(axis=2), rtol=1e-12, atol=1e-12)
+    assert np.allclose(plain["feat"][:, :, 1], all_s["saved"][:, :, 1:].std(axis=2, ddof=1), rtol=1e-9, atol=1e-12)
+    # a run that hits maxiters keeps NaN for the samples it never reached
+    ctx_f = _setup(mcbb, prob, maxiters=8)
+    cut = emul(*ctx_f, save_mode=abi.SAVE_ALL)
+    assert np.all(cut["retcode"] == abi.RET_MAXITERS) and np.isnan(cut["saved"][:, :, -1]).all()
+
+
+def test_lane_source_correlation_measures_real_and_complex(mcbb, orc, emul):
+    m = mcbb
+    for f in (m.correlation_hist, m.correlation_ecdf):
+        prob, _ = cases.c3_problem(m, n_mc=10, seed=5, N=10, tspan=(0.0, 60.0), tail=0.5)
+        prob.eval_ode_func = m.EvalOdeRun(state_filter=list(range(11, 21)), eval_funcs=(m.mean, m.std),
+                                          matrix_eval_funcs=[f])
+        ctx = _setup(m, prob, reltol=1e-9, abstol=1e-9)
+        got, ref = emul(*ctx), orc.solve_features(*ctx)
+        assert np.allclose(got["matrix"], ref["matrix"], rtol=0, atol=1e-15)
+        if f == m.correlation_hist:
+            assert np.all(got["matrix"].sum(axis=1) == 90) and (got["matrix"][:, :-1].sum(axis=1) > 0).all()
+    Ns = 8
+    A1 = np.roll(np.eye(Ns), 1, 0) + np.roll(np.eye(Ns), -1, 0)
+    A2 = A1 + np.roll(np.eye(Ns), 2, 0) + np.roll(np.eye(Ns), -2, 0)
+    for f, filt in ((m.correlation_hist, None), (m.correlation_ecdf, [1, 3, 4, 8])):
+        rng, prng = np.random.default_rng(31), np.random.default_rng(32)
+        pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.9, Ns, 1, 2, A1, A2)
+        ev = m.EvalOdeRun(state_filter=filt, eval_funcs=("mean_real", "std_real", "mean_imag", "std_imag"),
+                          matrix_eval_funcs=[f])
+        rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(Ns, dtype=complex), (0.0, 10.0), pars)
+        prob = m.DEMCBBProblem(rp, lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1)), 12, pars,
+                               ("eps", lambda: prng.uniform(1.8, 2.1)), ev, 0.0)
+        ctx = _setup(m, prob, reltol=1e-9, abstol=1e-9)
+        got, ref = emul(*ctx), orc.solve_features(*ctx)
+        cases.compare_features(got["feat"], ref, orc, *ctx, min_checked=0.8)
+        assert np.allclose(got["matrix"], ref["matrix"], rtol=0, atol=1e-15)
+        if filt is None:
+            assert np.all(got["matrix"].sum(axis=1) == 56) and (got["matrix"][:, :-1].sum(axis=1) > 0).all()
