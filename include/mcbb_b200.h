@@ -178,6 +178,23 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
  * Samples a failed run never reached are NaN.  Complex states are interleaved (re, im) like `ic`.  The export runs
  * the one-trajectory-per-lane kernels (the batched tensor-core kernels keep no per-sample state). */
 enum mcbb_save_mode { MCBB_SAVE_NONE = 0, MCBB_SAVE_ALL = 1, MCBB_SAVE_LAST = 2 };
+/* Per-run solver options — SolverParameterVar / SolverVarEnsembleProblem (src/solver_parametervar.jl:5-90;
+ * test/solver_parametervar.jl varies :reltol): `solve(prob_i, alg; name => par[i], kwargs...)`.  One option of
+ * mcbb_solver_opts is overridden per run by solver_vals[i]; the system parameters then usually stay fixed
+ * (sys->n_par = 0, par = NULL), as in the reference, but a simultaneous system-parameter sweep is allowed.
+ * Set with mcbb_set_solver_parameter_var before a solve_features* call of the SAME host thread; it applies to that one
+ * call and is cleared by it.  solver_vals is a HOST array of n_mc values for the host entry points and a DEVICE array
+ * for the *_dev ones.  Runs the lane kernels. */
+enum mcbb_solver_field {
+    MCBB_SOLVER_NONE = 0,
+    MCBB_SOLVER_ABSTOL = 1,
+    MCBB_SOLVER_RELTOL = 2,
+    MCBB_SOLVER_DT = 3,
+    MCBB_SOLVER_DTMAX = 4,
+    MCBB_SOLVER_DTMIN = 5
+};
+int mcbb_set_solver_parameter_var(int32_t solver_field, const double* solver_vals, int64_t n_vals);
+
 int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opts* opts,
                               const mcbb_feat_opts* feat, int64_t n_mc, const double* ic, const double* par,
                               const double* t_save, int32_t n_t, double* feat_out, double* matrix_out,

@@ -40,6 +40,7 @@ MAT_NONE = 0
 MAT_CORR_ECDF = 1
 MAT_CORR_HIST = 2
 SAVE_NONE, SAVE_ALL, SAVE_LAST = 0, 1, 2
+SOLVER_FIELDS = {"abstol": 1, "reltol": 2, "dt": 3, "dtmax": 4, "dtmin": 5}
 GLOB_SUM = 0
 
 c_double_p = C.POINTER(C.c_double)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmcbb_b200.so")
 EXPORTS = [
     "mcbb_version", "mcbb_init", "mcbb_finalize", "mcbb_last_error", "mcbb_device_info",
     "mcbb_kernel_launch_count", "mcbb_tsave_array", "mcbb_solve_features", "mcbb_solve_features_dev",
-    "mcbb_solve_features_saved", "mcbb_solve_features_saved_dev",
+    "mcbb_solve_features_saved", "mcbb_solve_features_saved_dev", "mcbb_set_solver_parameter_var",
     "mcbb_distance_matrix", "mcbb_distance_matrix_dev", "mcbb_dbscan_dense", "mcbb_dbscan_dense_dev",
     "mcbb_dbscan_features", "mcbb_dbscan_features_dev", "mcbb_dbscan_rows_count_dev",
     "mcbb_dbscan_rows_union_dev", "mcbb_dbscan_merge_parents_dev", "mcbb_dbscan_rows_border_dev",
@@ -52,6 +52,7 @@ def lib():
     L.mcbb_solve_features_dev.argtypes = [SD, SO, FO, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.mcbb_solve_features_saved.argtypes = [SD, SO, FO, C.c_int64, dp, dp, dp, C.c_int32, dp, dp, dp, ip, lp,
                                             C.c_int32, dp]
+    L.mcbb_set_solver_parameter_var.argtypes = [C.c_int32, dp, C.c_int64]
     L.mcbb_solve_features_saved_dev.argtypes = [SD, SO, FO, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp,
                                                 C.c_int32, vp, vp]
     L.mcbb_distance_matrix.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, dp]

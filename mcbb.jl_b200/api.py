@@ -299,8 +299,21 @@ eval_ode_run = EvalOdeRun()  # default: mean, std (corrected, given mean), KL-hi
 # ------------------------------------------------------------------------------------------------------------
 
 
+class SolverParameterVar:
+    """SolverParameterVar(name, new_val) (src/solver_parametervar.jl:5-35): a SOLVER option instead of a system
+    parameter is varied over the ensemble — `solve(prob_i, alg; name => par[i], kwargs...)` (:75-90).  `new_val` is
+    a generator `()->value` or an array of values; `name` one of abstol, reltol, dt, dtmax, dtmin."""
+
+    def __init__(self, name, new_val):
+        if name not in abi.SOLVER_FIELDS:
+            raise MCBBError("solver option %r cannot be varied per run on the B200 integrator (known: %s)"
+                            % (name, ", ".join(sorted(abi.SOLVER_FIELDS))))
+        self.name, self.new_val = name, new_val
+
+
 class DEMCBBProblem:
     """DEMCBBProblem(p, ic_gens | ic_ranges, [N_ic,] pars, (name, range | generator), eval_ode_func, tail_frac)
+    DEMCBBProblem(p, ic_gens | ic_ranges, [N_ic,] pars, SolverParameterVar(name, ...), eval_ode_func, tail_frac)
 
     * ic_ranges: list of arrays + parameter array      -> cartesian product, IC index fastest (:850-882)
     * ic generator(s), N_ic, parameter generator       -> N_ic random runs                     (:888-923)
@@ -322,9 +335,15 @@ class DEMCBBProblem:
         self.pars = pars
         self.eval_ode_func = eval_func
         self.rel_transient_time = float(tail_frac)
-        name, values = par_var[0], par_var[1]
+        self.solver_par = None
+        if isinstance(par_var, SolverParameterVar):  # setup_mc_prob.jl:354-364: the system parameters stay fixed
+            name, values = par_var.name, par_var.new_val
+            self.solver_par = name
+            self.par_names = []
+        else:
+            name, values = par_var[0], par_var[1]
+            self.par_names = [name]
         self.par_var = (name, values)
-        self.par_names = [name]
         n_dim = pars.n_dim() if not np.iscomplexobj(p.u0) else len(p.u0)
         self.ic_gens = None
         if callable(ic) or (isinstance(ic, (list, tuple)) and len(ic) > 0 and callable(ic[0])):
@@ -491,6 +510,11 @@ def _solve_b200(prob, t_save, alg, save_mode, kwargs):
     ret = np.zeros(n_mc, dtype=np.int32)
     nsteps = np.zeros((n_mc, 2), dtype=np.int64, order="F")
     dp = abi.c_double_p
+    if getattr(prob, "solver_par", None) is not None:  # the parameter column holds the per-run solver option
+        if prob.solver_par in kwargs:
+            raise MCBBError("solver option %r is both varied per run and given as a keyword" % prob.solver_par)
+        sv = np.ascontiguousarray(prob.par[:, 0], dtype=np.float64)
+        check(lib().mcbb_set_solver_parameter_var(abi.SOLVER_FIELDS[prob.solver_par], sv.ctypes.data_as(dp), n_mc))
     saved = None
     if save_mode == abi.SAVE_ALL:
         saved = np.empty((n_mc, len(t_save), psys.n_dim))  # per run: n_dim x n_t column-major

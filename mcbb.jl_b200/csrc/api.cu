@@ -339,12 +339,36 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
                                          global_dev, retcode_dev, nsteps_dev, MCBB_SAVE_NONE, nullptr, stream);
 }
 
+// one-shot per-thread request set by mcbb_set_solver_parameter_var and consumed by the next solve of this thread
+struct SolverVarRequest {
+    int field = MCBB_SOLVER_NONE;
+    const double* vals = nullptr;
+    long long n = 0;
+};
+static thread_local SolverVarRequest t_solver_var;
+
+int mcbb_set_solver_parameter_var(int32_t solver_field, const double* solver_vals, int64_t n_vals) {
+    if (solver_field == MCBB_SOLVER_NONE) {
+        t_solver_var = SolverVarRequest();
+        return 0;
+    }
+    if (solver_field < MCBB_SOLVER_ABSTOL || solver_field > MCBB_SOLVER_DTMIN) MCBB_FAIL("unknown solver option id");
+    if (!solver_vals || n_vals < 1) MCBB_FAIL("solver parameter variation: NULL or empty value array");
+    t_solver_var.field = solver_field;
+    t_solver_var.vals = solver_vals;
+    t_solver_var.n = n_vals;
+    return 0;
+}
+
 int mcbb_solve_features_saved_dev(const mcbb_system_desc* sys, const mcbb_solver_opts* opts,
                                   const mcbb_feat_opts* feat, int64_t n_mc, const double* ic_dev,
                                   const double* par_dev, const double* t_save_dev, int32_t n_t, double* feat_dev,
                                   double* matrix_dev, double* global_dev, int32_t* retcode_dev, int64_t* nsteps_dev,
                                   int32_t save_mode, double* saved_dev, void* stream) {
+    const SolverVarRequest sv = t_solver_var;  // applies to this call only
+    t_solver_var = SolverVarRequest();
     if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
+    if (sv.field != MCBB_SOLVER_NONE && sv.n != n_mc) MCBB_FAIL("solver parameter variation: need one value per run");
     if (save_mode != MCBB_SAVE_NONE && save_mode != MCBB_SAVE_ALL && save_mode != MCBB_SAVE_LAST)
         MCBB_FAIL("solve: unknown save mode");
     if (save_mode != MCBB_SAVE_NONE && !saved_dev) MCBB_FAIL("solve: sample export requested but saved_out is NULL");
@@ -384,6 +408,10 @@ int mcbb_solve_features_saved_dev(const mcbb_system_desc* sys, const mcbb_solver
         io.ckpt = (double*)scratch_get(7, sizeof(double) * (size_t)(2 * S.n_dim + 4) * (size_t)n_mc);
         if (!io.ckpt) MCBB_FAIL("solve: device allocation of the KL checkpoint buffer failed");
     }
+    if (sv.field != MCBB_SOLVER_NONE) {
+        io.solver_par = sv.vals;
+        io.solver_field = sv.field;
+    }
     if (save_mode != MCBB_SAVE_NONE) {
         io.saved = saved_dev;
         io.save_mode = save_mode;
@@ -409,6 +437,9 @@ int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opt
     if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
     if (save_mode != MCBB_SAVE_NONE && !saved_out) MCBB_FAIL("solve: sample export requested but saved_out is NULL");
     if (save_mode < MCBB_SAVE_NONE || save_mode > MCBB_SAVE_LAST) MCBB_FAIL("solve: unknown save mode");
+    const SolverVarRequest sv_host = t_solver_var;  // host values: uploaded below, then handed to the device entry
+    t_solver_var = SolverVarRequest();
+    if (sv_host.field != MCBB_SOLVER_NONE && sv_host.n != n_mc) MCBB_FAIL("solver parameter variation: need one value per run");
     if (n_mc < 1) MCBB_FAIL("solve: N_mc must be positive");
     if (!ic || !t_save || !feat_out) MCBB_FAIL("solve: NULL ic / t_save / feat_out");
     const bool cplx = sys->system == MCBB_SYS_STUART_LANDAU;
@@ -446,6 +477,14 @@ int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opt
         MCBB_CUDA_OK(cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, st));
     }
     MCBB_CUDA_OK(cudaMemcpyAsync(d_ts, t_save, b_ts, cudaMemcpyHostToDevice, st));
+    if (sv_host.field != MCBB_SOLVER_NONE) {
+        double* d_sv = (double*)scratch_get(65, sizeof(double) * (size_t)n_mc);
+        if (!d_sv) MCBB_FAIL("solve: device allocation failed");
+        MCBB_CUDA_OK(cudaMemcpyAsync(d_sv, sv_host.vals, sizeof(double) * (size_t)n_mc, cudaMemcpyHostToDevice, st));
+        t_solver_var.field = sv_host.field;
+        t_solver_var.vals = d_sv;
+        t_solver_var.n = n_mc;
+    }
     if (int rc = mcbb_solve_features_saved_dev(sys, opts, feat, n_mc, d_ic, d_par, d_ts, n_t, d_feat,
                                                feat->matrix_meas != MCBB_MAT_NONE ? d_mat : nullptr,
                                                feat->n_global > 0 ? d_glob : nullptr, d_ret, (int64_t*)d_ns,

@@ -90,6 +90,9 @@ struct SolveIO {
     // the continuation analysis restarts from, eval_mc_prob.jl:210-216).  Lane kernels only.
     double* saved;   // save_mode 1: [n_mc][n_t][n_dim]; save_mode 2: the last sample, [n_dim][n_mc] (the ic layout)
     int save_mode;   // 0 = none
+    // optional per-run value of ONE solver option (SolverParameterVar, src/solver_parametervar.jl).  Lane kernels only.
+    const double* solver_par;  // [n_mc] or null
+    int solver_field;          // enum mcbb_solver_field
 };
 
 SolverDev resolve_solver(const mcbb_solver_opts* o);

@@ -92,10 +92,15 @@ struct LaneShared {  // CTA-wide read-only data staged in shared memory
     SysTabs tabs;
 };
 
-template <int SYS, class WorkQ>
-MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io,
+// SOLVAR: one solver option (io.solver_field) is taken per run from io.solver_par — SolverParameterVar /
+// SolverVarEnsembleProblem, src/solver_parametervar.jl:75-90 (`solve(prob_i, alg; name => par[i], kwargs...)`).
+template <int SYS, class WorkQ, bool SOLVAR = false>
+MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F, const SolveIO& io,
                        const LaneShared& L, double* st, double* acc, unsigned short* bins, double* como,
                        const int bs, WorkQ& wq) {
+    SolverDev o_lane;  // per-lane copy, only live in the SOLVAR instantiations
+    if constexpr (SOLVAR) o_lane = o_in;
+    const SolverDev& o = SOLVAR ? o_lane : o_in;
     const int n = S.n_dim;
     const int n_ch = F.n_ch;
     const int nb = F.kl_bins;
@@ -426,6 +431,17 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o, const FeatDev& F, co
             } else {
                 for (int q = 0; q < MCBB_N_SCALARS; q++) sc[q] = S.scalars[q];
                 for (int p = 0; p < S.n_par; p++) sc[S.par_slot[p]] = io.par[(long long)p * io.n_mc + run];
+                if constexpr (SOLVAR) {
+                    const double v = io.solver_par[run];
+                    switch (io.solver_field) {
+                    case MCBB_SOLVER_ABSTOL: o_lane.abstol = v; break;
+                    case MCBB_SOLVER_RELTOL: o_lane.reltol = v; break;
+                    case MCBB_SOLVER_DT: o_lane.dt_user = v; break;
+                    case MCBB_SOLVER_DTMAX: o_lane.dtmax = v; break;
+                    case MCBB_SOLVER_DTMIN: o_lane.dtmin = v; break;
+                    default: break;
+                    }
+                }
                 pass = 0;
                 start_pass();
             }

@@ -18,7 +18,7 @@ struct LaneLayout {  // byte offsets into dynamic shared memory
     int n_slots, n_acc;
 };
 
-template <int SYS>
+template <int SYS, bool SOLVAR>
 __global__ void __launch_bounds__(128) k_solve_lane(const SysDev S, const SolverDev o, const FeatDev F,
                                                     const SolveIO io, const LaneLayout lay) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -50,13 +50,13 @@ __global__ void __launch_bounds__(128) k_solve_lane(const SysDev S, const Solver
     unsigned short* bins = (unsigned short*)(smem + lay.off_bins) + tid;
     double* como = (double*)(smem + lay.off_como) + tid;
     DevWorkQ wq{io.work_counter};
-    lane_main<SYS>(S, o, F, io, L, st, acc, bins, como, bs, wq);
+    lane_main<SYS, DevWorkQ, SOLVAR>(S, o, F, io, L, st, acc, bins, como, bs, wq);
 }
 
 // Large systems (state does not fit shared memory, no batched kernel for the system): same lane state machine,
 // per-lane state vectors in an L2/HBM-resident scratch laid out [slot][dim][lane] (coalesced across lanes).
 // Correct for any size; throughput is bounded by L2/HBM traffic of the stage vectors, not by the FP64 pipe.
-template <int SYS>
+template <int SYS, bool SOLVAR>
 __global__ void __launch_bounds__(128) k_solve_lane_gmem(const SysDev S, const SolverDev o, const FeatDev F,
                                                          const SolveIO io, double* state, double* accs,
                                                          unsigned short* bins_g, double* como_g) {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_solve_lane_gmem(const SysDev S, const S
     const int lanes = gridDim.x * blockDim.x;
     const int lane = blockIdx.x * blockDim.x + tid;
     DevWorkQ wq{io.work_counter};
-    lane_main<SYS>(S, o, F, io, L, state + lane, accs + lane, bins_g + lane, como_g + lane, lanes, wq);
+    lane_main<SYS, DevWorkQ, SOLVAR>(S, o, F, io, L, state + lane, accs + lane, bins_g + lane, como_g + lane, lanes, wq);
 }
 
 SolverDev resolve_solver(const mcbb_solver_opts* o) {
@@ -217,8 +217,8 @@ int resolve_feat(const mcbb_system_desc* sys, const mcbb_feat_opts* f, FeatDev* 
     return 0;
 }
 
-template <int SYS>
-static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io, cudaStream_t st) {
+template <int SYS, bool SOLVAR>
+static int launch_lane_impl(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io, cudaStream_t st) {
     const int n = S.n_dim;
     LaneLayout lay = {};
     lay.n_slots = 9 + n_scratch_for(SYS);
@@ -259,9 +259,9 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
         double* como_g = (double*)scratch_get(29, sizeof(double) * (size_t)(n_pairs > 0 ? n_pairs : 1) * lanes);
         if (!state || !accs || !bins_g || !como_g) MCBB_FAIL("solve: device allocation of the lane state failed");
         const size_t smem_g = sizeof(double) * (size_t)io.n_t + 16;
-        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_lane_gmem<SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_lane_gmem<SYS, SOLVAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-        k_solve_lane_gmem<SYS><<<grid, block, smem_g, st>>>(S, o, F, io, state, accs, bins_g, como_g);
+        k_solve_lane_gmem<SYS, SOLVAR><<<grid, block, smem_g, st>>>(S, o, F, io, state, accs, bins_g, como_g);
         MCBB_LAUNCHED();
         return 0;
     }
@@ -283,18 +283,23 @@ static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, co
     lay.off_bins = (int)off;
     off += F.need_kl ? sizeof(unsigned short) * (size_t)F.n_ch * F.kl_bins * bs : 0;
     const size_t smem = off;
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_lane<SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_lane<SYS, SOLVAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, per_sm = 1;
     MCBB_CUDA_OK(cudaGetDevice(&dev));
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MCBB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lane<SYS>, bs, smem));
+    MCBB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_lane<SYS, SOLVAR>, bs, smem));
     if (per_sm < 1) per_sm = 1;
     long long want = (io.n_mc + bs - 1) / bs;
     long long grid = std::min<long long>(want, (long long)sms * per_sm);  // persistent CTAs, dynamic queue
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-    k_solve_lane<SYS><<<(unsigned)grid, bs, smem, st>>>(S, o, F, io, lay);
+    k_solve_lane<SYS, SOLVAR><<<(unsigned)grid, bs, smem, st>>>(S, o, F, io, lay);
     MCBB_LAUNCHED();
     return 0;
+}
+
+template <int SYS>
+static int launch_lane(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io, cudaStream_t st) {
+    return io.solver_par ? launch_lane_impl<SYS, true>(S, o, F, io, st) : launch_lane_impl<SYS, false>(S, o, F, io, st);
 }
 
 int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
@@ -311,12 +316,17 @@ int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const Sol
         MCBB_FAIL("FunctionMap stepping is only defined for the map systems (logistic)");
     if (o.alg != MCBB_ALG_FUNCTIONMAP && S.system == MCBB_SYS_LOGISTIC)
         MCBB_FAIL("logistic is a map: use MCBB_ALG_FUNCTIONMAP");
-    if (o.alg == MCBB_ALG_RK4 && !(o.dt_user > 0)) MCBB_FAIL("RK4 is fixed-step: opts.dt must be > 0");
+    if (o.alg == MCBB_ALG_RK4 && !(o.dt_user > 0) && !(io.solver_par && io.solver_field == MCBB_SOLVER_DT))
+        MCBB_FAIL("RK4 is fixed-step: opts.dt must be > 0");
     if (o.alg < 0 || o.alg > 2) MCBB_FAIL("unknown algorithm id");
     if (!(o.t1 > o.t0)) MCBB_FAIL("tspan must be increasing");
     if (io.n_t < 2) MCBB_FAIL("need at least two save times (the first saved sample is dropped)");
     bool handled = false;
-    if (!io.saved) {  // the batched kernels keep no per-sample state to export: sample export runs the lane kernels
+    if (io.solver_par && (io.solver_field < MCBB_SOLVER_ABSTOL || io.solver_field > MCBB_SOLVER_DTMIN))
+        MCBB_FAIL("unknown solver option id for the per-run solver parameter");
+    // the batched kernels keep no per-sample state to export and take their solver options per launch: sample export
+    // and per-run solver options run the lane kernels
+    if (!io.saved && !io.solver_par) {
         if (int rc = launch_batched_umma(hs, S, o, F, io, st, &handled)) return rc;  // tcgen05 + tensor memory
         if (handled) return 0;
         if (int rc = launch_batched_imma(hs, S, o, F, io, st, &handled)) return rc;

@@ -19,8 +19,8 @@ struct HostWorkQ {
     bool all_done(bool f) { return f; }
 };
 
-template <int SYS>
-static void run_host(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io) {
+template <int SYS, bool SOLVAR>
+static void run_host_impl(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io) {
     const int n = S.n_dim;
     std::vector<double> st((size_t)(9 + SysTraits<SYS>::n_scratch) * n + 8), acc((size_t)ACC_SLOTS_CORR * F.n_ch + 8);
     std::vector<double> como((size_t)F.n_ch * F.n_ch + 8);
@@ -29,13 +29,22 @@ static void run_host(const SysDev& S, const SolverDev& o, const FeatDev& F, cons
     L.t_save = io.t_save;
     L.tabs = SysTabs{S.mat_a, S.mat_b, S.vec_a, S.vec_b, S.vec_c};
     HostWorkQ wq;
-    lane_main<SYS>(S, o, F, io, L, st.data(), acc.data(), bins.data(), como.data(), 1, wq);
+    lane_main<SYS, HostWorkQ, SOLVAR>(S, o, F, io, L, st.data(), acc.data(), bins.data(), como.data(), 1, wq);
+}
+
+template <int SYS>
+static void run_host(const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io) {
+    if (io.solver_par)
+        run_host_impl<SYS, true>(S, o, F, io);
+    else
+        run_host_impl<SYS, false>(S, o, F, io);
 }
 
 extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
                                    int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
                                    double* feat_out, double* global_out, int32_t* retcode_out, int64_t* nsteps_out,
-                                   double* matrix_out, int32_t save_mode, double* saved_out) {
+                                   double* matrix_out, int32_t save_mode, double* saved_out, int32_t solver_field,
+                                   const double* solver_vals) {
     int len[5];
     if (table_lengths(sys, len)) return 1;
     SysDev S = {};
@@ -67,6 +76,8 @@ extern "C" int emul_solve_features(const mcbb_system_desc* sys, const mcbb_solve
     io.glob = global_out; io.matrix = matrix_out; io.retcode = retcode_out; io.nsteps = (long long*)nsteps_out; io.ckpt = ckpt.data();
     io.saved = save_mode ? saved_out : nullptr;
     io.save_mode = save_mode;
+    io.solver_par = solver_field ? solver_vals : nullptr;
+    io.solver_field = solver_field;
     switch (S.system) {
     case MCBB_SYS_LOGISTIC: run_host<MCBB_SYS_LOGISTIC>(S, o, F, io); break;
     case MCBB_SYS_KURAMOTO: run_host<MCBB_SYS_KURAMOTO>(S, o, F, io); break;

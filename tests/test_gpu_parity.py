@@ -566,6 +566,46 @@ def test_continuation_response_analysis(gpu, orc):
     assert D.data.shape == (prob.N_mc, prob.N_mc) and np.isfinite(D.data).all()
 
 
+def test_solver_parameter_var(gpu, orc):
+    """test/solver_parametervar.jl: Kuramoto network N=20, `SolverParameterVar(:reltol, ()->rand(Uniform(1e-6,1e-3)))`,
+    random ICs, default eval_ode_run — every run equals the oracle solved alone with that run's reltol.  Also a
+    per-run fixed step (RK4 dt) and that the request is one-shot (the next plain solve is unaffected)."""
+    m = gpu
+    rng, vgen = np.random.default_rng(51), np.random.default_rng(52)
+    N = 20
+    pars = m.kuramoto_network_parameters(0.5, rng.normal(0.5, 0.005, N), N, np.ones((N, N)))
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), (0.0, 40.0), pars)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 100, pars,
+                           m.SolverParameterVar("reltol", lambda: vgen.uniform(1e-6, 1e-3)), m.eval_ode_run, 0.9)
+    sol = m.solve(prob, m.Tsit5())
+    assert np.all(np.diff(prob.par[:, 0]) >= 0) and np.all(sol.retcode == 0)  # sorted by the solver option
+    psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    tol_ok = 0
+    for i in range(0, prob.N_mc, 7):
+        oi = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan, reltol=float(prob.par[i, 0]))
+        ref = orc.solve_features(psys, oi, pfeat, prob.ic[i:i + 1], prob.par[i:i + 1], ts)
+        assert np.array_equal(sol.nsteps[i], ref["nsteps"][0]), i
+        tol_ok += np.allclose(sol.feat[i, :, :2], ref["feat"][0, :, :2], rtol=1e-6, atol=1e-7)
+    assert tol_ok >= 13  # 15 runs checked; K = 0.5 is incoherent, a run may amplify rounding differences
+    assert len(set(sol.nsteps[:, 0].tolist())) > 10  # tighter reltol -> more steps
+    assert sol.nsteps[:10, 0].mean() > sol.nsteps[-10:, 0].mean()
+    # one-shot: a plain parameter sweep right after is untouched by the previous request
+    prob2, _ = cases.c1_problem(m, n_ics=8, seed=3)
+    ic0, par0 = prob2.ic.copy(), prob2.par.copy()
+    ref2, _ = _oracle_ref(m, orc, prob2, ic0, par0)
+    assert np.array_equal(m.solve(prob2).nsteps, ref2["nsteps"])
+    # per-run fixed step
+    prob3 = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 5, pars,
+                            m.SolverParameterVar("dt", [0.01, 0.02, 0.04]), m.EvalOdeRun(eval_funcs=(m.mean, m.std)), 0.9)
+    with pytest.raises(m.MCBBError):
+        m.solve(prob3, m.RK4(), dt=0.03)  # both varied and given
+    sol3 = m.solve(prob3, m.RK4())
+    assert np.all(sol3.retcode == 0) and sol3.feat.shape == (15, N, 2)
+    want = np.rint(40.0 / prob3.par[:, 0]).astype(np.int64)  # fixed steps of the run's own dt
+    assert np.all(np.abs(sol3.nsteps[:, 0] - want) <= 1), (sol3.nsteps[:, 0], want)
+
+
 def test_k_dist_and_knn_helpers(gpu):
     """k_dist / KNN_dist / KNN_dist_relative (eval_clustering.jl:1504-1553) against numpy on the same matrix."""
     m = gpu

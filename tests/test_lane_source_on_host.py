@@ -34,9 +34,9 @@ def emul(mcbb):
     dp = abi.c_double_p
     L.emul_solve_features.argtypes = [C.POINTER(abi.SystemDesc), C.POINTER(abi.SolverOpts), C.POINTER(abi.FeatOpts),
                                       C.c_int64, dp, dp, dp, C.c_int32, dp, dp, abi.c_int32_p, abi.c_int64_p, dp,
-                                      C.c_int32, dp]
+                                      C.c_int32, dp, C.c_int32, dp]
 
-    def solve(psys, opts, pfeat, ic, par, t_save, save_mode=0):
+    def solve(psys, opts, pfeat, ic, par, t_save, save_mode=0, solver_var=None):
         ic = np.asfortranarray(ic, dtype=np.float64)
         par = np.asfortranarray(np.asarray(par, dtype=np.float64).reshape(ic.shape[0], -1))
         t_save = np.ascontiguousarray(t_save, dtype=np.float64)
@@ -51,11 +51,15 @@ def emul(mcbb):
             saved = np.full((n_mc, len(t_save), psys.n_dim), np.nan)
         elif save_mode == abi.SAVE_LAST:
             saved = np.full((n_mc, psys.n_dim), np.nan, order="F")
+        field, vals = 0, None
+        if solver_var is not None:
+            field, vals = abi.SOLVER_FIELDS[solver_var[0]], np.ascontiguousarray(solver_var[1], dtype=np.float64)
         rc = L.emul_solve_features(C.byref(psys.desc), C.byref(opts), C.byref(pfeat.opts), n_mc, ic.ctypes.data_as(dp),
                                    par.ctypes.data_as(dp), t_save.ctypes.data_as(dp), len(t_save),
                                    feat.ctypes.data_as(dp), glob.ctypes.data_as(dp), ret.ctypes.data_as(abi.c_int32_p),
                                    ns.ctypes.data_as(abi.c_int64_p), mat.ctypes.data_as(dp), int(save_mode),
-                                   saved.ctypes.data_as(dp) if saved is not None else dp())
+                                   saved.ctypes.data_as(dp) if saved is not None else dp(), field,
+                                   vals.ctypes.data_as(dp) if vals is not None else dp())
         assert rc == 0
         if save_mode == abi.SAVE_ALL:
             saved = np.transpose(saved, (0, 2, 1))
@@ -137,3 +141,41 @@ def test_lane_source_correlation_measures_real_and_complex(mcbb, orc, emul):
         assert np.allclose(got["matrix"], ref["matrix"], rtol=0, atol=1e-15)
         if filt is None:
             assert np.all(got["matrix"].sum(axis=1) == 56) and (got["matrix"][:, :-1].sum(axis=1) > 0).all()
+
+
+def test_lane_source_per_run_solver_options(mcbb, orc, emul):
+    """SolverParameterVar (src/solver_parametervar.jl; test/solver_parametervar.jl varies :reltol per run): every run
+    equals the oracle solved alone with that run's option."""
+    m = mcbb
+    rng = np.random.default_rng(7)
+    w = rng.normal(0.5, 0.005, 6)
+    pars = m.kuramoto_network_parameters(0.5, w, 6, np.ones((6, 6)))
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(6), (0.0, 40.0), pars)
+    vgen = np.random.default_rng(8)
+    for name, gen, kw in (("reltol", lambda: vgen.uniform(1e-6, 1e-3), {}),
+                          ("abstol", lambda: 10.0 ** vgen.uniform(-9, -4), {}),
+                          ("dtmax", lambda: vgen.uniform(0.05, 0.5), {}),
+                          ("dt", [0.01, 0.02, 0.05], dict(alg=m.RK4()))):
+        prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 4, pars, m.SolverParameterVar(name, gen),
+                               m.EvalOdeRun(eval_funcs=(m.mean, m.std)), 0.9)
+        assert prob.par_names == [] and prob.solver_par == name and prob.par.shape == (prob.N_mc, 1)
+        psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+        assert psys.desc.n_par == 0
+        alg = m.abi.ALG_RK4 if "alg" in kw else m.abi.ALG_TSIT5
+        base = {} if name == "dt" else {}
+        if name == "dt":
+            base = dict(dt=0.03)  # overridden per run
+        o = m.abi.solver_opts(alg, prob.p.tspan, **base)
+        ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+        got = emul(psys, o, pfeat, prob.ic, prob.par, ts, solver_var=(name, prob.par[:, 0]))
+        steps = set()
+        for i in range(prob.N_mc):
+            oi = m.abi.solver_opts(alg, prob.p.tspan, **{name: float(prob.par[i, 0])})
+            ref = orc.solve_features(psys, oi, pfeat, prob.ic[i:i + 1], prob.par[i:i + 1], ts)
+            assert got["retcode"][i] == ref["retcode"][0] == 0
+            assert np.array_equal(got["nsteps"][i], ref["nsteps"][0]), (name, i)
+            assert np.allclose(got["feat"][i], ref["feat"][0], rtol=1e-6, atol=1e-7), (name, i)
+            steps.add(int(ref["nsteps"][0, 0]))
+        assert len(steps) > 1  # the option really changed the integration
+    with pytest.raises(m.MCBBError):
+        m.SolverParameterVar("maxiters", [1, 2])
