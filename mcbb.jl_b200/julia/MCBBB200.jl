@@ -114,6 +114,7 @@ Base.@kwdef struct B200Eval
     correlation_hist::Bool = false     # matrix_eval_funcs = [correlation_hist] (30 bins, raw weights)
     global_sum::Bool = false           # global_eval_funcs = [(x)->sum(x)]
 end
+const SOLVER_FIELD = Dict(:abstol => Int32(1), :reltol => Int32(2), :dt => Int32(3), :dtmax => Int32(4), :dtmin => Int32(5))
 const MEAS_ID = Dict(:mean => MEAS_MEAN, :std => MEAS_STD, :kl_hist => MEAS_KL_HIST)
 
 """
@@ -126,7 +127,15 @@ measure vectors `eval_ode_run` would have produced, in the original run order.
 function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eval::B200Eval=B200Eval(),
                            alg::Int32=(prob.p.prob isa DiscreteProblem ? ALG_FUNCTIONMAP : ALG_TSIT5),
                            abstol=0.0, reltol=0.0, dt=0.0, maxiters=0)
-    names = [prob.par_var[i].name for i in 1:length(prob.par_var)]
+    # SolverParameterVar (src/solver_parametervar.jl): the parameter column is a per-run SOLVER option, the system
+    # parameters stay fixed -> no swept system parameter, and a one-shot request for the next solve of this thread
+    solver_var = prob.par_var isa MCBB.AbstractSolverParameterVar
+    names = solver_var ? Symbol[] : [prob.par_var[i].name for i in 1:length(prob.par_var)]
+    if solver_var
+        field = SOLVER_FIELD[prob.par_var.name]
+        vals = Vector{Float64}(prob.par[:, 1])
+        check(ccall((:mcbb_set_solver_parameter_var, LIB), Cint, (Int32, Ptr{Float64}, Int64), field, vals, length(vals)))
+    end
     desc, keep = system_desc(prob.p.prob.p, names)
     tspan = prob.p.prob.tspan
     opts = SolverOpts(alg, 0, tspan[1], tspan[2], abstol, reltol, dt, 0.0, 0.0, maxiters, 0, 0, 0, 0, 0, 0)
