@@ -131,11 +131,7 @@ function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eva
     # parameters stay fixed -> no swept system parameter, and a one-shot request for the next solve of this thread
     solver_var = prob.par_var isa MCBB.AbstractSolverParameterVar
     names = solver_var ? Symbol[] : [prob.par_var[i].name for i in 1:length(prob.par_var)]
-    if solver_var
-        field = SOLVER_FIELD[prob.par_var.name]
-        vals = Vector{Float64}(prob.par[:, 1])
-        check(ccall((:mcbb_set_solver_parameter_var, LIB), Cint, (Int32, Ptr{Float64}, Int64), field, vals, length(vals)))
-    end
+    solver_vals = solver_var ? Vector{Float64}(prob.par[:, 1]) : Float64[]   # the library keeps the POINTER until the solve
     desc, keep = system_desc(prob.p.prob.p, names)
     tspan = prob.p.prob.tspan
     opts = SolverOpts(alg, 0, tspan[1], tspan[2], abstol, reltol, dt, 0.0, 0.0, maxiters, 0, 0, 0, 0, 0, 0)
@@ -156,7 +152,9 @@ function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eva
     feat = Array{Float64}(undef, prob.N_mc, nf, nm)
     retcode = Vector{Int32}(undef, prob.N_mc)
     nsteps = Matrix{Int64}(undef, prob.N_mc, 2)
-    GC.@preserve keep filt ic par ts feat mat glob retcode nsteps begin
+    GC.@preserve keep filt ic par ts feat mat glob retcode nsteps solver_vals begin
+        solver_var && check(ccall((:mcbb_set_solver_parameter_var, LIB), Cint, (Int32, Ptr{Float64}, Int64),
+                                  SOLVER_FIELD[prob.par_var.name], solver_vals, length(solver_vals)))
         check(ccall((:mcbb_solve_features, LIB), Cint,
                     (Ref{SystemDesc}, Ref{SolverOpts}, Ref{FeatOpts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                      Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
