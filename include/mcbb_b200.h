@@ -250,6 +250,15 @@ int mcbb_dbscan_features_dev(const double* X_dev, int64_t n, int32_t n_groups, c
 int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double* kth_out, double* cum_out);
 int mcbb_knn_dist_dense_dev(const double* D_dev, int64_t n, int32_t k, int32_t K, double* kth_dev,
                             double* cum_dev, void* stream);
+/* The same from the feature matrix (layout of mcbb_distance_matrix), for ensembles whose D is never materialised:
+ * D is produced in blocks of `block_rows` rows (0 = about 2 GB per block), each block sorted per row and reduced.
+ * Exact — identical to the dense entry on the same features. */
+int mcbb_knn_dist_features(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                           const double* group_weight, int32_t k, int32_t K, int64_t block_rows, double* kth_out,
+                           double* cum_out);
+int mcbb_knn_dist_features_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, int32_t k, int32_t K, int64_t block_rows,
+                               double* kth_dev, double* cum_dev, void* stream);
 
 /* ---- sparse interchange ------------------------------------------------------------
  * Replace the NonzeroSparseMatrix branch of distance_matrix (src/eval_clustering.jl:541-550 builds it column by

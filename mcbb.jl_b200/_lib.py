@@ -15,6 +15,7 @@ EXPORTS = [
     "mcbb_version", "mcbb_init", "mcbb_finalize", "mcbb_last_error", "mcbb_device_info",
     "mcbb_kernel_launch_count", "mcbb_tsave_array", "mcbb_solve_features", "mcbb_solve_features_dev",
     "mcbb_solve_features_saved", "mcbb_solve_features_saved_dev", "mcbb_set_solver_parameter_var",
+    "mcbb_knn_dist_features", "mcbb_knn_dist_features_dev",
     "mcbb_distance_matrix", "mcbb_distance_matrix_dev", "mcbb_dbscan_dense", "mcbb_dbscan_dense_dev",
     "mcbb_dbscan_features", "mcbb_dbscan_features_dev", "mcbb_dbscan_rows_count_dev",
     "mcbb_dbscan_rows_union_dev", "mcbb_dbscan_merge_parents_dev", "mcbb_dbscan_rows_border_dev",
@@ -73,6 +74,9 @@ def lib():
     L.mcbb_measure_fp64_fma_peak.argtypes = [dp, dp]
     L.mcbb_knn_dist_dense.argtypes = [dp, C.c_int64, C.c_int32, C.c_int32, dp, dp]
     L.mcbb_knn_dist_dense_dev.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp]
+    L.mcbb_knn_dist_features.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_int32, C.c_int32, C.c_int64, dp, dp]
+    L.mcbb_knn_dist_features_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_int32, C.c_int32, C.c_int64, vp, vp,
+                                             vp]
     L.mcbb_distance_sparse_count.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_double, ip]
     L.mcbb_distance_sparse_count_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, vp, vp]
     L.mcbb_distance_sparse_fill.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_double, lp, ip, dp]

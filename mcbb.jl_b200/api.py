@@ -1122,7 +1122,16 @@ def cluster_membership(prob, clusters, window_size, window_offset, normalize=Tru
 # ------------------------------------------------------------------------------------------------------------
 # eps-selection helpers (src/eval_clustering.jl:1504-1553)
 # ------------------------------------------------------------------------------------------------------------
-def _knn(D, k, K):
+def _knn(D, k, K, block_rows=0):
+    if isinstance(D, B200FeatureMatrix):  # D is never materialised: row blocks from the features, sorted per row
+        n = D.X.shape[0]
+        kth, cum = np.zeros(n), np.zeros(n)
+        check(lib().mcbb_knn_dist_features(D.X.ctypes.data_as(abi.c_double_p), n, len(D.group_len),
+                                           D.group_len.ctypes.data_as(abi.c_int32_p),
+                                           D.group_weight.ctypes.data_as(abi.c_double_p), int(k), int(K),
+                                           int(block_rows), kth.ctypes.data_as(abi.c_double_p),
+                                           cum.ctypes.data_as(abi.c_double_p)))
+        return kth, cum
     data = D.data if isinstance(D, (DistanceMatrix, DistanceMatrixHist)) else D
     data = np.asfortranarray(data, dtype=np.float64)
     n = data.shape[0]
@@ -1149,5 +1158,8 @@ def KNN_dist(D, K):
 
 def KNN_dist_relative(D, rel_K=0.005):
     """KNN_dist_relative(D, rel_K): K = round(N * rel_K) (:1526-1530)."""
-    n = (D.data if isinstance(D, DistanceMatrix) else np.asarray(D)).shape[0]
+    if isinstance(D, B200FeatureMatrix):
+        n = D.X.shape[0]
+    else:
+        n = (D.data if isinstance(D, (DistanceMatrix, DistanceMatrixHist)) else np.asarray(D)).shape[0]
     return KNN_dist(D, int(round(n * rel_K)))

@@ -87,6 +87,9 @@ int labels_dev(const int* root_label, long long n, long long* assignments, long 
 int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
                        cudaStream_t st);
 int knn_dist_dense_dev(const double* D, long long n, int k, int K, double* kth, double* cum, cudaStream_t st);
+int knn_dist_features_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                          const double* group_weight, int k, int K, long long block_rows, double* kth, double* cum,
+                          cudaStream_t st);
 int distance_rows_dev(const double* X, long long n, int n_groups, const int32_t* group_len, const double* group_weight,
                       long long row0, long long row1, double* out, cudaStream_t st);
 int distance_sparse_count_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
@@ -660,6 +663,36 @@ int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double
     cudaStream_t st = 0;
     MCBB_CUDA_OK(cudaMemcpyAsync(d_D, D, sizeof(double) * (size_t)n * (size_t)n, cudaMemcpyHostToDevice, st));
     if (int rc = knn_dist_dense_dev(d_D, n, k, K, kth_out ? d_k : nullptr, cum_out ? d_c : nullptr, st)) return rc;
+    if (kth_out) MCBB_CUDA_OK(cudaMemcpyAsync(kth_out, d_k, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (cum_out) MCBB_CUDA_OK(cudaMemcpyAsync(cum_out, d_c, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_knn_dist_features_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, int32_t k, int32_t K, int64_t block_rows, double* kth_dev,
+                               double* cum_dev, void* stream) {
+    if (!X_dev || !group_len || !group_weight || (!kth_dev && !cum_dev)) MCBB_FAIL("k_dist: NULL argument");
+    if (n_groups < 1) MCBB_FAIL("k_dist: empty input");
+    return knn_dist_features_dev(X_dev, n, n_groups, group_len, group_weight, k, K, block_rows, kth_dev, cum_dev,
+                                 (cudaStream_t)stream);
+}
+int mcbb_knn_dist_features(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                           const double* group_weight, int32_t k, int32_t K, int64_t block_rows, double* kth_out,
+                           double* cum_out) {
+    if (!X || !group_len || !group_weight || (!kth_out && !cum_out)) MCBB_FAIL("k_dist: NULL argument");
+    if (n < 1 || n_groups < 1) MCBB_FAIL("k_dist: empty input");
+    size_t F = 0;
+    for (int g = 0; g < n_groups; g++) F += group_len[g] > 0 ? group_len[g] : 0;
+    double* d_X = (double*)scratch_get(40, sizeof(double) * F * (size_t)n);
+    double* d_k = (double*)scratch_get(48, sizeof(double) * (size_t)n);
+    double* d_c = (double*)scratch_get(49, sizeof(double) * (size_t)n);
+    if (!d_X || !d_k || !d_c) MCBB_FAIL("k_dist: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_X, X, sizeof(double) * F * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (int rc = knn_dist_features_dev(d_X, n, n_groups, group_len, group_weight, k, K, block_rows,
+                                       kth_out ? d_k : nullptr, cum_out ? d_c : nullptr, st))
+        return rc;
     if (kth_out) MCBB_CUDA_OK(cudaMemcpyAsync(kth_out, d_k, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (cum_out) MCBB_CUDA_OK(cudaMemcpyAsync(cum_out, d_c, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));

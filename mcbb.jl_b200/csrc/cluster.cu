@@ -916,11 +916,16 @@ __global__ void k_row_offsets(long long* off, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) off[i] = i * n;
 }
+__global__ void k_row_offsets_ld(long long* off, long long m, long long ld) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= m) off[i] = i * ld;
+}
 // kth[i] = sorted_row_i[k-1];  cum[i] = sum of the K smallest entries of row i (the zero self-distance included,
 // exactly like `sort(D[i,:])[1:K]` in the reference)
-__global__ void k_knn_pick(const double* sorted, long long n, int k, int K, double* kth, double* cum) {
+__global__ void k_knn_pick(const double* sorted, long long n, int k, int K, double* kth, double* cum,
+                           long long n_rows = -1) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
+    if (i < (n_rows < 0 ? n : n_rows)) {
         const double* row = sorted + i * n;
         if (kth) kth[i] = row[k - 1];
         if (cum) {
@@ -949,6 +954,40 @@ int knn_dist_dense_dev(const double* D, long long n, int k, int K, double* kth, 
     g_launch_count.fetch_add(1);
     k_knn_pick<<<nblk(n), 256, 0, st>>>(sorted, n, k, K, kth, cum);
     MCBB_LAUNCHED();
+    return 0;
+}
+
+// The same from the FEATURES, for ensembles whose D does not fit (C3-C5): blocks of rows of D are produced by the
+// pair tiles (distance_rows_dev), sorted per row and reduced to (k-th, cumulative-K); only one block is ever resident.
+// block_rows = 0 picks a block of about 2 GB.
+int knn_dist_features_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
+                          const double* group_weight, int k, int K, long long block_rows, double* kth, double* cum,
+                          cudaStream_t st) {
+    if (n < 1) MCBB_FAIL("k_dist: empty input");
+    if ((kth && (k < 1 || k > n)) || (cum && (K < 1 || K > n))) MCBB_FAIL("k_dist: k out of range");
+    if (block_rows <= 0) block_rows = std::max<long long>(1, (1LL << 28) / n);
+    block_rows = std::min<long long>(block_rows, n);
+    if (block_rows * n >= (1LL << 31)) MCBB_FAIL("k_dist: block_rows * n must stay below 2^31");
+    double* blk = (double*)scratch_get(66, sizeof(double) * (size_t)n * (size_t)block_rows);
+    double* sorted = (double*)scratch_get(67, sizeof(double) * (size_t)n * (size_t)block_rows);
+    long long* off = (long long*)scratch_get(46, sizeof(long long) * (size_t)(block_rows + 1));
+    if (!blk || !sorted || !off) MCBB_FAIL("k_dist: device scratch allocation failed");
+    k_row_offsets_ld<<<nblk(block_rows + 1), 256, 0, st>>>(off, block_rows, n);
+    MCBB_LAUNCHED();
+    size_t tb = 0;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, tb, blk, sorted, (int)(n * block_rows), (int)block_rows, off, off + 1, st);
+    void* tmp = scratch_get(47, tb);
+    if (!tmp) MCBB_FAIL("k_dist: device scratch allocation failed");
+    for (long long r0 = 0; r0 < n; r0 += block_rows) {
+        const long long r1 = std::min(n, r0 + block_rows), m = r1 - r0;
+        // rows r0..r1 of D, each contiguous (column-major block of the symmetric matrix)
+        if (int rc = distance_rows_dev(X, n, n_groups, group_len, group_weight, r0, r1, blk, st)) return rc;
+        size_t tb2 = tb;
+        MCBB_CUDA_OK(cub::DeviceSegmentedSort::SortKeys(tmp, tb2, blk, sorted, (int)(n * m), (int)m, off, off + 1, st));
+        g_launch_count.fetch_add(1);
+        k_knn_pick<<<nblk(m), 256, 0, st>>>(sorted, n, k, K, kth ? kth + r0 : nullptr, cum ? cum + r0 : nullptr, m);
+        MCBB_LAUNCHED();
+    }
     return 0;
 }
 

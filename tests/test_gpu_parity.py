@@ -619,6 +619,21 @@ def test_k_dist_and_knn_helpers(gpu):
     assert np.allclose(m.KNN_dist_relative(D)[:, 0], Ds[:, :K].sum(1), rtol=1e-14)
     with pytest.raises(m.MCBBError, match="k out of range"):
         m.k_dist(D, 0)
+    # the same from the features, D never materialised: row blocks (ragged last block) sorted one block at a time
+    X = np.asfortranarray(np.concatenate([pts, rng.normal(size=(700, 2))], axis=1))
+    gl, gw = np.array([3, 1, 1], dtype=np.int32), np.array([1.0, 0.5, 2.0])
+    fm = m.B200FeatureMatrix(X, gl, gw, [1.0, 0.5, 2.0], False)
+    Dm = m.lib().mcbb_distance_matrix
+    Dd = np.zeros((700, 700), order="F")
+    m.check(Dm(X.ctypes.data_as(m.abi.c_double_p), 700, 3, gl.ctypes.data_as(m.abi.c_int32_p),
+               gw.ctypes.data_as(m.abi.c_double_p), Dd.ctypes.data_as(m.abi.c_double_p)))
+    assert np.array_equal(m.k_dist(fm, 4), m.k_dist(Dd, 4))
+    assert np.array_equal(m.KNN_dist(fm, 9), m.KNN_dist(Dd, 9))
+    assert np.array_equal(m.KNN_dist_relative(fm, 0.01), m.KNN_dist_relative(Dd, 0.01))
+    for br in (1, 64, 333, 700, 5000):
+        kth, cum = m.api._knn(fm, 5, 11, block_rows=br)
+        kd, cd = m.api._knn(Dd, 5, 11)
+        assert np.array_equal(kth, kd) and np.array_equal(cum, cd), br
 
 
 def test_failure_handling_repeat_and_inf(gpu):
