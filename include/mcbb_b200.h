@@ -184,7 +184,8 @@ enum mcbb_save_mode { MCBB_SAVE_NONE = 0, MCBB_SAVE_ALL = 1, MCBB_SAVE_LAST = 2 
  * (sys->n_par = 0, par = NULL), as in the reference, but a simultaneous system-parameter sweep is allowed.
  * Set with mcbb_set_solver_parameter_var before a solve_features* call of the SAME host thread; it applies to that one
  * call and is cleared by it.  solver_vals is a HOST array of n_mc values for the host entry points and a DEVICE array
- * for the *_dev ones.  Runs the lane kernels. */
+ * for the *_dev ones and must stay valid until that solve returns (the library keeps the pointer, not a copy).
+ * Runs the lane kernels. */
 enum mcbb_solver_field {
     MCBB_SOLVER_NONE = 0,
     MCBB_SOLVER_ABSTOL = 1,
