@@ -311,9 +311,35 @@ class SolverParameterVar:
         self.name, self.new_val = name, new_val
 
 
+class MultiDimParameterVar:
+    """MultiDimParameterVar(data) (setup_mc_prob.jl:176-236): several parameters varied simultaneously; `data` is a
+    list of `(name, range | generator)` tuples, all ranges or all generators.  The new-parameter function is
+    Parameters.reconstruct (the default, :233), i.e. the named fields are overwritten per run."""
+
+    def __init__(self, data):
+        data = [tuple(d[:2]) for d in data]
+        if len(data) < 1:
+            raise MCBBError("MultiDimParameterVar needs at least one parameter")
+        kinds = {callable(d[1]) for d in data}
+        if len(kinds) != 1:
+            raise MCBBError("MultiDimParameterVar: either all parameters are ranges or all are generators")
+        if len(data) > abi.MCBB_MAX_PAR:
+            raise MCBBError("at most %d parameters can be varied simultaneously" % abi.MCBB_MAX_PAR)
+        self.data = data
+        self.N = len(data)
+        self.is_func = kinds.pop()
+
+    def __len__(self):
+        return self.N
+
+    def __getitem__(self, i):
+        return self.data[i]
+
+
 class DEMCBBProblem:
     """DEMCBBProblem(p, ic_gens | ic_ranges, [N_ic,] pars, (name, range | generator), eval_ode_func, tail_frac)
     DEMCBBProblem(p, ic_gens | ic_ranges, [N_ic,] pars, SolverParameterVar(name, ...), eval_ode_func, tail_frac)
+    DEMCBBProblem(p, ic_gens | ic_ranges, [N_ic,] pars, MultiDimParameterVar([...]) | [(name, ...), ...], ...)
 
     * ic_ranges: list of arrays + parameter array      -> cartesian product, IC index fastest (:850-882)
     * ic generator(s), N_ic, parameter generator       -> N_ic random runs                     (:888-923)
@@ -340,6 +366,13 @@ class DEMCBBProblem:
             name, values = par_var.name, par_var.new_val
             self.solver_par = name
             self.par_names = []
+        elif isinstance(par_var, MultiDimParameterVar) or (isinstance(par_var, list) and len(par_var) > 0
+                                                          and isinstance(par_var[0], (tuple, list))):
+            mv = par_var if isinstance(par_var, MultiDimParameterVar) else MultiDimParameterVar(par_var)
+            self.par_names = [d[0] for d in mv.data]
+            self.par_var = mv
+            self._init_multidim(p, ic, N_ic, pars, mv)
+            return
         else:
             name, values = par_var[0], par_var[1]
             self.par_names = [name]
@@ -366,6 +399,41 @@ class DEMCBBProblem:
             cols = [g.reshape(-1, order="F") for g in grids]
             self.ic = np.stack(cols[:-1], axis=1)
             self.par = cols[-1][:, None].astype(np.float64)
+        self.ic = np.asfortranarray(self.ic)
+        self.par = np.asfortranarray(self.par)
+        self.N_mc = self.ic.shape[0]
+        if self.N_mc == 0:
+            raise MCBBError("Zero inital conditions. Either at least one of the ranges has length 0 or an "
+                            "overflow occured")
+
+    def _init_multidim(self, p, ic, N_ic, pars, mv):
+        """_ic_par_matrix for several varied parameters (setup_mc_prob.jl:850-969)."""
+        n_dim = pars.n_dim() if not np.iscomplexobj(p.u0) else len(p.u0)
+        self.ic_gens = None
+        if callable(ic) or (isinstance(ic, (list, tuple)) and len(ic) > 0 and callable(ic[0])):
+            gens = [ic] if callable(ic) else list(ic)
+            self.ic_gens = gens
+            if N_ic is None:
+                raise MCBBError("random initial conditions need N_ic")
+            if not mv.is_func:
+                if mv.N > 1:  # :931-933
+                    raise MCBBError("Random IC and Parameter with Ranges is so far only supported for N_par=1")
+                ics = self._draw_ics(gens, N_ic, n_dim)
+                vals = np.asarray(list(mv[0][1]), dtype=np.float64)
+                self.ic = np.tile(ics, (len(vals), 1))
+                self.par = np.repeat(vals, N_ic)[:, None]
+            else:  # random x random, :888-923
+                self.ic = self._draw_ics(gens, N_ic, n_dim)
+                self.par = np.array([[d[1]() for d in mv.data] for _ in range(N_ic)], dtype=np.float64)
+        else:  # ranges x ranges: cartesian product, IC dimensions first, first index fastest (:850-882)
+            if mv.is_func:
+                raise MCBBError("initial condition ranges need parameter ranges, not generators")
+            ranges = [np.asarray(list(r)) for r in ic]
+            pvals = [np.asarray(list(d[1]), dtype=np.float64) for d in mv.data]
+            grids = np.meshgrid(*ranges, *pvals, indexing="ij")
+            cols = [g.reshape(-1, order="F") for g in grids]
+            self.ic = np.stack(cols[:len(ranges)], axis=1)
+            self.par = np.stack(cols[len(ranges):], axis=1).astype(np.float64)
         self.ic = np.asfortranarray(self.ic)
         self.par = np.asfortranarray(self.par)
         self.N_mc = self.ic.shape[0]
@@ -1094,10 +1162,53 @@ class ClusterMembershipResult:
         self.par, self.data, self.multidim_flag = par, data, multidim_flag
 
 
+def _cluster_membership_multidim(prob, clusters, window_size, window_offset, normalize, min_members):
+    """cluster_membership for several varied parameters (eval_clustering.jl:1206-1265): a window is the open box
+    prod_p (ip_p, ip_p + window_size_p); `data` is [N_windows_1, ..., N_windows_P, N_cluster], `par` the mesh of the
+    window minima [N_windows_1, ..., N_windows_P, P]."""
+    n_par = prob.par.shape[1]
+    window_size, window_offset = np.atleast_1d(window_size).astype(float), np.atleast_1d(window_offset).astype(float)
+    if len(window_size) != n_par or len(window_offset) != n_par:
+        raise MCBBError("Window Size and Window Offset need to have as many elements as they are parameters")
+    ca = np.asarray(clusters.assignments)
+    n_cluster = len(clusters.seeds) + 1
+    mins = []
+    for p in range(n_par):
+        col = prob.par[:, p]
+        mins.append(_julia_range(col.min(), window_offset[p], col.max() - window_size[p]))
+        if len(mins[p]) <= 1:
+            import warnings
+            warnings.warn("Only 1 or less Windows in cluster_membership")
+    shape = [len(m) for m in mins]
+    data = np.zeros(shape + [n_cluster])
+    mesh = np.zeros(shape + [n_par])
+    for idx in np.ndindex(*shape):
+        ind = np.ones(prob.N_mc, dtype=bool)
+        for p in range(n_par):
+            lo = mins[p][idx[p]]
+            ind &= (prob.par[:, p] > lo) & (prob.par[:, p] < lo + window_size[p])
+            mesh[idx + (p,)] = lo
+        cnt = np.bincount(ca[ind], minlength=n_cluster).astype(float)
+        if normalize:
+            with np.errstate(invalid="ignore", divide="ignore"):
+                cnt = cnt / np.count_nonzero(ind)
+        data[idx] = cnt
+    if min_members > 0:
+        keep = [0] if cluster_n_noise(clusters) > min_members else []
+        keep += [i + 1 for i in range(n_cluster - 1) if clusters.counts[i] > min_members]
+        data = data[..., keep]
+    return ClusterMembershipResult(mesh, data, True)
+
+
 def cluster_membership(prob, clusters, window_size, window_offset, normalize=True, min_members=0):
-    """Sliding-window cluster membership, one swept parameter (eval_clustering.jl:1206-1265)."""
+    """Sliding-window cluster membership (eval_clustering.jl:1206-1265); arrays of window sizes / offsets for several
+    varied parameters."""
     if prob.par.shape[1] != 1:
-        raise MCBBError("cluster_membership: only one swept parameter is supported by this mirror")
+        return _cluster_membership_multidim(prob, clusters, window_size, window_offset, normalize, min_members)
+    if np.ndim(window_size) > 0 or np.ndim(window_offset) > 0:
+        if np.size(window_size) != 1 or np.size(window_offset) != 1:
+            raise MCBBError("Window Size and Window Offset need to have as many elements as they are parameters")
+        window_size, window_offset = float(np.ravel(window_size)[0]), float(np.ravel(window_offset)[0])
     ca = np.asarray(clusters.assignments)
     n_cluster = len(clusters.seeds) + 1
     par = prob.par[:, 0]

@@ -606,6 +606,37 @@ def test_solver_parameter_var(gpu, orc):
     assert np.all(np.abs(sol3.nsteps[:, 0] - want) <= 1), (sol3.nsteps[:, 0], want)
 
 
+def test_two_swept_parameters_end_to_end(gpu, orc):
+    """MultiDimParameterVar (setup_mc_prob.jl:176-236): coupling AND damping of the power grid drawn per run; solve,
+    distance matrix with one weight per parameter, DBSCAN and the two-parameter cluster_membership."""
+    m = gpu
+    N = 6
+    rng = np.random.default_rng(9)
+    E = cases.ring_incidence(N, [(0, 3)])
+    pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, np.array([1.0, -1.0] * (N // 2)))
+    rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), (0.0, 60.0), pars)
+    ev = m.EvalOdeRun(state_filter=list(range(N + 1, 2 * N + 1)), eval_funcs=(m.mean, m.std))
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 300, pars,
+                           [("coupling", lambda: rng.uniform(0.5, 4.0)), ("damping", lambda: rng.uniform(0.05, 0.5))],
+                           ev, 0.5)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    kw = dict(reltol=1e-8, abstol=1e-8)
+    sol = m.solve(prob, **kw)
+    assert np.all(np.diff(prob.par[:, 0]) >= 0)  # sorted by the FIRST parameter, setup_mc_prob.jl:520-536
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
+    assert ctx[0].desc.n_par == 2 and np.array_equal(sol.nsteps, ref["nsteps"])
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.5)
+    weights = [1.0, 0.5, 1.0, 2.0]
+    D = m.distance_matrix(sol, prob, weights)
+    X, gl, gw = m.feature_groups(sol, prob, weights)
+    assert list(gl) == [N, N, 1, 1] and np.allclose(D.data, orc.distance_matrix(X, gl, gw), rtol=1e-12, atol=1e-13)
+    db = m.dbscan(D, float(np.median(m.k_dist(D, 4))), 4)
+    cm = m.cluster_membership(prob, db, [1.0, 0.15], [0.5, 0.075])
+    assert cm.multidim_flag and cm.data.shape[2] == len(db.seeds) + 1
+    filled = ~np.isnan(cm.data[..., 0])
+    assert filled.any() and np.allclose(cm.data[filled].sum(axis=-1), 1.0)
+
+
 def test_k_dist_and_knn_helpers(gpu):
     """k_dist / KNN_dist / KNN_dist_relative (eval_clustering.jl:1504-1553) against numpy on the same matrix."""
     m = gpu

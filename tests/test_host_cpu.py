@@ -427,3 +427,56 @@ def test_fixed_point_coupling_sum_identities():
         assert abs(Fraction(got) - want) <= Fraction(abs(exact), 2 ** 50) * Fraction(1, 2 ** 53) + 0
         # and the fixed-point terms are within 2^-51 of the true values
         assert np.max(np.abs(np.array([float(Fraction(int(ui) - 2 ** 51, 2 ** 50)) for ui in u]) - x)) <= 2.0 ** -51
+
+
+def test_multidim_parameter_var_problem_and_cluster_membership(mcbb):
+    """MultiDimParameterVar (setup_mc_prob.jl:176-236, 850-969) and the multi-parameter cluster_membership
+    (eval_clustering.jl:1206-1265) against literal loops."""
+    m = mcbb
+    N = 4
+    E = np.zeros((N, N))
+    for e in range(N):
+        E[e, e], E[(e + 1) % N, e] = -1.0, 1.0
+    pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, np.array([1.0, -1.0, 1.0, -1.0]))
+    rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), (0.0, 10.0), pars)
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std))
+    # ranges x ranges: cartesian product, IC dimensions first, first index fastest
+    ic_ranges = [[0.0, 1.0]] + [[0.5]] * (2 * N - 1)
+    prob = m.DEMCBBProblem(rp, ic_ranges, pars, [("coupling", [1.0, 2.0, 3.0]), ("damping", [0.1, 0.2])], ev, 0.5)
+    assert prob.N_mc == 12 and prob.par.shape == (12, 2) and prob.par_names == ["coupling", "damping"]
+    assert prob.ic[:, 0].tolist() == [0.0, 1.0] * 6
+    assert prob.par[:, 0].tolist() == [1.0, 1.0, 2.0, 2.0, 3.0, 3.0] * 2
+    assert prob.par[:, 1].tolist() == [0.1] * 6 + [0.2] * 6
+    psys = prob.pars.pack(prob.par_names)
+    assert psys.desc.n_par == 2 and list(psys.desc.par_slot)[:2] == [1, 0]
+    # generators x generators
+    rng = np.random.default_rng(0)
+    mv = m.MultiDimParameterVar([("coupling", lambda: rng.uniform(0, 4)), ("damping", lambda: rng.uniform(0, 1))])
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-1, 1), 500, pars, mv, ev, 0.5)
+    assert prob.par.shape == (500, 2) and len(mv) == 2 and mv[1][0] == "damping"
+    assert prob.par[:, 0].max() > 3 and prob.par[:, 1].max() <= 1
+    with pytest.raises(m.MCBBError, match="only supported for N_par=1"):
+        m.DEMCBBProblem(rp, lambda: 0.0, 5, pars, [("coupling", [1.0, 2.0]), ("damping", [0.1])], ev, 0.5)
+    with pytest.raises(m.MCBBError):
+        m.MultiDimParameterVar([("coupling", [1.0]), ("damping", lambda: 0.1)])
+    # sliding windows in two parameters
+    ca = rng.integers(0, 4, size=500)
+    counts = np.bincount(ca, minlength=4)[1:]
+    db = m.DbscanResult(np.arange(3), ca, counts)
+    ws, wo = [1.0, 0.25], [0.5, 0.125]
+    cm = m.cluster_membership(prob, db, ws, wo)
+    assert cm.multidim_flag and cm.data.ndim == 3 and cm.data.shape[2] == 4 and cm.par.shape == cm.data.shape[:2] + (2,)
+    p1, p2 = prob.par[:, 0], prob.par[:, 1]
+    n1 = len(np.arange(p1.min(), p1.max() - ws[0] + 1e-12, wo[0]))
+    assert abs(cm.data.shape[0] - n1) <= 1
+    for i in range(cm.data.shape[0]):
+        for j in range(cm.data.shape[1]):
+            lo1, lo2 = cm.par[i, j]
+            ind = (p1 > lo1) & (p1 < lo1 + ws[0]) & (p2 > lo2) & (p2 < lo2 + ws[1])
+            want = np.bincount(ca[ind], minlength=4) / max(1, ind.sum())
+            if ind.sum() > 0:
+                assert np.allclose(cm.data[i, j], want)
+    raw = m.cluster_membership(prob, db, ws, wo, normalize=False, min_members=int(counts.min()))
+    assert raw.data.shape[2] == 1 + (counts > counts.min()).sum() - (0 if (ca == 0).sum() > counts.min() else 1)
+    with pytest.raises(m.MCBBError, match="as many elements"):
+        m.cluster_membership(prob, db, 1.0, 0.5)

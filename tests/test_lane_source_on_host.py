@@ -179,3 +179,26 @@ def test_lane_source_per_run_solver_options(mcbb, orc, emul):
         assert len(steps) > 1  # the option really changed the integration
     with pytest.raises(m.MCBBError):
         m.SolverParameterVar("maxiters", [1, 2])
+
+
+def test_lane_source_two_swept_parameters(mcbb, orc, emul):
+    """MultiDimParameterVar: two system parameters (coupling, damping of the power grid) overridden per run."""
+    m = mcbb
+    N = 6
+    rng = np.random.default_rng(9)
+    E = cases.ring_incidence(N, [(0, 3)])
+    pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, np.array([1.0, -1.0] * (N // 2)))
+    rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), (0.0, 60.0), pars)
+    ev = m.EvalOdeRun(state_filter=list(range(N + 1, 2 * N + 1)), eval_funcs=(m.mean, m.std))
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 16, pars,
+                           [("coupling", lambda: rng.uniform(0.5, 4.0)), ("damping", lambda: rng.uniform(0.05, 0.5))],
+                           ev, 0.5)
+    ctx = _setup(m, prob, reltol=1e-8, abstol=1e-8)
+    assert ctx[0].desc.n_par == 2
+    got, ref = emul(*ctx), orc.solve_features(*ctx)
+    assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["nsteps"], ref["nsteps"])
+    cases.compare_features(got["feat"], ref, orc, *ctx, min_checked=0.5)
+    # the second parameter matters: the same runs with the damping column held fixed differ
+    prob.par[:, 1] = 0.1
+    ctx2 = _setup(m, prob, reltol=1e-8, abstol=1e-8)
+    assert not np.allclose(emul(*ctx2)["feat"], got["feat"])
