@@ -514,10 +514,13 @@ class DEMCBBSol:
         return [self[i] for i in range(self.N_mc)]
 
 
-def get_measure(sol, k):
-    """get_measure(sol, k) (setup_mc_prob.jl:601-624), k 1-based."""
+def get_measure(sol, k, state_filter=None):
+    """get_measure(sol, k; state_filter) (setup_mc_prob.jl:601-624), k 1-based; `state_filter` (1-based indices into
+    the measured dimensions) applies to per-dimension measures only."""
     k -= 1
     if k < sol.N_meas_dim:
+        if state_filter is not None:
+            return sol.feat[:, np.asarray(list(state_filter), dtype=np.int64) - 1, k]
         return sol.feat[:, :, k]
     k -= sol.N_meas_dim
     if k < sol.N_meas_matrix:
@@ -768,6 +771,60 @@ def sort_(sol, prob, i=1):
     sol.retcode = sol.retcode[idx]
     sol.nsteps = sol.nsteps[idx]
     return idx
+
+
+def sort_prob_(prob, i=1):
+    """sort!(prob, i) (setup_mc_prob.jl:558-573): the problem alone."""
+    p = parameter(prob, i)
+    idx = np.argsort(np.abs(p) if np.iscomplexobj(p) else p, kind="stable")
+    prob.ic[:, :] = prob.ic[idx, :]
+    prob.par[:, :] = prob.par[idx, :]
+    return idx
+
+
+def sort(sol, prob, i=1):
+    """sort(sol, prob, i) (setup_mc_prob.jl:505-511): sorted COPIES of both."""
+    import copy
+    sol_c, prob_c = copy.copy(sol), copy.copy(prob)
+    prob_c.ic, prob_c.par = prob.ic.copy(order="F"), prob.par.copy(order="F")
+    sort_(sol_c, prob_c, i)
+    return sol_c, prob_c
+
+
+def show_results(sol, prob, min_par, max_par, i=1, sorted=False):
+    """show_results (setup_mc_prob.jl:583-593): the measure tuples of the runs whose i-th parameter lies in the OPEN
+    interval (min_par, max_par), in sorted order."""
+    if not sorted:
+        sol, prob = sort(sol, prob, i)
+    p = parameter(prob, i)
+    return [sol[int(r)] for r in np.nonzero((p > min_par) & (p < max_par))[0]]
+
+
+def normalize(sol, k=None):
+    """normalize(sol, k) (setup_mc_prob.jl:635-660): a copy of `sol` whose measures k (1-based; default all) are
+    rescaled to [0, 1] by the minimum and range over ALL runs and dimensions of that measure.  Global measures are
+    left alone with the reference's warning."""
+    import copy
+    import warnings
+    ks = list(range(1, sol.N_meas + 1)) if k is None else [int(q) for q in k]
+    out = copy.copy(sol)
+    out.feat = sol.feat.copy(order="F")
+    out.matrix = None if sol.matrix is None else sol.matrix.copy(order="F")
+    out.glob = None if sol.glob is None else sol.glob.copy(order="F")
+    for q in ks:
+        if not 1 <= q <= sol.N_meas:
+            raise MCBBError("normalize: measure index %d out of range" % q)
+        if q > sol.N_meas_dim + sol.N_meas_matrix:
+            warnings.warn("Global measures are not normlized.")
+            continue
+        src = np.asarray(get_measure(sol, q))
+        lo, rng = src.min(), src.max() - src.min()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if q <= sol.N_meas_dim:
+                out.feat[:, :, q - 1] = (src - lo) / rng
+            else:
+                out.matrix[:, :] = (src - lo) / rng
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------

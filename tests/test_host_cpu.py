@@ -480,3 +480,48 @@ def test_multidim_parameter_var_problem_and_cluster_membership(mcbb):
     assert raw.data.shape[2] == 1 + (counts > counts.min()).sum() - (0 if (ca == 0).sum() > counts.min() else 1)
     with pytest.raises(m.MCBBError, match="as many elements"):
         m.cluster_membership(prob, db, 1.0, 0.5)
+
+
+def test_normalize_sort_show_results_get_measure(mcbb):
+    """normalize / sort / show_results / get_measure(state_filter) (setup_mc_prob.jl:505-660) on a synthetic
+    solution: literal per-run loops as in the reference."""
+    m = mcbb
+    rng = np.random.default_rng(5)
+    n, nd = 40, 3
+    feat = np.asfortranarray(rng.normal(size=(n, nd, 2)) * [3.0, 0.2] + [1.0, 5.0])
+    mat = np.asfortranarray(rng.random((n, 30)))
+    glob = np.asfortranarray(rng.normal(size=(n, 1)))
+    sol = m.DEMCBBSol(feat.copy(order="F"), mat.copy(order="F"), glob.copy(order="F"), np.zeros(n, np.int32),
+                      np.zeros((n, 2), np.int64), 400, None)
+    assert (sol.N_meas_dim, sol.N_meas_matrix, sol.N_meas_global, sol.N_meas) == (2, 1, 1, 4)
+    with pytest.warns(UserWarning, match="Global measures"):
+        nsol = m.normalize(sol)
+    for q in (1, 2):
+        a = m.get_measure(nsol, q)
+        want = (feat[:, :, q - 1] - feat[:, :, q - 1].min()) / (feat[:, :, q - 1].max() - feat[:, :, q - 1].min())
+        assert np.array_equal(a, want) and a.min() == 0.0 and a.max() == 1.0
+    assert np.array_equal(m.get_measure(nsol, 3), (mat - mat.min()) / (mat.max() - mat.min()))
+    assert np.array_equal(m.get_measure(nsol, 4), glob[:, 0]) and np.array_equal(sol.feat, feat)  # input untouched
+    only2 = m.normalize(sol, [2])
+    assert np.array_equal(only2.feat[:, :, 0], feat[:, :, 0]) and only2.feat[:, :, 1].max() == 1.0
+    assert np.array_equal(m.get_measure(sol, 1, state_filter=[3, 1]), feat[:, [2, 0], 0])
+
+    class P:  # the fields sort / parameter read
+        pass
+    prob = P()
+    prob.ic = np.asfortranarray(rng.normal(size=(n, nd)))
+    prob.par = np.asfortranarray(rng.permutation(np.repeat(np.arange(10.0), 4))[:, None])
+    prob.N_mc = n
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    ssol, sprob = m.sort(sol, prob)
+    idx = np.argsort(par0[:, 0], kind="stable")
+    assert np.array_equal(sprob.par, par0[idx]) and np.array_equal(sprob.ic, ic0[idx])
+    assert np.array_equal(ssol.feat, feat[idx]) and np.array_equal(ssol.matrix, mat[idx])
+    assert np.array_equal(prob.par, par0) and np.array_equal(sol.feat, feat)  # copies: inputs untouched
+    got = m.show_results(sol, prob, 2.0, 5.0)
+    rows = [r for r in idx if 2.0 < par0[r, 0] < 5.0]
+    assert len(got) == len(rows) == 8
+    for g, r in zip(got, rows):
+        assert np.array_equal(g[0], feat[r, :, 0]) and np.array_equal(g[2], mat[r]) and g[3] == glob[r, 0]
+    m.sort_prob_(prob)
+    assert np.array_equal(prob.par, par0[idx])
