@@ -830,12 +830,25 @@ def normalize(sol, k=None):
 # ------------------------------------------------------------------------------------------------------------
 # distance_matrix / dbscan (src/eval_clustering.jl:164-241, 84)
 # ------------------------------------------------------------------------------------------------------------
-def _compute_hist_edges(data, N_dim, k_bin, nbin_default=50):
-    """_compute_hist_edges (eval_clustering.jl:607-642, automatic binning): common edges of one measure from the
+def _compute_hist_edges(data, N_dim, k_bin, nbin_default=50, nbin=None, bin_edges=None):
+    """_compute_hist_edges (eval_clustering.jl:607-642): common edges of one measure from the
     Freedman-Draconis rule 0.5*k_bin*IQR/N_dim^(1/3); falls back to `nbin_default` equidistant edges over
-    [min-0.1min, max+0.1max] when the IQR is 0 or the rule yields more than nbin_default edges."""
+    [min-0.1min, max+0.1max] when the IQR is 0 or the rule yields more than nbin_default edges.  `nbin` (edges
+    (min-bw):bw:(max+bw) with bw = (max-min)/(nbin-1)) or explicit equidistant `bin_edges` switch the rule off."""
     data = np.asarray(data, dtype=np.float64)
     minval, maxval = float(data.min()), float(data.max())
+    if bin_edges is not None and nbin is not None:
+        raise MCBBError("bin_edges and nbin in kwargs. Please choose only one.")
+    if nbin is not None:
+        if not nbin > 1:
+            raise MCBBError("nbin must be larger than 1")
+        bw = (maxval - minval) / (nbin - 1)
+        return _julia_range(minval - bw, bw, maxval + bw), bw
+    if bin_edges is not None:
+        edges = np.asarray(list(bin_edges), dtype=np.float64)
+        if len(edges) < 2:
+            raise MCBBError("bin_edges needs all edges of the histogram (one more element than bins)")
+        return edges, float(edges[1] - edges[0])
     q75, q25 = np.percentile(data, [75, 25])  # type-7 quantiles, like StatsBase.iqr
     bw = 0.5 * k_bin * float(q75 - q25) / N_dim ** (1 / 3.0)
     if bw != 0:
@@ -945,7 +958,8 @@ def feature_groups(sol, prob, weights, relative_parameter=False):
     return X, np.asarray(glen, dtype=np.int32), np.asarray(weights, dtype=np.float64)
 
 
-def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_ecdf, k_bin, nbin_default):
+def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_ecdf, k_bin, nbin_default, nbin=None,
+                       bin_edges=None):
     """Feature matrix X [N_mc, F] + L1 groups (lengths, weights) whose weighted group sums are the reference distance
     (eval_clustering.jl:164-241), for the plain and the histogram variant; also the histogram edges / bin widths."""
     hist_edges, bin_widths = [], []
@@ -957,7 +971,13 @@ def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_e
             raise MCBBError("Amount of weights not the same as Measures + Parameters")
         cols, glen, gw = [], [], []
         for mi in range(sol.N_meas_dim):
-            edges, bw = _compute_hist_edges(sol.feat[:, :, mi], sol.N_dim, k_bin, nbin_default)
+            if nbin is not None and mi == 0:
+                import warnings
+                warnings.warn("nbin amount specified, all usual histogram binning function will not be used")
+            if bin_edges is not None and len(bin_edges) != sol.N_meas_dim:
+                raise MCBBError("bin_edges needs one entry (a range or None) per per-dimension measure")
+            edges, bw = _compute_hist_edges(sol.feat[:, :, mi], sol.N_dim, k_bin, nbin_default, nbin,
+                                            None if bin_edges is None else bin_edges[mi])
             H = _compute_hist_weights(sol.feat[:, :, mi], edges, use_ecdf)
             hist_edges.append(edges)
             bin_widths.append(bw)
@@ -989,12 +1009,12 @@ def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_e
 
 
 def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
-                    nbin_default=50, materialize=True):
+                    nbin_default=50, materialize=True, nbin=None, bin_edges=None):
     """distance_matrix(sol, prob, weights; relative_parameter, histograms, use_ecdf, k_bin, nbin_default) with the
     default L1 distance_func / wasserstein_histogram_distance (eval_clustering.jl:164-241).
     materialize=False returns a B200FeatureMatrix (distances are then recomputed on the fly by dbscan)."""
     X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
-                                                             use_ecdf, k_bin, nbin_default)
+                                                             use_ecdf, k_bin, nbin_default, nbin, bin_edges)
     if not materialize:
         return B200FeatureMatrix(X, glen, gw, weights, relative_parameter)
     n = X.shape[0]
@@ -1040,7 +1060,7 @@ class NonzeroSparseMatrix:
 
 
 def distance_matrix_sparse(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
-                           nbin_default=50, sparse_threshold=np.inf, el_type=np.float32):
+                           nbin_default=50, sparse_threshold=np.inf, el_type=np.float32, nbin=None, bin_edges=None):
     """distance_matrix_sparse (eval_clustering.jl:451-559): only distances below `sparse_threshold` are kept, as a
     NonzeroSparseMatrix.  The columns come straight from the feature matrix (two passes over the pair tiles on the
     GPU), D is never materialised.  Distances are accumulated in Float64 and rounded to `el_type` once (the reference
@@ -1048,7 +1068,7 @@ def distance_matrix_sparse(sol, prob, weights, relative_parameter=False, histogr
     if not np.isfinite(sparse_threshold) or not sparse_threshold > 0:
         raise MCBBError("sparse_threshold must be a finite positive number")
     X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
-                                                             use_ecdf, k_bin, nbin_default)
+                                                             use_ecdf, k_bin, nbin_default, nbin, bin_edges)
     n = X.shape[0]
     thr = float(el_type(sparse_threshold))
     ip, dp, lp = abi.c_int32_p, abi.c_double_p, abi.c_int64_p
@@ -1069,12 +1089,13 @@ def distance_matrix_sparse(sol, prob, weights, relative_parameter=False, histogr
 
 
 def distance_matrix_mmap(sol, prob, weights, relative_parameter=False, histograms=False, use_ecdf=True, k_bin=1,
-                         nbin_default=50, el_type=np.float32, save_name="mmap-distance-matrix.bin", block_rows=None):
+                         nbin_default=50, el_type=np.float32, save_name="mmap-distance-matrix.bin", block_rows=None,
+                         nbin=None, bin_edges=None):
     """distance_matrix_mmap (eval_clustering.jl:317-406): the matrix goes to `save_name` — two Int64 (N_mc, N_mc)
     followed by the rows in `el_type` — block of rows by block of rows from the GPU, and is returned memory-mapped
     (column-major (m, n) view of the file like Mmap.mmap(f, Matrix{el_type}, (m, n)); D is symmetric)."""
     X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
-                                                             use_ecdf, k_bin, nbin_default)
+                                                             use_ecdf, k_bin, nbin_default, nbin, bin_edges)
     n = X.shape[0]
     ip, dp = abi.c_int32_p, abi.c_double_p
     if block_rows is None:

@@ -525,3 +525,33 @@ def test_normalize_sort_show_results_get_measure(mcbb):
         assert np.array_equal(g[0], feat[r, :, 0]) and np.array_equal(g[2], mat[r]) and g[3] == glob[r, 0]
     m.sort_prob_(prob)
     assert np.array_equal(prob.par, par0[idx])
+
+
+def test_hist_edges_nbin_and_explicit_bin_edges(mcbb):
+    """nbin / bin_edges of distance_matrix(...; histograms=true) (eval_clustering.jl:607-642): (min-bw):bw:(max+bw)
+    with bw = (max-min)/(nbin-1), or the edges as given with bin_width = edges[2]-edges[1]; both at once is an error."""
+    api = mcbb.api
+    rng = np.random.default_rng(2)
+    data = rng.normal(size=(50, 7))
+    e, bw = api._compute_hist_edges(data, 7, 1.0, 50, nbin=12)
+    assert bw == (data.max() - data.min()) / 11 and e[0] == data.min() - bw and abs(e[1] - e[0] - bw) < 1e-15
+    assert 13 <= len(e) <= 14 and e[-1] >= data.max()
+    e2, bw2 = api._compute_hist_edges(data, 7, 1.0, 50, bin_edges=np.arange(-5.0, 5.01, 0.5))
+    assert bw2 == 0.5 and len(e2) == 21 and e2[0] == -5.0
+    with pytest.raises(mcbb.MCBBError, match="choose only one"):
+        api._compute_hist_edges(data, 7, 1.0, 50, nbin=5, bin_edges=[0.0, 1.0])
+    with pytest.raises(mcbb.MCBBError):
+        api._compute_hist_edges(data, 7, 1.0, 50, nbin=1)
+    # through the feature assembly: one ECDF group per measure with weight w * bin_width
+    feat = np.asfortranarray(rng.normal(size=(50, 7, 2)))
+    sol = mcbb.DEMCBBSol(feat, None, None, np.zeros(50, np.int32), np.zeros((50, 2), np.int64), 400, None)
+
+    class P:
+        pass
+    prob = P()
+    prob.par = np.asfortranarray(rng.random((50, 1)))
+    edges = [np.arange(-5.0, 5.01, 0.5), None]
+    X, gl, gw, he, bws = api._assemble_features(sol, prob, [1.0, 2.0, 1.0], False, True, True, 1.0, 50, None, edges)
+    assert list(gl)[:2] == [20, len(he[1]) - 1] and gw[0] == 0.5 and gw[1] == 2.0 * bws[1] and bws[0] == 0.5
+    with pytest.raises(mcbb.MCBBError, match="one entry"):
+        api._assemble_features(sol, prob, [1.0, 2.0, 1.0], False, True, True, 1.0, 50, None, edges[:1])
