@@ -202,3 +202,65 @@ def test_lane_source_two_swept_parameters(mcbb, orc, emul):
     prob.par[:, 1] = 0.1
     ctx2 = _setup(m, prob, reltol=1e-8, abstol=1e-8)
     assert not np.allclose(emul(*ctx2)["feat"], got["feat"])
+
+
+def test_lane_source_every_system_features_and_samples(mcbb, orc, emul):
+    """All seven systems of src/systems.jl (+ the Stuart-Landau notebook system) through the lane source on the host:
+    retcodes, step counts, measures and the exported samples against the oracle."""
+    m = mcbb
+    rng = np.random.default_rng(21)
+    N = 6
+    checks = []
+    pars = m.kuramoto_parameters(1.0, rng.normal(0.5, 0.05, N), N)
+    checks.append((pars, m.kuramoto, N, "K", (0.5, 3.0), (0.0, 30.0), m.EvalOdeRun(eval_funcs=(m.mean, m.std)), False))
+    pars = m.non_local_kuramoto_ring_parameters(N, 0.3, 0.2, lambda x: np.exp(-abs(x)) / (2 * np.pi))
+    checks.append((pars, m.non_local_kuramoto_ring, N, "phase_delay", (0.0, 1.4), (0.0, 30.0),
+                   m.EvalOdeRun(eval_funcs=(m.mean, m.std), cyclic_setback=True), False))
+    Nr = 3
+    Lp = 2 * np.eye(Nr) - np.roll(np.eye(Nr), 1, 0) - np.roll(np.eye(Nr), -1, 0)
+    pars = m.roessler_parameters(0.2 * np.ones(Nr), 0.2 * np.ones(Nr), 5.7 * np.ones(Nr), 0.05, Lp, Nr)
+    checks.append((pars, m.roessler_network, 3 * Nr, "K", (0.0, 0.1), (0.0, 15.0),
+                   m.EvalOdeRun(eval_funcs=(m.mean, m.std)), False))
+    A1 = np.roll(np.eye(N), 1, 0) + np.roll(np.eye(N), -1, 0)
+    A2 = A1 + np.roll(np.eye(N), 2, 0) + np.roll(np.eye(N), -2, 0)
+    pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.9, N, 1, 2, A1, A2)
+    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"))
+    checks.append((pars, m.stuart_landau_sathiyadevi, N, "eps", (1.8, 2.1), (0.0, 20.0), ev, True))
+    E = cases.ring_incidence(N, [(0, 3)])
+    pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, np.array([1.0, -1.0] * (N // 2)))
+    checks.append((pars, m.second_order_kuramoto, 2 * N, "coupling", (0.5, 4.0), (0.0, 30.0),
+                   m.EvalOdeRun(state_filter=list(range(N + 1, 2 * N + 1)), eval_funcs=(m.mean, m.std)), False))
+    w = rng.normal(0.5, 0.01, N)
+    pars = m.kuramoto_network_parameters(0.5, w, N, (rng.random((N, N)) < 0.6).astype(float))
+    checks.append((pars, m.kuramoto_network, N, "K", (0.5, 3.0), (0.0, 30.0), m.eval_ode_run, False))
+    for pars, f, ndim, pname, prange, tspan, ev, cplx in checks:
+        prng = np.random.default_rng(5)
+        if cplx:
+            gen, u0 = (lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1))), np.zeros(ndim, dtype=complex)
+        else:
+            gen, u0 = (lambda: rng.uniform(-1.0, 1.0)), np.zeros(ndim)
+        rp = m.ODEProblem(f, u0, tspan, pars)
+        prob = m.DEMCBBProblem(rp, gen, 10, pars, (pname, lambda: prng.uniform(*prange)), ev, 0.7)
+        ctx = _setup(m, prob)
+        psys, o, pfeat, ic, par, ts = ctx
+        got, ref = emul(*ctx, save_mode=m.abi.SAVE_ALL), orc.solve_features(*ctx)
+        assert np.array_equal(got["retcode"], ref["retcode"]), f.__name__
+        assert np.array_equal(got["nsteps"], ref["nsteps"]), f.__name__
+        cases.compare_features(got["feat"], ref, orc, *ctx, min_checked=0.3)
+        for i in (0, 9):
+            want = orc.trajectory(psys, o, ic[i], par[i], ts)[0]
+            scale = max(1.0, np.abs(want).max())
+            assert np.abs(got["saved"][i] - want).max() <= 1e-7 * scale, (f.__name__, i)
+    # the map: FunctionMap stepping, every iterate after the transient is a sample
+    prob, _ = cases.c2_problem(m, n_mc=16, tspan=(0.0, 300.0))
+    ctx = _setup(m, prob)
+    psys, o, pfeat, ic, par, ts = ctx
+    got = emul(*ctx, save_mode=m.abi.SAVE_ALL)
+    for i in range(16):
+        x, r = ic[i, 0], par[i, 0]
+        orbit = []
+        for t in range(300):
+            if t >= int(ts[0]):
+                orbit.append(x)
+            x = r * x * (1 - x)
+        assert np.array_equal(got["saved"][i, 0], np.array(orbit[:len(ts)]))
