@@ -329,6 +329,56 @@ def test_c5_batched_converged(gpu, orc):
     print("c5 converged parity", stats)
 
 
+def test_c5_full_size_properties(gpu):
+    """The bench workload at its full single-GPU size (C5: 125 000 runs, Kuramoto N = 100, tspan (0, 1000), default
+    tolerances) through the tcgen05 kernel, checked by size-independent properties instead of an oracle pass:
+    * uncoupled runs (K = 0) have the closed form u_i(t) = u_i(0) + w_i t -> mean / std incl. the cyclic setback;
+    * a run's result does not depend on where it sits in the ensemble or on its batch neighbours: twins placed far
+      apart are bitwise equal, and a shuffled sub-ensemble solved alone reproduces its rows bitwise;
+    * every run succeeds and reports a plausible step count."""
+    m = gpu
+    n = 125000
+    N = 100
+    A = cases.erdos_renyi(N, 0.2, 10)
+    w = np.random.default_rng(11).normal(0.5, 0.1, N)
+    pars = m.kuramoto_network_parameters(0.5, w, N, A)
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), (0.0, 1000.0), pars)
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std), cyclic_setback=True)
+    rng = np.random.default_rng(12)
+    prob = m.DEMCBBProblem(rp, lambda: 0.0, 1, pars, ("K", lambda: 0.0), ev, 0.9)  # shell; arrays set below
+    prob.ic = np.asfortranarray(rng.uniform(-np.pi, np.pi, size=(n, N)))
+    prob.par = np.asfortranarray(rng.uniform(0.0, 8.0, size=(n, 1)))
+    prob.N_mc = n
+    free = np.arange(0, n, 1000)
+    prob.par[free, 0] = 0.0
+    src, dst = np.arange(7, n, 2500), np.arange(7, n, 2500)[::-1] + 1  # 50 twins, far apart
+    prob.ic[dst], prob.par[dst] = prob.ic[src], prob.par[src]
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    before = m.kernel_launch_count()
+    feat, _, _, ret, ns = m.custom_solve_b200(prob, ts)
+    assert m.kernel_launch_count() - before == 1  # one launch of the batched kernel for the whole ensemble
+    assert np.all(ret == 0) and np.isfinite(feat).all()
+    assert ns[:, 0].min() >= 3 and ns[:, 0].max() < 100000 and np.all(ns[:, 1] <= ns[:, 0])
+    # closed form of the uncoupled runs
+    t = ts[1:]
+    x1 = prob.ic[free] + w[None, :] * t[0]
+    v = np.mod(x1, 2 * np.pi)
+    v = np.where(v > np.pi, v - 2 * np.pi, v)
+    want_mean = v + w[None, :] * (t - t[0]).mean()
+    want_std = np.abs(w)[None, :] * t.std(ddof=1)
+    near_cut = np.abs(np.abs(v) - np.pi) < 1e-6  # a sample within rounding of the branch cut may wrap either way
+    assert np.abs(feat[free, :, 0] - want_mean)[~near_cut].max() < 1e-7
+    assert np.abs(feat[free, :, 1] - want_std).max() < 1e-7
+    # twins
+    assert np.array_equal(feat[src], feat[dst]) and np.array_equal(ns[src], ns[dst])
+    # a shuffled sub-ensemble solved alone
+    pick = rng.permutation(n)[:6000]
+    sub = m.DEMCBBProblem(rp, lambda: 0.0, 1, pars, ("K", lambda: 0.0), ev, 0.9)
+    sub.ic, sub.par, sub.N_mc = np.asfortranarray(prob.ic[pick]), np.asfortranarray(prob.par[pick]), len(pick)
+    f2, _, _, r2, n2 = m.custom_solve_b200(sub, ts)
+    assert np.array_equal(f2, feat[pick]) and np.array_equal(n2, ns[pick]) and np.all(r2 == 0)
+
+
 @pytest.mark.parametrize("N,filt", [(30, None), (40, None), (64, None), (97, [0, 5, 63, 64, 95, 96]), (128, None)])
 def test_tensor_core_kernel_network_sizes(gpu, orc, N, filt):
     """The tcgen05 integrator maps oscillator r to row r of a 128-row MMA tile: sizes that leave whole warps idle
