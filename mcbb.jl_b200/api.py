@@ -1236,8 +1236,35 @@ def _julia_range(start, step, stop):
 
 
 class ClusterMembershipResult:
+    """ClusterMembershipResult (eval_clustering.jl:1268-1340): `par` window grid, `data[..., cluster]` memberships;
+    indexable by cluster (1-based like the reference, column 1 = noise), sortable by total membership, summable."""
+
     def __init__(self, par, data, multidim_flag=False):
         self.par, self.data, self.multidim_flag = par, data, multidim_flag
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __getitem__(self, i):  # cm[i] / cm[[i, j]]: the selected clusters, window axes kept
+        idx = [int(i) - 1] if np.ndim(i) == 0 else [int(q) - 1 for q in i]
+        return ClusterMembershipResult(self.par, self.data[..., idx], self.multidim_flag)
+
+    def sort_(self, ignore_first=False):
+        """sort!(cm; ignore_first) (:1308-1322): clusters ordered by their summed membership, low to high; with
+        ignore_first the noise column stays first."""
+        tot = self.data.reshape(-1, self.data.shape[-1]).sum(axis=0)
+        if ignore_first:
+            order = np.concatenate([[0], np.argsort(tot[1:], kind="stable") + 1])
+        else:
+            order = np.argsort(tot, kind="stable")
+        self.data = self.data[..., order]
+        return order
+
+    def sum(self, indices):
+        """sum(cm, indices) (:1332-1338): the selected clusters (1-based) added into one column."""
+        idx = [int(q) - 1 for q in indices]
+        return ClusterMembershipResult(self.par, self.data[..., idx].sum(axis=-1).reshape(-1, 1), self.multidim_flag)
 
 
 def _cluster_membership_multidim(prob, clusters, window_size, window_offset, normalize, min_members):

@@ -555,3 +555,19 @@ def test_hist_edges_nbin_and_explicit_bin_edges(mcbb):
     assert list(gl)[:2] == [20, len(he[1]) - 1] and gw[0] == 0.5 and gw[1] == 2.0 * bws[1] and bws[0] == 0.5
     with pytest.raises(mcbb.MCBBError, match="one entry"):
         api._assemble_features(sol, prob, [1.0, 2.0, 1.0], False, True, True, 1.0, 50, None, edges[:1])
+
+
+def test_cluster_membership_result_operations(mcbb):
+    """Indexing, sort! and sum of ClusterMembershipResult (eval_clustering.jl:1290-1338)."""
+    rng = np.random.default_rng(1)
+    data = rng.random((9, 4)) * [1.0, 5.0, 0.1, 2.0]
+    cm = mcbb.ClusterMembershipResult(np.arange(9.0), data.copy(), False)
+    assert cm.shape == (9, 4) and np.array_equal(cm[2].data, data[:, 1:2]) and np.array_equal(cm[[1, 4]].data, data[:, [0, 3]])
+    s = cm.sum([2, 3])
+    assert s.data.shape == (9, 1) and np.allclose(s.data[:, 0], data[:, 1] + data[:, 2])
+    order = cm.sort_()
+    assert list(order) == [2, 0, 3, 1] and np.array_equal(cm.data, data[:, [2, 0, 3, 1]])
+    cm2 = mcbb.ClusterMembershipResult(np.arange(9.0), data.copy(), False)
+    assert list(cm2.sort_(ignore_first=True)) == [0, 2, 3, 1]
+    multi = mcbb.ClusterMembershipResult(np.zeros((3, 3, 2)), rng.random((3, 3, 4)), True)
+    assert multi[3].data.shape == (3, 3, 1) and multi.sum([1, 2]).data.shape == (9, 1)
