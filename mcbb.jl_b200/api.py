@@ -1305,6 +1305,47 @@ def _cluster_membership_multidim(prob, clusters, window_size, window_offset, nor
     return ClusterMembershipResult(mesh, data, True)
 
 
+def measure_on_parameter_sliding_window(prob, sol, i, *args):
+    """measure_on_parameter_sliding_window(prob, sol, i, [clusters,] window_size, window_offset)
+    (eval_clustering.jl:1369-1430): the mean of the i-th measure (1-based) over the runs of every cluster inside every
+    open parameter window; NaN where a cluster has no member in the window.  Returns (parameter_mesh,
+    cluster_meas[N_cluster, N_dim, N_windows...]); without `clusters` all runs form one group."""
+    if len(args) == 3:
+        clusters, window_size, window_offset = args
+        ca, n_cluster = np.asarray(clusters.assignments), len(clusters.seeds) + 1
+    elif len(args) == 2:
+        window_size, window_offset = args
+        ca, n_cluster = np.zeros(prob.N_mc, dtype=np.int64), 1
+    else:
+        raise MCBBError("measure_on_parameter_sliding_window(prob, sol, i, [clusters,] window_size, window_offset)")
+    n_par = prob.par.shape[1]
+    window_size, window_offset = np.atleast_1d(window_size).astype(float), np.atleast_1d(window_offset).astype(float)
+    if len(window_size) != n_par or len(window_offset) != n_par:
+        raise MCBBError("Window Size and Window Offset need to have as many elements as they are parameters")
+    mins = [_julia_range(prob.par[:, p].min(), window_offset[p], prob.par[:, p].max() - window_size[p])
+            for p in range(n_par)]
+    shape = [len(q) for q in mins]
+    obs = np.asarray(get_measure(sol, i), dtype=np.float64)
+    obs = obs.reshape(len(obs), -1)
+    n_dim = obs.shape[1]
+    meas = np.zeros([n_cluster, n_dim] + shape)
+    mesh = np.zeros([n_par] + shape)
+    for idx in np.ndindex(*shape):
+        ind = np.ones(prob.N_mc, dtype=bool)
+        for p in range(n_par):
+            lo = mins[p][idx[p]]
+            ind &= (prob.par[:, p] > lo) & (prob.par[:, p] < lo + window_size[p])
+            mesh[(p,) + idx] = lo
+        cnt = np.bincount(ca[ind], minlength=n_cluster).astype(float)
+        acc = np.zeros((n_cluster, n_dim))
+        np.add.at(acc, ca[ind], obs[ind])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            meas[(slice(None), slice(None)) + idx] = np.where(cnt[:, None] > 0, acc / cnt[:, None], np.nan)
+    if n_par == 1:
+        mesh = mesh[0]
+    return mesh, meas
+
+
 def cluster_membership(prob, clusters, window_size, window_offset, normalize=True, min_members=0):
     """Sliding-window cluster membership (eval_clustering.jl:1206-1265); arrays of window sizes / offsets for several
     varied parameters."""

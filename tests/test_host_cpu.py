@@ -571,3 +571,40 @@ def test_cluster_membership_result_operations(mcbb):
     assert list(cm2.sort_(ignore_first=True)) == [0, 2, 3, 1]
     multi = mcbb.ClusterMembershipResult(np.zeros((3, 3, 2)), rng.random((3, 3, 4)), True)
     assert multi[3].data.shape == (3, 3, 1) and multi.sum([1, 2]).data.shape == (9, 1)
+
+
+def test_measure_on_parameter_sliding_window(mcbb):
+    """measure_on_parameter_sliding_window (eval_clustering.jl:1369-1430) against the reference's literal loops."""
+    m = mcbb
+    rng = np.random.default_rng(8)
+    n, nd = 120, 3
+    feat = np.asfortranarray(rng.normal(size=(n, nd, 2)))
+    glob = np.asfortranarray(rng.normal(size=(n, 1)))
+    sol = m.DEMCBBSol(feat, None, glob, np.zeros(n, np.int32), np.zeros((n, 2), np.int64), 400, None)
+
+    class P:
+        pass
+    prob = P()
+    prob.N_mc = n
+    prob.par = np.asfortranarray(np.sort(rng.uniform(0, 4, n))[:, None])
+    ca = rng.integers(0, 3, n)
+    db = m.DbscanResult(np.arange(2), ca, np.bincount(ca, minlength=3)[1:])
+    ws, wo = 1.0, 0.5
+    mesh, meas = m.measure_on_parameter_sliding_window(prob, sol, 2, db, ws, wo)
+    assert mesh.ndim == 1 and meas.shape == (3, nd, len(mesh))
+    p = prob.par[:, 0]
+    for k, lo in enumerate(mesh):
+        ind = (p > lo) & (p < lo + ws)
+        for c in range(3):
+            sel = ind & (ca == c)
+            want = feat[sel, :, 1].mean(axis=0) if sel.any() else np.full(nd, np.nan)
+            assert np.allclose(meas[c, :, k], want, equal_nan=True)
+    mesh2, meas2 = m.measure_on_parameter_sliding_window(prob, sol, 3, ws, wo)  # the global measure, all runs
+    assert meas2.shape == (1, 1, len(mesh)) and np.array_equal(mesh2, mesh)
+    ind0 = (p > mesh[0]) & (p < mesh[0] + ws)
+    assert np.isclose(meas2[0, 0, 0], glob[ind0, 0].mean())
+    # a cluster absent from a window reads NaN
+    ca2 = np.where(p < 2.0, 1, 2)
+    db2 = m.DbscanResult(np.arange(2), ca2, np.bincount(ca2, minlength=3)[1:])
+    _, meas3 = m.measure_on_parameter_sliding_window(prob, sol, 1, db2, ws, wo)
+    assert np.isnan(meas3[0]).all() and np.isnan(meas3[2, :, 0]).all() and np.isfinite(meas3[1, :, 0]).all()
