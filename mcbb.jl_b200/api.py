@@ -1305,6 +1305,84 @@ def _cluster_membership_multidim(prob, clusters, window_size, window_offset, nor
     return ClusterMembershipResult(mesh, data, True)
 
 
+def cluster_means(sol, clusters):
+    """cluster_means (eval_clustering.jl:770-787): mean of every per-dimension measure per cluster,
+    [N_cluster (noise first), N_meas_dim, N_dim]."""
+    if len(clusters.counts) == 0:
+        import warnings
+        warnings.warn("No clusters found")
+        return False
+    ca = np.asarray(clusters.assignments)
+    n_cluster = len(clusters.seeds) + 1
+    counts = np.concatenate([[cluster_n_noise(clusters)], np.asarray(clusters.counts)]).astype(np.float64)
+    out = np.zeros((n_cluster, sol.N_meas_dim, sol.N_dim))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        contrib = np.transpose(sol.feat, (0, 2, 1)) / counts[ca][:, None, None]  # summed as x / count, like the reference
+    np.add.at(out, ca, contrib)
+    return out
+
+
+def cluster_measure_mean(sol, clusters, i):
+    """cluster_measure_mean (eval_clustering.jl:794-802): mean of measure i over all runs AND dimensions of a cluster."""
+    meas = np.asarray(get_measure(sol, i), dtype=np.float64).reshape(sol.N_mc, -1)
+    ca = np.asarray(clusters.assignments)
+    with np.errstate(invalid="ignore"), _quiet():
+        return np.array([meas[ca == c].mean() for c in range(len(clusters.seeds) + 1)])
+
+
+def cluster_measure_std(sol, clusters, i):
+    """cluster_measure_std (eval_clustering.jl:809-817): corrected std over all runs and dimensions of a cluster."""
+    meas = np.asarray(get_measure(sol, i), dtype=np.float64).reshape(sol.N_mc, -1)
+    ca = np.asarray(clusters.assignments)
+    with np.errstate(invalid="ignore", divide="ignore"), _quiet():
+        return np.array([meas[ca == c].std(ddof=1) for c in range(len(clusters.seeds) + 1)])
+
+
+class _quiet:
+    def __enter__(self):
+        import warnings
+        self._c = warnings.catch_warnings()
+        self._c.__enter__()
+        warnings.simplefilter("ignore")
+
+    def __exit__(self, *a):
+        return self._c.__exit__(*a)
+
+
+def get_cluster_measure(sol, i, clusters, i_cluster, prob=None, min_par=-np.inf, max_par=np.inf, i_par=1):
+    """get_measure(sol, i, clusters, i_cluster, prob, min_par, max_par, i_par) (eval_clustering.jl:824-858): measure
+    i of the runs in cluster i_cluster (1-based, 1 = noise) whose parameter lies in the open interval."""
+    ind = np.asarray(clusters.assignments) == (int(i_cluster) - 1)
+    if prob is not None:
+        par = prob.par[:, i_par - 1] if prob.par.shape[1] > 1 else prob.par[:, 0]
+        ind &= (par > min_par) & (par < max_par)
+    return np.asarray(get_measure(sol, i))[ind]
+
+
+class ClusterMeasureResult:
+    """ClusterMeasureResult (eval_clustering.jl:928-933)."""
+
+    def __init__(self, par, cluster_measures, cluster_measures_global, multidim_flag):
+        self.par, self.cluster_measures = par, cluster_measures
+        self.cluster_measures_global, self.multidim_flag = cluster_measures_global, multidim_flag
+
+
+def cluster_measures(prob, sol, clusters, window_size, window_offset):
+    """cluster_measures (eval_clustering.jl:883-906): every per-dimension measure [N_cluster, N_meas_dim, N_dim,
+    N_windows...] and every global measure [N_cluster, N_meas_global, N_windows...] on the sliding windows."""
+    par, per_dim, glob = None, [], []
+    for q in range(1, sol.N_meas_dim + 1):
+        par, cm = measure_on_parameter_sliding_window(prob, sol, q, clusters, window_size, window_offset)
+        per_dim.append(cm)
+    for q in range(sol.N_meas_dim + sol.N_meas_matrix + 1, sol.N_meas + 1):
+        par, cm = measure_on_parameter_sliding_window(prob, sol, q, clusters, window_size, window_offset)
+        glob.append(cm[:, 0])
+    n_cluster = len(clusters.seeds) + 1
+    cmeas = np.stack(per_dim, axis=1)
+    cglob = np.stack(glob, axis=1) if glob else np.zeros((n_cluster, 0) + cmeas.shape[3:])
+    return ClusterMeasureResult(par, cmeas, cglob, prob.par.shape[1] > 1)
+
+
 def measure_on_parameter_sliding_window(prob, sol, i, *args):
     """measure_on_parameter_sliding_window(prob, sol, i, [clusters,] window_size, window_offset)
     (eval_clustering.jl:1369-1430): the mean of the i-th measure (1-based) over the runs of every cluster inside every

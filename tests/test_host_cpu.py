@@ -608,3 +608,42 @@ def test_measure_on_parameter_sliding_window(mcbb):
     db2 = m.DbscanResult(np.arange(2), ca2, np.bincount(ca2, minlength=3)[1:])
     _, meas3 = m.measure_on_parameter_sliding_window(prob, sol, 1, db2, ws, wo)
     assert np.isnan(meas3[0]).all() and np.isnan(meas3[2, :, 0]).all() and np.isfinite(meas3[1, :, 0]).all()
+
+
+def test_cluster_means_measures_and_per_cluster_getters(mcbb):
+    """cluster_means / cluster_measure_mean / cluster_measure_std / get_measure by cluster / cluster_measures
+    (eval_clustering.jl:770-906) against literal loops."""
+    m = mcbb
+    rng = np.random.default_rng(13)
+    n, nd = 90, 4
+    feat = np.asfortranarray(rng.normal(size=(n, nd, 2)))
+    glob = np.asfortranarray(rng.normal(size=(n, 1)))
+    sol = m.DEMCBBSol(feat, None, glob, np.zeros(n, np.int32), np.zeros((n, 2), np.int64), 400, None)
+    ca = rng.integers(0, 3, n)
+    db = m.DbscanResult(np.arange(2), ca, np.bincount(ca, minlength=3)[1:])
+    cmn = m.cluster_means(sol, db)
+    assert cmn.shape == (3, 2, nd)
+    for c in range(3):
+        assert np.allclose(cmn[c], feat[ca == c].mean(axis=0).T)
+    assert np.allclose(m.cluster_measure_mean(sol, db, 2), [feat[ca == c, :, 1].mean() for c in range(3)])
+    assert np.allclose(m.cluster_measure_std(sol, db, 1), [feat[ca == c, :, 0].std(ddof=1) for c in range(3)])
+    assert np.allclose(m.cluster_measure_mean(sol, db, 3), [glob[ca == c, 0].mean() for c in range(3)])
+
+    class P:
+        pass
+    prob = P()
+    prob.N_mc = n
+    prob.par = np.asfortranarray(rng.uniform(0, 3, n)[:, None])
+    got = m.get_cluster_measure(sol, 1, db, 2, prob, 1.0, 2.0)
+    sel = (ca == 1) & (prob.par[:, 0] > 1.0) & (prob.par[:, 0] < 2.0)
+    assert np.array_equal(got, feat[sel, :, 0]) and np.array_equal(m.get_cluster_measure(sol, 3, db, 1), glob[ca == 0, 0])
+    res = m.cluster_measures(prob, sol, db, 1.0, 0.5)
+    nw = len(res.par)
+    assert res.cluster_measures.shape == (3, 2, nd, nw) and res.cluster_measures_global.shape == (3, 1, nw)
+    assert not res.multidim_flag
+    lo = res.par[1]
+    ind = (prob.par[:, 0] > lo) & (prob.par[:, 0] < lo + 1.0)
+    assert np.allclose(res.cluster_measures[2, 1, :, 1], feat[ind & (ca == 2), :, 1].mean(axis=0))
+    assert np.isclose(res.cluster_measures_global[0, 0, 1], glob[ind & (ca == 0), 0].mean())
+    with pytest.warns(UserWarning, match="No clusters"):
+        assert m.cluster_means(sol, m.DbscanResult(np.zeros(0, int), np.zeros(n, int), np.zeros(0, int))) is False
