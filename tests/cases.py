@@ -133,3 +133,35 @@ def compare_features(feat, ref, orc, psys, opts, pfeat, ic, par, t_save, min_che
         stats["kl_bad"] = int(bad_kl.sum())
         assert stats["kl_bad"] <= allow_bad, "KL-hist differs from both oracle variants: %s" % stats
     return stats
+
+
+def check_solves_against_golden(G, I, orc, solve, tsave):
+    """The solve-related golden vectors (tests/golden/oracle_golden.json) against `solve(psys, opts, pfeat, ic, par,
+    t_save, save_mode) -> dict(feat, matrix, nsteps, retcode, saved)` — the CUDA path through the C-ABI, or the host
+    build of the lane source.  `tsave(opts, N_t, tail)` is the product's save grid.  The oracle is only used by
+    compare_features to tell which runs are too sensitive to compare (and for the KL range-length variants)."""
+    abi = orc.abi
+    # C1 shape: measures within the feature tolerance, identical step sequences
+    ts = tsave(I["c1_opts"], 400, 0.9)
+    ctx = (I["c1_sys"], I["c1_opts"], I["feat_default"], I["c1_ic"], I["c1_par"], ts)
+    got = solve(*ctx, 0)
+    assert np.all(got["retcode"] == 0) and np.array_equal(got["nsteps"], np.array(G["c1_nsteps"]))
+    stats = compare_features(got["feat"], {"feat": np.array(G["c1_feat"])}, orc, *ctx)
+    assert stats["checked"] >= 12
+    # C2 shape: the map is evaluated with the reference's literal expression
+    tl = tsave(I["c2_opts"], 400, 0.8)
+    ctx = (I["c2_sys"], I["c2_opts"], I["feat_default"], I["c2_ic"], I["c2_par"], tl)
+    got = solve(*ctx, 0)
+    compare_features(got["feat"], {"feat": np.array(G["c2_feat"])}, orc, *ctx, min_checked=0.3)
+    # correlation_hist / correlation_ecdf of the grid frequencies: a |cor| within rounding of a bin edge may move
+    tg = tsave(I["c3_opts"], 400, 0.5)
+    for name in ("hist", "ecdf"):
+        got = solve(I["c3_sys"], I["c3_opts"], I["c3_feat"][name], I["c3_ic"], I["c3_par"], tg, 0)
+        want = np.array(G["c3_corr_" + name])
+        same = np.all(np.abs(got["matrix"] - want) < 1e-12, axis=1)
+        assert same.sum() >= 7, (name, same)
+        assert np.abs(got["matrix"] - want).max() <= (4 if name == "hist" else 4 / 30 + 1e-12)
+    # the saved samples of run 0 (get_trajectory)
+    got = solve(I["c3_sys"], I["c3_opts"], I["c3_feat"]["hist"], I["c3_ic"][:1], I["c3_par"][:1], tg, abi.SAVE_ALL)
+    want = np.array(G["c3_trajectory_run0"])
+    assert np.abs(got["saved"][0][:, ::40] - want).max() <= 1e-7 * max(1.0, np.abs(want).max())

@@ -892,3 +892,43 @@ def test_tensor_core_kernel_retcodes_and_fixed_dt(gpu, orc):
     ref2, ctx2 = _oracle_ref(m, orc, prob2, ic0, par0, **kw)
     assert np.array_equal(sol2.retcode, ref2["retcode"])
     cases.compare_features(sol2.feat, ref2, orc, *ctx2, min_checked=0.9)
+
+
+def test_cuda_path_against_committed_golden_vectors(gpu, orc):
+    """The CUDA path through the C-ABI against tests/golden/oracle_golden.json — the committed vectors, not a fresh
+    oracle solve (the oracle only tells compare_features which runs are too sensitive to compare): C1- and C2-shape
+    measures and step counts, the correlation measures and one saved trajectory of the power grid, and DBSCAN labels /
+    seeds on the tie-rich lattice (dense and fused) with the lattice distances bit-exact."""
+    import json
+    import types
+    from tests.golden.make_golden import build_inputs
+    m = gpu
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.json")))
+    I = build_inputs(m.abi)
+
+    def tsave(opts, n_t, tail):
+        shim = types.SimpleNamespace(discrete=opts.alg == m.abi.ALG_FUNCTIONMAP, tspan=(opts.t0, opts.t1))
+        return m.tsave_array(shim, n_t, tail)
+
+    def solve(psys, opts, pfeat, ic, par, ts, save_mode):
+        prob = types.SimpleNamespace(
+            par_names=[], pars=types.SimpleNamespace(pack=lambda names: psys),
+            eval_ode_func=types.SimpleNamespace(pack=lambda: pfeat, failure_handling="None"),
+            ic=np.asfortranarray(ic), par=np.asfortranarray(par), solver_par=None,
+            p=types.SimpleNamespace(tspan=(opts.t0, opts.t1), discrete=opts.alg == m.abi.ALG_FUNCTIONMAP))
+        kw = {k: getattr(opts, k) for k in ("reltol", "abstol") if getattr(opts, k) > 0}
+        feat, mat, glob, ret, ns, saved = m.api._solve_b200(prob, ts, None, save_mode, kw)
+        return dict(feat=feat, matrix=mat, glob=glob, retcode=ret, nsteps=ns, saved=saved)
+
+    cases.check_solves_against_golden(G, I, orc, solve, tsave)
+    X = np.asfortranarray(I["lattice"])
+    gl, gw = np.array([2], dtype=np.int32), np.array([1.0])
+    D = np.zeros((50, 50), order="F")
+    m.check(m.lib().mcbb_distance_matrix(X.ctypes.data_as(m.abi.c_double_p), 50, 1, gl.ctypes.data_as(m.abi.c_int32_p),
+                                         gw.ctypes.data_as(m.abi.c_double_p), D.ctypes.data_as(m.abi.c_double_p)))
+    assert np.array_equal(D[0], np.array(G["D_lattice_row0"])) and np.array_equal(D, D.T)
+    fm = m.B200FeatureMatrix(X, gl, gw, [1.0], False)
+    for eps, mp in I["lattice_cases"]:
+        for res in (m.dbscan(D, eps, mp), m.dbscan(fm, eps, mp)):
+            assert np.array_equal(res.assignments, np.array(G["db_%s_%d" % (eps, mp)]))
+            assert np.array_equal(res.seeds, np.array(G["db_seeds_%s_%d" % (eps, mp)]))

@@ -264,3 +264,20 @@ def test_lane_source_every_system_features_and_samples(mcbb, orc, emul):
                 orbit.append(x)
             x = r * x * (1 - x)
         assert np.array_equal(got["saved"][i, 0], np.array(orbit[:len(ts)]))
+
+
+def test_lane_source_against_committed_golden_vectors(mcbb, orc, emul):
+    """The host build of the lane source against tests/golden/oracle_golden.json (no fresh oracle solve)."""
+    import json
+    from tests.golden.make_golden import build_inputs
+    G = json.load(open(os.path.join(HERE, "golden", "oracle_golden.json")))
+    I = build_inputs(mcbb.abi)
+
+    def tsave(opts, n_t, tail):
+        class P:
+            discrete = opts.alg == mcbb.abi.ALG_FUNCTIONMAP
+            tspan = (opts.t0, opts.t1)
+        ts = mcbb.tsave_array(P, n_t, tail)
+        assert np.array_equal(ts, orc.tsave_array(opts, n_t, tail))
+        return ts
+    cases.check_solves_against_golden(G, I, orc, lambda *a: emul(*a[:6], save_mode=a[6]), tsave)
