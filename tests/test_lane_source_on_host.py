@@ -162,9 +162,7 @@ def test_lane_source_per_run_solver_options(mcbb, orc, emul):
         psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
         assert psys.desc.n_par == 0
         alg = m.abi.ALG_RK4 if "alg" in kw else m.abi.ALG_TSIT5
-        base = {} if name == "dt" else {}
-        if name == "dt":
-            base = dict(dt=0.03)  # overridden per run
+        base = dict(dt=0.03) if name == "dt" else {}  # the launch-wide dt is overridden per run
         o = m.abi.solver_opts(alg, prob.p.tspan, **base)
         ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
         got = emul(psys, o, pfeat, prob.ic, prob.par, ts, solver_var=(name, prob.par[:, 0]))
