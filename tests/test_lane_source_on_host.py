@@ -279,3 +279,74 @@ def test_lane_source_against_committed_golden_vectors(mcbb, orc, emul):
         assert np.array_equal(ts, orc.tsave_array(opts, n_t, tail))
         return ts
     cases.check_solves_against_golden(G, I, orc, lambda *a: emul(*a[:6], save_mode=a[6]), tsave)
+
+
+def test_lane_source_option_combinations(mcbb, orc, emul):
+    """Seeded random combinations of what eval_ode_run / solve can be asked for — measures (with and without KL),
+    state_filter, cyclic_setback, global sum, a matrix measure, Tsit5 at several tolerances or fixed-step RK4,
+    maxiters failures — on three systems: retcodes and step counts identical to the oracle, measures within the feature
+    tolerance, failed runs NaN."""
+    m, abi = mcbb, mcbb.abi
+    rng = np.random.default_rng(77)
+    N = 5
+    E = cases.ring_incidence(N, [(0, 2)])
+    systems = [
+        lambda: (m.kuramoto_network_parameters(0.5, rng.normal(0.5, 0.02, N), N, (rng.random((N, N)) < 0.7) * 1.0),
+                 m.kuramoto_network, N, "K", (0.5, 3.0)),
+        lambda: (m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, rng.normal(0, 1, N)), m.second_order_kuramoto,
+                 2 * N, "coupling", (0.5, 3.0)),
+        lambda: (m.kuramoto_parameters(1.0, rng.normal(0.5, 0.05, N), N), m.kuramoto, N, "K", (0.2, 2.0)),
+    ]
+    n_fail_cases = 0
+    for trial in range(30):
+        pars, f, ndim, pname, prange = systems[trial % 3]()
+        funcs = [(m.mean, m.std), (m.mean, m.std, m.empirical_1D_KL_divergence_hist), (m.mean,)][rng.integers(3)]
+        filt = None if rng.random() < 0.5 else sorted(rng.choice(np.arange(1, ndim + 1), size=3, replace=False).tolist())
+        mat = [None, [m.correlation_ecdf], [m.correlation_hist]][rng.integers(3)]
+        ev = m.EvalOdeRun(state_filter=filt, eval_funcs=funcs, matrix_eval_funcs=mat,
+                          global_eval_funcs=["sum"] if rng.random() < 0.5 else None,
+                          cyclic_setback=bool(rng.random() < 0.5))
+        rp = m.ODEProblem(f, np.zeros(ndim), (0.0, float(rng.choice([20.0, 40.0]))), pars)
+        prng = np.random.default_rng(int(rng.integers(1 << 30)))
+        prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-2.0, 2.0), 6, pars, (pname, lambda: prng.uniform(*prange)), ev,
+                               float(rng.choice([0.5, 0.8, 0.9])))
+        mode = rng.integers(4)
+        if mode == 0:
+            kw, alg = {}, None
+        elif mode == 1:
+            kw, alg = dict(reltol=1e-7, abstol=1e-8), None
+        elif mode == 2:
+            kw, alg = dict(dt=0.05), m.abi.ALG_RK4
+        else:
+            kw, alg = dict(maxiters=int(rng.integers(3, 40))), None
+        psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+        o = abi.solver_opts(alg if alg is not None else abi.ALG_TSIT5, prob.p.tspan, **kw)
+        ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+        ctx = (psys, o, pfeat, prob.ic, prob.par, ts)
+        got, ref = emul(*ctx), orc.solve_features(*ctx)
+        tag = (trial, f.__name__, mode)
+        assert np.array_equal(got["retcode"], ref["retcode"]), tag
+        assert np.array_equal(got["nsteps"], ref["nsteps"]), tag
+        failed = ref["retcode"] != 0
+        n_fail_cases += int(failed.any())
+        assert np.isnan(got["feat"][failed]).all(), tag
+        if (~failed).sum() >= 2:
+            ok = ~failed
+            sub_ctx = (psys, o, pfeat, prob.ic[ok], prob.par[ok], ts)
+            cases.compare_features(got["feat"][ok], {"feat": ref["feat"][ok]}, orc, *sub_ctx, min_checked=0.3)
+            if ev.global_eval_funcs:
+                assert np.allclose(got["glob"][ok, :1], ref["glob"][ok], rtol=1e-6, atol=1e-8), tag
+            if mat is not None:
+                # locked oscillators have |cor| within rounding of 1, the open end of the last bin: whether a pair
+                # is counted there or dropped hangs on the last bit, so the last bin (and rows whose whole mass sits
+                # in it, whose ECDF is 0/0 or 0,...,0,1) are left out of the comparison
+                g, r = got["matrix"][ok], ref["matrix"][ok]
+                if mat == [m.correlation_hist]:
+                    assert np.array_equal(g[:, :-1], r[:, :-1]), tag
+                    assert np.all(g[:, -1] <= ndim * (ndim - 1)) and np.all(g >= 0), tag
+                else:
+                    spread = np.nan_to_num(r[:, -2], nan=0.0) > 0
+                    unaffected = spread & (np.abs(g[:, -2] - r[:, -2]) < 1e-12)
+                    assert np.all(np.abs(g[unaffected] - r[unaffected]) < 1e-12), tag
+                    assert unaffected.sum() >= 0.5 * spread.sum(), (tag, spread, unaffected)
+    assert n_fail_cases >= 1  # the maxiters mode really produced failed runs somewhere
