@@ -350,3 +350,40 @@ def test_lane_source_option_combinations(mcbb, orc, emul):
                     assert np.all(np.abs(g[unaffected] - r[unaffected]) < 1e-12), tag
                     assert unaffected.sum() >= 0.5 * spread.sum(), (tag, spread, unaffected)
     assert n_fail_cases >= 1  # the maxiters mode really produced failed runs somewhere
+
+
+def test_lane_source_failure_retcodes(mcbb, orc, emul):
+    """Integrator failures are data (retcode per run): MaxIters, DtLessThanMin (a large dtmin against a tight tolerance)
+    and Unstable (a diverging Roessler network) — same codes, same step counts and NaN measures as the oracle; the
+    escaping logistic orbit (r > 4) stays `Success` with non-finite measures."""
+    m, abi = mcbb, mcbb.abi
+    prob, _ = cases.c1_problem(m, n_ics=4, seed=3, eval_funcs=(m.mean, m.std))
+    seen = set()
+    for kw in (dict(maxiters=7), dict(dtmin=0.5, reltol=1e-10, abstol=1e-10), dict(dtmax=0.01, maxiters=500)):
+        ctx = _setup(m, prob, **kw)
+        got, ref = emul(*ctx), orc.solve_features(*ctx)
+        assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["nsteps"], ref["nsteps"]), kw
+        assert np.all(ref["retcode"] != abi.RET_SUCCESS) and np.isnan(got["feat"]).all(), kw
+        seen |= set(ref["retcode"].tolist())
+    assert {abi.RET_MAXITERS, abi.RET_DTLESSTHANMIN} <= seen
+    Nr = 3
+    Lp = 2 * np.eye(Nr) - np.roll(np.eye(Nr), 1, 0) - np.roll(np.eye(Nr), -1, 0)
+    pars = m.roessler_parameters(0.2 * np.ones(Nr), 0.2 * np.ones(Nr), 5.7 * np.ones(Nr), 0.05, Lp, Nr)
+    rp = m.ODEProblem(m.roessler_network, np.zeros(3 * Nr), (0.0, 60.0), pars)
+    rng = np.random.default_rng(1)
+    probr = m.DEMCBBProblem(rp, lambda: rng.uniform(-1, 1), 2, pars, ("K", [0.05, 60.0, 200.0]),
+                            m.EvalOdeRun(eval_funcs=(m.mean, m.std)), 0.5)
+    ctx = _setup(m, probr)
+    got, ref = emul(*ctx), orc.solve_features(*ctx)
+    assert np.array_equal(got["retcode"], ref["retcode"]) and np.array_equal(got["nsteps"], ref["nsteps"])
+    assert (ref["retcode"] == abi.RET_SUCCESS).any() and (ref["retcode"] != abi.RET_SUCCESS).any(), ref["retcode"]
+    bad = ref["retcode"] != abi.RET_SUCCESS
+    assert np.isnan(got["feat"][bad]).all() and np.isfinite(got["feat"][~bad]).all()
+    parsl = m.logistic_parameters(4.5)
+    dp = m.DiscreteProblem(m.logistic, np.array([0.5]), (0.0, 500.0), parsl)
+    probl = m.DEMCBBProblem(dp, lambda: 0.3, 2, parsl, ("r", [3.9, 4.5]), m.eval_ode_run, 0.8)
+    ctx = _setup(m, probl)
+    got, ref = emul(*ctx), orc.solve_features(*ctx)
+    assert np.array_equal(got["retcode"], ref["retcode"]) and np.all(ref["retcode"] == abi.RET_SUCCESS)
+    assert np.array_equal(np.isfinite(got["feat"]), np.isfinite(ref["feat"]))
+    assert np.isfinite(got["feat"][probl.par[:, 0] < 4]).all() and not np.isfinite(got["feat"][probl.par[:, 0] > 4]).all()
