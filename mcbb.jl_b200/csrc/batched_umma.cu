@@ -31,6 +31,7 @@
 
 #include "fixedpoint.cuh"
 #include "lane_core.cuh"
+#include "umma_math.cuh"  // after lane_core.cuh: keeps the constant-bank layout of the kernel
 
 namespace mcbb {
 
@@ -140,57 +141,6 @@ __device__ __forceinline__ double um_warp_sum(double p) {
     return p;
 }
 
-// save times t_save (eval_ode_run's saveat grid), read with uniform or near-uniform indices: constant bank instead of
-// 8 n_t bytes of every CTA's shared memory
-constexpr int UM_MAX_NT = 4096;
-static __constant__ double c_um_ts[UM_MAX_NT];
-
-// sincos / fixed-point constants live in the constant bank: DFMA takes them as c[bank][offset] operands, no
-// per-use immediate moves
-static __constant__ double c_um[20] = {
-    0.6366197723675814,       // 0  2/pi
-    6755399441055744.0,       // 1  1.5 * 2^52
-    1.5707963267948966,       // 2  pi/2 high
-    6.123233995736766e-17,    // 3  pi/2 low
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
-    8.33333333332248946124e-03, -1.66666666666666324348e-01,                                       // 4..9  sin kernel
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
-    -1.38888888888741095749e-03, 4.16666666666666019037e-02,                                       // 10..15 cos kernel
-    1125899906842624.0,       // 16 2^50
-    0., 0., 0.};
-
-// G independent sincos chains written side by side so that the scheduler interleaves them (one basic block);
-// same arithmetic as sincos_fast2 (fixedpoint.cuh)
-template <int G>
-__device__ __forceinline__ void um_sincos_vec(const double (&x)[G], double* s, double* c) {
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const double qd = fma(x[i], c_um[0], c_um[1]);
-        const int q = __double2loint(qd);
-        const double qf = qd - c_um[1];
-        double r = fma(-qf, c_um[2], x[i]);
-        r = fma(-qf, c_um[3], r);
-        const double z = r * r;
-        double ps = fma(z, c_um[4], c_um[5]);
-        ps = fma(z, ps, c_um[6]);
-        ps = fma(z, ps, c_um[7]);
-        ps = fma(z, ps, c_um[8]);
-        ps = fma(z, ps, c_um[9]);
-        const double sr = fma(z * r, ps, r);
-        double pc = fma(z, c_um[10], c_um[11]);
-        pc = fma(z, pc, c_um[12]);
-        pc = fma(z, pc, c_um[13]);
-        pc = fma(z, pc, c_um[14]);
-        pc = fma(z, pc, c_um[15]);
-        const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-        const double a = (q & 1) ? cr : sr;
-        const double b = (q & 1) ? sr : cr;
-        // quadrant signs on the integer pipe (the FP64 pipe is the scarce one)
-        s[i] = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
-        c[i] = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
-    }
-}
-
 // Tsit5 dense-output weights b_q(theta) (OrdinaryDiffEq tsit_interpolants): b_0 = th (1 + th (A + th (B + th C))),
 // b_q = th^2 (A + th (B + th C)) for q = 1..6; lane q of a warp evaluates polynomial q
 static __constant__ double c_um_bth[7][3] = {
@@ -201,25 +151,6 @@ static __constant__ double c_um_bth[7][3] = {
     {37.50931341651104, -88.1789048947664, 47.37952196281928},
     {-27.896526289197286, 65.09189467479366, -34.87065786149661},
     {1.5, -4., 2.5}};
-
-// x in [-1, 1] -> (low 32 bits, high 20 bits) of round(x 2^50) + 2^51, constants from the constant bank
-__device__ __forceinline__ void um_fixed52(const double x, unsigned& lo, unsigned& hi) {
-    const double t = fma(x, c_um[16], c_um[1]);
-    lo = (unsigned)__double2loint(t);
-    hi = (unsigned)__double2hiint(t) & 0xFFFFFu;
-}
-
-// sum_k v[k] 2^(8k) - deg 2^51 as a double (one rounding).  Digit sums are < 2^15 (<= 128 couplings of <= 255), so
-// three of them pack into 31 bits; one wide multiply-add joins the two packs, v6 and the degree only touch the
-// high word.  degh = deg << 19.
-__device__ __forceinline__ double um_recombine(const unsigned v0, const unsigned v1, const unsigned v2, const unsigned v3,
-                                               const unsigned v4, const unsigned v5, const unsigned v6, const int degh) {
-    const unsigned lo3 = v0 + (v1 << 8) + (v2 << 16);
-    const unsigned mid3 = v3 + (v4 << 8) + (v5 << 16);
-    const unsigned long long w = (unsigned long long)mid3 * 16777216ull + lo3;
-    const int hi = (int)(unsigned)(w >> 32) + ((int)(v6 << 16) - degh);
-    return (double)(long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)w);
-}
 
 // a / b for normal, well-scaled b without the compiler's slow-path branch: reciprocal seed, two Newton steps,
 // one residual correction (used only inside the step-size error norm)
