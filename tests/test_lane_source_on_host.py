@@ -387,3 +387,88 @@ def test_lane_source_failure_retcodes(mcbb, orc, emul):
     assert np.array_equal(got["retcode"], ref["retcode"]) and np.all(ref["retcode"] == abi.RET_SUCCESS)
     assert np.array_equal(np.isfinite(got["feat"]), np.isfinite(ref["feat"]))
     assert np.isfinite(got["feat"][probl.par[:, 0] < 4]).all() and not np.isfinite(got["feat"][probl.par[:, 0] > 4]).all()
+
+
+@pytest.fixture
+def cpu_engine(monkeypatch, mcbb, emul):
+    """Replaces the two functions of the host mirror that call the CUDA library by the host build of the lane source,
+    so that the mirror's own logic (solve: sorting, :Repeat, the response analysis; get_trajectory) runs in the CPU
+    suite.  Test-only: the product has no such path."""
+    api, abi = mcbb.api, mcbb.abi
+
+    def fake_solve(prob, t_save, alg, save_mode, kwargs):
+        psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+        o = api._solver_opts(prob, alg, kwargs)
+        ic = prob.ic
+        cplx = np.iscomplexobj(ic)
+        if cplx:
+            ic = np.stack([ic.real, ic.imag], axis=2).reshape(ic.shape[0], -1)
+        sv = None
+        if getattr(prob, "solver_par", None) is not None:
+            sv = (prob.solver_par, prob.par[:, 0])
+        r = emul(psys, o, pfeat, ic, prob.par, t_save, save_mode=save_mode, solver_var=sv)
+        saved = r["saved"]
+        if saved is not None and cplx:
+            saved = saved[:, 0::2] + 1j * saved[:, 1::2]
+        mat = r["matrix"] if pfeat.matrix_meas else None
+        glob = r["glob"] if pfeat.n_global else None
+        return r["feat"], mat, glob, r["retcode"], r["nsteps"], saved
+
+    monkeypatch.setattr(api, "_solve_b200", fake_solve)
+    monkeypatch.setattr(api, "custom_solve_b200", lambda prob, ts, alg=None, **kw: fake_solve(prob, ts, alg, 0, kw)[:5])
+    return mcbb
+
+
+def test_host_mirror_response_analysis_and_get_trajectory_on_cpu(cpu_engine, orc):
+    """solve() with the response analysis (eval_mc_prob.jl:202-257), get_trajectory and failure_handling = :Repeat —
+    the host mirror's logic end to end, the lane source standing in for the GPU — against the oracle composed from its
+    single-trajectory, featurize and distance functions."""
+    m = cpu_engine
+    eps, bounds, w_inner = 0.25, (1.0, 3.0), [1.0, 0.5, 1.0]
+    prob, _ = cases.c1_problem(m, n_ics=5, seed=29, eval_funcs=(m.mean, m.std))
+    prob.eval_ode_func = m.EvalOdeRun(eval_funcs=(m.mean, m.std),
+                                      continuation=m.ContinuationResponse(eps, bounds, w_inner, N_t=200))
+    sol = m.solve(prob)
+    assert (sol.N_meas_dim, sol.N_meas_global) == (2, 2) and np.all(np.diff(prob.par[:, 0]) >= 0)
+    psys, pfeat = prob.pars.pack(prob.par_names), m.EvalOdeRun(eval_funcs=(m.mean, m.std)).pack()
+    o = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan)
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    n = prob.N_mc
+    end = np.stack([orc.trajectory(psys, o, prob.ic[i], prob.par[i], ts)[0][:, -1] for i in range(n)])
+    p0 = prob.par[:, 0]
+    par3 = np.stack([np.maximum(p0 - eps, bounds[0]), p0, np.minimum(p0 + eps, bounds[1])], axis=1)
+    t0, t1 = prob.p.tspan
+    span2 = (t0, t0 + 0.15 * (t1 - t0))
+    o2 = m.abi.solver_opts(m.abi.ALG_TSIT5, span2)
+    ts2 = m.tsave_array(m.ODEProblem(m.kuramoto_network, np.zeros(6), span2, prob.pars), 200, 0.1)
+    ref3 = orc.solve_features(psys, o2, pfeat, np.repeat(end, 3, axis=0), par3.reshape(-1, 1), ts2)["feat"]
+    X = np.concatenate([ref3[:, :, 0], ref3[:, :, 1], par3.reshape(-1, 1)], axis=1)
+    want = np.array([[orc.distance_matrix(X[3 * i:3 * i + 3], [6, 6, 1], w_inner)[a, a + 1] for a in (0, 1)]
+                     for i in range(n)])
+    assert np.allclose(sol.glob, want, rtol=1e-6, atol=1e-9), np.abs(sol.glob - want).max()
+    assert np.all(sol.glob[par3[:, 0] == p0, 0] == 0.0)  # clipped onto p itself: identical twin runs
+    # get_trajectory: a given run, and a random member of a "cluster"
+    tr = m.get_trajectory(prob, sol, 3)
+    ref = orc.trajectory(psys, o, prob.ic[3], prob.par[3], ts)[0]
+    assert np.allclose(np.asarray(tr), ref, rtol=1e-9, atol=1e-9) and tr.i_run == 3 and len(tr) == 400
+    ca = np.arange(n) % 2
+    db = m.DbscanResult(np.array([1]), ca, np.array([int((ca == 1).sum())]))
+    tr2, sub, i_run = m.get_trajectory(prob, sol, db, 2, only_sol=False, rng=np.random.default_rng(1))
+    assert ca[i_run] == 1 and sub.N_mc == 1
+    # failure_handling = :Repeat: runs that hit maxiters get fresh initial conditions until they pass, at most 10 times
+    draws = {"n": 0}
+    rng = np.random.default_rng(4)
+
+    def ic_gen():
+        draws["n"] += 1
+        return rng.uniform(-np.pi, np.pi)
+    pars = m.kuramoto_network_parameters(0.5, np.full(6, 0.5), 6, np.ones((6, 6)))
+    rp = m.ODEProblem(m.kuramoto_network, np.zeros(6), (0.0, 40.0), pars)
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std), failure_handling="Repeat")
+    probr = m.DEMCBBProblem(rp, ic_gen, 6, pars, ("K", lambda: 2.0), ev, 0.9)
+    first = draws["n"]
+    with pytest.raises(m.MCBBError, match="More than 10 Repeats"):
+        m.solve(probr, maxiters=5)  # nothing can succeed in five steps
+    assert draws["n"] == first + 10 * 6 * 6  # ten redraws of all six runs, six dimensions each
+    solr = m.solve(probr, maxiters=100000)
+    assert np.all(solr.retcode == 0)
