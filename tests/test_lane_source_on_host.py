@@ -472,3 +472,41 @@ def test_host_mirror_response_analysis_and_get_trajectory_on_cpu(cpu_engine, orc
     assert draws["n"] == first + 10 * 6 * 6  # ten redraws of all six runs, six dimensions each
     solr = m.solve(probr, maxiters=100000)
     assert np.all(solr.retcode == 0)
+
+
+def test_host_mirror_parameter_variations_on_cpu(cpu_engine, orc):
+    """solve() for the three kinds of parameter variation — one system parameter, several (MultiDimParameterVar) and a
+    solver option (SolverParameterVar) — through the host mirror with the lane source as the engine: results come back
+    sorted by the first parameter column and equal the oracle run by run."""
+    m = cpu_engine
+    rng = np.random.default_rng(6)
+    N = 5
+    E = cases.ring_incidence(N, [(0, 2)])
+    pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, np.array([1.0, -1.0, 1.0, -1.0, 0.0]))
+    rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), (0.0, 30.0), pars)
+    ev = m.EvalOdeRun(state_filter=list(range(N + 1, 2 * N + 1)), eval_funcs=(m.mean, m.std))
+    variations = [("coupling", lambda: rng.uniform(0.5, 3.0)),
+                  [("coupling", lambda: rng.uniform(0.5, 3.0)), ("damping", lambda: rng.uniform(0.05, 0.4))],
+                  m.SolverParameterVar("reltol", lambda: 10.0 ** rng.uniform(-7, -3))]
+    for pv in variations:
+        prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-1.0, 1.0), 8, pars, pv, ev, 0.6)
+        ic0, par0 = prob.ic.copy(), prob.par.copy()
+        sol = m.solve(prob)
+        idx = np.argsort(par0[:, 0], kind="stable")
+        assert np.array_equal(prob.par, par0[idx]) and np.array_equal(prob.ic, ic0[idx])
+        psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+        ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+        same_steps = 0
+        for i in range(prob.N_mc):
+            kw = {"reltol": float(prob.par[i, 0])} if prob.solver_par else {}
+            o = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan, **kw)
+            ref = orc.solve_features(psys, o, pfeat, prob.ic[i:i + 1], prob.par[i:i + 1], ts)
+            # a step whose error estimate sits at the accept threshold may flip between two correct FP64
+            # implementations (DESIGN.md, step-size-controller sensitivity): such a run is compared loosely
+            if np.array_equal(sol.nsteps[i], ref["nsteps"][0]):
+                same_steps += 1
+                assert np.allclose(sol.feat[i], ref["feat"][0], rtol=1e-6, atol=1e-7), i
+            else:
+                assert abs(int(sol.nsteps[i, 0]) - int(ref["nsteps"][0, 0])) <= 0.1 * ref["nsteps"][0, 0]
+                assert np.allclose(sol.feat[i], ref["feat"][0], rtol=2e-2, atol=2e-2), i
+        assert same_steps >= 6, same_steps
