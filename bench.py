@@ -3,17 +3,21 @@
 
     python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
     python bench.py --impl reference ...                      the CPU arm (the oracle restatement; Julia is absent)
+    python bench.py --config C4 ...                           the Stuart-Landau pipeline (BASELINE.json configs[3])
 
-Workload (BASELINE.json configs[4], "C5"): Kuramoto network N=100, Erdos-Renyi p=0.2 adjacency, w~N(0.5,0.1),
+Workload C5 (BASELINE.json configs[4]): Kuramoto network N=100, Erdos-Renyi p=0.2 adjacency, w~N(0.5,0.1),
 ICs~U(-pi,pi)^100, K~U(0,8), tspan (0,1000), tail 0.9 (N_t=400), Tsit5 abstol 1e-6 / reltol 1e-3, measures
 [mean, std] with cyclic_setback.  One STEP = integrate + featurize one batch of `--runs-per-gpu` trajectories per
 GPU (default 125 000 = 10^6 / 8, so that --gpus 8 is the 10^6-run configuration; weak scaling).
 `value` = trajectories/s with inputs resident in HBM; `e2e` = the same through the host C-ABI call
-(mcbb_solve_features: pinned host buffers, H2D of ic/par and D2H of the features inside the timed region).
-After the timed steps the features are all-gathered and DBSCAN-clustered once (fused, row-sharded): `cluster`.
+(mcbb_solve_features: pinned host buffers, H2D of ic/par and D2H of the features inside the timed region; also
+measured with pageable numpy arrays, what a Julia `ccall` passes).  After the timed steps the whole pipeline is run
+once more as ONE wall-clock region (`pipeline_s`: H2D -> solve -> feature all-gather -> sort -> eps from the
+reference's KNN heuristic -> fused DBSCAN -> labels D2H), and the cluster stage gets its own roofline.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -31,20 +35,58 @@ TSPAN = (0.0, 1000.0)
 TAIL = 0.9
 N_T = 400
 SINCOS_FLOPS = 40  # sincos_fast: 20 FMA-class FP64 instructions
+METRIC = "trajectories/sec (integrate+featurize)"
+WORKLOAD = ("C5 kuramoto_network N=100 ER p=0.2 (seed 10), w~N(0.5,0.1), ic~U(-pi,pi)^100, K~U(0,8), tspan (0,1000), "
+            "tail 0.9, N_t=400, Tsit5 abstol 1e-6 reltol 1e-3, measures [mean,std] cyclic_setback")
 
 
-def make_inputs(m, n_runs, seed_offset):
-    """Synthetic C5 inputs for one rank (numpy PCG64, seeded per rank)."""
-    from tests import cases
-    A = cases.erdos_renyi(N_OSC, 0.2, 10)
+def config_dict(world, runs_per_gpu):
+    """Identical for both arms (the reference arm times a bounded sample of this configuration per step)."""
+    return {"workload": WORKLOAD, "runs_per_gpu_per_step": runs_per_gpu, "runs_per_step": world * runs_per_gpu,
+            "l2": "flushed between timed steps"}
+
+
+def load_abi():
+    """mcbb.jl_b200/_abi.py alone: ctypes declarations, loads no library (shared by both arms)."""
+    import importlib.util
+    name = "mcbb_jl_b200._abi"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "mcbb.jl_b200", "_abi.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def erdos_renyi(N, p, seed):
+    rng = np.random.default_rng(seed)
+    U = np.triu(rng.random((N, N)) < p, 1)
+    return (U | U.T).astype(np.float64)
+
+
+def make_system(abi):
+    """The C5 system / featurizer / solver descriptors from the ABI declarations alone."""
+    A = erdos_renyi(N_OSC, 0.2, 10)
     w = np.random.default_rng(11).normal(0.5, 0.1, N_OSC)
-    pars = m.kuramoto_network_parameters(0.5, w, N_OSC, A)
+    psys = abi.PackedSystem(abi.SYS_KURAMOTO_NETWORK, N_OSC, N_OSC, [0.5], [0], mat_a=A, vec_a=w)
+    pfeat = abi.PackedFeat([abi.MEAS_MEAN, abi.MEAS_STD], cyclic_setback=True)
+    opts = abi.solver_opts(abi.ALG_TSIT5, TSPAN)
+    return A, psys, pfeat, opts
+
+
+def make_runs(n_runs, seed_offset):
+    """Synthetic C5 initial conditions and parameters (numpy PCG64, seeded per rank / per sample)."""
     rng = np.random.default_rng(1000 + seed_offset)
     ic = np.asfortranarray(rng.uniform(-np.pi, np.pi, size=(n_runs, N_OSC)))
     par = np.asfortranarray(rng.uniform(0.0, 8.0, size=(n_runs, 1)))
-    psys = pars.pack(["K"])
-    pfeat = m.EvalOdeRun(eval_funcs=(m.mean, m.std), cyclic_setback=True).pack()
-    opts = m.abi.solver_opts(m.abi.ALG_TSIT5, TSPAN)
+    return ic, par
+
+
+def make_inputs(m, n_runs, seed_offset):
+    """Our arm: descriptors + runs + the product's tsave_array."""
+    A, psys, pfeat, opts = make_system(m.abi)
+    ic, par = make_runs(n_runs, seed_offset)
     n = C.c_int32(0)
     m.check(m.lib().mcbb_tsave_array(C.byref(opts), N_T, TAIL, m.abi.c_double_p(), C.byref(n)))
     ts = np.zeros(n.value)
@@ -97,54 +139,57 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline(m, A, psys, pfeat, opts, ts, n_sample, seed_offset=0):
-    """The oracle restatement (literal N^2-sin formulas, OpenMP over trajectories) on a bounded sample."""
-    from oracle import oracle as orc
-    rng = np.random.default_rng(1000 + seed_offset)
-    ic = np.asfortranarray(rng.uniform(-np.pi, np.pi, size=(n_sample, N_OSC)))
-    par = np.asfortranarray(rng.uniform(0.0, 8.0, size=(n_sample, 1)))
+def cpu_baseline(orc, psys, pfeat, opts, ts, n_sample, seed_offset=0):
+    """The oracle restatement (literal N^2-sin formulas, OpenMP over trajectories) on a bounded sample.
+    Returns (traj/s, seconds, threads, oracle result, ic, par)."""
+    ic, par = make_runs(n_sample, seed_offset)
     threads = os.cpu_count() or 1  # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     t0 = time.perf_counter()
-    orc.solve_features(psys, opts, pfeat, ic, par, ts, n_threads=threads)
+    res = orc.solve_features(psys, opts, pfeat, ic, par, ts, n_threads=threads)
     dt = time.perf_counter() - t0
-    return n_sample / dt, dt, threads
+    return n_sample / dt, dt, threads, res, ic, par
 
 
 def run_reference(args):
     """--impl reference: Julia is not installed here or on the GPU box, so the reference arm is the CPU oracle
     (oracle/mcbb_oracle.c, a restatement of the reference's DifferentialEquations.jl + StatsBase path) on all
-    host threads, on a bounded sample of the same workload per step."""
+    host threads, on a bounded sample of the same workload per step.  Loads oracle/_ref/libmcbb_oracle.so and the
+    ctypes declarations only: the product library is never touched on this arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from __graft_entry__ import load_package
-    m = load_package()
+    abi = load_abi()
     from oracle import oracle as orc
     orc.build()
     n_sample = args.cpu_sample
-    A, _, _, psys, pfeat, opts, ts = make_inputs(m, 8, 0)
+    _, psys, pfeat, opts = make_system(abi)
+    ts = orc.tsave_array(opts, N_T, TAIL)
     for w in range(args.warmup):
-        cpu_baseline(m, A, psys, pfeat, opts, ts, max(8, n_sample // 8), seed_offset=100 + w)
+        cpu_baseline(orc, psys, pfeat, opts, ts, max(8, n_sample // 8), seed_offset=100 + w)
     t_tot, n_tot, threads = 0.0, 0, 1
     for k in range(args.steps):
-        v, dt, threads = cpu_baseline(m, A, psys, pfeat, opts, ts, n_sample, seed_offset=k)
+        _, dt, threads, _, _, _ = cpu_baseline(orc, psys, pfeat, opts, ts, n_sample, seed_offset=k)
         t_tot += dt
         n_tot += n_sample
     value = n_tot / t_tot
+    assert "mcbb_jl_b200._lib" not in sys.modules, "the reference arm must not load the product library"
     line = {
-        "impl": "reference", "metric": "trajectories/sec (integrate+featurize)", "value": value,
-        "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C5 kuramoto_network N=100 ER p=0.2, tspan (0,1000), tail 0.9, Tsit5 1e-6/1e-3, "
-                               "measures [mean,std] cyclic_setback", "runs_per_step": n_sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.gpus, args.runs_per_gpu),
         "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": threads, "kind": "port",
-                         "sample": "%d trajectories per step of the same C5 workload (oracle restatement, not Julia)"
+                         "sample": "%d trajectories per step of the same C5 workload (oracle restatement of the "
+                                   "reference's CPU path, all host threads; Julia itself is not installable here)"
                                    % n_sample},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def labels_hash(t):
+    return hashlib.sha1(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes()).hexdigest()[:16]
 
 
 def main():
@@ -153,11 +198,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C5", choices=["C5", "C4"])
     ap.add_argument("--runs-per-gpu", type=int, default=125000)
     ap.add_argument("--cpu-sample", type=int, default=384)
     ap.add_argument("--no-cluster", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.config == "C4":
+        from tools import bench_c4
+        return bench_c4.main(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -194,6 +243,7 @@ def main():
     par_d = torch.from_numpy(np.ascontiguousarray(par.T)).to(dev)
     ts_d = torch.from_numpy(ts).to(dev)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream_ptr = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,39 +281,48 @@ def main():
     ms_total = float(ms_total.item())
     value = world * R * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end through the host C-ABI (pinned host buffers, H2D + D2H inside the timed region) ----------
-    ic_h = torch.from_numpy(ic).pin_memory() if False else torch.empty((N_OSC, R), dtype=torch.float64).pin_memory()
+    # ---- end to end through the host C-ABI (host buffers, H2D + D2H inside the timed region) --------------------
+    nf = pfeat.n_filter(psys)
+    dp, ip, lp = m.abi.c_double_p, m.abi.c_int32_p, m.abi.c_int64_p
+    ic_h = torch.empty((N_OSC, R), dtype=torch.float64).pin_memory()
     ic_h.copy_(torch.from_numpy(np.ascontiguousarray(ic.T)))
     par_h = torch.empty((1, R), dtype=torch.float64).pin_memory()
     par_h.copy_(torch.from_numpy(np.ascontiguousarray(par.T)))
-    nf = pfeat.n_filter(psys)
     feat_h = torch.empty((pfeat.n_meas * nf, R), dtype=torch.float64).pin_memory()
     ret_h = torch.empty((R,), dtype=torch.int32).pin_memory()
     ns_h = torch.empty((2, R), dtype=torch.int64).pin_memory()
-    dp, ip, lp = m.abi.c_double_p, m.abi.c_int32_p, m.abi.c_int64_p
 
-    def step_e2e():
+    def call_host(ic_p, par_p, feat_p, ret_p, ns_p):
         m.check(m.lib().mcbb_solve_features(
-            C.byref(psys.desc), C.byref(opts), C.byref(pfeat.opts), R, C.cast(ic_h.data_ptr(), dp),
-            C.cast(par_h.data_ptr(), dp), ts.ctypes.data_as(dp), len(ts), C.cast(feat_h.data_ptr(), dp), dp(), dp(),
-            C.cast(ret_h.data_ptr(), ip), C.cast(ns_h.data_ptr(), lp)))
+            C.byref(psys.desc), C.byref(opts), C.byref(pfeat.opts), R, C.cast(ic_p, dp), C.cast(par_p, dp),
+            ts.ctypes.data_as(dp), len(ts), C.cast(feat_p, dp), dp(), dp(), C.cast(ret_p, ip), C.cast(ns_p, lp)))
 
-    step_e2e()
-    barrier()
+    def time_host(fn, steps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * R * steps / float(t.item())
+
     e2e_steps = max(2, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * R * e2e_steps / float(t_e2e.item())
+    e2e_value = time_host(lambda: call_host(ic_h.data_ptr(), par_h.data_ptr(), feat_h.data_ptr(), ret_h.data_ptr(),
+                                            ns_h.data_ptr()), e2e_steps)
     same = bool(torch.equal(torch.nan_to_num(feat_h), torch.nan_to_num(feat_d.cpu())))
+    # pageable numpy arrays, exactly what a Julia ccall hands over (Array{Float64} is ordinary malloc'ed memory)
+    feat_p = np.empty((pfeat.n_meas * nf, R))
+    ret_p = np.empty(R, dtype=np.int32)
+    ns_p = np.empty((2, R), dtype=np.int64)
+    e2e_pageable = time_host(lambda: call_host(ic.ctypes.data, par.ctypes.data, feat_p.ctypes.data, ret_p.ctypes.data,
+                                               ns_p.ctypes.data), e2e_steps)
     h2d = ic_h.numel() * 8 + par_h.numel() * 8 + len(ts) * 8
     d2h = feat_h.numel() * 8 + ret_h.numel() * 4 + ns_h.numel() * 8
 
-    # ---- roofline of the dominant kernel (k_solve_batched: FP64 FMA pipe) ------------------------------------
+    # ---- roofline of the dominant kernel (FP64 FMA pipe) -----------------------------------------------------
     peak = C.c_double(0.0)
     mhz = C.c_double(0.0)
     m.check(m.lib().mcbb_measure_fp64_fma_peak(C.byref(peak), C.byref(mhz)))
@@ -272,11 +331,14 @@ def main():
     traffic = None
     try:  # DRAM traffic of the same kernel from the committed ncu --set full capture (one launch of 125 000 runs)
         import csv
-        rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_k_solve_batched_umma.csv")))}
+        src = next(p for p in ("r2_ncu_k_solve_batched_umma.csv", "r1_ncu_k_solve_batched_umma.csv")
+                   if os.path.exists(os.path.join(ROOT, "profiles", p)))
+        rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", src)))}
         unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
         ncu_runs = 125000
-        traffic_ncu = {"runs_per_launch": ncu_runs, "dram_bytes": float(rd[2]) * unit[rd[1]] + float(wr[2]) * unit[wr[1]],
+        traffic_ncu = {"runs_per_launch": ncu_runs, "source": "profiles/" + src,
+                       "dram_bytes": float(rd[2]) * unit[rd[1]] + float(wr[2]) * unit[wr[1]],
                        "algorithmic_bytes": ncu_runs * (N_OSC * 8 + 8 + 2 * N_OSC * 8 + 4 + 16)}
         if R == ncu_runs:
             traffic = traffic_ncu["dram_bytes"]
@@ -286,17 +348,14 @@ def main():
     roofline = {
         "bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value > 0 else None, "traffic": traffic,
-        "kernel": "k_solve_batched_umma<6,4> (tcgen05.mma kind::i8, A and accumulators in TMEM)", "traffic_ncu": traffic_ncu,
+        "kernel": "k_solve_batched_umma (tcgen05.mma kind::i8, A and accumulators in TMEM)", "traffic_ncu": traffic_ncu,
         "peak_source": "measured in this run by the library's DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 "
                        "entry; nominal B200 ~37 TFLOP/s)",
         "achieved_dense_equiv": fl_dense / (ms_total * 1e-3) / world / 1e12,
-        "note": "achieved = algorithmic FP64 flops of the zero-skipping factored algorithm (DESIGN.md §5) / CUDA-event "
-                "time of the kernel launches; the HBM roofline named by the contract does not bound this kernel "
-                "(arithmetic intensity > 1e4 flop/B)",
+        "note": "achieved = algorithmic FP64 flops of the zero-skipping factored algorithm (DESIGN.md §5) x the kernel's "
+                "step attempts (checked against the oracle's: steps_ratio) / CUDA-event time of the kernel launches; "
+                "the HBM roofline named by the contract does not bound this kernel (arithmetic intensity > 1e4 flop/B)",
     }
-
-    # tensor-pipe view of the same kernel: every right-hand-side evaluation of a CTA (6 trajectories) is one
-    # D[128 x 96] += A[128 x 128] B[128 x 96] int8 GEMM (zero padding of rows / K / the two pad columns included)
     evals = 6.0 * float(nst.item()) * args.steps / world  # per GPU in the timed region
     int8_ops = evals * (2.0 * 128 * 128 * 16)             # 16 accumulator columns per trajectory
     roofline["tensor"] = {
@@ -306,73 +365,183 @@ def main():
         "note": "the tensor cores replace 54 % of the algorithmic FP64 flops; they are not the bound of the kernel",
     }
 
-    # ---- cluster time at N runs (fused row-sharded DBSCAN on the all-gathered features) -----------------------
-    cluster = None
-    if not args.no_cluster:
-        Xl = torch.cat([feat_d, par_d], dim=0).contiguous()  # [F, R] features + parameter column
+    # ---- the whole pipeline as one wall-clock region + the cluster stage's own numbers ------------------------
+    gl = np.array([nf, nf, 1], dtype=np.int32)
+    gw = np.array([1.0, 0.5, 1.0])
+    minpts = 20
+
+    def knn_eps(X):
+        """median(KNN_dist_relative(D, 0.005)) (src/eval_clustering.jl:1526-1553, docs/src/basic_usage.md:72) on a
+        10^4-run subsample, identical on every rank."""
+        n_all = X.shape[1]
+        ms_ = min(10000, n_all)
+        sub = torch.from_numpy(np.sort(np.random.default_rng(7).choice(n_all, size=ms_, replace=False))).to(dev)
+        Xs = X[:, sub].contiguous()
+        K = max(1, int(round(0.005 * ms_)))
+        cum = torch.empty((ms_,), dtype=torch.float64, device=dev)
+        m.check(m.lib().mcbb_knn_dist_features_dev(C.c_void_p(Xs.data_ptr()), ms_, 3, gl.ctypes.data_as(ip),
+                                                   gw.ctypes.data_as(dp), 1, K, 0, C.c_void_p(0),
+                                                   C.c_void_p(cum.data_ptr()), stream_ptr()))
+        return float(cum.median().item()), K, ms_
+
+    def pipeline(trace=None):
+        """H2D -> solve -> all-gather -> sort by parameter -> eps -> fused (row-sharded) DBSCAN -> labels D2H."""
+        t = {}
+        barrier()
+        t0 = time.perf_counter()
+        icd = ic_h.to(dev, non_blocking=True)
+        pard = par_h.to(dev, non_blocking=True)
+        f_d, _, _, _ = m.dist.solve_features_device(psys, opts, pfeat, icd, pard, ts_d)
+        Xl = torch.cat([f_d, pard], dim=0)
+        torch.cuda.synchronize()
+        t["h2d_solve_s"] = time.perf_counter() - t0
         if dist is not None:
             parts = [torch.empty_like(Xl) for _ in range(world)]
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
             dist.all_gather(parts, Xl)
+            X = torch.cat(parts, dim=1)
             torch.cuda.synchronize()
-            t_gather = time.perf_counter() - t0
-            X = torch.cat(parts, dim=1).contiguous()
         else:
-            X, t_gather = Xl, 0.0
+            X = Xl
+        t["allgather_s"] = time.perf_counter() - t0 - t["h2d_solve_s"]
         X = torch.nan_to_num(X, nan=1e30)
-        # MCBB.solve sorts the runs by parameter before any clustering (sort!, setup_mc_prob.jl:1124-1126):
+        # MCBB.solve sorts the runs by parameter before any clustering (sort!, setup_mc_prob.jl:520-536):
         # stable sort on the parameter row, identical on every rank
         order = torch.sort(X[-1], stable=True).indices
         X = X[:, order].contiguous()
-        n_all = X.shape[1]
-        gl = np.array([nf, nf, 1], dtype=np.int32)
-        gw = np.array([1.0, 0.5, 1.0])
-        # eps: median distance to the 0.5 %-th nearest neighbour on a 4096-run subsample (KNN_dist_relative's
-        # rel_K = 0.005, eval_clustering.jl:1526-1553), identical on every rank
-        sub = torch.from_numpy(np.random.default_rng(7).choice(n_all, size=min(4096, n_all), replace=False)).to(dev)
-        Xs = X[:, sub].contiguous()
-        ms_ = Xs.shape[1]
-        Ds = torch.empty((ms_, ms_), dtype=torch.float64, device=dev)
-        m.check(m.lib().mcbb_distance_matrix_dev(C.c_void_p(Xs.data_ptr()), ms_, 3, gl.ctypes.data_as(ip),
-                                                 gw.ctypes.data_as(dp), C.c_void_p(Ds.data_ptr()),
-                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        kth = max(2, int(round(0.005 * ms_)))
-        eps = float(torch.sort(Ds, dim=0).values[kth].median().item())
-        minpts = 20
-        barrier()
-        t0 = time.perf_counter()
+        eps, K, n_sub = knn_eps(X)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        t["sort_eps_s"] = t1 - t0 - t["h2d_solve_s"] - t["allgather_s"]
         if world > 1:
             a_, s_, c_ = m.dist.dbscan_features_sharded(X, gl, gw, eps, minpts, rank, world, dist)
         else:
             a_, s_, c_ = m.dist.dbscan_features_device(X, gl, gw, eps, minpts)
+        labels = a_.cpu()
+        torch.cuda.synchronize()
+        t["dbscan_labels_s"] = time.perf_counter() - t1
         barrier()
-        t_cl = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        t["pipeline_s"] = time.perf_counter() - t0
+        return t, X, eps, K, n_sub, a_, s_, c_, labels
+
+    cluster = None
+    pipe = None
+    if not args.no_cluster:
+        pipeline()  # first pass allocates the DBSCAN scratch (reported separately as the cold run would mislead)
+        m.check(m.lib().mcbb_pair_feature_counter(1, None, stream_ptr()))
+        t, X, eps, K, n_sub, a_, s_, c_, labels = pipeline()
+        pf = C.c_int64(0)
+        m.check(m.lib().mcbb_pair_feature_counter(0, C.byref(pf), stream_ptr()))
+        # the counter also saw the 10^4-run eps subsample (materialised blocks): n_sub^2/2-ish pairs x F, negligible
+        tt = torch.tensor([t[k] for k in ("h2d_solve_s", "allgather_s", "sort_eps_s", "dbscan_labels_s", "pipeline_s")]
+                          + [float(pf.value)], dtype=torch.float64, device=dev)
+        tsum = tt.clone()
         if dist is not None:
-            dist.all_reduce(t_cl, op=dist.ReduceOp.MAX)
-        cluster = {"n_runs": int(n_all), "time_s": float(t_cl.item()), "allgather_s": t_gather, "eps": eps,
-                   "minpts": minpts, "n_clusters": int(s_.numel()), "n_noise": int((a_ == 0).sum().item()),
-                   "n_features": int(X.shape[0]),
-                   "pairs_per_s": 0.5 * n_all * (n_all - 1) / float(t_cl.item())}
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        n_all = int(X.shape[1])
+        Ftot = int(X.shape[0])
+        t_cl = float(tt[3].item())
+        executed = float(tsum[5].item())  # pair x feature terms over all ranks
+        dadd_peak = peak.value / 2.0  # T instr/s: a DADD occupies the pipe like a DFMA and counts one flop
+        pipe = {"pipeline_s": float(tt[4].item()), "h2d_solve_s": float(tt[0].item()),
+                "allgather_s": float(tt[1].item()), "sort_eps_s": float(tt[2].item()),
+                "dbscan_labels_s": t_cl, "n_runs": n_all,
+                "what": "wall clock, max over ranks: pinned H2D of ic/par -> integrate+featurize -> NCCL all-gather -> "
+                        "stable sort by parameter -> eps = median(KNN_dist_relative) on a 10^4 subsample -> fused "
+                        "(row-sharded) DBSCAN -> labels D2H"}
+        cluster = {"n_runs": n_all, "time_s": t_cl, "eps": eps, "eps_rule": "median(KNN_dist_relative(D,0.005)) on "
+                   "%d runs: cumulative distance to the K=%d nearest" % (n_sub, K), "minpts": minpts,
+                   "n_clusters": int(s_.numel()), "n_noise": int((a_ == 0).sum().item()), "n_features": Ftot,
+                   "largest_clusters": sorted([int(x) for x in c_.tolist()], reverse=True)[:5],
+                   "pairs_per_s": 0.5 * n_all * (n_all - 1) / t_cl, "labels_sha1": labels_hash(a_),
+                   "roofline": {"bound": "fp64_add", "unit": "TFLOP/s (FP64 add/sub)",
+                                "achieved": 2.0 * executed / t_cl / world / 1e12, "peak": dadd_peak,
+                                "frac": 2.0 * executed / t_cl / world / 1e12 / dadd_peak,
+                                "executed_pair_features": executed,
+                                "brute_force_pair_features": 2.0 * 0.5 * n_all * (n_all - 1) * Ftot,
+                                "note": "2 FP64 adds (x_i - x_j, accumulate |.|) per executed pair x feature term, counted "
+                                        "by the tiles themselves (early exits and saturation skips excluded), over the "
+                                        "wall time of the whole DBSCAN incl. compaction, sorts and the labels D2H; "
+                                        "peak = DFMA peak / 2"}}
+        if world == 1:
+            # worst case for the early exits: the same points in random order (no locality along the index)
+            perm = torch.from_numpy(np.random.default_rng(3).permutation(n_all)).to(dev)
+            Xs = X[:, perm].contiguous()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            a2, s2, c2 = m.dist.dbscan_features_device(Xs, gl, gw, eps, minpts)
+            torch.cuda.synchronize()
+            cluster["shuffled_order_time_s"] = time.perf_counter() - t0
+            cluster["shuffled_same_partition"] = bool(int(s2.numel()) == int(s_.numel())
+                                                      and int((a2 == 0).sum()) == int((a_ == 0).sum()))
+            # materialised distance matrix of 20 000 runs: the HBM-bound consumer of the same tiles
+            nm = min(20000, n_all)
+            Xm = X[:, :nm].contiguous()
+            Dm = torch.empty((nm, nm), dtype=torch.float64, device=dev)
+            best = None
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m.check(m.lib().mcbb_distance_matrix_dev(C.c_void_p(Xm.data_ptr()), nm, 3, gl.ctypes.data_as(ip),
+                                                         gw.ctypes.data_as(dp), C.c_void_p(Dm.data_ptr()), stream_ptr()))
+                e1.record()
+                torch.cuda.synchronize()
+                ms_ = e0.elapsed_time(e1)
+                best = ms_ if best is None else min(best, ms_)
+            gbs = 8.0 * nm * nm / (best * 1e-3) / 1e9
+            hbm_peak = 6551.7
+            try:
+                hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:
+                pass
+            cluster["materialize"] = {"bound": "hbm", "n": nm, "n_features": Ftot, "ms": best, "achieved": gbs,
+                                      "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                      "note": "8 n^2 bytes written / best of 3 launches (mcbb_distance_matrix_dev)"}
+            del Dm
+        else:
+            # sharded labels == single-GPU fused labels on a 2*10^5-run subset (every rank runs the sharded stages,
+            # rank 0 alone the single-GPU DBSCAN)
+            ns_ = min(200000, n_all)
+            Xsub = X[:, :ns_].contiguous()
+            a_sh, s_sh, c_sh = m.dist.dbscan_features_sharded(Xsub, gl, gw, eps, minpts, rank, world, dist)
+            if rank == 0:
+                a_1, s_1, c_1 = m.dist.dbscan_features_device(Xsub, gl, gw, eps, minpts)
+                same_lab = bool(torch.equal(a_sh, a_1) and torch.equal(s_sh, s_1) and torch.equal(c_sh, c_1))
+                cluster["sharded_equals_single_gpu"] = {"n_runs": ns_, "equal": same_lab,
+                                                        "sha1_sharded": labels_hash(a_sh), "sha1_single": labels_hash(a_1)}
+                assert same_lab, "row-sharded DBSCAN labels differ from the single-GPU fused DBSCAN"
+            barrier()
 
     if rank == 0:
         cpu = None
+        steps_ratio = None
         if not args.no_cpu and world == 1:  # reported at N=1 only (rank 0)
-            v, dt, threads = cpu_baseline(m, A, psys, pfeat, opts, ts, args.cpu_sample)
+            from oracle import oracle as orc
+            v, dt, threads, ores, ic_s, par_s = cpu_baseline(orc, psys, pfeat, opts, ts, args.cpu_sample)
             cpu = {"value": v, "unit": "trajectories/s", "cores": threads, "kind": "port",
                    "sample": "%d trajectories of the same C5 workload in %.1f s (oracle restatement of the reference's "
                              "CPU path; Julia itself is not installable here)" % (args.cpu_sample, dt)}
+            # the same sample through the GPU kernel: its step attempts must be the oracle's (roofline.achieved
+            # multiplies algorithmic flops per step by the KERNEL's count)
+            ics_d = torch.from_numpy(np.ascontiguousarray(ic_s.T)).to(dev)
+            pars_d = torch.from_numpy(np.ascontiguousarray(par_s.T)).to(dev)
+            _, _, _, ns_s = m.dist.solve_features_device(psys, opts, pfeat, ics_d, pars_d, ts_d)
+            g = ns_s[0].double().cpu().numpy()
+            o = ores["nsteps"][:, 0].astype(float)
+            steps_ratio = {"gpu_over_oracle": float(g.sum() / o.sum()), "gpu_mean": float(g.mean()),
+                           "oracle_mean": float(o.mean()), "runs": int(len(o)),
+                           "identical_runs_frac": float((g == o).mean())}
         line = {
-            "metric": "trajectories/sec (integrate+featurize)", "value": value, "unit": "trajectories/s",
+            "metric": METRIC, "value": value, "unit": "trajectories/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C5 kuramoto_network N=100 ER p=0.2, tspan (0,1000), tail 0.9, N_t=400, Tsit5 "
-                                   "abstol 1e-6 reltol 1e-3, measures [mean,std] cyclic_setback",
-                       "runs_per_gpu_per_step": R, "runs_per_step": world * R, "l2": "flushed between timed steps",
-                       "mean_step_attempts_per_run": float(nst.item()) / (world * R)},
+            "config": config_dict(world, R),
+            "mean_step_attempts_per_run": float(nst.item()) / (world * R), "steps_ratio": steps_ratio,
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "bitwise_equal_to_resident": same},
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "bitwise_equal_to_resident": same,
+                    "host_memory": "pinned", "pageable_value": e2e_pageable},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "pipeline": pipe, "pipeline_s": pipe["pipeline_s"] if pipe else None,
             "cluster": cluster, "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line))

@@ -19,6 +19,11 @@
  *   - Labels follow Clustering.jl: 0 = noise, 1..k = cluster id (src/sparse_clustering.jl:138-164).
  *   - Per-trajectory integrator failures are data (retcode_out), not errors
  *     (failure_handling, src/eval_mc_prob.jl:95-126).
+ *   - Threads and streams: working state (device scratch, the trajectory queue, constant-bank tables) is kept per
+ *     DEVICE.  Every compute entry point takes that device's lock for the duration of the call, and a call arriving on
+ *     a different stream than the device's previous call first waits for that stream to drain.  So: any number of host
+ *     threads may call concurrently (different devices overlap, one device takes turns), results are never corrupted
+ *     by mixing streams, but only ONE stream per device overlaps with the host — use one stream per device.
  */
 #ifndef MCBB_B200_H
 #define MCBB_B200_H
@@ -133,6 +138,17 @@ size_t mcbb_last_error(char* buf, size_t len); /* copies the last error text (th
 int mcbb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes);
 /* number of library kernels launched by this process so far (bench.py's gpu_launches) */
 int64_t mcbb_kernel_launch_count(void);
+
+/* Test / experiment hook — NOT part of the drop-in surface.  Sets a named integer switch read by the kernel dispatch
+ * (e.g. "no_umma", "umma_jb", "force_gmem", "trace"); value INT64_MIN erases the key.  Nothing in the library reads the
+ * process environment to choose a kernel: production callers never call this and get the default dispatch. */
+int mcbb_test_hook_set(const char* key, int64_t value);
+
+/* Diagnostic behind bench.py's cluster.roofline: counts the pair x feature terms the distance tiles actually execute
+ * on the current device (early exits and saturation skips excluded).  The current value is written to *value_out (may
+ * be NULL; synchronises `stream`) BEFORE `enable` is applied: enable > 0 zeroes and switches the counter on, 0 switches
+ * it off, < 0 leaves it as it is.  Off by default (one atomic per warp and tile when on). */
+int mcbb_pair_feature_counter(int32_t enable, int64_t* value_out, void* stream);
 
 /* FP64 FMA-pipe peak of the current device in TFLOP/s (DFMA micro-benchmark, best of 5) — the roofline
  * denominator of the ensemble integrator; MEASURED_PEAKS.json carries no FP64 figure. */

@@ -22,6 +22,7 @@ EXPORTS = [
     "mcbb_dbscan_labels_dev", "mcbb_gather_columns_dev", "mcbb_measure_fp64_fma_peak", "mcbb_knn_dist_dense", "mcbb_knn_dist_dense_dev",
     "mcbb_distance_sparse_count", "mcbb_distance_sparse_count_dev", "mcbb_distance_sparse_fill", "mcbb_distance_sparse_fill_dev",
     "mcbb_dbscan_sparse", "mcbb_dbscan_sparse_dev", "mcbb_dbscan_rows_count_lists_dev", "mcbb_dbscan_rows_union_more_dev", "mcbb_distance_matrix_rows", "mcbb_distance_matrix_rows_dev",
+    "mcbb_test_hook_set", "mcbb_pair_feature_counter",
 ]
 
 _lib = None
@@ -88,6 +89,8 @@ def lib():
     L.mcbb_dbscan_rows_union_more_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int64, C.c_int64, vp, vp]
     L.mcbb_dbscan_sparse.argtypes = [C.c_int64, lp, ip, dp, C.c_double, C.c_double, C.c_int32, lp, lp, lp, lp]
     L.mcbb_dbscan_sparse_dev.argtypes = [C.c_int64, vp, vp, vp, C.c_double, C.c_double, C.c_int32, vp, vp, vp, lp, vp]
+    L.mcbb_pair_feature_counter.argtypes = [C.c_int32, lp, vp]
+    L.mcbb_test_hook_set.argtypes = [C.c_char_p, C.c_int64]
     L.mcbb_gather_columns_dev.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp]
     _lib = L
     return L

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -18,18 +19,44 @@ void set_error(const std::string& msg) { t_last_error = msg; }
 struct ScratchSlot {
     void* p = nullptr;
     size_t cap = 0;
-    int dev = -1;
 };
-static ScratchSlot g_scratch[72];
+constexpr int MAX_DEV = 16;
+constexpr int N_SCRATCH = 96;
+static ScratchSlot g_scratch[MAX_DEV][N_SCRATCH];
 static std::mutex g_scratch_mu;
+
+// Working state (scratch buffers, the trajectory queue counter, constant-bank tables) is kept PER DEVICE, not per
+// stream.  ApiGuard makes that safe: every compute entry point holds the device's lock for the duration of the call
+// (host threads driving different devices run concurrently, two threads on one device take turns), and a call that
+// arrives on another stream than the previous one of that device first waits for the previous stream to drain, so a
+// kernel still running there never sees its tables overwritten.  One stream per device costs nothing.
+struct DevState {
+    std::recursive_mutex mu;
+    cudaStream_t last = nullptr;
+    bool used = false;
+};
+static DevState g_dev[MAX_DEV];
+
+static int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEV) ? dev : 0;
+}
+
+ApiGuard::ApiGuard(cudaStream_t st) : dev_(current_device_slot()) {
+    DevState& d = g_dev[dev_];
+    d.mu.lock();
+    if (d.used && d.last != st) cudaStreamSynchronize(d.last);
+    d.last = st;
+    d.used = true;
+}
+ApiGuard::~ApiGuard() { g_dev[dev_].mu.unlock(); }
 
 void* scratch_get(int slot, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     if (bytes == 0) bytes = 16;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    ScratchSlot& s = g_scratch[slot];
-    if (s.p && s.cap >= bytes && s.dev == dev) return s.p;
+    ScratchSlot& s = g_scratch[current_device_slot()][slot];
+    if (s.p && s.cap >= bytes) return s.p;
     if (s.p) {
         cudaDeviceSynchronize();
         cudaFree(s.p);
@@ -47,16 +74,35 @@ void* scratch_get(int slot, size_t bytes) {
         }
     }
     s.cap = want;
-    s.dev = dev;
     return s.p;
 }
 
 void scratch_free_all() {
     std::lock_guard<std::mutex> lk(g_scratch_mu);
-    for (auto& s : g_scratch) {
-        if (s.p) cudaFree(s.p);
-        s = ScratchSlot();
+    int cur = 0, ndev = 0;
+    cudaGetDevice(&cur);
+    cudaGetDeviceCount(&ndev);
+    for (int d = 0; d < MAX_DEV && d < ndev; d++) {
+        bool any = false;
+        for (auto& s : g_scratch[d]) any |= (s.p != nullptr);
+        if (!any) continue;
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        for (auto& s : g_scratch[d]) {
+            if (s.p) cudaFree(s.p);
+            s = ScratchSlot();
+        }
     }
+    cudaSetDevice(cur);
+    cudaGetLastError();
+}
+
+static std::mutex g_tune_mu;
+static std::map<std::string, long long> g_tune;
+long long tune_get(const char* key, long long dflt) {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    auto it = g_tune.find(key);
+    return it == g_tune.end() ? dflt : it->second;
 }
 
 // defined in solve.cu / cluster.cu
@@ -97,6 +143,7 @@ int distance_sparse_count_dev(const double* X, long long n, int n_groups, const 
 int distance_sparse_fill_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
                              const double* group_weight, double thr, const long long* colptr, long long nnz,
                              int* rowval, double* nzval, cudaStream_t st);
+int pair_feature_counter(int enable, long long* value_out, cudaStream_t st);
 int dbscan_sparse_dev(long long n, const long long* colptr, const int* rowval, const double* nzval, double value,
                       double eps, int minpts, long long* assignments, long long* seeds, long long* counts,
                       long long* n_clusters_host, cudaStream_t st);
@@ -317,6 +364,21 @@ int mcbb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, in
 
 int64_t mcbb_kernel_launch_count(void) { return g_launch_count.load(); }
 
+int mcbb_pair_feature_counter(int32_t enable, int64_t* value_out, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
+    return pair_feature_counter(enable, (long long*)value_out, (cudaStream_t)stream);
+}
+
+int mcbb_test_hook_set(const char* key, int64_t value) {
+    if (!key) MCBB_FAIL("test hook: NULL key");
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    if (value == INT64_MIN)
+        g_tune.erase(key);
+    else
+        g_tune[key] = value;
+    return 0;
+}
+
 int mcbb_tsave_array(const mcbb_solver_opts* o, int32_t n_t, double rel_transient_time, double* t_save,
                      int32_t* n_out) {
     if (!o || !n_out) MCBB_FAIL("tsave_array: NULL argument");
@@ -338,6 +400,7 @@ int mcbb_solve_features_dev(const mcbb_system_desc* sys, const mcbb_solver_opts*
                             int64_t n_mc, const double* ic_dev, const double* par_dev, const double* t_save_dev,
                             int32_t n_t, double* feat_dev, double* matrix_dev, double* global_dev,
                             int32_t* retcode_dev, int64_t* nsteps_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     return mcbb_solve_features_saved_dev(sys, opts, feat, n_mc, ic_dev, par_dev, t_save_dev, n_t, feat_dev, matrix_dev,
                                          global_dev, retcode_dev, nsteps_dev, MCBB_SAVE_NONE, nullptr, stream);
 }
@@ -368,6 +431,7 @@ int mcbb_solve_features_saved_dev(const mcbb_system_desc* sys, const mcbb_solver
                                   const double* par_dev, const double* t_save_dev, int32_t n_t, double* feat_dev,
                                   double* matrix_dev, double* global_dev, int32_t* retcode_dev, int64_t* nsteps_dev,
                                   int32_t save_mode, double* saved_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     const SolverVarRequest sv = t_solver_var;  // applies to this call only
     t_solver_var = SolverVarRequest();
     if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
@@ -429,6 +493,7 @@ int mcbb_solve_features(const mcbb_system_desc* sys, const mcbb_solver_opts* opt
                         int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
                         double* feat_out, double* matrix_out, double* global_out, int32_t* retcode_out,
                         int64_t* nsteps_out) {
+    ApiGuard guard_((cudaStream_t)0);
     return mcbb_solve_features_saved(sys, opts, feat, n_mc, ic, par, t_save, n_t, feat_out, matrix_out, global_out,
                                      retcode_out, nsteps_out, MCBB_SAVE_NONE, nullptr);
 }
@@ -437,6 +502,7 @@ int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opt
                               int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
                               double* feat_out, double* matrix_out, double* global_out, int32_t* retcode_out,
                               int64_t* nsteps_out, int32_t save_mode, double* saved_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!sys || !opts || !feat) MCBB_FAIL("solve: NULL descriptor");
     if (save_mode != MCBB_SAVE_NONE && !saved_out) MCBB_FAIL("solve: sample export requested but saved_out is NULL");
     if (save_mode < MCBB_SAVE_NONE || save_mode > MCBB_SAVE_LAST) MCBB_FAIL("solve: unknown save mode");
@@ -474,6 +540,8 @@ int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opt
         if (!d_saved) MCBB_FAIL("solve: device allocation of the sample export buffer failed");
     }
     cudaStream_t st = 0;
+    // a matrix measure no kernel wrote must read as NaN, never as stale scratch (all-ones bytes = quiet NaN)
+    if (feat->matrix_meas != MCBB_MAT_NONE) MCBB_CUDA_OK(cudaMemsetAsync(d_mat, 0xFF, b_mat, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(d_ic, ic, b_ic, cudaMemcpyHostToDevice, st));
     if (sys->n_par > 0) {
         if (!par) MCBB_FAIL("solve: NULL par with n_par > 0");
@@ -508,6 +576,7 @@ int mcbb_solve_features_saved(const mcbb_system_desc* sys, const mcbb_solver_opt
 
 int mcbb_distance_matrix_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                              const double* group_weight, double* D_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !D_dev || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
     return distance_matrix_dev(X_dev, n, n_groups, group_len, group_weight, D_dev, (cudaStream_t)stream);
@@ -515,6 +584,7 @@ int mcbb_distance_matrix_dev(const double* X_dev, int64_t n, int32_t n_groups, c
 
 int mcbb_distance_matrix(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
                          const double* group_weight, double* D_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!X || !D_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
     size_t F = 0;
@@ -532,6 +602,7 @@ int mcbb_distance_matrix(const double* X, int64_t n, int32_t n_groups, const int
 
 int mcbb_dbscan_dense_dev(const double* D_dev, int64_t n, double eps, int32_t minpts, int64_t* assignments_dev,
                           int64_t* seeds_dev, int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!D_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host) MCBB_FAIL("dbscan: NULL argument");
     return dbscan_dense_dev(D_dev, n, eps, minpts, (long long*)assignments_dev, (long long*)seeds_dev,
                             (long long*)counts_dev, (long long*)n_clusters_host, (cudaStream_t)stream);
@@ -548,6 +619,7 @@ static int dbscan_copy_back(long long n, long long* d_a, long long* d_s, long lo
 
 int mcbb_dbscan_dense(const double* D, int64_t n, double eps, int32_t minpts, int64_t* assignments, int64_t* seeds,
                       int64_t* counts, int64_t* n_clusters) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!D || !assignments || !seeds || !counts || !n_clusters) MCBB_FAIL("dbscan: NULL argument");
     if (n < 2) MCBB_FAIL("At least two data points are required.");
     double* d_D = (double*)scratch_get(41, sizeof(double) * (size_t)n * (size_t)n);
@@ -566,6 +638,7 @@ int mcbb_dbscan_dense(const double* D, int64_t n, double eps, int32_t minpts, in
 int mcbb_dbscan_features_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                              const double* group_weight, double eps, int32_t minpts, int64_t* assignments_dev,
                              int64_t* seeds_dev, int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host || !group_len || !group_weight)
         MCBB_FAIL("dbscan: NULL argument");
     return dbscan_features_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, (long long*)assignments_dev,
@@ -576,6 +649,7 @@ int mcbb_dbscan_features_dev(const double* X_dev, int64_t n, int32_t n_groups, c
 int mcbb_dbscan_features(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
                          const double* group_weight, double eps, int32_t minpts, int64_t* assignments,
                          int64_t* seeds, int64_t* counts, int64_t* n_clusters) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!X || !assignments || !seeds || !counts || !n_clusters || !group_len || !group_weight)
         MCBB_FAIL("dbscan: NULL argument");
     if (n < 2) MCBB_FAIL("At least two data points are required.");
@@ -598,6 +672,7 @@ int mcbb_dbscan_features(const double* X, int64_t n, int32_t n_groups, const int
 int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                                const double* group_weight, double eps, int32_t minpts, int64_t row0, int64_t row1,
                                int32_t* count_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !count_dev || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
     return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, row0, row1, count_dev, nullptr,
                           nullptr, (cudaStream_t)stream);
@@ -605,6 +680,7 @@ int mcbb_dbscan_rows_count_dev(const double* X_dev, int64_t n, int32_t n_groups,
 int mcbb_dbscan_rows_count_lists_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                                      const double* group_weight, double eps, int32_t minpts, int64_t row0, int64_t row1,
                                      int32_t* count_dev, int32_t* nbr_dev, int32_t* nfill_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !count_dev || !nbr_dev || !nfill_dev || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
     return rows_count_dev(X_dev, n, n_groups, group_len, group_weight, eps, minpts, row0, row1, count_dev, nbr_dev,
                           nfill_dev, (cudaStream_t)stream);
@@ -612,6 +688,7 @@ int mcbb_dbscan_rows_count_lists_dev(const double* X_dev, int64_t n, int32_t n_g
 int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups, const int32_t* group_len,
                                const double* group_weight, double eps, int64_t row0, int64_t row1,
                                int32_t* parent_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if ((n_core > 0 && (!Xcore_dev || !parent_dev)) || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
     return rows_union_dev(Xcore_dev, n_core, n_groups, group_len, group_weight, eps, row0, row1, parent_dev, 1,
                           (cudaStream_t)stream);
@@ -619,11 +696,13 @@ int mcbb_dbscan_rows_union_dev(const double* Xcore_dev, int64_t n_core, int32_t 
 int mcbb_dbscan_rows_union_more_dev(const double* Xcore_dev, int64_t n_core, int32_t n_groups, const int32_t* group_len,
                                     const double* group_weight, double eps, int64_t row0, int64_t row1,
                                     int32_t* parent_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if ((n_core > 0 && (!Xcore_dev || !parent_dev)) || !group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
     return rows_union_dev(Xcore_dev, n_core, n_groups, group_len, group_weight, eps, row0, row1, parent_dev, 0,
                           (cudaStream_t)stream);
 }
 int mcbb_dbscan_merge_parents_dev(int32_t* parent_dev, const int32_t* other_parent_dev, int64_t n_core, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (n_core > 0 && (!parent_dev || !other_parent_dev)) MCBB_FAIL("dbscan merge: NULL argument");
     return merge_parents_dev(parent_dev, other_parent_dev, n_core, (cudaStream_t)stream);
 }
@@ -631,12 +710,14 @@ int mcbb_dbscan_rows_border_dev(const double* Xnon_dev, int64_t n_non, int64_t r
                                 const double* Xcore_dev, int64_t n_core, const int32_t* core_seed_dev,
                                 int32_t n_groups, const int32_t* group_len, const double* group_weight, double eps,
                                 int32_t* best_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!group_len || !group_weight) MCBB_FAIL("dbscan rows: NULL argument");
     return rows_border_dev(Xnon_dev, n_non, row0, row1, Xcore_dev, n_core, core_seed_dev, n_groups, group_len,
                            group_weight, eps, best_dev, (cudaStream_t)stream);
 }
 int mcbb_dbscan_labels_dev(const int32_t* root_label_dev, int64_t n, int64_t* assignments_dev, int64_t* seeds_dev,
                            int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!root_label_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host)
         MCBB_FAIL("dbscan labels: NULL argument");
     return labels_dev(root_label_dev, n, (long long*)assignments_dev, (long long*)seeds_dev, (long long*)counts_dev,
@@ -644,16 +725,19 @@ int mcbb_dbscan_labels_dev(const int32_t* root_label_dev, int64_t n, int64_t* as
 }
 int mcbb_gather_columns_dev(const double* X_dev, int64_t ld, const int32_t* idx_dev, int64_t m, int32_t F,
                             double* Xout_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (m > 0 && (!X_dev || !idx_dev || !Xout_dev)) MCBB_FAIL("gather: NULL argument");
     return gather_columns_dev(X_dev, ld, idx_dev, m, F, Xout_dev, (cudaStream_t)stream);
 }
 
 int mcbb_knn_dist_dense_dev(const double* D_dev, int64_t n, int32_t k, int32_t K, double* kth_dev, double* cum_dev,
                             void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!D_dev || (!kth_dev && !cum_dev)) MCBB_FAIL("k_dist: NULL argument");
     return knn_dist_dense_dev(D_dev, n, k, K, kth_dev, cum_dev, (cudaStream_t)stream);
 }
 int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double* kth_out, double* cum_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!D || (!kth_out && !cum_out)) MCBB_FAIL("k_dist: NULL argument");
     if (n < 1) MCBB_FAIL("k_dist: empty matrix");
     double* d_D = (double*)scratch_get(41, sizeof(double) * (size_t)n * (size_t)n);
@@ -672,6 +756,7 @@ int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double
 int mcbb_knn_dist_features_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                                const double* group_weight, int32_t k, int32_t K, int64_t block_rows, double* kth_dev,
                                double* cum_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !group_len || !group_weight || (!kth_dev && !cum_dev)) MCBB_FAIL("k_dist: NULL argument");
     if (n_groups < 1) MCBB_FAIL("k_dist: empty input");
     return knn_dist_features_dev(X_dev, n, n_groups, group_len, group_weight, k, K, block_rows, kth_dev, cum_dev,
@@ -680,6 +765,7 @@ int mcbb_knn_dist_features_dev(const double* X_dev, int64_t n, int32_t n_groups,
 int mcbb_knn_dist_features(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
                            const double* group_weight, int32_t k, int32_t K, int64_t block_rows, double* kth_out,
                            double* cum_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!X || !group_len || !group_weight || (!kth_out && !cum_out)) MCBB_FAIL("k_dist: NULL argument");
     if (n < 1 || n_groups < 1) MCBB_FAIL("k_dist: empty input");
     size_t F = 0;
@@ -702,6 +788,7 @@ int mcbb_knn_dist_features(const double* X, int64_t n, int32_t n_groups, const i
 int mcbb_distance_sparse_count_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                                    const double* group_weight, double sparse_threshold, int32_t* count_dev,
                                    void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !count_dev || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     return distance_sparse_count_dev(X_dev, n, n_groups, group_len, group_weight, sparse_threshold, count_dev,
                                      (cudaStream_t)stream);
@@ -709,6 +796,7 @@ int mcbb_distance_sparse_count_dev(const double* X_dev, int64_t n, int32_t n_gro
 int mcbb_distance_sparse_fill_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                                   const double* group_weight, double sparse_threshold, const int64_t* colptr_dev,
                                   int64_t nnz, int32_t* rowval_dev, double* nzval_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !colptr_dev || !rowval_dev || !nzval_dev || !group_len || !group_weight)
         MCBB_FAIL("distance_matrix: NULL argument");
     return distance_sparse_fill_dev(X_dev, n, n_groups, group_len, group_weight, sparse_threshold,
@@ -717,6 +805,7 @@ int mcbb_distance_sparse_fill_dev(const double* X_dev, int64_t n, int32_t n_grou
 int mcbb_dbscan_sparse_dev(int64_t n, const int64_t* colptr_dev, const int32_t* rowval_dev, const double* nzval_dev,
                            double value, double eps, int32_t minpts, int64_t* assignments_dev, int64_t* seeds_dev,
                            int64_t* counts_dev, int64_t* n_clusters_host, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!colptr_dev || !assignments_dev || !seeds_dev || !counts_dev || !n_clusters_host) MCBB_FAIL("dbscan: NULL argument");
     return dbscan_sparse_dev(n, (const long long*)colptr_dev, rowval_dev, nzval_dev, value, eps, minpts,
                              (long long*)assignments_dev, (long long*)seeds_dev, (long long*)counts_dev,
@@ -731,11 +820,13 @@ static size_t total_features(int32_t n_groups, const int32_t* group_len) {
 
 int mcbb_distance_matrix_rows_dev(const double* X_dev, int64_t n, int32_t n_groups, const int32_t* group_len,
                                   const double* group_weight, int64_t row0, int64_t row1, double* rows_dev, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
     if (!X_dev || !rows_dev || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     return distance_rows_dev(X_dev, n, n_groups, group_len, group_weight, row0, row1, rows_dev, (cudaStream_t)stream);
 }
 int mcbb_distance_matrix_rows(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
                               const double* group_weight, int64_t row0, int64_t row1, double* rows_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!X || !rows_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
     if (row0 < 0 || row1 > n || row0 > row1) MCBB_FAIL("distance_matrix: bad row range");
@@ -754,6 +845,7 @@ int mcbb_distance_matrix_rows(const double* X, int64_t n, int32_t n_groups, cons
 
 int mcbb_distance_sparse_count(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
                                const double* group_weight, double sparse_threshold, int32_t* count_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!X || !count_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
     const size_t F = total_features(n_groups, group_len);
@@ -771,6 +863,7 @@ int mcbb_distance_sparse_count(const double* X, int64_t n, int32_t n_groups, con
 int mcbb_distance_sparse_fill(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
                               const double* group_weight, double sparse_threshold, const int64_t* colptr,
                               int32_t* rowval_out, double* nzval_out) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!X || !colptr || !rowval_out || !nzval_out || !group_len || !group_weight) MCBB_FAIL("distance_matrix: NULL argument");
     if (n < 1 || n_groups < 1) MCBB_FAIL("distance_matrix: empty input");
     const long long nnz = colptr[n];
@@ -795,6 +888,7 @@ int mcbb_distance_sparse_fill(const double* X, int64_t n, int32_t n_groups, cons
 int mcbb_dbscan_sparse(int64_t n, const int64_t* colptr, const int32_t* rowval, const double* nzval, double value,
                        double eps, int32_t minpts, int64_t* assignments, int64_t* seeds, int64_t* counts,
                        int64_t* n_clusters) {
+    ApiGuard guard_((cudaStream_t)0);
     if (!colptr || !assignments || !seeds || !counts || !n_clusters) MCBB_FAIL("dbscan: NULL argument");
     if (n < 2) MCBB_FAIL("At least two data points are required.");
     const long long nnz = colptr[n];

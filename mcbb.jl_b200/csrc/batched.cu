@@ -581,6 +581,7 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     constexpr int TI = TI_;
     if (S.system != MCBB_SYS_KURAMOTO_NETWORK && S.system != MCBB_SYS_NONLOCAL_KURAMOTO_RING) return 0;
     if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1) return 0;
+    if (F.matrix_meas != MCBB_MAT_NONE) return 0;  // no matrix measure here: the lane kernels compute it
     if (N < 24 || N > 160 || hs == nullptr) return 0;
     for (int m = 0; m < F.n_meas; m++)
         if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
@@ -685,7 +686,7 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     // register block width: 2 trajectories per thread doubles the resident warps (latency hiding) at the same
     // shared-memory footprint; MCBB_BATCH_TB=4 selects the wider block for experiments
     int TB = 2;
-    if (const char* e = getenv("MCBB_BATCH_TB")) TB = (atoi(e) == 4) ? 4 : 2;
+    if (const long long e = tune_get("batch_tb", 0)) TB = (e == 4) ? 4 : 2;
     // batch size: as many TB-trajectory groups as shared memory holds (<= 256 threads)
     const size_t cap = 227 * 1024;
     int BG = 0;

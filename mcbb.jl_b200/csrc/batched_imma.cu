@@ -589,7 +589,7 @@ static int launch_imma_spec(ImmaArgs& a, size_t smem, int grid, cudaStream_t st)
 }
 
 static int launch_imma(ImmaArgs& a, size_t smem, int grid, int per_sm, cudaStream_t st) {
-    if (per_sm == 2 && a.WS == 1 && !getenv("MCBB_IMMA_GENERIC")) {
+    if (per_sm == 2 && a.WS == 1 && !tune_get("imma_generic", 0)) {
         const int CT = a.B / 4;
 #define MCBB_SPEC(c, k) if (CT == c && a.KS == k) return launch_imma_spec<c, k>(a, smem, grid, st);
         MCBB_SPEC(1, 4) MCBB_SPEC(2, 4) MCBB_SPEC(2, 3) MCBB_SPEC(3, 3) MCBB_SPEC(3, 2) MCBB_SPEC(4, 2)
@@ -619,8 +619,9 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     const int N = S.n_osc;
     if (S.system != MCBB_SYS_KURAMOTO_NETWORK || hs == nullptr) return 0;
     if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1) return 0;
+    if (F.matrix_meas != MCBB_MAT_NONE) return 0;  // no matrix measure here: the lane kernels compute it
     if (N < 24 || N > 128) return 0;
-    if (getenv("MCBB_NO_IMMA")) return 0;
+    if (tune_get("no_imma", 0)) return 0;
     for (int m = 0; m < F.n_meas; m++)
         if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
     // unit-weight adjacency?
@@ -642,7 +643,7 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
         const int kpairs = (a.KS + 1) / 2;
         a.kstr = (kpairs * 64) % 128 == 0 ? kpairs * 64 + 64 : kpairs * 64;
     }
-    a.WS = getenv("MCBB_IMMA_WS") ? atoi(getenv("MCBB_IMMA_WS")) : 2;
+    a.WS = (int)tune_get("imma_ws", 2);
     if (a.WS < 1 || a.WS * a.MT * 32 > 512) a.WS = 1;
     a.nthreads = a.MT * a.WS * 32;
     a.unit_weight = uw;
@@ -701,7 +702,7 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
 
     // batch per CTA: default two resident CTAs per SM with half the shared memory each (their phases drift apart,
     // so one CTA's FP64 work overlaps the other's IMMA work: +21 % measured); MCBB_IMMA_PER_SM=1,3,4 for experiments
-    int per_sm = getenv("MCBB_IMMA_PER_SM") ? atoi(getenv("MCBB_IMMA_PER_SM")) : 2;
+    int per_sm = (int)tune_get("imma_per_sm", 2);
     if (per_sm < 1 || per_sm > 4) per_sm = 1;
     if (per_sm >= 2) {
         a.WS = 1;

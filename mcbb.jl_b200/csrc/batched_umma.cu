@@ -762,7 +762,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     if (F.need_kl && (F.kl_bins > UM_MAX_KL_BINS || F.kl_bins < 3)) return 0;
     if (N < 33 || N > 128) return 0;  // one 128-row MMA tile; small networks stay on the mma.sync kernel
     if (io.n_t > UM_MAX_NT) return 0;  // save times are kept in the constant bank
-    if (getenv("MCBB_NO_IMMA") || getenv("MCBB_NO_UMMA")) return 0;
+    if (tune_get("no_imma", 0) || tune_get("no_umma", 0)) return 0;  // test hook (mcbb_test_hook_set), never set in production
     for (int m = 0; m < F.n_meas; m++)
         if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD && F.meas[m] != MCBB_MEAS_KL_HIST) return 0;
     double uw = 0.;  // unit-weight adjacency?
@@ -827,8 +827,8 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     // configurations (trajectories per CTA, CTAs per SM): TMEM columns and shared memory both have to fit
     struct Cfg { int jb, per_sm; };
     static const Cfg cfgs[] = {{6, 4}, {4, 4}, {6, 3}, {8, 2}, {4, 3}, {4, 2}, {2, 2}, {2, 1}};
-    int want_jb = getenv("MCBB_UMMA_JB") ? atoi(getenv("MCBB_UMMA_JB")) : 0;
-    int want_per = getenv("MCBB_UMMA_PER_SM") ? atoi(getenv("MCBB_UMMA_PER_SM")) : 0;
+    int want_jb = (int)tune_get("umma_jb", 0);
+    int want_per = (int)tune_get("umma_per_sm", 0);
     const Cfg* pick = nullptr;
     for (const Cfg& c : cfgs) {
         if (want_jb && c.jb != want_jb) continue;
@@ -859,7 +859,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     int rc = 1;
-    if (getenv("MCBB_UMMA_TIMING") && pick->jb == 4 && (pick->per_sm == 4 || pick->per_sm == 2)) {  // development aid
+    if (tune_get("umma_timing", 0) && pick->jb == 4 && (pick->per_sm == 4 || pick->per_sm == 2)) {  // development aid
         a.timing = (unsigned long long*)scratch_get(63, 64);
         if (!a.timing) MCBB_FAIL("solve: device allocation failed");
         MCBB_CUDA_OK(cudaMemsetAsync(a.timing, 0, 64, st));

@@ -165,7 +165,7 @@ struct PassTimer {  // MCBB_TRACE=1: per-pass device times on stderr
     cudaStream_t st;
     cudaEvent_t e0, e1;
     bool on;
-    explicit PassTimer(cudaStream_t s) : st(s), on(getenv("MCBB_TRACE") != nullptr) {
+    explicit PassTimer(cudaStream_t s) : st(s), on(getenv("MCBB_TRACE") != nullptr || tune_get("trace", 0) != 0) {
         if (on) {
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
@@ -233,9 +233,41 @@ static int upload_groups(int n_groups, const int32_t* group_len, const double* g
     return 0;
 }
 
+// diagnostic counter of executed pair x feature terms (one per device), enabled by mcbb_pair_feature_counter
+static unsigned long long* g_pf_ctr[16] = {};
+static unsigned long long* pf_counter() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 16) ? g_pf_ctr[dev] : nullptr;
+}
+int pair_feature_counter(int enable, long long* value_out, cudaStream_t st) {
+    int dev = 0;
+    MCBB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) MCBB_FAIL("pair feature counter: device index out of range");
+    if (value_out) {
+        *value_out = 0;
+        if (g_pf_ctr[dev]) {
+            MCBB_CUDA_OK(cudaStreamSynchronize(st));
+            unsigned long long h = 0;
+            MCBB_CUDA_OK(cudaMemcpy(&h, g_pf_ctr[dev], sizeof(h), cudaMemcpyDeviceToHost));
+            *value_out = (long long)h;
+        }
+    }
+    if (enable > 0) {
+        unsigned long long* p = (unsigned long long*)scratch_get(68, 64);
+        if (!p) MCBB_FAIL("pair feature counter: device allocation failed");
+        MCBB_CUDA_OK(cudaMemsetAsync(p, 0, 64, st));
+        g_pf_ctr[dev] = p;
+    } else if (enable == 0) {
+        g_pf_ctr[dev] = nullptr;
+    }
+    return 0;
+}
+
 template <int MODE>
 static int launch_tiles(const TileArgs& a_in, cudaStream_t st) {
     TileArgs a = a_in;
+    a.pf_ctr = pf_counter();
     const long long nr = a.r1 - a.r0, nc = a.c1 - a.c0;
     if (nr <= 0 || nc <= 0) return 0;
     dim3 grid((unsigned)((nc + TILE - 1) / TILE), (unsigned)((nr + TILE - 1) / TILE));
@@ -294,6 +326,7 @@ static int count_rows(const double* X, long long n, const GroupTables& gt, doubl
     a.fmask = gt.fmask;
     a.eps = eps;
     a.symmetric = 0;  // full rows: the diagonal pair (d = 0 < eps) supplies the self count
+    a.self_zero = 1;
     a.early_exit = gt.early_exit;
     a.cnt = cnt - row0;
     a.sat_count = minpts;
@@ -448,6 +481,7 @@ int distance_rows_dev(const double* X, long long n, int n_groups, const int32_t*
     a.fend = gt.fend;
     a.fmask = gt.fmask;
     a.symmetric = 0;
+    a.self_zero = 1;
     a.D = out - n * row0;
     a.sat_seed = -1;
     return launch_tiles_rows<TM_MATERIALIZE>(a, st);
@@ -514,7 +548,7 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
     // pass 1: neighbour counts (the diagonal pair, D_pp = 0 < eps, supplies the self count)
     // neighbour lists of the (eventual) non-core points: minpts entries per point are enough
     int *nbr = nullptr, *nfill = nullptr;
-    if ((size_t)n * (size_t)minpts * sizeof(int) <= ((size_t)512 << 20) && !getenv("MCBB_DBSCAN_NO_LISTS")) {
+    if ((size_t)n * (size_t)minpts * sizeof(int) <= ((size_t)512 << 20) && !tune_get("dbscan_no_lists", 0)) {
         nbr = (int*)scratch_get(34, sizeof(int) * (size_t)n * (size_t)minpts);
         nfill = (int*)scratch_get(35, sizeof(int) * (size_t)n);
         if (!nbr || !nfill) MCBB_FAIL("dbscan: device scratch allocation failed");

@@ -101,4 +101,17 @@ SolverDev resolve_solver(const mcbb_solver_opts* o);
 void* scratch_get(int slot, size_t bytes);
 void scratch_free_all();
 
+// test / experiment switches: set only through mcbb_test_hook_set (never from the environment), 0 / default in production
+long long tune_get(const char* key, long long dflt);
+
+// serialises the library's per-device working state across host threads and streams (api.cu)
+struct ApiGuard {
+    explicit ApiGuard(cudaStream_t st);
+    ~ApiGuard();
+    ApiGuard(const ApiGuard&) = delete;
+    ApiGuard& operator=(const ApiGuard&) = delete;
+  private:
+    int dev_;
+};
+
 }  // namespace mcbb

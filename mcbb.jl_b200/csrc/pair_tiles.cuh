@@ -70,6 +70,10 @@ struct TileArgs {
     int fold;             // symmetric full launch: the grid is nt x (nt/2 + 1); block (x, y) owns tile (y, x) if x >= y,
                           // else tile (nt - y, nt - 1 - x): every block lands on or above the diagonal, none is launched
                           // only to return
+    unsigned long long* pf_ctr;  // diagnostic (mcbb_pair_feature_counter): executed pair x feature terms, or null
+    int self_zero;        // non-symmetric launch whose rows and columns index the same points: the pair (p, p) is the
+                          // diagonal D[p,p] = 0 of the reference (eval_clustering.jl:242-247 never computes it), also
+                          // when a feature of p is Inf / NaN (|Inf - Inf| = NaN would drop the point's self count)
     int band;             // > 0: only column tiles within `band` tiles of the row tile are visited; blockIdx.x is
                           // the offset (symmetric: 0..band, else -band..band).  Runs are sorted by parameter, so
                           // index neighbours are the likely distance neighbours: a cheap first pass that saturates
@@ -192,6 +196,10 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
     issue_slab(0, 0);
     int buf = 0;
     bool warp_alive = true;
+    int nf_done = 0;  // features this warp accumulated (x 512 pairs per warp): the executed work behind cluster.roofline
+    auto flush_count = [&]() {
+        if (a.pf_ctr && (tid & 31) == 0 && nf_done) atomicAdd(a.pf_ctr, (unsigned long long)nf_done * 512ull);
+    };
     for (int f0 = 0; f0 < a.F; f0 += FC, buf ^= 1) {
         const int fc = min(FC, a.F - f0);
         asm volatile("cp.async.wait_group 0;");
@@ -200,6 +208,7 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
         const unsigned emask = a.fmask[f0 / FC];
         const double (*s_r)[TILE] = s_slab[buf][0];
         const double (*s_c)[TILE] = s_slab[buf][1];
+        nf_done += warp_alive ? fc : 0;
         // warp_alive: some pair of this warp's 64 x 8 block can still fall below eps.  A warp whose pairs are all
         // provably >= eps (monotone partial sums) stops accumulating — its values no longer matter to any consumer
         // but the materialising one — while the rest of the tile goes on.
@@ -243,11 +252,13 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
             }
             if (!__syncthreads_or(alive)) {  // no pair of this tile can still fall below eps
                 asm volatile("cp.async.wait_group 0;");  // do not leave the prefetch in flight
+                flush_count();
                 return;
             }
         }
     }
 
+    flush_count();
     // ---- consume the 4 x 4 block ---------------------------------------------------------------------
     if (MODE == TM_MATERIALIZE) {
         // Stage the tile in shared memory (reusing the feature slabs: 2 x 16 x 64 doubles = one 64 x 32 half
@@ -277,7 +288,11 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
                     const int cl = q >> 5, rl = (q & 31) * 2;
                     const long long ri = tr + rl, cj = tc + 32 * half + cl;
                     if (cj >= a.c1 || ri >= a.r1) continue;
-                    const double d0 = s_t[cl * TILE + (rl ^ cl)], d1 = s_t[cl * TILE + ((rl + 1) ^ cl)];
+                    double d0 = s_t[cl * TILE + (rl ^ cl)], d1 = s_t[cl * TILE + ((rl + 1) ^ cl)];
+                    if (a.self_zero) {
+                        if (ri == cj) d0 = 0.;
+                        if (ri + 1 == cj) d1 = 0.;
+                    }
                     if (ri + 1 < a.r1)
                         __stcs(reinterpret_cast<double2*>(a.D + ri + a.ldr * cj), make_double2(d0, d1));
                     else
@@ -293,6 +308,7 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
                             if (cj < ri && diag) continue;      // lower part of a diagonal tile comes from the mirror
                             if (cj == ri) d = 0.;
                         }
+                        if (a.self_zero && cj == ri) d = 0.;
                         __stcs(a.D + ri + a.ldr * cj, d);
                     }
                 }
@@ -335,7 +351,8 @@ __global__ void __launch_bounds__(256) k_pair_tiles(const TileArgs a) {
                 const long long cj = tc + ty * TT + j;
                 if (cj >= a.c1) continue;
                 if (a.symmetric && cj <= ri) continue;
-                if (!(acc[i][j] < a.eps)) continue;  // strict, sparse_clustering.jl:173
+                const bool self = a.self_zero && ((a.rid ? (long long)a.rid[ri] + a.nbr_row0 : ri) == cj);
+                if (!((self ? 0. : acc[i][j]) < a.eps)) continue;  // strict, sparse_clustering.jl:173
                 local++;
                 if (a.symmetric) atomicAdd(&s_cnt[TILE + ty * TT + j], 1);
                 if (a.nbr) {

@@ -241,7 +241,7 @@ static int launch_lane_impl(const SysDev& S, const SolverDev& o, const FeatDev& 
             break;
         }
     }
-    if (getenv("MCBB_FORCE_GMEM")) bs = 0;  // experiment switch: L2/HBM-resident lane state
+    if (tune_get("force_gmem", 0)) bs = 0;  // experiment switch: L2/HBM-resident lane state
     if (bs == 0) {
         // state in global memory.  The kernel is latency bound (dependent loads of the stage vectors), so fill the
         // machine: 8 CTAs of 64 lanes per SM (~76 k lanes; at most 8 GB of stage vectors, HBM-resident)

@@ -17,12 +17,15 @@ _ROOT = os.path.dirname(_HERE)
 
 
 def _load_abi():
+    """The declaration module mcbb.jl_b200/_abi.py (structs / enums only, loads no library), registered under its
+    canonical name so that the product package — whichever of the two is imported first — shares the SAME ctypes
+    classes (a second copy would make `expected LP_SystemDesc instance` errors depend on the import order)."""
     name = "mcbb_jl_b200._abi"
     if name in sys.modules:
         return sys.modules[name]
-    spec = importlib.util.spec_from_file_location("_mcbb_abi_for_oracle",
-                                                  os.path.join(_ROOT, "mcbb.jl_b200", "_abi.py"))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(_ROOT, "mcbb.jl_b200", "_abi.py"))
     mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
 

@@ -33,8 +33,25 @@ def c2_problem(m, n_mc=2000, seed=3, tspan=(0.0, 1000.0), tail=0.8):
     return prob, [1.0, 0.75, 0.5, 1.0]
 
 
-def ring_incidence(N, chords):
-    edges = [(i, (i + 1) % N) for i in range(N)] + list(chords)
+def random_regular_graph(N, d, seed):
+    """Simple d-regular graph on N nodes from the pairing model (stubs shuffled with numpy PCG64(seed); a draw with a
+    self-loop or a double edge is rejected and redrawn).  Returns the edge list (a < b), sorted."""
+    rng = np.random.default_rng(seed)
+    assert (N * d) % 2 == 0
+    while True:
+        stubs = rng.permutation(np.repeat(np.arange(N), d))
+        pairs = stubs.reshape(-1, 2)
+        a, b = pairs.min(axis=1), pairs.max(axis=1)
+        if np.any(a == b):
+            continue
+        edges = sorted(set(zip(a.tolist(), b.tolist())))
+        if len(edges) == N * d // 2:
+            return edges
+
+
+def incidence(N, edges):
+    """Oriented incidence matrix (N x n_edges): -1 at the tail, +1 at the head (LightGraphs incidence_matrix(g,
+    oriented=true), paper/kuramoto/1-simulate.jl:25)."""
     E = np.zeros((N, len(edges)))
     for e, (a, b) in enumerate(edges):
         E[a, e] = -1.0
@@ -42,18 +59,61 @@ def ring_incidence(N, chords):
     return E
 
 
-def c3_problem(m, n_mc=400, seed=5, N=10, tspan=(0.0, 200.0), tail=0.9, lam_max=2.0):
-    """C3 shape: second-order Kuramoto power grid (paper/kuramoto/1-simulate.jl), features on the frequencies."""
+def watts_strogatz(N, k, beta, seed):
+    """Watts-Strogatz small world as LightGraphs.watts_strogatz(n, k, beta) builds it: ring lattice with k/2
+    neighbours on each side; every lattice edge (s, s+j) is rewired with probability beta to (s, random target)
+    avoiding self-loops and existing edges.  Symmetric 0/1 adjacency (p_r = 0.04, seed 7)."""
     rng = np.random.default_rng(seed)
-    E = ring_incidence(N, [(i, (i + N // 2) % N) for i in range(N // 2)])
+    A = np.zeros((N, N), dtype=bool)
+    for j in range(1, k // 2 + 1):
+        for s in range(N):
+            t = (s + j) % N
+            if rng.random() < beta:
+                while True:
+                    t = int(rng.integers(0, N))
+                    if t != s and not A[s, t]:
+                        break
+            A[s, t] = A[t, s] = True
+    return A.astype(np.float64)
+
+
+def ring_incidence(N, chords):
+    """Ring plus chords: the small hand-made grids of the unit tests (the C3 case itself uses random_regular_graph)."""
+    return incidence(N, [(i, (i + 1) % N) for i in range(N)] + list(chords))
+
+
+def c3_problem(m, n_mc=400, seed=5, N=10, tspan=(0.0, 200.0), tail=0.9, lam_max=2.0):
+    """C3: second-order Kuramoto power grid on a random 3-regular graph (seed 5), drive +-1 alternating,
+    damping 0.1, coupling swept (paper/kuramoto/1-simulate.jl:22-26, 61), features on the frequencies."""
+    rng = np.random.default_rng(seed + 1)
+    E = incidence(N, random_regular_graph(N, 3, seed))
     drive = np.array([1.0, -1.0] * (N // 2))
     pars = m.second_order_kuramoto_parameters(N, 0.1, 1.0, E, drive)
     rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), tspan, pars)
     ev = m.EvalOdeRun(state_filter=list(range(N + 1, 2 * N + 1)), eval_funcs=(m.mean, m.std))
-    lam = np.random.default_rng(seed + 1)
+    lam = np.random.default_rng(seed + 2)
     prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), n_mc, pars,
                            ("coupling", lambda: lam.uniform(0.05, lam_max)), ev, tail)
     return prob, [1.0, 0.0, 1.0]
+
+
+def c4_problem(m, n_mc, N=100, tspan=(0.0, 200.0), tail=0.7, seed=7, corr=True, p_r=0.04):
+    """C4 (paper/stuartlandau/stuart_landau_sathiyadevi-standard-config.ipynb cell 1): Stuart-Landau ring,
+    lambda=1, omega=2, r1=0.01 (P1=1), r2=0.22 (P2=22), A1/A2 Watts-Strogatz p_r=0.04 (seed 7 / 7+1000), eps~U(1.8,2.1)
+    (seed 8), z0~U(-1,1)+iU(-1,1) (seed 9), measures mean/std/KL of re and im + correlation_ecdf."""
+    P1, P2 = int(round(0.01 * N)) or 1, int(round(0.22 * N))
+    A1 = watts_strogatz(N, 2 * P1, p_r, seed)
+    A2 = watts_strogatz(N, 2 * P2, p_r, seed + 1000)
+    pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.925, N, P1, P2, A1, A2)
+    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"),
+                      matrix_eval_funcs=[m.correlation_ecdf] if corr else [])
+    rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(N, dtype=complex), tspan, pars)
+    erng = np.random.default_rng(seed + 1)
+    zrng = np.random.default_rng(seed + 2)
+    prob = m.DEMCBBProblem(rp, lambda: complex(zrng.uniform(-1, 1), zrng.uniform(-1, 1)), n_mc, pars,
+                           ("eps", lambda: erng.uniform(1.8, 2.1)), ev, tail)
+    weights = [0.25, 1.0, 0.0, 0.25, 1.0, 0.0] + ([0.0] if corr else []) + [1.0]
+    return prob, weights
 
 
 def erdos_renyi(N, p, seed):

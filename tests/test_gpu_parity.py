@@ -748,25 +748,12 @@ def test_failure_handling_repeat_and_inf(gpu):
 
 
 def test_c4_stuart_landau_n100_global_state_path(gpu, orc):
-    """C4's system at its real size: Stuart-Landau ring N=100 (200 real state dimensions; A_1 degree 2, A_2 degree 44),
-    eps swept, measures mean/std/KL of real and imaginary parts.  The state does not fit shared memory, so this runs
-    the lane kernel with L2-resident state."""
+    """C4's system at its real size with SURVEY §8(d)'s inputs: Stuart-Landau N=100 (200 real state dimensions), A_1 / A_2
+    Watts-Strogatz small worlds (degree 2 and 44, p_r = 0.04, seed 7), eps ~ U(1.8, 2.1), z0 ~ U(-1,1) + i U(-1,1),
+    measures mean/std/KL of real and imaginary parts + correlation_ecdf.  Short time span at converged tolerances: every
+    run against the oracle (the time span of the paper, T = 200, is covered by tests/test_gpu_c4.py)."""
     m = gpu
-    N = 100
-    rng = np.random.default_rng(7)
-
-    def ring_adj(P):
-        A = np.zeros((N, N))
-        for d in range(1, P + 1):
-            A += np.roll(np.eye(N), d, 0) + np.roll(np.eye(N), -d, 0)
-        return A
-    pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.925, N, 1, 22, ring_adj(1), ring_adj(22))
-    ev = m.EvalOdeRun(eval_funcs=("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"),
-                      matrix_eval_funcs=[m.correlation_ecdf])  # the notebook's full measure set
-    rp = m.ODEProblem(m.stuart_landau_sathiyadevi, np.zeros(N, dtype=complex), (0.0, 20.0), pars)
-    prng = np.random.default_rng(8)
-    prob = m.DEMCBBProblem(rp, lambda: complex(rng.uniform(-1, 1), rng.uniform(-1, 1)), 48, pars,
-                           ("eps", lambda: prng.uniform(1.8, 2.1)), ev, 0.7)
+    prob, _ = cases.c4_problem(m, 48, tspan=(0.0, 20.0))
     ic0, par0 = prob.ic.copy(), prob.par.copy()
     kw = dict(reltol=1e-8, abstol=1e-8, maxiters=10 ** 6)
     sol = m.solve(prob, **kw)

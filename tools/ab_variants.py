@@ -1,13 +1,12 @@
 #!/usr/bin/env python
-"""A/B harness for kernel experiments: runs the C5 headline workload (resident inputs) under several environment
-variants IN ONE PROCESS — one gpurun call instead of one per variant — times each with CUDA events and checks that every
+"""A/B harness for kernel experiments: runs the C5 headline workload (resident inputs) under several test-hook
+variants (mcbb_test_hook_set keys) IN ONE PROCESS — one gpurun call instead of one per variant — times each with CUDA events and checks that every
 variant returns bitwise the same features and step counts as the first one.
 
-    python tools/ab_variants.py "" "MCBB_UMMA_JB=4,MCBB_UMMA_PER_SM=4" "MCBB_NO_UMMA=1"
+    python tools/ab_variants.py "" "umma_jb=4,umma_per_sm=4" "no_umma=1"
     RUNS=125000 REPS=3 python tools/ab_variants.py ...
 
-The switches are read by the library at launch time (csrc/batched_umma.cu, solve.cu, cluster.cu), so setting them
-between launches is enough.  Prints one JSON object: variant -> {traj_per_s, ms, launches, equal_to_first}."""
+The switches are read by the library at launch time (tune_get in csrc/), so setting them between launches is enough.  Prints one JSON object: variant -> {traj_per_s, ms, launches, equal_to_first}."""
 import json
 import os
 import sys
@@ -23,7 +22,7 @@ def parse(spec):
     env = {}
     for item in filter(None, (s.strip() for s in spec.split(","))):
         k, _, v = item.partition("=")
-        env[k] = v if v != "" else "1"
+        env[k] = int(v) if v != "" else 1
     return env
 
 
@@ -45,8 +44,9 @@ def main():
     for spec in variants:
         env = parse(spec)
         for k in touched:
-            os.environ.pop(k, None)
-        os.environ.update(env)
+            m.lib().mcbb_test_hook_set(k.encode(), -2**63)  # INT64_MIN erases the key
+        for k, v in env.items():
+            m.lib().mcbb_test_hook_set(k.encode(), v)
         touched |= set(env)
         for _ in range(2):  # warm-up: module load, scratch allocation
             feat, _, ret, nst = m.dist.solve_features_device(psys, opts, pfeat, ic_d, par_d, ts_d)
