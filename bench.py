@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--config", default="C5", choices=["C5", "C4"])
     ap.add_argument("--runs-per-gpu", type=int, default=125000)
     ap.add_argument("--cpu-sample", type=int, default=384)
+    ap.add_argument("--c4-runs", type=int, default=200000, help="--config C4: runs of the whole ensemble (all GPUs)")
     ap.add_argument("--no-cluster", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

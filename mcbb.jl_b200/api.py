@@ -875,9 +875,9 @@ def _compute_hist_weights(meas, edges, use_ecdf=True):
         k = np.rint(np.where(np.isnan(f), 1.0, f)).astype(np.int64)
         k -= (meas < edges[k - 1]).astype(np.int64)
         ok = (k >= 1) & (k <= nb) & ~np.isnan(meas)
-    H = np.zeros((n_mc, nb), dtype=np.float32)
-    rows = np.broadcast_to(np.arange(n_mc)[:, None], meas.shape)
-    np.add.at(H, (rows[ok], k[ok] - 1), np.float32(1))
+    # counts are integers < 2^24: exact in Float32 whichever way they are accumulated
+    flat = (np.arange(n_mc, dtype=np.int64)[:, None] * nb + (k - 1))[ok]
+    H = np.bincount(flat, minlength=n_mc * nb).reshape(n_mc, nb).astype(np.float32)
     if use_ecdf:
         H = np.cumsum(H, axis=1, dtype=np.float32)
         with np.errstate(invalid="ignore", divide="ignore"):
@@ -1016,6 +1016,16 @@ def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=Fal
     X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
                                                              use_ecdf, k_bin, nbin_default, nbin, bin_edges)
     if not materialize:
+        # groups of weight 0 contribute w * d = 0 to every distance as long as their values are finite (0 * NaN would
+        # be NaN in the reference, eval_clustering.jl:242-254): leave them out of the on-the-fly tiles
+        keep, start = [], 0
+        for g, (ln, w) in enumerate(zip(glen, gw)):
+            if w != 0 or not np.isfinite(X[:, start:start + ln]).all():
+                keep.append((g, start, int(ln)))
+            start += int(ln)
+        if 0 < len(keep) < len(glen):
+            X = np.asfortranarray(np.concatenate([X[:, s0:s0 + ln] for _, s0, ln in keep], axis=1))
+            glen, gw = glen[[g for g, _, _ in keep]], gw[[g for g, _, _ in keep]]
         return B200FeatureMatrix(X, glen, gw, weights, relative_parameter)
     n = X.shape[0]
     D = np.zeros((n, n), order="F")

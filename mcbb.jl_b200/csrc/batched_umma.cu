@@ -29,15 +29,9 @@
 #include <cmath>
 #include <vector>
 
-#include "fixedpoint.cuh"
-#include "lane_core.cuh"
-#include "umma_math.cuh"  // after lane_core.cuh: keeps the constant-bank layout of the kernel
+#include "umma_common.cuh"
 
 namespace mcbb {
-
-constexpr int UM_NSLOT = 8;  // u, k1..k7
-constexpr int UM_A_BYTES = 128 * 128;
-constexpr int UM_MAX_KL_BINS = 64;
 
 struct UmmaArgs {
     int N, KS, n_sms;
@@ -61,202 +55,35 @@ struct UmmaArgs {
     double* smp;
 };
 
-struct UmSlotCtl {
-    long long run, fin_run, iter, nrej, natt;
-    double t, dt, dts, lq, al1s, d0, d1, dt0, t_old, dts_old;  // lq = ln(qold) of the PI controller
-    double hstep;  // step of the stage inputs: dts while running, the probe step dt0 while measuring the initial dt
-    int mode, isave, ret, clipped, accept, fresh, fin, fin_ok, s0, s1;
-};
-
-// ---- tcgen05 / mbarrier plumbing (PTX ISA 8.7, sm_100a) ------------------------------------------------------
-__device__ __forceinline__ unsigned um_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-// shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets in 16-byte units
-__device__ __forceinline__ unsigned long long um_desc(const unsigned addr, const unsigned lbo, const unsigned sbo) {
-    return (unsigned long long)((addr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-// A operand from tensor memory (lane = row, 32-bit column = four consecutive K bytes)
-__device__ __forceinline__ void um_mma_i8_ts(const unsigned d_tmem, const unsigned a_tmem, const unsigned long long db,
-                                             const unsigned idesc, const unsigned accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void um_tmem_st32(const unsigned taddr, const unsigned (&w)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n\t"
-        "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
-        "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]),
-        "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]),
-        "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]),
-        "r"(w[31])
-        : "memory");
-}
-
-__device__ __forceinline__ void um_commit(const unsigned mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-
-__device__ __forceinline__ void um_mbar_wait(const unsigned mbar, const unsigned parity) {
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(mbar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware until the phase flips
-            : "memory");
-    }
-}
-
-// 32 lanes x 32 columns (two trajectories), load and wait in one statement
-__device__ __forceinline__ void um_tmem_ld32(const unsigned taddr, unsigned (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-
-// tensor-memory allocation: power of two >= 32 columns
-template <int JB>
-struct UmCols {
-    static constexpr unsigned need = 16 * JB + 32;  // accumulators + the A operand
-    static constexpr unsigned value = need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
-};
-
-// warp-level sum with a fixed tree (deterministic)
-__device__ __forceinline__ double um_warp_sum(double p) {
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-    return p;
-}
-
-// Tsit5 dense-output weights b_q(theta) (OrdinaryDiffEq tsit_interpolants): b_0 = th (1 + th (A + th (B + th C))),
-// b_q = th^2 (A + th (B + th C)) for q = 1..6; lane q of a warp evaluates polynomial q
-static __constant__ double c_um_bth[7][3] = {
-    {-2.763706197274826, 2.9132554618219126, -1.0530884977290216},
-    {0.13169999999999998, -0.2234, 0.1017},
-    {3.9302962368947516, -5.941033872131505, 2.490627285651253},
-    {-12.411077166933676, 30.33818863028232, -16.548102889244902},
-    {37.50931341651104, -88.1789048947664, 47.37952196281928},
-    {-27.896526289197286, 65.09189467479366, -34.87065786149661},
-    {1.5, -4., 2.5}};
-
-// a / b for normal, well-scaled b without the compiler's slow-path branch: reciprocal seed, two Newton steps,
-// one residual correction (used only inside the step-size error norm)
-__device__ __forceinline__ double um_div(const double a, const double b) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
-    double e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    const double q = a * y;
-    return fma(fma(-b, q, a), y, q);
-}
-
-// KL divergence of the saved samples of one state dimension to the normal distribution with their mean and standard
-// deviation, on the histogram of empirical_1D_KL_divergence_hist (eval_mc_prob.jl:312-330; same arithmetic as the lane
-// kernel, lane_core.cuh).  Sample k of the dimension is smp[k * stride], k = 1 .. n_t - 1.
-// The per-thread histogram lives in shared memory when the caller can lend some (hs[bin * 128 + thread]): a local
-// array indexed by a data-dependent bin scatters over 32 cache lines per warp access.
-__device__ __noinline__ double um_kl_hist(const double* smp, const long long stride, const int n_t, const double mu, const double sig,
-                             const int nb, const double nstd, const double tol, unsigned short* hs) {
-    const double NaN = nan("");
-    const double kq = (nb - 1) / 2.;
-    const double bw = (nstd * sig) / kq;
-    const double start = mu - kq * bw, stop = mu + kq * bw;
-    int nc = 0;
-    if (sig >= tol) nc = julia_range_len(start, bw, stop);
-    if (nc > nb) nc = nb;
-    if (sig != sig) return NaN;  // NaN std (non-finite samples): the reference's KL is NaN
-    if (nc <= 0) return 0.;      // sig < sig_tol
-    int hist[UM_MAX_KL_BINS];
-    if (hs) {
-        for (int b = 0; b < nc; b++) hs[b * 128] = 0;
-    } else {
-        for (int b = 0; b < nc; b++) hist[b] = 0;
-    }
-    const double hb = bw / 2.;
-    const double last_edge = kq * bw + hb;  // `mu` missing: eval_mc_prob.jl:328
-    const double e1 = start - hb, ibw = 1. / bw;
-    auto edge = [&](const int m) { return fma((double)(m - 1), bw, start) - hb; };  // edges 1..nc (ascending)
-    // fit(Histogram, u, edges; closed=:left) = searchsortedlast on the vector [edge(1..nc), last_edge].  Its bisection
-    // probes last_edge only after x >= edge(nc) (everything before it is ascending), so the result is: r = position
-    // among the ascending edges — taken directly and corrected against the very same edge expression — and, when
-    // r == nc, bin nc if x < last_edge, else outside.  Eight samples are fetched at a time (the scratch lives in
-    // L2 / HBM: keep the loads in flight).
-    for (int k0 = 1; k0 < n_t; k0 += 8) {
-        double xs[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) xs[q] = (k0 + q < n_t) ? __ldcg(smp + (long long)(k0 + q) * stride) : nan("");
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const double x = xs[q];
-            if (!(x == x)) continue;  // NaN compares false everywhere: the bisection runs off the right end
-            const double f = floor((x - e1) * ibw) + 1.;
-            int r = f < 0. ? 0 : (f > (double)nc ? nc : (int)f);
-            while (r >= 1 && x < edge(r)) r--;
-            while (r < nc && x >= edge(r + 1)) r++;
-            if (r >= 1 && (r < nc || x < last_edge)) {
-                if (hs)
-                    hs[(r - 1) * 128] += 1;
-                else
-                    hist[r - 1] += 1;
-            }
-        }
-    }
-    double tot = 0., rs = 0.;
-    double qn[UM_MAX_KL_BINS];  // unnormalised normal weights of the bin centres
-    for (int b = 0; b < nc; b++) {
-        if (hs) hist[b] = hs[b * 128];
-        tot += (double)hist[b];
-        const double z = (fma((double)b, bw, start) - mu) / sig;
-        qn[b] = exp(-(z * z) / 2.);
-        rs += qn[b];
-    }
-    if (tot == 0.) return NaN;  // 0/0 weights -> NaN, as StatsBase would give
-    double kl = 0.;
-    for (int b = 0; b < nc; b++) {
-        const double p = (double)hist[b] / tot;
-        if (p > 0.) {
-            const double q = qn[b] / rs;
-            kl += p * log(p / q);
-        }
-    }
-    return kl;
-}
-
 // TIMING = true: thread 0 of every CTA accumulates clock64() per phase into a.timing (development aid,
 // MCBB_UMMA_TIMING=1; the compiler may move arithmetic across the ticks, so treat the split as approximate)
 // KL = true: the instantiation that keeps the saved samples and evaluates the KL-histogram measure (a separate
 // instantiation: the call and the sample stores cost the plain mean / std kernel ~5 % through register allocation)
-template <int JB, int MINB, bool TIMING = false, bool KL = false>
-__global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs a) {
+// NW = warps per tensor-memory lane quadrant.  NW = 1: one thread per oscillator row carries all JB trajectories of the
+// CTA.  NW = 2: two threads per row (warps w and w + 4 may both address TMEM lanes 32 (w % 4) ..), each carrying JB / 2
+// trajectories: twice the warps per scheduler for the same tensor memory and shared memory, half the serial work per
+// warp and stage.
+template <int JB, int MINB, bool TIMING = false, bool KL = false, int NW = 1>
+__global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const UmmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NT = 128 * NW;          // threads per CTA
+    constexpr int JBT = JB / NW;          // trajectories per thread
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int wq = wid & 3;               // tensor-memory lane quadrant of this warp
+    const int j0 = (NW == 1) ? 0 : (wid >> 2) * JBT;  // first trajectory slot of this thread (warp-uniform)
     const int N = a.N;
-    const int row = tid;
+    const int row = tid & 127;
     const bool valid = row < N;
     const int rr = valid ? row : N;  // idle lanes (rows >= N of the MMA tile) work on a dummy row: no branches
     const SolverDev& o = a.o;
     const int n_t = a.io.n_t;
     const long long n_mc = a.io.n_mc;
     constexpr unsigned NCOL = 16 * JB;            // MMA N: 16 accumulator columns per trajectory (7 + 7 digits, 2 zero)
-    constexpr int G = JB <= 4 ? JB : (JB % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved (2 measures the same)
+    constexpr int G = JBT <= 4 ? JBT : (JBT % 3 == 0 ? 3 : 4);  // trajectories whose dependent chains are interleaved (2 measures the same)
     constexpr int RS = UM_NSLOT * JB + 2;         // row stride (doubles) = 2 (mod 4): 16-byte aligned thread-private
                                                   // blocks whose 128-bit accesses are bank-conflict free
-    static_assert(JB % G == 0 && JB % 2 == 0, "batch must be a multiple of the interleave group and even");
+    static_assert(JB % NW == 0 && JBT % G == 0, "trajectories per thread must be a multiple of the interleave group");
+    static_assert(!KL || NW == 1, "the KL instantiation lends the digit panel to 128 per-thread histograms");
 
     unsigned char* sB = smem;                                   // [JB][128][16]
     double* sm_k = (double*)(sB + JB * 2048);                   // [N + 1][JB][8] (+2 pad)  u, k1..k7 per element
@@ -273,10 +100,10 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 
 #define KP(slot, j) kb[(j)*UM_NSLOT + (slot)]
 
-    for (int i = tid; i < JB * 2048 / 16; i += 128) ((uint4*)sB)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < (N + 1) * RS; i += 128) sm_k[i] = 0.;  // stage slots are read before written (x 0)
+    for (int i = tid; i < JB * 2048 / 16; i += NT) ((uint4*)sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (N + 1) * RS; i += NT) sm_k[i] = 0.;  // stage slots are read before written (x 0)
     // the controller lanes sit in a different warp (scheduler partition) for each CTA resident on an SM
-    const int cw = (blockIdx.x / a.n_sms) & 3;
+    const int cw = (blockIdx.x / a.n_sms) & (4 * NW - 1);
     const bool is_ctl = (wid == cw) && lane < JB;
     if (is_ctl) {
         UmSlotCtl& c = ctl[lane];
@@ -288,7 +115,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(mbar_full));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_full), "n"(4 * NW));
     }
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)),
@@ -300,10 +127,11 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
-    const unsigned tmem_row = tmem_base + ((unsigned)(32 * wid) << 16);  // this warp's 32 TMEM lanes
+    const unsigned tmem_row = tmem_base + ((unsigned)(32 * wq) << 16);  // this warp's 32 TMEM lanes
     const unsigned tmem_a = tmem_base + NCOL;                            // A operand: 32 columns behind the accumulators
-    {  // row r of A -> lane r: 128 K bytes = 32 columns
+    {  // row r of A -> lane r: 128 K bytes = 32 columns (the first warp of every quadrant writes it)
         unsigned w[32];
+        if (wid < 4) {
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const uint4 t4 = reinterpret_cast<const uint4*>(a.a_img + (size_t)row * 128)[q];
@@ -313,6 +141,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             w[4 * q + 3] = t4.w;
         }
         um_tmem_st32(tmem_row + NCOL, w);
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -331,9 +160,9 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
     unsigned phase = 0;
 
     // thread-private state of the JB elements of this oscillator row
-    double sv[JB], cv[JB], un[JB], am[JB], a2[JB], as[JB];
+    double sv[JBT], cv[JBT], am[JBT], a2[JBT], as[JBT];
 #pragma unroll
-    for (int j = 0; j < JB; j++) sv[j] = cv[j] = un[j] = am[j] = a2[j] = as[j] = 0.;
+    for (int j = 0; j < JBT; j++) sv[j] = cv[j] = am[j] = a2[j] = as[j] = 0.;
 
     auto begin_attempt = [&](UmSlotCtl& c) -> bool {
         if (++c.iter > o.maxiters) {
@@ -454,17 +283,25 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 #pragma unroll
         for (int j = 0; j < JB; j++) {
             const UmSlotCtl& c = ctl[j];
-            if (c.accept) {  // uniform over the CTA; idle lanes run along on the dummy row
-                const int ks0 = c.s0 < 1 ? 1 : c.s0, ks1 = c.s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
-                if (ks0 < ks1) {
-                    const double dts = c.dts_old, t_old = c.t_old;
-                    double kk[8];
+            any_init |= (c.mode == MODE_INIT);
+            runmask |= (c.mode == MODE_RUN ? 1u : 0u) << j;
+            any_fin |= (c.fin != 0);
+        }
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const double2 t2 = reinterpret_cast<const double2*>(kb + j * UM_NSLOT)[q];
-                        kk[2 * q] = t2.x;
-                        kk[2 * q + 1] = t2.y;
-                    }
+        for (int jj = 0; jj < JBT; jj++) {
+            const int j = j0 + jj;
+            const UmSlotCtl& c = ctl[j];
+            if (c.accept) {  // uniform over the warps that carry slot j; idle lanes run along on the dummy row
+                const int ks0 = c.s0 < 1 ? 1 : c.s0, ks1 = c.s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
+                const double dts = c.dts_old, t_old = c.t_old;
+                double kk[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double2 t2 = reinterpret_cast<const double2*>(kb + j * UM_NSLOT)[q];
+                    kk[2 * q] = t2.x;
+                    kk[2 * q + 1] = t2.y;
+                }
+                if (ks0 < ks1) {
                     const int lq = lane < 7 ? lane : 0;
                     const double pa = c_um_bth[lq][0], pb = c_um_bth[lq][1], pc = c_um_bth[lq][2];
                     for (int k = ks0; k < ks1; k++) {
@@ -481,31 +318,36 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                                 const double twopi = 6.283185307179586, pi = 3.141592653589793;
                                 double vv = julia_mod_pos(x, twopi);
                                 if (vv > pi) vv -= twopi;
-                                as[j] = x - vv;
+                                as[jj] = x - vv;
                                 x = vv;
                             } else {
-                                x = x - as[j];
+                                x = x - as[jj];
                             }
                         }
                         if (KL && valid) a.smp[(((size_t)blockIdx.x * JB + j) * n_t + k) * N + row] = x;
-                        const double delta = x - am[j];
+                        const double delta = x - am[jj];
                         if (fabs(delta) <= 1.7976931348623157e308) {
-                            const double mnew = fma(delta, um_div(1., (double)k), am[j]);
-                            a2[j] = fma(delta, x - mnew, a2[j]);
-                            am[j] = mnew;
+                            const double mnew = fma(delta, um_div(1., (double)k), am[jj]);
+                            a2[jj] = fma(delta, x - mnew, a2[jj]);
+                            am[jj] = mnew;
                         } else {
-                            am[j] = nonfinite_mean(am[j], x);
-                            a2[j] = nan("");
+                            am[jj] = nonfinite_mean(am[jj], x);
+                            a2[jj] = nan("");
                         }
                     }
                 }
-                KP(0, j) = un[j];
-                KP(1, j) = KP(7, j);  // FSAL
+                // the accepted state: the same expression (bit for bit) the error estimate evaluated before the
+                // controller ran — recomputed here instead of being carried in registers across the barrier
+                double lu = TS_A(5, 0) * kk[1];
+#pragma unroll
+                for (int q = 1; q < 6; q++) lu = fma(TS_A(5, q), kk[1 + q], lu);
+                KP(0, j) = fma(dts, lu, kk[0]);
+                KP(1, j) = kk[7];  // FSAL
             }
             if (c.fin && valid && fpos >= 0) {
                 const bool ok = c.fin_ok != 0;
-                const double mean = ok ? am[j] : nan("");
-                const double sd = ok ? sqrt((a2[j] < 0. ? 0. : a2[j]) / (double)(n_t - 2)) : nan("");
+                const double mean = ok ? am[jj] : nan("");
+                const double sd = ok ? sqrt((a2[jj] < 0. ? 0. : a2[jj]) / (double)(n_t - 2)) : nan("");
                 double kl = nan("");
                 if (KL && ok)
                     kl = um_kl_hist(a.smp + ((size_t)blockIdx.x * JB + j) * n_t * N + row, N, n_t, mean, sd, a.kl_bins, a.kl_nstd,
@@ -522,11 +364,8 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
 #pragma unroll
                     for (int q = 1; q < UM_NSLOT; q++) KP(q, j) = 0.;  // no stale values from the slot's previous run
                 }
-                am[j] = a2[j] = as[j] = 0.;
+                am[jj] = a2[jj] = as[jj] = 0.;
             }
-            any_init |= (c.mode == MODE_INIT);
-            runmask |= (c.mode == MODE_RUN ? 1u : 0u) << j;
-            any_fin |= (c.fin != 0);
         }
         if (KL && any_fin) __syncthreads();  // the digit panel served as histogram scratch: all done before it is rewritten
         if (all_done) break;
@@ -544,11 +383,11 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             const double ci0 = (s == 1) ? 1. : 0.;  // initial-dt probe: u0 + dt0 f(u0) in the second evaluation
             // (a) stage input Y -> sin, cos -> the 16 digit bytes of this (row, trajectory) element
 #pragma unroll
-            for (int g0 = 0; g0 < JB; g0 += G) {
+            for (int g0 = 0; g0 < JBT; g0 += G) {
                 double y[G];
 #pragma unroll
                 for (int i = 0; i < G; i++) {
-                    const int j = g0 + i;
+                    const int j = j0 + g0 + i;
                     const double2* kq = reinterpret_cast<const double2*>(kb + j * UM_NSLOT);
                     const double2 k01 = kq[0], k23 = kq[1], k45 = kq[2];  // (u, k1) (k2, k3) (k4, k5)
                     const double k6 = kq[3].x;  // 128-bit like the others: 64-bit accesses at this row stride conflict 2-way
@@ -567,12 +406,12 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                     uint4 dg;
                     um_fixed52(sv[g0 + i], dg.x, dg.y);
                     um_fixed52(cv[g0 + i], dg.z, dg.w);
-                    *reinterpret_cast<uint4*>(sB_row + (g0 + i) * 2048) = dg;  // rows >= N meet zero columns of A
+                    *reinterpret_cast<uint4*>(sB_row + (j0 + g0 + i) * 2048) = dg;  // rows >= N meet zero columns of A
                 }
             }
             UM_TICK(2)  // stage input, sincos, digits
             // (b) D = A * digits on the tensor core.  No CTA barrier: every warp publishes its rows (generic -> async
-            //     proxy fence, then a release-arrive on a 4-count mbarrier); the lane whose arrival completes the phase
+            //     proxy fence, then a release-arrive on a 4 NW-count mbarrier); the lane whose arrival completes the phase
             //     (pending count 1, profiles/microbench/mbar_probe.cu) issues the MMAs; their completion arrives on
             //     the second mbarrier, the one everybody waits on.
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -596,59 +435,65 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                 }
             }
             // Only the issuing warp polls the completion mbarrier (a polling warp burns issue slots: ~10 % of all
-            // issued instructions when all four polled); the other three sleep on hardware barrier 1 until it joins.
+            // issued instructions when all four polled); the others sleep on hardware barrier 1 until it joins.
             issuer = __shfl_sync(0xffffffffu, issuer, 0);
             UM_TICK(3)  // publish (+ issue)
             if (issuer) {
                 um_mbar_wait(mbar, phase);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
             UM_TICK(4)  // MMA wait
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // (c) row r of P, Q from tensor memory, int64 recombination, k = a1 (c P - s Q) + w
-            double kv[JB];
+            double kv[JBT];
             double* const kst = kb + 2 + s;
+            auto to_k = [&](const int jj, const unsigned* w) {
+                const int j = j0 + jj;
+                const double P = um_recombine(w[0], w[1], w[2], w[3], w[4], w[5], w[6], degh);
+                const double Q = um_recombine(w[8], w[9], w[10], w[11], w[12], w[13], w[14], degh);
+                kv[jj] = fma(ctl[j].al1s, cv[jj] * P - sv[jj] * Q, bias);
+                kst[j * UM_NSLOT] = ((runmask >> j) & 1u) ? kv[jj] : 0.;  // slots that do not integrate keep zeros
+            };
 #pragma unroll
-            for (int g0 = 0; g0 < JB; g0 += 2) {  // two trajectories per tensor-memory load
+            for (int g0 = 0; g0 + 1 < JBT; g0 += 2) {  // two trajectories per tensor-memory load
                 unsigned v[32];
-                um_tmem_ld32(tmem_row + 16u * g0, v);
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int j = g0 + i;
-                    const unsigned* w = v + 16 * i;
-                    const double P = um_recombine(w[0], w[1], w[2], w[3], w[4], w[5], w[6], degh);
-                    const double Q = um_recombine(w[8], w[9], w[10], w[11], w[12], w[13], w[14], degh);
-                    kv[j] = fma(ctl[j].al1s, cv[j] * P - sv[j] * Q, bias);
-                    kst[j * UM_NSLOT] = ((runmask >> j) & 1u) ? kv[j] : 0.;  // slots that do not integrate keep zeros
-                }
+                um_tmem_ld32(tmem_row + 16u * (unsigned)(j0 + g0), v);
+                to_k(g0, v);
+                to_k(g0 + 1, v + 16);
+            }
+            if (JBT & 1) {
+                unsigned v[16];
+                um_tmem_ld16(tmem_row + 16u * (unsigned)(j0 + JBT - 1), v);
+                to_k(JBT - 1, v);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads done before the next MMA
             UM_TICK(5)  // accumulators -> k
             if (any_init && s < 2) {  // initial step size (OrdinaryDiffEq initdt.jl), only in rounds that start a run
 #pragma unroll
-                for (int j = 0; j < JB; j++) {
+                for (int jj = 0; jj < JBT; jj++) {
+                    const int j = j0 + jj;
                     if (ctl[j].mode == MODE_INIT) {
                         double p0 = 0., p1 = 0.;
                         if (valid) {
                             const double u0 = KP(0, j);
                             const double sk = o.abstol + fabs(u0) * o.reltol;
                             if (s == 0) {
-                                KP(1, j) = kv[j];
-                                const double w0 = u0 / sk, w1 = kv[j] / sk;
+                                KP(1, j) = kv[jj];
+                                const double w0 = u0 / sk, w1 = kv[jj] / sk;
                                 p0 = w0 * w0;
                                 p1 = w1 * w1;
                             } else {
-                                const double vv = (kv[j] - KP(1, j)) / sk;
+                                const double vv = (kv[jj] - KP(1, j)) / sk;
                                 p0 = vv * vv;
                             }
                         }
                         p0 = um_warp_sum(p0);
                         p1 = um_warp_sum(p1);
                         if (lane == 0) {
-                            sm_red0[wid * JB + j] = p0;
-                            sm_red1[wid * JB + j] = p1;
+                            sm_red0[wq * JB + j] = p0;
+                            sm_red1[wq * JB + j] = p1;
                         }
                     }
                 }
@@ -680,12 +525,13 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
             }
         }
 
-        // ---- error estimate partials and the candidate new state (branch-free; the controller ignores idle slots) ---
+        // ---- error estimate partials (branch-free; the controller ignores idle slots) -----------------------------
         {
-            double pe[JB];
-            bool bad[JB];
+            double pe[JBT];
+            bool bad[JBT];
 #pragma unroll
-            for (int j = 0; j < JB; j++) {
+            for (int jj = 0; jj < JBT; jj++) {
+                const int j = j0 + jj;
                 const double dts = ctl[j].dts;
                 double kk[8];  // u, k1..k7: four 128-bit loads
 #pragma unroll
@@ -704,20 +550,19 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
                 const double u0 = kk[0];
                 const double u1 = fma(dts, lu, u0);
                 const double r = um_div(dts * lin, o.abstol + fmax(fabs(u0), fabs(u1)) * o.reltol);
-                pe[j] = valid ? r * r : 0.;
-                un[j] = u1;
-                bad[j] = valid && (u1 != u1);
+                pe[jj] = valid ? r * r : 0.;
+                bad[jj] = valid && (u1 != u1);
             }
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1)
 #pragma unroll
-                for (int j = 0; j < JB; j++) pe[j] += __shfl_xor_sync(0xffffffffu, pe[j], off);
+                for (int jj = 0; jj < JBT; jj++) pe[jj] += __shfl_xor_sync(0xffffffffu, pe[jj], off);
 #pragma unroll
-            for (int j = 0; j < JB; j++) {
-                const bool anybad = __any_sync(0xffffffffu, bad[j]);
+            for (int jj = 0; jj < JBT; jj++) {
+                const bool anybad = __any_sync(0xffffffffu, bad[jj]);
                 if (lane == 0) {
-                    sm_red0[wid * JB + j] = pe[j];
-                    sm_red1[wid * JB + j] = anybad ? 1. : 0.;
+                    sm_red0[wq * JB + j0 + jj] = pe[jj];
+                    sm_red1[wq * JB + j0 + jj] = anybad ? 1. : 0.;
                 }
             }
         }
@@ -734,16 +579,17 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma(const UmmaArgs
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
 }
 
-template <int JB, int MINB, bool TIMING = false, bool KL = false>
+template <int JB, int MINB, bool TIMING = false, bool KL = false, int NW = 1>
 static int launch_umma_one(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_batched_umma<JB, MINB, TIMING, KL><<<grid, 128, smem, st>>>(a);
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING, KL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_umma<JB, MINB, TIMING, KL, NW><<<grid, 128 * NW, smem, st>>>(a);
     MCBB_LAUNCHED();
     return 0;
 }
-template <int JB, int MINB, bool TIMING = false>
+template <int JB, int MINB, bool TIMING = false, int NW = 1>
 static int launch_umma_spec(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
-    return a.need_kl ? launch_umma_one<JB, MINB, false, true>(a, smem, grid, st) : launch_umma_one<JB, MINB, TIMING, false>(a, smem, grid, st);
+    if (a.need_kl) return launch_umma_one<JB, MINB, false, true, 1>(a, smem, grid, st);  // KL: one thread per row
+    return launch_umma_one<JB, MINB, TIMING, false, NW>(a, smem, grid, st);
 }
 
 static size_t umma_smem_bytes(int JB, int N, int n_t) {
@@ -825,12 +671,16 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.io = io;
 
     // configurations (trajectories per CTA, CTAs per SM): TMEM columns and shared memory both have to fit
-    struct Cfg { int jb, per_sm; };
-    static const Cfg cfgs[] = {{6, 4}, {4, 4}, {6, 3}, {8, 2}, {4, 3}, {4, 2}, {2, 2}, {2, 1}};
+    struct Cfg { int jb, per_sm, nw; };
+    static const Cfg cfgs[] = {{6, 4, 1}, {4, 4, 1}, {6, 3, 1}, {8, 2, 1}, {4, 3, 1}, {4, 2, 1}, {2, 2, 1}, {2, 1, 1},
+                               // two threads per oscillator row (experiment switch "umma_nw" = 2)
+                               {6, 3, 2}, {6, 4, 2}, {4, 4, 2}, {6, 2, 2}};
     int want_jb = (int)tune_get("umma_jb", 0);
     int want_per = (int)tune_get("umma_per_sm", 0);
+    const int want_nw = F.need_kl ? 1 : (int)tune_get("umma_nw", 1);
     const Cfg* pick = nullptr;
     for (const Cfg& c : cfgs) {
+        if (c.nw != want_nw) continue;
         if (want_jb && c.jb != want_jb) continue;
         if (want_per && c.per_sm != want_per) continue;
         const size_t need = umma_smem_bytes(c.jb, N, io.n_t);
@@ -877,7 +727,12 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
         *handled = true;
         return 0;
     }
-    if (pick->jb == 6 && pick->per_sm == 4) rc = launch_umma_spec<6, 4>(a, smem, grid, st);
+    if (pick->nw == 2) {
+        if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3, false, 2>(a, smem, grid, st);
+        else if (pick->jb == 6 && pick->per_sm == 4) rc = launch_umma_spec<6, 4, false, 2>(a, smem, grid, st);
+        else if (pick->jb == 4 && pick->per_sm == 4) rc = launch_umma_spec<4, 4, false, 2>(a, smem, grid, st);
+        else if (pick->jb == 6 && pick->per_sm == 2) rc = launch_umma_spec<6, 2, false, 2>(a, smem, grid, st);
+    } else if (pick->jb == 6 && pick->per_sm == 4) rc = launch_umma_spec<6, 4>(a, smem, grid, st);
     else if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 4) rc = launch_umma_spec<4, 4>(a, smem, grid, st);
     else if (pick->jb == 8 && pick->per_sm == 2) rc = launch_umma_spec<8, 2>(a, smem, grid, st);

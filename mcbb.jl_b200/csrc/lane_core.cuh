@@ -116,6 +116,15 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F,
 #define B(ch, b) bins[((size_t)(ch)*nb + (b)) * bs]
 #define CM(p) como[(size_t)(p)*bs]  /* co-moments of channel pairs (i > j), p = i(i-1)/2 + j */
     const bool corr = F.matrix_meas != MCBB_MAT_NONE;  // correlation_ecdf or correlation_hist
+    // DiffEqBase.ODE_DEFAULT_NORM works on the ELEMENTS of the state array: for the Complex{Float64} state of
+    // Stuart-Landau an element is one complex number — its error scale uses the complex modulus (shared by both
+    // components) and the RMS divides by N, not 2N (calculate_residuals / ODE_DEFAULT_NORM, DiffEqBase 6.10.1)
+    constexpr bool CPLX = (SYS == MCBB_SYS_STUART_LANDAU);
+    const int n_elem = CPLX ? n / 2 : n;
+    auto elem_abs = [&](const int slot, const int d) -> double {
+        if (CPLX) return hypot(X(slot, d & ~1), X(slot, d | 1));
+        return fabs(X(slot, d));
+    };
 
     int mode = MODE_FETCH;
     long long run = -1;
@@ -487,24 +496,24 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F,
                     double a0 = 0., a1 = 0.;
                     for (int d = 0; d < n; d++) {
                         const double u0 = X(SLOT_U, d);
-                        const double sk = o.abstol + fabs(u0) * o.reltol;
+                        const double sk = o.abstol + elem_abs(SLOT_U, d) * o.reltol;
                         const double v0 = u0 / sk, v1 = X(SLOT_K1, d) / sk;
                         a0 = fma(v0, v0, a0);
                         a1 = fma(v1, v1, a1);
                     }
-                    d0 = sqrt(a0 / n);
-                    d1 = sqrt(a1 / n);
+                    d0 = sqrt(a0 / n_elem);
+                    d1 = sqrt(a1 / n_elem);
                     dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
                     dt0 = fmin(dt0, o.dtmax);
                     for (int d = 0; d < n; d++) X(SLOT_TMP, d) = fma(dt0, X(SLOT_K1, d), X(SLOT_U, d));
                 } else if (s == 1) {
                     double a2 = 0.;
                     for (int d = 0; d < n; d++) {
-                        const double sk = o.abstol + fabs(X(SLOT_U, d)) * o.reltol;
+                        const double sk = o.abstol + elem_abs(SLOT_U, d) * o.reltol;
                         const double v = (X(SLOT_K1 + 1, d) - X(SLOT_K1, d)) / sk;
                         a2 = fma(v, v, a2);
                     }
-                    const double d2 = sqrt(a2 / n) / dt0;
+                    const double d2 = sqrt(a2 / n_elem) / dt0;
                     const double dm = fmax(d1, d2);
                     const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10., -(2. + log10(dm)) / 5.);
                     dt = fmin(fmin(100. * dt0, dt1), o.dtmax);
@@ -526,10 +535,10 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F,
                     double lin = TS_BT(0) * X(SLOT_K1, d);
                     for (int j = 1; j < 7; j++) lin = fma(TS_BT(j), X(SLOT_K1 + j, d), lin);
                     const double ut = dts * lin;
-                    const double r = ut / (o.abstol + fmax(fabs(X(SLOT_U, d)), fabs(X(SLOT_TMP, d))) * o.reltol);
+                    const double r = ut / (o.abstol + fmax(elem_abs(SLOT_U, d), elem_abs(SLOT_TMP, d)) * o.reltol);
                     e2 = fma(r, r, e2);
                 }
-                const double EEst = sqrt(e2 / n);
+                const double EEst = sqrt(e2 / n_elem);
                 if (EEst == 0.) {
                     q = 1. / o.qmax;
                 } else {

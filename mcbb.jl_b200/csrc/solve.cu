@@ -306,6 +306,8 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
                         const SolveIO& io, cudaStream_t st, bool* handled);
 int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
                         const SolveIO& io, cudaStream_t st, bool* handled);
+int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
+                           const SolveIO& io, cudaStream_t st, bool* handled);
 int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
                             const SolveIO& io, cudaStream_t st, bool* handled);
 
@@ -328,6 +330,8 @@ int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const Sol
     // and per-run solver options run the lane kernels
     if (!io.saved && !io.solver_par) {
         if (int rc = launch_batched_umma(hs, S, o, F, io, st, &handled)) return rc;  // tcgen05 + tensor memory
+        if (handled) return 0;
+        if (int rc = launch_batched_umma_sl(hs, S, o, F, io, st, &handled)) return rc;  // Stuart-Landau on the same path
         if (handled) return 0;
         if (int rc = launch_batched_imma(hs, S, o, F, io, st, &handled)) return rc;
         if (handled) return 0;

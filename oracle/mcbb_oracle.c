@@ -192,22 +192,35 @@ static sopts resolve_opts(const mcbb_solver_opts* o) { /* DiffEq defaults, SURVE
     return s;
 }
 
-static double rms_scaled(const double* x, const double* sk, int n) {
+/* DiffEqBase.ODE_DEFAULT_NORM: sqrt(sum(abs2, x) / length(x)) over the ELEMENTS of the state array.  For a
+ * Complex{Float64} state (Stuart-Landau) an element is one complex number: the scale of element i is
+ * abstol + abs(z_i) * reltol with the complex modulus (ODE_DEFAULT_NORM(z::Complex) = abs(z)), both components are
+ * divided by it, and length(x) = N — not 2N.  x and sk are indexed by real component; sk[2i] == sk[2i+1] then. */
+static int is_complex_state(const sysctx* S) { return S->d->system == MCBB_SYS_STUART_LANDAU; }
+
+static double rms_scaled(const double* x, const double* sk, int n, int cplx) {
     double acc = 0.;
     for (int i = 0; i < n; i++) {
         const double v = x[i] / sk[i];
         acc += v * v;
     }
-    return sqrt(acc / n);
+    return sqrt(acc / (cplx ? n / 2 : n));
+}
+
+/* element-wise magnitude used in the error scale: |x| for reals, the modulus of the complex element otherwise */
+static double elem_abs(const double* u, int i, int cplx) {
+    return cplx ? hypot(u[i & ~1], u[i | 1]) : fabs(u[i]);
 }
 
 /* OrdinaryDiffEq initdt.jl (Hairer-Wanner), order 5.  f0 = f(u0,t0) is passed in. */
 static double tsit5_initdt(const sysctx* S, const sopts* o, const double* u0, const double* f0, int n,
                            double* w1, double* w2, double* w3) {
+    const int cplx = is_complex_state(S);
+    const int ne = cplx ? n / 2 : n;
     double* sk = w1;
-    for (int i = 0; i < n; i++) sk[i] = o->abstol + fabs(u0[i]) * o->reltol;
-    const double d0 = rms_scaled(u0, sk, n);
-    const double d1 = rms_scaled(f0, sk, n);
+    for (int i = 0; i < n; i++) sk[i] = o->abstol + elem_abs(u0, i, cplx) * o->reltol;
+    const double d0 = rms_scaled(u0, sk, n, cplx);
+    const double d1 = rms_scaled(f0, sk, n, cplx);
     double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
     dt0 = fmin(dt0, o->dtmax);
     double* u1 = w2;
@@ -219,7 +232,7 @@ static double tsit5_initdt(const sysctx* S, const sopts* o, const double* u0, co
         const double v = (f1[i] - f0[i]) / sk[i];
         acc += v * v;
     }
-    const double d2 = sqrt(acc / n) / dt0;
+    const double d2 = sqrt(acc / ne) / dt0;
     const double dm = fmax(d1, d2);
     double dt1;
     if (dm <= 1e-15)
@@ -233,6 +246,7 @@ static double tsit5_initdt(const sysctx* S, const sopts* o, const double* u0, co
  * Returns the retcode; *n_saved = number of columns actually written (all nt on success). */
 static int integrate(const sysctx* S, const sopts* o, const double* u0, int n, const double* tsave, int nt,
                      double* saved, int64_t* nsteps, int64_t* nrej, int* n_saved, double* work /* 12n */) {
+    const int cplx = is_complex_state(S);
     double* u = work;
     double* k[7];
     for (int s = 0; s < 7; s++) k[s] = work + (size_t)(1 + s) * n;
@@ -368,10 +382,11 @@ static int integrate(const sysctx* S, const sopts* o, const double* u0, int n, c
         for (int i = 0; i < n; i++) {
             const double ut = dts * (c_bt1 * k[0][i] + c_bt2 * k[1][i] + c_bt3 * k[2][i] + c_bt4 * k[3][i] +
                                      c_bt5 * k[4][i] + c_bt6 * k[5][i] + c_bt7 * k[6][i]);
-            const double r = ut / (o->abstol + fmax(fabs(u[i]), fabs(unew[i])) * o->reltol);
+            /* calculate_residuals: ut / (abstol + max(norm(u_i), norm(unew_i)) * reltol), element-wise norm */
+            const double r = ut / (o->abstol + fmax(elem_abs(u, i, cplx), elem_abs(unew, i, cplx)) * o->reltol);
             acc += r * r;
         }
-        const double EEst = sqrt(acc / n);
+        const double EEst = sqrt(acc / (cplx ? n / 2 : n));
         (*nsteps)++;
         /* stepsize_controller! (standard PI) */
         double q, q11 = 0.;

@@ -119,6 +119,50 @@ def test_c5_bench_tolerances_cluster_membership_ari(c5_bench_ensemble, orc):
     assert np.allclose(cm.par, mesh) and cm.data.shape == rcm.shape and diff <= 0.01
 
 
+def test_c5_default_tolerances_structured_ensemble_ari(gpu, orc):
+    """The bench ensemble above collapses to one cluster under the reference's eps heuristic (the mean of a phase that
+    has drifted to ~500 rad carries +-30 rad of integration noise at reltol 1e-3, in the oracle itself), so its ARI of 1
+    says little.  A shorter horizon (tspan (0, 100), tail 0.5) of the SAME network at the SAME default tolerances keeps
+    cluster structure (a synchronised cluster, a small second one, ~25 % noise).  Even there the reference path is not
+    reproducible to ARI 0.99 against ITSELF at every eps (oracle vs oracle with a 1e-12 perturbed IC: 0.93 at 1x eps),
+    so the bar is north_star's 0.99 wherever the oracle reproduces itself that well, and the oracle's own
+    reproducibility (minus 0.03) otherwise — both printed."""
+    from sklearn.metrics import adjusted_rand_score
+    m = gpu
+    n = 640
+    prob, weights = cases.c5_problem(m, n, tspan=(0.0, 100.0), tail=0.5, seed=30)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    sol = m.solve(prob)
+    psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
+    o = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan)
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    idx = np.argsort(par0[:, 0], kind="stable")
+    ic, par = ic0[idx], par0[idx]
+    ref = orc.solve_features(psys, o, pfeat, ic, par, ts)
+    prng = np.random.default_rng(77)
+    perts = [orc.solve_features(psys, o, pfeat, ic * (1.0 + 1e-12 * prng.standard_normal(ic.shape)), par, ts)
+             for _ in range(2)]
+
+    def dist_of(feat):
+        rsol = m.DEMCBBSol(feat, None, None, ref["retcode"], ref["nsteps"], 400, None)
+        X, gl, gw = m.feature_groups(rsol, prob, weights)
+        return orc.distance_matrix(X, gl, gw)
+    Dref = dist_of(ref["feat"])
+    Dp = [dist_of(p["feat"]) for p in perts]
+    Dg = m.distance_matrix(sol, prob, weights).data
+    K = int(round(0.005 * n))
+    eps0 = float(np.median(np.sort(Dref, axis=0)[:K].sum(axis=0)))  # median(KNN_dist_relative(D))
+    for fac in (1.0, 2.0, 4.0):
+        eps = fac * eps0
+        lab_ref = orc.dbscan(Dref, eps, 5)["assignments"]
+        lab_gpu = m.dbscan(np.asfortranarray(Dg), eps, 5).assignments
+        self_ari = min(adjusted_rand_score(lab_ref, orc.dbscan(D, eps, 5)["assignments"]) for D in Dp)
+        ari = adjusted_rand_score(lab_ref, lab_gpu)
+        print("structured C5 ensemble: eps %.2f (%.0fx heuristic): %d clusters, %d noise; ARI gpu-vs-oracle %.4f, "
+              "oracle-vs-perturbed-oracle %.4f" % (eps, fac, lab_ref.max(), int((lab_ref == 0).sum()), ari, self_ari))
+        assert ari >= min(0.99, self_ari - 0.03), (fac, ari, self_ari)
+
+
 @pytest.mark.parametrize("N", [28, 40, 100])
 def test_batched_sizes_with_a_matrix_measure_fall_through(gpu, orc, N):
     """kuramoto_network sizes that the batched kernels take for (mean, std) must NOT take a problem that also asks for a

@@ -198,6 +198,31 @@ def _ssl(v, x):  # Base.searchsortedlast on a Vector, binary search as in sort.j
     return lo
 
 
+def test_complex_state_error_norm_is_rotation_invariant(orc):
+    """DiffEqBase's default norm works per ELEMENT of the state array: for a Complex{Float64} state the error scale is
+    abstol + |z_i| reltol with the complex modulus and the RMS runs over N complex elements.  Uncoupled Stuart-Landau
+    oscillators (eps = 0) are invariant under z -> z e^{i phi}; with the element-wise complex norm so is every
+    accept / reject decision and every step size — a per-real-component norm would break that."""
+    abi = orc.abi
+    N = 5
+    ring = np.roll(np.eye(N), 1, 0) + np.roll(np.eye(N), -1, 0)
+    psys = abi.PackedSystem(abi.SYS_STUART_LANDAU, N, 2 * N, [0.0, 1.0, 2.0, 1.0, 1.0], [], mat_a=ring, mat_b=ring)
+    opts = abi.solver_opts(abi.ALG_TSIT5, (0.0, 30.0))
+    rng = np.random.default_rng(3)
+    z = rng.uniform(-1, 1, N) + 1j * rng.uniform(-1, 1, N)
+    ts = orc.tsave_array(opts, 50, 0.5)
+    res = []
+    for phi in (0.0, 0.7, 2.1):
+        w = z * np.exp(1j * phi)
+        u0 = np.stack([w.real, w.imag], axis=1).ravel()
+        saved, ret, ns, nsv = orc.trajectory(psys, opts, u0, np.zeros(0), ts)
+        res.append((saved[0::2] + 1j * saved[1::2], ns.copy()))
+        assert ret == 0 and nsv == len(ts)
+    for (zz, ns), phi in zip(res[1:], (0.7, 2.1)):
+        assert np.array_equal(ns, res[0][1]), "step sequence depends on the global phase: per-component norm?"
+        assert np.allclose(zz, res[0][0] * np.exp(1j * phi), rtol=0, atol=1e-12)
+
+
 def test_distance_matrix_and_dbscan_vs_sklearn(orc):
     from sklearn.cluster import DBSCAN
     rng = np.random.default_rng(5)
