@@ -355,6 +355,40 @@ int mcbb_dbscan_labels_dev(const int32_t* root_label_dev, int64_t n, int64_t* as
 int mcbb_gather_columns_dev(const double* X_dev, int64_t ld, const int32_t* idx_dev, int64_t m, int32_t F,
                             double* Xout_dev, void* stream);
 
+/* ---- several devices driven from ONE host process (SURVEY §8(b) "Threading"; docs/src/hpc.md:27-35 and the
+ * EnsembleDistributed() default of solve, src/setup_mc_prob.jl:1098, are the reference's way to scale out) ---------------
+ * mcbb_multi_init binds `n_devices` GPUs (devices == NULL: 0 .. n_devices-1), creates one NCCL communicator per device
+ * inside the library (libnccl.so.2 is loaded with dlopen, no link-time dependency) and one stream per device.  The *_multi
+ * entry points take the same HOST buffers as their single-device twins, run one host thread per device and return when
+ * all devices are done.  One *_multi call at a time per process. */
+int mcbb_multi_init(int32_t n_devices, const int32_t* devices);
+int mcbb_multi_finalize(void);
+int mcbb_multi_info(int32_t* n_devices, int32_t* nccl_version);
+/* mcbb_solve_features over all devices: contiguous blocks of runs per device, no collective (runs are independent);
+ * every device writes its block straight into the caller's arrays.  Same arguments and results as mcbb_solve_features. */
+int mcbb_solve_features_multi(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
+                              int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
+                              double* feat_out, double* matrix_out, double* global_out, int32_t* retcode_out,
+                              int64_t* nsteps_out);
+/* mcbb_dbscan_features over all devices: X is copied to every device, the pair space is sharded by interleaved row
+ * blocks, neighbour counts / union-find parents / border labels are exchanged with NCCL.  Labels are identical to
+ * mcbb_dbscan_features (and so to Clustering.dbscan on the materialised matrix). */
+int mcbb_dbscan_features_multi(const double* X, int64_t n, int32_t n_groups, const int32_t* group_len,
+                               const double* group_weight, double eps, int32_t minpts, int64_t* assignments,
+                               int64_t* seeds, int64_t* counts, int64_t* n_clusters);
+/* solve -> sort -> distance -> dbscan in one call, the features never leave the devices: shard, integrate + featurize,
+ * NCCL all-gather of the per-device feature blocks, STABLE sort of the runs by par[:,0] on the device (what sort!(sol,
+ * prob) does on the host, src/setup_mc_prob.jl:520-536), sharded on-the-fly DBSCAN with the distance of
+ * distance_matrix(sol, prob, weights) (per-dimension measures + parameter columns; `weights` has n_meas + n_par entries).
+ *   feat_out / retcode_out / nsteps_out   in the CALLER's run order (any may be NULL)
+ *   order_out[n_mc]                       0-based sortperm: sorted position k holds run order_out[k]
+ *   assignments / seeds / counts          refer to the SORTED runs, as dbscan(distance_matrix(sol, prob, ...)) would */
+int mcbb_solve_cluster_multi(const mcbb_system_desc* sys, const mcbb_solver_opts* opts, const mcbb_feat_opts* feat,
+                             int64_t n_mc, const double* ic, const double* par, const double* t_save, int32_t n_t,
+                             const double* weights, double eps, int32_t minpts, double* feat_out, int32_t* retcode_out,
+                             int64_t* nsteps_out, int64_t* order_out, int64_t* assignments, int64_t* seeds,
+                             int64_t* counts, int64_t* n_clusters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,8 @@ EXPORTS = [
     "mcbb_distance_sparse_count", "mcbb_distance_sparse_count_dev", "mcbb_distance_sparse_fill", "mcbb_distance_sparse_fill_dev",
     "mcbb_dbscan_sparse", "mcbb_dbscan_sparse_dev", "mcbb_dbscan_rows_count_lists_dev", "mcbb_dbscan_rows_union_more_dev", "mcbb_distance_matrix_rows", "mcbb_distance_matrix_rows_dev",
     "mcbb_test_hook_set", "mcbb_pair_feature_counter",
+    "mcbb_multi_init", "mcbb_multi_finalize", "mcbb_multi_info", "mcbb_solve_features_multi", "mcbb_dbscan_features_multi",
+    "mcbb_solve_cluster_multi",
 ]
 
 _lib = None
@@ -89,6 +91,12 @@ def lib():
     L.mcbb_dbscan_rows_union_more_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int64, C.c_int64, vp, vp]
     L.mcbb_dbscan_sparse.argtypes = [C.c_int64, lp, ip, dp, C.c_double, C.c_double, C.c_int32, lp, lp, lp, lp]
     L.mcbb_dbscan_sparse_dev.argtypes = [C.c_int64, vp, vp, vp, C.c_double, C.c_double, C.c_int32, vp, vp, vp, lp, vp]
+    L.mcbb_multi_init.argtypes = [C.c_int32, ip]
+    L.mcbb_multi_info.argtypes = [ip, ip]
+    L.mcbb_solve_features_multi.argtypes = [SD, SO, FO, C.c_int64, dp, dp, dp, C.c_int32, dp, dp, dp, ip, lp]
+    L.mcbb_dbscan_features_multi.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_double, C.c_int32, lp, lp, lp, lp]
+    L.mcbb_solve_cluster_multi.argtypes = [SD, SO, FO, C.c_int64, dp, dp, dp, C.c_int32, dp, C.c_double, C.c_int32, dp, ip,
+                                           lp, lp, lp, lp, lp, lp]
     L.mcbb_pair_feature_counter.argtypes = [C.c_int32, lp, vp]
     L.mcbb_test_hook_set.argtypes = [C.c_char_p, C.c_int64]
     L.mcbb_gather_columns_dev.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp]

@@ -959,9 +959,11 @@ def feature_groups(sol, prob, weights, relative_parameter=False):
 
 
 def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_ecdf, k_bin, nbin_default, nbin=None,
-                       bin_edges=None):
+                       bin_edges=None, skip_zero_weight=False):
     """Feature matrix X [N_mc, F] + L1 groups (lengths, weights) whose weighted group sums are the reference distance
-    (eval_clustering.jl:164-241), for the plain and the histogram variant; also the histogram edges / bin widths."""
+    (eval_clustering.jl:164-241), for the plain and the histogram variant; also the histogram edges / bin widths.
+    skip_zero_weight (the on-the-fly DBSCAN path only): a per-dimension measure of weight 0 whose values are all finite
+    contributes exactly 0 to every distance, so its histogram is not built at all (its edges come back as None)."""
     hist_edges, bin_widths = [], []
     if histograms:
         # per-dimension measures are replaced by per-run Float32 ECDF rows over common edges; the distance of two
@@ -969,16 +971,36 @@ def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_e
         n_par = prob.par.shape[1]
         if len(weights) != sol.N_meas + n_par:
             raise MCBBError("Amount of weights not the same as Measures + Parameters")
+        if nbin is not None:
+            import warnings
+            warnings.warn("nbin amount specified, all usual histogram binning function will not be used")
+        if bin_edges is not None and len(bin_edges) != sol.N_meas_dim:
+            raise MCBBError("bin_edges needs one entry (a range or None) per per-dimension measure")
+
+        def one_measure(mi):
+            data = sol.feat[:, :, mi]
+            if skip_zero_weight and weights[mi] == 0 and np.isfinite(data).all():
+                return None
+            import warnings
+            with warnings.catch_warnings(record=True) as rec:
+                warnings.simplefilter("always")
+                edges, bw = _compute_hist_edges(data, sol.N_dim, k_bin, nbin_default, nbin,
+                                                None if bin_edges is None else bin_edges[mi])
+            return edges, bw, _compute_hist_weights(data, edges, use_ecdf), [str(w.message) for w in rec]
+        # the measures are independent and numpy releases the GIL inside its loops: one host thread per measure
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, max(1, sol.N_meas_dim))) as pool:
+            per_meas = list(pool.map(one_measure, range(sol.N_meas_dim)))
         cols, glen, gw = [], [], []
-        for mi in range(sol.N_meas_dim):
-            if nbin is not None and mi == 0:
+        for mi, res in enumerate(per_meas):
+            if res is None:
+                hist_edges.append(None)
+                bin_widths.append(None)
+                continue
+            edges, bw, H, msgs = res
+            for msg in msgs:
                 import warnings
-                warnings.warn("nbin amount specified, all usual histogram binning function will not be used")
-            if bin_edges is not None and len(bin_edges) != sol.N_meas_dim:
-                raise MCBBError("bin_edges needs one entry (a range or None) per per-dimension measure")
-            edges, bw = _compute_hist_edges(sol.feat[:, :, mi], sol.N_dim, k_bin, nbin_default, nbin,
-                                            None if bin_edges is None else bin_edges[mi])
-            H = _compute_hist_weights(sol.feat[:, :, mi], edges, use_ecdf)
+                warnings.warn(msg)
             hist_edges.append(edges)
             bin_widths.append(bw)
             cols.append(H.astype(np.float64))
@@ -1014,7 +1036,8 @@ def distance_matrix(sol, prob, weights, relative_parameter=False, histograms=Fal
     default L1 distance_func / wasserstein_histogram_distance (eval_clustering.jl:164-241).
     materialize=False returns a B200FeatureMatrix (distances are then recomputed on the fly by dbscan)."""
     X, glen, gw, hist_edges, bin_widths = _assemble_features(sol, prob, weights, relative_parameter, histograms,
-                                                             use_ecdf, k_bin, nbin_default, nbin, bin_edges)
+                                                             use_ecdf, k_bin, nbin_default, nbin, bin_edges,
+                                                             skip_zero_weight=not materialize)
     if not materialize:
         # groups of weight 0 contribute w * d = 0 to every distance as long as their values are finite (0 * NaN would
         # be NaN in the reference, eval_clustering.jl:242-254): leave them out of the on-the-fly tiles

@@ -36,6 +36,15 @@
 
 namespace mcbb {
 
+// what the (out-of-line, once per run) finish needs: read from device memory, so that the call costs the hot loop no stack
+struct SlFin {
+    int N, n_t, n_meas, meas[MCBB_MAX_MEAS], comp[MCBB_MAX_MEAS], n_filter, kl_bins, matrix_meas, corr_nbins;
+    long long n_mc;
+    double kl_nstd, kl_tol;
+    double* feat;
+    double* matrix;
+};
+
 struct SlArgs {
     int N, KS, n_sms;
     double inv_n, ln_qoldinit;
@@ -56,6 +65,7 @@ struct SlArgs {
     double* smp;                  // [grid][JB][n_t][2N] saved samples of the runs in flight (KL / correlation)
     double fx_scale, fx_inv, fx_max;  // 2^50 / R, R / 2^50, largest representable magnitude
     unsigned int* ovf;            // number of runs that accepted a clamped stage
+    const SlFin* fin;             // device copy of the finish parameters
 };
 
 struct SlSlotCtl {
@@ -70,86 +80,141 @@ __device__ __forceinline__ void sl_tmem_ld16(const unsigned taddr, unsigned (&v)
 
 // |cor| histogram of the complex series of one finished run (Statistics.cor(x, dims = 2) of a Complex matrix: rows
 // centred, x x' with the second factor conjugated, divided by the roots of the diagonal; eval_mc_prob.jl:462-481).
-// All 128 threads of the CTA.  Pairs i < j are tiled 4 x 4 per thread; the centred samples are staged through `stage`
-// (shared memory, KC samples of 2N doubles at a time).  hist receives 2 per pair ((i,j) and (j,i)).
-// KC = samples staged at a time: (bytes of the lent scratch / 8 - 8) / 2N.
-static __device__ __noinline__ void sl_corr_hist(const double* __restrict__ smp, const int n_t, const int N, const double* s_mx,
-                                          const double* s_my, const double* s_var, double* stage, const int KC, int* hist,
-                                          const int nb) {
+// All 128 threads of the CTA.  The run's saved samples are first centred IN PLACE in the device scratch (they are dead
+// afterwards); then every thread accumulates 4 x 4 tiles of the upper triangle (pairs i < j) straight from the scratch
+// — each sample row is 2N doubles shared by all threads, so the loads hit L1 — without any CTA barrier in the sample loop.
+// hist receives 2 per pair ((i,j) and (j,i)).
+static __device__ __noinline__ void sl_corr_hist(double* __restrict__ smp, const int n_t, const int N, const double* s_mx,
+                                                 const double* s_my, const double* s_var, int* hist, const int nb) {
     const int tid = threadIdx.x;
     const int NBk = (N + 3) >> 2;
     const int n_blocks = NBk * (NBk + 1) / 2;
     const int n2 = 2 * N;
     for (int b = tid; b < nb; b += 128) hist[b] = 0;
-    for (int base = 0; base < n_blocks; base += 128) {
-        const int id = base + tid;
-        int bi = 0, bj = 0;
-        const bool have = id < n_blocks;
-        if (have) {  // id -> (bi, bj), bi <= bj, rows enumerated bi = 0, 1, ... with NBk - bi entries each
-            int rem = id;
-            while (rem >= NBk - bi) {
-                rem -= NBk - bi;
-                bi++;
-            }
-            bj = bi + rem;
+    // the samples were written long ago and have left the L2 (the scratch of all slots is ~1 GB): keep 16 independent
+    // loads in flight per thread, or the loop is bound by one HBM round trip per row
+    for (int d = tid; d < n2; d += 128) {
+        const double mu = (d & 1) ? s_my[d >> 1] : s_mx[d >> 1];
+        for (int k0 = 1; k0 < n_t; k0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = (k0 + q < n_t) ? __ldcs(smp + (size_t)(k0 + q) * n2 + d) : 0.;
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+                if (k0 + q < n_t) smp[(size_t)(k0 + q) * n2 + d] = v[q] - mu;
         }
+    }
+    __syncthreads();  // centred samples (global) and the zeroed histogram (shared) visible to the whole CTA
+    const double step = 1. / (double)nb;
+    for (int id = tid; id < n_blocks; id += 128) {
+        int bi = 0, rem = id;  // id -> (bi, bj), bi <= bj, rows enumerated bi = 0, 1, ... with NBk - bi entries each
+        while (rem >= NBk - bi) {
+            rem -= NBk - bi;
+            bi++;
+        }
+        const int bj = bi + rem;
+        // the last tile row / column may reach past N: clamp the loads to valid rows, the pairs are skipped below
+        const int ia = min(4 * bi, N - 4 < 0 ? 0 : N - 4), ic = min(4 * bj, N - 4 < 0 ? 0 : N - 4);
+        const int sa = 4 * bi - ia, sc = 4 * bj - ic;  // shift of the tile inside the loaded window (0 unless clamped)
         double re[4][4], im[4][4];
 #pragma unroll
         for (int p = 0; p < 4; p++)
 #pragma unroll
             for (int q = 0; q < 4; q++) re[p][q] = im[p][q] = 0.;
-        for (int k0 = 1; k0 < n_t; k0 += KC) {
-            const int kc = min(KC, n_t - k0);
-            __syncthreads();  // previous chunk consumed
-            for (int q = tid; q < KC * n2 + 8; q += 128) {
-                const int kk = q / n2, d = q - kk * n2;
-                double v = 0.;
-                if (kk < kc) v = __ldcg(smp + (size_t)(k0 + kk) * n2 + d) - ((d & 1) ? s_my[d >> 1] : s_mx[d >> 1]);
-                stage[q] = v;
+#pragma unroll 4
+        for (int k = 1; k < n_t; k++) {
+            const double2* ra = reinterpret_cast<const double2*>(smp + (size_t)k * n2 + 2 * ia);
+            const double2* rc = reinterpret_cast<const double2*>(smp + (size_t)k * n2 + 2 * ic);
+            double2 za[4], zc[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                za[p] = ra[p];
+                zc[p] = rc[p];
             }
-            __syncthreads();
-            if (have) {
-                for (int kk = 0; kk < kc; kk++) {
-                    const double2* ra = reinterpret_cast<const double2*>(stage + kk * n2 + 8 * bi);
-                    const double2* rc = reinterpret_cast<const double2*>(stage + kk * n2 + 8 * bj);
-                    double2 za[4], zc[4];
-#pragma unroll
-                    for (int p = 0; p < 4; p++) {
-                        za[p] = ra[p];
-                        zc[p] = rc[p];
-                    }
-#pragma unroll
-                    for (int p = 0; p < 4; p++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {  // (a + ib)(c - id)
-                            re[p][q] = fma(za[p].x, zc[q].x, re[p][q]);
-                            re[p][q] = fma(za[p].y, zc[q].y, re[p][q]);
-                            im[p][q] = fma(za[p].y, zc[q].x, im[p][q]);
-                            im[p][q] = fma(-za[p].x, zc[q].y, im[p][q]);
-                        }
-                }
-            }
-        }
-        if (have) {
-            const double step = 1. / (double)nb;
 #pragma unroll
             for (int p = 0; p < 4; p++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int i = 4 * bi + p, j = 4 * bj + q;
-                    if (i >= j || j >= N) continue;
-                    const double den = sqrt(s_var[i]) * sqrt(s_var[j]);
-                    const double c = hypot(re[p][q] / den, im[p][q] / den);
-                    if (c != c) continue;  // zero-variance oscillator: dropped, as in the lane kernels and the oracle
-                    double f = c / step + 1.;  // Base.searchsortedlast on the range 0:1/nbins:1
-                    f = fmin(fmax(f, 1.), (double)(nb + 1));
-                    const int n0 = (int)rint(f);
-                    const int idx = (c < (double)(n0 - 1) / (double)nb) ? n0 - 1 : n0;
-                    if (idx >= 1 && idx <= nb) atomicAdd(&hist[idx - 1], 2);
+                for (int q = 0; q < 4; q++) {  // (a + ib)(c - id)
+                    re[p][q] = fma(za[p].x, zc[q].x, re[p][q]);
+                    re[p][q] = fma(za[p].y, zc[q].y, re[p][q]);
+                    im[p][q] = fma(za[p].y, zc[q].x, im[p][q]);
+                    im[p][q] = fma(-za[p].x, zc[q].y, im[p][q]);
                 }
         }
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = ia + p, j = ic + q;
+                if (p < sa || q < sc) continue;  // rows of a clamped window that belong to the previous tile
+                if (i >= j || j >= N) continue;
+                const double den = sqrt(s_var[i]) * sqrt(s_var[j]);
+                const double c = hypot(re[p][q] / den, im[p][q] / den);
+                if (c != c) continue;  // zero-variance oscillator: dropped, as in the lane kernels and the oracle
+                double f = c / step + 1.;  // Base.searchsortedlast on the range 0:1/nbins:1
+                f = fmin(fmax(f, 1.), (double)(nb + 1));
+                const int n0 = (int)rint(f);
+                const int idx = (c < (double)(n0 - 1) / (double)nb) ? n0 - 1 : n0;
+                if (idx >= 1 && idx <= nb) atomicAdd(&hist[idx - 1], 2);
+            }
     }
     __syncthreads();
+}
+
+// results of one finished run: the per-oscillator measures (every thread its own oscillator), the KL-hist measures from the
+// run's saved samples, the correlation histogram by the whole CTA.  `scratch` = the digit panels, dead between two rounds.
+template <bool SMP>
+static __device__ __noinline__ void sl_finish_run(const SlFin* __restrict__ fp, double* smp_run, const bool ok, const long long run,
+                                                  const int fpos, const double amx, const double a2x, const double amy,
+                                                  const double a2y, unsigned char* scratch, const int scratch_bytes,
+                                                  double* sm_mx, double* sm_my, double* sm_var, int* sm_hist) {
+    const SlFin a = *fp;
+    const int tid = threadIdx.x, N = a.N, n_t = a.n_t;
+    const long long n_mc = a.n_mc;
+    if (fpos >= 0) {
+        // std(u; mean, corrected = true) = sqrt(sum (u - mean)^2 / (n - 1)), n = n_t - 1 samples
+        const double inv = 1. / (double)(n_t - 2);
+        const double mean_c[2] = {ok ? amx : nan(""), ok ? amy : nan("")};
+        const double sd_c[2] = {ok ? sqrt((a2x < 0. ? 0. : a2x) * inv) : nan(""), ok ? sqrt((a2y < 0. ? 0. : a2y) * inv) : nan("")};
+        for (int m = 0; m < a.n_meas; m++) {
+            const int cp = a.comp[m];
+            double v;
+            if (a.meas[m] == MCBB_MEAS_MEAN) {
+                v = mean_c[cp];
+            } else if (a.meas[m] == MCBB_MEAS_STD) {
+                v = sd_c[cp];
+            } else {
+                v = nan("");
+                if (SMP && ok)
+                    v = um_kl_hist(smp_run + 2 * tid + cp, 2 * N, n_t, mean_c[cp], sd_c[cp], a.kl_bins, a.kl_nstd, a.kl_tol,
+                                   (scratch_bytes >= a.kl_bins * 256) ? reinterpret_cast<unsigned short*>(scratch) + tid : nullptr);
+            }
+            a.feat[((long long)m * a.n_filter + fpos) * n_mc + run] = v;
+        }
+    }
+    if (SMP && a.matrix_meas != MCBB_MAT_NONE) {
+        const int nbn = a.corr_nbins;
+        if (!ok) {
+            for (int b = tid; b < nbn; b += 128) a.matrix[(long long)b * n_mc + run] = nan("");
+        } else {
+            // correlation runs over the FILTERED oscillators in filter order; only the identity filter is dispatched here,
+            // so oscillator index = position
+            sm_mx[tid] = amx;
+            sm_my[tid] = amy;
+            sm_var[tid] = a2x + a2y;
+            __syncthreads();
+            sl_corr_hist(smp_run, n_t, N, sm_mx, sm_my, sm_var, sm_hist, nbn);
+            if (tid == 0) {
+                double tot = 0., cum = 0.;
+                for (int b = 0; b < nbn; b++) tot += (double)sm_hist[b];
+                for (int b = 0; b < nbn; b++) {
+                    cum += (double)sm_hist[b];
+                    a.matrix[(long long)b * n_mc + run] = (a.matrix_meas == MCBB_MAT_CORR_HIST) ? (double)sm_hist[b] : cum / tot;
+                }
+            }
+        }
+    }
+    if (SMP) __syncthreads();  // the digit panels served as scratch: all done before they are rewritten
 }
 
 // SMP = true: the instantiation that keeps the saved samples (KL-hist measures and / or a correlation matrix measure)
@@ -249,7 +314,8 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
     const int degh1 = a.deg1[row] << 19, degh2 = a.deg2[row] << 19;  // deg 2^51 in units of the high word
     const double dg1 = (double)a.deg1[row], dg2 = (double)a.deg2[row];
     const int fpos = a.filter_pos[row];
-    const double fxs = a.fx_scale, fxi = a.fx_inv, fxm = a.fx_max;
+    const double fxs = a.fx_scale, fxi = a.fx_inv;
+    const int fx_hi_max = valid ? __double2hiint(a.fx_max) : 0x7fffffff;  // rows >= N never raise the flag
     unsigned phase = 0;
 
     // thread-private state of the JB elements (complex) of this oscillator
@@ -442,58 +508,10 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                 KX(1, j) = kx[7];  // FSAL
                 KY(1, j) = ky[7];
             }
-            if (c.fin) {  // uniform over the CTA
-                const bool ok = c.fin_ok != 0;
-                const double* smp_run = SMP ? a.smp + ((size_t)blockIdx.x * JB + j) * n_t * (2 * N) : nullptr;
-                if (valid && fpos >= 0) {
-                    const double inv = 1. / (double)(n_t - 2);
-                    const double mean_c[2] = {ok ? amx[j] : nan(""), ok ? amy[j] : nan("")};
-                    const double sd_c[2] = {ok ? sqrt((a2x[j] < 0. ? 0. : a2x[j]) * inv) : nan(""),
-                                            ok ? sqrt((a2y[j] < 0. ? 0. : a2y[j]) * inv) : nan("")};
-                    // std(u; mean, corrected = true) = sqrt(sum (u - mean)^2 / (n - 1)), n = n_t - 1 samples
-                    for (int m = 0; m < a.n_meas; m++) {
-                        const int cp = a.comp[m];
-                        double v;
-                        if (a.meas[m] == MCBB_MEAS_MEAN) {
-                            v = mean_c[cp];
-                        } else if (a.meas[m] == MCBB_MEAS_STD) {
-                            v = sd_c[cp];
-                        } else {
-                            v = nan("");
-                            if (SMP && ok)
-                                v = um_kl_hist(smp_run + 2 * row + cp, 2 * N, n_t, mean_c[cp], sd_c[cp], a.kl_bins, a.kl_nstd,
-                                               a.kl_tol,
-                                               (JB * 2048 >= a.kl_bins * 256) ? reinterpret_cast<unsigned short*>(smem) + tid : nullptr);
-                        }
-                        a.io.feat[((long long)m * a.n_filter + fpos) * n_mc + c.fin_run] = v;
-                    }
-                }
-                if (SMP && a.matrix_meas != MCBB_MAT_NONE) {
-                    const int nbn = a.corr_nbins;
-                    if (!ok) {
-                        for (int b = tid; b < nbn; b += 128) a.io.matrix[(long long)b * n_mc + c.fin_run] = nan("");
-                    } else {
-                        // correlation runs over the FILTERED oscillators in filter order; only the identity filter is
-                        // dispatched here, so oscillator index = position
-                        sm_mx[tid] = amx[j];
-                        sm_my[tid] = amy[j];
-                        sm_var[tid] = a2x[j] + a2y[j];
-                        __syncthreads();
-                        sl_corr_hist(smp_run, n_t, N, sm_mx, sm_my, sm_var, reinterpret_cast<double*>(smem),
-                                     (JB * 2048 / 8 - 8) / (2 * N), sm_hist, nbn);
-                        if (tid == 0) {
-                            double tot = 0., cum = 0.;
-                            for (int b = 0; b < nbn; b++) tot += (double)sm_hist[b];
-                            for (int b = 0; b < nbn; b++) {
-                                cum += (double)sm_hist[b];
-                                a.io.matrix[(long long)b * n_mc + c.fin_run] =
-                                    (a.matrix_meas == MCBB_MAT_CORR_HIST) ? (double)sm_hist[b] : cum / tot;
-                            }
-                        }
-                    }
-                }
-                if (SMP) __syncthreads();  // the digit panels served as scratch: all done before they are rewritten
-            }
+            if (c.fin)  // uniform over the CTA; out of line: it runs once per trajectory, the loop around it once per step
+                sl_finish_run<SMP>(a.fin, SMP ? a.smp + ((size_t)blockIdx.x * JB + j) * n_t * (2 * N) : nullptr, c.fin_ok != 0,
+                                   c.fin_run, valid ? fpos : -1, amx[j], a2x[j], amy[j], a2y[j], smem, JB * 2048, sm_mx, sm_my,
+                                   sm_var, sm_hist);
             if (c.fresh) {
                 if (valid) {
                     KX(0, j) = a.io.ic[(long long)(2 * row) * n_mc + c.run];
@@ -539,14 +557,17 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                 const double x = fma(h, lx, x01.x), y = fma(h, ly, y01.x);
                 xs[j] = x;
                 ys[j] = y;
-                const double xc = fmin(fmax(x, -fxm), fxm), yc = fmin(fmax(y, -fxm), fxm);
-                if (valid && (fabs(x) > fxm || fabs(y) > fxm)) clampmask |= 1u << j;
+                // out of the fixed-point range (or NaN)?  One integer compare on the exponent words; the digits of such a
+                // value are meaningless, which is harmless: a step that is ACCEPTED with the flag set invalidates the launch
+                // (the ensemble is repeated on the lane kernels), a rejected one is simply retried with a smaller step
+                const int hmx = max(UM_HI(x) & 0x7fffffff, UM_HI(y) & 0x7fffffff);
+                clampmask |= (hmx >= fx_hi_max ? 1u : 0u) << j;
                 uint2 dx, dy;
                 {
-                    const double t = fma(xc, fxs, UM_C(1));
+                    const double t = fma(x, fxs, UM_C(1));
                     dx.x = (unsigned)UM_LO(t);
                     dx.y = (unsigned)UM_HI(t) & 0xFFFFFu;
-                    const double t2 = fma(yc, fxs, UM_C(1));
+                    const double t2 = fma(y, fxs, UM_C(1));
                     dy.x = (unsigned)UM_LO(t2);
                     dy.y = (unsigned)UM_HI(t2) & 0xFFFFFu;
                 }
@@ -763,7 +784,6 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     if (tune_get("no_umma", 0) || tune_get("no_umma_sl", 0)) return 0;  // test hook
     if (F.need_kl && (F.kl_bins > UM_MAX_KL_BINS || F.kl_bins < 3)) return 0;
     if (F.matrix_meas != MCBB_MAT_NONE && (F.filter != nullptr || F.corr_nbins > 64 || F.corr_nbins < 1)) return 0;
-    if (F.matrix_meas != MCBB_MAT_NONE && N > 126) return 0;  // staging of the correlation needs >= 1 sample of 2N doubles
     for (int m = 0; m < F.n_meas; m++)
         if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD && F.meas[m] != MCBB_MEAS_KL_HIST) return 0;
     for (int p = 0; p < S.n_par; p++)
@@ -878,6 +898,28 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
         a.smp = (double*)scratch_get(39, sizeof(double) * (size_t)grid * pick->jb * (size_t)io.n_t * (size_t)(2 * N));
         if (!a.smp) MCBB_FAIL("solve: device allocation failed");
     }
+    SlFin hf = {};
+    hf.N = N;
+    hf.n_t = io.n_t;
+    hf.n_meas = F.n_meas;
+    for (int m = 0; m < F.n_meas; m++) {
+        hf.meas[m] = F.meas[m];
+        hf.comp[m] = F.comp[m];
+    }
+    hf.n_filter = F.n_filter;
+    hf.kl_bins = F.kl_bins;
+    hf.matrix_meas = F.matrix_meas;
+    hf.corr_nbins = F.corr_nbins;
+    hf.n_mc = io.n_mc;
+    hf.kl_nstd = F.kl_nstd;
+    hf.kl_tol = F.kl_tol;
+    hf.feat = io.feat;
+    hf.matrix = io.matrix;
+    SlFin* d_fin = (SlFin*)scratch_get(92, sizeof(SlFin));
+    if (!d_fin) MCBB_FAIL("solve: device allocation failed");
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_fin, &hf, sizeof(SlFin), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));  // hf is stack-owned
+    a.fin = d_fin;
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     int rc = 1;

@@ -13,9 +13,13 @@
 
 #include <limits.h>
 
+#include <algorithm>
+#include <cmath>
+
 #include <vector>
 
 #include "pair_tiles.cuh"
+#include "multi.cuh"
 
 namespace mcbb {
 
@@ -629,6 +633,160 @@ int dbscan_features_dev(const double* X, long long n, int n_groups, const int32_
         }
     }
     k_root_labels<<<nblk(n), 256, 0, st>>>(n_core, core_idx, col_root, n_non, non_idx, best, root_label, is_seed);
+    MCBB_LAUNCHED();
+    return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
+}
+
+// ---- several devices in one process: the per-rank body of mcbb_dbscan_features_multi (csrc/multi.cu) ------------------
+// Every rank holds the whole feature matrix X [F][n] and produces identical labels.  The pair space is sharded by
+// INTERLEAVED row blocks (rank r owns blocks b = r, r + world, ... of MULTI_BLOCKS_PER_RANK * world equal blocks): runs
+// arrive sorted by parameter and the cost of a row varies strongly along that order, so contiguous shards would be
+// unbalanced, while interleaving needs no permutation of X.  Exchanges (all O(n) integers):
+//   counts           every rank fills the rows it owns of a zeroed full-length array        -> all-reduce SUM
+//   union-find       per-rank parent array over its blocks of the core pair triangle         -> all-gather + merge
+//   border labels    owned non-core rows from their recorded neighbour lists (INT_MAX else)  -> all-reduce MIN
+constexpr int MULTI_BLOCKS_PER_RANK = 16;
+__global__ void k_merge_parents(int* parent, const int* other, long long m);
+
+__global__ void k_border_owned_rows(const int* core, const int* core_pos, const int* col_root, const int* nbr,
+                                    const int* nfill, int cap, long long r0, long long r1, int* best) {
+    const long long i = r0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1 || core[i]) return;
+    const int m = min(nfill[i], cap);
+    int b = INT_MAX;
+    for (int s = 0; s < m; s++) {
+        const int q = nbr[i * cap + s];
+        if (core[q]) b = min(b, col_root[core_pos[q]]);
+    }
+    best[i] = b;
+}
+__global__ void k_root_labels_full(const int* core, const int* core_pos, const int* col_root, const int* best, long long n,
+                                   int* root_label, int* is_seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (core[i]) {
+        const int r = col_root[core_pos[i]];
+        root_label[i] = r;
+        is_seed[i] = (r == (int)i);
+    } else {
+        root_label[i] = best[i] == INT_MAX ? -1 : best[i];
+        is_seed[i] = 0;
+    }
+}
+
+// row block [lo, hi) number k of `parts` equal-AREA blocks of the pair triangle {col > row} over m points (tile aligned)
+static void triangle_block(long long m, int k, int parts, long long* lo, long long* hi) {
+    auto edge = [&](int q) -> long long {
+        if (q >= parts) return m;
+        const long long b = (long long)((double)m * (1.0 - std::sqrt(1.0 - (double)q / (double)parts)));
+        return std::min<long long>(m, (b / TILE) * TILE);
+    };
+    *lo = edge(k);
+    *hi = edge(k + 1);
+}
+
+int dbscan_features_multi_rank(const double* X, long long n, int n_groups, const int32_t* group_len,
+                               const double* group_weight, double eps, int minpts, const MultiComm& mc, long long* assignments,
+                               long long* seeds, long long* counts, long long* n_clusters_host, cudaStream_t st) {
+    if (int rc = check_dbscan_args(n, eps, minpts)) return rc;
+    if ((size_t)n * (size_t)minpts * sizeof(int) > ((size_t)2 << 30))
+        MCBB_FAIL("dbscan (multi-device): n * minpts neighbour lists exceed 2 GB; lower minpts or use fewer points");
+    GroupTables gt;
+    if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    const int F = gt.F;
+    const int world = mc.world, rank = mc.rank;
+    int* cnt = (int*)scratch_get(12, sizeof(int) * n);
+    int* core = (int*)scratch_get(75, sizeof(int) * n);
+    int* noncore = (int*)scratch_get(76, sizeof(int) * n);
+    int* core_pos = (int*)scratch_get(77, sizeof(int) * n);
+    int* non_pos = (int*)scratch_get(78, sizeof(int) * n);
+    int* core_idx = (int*)scratch_get(79, sizeof(int) * n);
+    int* non_idx = (int*)scratch_get(18, sizeof(int) * n);
+    int* root_label = (int*)scratch_get(19, sizeof(int) * n);
+    int* is_seed = (int*)scratch_get(22, sizeof(int) * n);
+    int* best = (int*)scratch_get(27, sizeof(int) * n);
+    int* nbr = (int*)scratch_get(34, sizeof(int) * (size_t)n * (size_t)minpts);
+    int* nfill = (int*)scratch_get(35, sizeof(int) * (size_t)n);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, core, core_pos, (int)n, st);
+    void* tmp = scratch_get(80, tb);
+    if (!cnt || !core || !noncore || !core_pos || !non_pos || !core_idx || !non_idx || !root_label || !is_seed || !best ||
+        !nbr || !nfill || !tmp)
+        MCBB_FAIL("dbscan: device scratch allocation failed");
+    PassTimer pt(st);
+    // ---- stage 1: neighbour counts (+ the first minpts neighbours) of the owned row blocks -----------------
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(cnt, n, 0);
+    MCBB_LAUNCHED();
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(nfill, n, 0);
+    MCBB_LAUNCHED();
+    const int n_blocks = world * MULTI_BLOCKS_PER_RANK;
+    const long long bs = ((n + n_blocks - 1) / n_blocks + TILE - 1) / TILE * TILE;  // tile-aligned block size
+    for (long long b = rank; b * bs < n; b += world) {
+        const long long r0 = b * bs, r1 = std::min<long long>(n, r0 + bs);
+        if (int rc = count_rows(X, n, gt, eps, minpts, r0, r1, cnt + r0, st, nullptr, nbr + r0 * minpts, nfill + r0, minpts))
+            return rc;
+    }
+    pt.lap("multi: count owned row blocks");
+    if (int rc = mc.allreduce_i32(mc.ctx, cnt, n, 0, st)) return rc;
+    pt.lap("multi: all-reduce counts");
+    // ---- core flags and stable compaction (replicated: O(n)) ---------------------------------------------------
+    k_core_flags<<<nblk(n), 256, 0, st>>>(cnt, n, minpts, core, noncore);
+    MCBB_LAUNCHED();
+    MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, core, core_pos, (int)n, st));
+    MCBB_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, noncore, non_pos, (int)n, st));
+    g_launch_count.fetch_add(2);
+    int h_pos = 0, h_flag = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(&h_pos, core_pos + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaMemcpyAsync(&h_flag, core + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    const long long n_core = (long long)h_pos + h_flag;
+    k_compact_idx<<<nblk(n), 256, 0, st>>>(core, core_pos, non_pos, n, core_idx, non_idx);
+    MCBB_LAUNCHED();
+    int* col_root = (int*)scratch_get(26, sizeof(int) * (size_t)(n_core > 0 ? n_core : 1));
+    if (!col_root) MCBB_FAIL("dbscan: device scratch allocation failed");
+    if (n_core > 0) {
+        // ---- stage 2: components of the core graph; the pair triangle in 4 * world equal-area blocks, dealt cyclically
+        double* Xc = (double*)scratch_get(23, sizeof(double) * (size_t)F * (size_t)n_core);
+        int* parent = (int*)scratch_get(25, sizeof(int) * (size_t)n_core);
+        int* others = (int*)scratch_get(81, sizeof(int) * (size_t)n_core * (size_t)world);
+        if (!Xc || !parent || !others) MCBB_FAIL("dbscan: device scratch allocation failed");
+        k_gather_cols<<<dim3(nblk(n_core), F), 256, 0, st>>>(X, n, core_idx, n_core, F, Xc);
+        MCBB_LAUNCHED();
+        k_iota_i32<<<nblk(n_core), 256, 0, st>>>(parent, n_core);
+        MCBB_LAUNCHED();
+        const int parts = 4 * world;
+        for (int k = rank; k < parts; k += world) {
+            long long c0, c1;
+            triangle_block(n_core, k, parts, &c0, &c1);
+            if (int rc = union_rows(Xc, n_core, gt, eps, c0, c1, parent, st, nullptr)) return rc;
+        }
+        pt.lap("multi: union owned triangle blocks");
+        if (world > 1) {
+            if (int rc = mc.allgather_i32(mc.ctx, parent, others, n_core, st)) return rc;
+            for (int r = 0; r < world; r++) {
+                if (r == rank) continue;
+                k_merge_parents<<<nblk(n_core), 256, 0, st>>>(parent, others + (size_t)r * n_core, n_core);
+                MCBB_LAUNCHED();
+            }
+        }
+        pt.lap("multi: all-gather + merge parents");
+        // cores are compacted in ascending original order, so the smallest position of a component is its seed
+        k_flatten_roots<<<nblk(n_core), 256, 0, st>>>(parent, n_core, core_idx, col_root);
+        MCBB_LAUNCHED();
+    }
+    // ---- stage 3: border labels of the owned non-core rows from their neighbour lists ---------------------------
+    k_fill_i32<<<nblk(n), 256, 0, st>>>(best, n, INT_MAX);
+    MCBB_LAUNCHED();
+    if (n_core > 0 && n_core < n) {
+        for (long long b = rank; b * bs < n; b += world) {
+            const long long r0 = b * bs, r1 = std::min<long long>(n, r0 + bs);
+            k_border_owned_rows<<<nblk(r1 - r0), 256, 0, st>>>(core, core_pos, col_root, nbr, nfill, minpts, r0, r1, best);
+            MCBB_LAUNCHED();
+        }
+        if (int rc = mc.allreduce_i32(mc.ctx, best, n, 1, st)) return rc;
+    }
+    pt.lap("multi: border labels");
+    k_root_labels_full<<<nblk(n), 256, 0, st>>>(core, core_pos, col_root, best, n, root_label, is_seed);
     MCBB_LAUNCHED();
     return finalize_labels(root_label, is_seed, n, assignments, seeds, counts, n_clusters_host, st);
 }

@@ -176,12 +176,13 @@ static __device__ __noinline__ double um_kl_hist(const double* smp, const long l
     // among the ascending edges — taken directly and corrected against the very same edge expression — and, when
     // r == nc, bin nc if x < last_edge, else outside.  Eight samples are fetched at a time (the scratch lives in
     // L2 / HBM: keep the loads in flight).
-    for (int k0 = 1; k0 < n_t; k0 += 8) {
-        double xs[8];
+    constexpr int KLC = 8;  // samples in flight per thread (16 measured slower: 357 k vs 376 k traj/s on C5 with KL)
+    for (int k0 = 1; k0 < n_t; k0 += KLC) {
+        double xs[KLC];
 #pragma unroll
-        for (int q = 0; q < 8; q++) xs[q] = (k0 + q < n_t) ? __ldcg(smp + (long long)(k0 + q) * stride) : nan("");
+        for (int q = 0; q < KLC; q++) xs[q] = (k0 + q < n_t) ? __ldcg(smp + (long long)(k0 + q) * stride) : nan("");
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < KLC; q++) {
             const double x = xs[q];
             if (!(x == x)) continue;  // NaN compares false everywhere: the bisection runs off the right end
             const double f = floor((x - e1) * ibw) + 1.;

@@ -99,6 +99,36 @@ function system_desc(p::MCBB.roessler_parameters, names)
                pad((p.K,), N_SCALARS, 0.0), length(names), pad(Int32[0 for _ in names], MAX_PAR, Int32(0))), (L,)
 end
 
+function system_desc(p::MCBB.kuramoto_parameters, names)   # all-to-all, src/systems.jl:85-94
+    w = Vector{Float64}(p.w)
+    SystemDesc(SYS_KURAMOTO, p.N, p.N, 0, C_NULL, C_NULL, pointer(w), C_NULL, C_NULL, pad((Float64(p.K),), N_SCALARS, 0.0),
+               length(names), pad(Int32[0 for _ in names], MAX_PAR, Int32(0))), (w,)
+end
+
+"""
+    stuart_landau_desc(p, names)
+
+The Stuart-Landau ring is not part of src/systems.jl: its parameter struct `stuart_landau_sathiyadevi_pars` (fields
+`lambda, omega, eps, N, P_1, P_2, A_1, A_2`) lives in the paper notebooks (paper/stuartlandau/stuart_landau_sathiyadevi-
+standard-config.ipynb cell 1).  Any struct with those fields works; register it with
+`MCBBB200.system_desc(p::MyPars, names) = MCBBB200.stuart_landau_desc(p, names)`.
+"""
+function stuart_landau_desc(p, names)
+    A1 = Matrix{Float64}(p.A_1); A2 = Matrix{Float64}(p.A_2)       # Bool adjacency -> 0.0 / 1.0 (non-zero = true)
+    slots = Dict(:eps => 0, :lambda => 1, :omega => 2, :P_1 => 3, :P_2 => 4)
+    SystemDesc(SYS_STUART_LANDAU, p.N, 2p.N, 0, pointer(A1), pointer(A2), C_NULL, C_NULL, C_NULL,
+               pad((Float64(p.eps), Float64(p.lambda), Float64(p.omega), Float64(p.P_1), Float64(p.P_2)), N_SCALARS, 0.0),
+               length(names), pad(Int32[slots[n] for n in names], MAX_PAR, Int32(0))), (A1, A2)
+end
+
+"Matrix{Complex{Float64}} (N_mc x N) -> N_mc x 2N Float64 with (re, im) interleaved per oscillator: the `ic` layout of complex systems."
+function interleave_complex(ic::AbstractMatrix{<:Complex})
+    out = Matrix{Float64}(undef, size(ic, 1), 2size(ic, 2))
+    out[:, 1:2:end] .= real.(ic)
+    out[:, 2:2:end] .= imag.(ic)
+    out
+end
+
 # ---- eval_ode_run as data: the closure is opaque, the user states what it computes ---------------------------
 """
     B200Eval(; measures=[:mean, :std, :kl_hist], state_filter=nothing, cyclic_setback=false)
@@ -107,7 +137,7 @@ Describes the `eval_ode_run` variant the problem was built with (src/eval_mc_pro
 reference's default `eval_ode_run(sol, i)` (eval_mc_prob.jl:191-198).
 """
 Base.@kwdef struct B200Eval
-    measures::Vector{Symbol} = [:mean, :std, :kl_hist]
+    measures::Vector{Symbol} = [:mean, :std, :kl_hist]   # complex states: :mean_real, :std_imag, :kl_real, ... as well
     state_filter::Union{Nothing,Vector{Int}} = nothing
     cyclic_setback::Bool = false
     correlation_ecdf::Bool = false     # matrix_eval_funcs = [correlation_ecdf] (30 bins)
@@ -115,7 +145,11 @@ Base.@kwdef struct B200Eval
     global_sum::Bool = false           # global_eval_funcs = [(x)->sum(x)]
 end
 const SOLVER_FIELD = Dict(:abstol => Int32(1), :reltol => Int32(2), :dt => Int32(3), :dtmax => Int32(4), :dtmin => Int32(5))
-const MEAS_ID = Dict(:mean => MEAS_MEAN, :std => MEAS_STD, :kl_hist => MEAS_KL_HIST)
+const MEAS_ID = Dict(:mean => MEAS_MEAN, :std => MEAS_STD, :kl_hist => MEAS_KL_HIST,
+                     :mean_real => MEAS_MEAN, :std_real => MEAS_STD, :kl_real => MEAS_KL_HIST,
+                     :mean_imag => MEAS_MEAN, :std_imag => MEAS_STD, :kl_imag => MEAS_KL_HIST)
+# component a measure works on (the notebook's mean_real / std_imag / ... closures): 0 = real part, 1 = imaginary part
+meas_comp(m::Symbol) = endswith(String(m), "_imag") ? Int32(1) : Int32(0)
 
 """
     custom_solve_b200(prob::DEMCBBProblem, t_save; eval=B200Eval(), alg=ALG_TSIT5, kwargs...)
@@ -136,17 +170,19 @@ function custom_solve_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eva
     tspan = prob.p.prob.tspan
     opts = SolverOpts(alg, 0, tspan[1], tspan[2], abstol, reltol, dt, 0.0, 0.0, maxiters, 0, 0, 0, 0, 0, 0)
     filt = eval.state_filter === nothing ? Int32[] : Int32.(eval.state_filter)
-    nf = eval.state_filter === nothing ? size(prob.ic, 2) : length(filt)
+    nf = eval.state_filter === nothing ? size(prob.ic, 2) : length(filt)   # complex ic: one column per oscillator
     nm = length(eval.measures)
     eval.correlation_ecdf && eval.correlation_hist && error("one matrix measure per problem")
     has_mat = eval.correlation_ecdf || eval.correlation_hist
-    fo = FeatOpts(nm, pad(Int32[MEAS_ID[m] for m in eval.measures], MAX_MEAS, Int32(0)), pad(Int32[], MAX_MEAS, Int32(0)),
+    fo = FeatOpts(nm, pad(Int32[MEAS_ID[m] for m in eval.measures], MAX_MEAS, Int32(0)),
+                  pad(Int32[meas_comp(m) for m in eval.measures], MAX_MEAS, Int32(0)),
                   length(filt), isempty(filt) ? C_NULL : pointer(filt), eval.cyclic_setback,
                   eval.correlation_ecdf ? 1 : (eval.correlation_hist ? 2 : 0), 30, eval.global_sum ? 1 : 0,
                   pad(Int32[], MAX_GLOBAL, Int32(0)), 31, 3.0, 1e-4)
     mat = has_mat ? Matrix{Float64}(undef, prob.N_mc, 30) : Matrix{Float64}(undef, 0, 0)
     glob = eval.global_sum ? Matrix{Float64}(undef, prob.N_mc, 1) : Matrix{Float64}(undef, 0, 0)
-    ic = Matrix{Float64}(prob.ic)            # N_mc x N_dim, column-major: already struct-of-arrays over runs
+    # N_mc x N_dim, column-major: already struct-of-arrays over runs; Complex{Float64} states as interleaved (re, im)
+    ic = eltype(prob.ic) <: Complex ? interleave_complex(prob.ic) : Matrix{Float64}(prob.ic)
     par = Matrix{Float64}(prob.par)
     ts = Vector{Float64}(t_save)
     feat = Array{Float64}(undef, prob.N_mc, nf, nm)
@@ -314,5 +350,50 @@ end
 k_dist_b200(D::AbstractMatrix{Float64}, k::Int=4) = sort(_knn(D, k, 1)[1], rev=true)
 KNN_dist_b200(D::AbstractMatrix{Float64}, K::Int) = reshape(_knn(D, 1, K)[2], :, 1)
 KNN_dist_relative_b200(D::AbstractMatrix{Float64}, rel_K::Float64=0.005) = KNN_dist_b200(D, Int(round(size(D, 1) * rel_K)))
+
+# ---- several GPUs from one Julia process (the reference scales out with addprocs + EnsembleDistributed, docs/src/hpc.md) ---
+"Binds `n` devices and creates the NCCL communicators inside the library; afterwards `solve_b200(...; multi=true)`-style calls shard themselves."
+multi_init(n::Integer) = check(ccall((:mcbb_multi_init, LIB), Cint, (Int32, Ptr{Int32}), n, C_NULL))
+multi_finalize() = check(ccall((:mcbb_multi_finalize, LIB), Cint, ()))
+
+"`dbscan` of a B200FeatureMatrix over all devices of `multi_init` (labels identical to the single-device call)."
+function dbscan_multi(fm::B200FeatureMatrix, eps::Real, minpts::Int)
+    n = size(fm.X, 1)
+    _dbscan_result(n, (a, s, c, k) -> ccall((:mcbb_dbscan_features_multi, LIB), Cint,
+        (Ptr{Float64}, Int64, Int32, Ptr{Int32}, Ptr{Float64}, Float64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}),
+        fm.X, n, length(fm.group_len), fm.group_len, fm.group_weight, Float64(eps), Int32(minpts), a, s, c, k))
+end
+# custom_solve_b200 over all devices: replace :mcbb_solve_features by :mcbb_solve_features_multi in the ccall above (same
+# argument list); mcbb_solve_cluster_multi runs solve -> sort -> dbscan without the features leaving the devices and
+# returns the sortperm MCBB.sort! would apply (`order_out`) next to the DbscanResult of the sorted runs.
+
+# ---- response analysis (eval_ode_run(sol, i, state_filter, eval_funcs, par_var, eps, par_bounds, distance_matrix_func),
+# src/eval_mc_prob.jl:202-257): the three short runs at p - eps, p, p + eps restart from the END STATES of the main solve.
+"End states of all runs (`sol[end]` per trajectory) in the `prob.ic` layout: input of the three continuation ensembles."
+function end_states_b200(prob::MCBB.DEMCBBProblem, t_save::AbstractVector; eval::B200Eval=B200Eval(), alg::Int32=ALG_TSIT5)
+    names = [prob.par_var[i].name for i in 1:length(prob.par_var)]
+    desc, keep = system_desc(prob.p.prob.p, names)
+    tspan = prob.p.prob.tspan
+    opts = SolverOpts(alg, 0, tspan[1], tspan[2], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    nm = length(eval.measures)
+    fo = FeatOpts(nm, pad(Int32[MEAS_ID[m] for m in eval.measures], MAX_MEAS, Int32(0)),
+                  pad(Int32[meas_comp(m) for m in eval.measures], MAX_MEAS, Int32(0)), 0, C_NULL, eval.cyclic_setback, 0, 30, 0,
+                  pad(Int32[], MAX_GLOBAL, Int32(0)), 31, 3.0, 1e-4)
+    ic = eltype(prob.ic) <: Complex ? interleave_complex(prob.ic) : Matrix{Float64}(prob.ic)
+    par = Matrix{Float64}(prob.par); ts = Vector{Float64}(t_save)
+    feat = Array{Float64}(undef, prob.N_mc, size(prob.ic, 2), nm)
+    retcode = Vector{Int32}(undef, prob.N_mc); nsteps = Matrix{Int64}(undef, prob.N_mc, 2)
+    last = Matrix{Float64}(undef, prob.N_mc, size(ic, 2))           # MCBB_SAVE_LAST = 2: the ic layout
+    GC.@preserve keep ic par ts feat retcode nsteps last begin
+        check(ccall((:mcbb_solve_features_saved, LIB), Cint,
+                    (Ref{SystemDesc}, Ref{SolverOpts}, Ref{FeatOpts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}, Int32, Ptr{Float64}),
+                    desc, opts, fo, prob.N_mc, ic, par, ts, length(ts), feat, C_NULL, C_NULL, retcode, nsteps, Int32(2), last))
+    end
+    last
+end
+# The response D(p - eps, p) + D(p, p + eps) of every run is then: three `custom_solve_b200` calls on a problem whose `ic`
+# is `end_states_b200(...)` and whose parameter column is shifted by -eps, 0, +eps (clamped to par_bounds), followed by
+# `feature_groups` + an L1 distance between corresponding runs — what mcbb.jl_b200/api.py::_continuation_response does.
 
 end # module
