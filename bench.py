@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
     python bench.py --impl reference ...                      the CPU arm (the oracle restatement; Julia is absent)
     python bench.py --config C4 ...                           the Stuart-Landau pipeline (BASELINE.json configs[3])
+    python bench.py --config C1|C2|C3 ...                     the small configs with SURVEY §8(d)'s inputs (single GPU)
 
 Workload C5 (BASELINE.json configs[4]): Kuramoto network N=100, Erdos-Renyi p=0.2 adjacency, w~N(0.5,0.1),
 ICs~U(-pi,pi)^100, K~U(0,8), tspan (0,1000), tail 0.9 (N_t=400), Tsit5 abstol 1e-6 / reltol 1e-3, measures
@@ -198,7 +199,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C5", choices=["C5", "C4"])
+    ap.add_argument("--config", default="C5", choices=["C5", "C4", "C3", "C2", "C1"])
     ap.add_argument("--runs-per-gpu", type=int, default=125000)
     ap.add_argument("--cpu-sample", type=int, default=384)
     ap.add_argument("--c4-runs", type=int, default=200000, help="--config C4: runs of the whole ensemble (all GPUs)")
@@ -208,6 +209,9 @@ def main():
     if args.config == "C4":
         from tools import bench_c4
         return bench_c4.main(args)
+    if args.config in ("C1", "C2", "C3"):
+        from tools import bench_small
+        return bench_small.main(args)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -23,6 +23,10 @@
 
 namespace mcbb {
 
+// dist_mat.cu
+int distance_matrix_tma(const double* X, long long n, int F, const double* fw, const unsigned short* fmask, double* D,
+                        cudaStream_t st, bool* handled);
+
 // ---- small helper kernels ------------------------------------------------------------------------------
 __global__ void k_fill_i32(int* p, long long n, int v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,6 +453,11 @@ int distance_matrix_dev(const double* X, long long n, int n_groups, const int32_
                         const double* group_weight, double* D, cudaStream_t st) {
     GroupTables gt;
     if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+    {  // large, evenly sized problems: the persistent TMA kernel (dist_mat.cu), same arithmetic per pair
+        bool handled = false;
+        if (int rc = distance_matrix_tma(X, n, gt.F, gt.fw, gt.fmask, D, st, &handled)) return rc;
+        if (handled) return 0;
+    }
     TileArgs a = {};
     a.Xr = a.Xc = X;
     a.ldr = a.ldc = n;

@@ -919,3 +919,37 @@ def test_cuda_path_against_committed_golden_vectors(gpu, orc):
         for res in (m.dbscan(D, eps, mp), m.dbscan(fm, eps, mp)):
             assert np.array_equal(res.assignments, np.array(G["db_%s_%d" % (eps, mp)]))
             assert np.array_equal(res.seeds, np.array(G["db_seeds_%s_%d" % (eps, mp)]))
+
+
+@pytest.mark.parametrize("n,gl,gw", [(1000, [6, 6, 6, 1], [1.0, 0.5, 0.5, 1.0]), (2570, [6, 6, 6, 1], [1.0, 0.5, 0.5, 1.0]),
+                                     (1536, [1, 1, 1, 1], [1.0, 0.75, 0.5, 1.0]), (1001, [3, 1], [1.0, 2.0]),
+                                     (4100, [40, 40, 1], [1.0, 0.3, 1.0])])
+def test_tma_distance_kernel_equals_tile_kernel_bitwise(gpu, orc, n, gl, gw):
+    """The persistent TMA kernel of the materialising path (csrc/dist_mat.cu) against the general tile kernel the
+    on-the-fly DBSCAN uses (pair_tiles.cuh): bit-identical distances (tiles on the diagonal, partial tiles at the edge,
+    a partial last feature slab, an odd n that falls back), and both within 1e-12 of the oracle."""
+    m = gpu
+    rng = np.random.default_rng(n)
+    F = int(np.sum(gl))
+    X = np.asfortranarray(rng.normal(size=(n, F)) * rng.uniform(0.1, 3.0, F))
+    X[rng.integers(0, n, 5), rng.integers(0, F, 5)] = 0.0
+    glen, gwt = np.asarray(gl, dtype=np.int32), np.asarray(gw, dtype=np.float64)
+
+    def dist():
+        D = np.full((n, n), np.nan, order="F")
+        m.check(m.lib().mcbb_distance_matrix(X.ctypes.data_as(m.abi.c_double_p), n, len(gl), glen.ctypes.data_as(m.abi.c_int32_p),
+                                             gwt.ctypes.data_as(m.abi.c_double_p), D.ctypes.data_as(m.abi.c_double_p)))
+        return D
+    before = m.kernel_launch_count()
+    D_old = dist()
+    m.lib().mcbb_test_hook_set(b"dist_tma", 1)  # opt-in experiment: slower than the staged tile kernel (DESIGN.md §4)
+    try:
+        D_new = dist()
+    finally:
+        m.lib().mcbb_test_hook_set(b"dist_tma", -2 ** 63)
+    assert m.kernel_launch_count() - before >= 2
+    assert np.array_equal(D_new, D_old), np.abs(D_new - D_old).max()
+    assert np.array_equal(D_new, D_new.T) and np.all(np.diag(D_new) == 0)
+    sub = rng.choice(n, 300, replace=False)
+    Dref = orc.distance_matrix(X[sub], glen, gwt)
+    assert np.allclose(D_new[np.ix_(sub, sub)], Dref, rtol=1e-12, atol=1e-12)

@@ -1,0 +1,49 @@
+"""Materialised distance matrix at n = 20 000 for the two HBM-bound feature counts of the BASELINE configs (C1: F = 19 in
+groups [6,6,6,1]; C2: F = 4 in groups [1,1,1,1]): 8 n^2 bytes written / device time, TMA kernel and the general tile kernel.
+
+    python tools/bench_distmat.py [n]     prints one JSON object"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from __graft_entry__ import load_package  # noqa: E402
+
+
+def main():
+    m = load_package()
+    m.check(m.lib().mcbb_init(0))
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+    dev = torch.device("cuda:0")
+    out = {"n": n, "hbm_copy_peak_gbs": 6551.7}
+    D = torch.empty((n, n), dtype=torch.float64, device=dev)
+    for name, gl, gw in (("C1_F19", [6, 6, 6, 1], [1.0, 0.5, 0.5, 1.0]), ("C2_F4", [1, 1, 1, 1], [1.0, 0.75, 0.5, 1.0])):
+        F = sum(gl)
+        X = torch.randn((F, n), dtype=torch.float64, device=dev)
+        glen, gwt = np.asarray(gl, dtype=np.int32), np.asarray(gw)
+        for kernel, hook in (("tma", 0), ("tiles", 1)):
+            m.lib().mcbb_test_hook_set(b"dist_tma", 1 if kernel == "tma" else -2 ** 63)
+            best = None
+            for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m.check(m.lib().mcbb_distance_matrix_dev(C.c_void_p(X.data_ptr()), n, len(gl), glen.ctypes.data_as(m.abi.c_int32_p),
+                                                         gwt.ctypes.data_as(m.abi.c_double_p), C.c_void_p(D.data_ptr()),
+                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            gbs = 8.0 * n * n / (best * 1e-3) / 1e9
+            out["%s_%s" % (name, kernel)] = {"ms": best, "gbs_written": gbs, "frac_of_hbm_copy": gbs / 6551.7,
+                                             "fp64_adds_per_s": n * (n - 1) / 2 * 2 * F / (best * 1e-3)}
+        m.lib().mcbb_test_hook_set(b"dist_tma", -2 ** 63)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
