@@ -384,9 +384,12 @@ def main():
         Xs = X[:, sub].contiguous()
         K = max(1, int(round(0.005 * ms_)))
         cum = torch.empty((ms_,), dtype=torch.float64, device=dev)
+        kth = torch.empty((ms_,), dtype=torch.float64, device=dev)
+        # k = minpts + 1: the distance to the minpts-th OTHER point (the zero self-distance is rank 1)
         m.check(m.lib().mcbb_knn_dist_features_dev(C.c_void_p(Xs.data_ptr()), ms_, 3, gl.ctypes.data_as(ip),
-                                                   gw.ctypes.data_as(dp), 1, K, 0, C.c_void_p(0),
+                                                   gw.ctypes.data_as(dp), minpts + 1, K, 0, C.c_void_p(kth.data_ptr()),
                                                    C.c_void_p(cum.data_ptr()), stream_ptr()))
+        knn_eps.kdist = float(kth.median().item())  # the docs' other heuristic: k-dist graph (basic_usage.md:64-66)
         return float(cum.median().item()), K, ms_
 
     def pipeline(trace=None):
@@ -468,6 +471,32 @@ def main():
                                         "by the tiles themselves (early exits and saturation skips excluded), over the "
                                         "wall time of the whole DBSCAN incl. compaction, sorts and the labels D2H; "
                                         "peak = DFMA peak / 2"}}
+        # The cumulative-KNN eps is as large as the integration noise of this workload: everything is one
+        # cluster and the saturation skips remove most of the pair space.  Second clustering on the record with the docs'
+        # k-dist heuristic (median distance to the minpts-th neighbour on the same subsample): a tight eps, most points
+        # noise or small clusters, NO saturation — the expensive case for the tiles.
+        eps2 = knn_eps.kdist
+        m.check(m.lib().mcbb_pair_feature_counter(1, None, stream_ptr()))
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            a3, s3, c3 = m.dist.dbscan_features_sharded(X, gl, gw, eps2, minpts, rank, world, dist)
+        else:
+            a3, s3, c3 = m.dist.dbscan_features_device(X, gl, gw, eps2, minpts)
+        barrier()
+        t3 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        pf3 = C.c_int64(0)
+        m.check(m.lib().mcbb_pair_feature_counter(0, C.byref(pf3), stream_ptr()))
+        ex3 = torch.tensor([float(pf3.value)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ex3, op=dist.ReduceOp.SUM)
+        cluster["kdist_eps"] = {"eps": eps2, "eps_rule": "median distance to the minpts-th neighbour (k_dist) on the same subsample",
+                                "time_s": float(t3.item()), "n_clusters": int(s3.numel()), "n_noise": int((a3 == 0).sum().item()),
+                                "largest_clusters": sorted([int(x) for x in c3.tolist()], reverse=True)[:5],
+                                "pairs_per_s": 0.5 * n_all * (n_all - 1) / float(t3.item()), "labels_sha1": labels_hash(a3),
+                                "roofline_frac_fp64_add": 2.0 * float(ex3.item()) / float(t3.item()) / world / 1e12 / dadd_peak,
+                                "executed_pair_features": float(ex3.item())}
         if world == 1:
             # worst case for the early exits: the same points in random order (no locality along the index)
             perm = torch.from_numpy(np.random.default_rng(3).permutation(n_all)).to(dev)
@@ -479,29 +508,42 @@ def main():
             cluster["shuffled_order_time_s"] = time.perf_counter() - t0
             cluster["shuffled_same_partition"] = bool(int(s2.numel()) == int(s_.numel())
                                                       and int((a2 == 0).sum()) == int((a_ == 0).sum()))
-            # materialised distance matrix of 20 000 runs: the HBM-bound consumer of the same tiles
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            a4, s4, c4 = m.dist.dbscan_features_device(Xs, gl, gw, eps2, minpts)
+            torch.cuda.synchronize()
+            cluster["kdist_eps"]["shuffled_order_time_s"] = time.perf_counter() - t0
+            cluster["kdist_eps"]["shuffled_same_partition"] = bool(int(s4.numel()) == int(s3.numel())
+                                                                   and int((a4 == 0).sum()) == int((a3 == 0).sum()))
+            # materialised distance matrix of 20 000 points at the two HBM-bound feature counts of the BASELINE configs
+            # (C1: F = 19 in groups [6,6,6,1]; C2: F = 4) — synthetic features, the kernel does not care — and at this
+            # workload's own F = 201 (FP64-add bound: 2 F adds per 16 bytes written)
             nm = min(20000, n_all)
-            Xm = X[:, :nm].contiguous()
             Dm = torch.empty((nm, nm), dtype=torch.float64, device=dev)
-            best = None
-            for _ in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                m.check(m.lib().mcbb_distance_matrix_dev(C.c_void_p(Xm.data_ptr()), nm, 3, gl.ctypes.data_as(ip),
-                                                         gw.ctypes.data_as(dp), C.c_void_p(Dm.data_ptr()), stream_ptr()))
-                e1.record()
-                torch.cuda.synchronize()
-                ms_ = e0.elapsed_time(e1)
-                best = ms_ if best is None else min(best, ms_)
-            gbs = 8.0 * nm * nm / (best * 1e-3) / 1e9
             hbm_peak = 6551.7
             try:
                 hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
             except Exception:
                 pass
-            cluster["materialize"] = {"bound": "hbm", "n": nm, "n_features": Ftot, "ms": best, "achieved": gbs,
-                                      "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                      "note": "8 n^2 bytes written / best of 3 launches (mcbb_distance_matrix_dev)"}
+            cluster["materialize"] = {"bound": "hbm", "n": nm, "peak": hbm_peak, "unit": "GB/s",
+                                      "note": "8 n^2 bytes written / best of 3 launches (mcbb_distance_matrix_dev); peak = "
+                                              "measured HBM copy bandwidth (MEASURED_PEAKS.json)"}
+            for name, Xm, glm, gwm in (("C1_F19", torch.randn((19, nm), dtype=torch.float64, device=dev), [6, 6, 6, 1], [1, .5, .5, 1]),
+                                       ("C2_F4", torch.randn((4, nm), dtype=torch.float64, device=dev), [1, 1, 1, 1], [1, .75, .5, 1]),
+                                       ("C5_F201", X[:, :nm].contiguous(), list(gl), list(gw))):
+                glm_, gwm_ = np.asarray(glm, dtype=np.int32), np.asarray(gwm, dtype=np.float64)
+                best = None
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    m.check(m.lib().mcbb_distance_matrix_dev(C.c_void_p(Xm.data_ptr()), nm, len(glm), glm_.ctypes.data_as(ip),
+                                                             gwm_.ctypes.data_as(dp), C.c_void_p(Dm.data_ptr()), stream_ptr()))
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms_ = e0.elapsed_time(e1)
+                    best = ms_ if best is None else min(best, ms_)
+                gbs = 8.0 * nm * nm / (best * 1e-3) / 1e9
+                cluster["materialize"][name] = {"ms": best, "achieved": gbs, "frac": gbs / hbm_peak}
             del Dm
         else:
             # sharded labels == single-GPU fused labels on a 2*10^5-run subset (every rank runs the sharded stages,

@@ -267,6 +267,12 @@ static int launch_lane_impl(const SysDev& S, const SolverDev& o, const FeatDev& 
     }
     // prefer two resident CTAs per SM when that costs nothing
     while (bs > 32 && base + per_lane * bs > cap / 2 && base + per_lane * (bs / 2) <= cap / 2) bs /= 2;
+    {   // small ensembles (C1: 2 500 runs): 128-lane CTAs would occupy 20 of the 148 SMs — spread the lanes out
+        int dev0 = 0, sms0 = 148;
+        MCBB_CUDA_OK(cudaGetDevice(&dev0));
+        MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0));
+        while (bs > 32 && (io.n_mc + bs - 1) / bs < (long long)sms0) bs /= 2;
+    }
     size_t off = 0;
     lay.off_tsave = (int)off;
     off += sizeof(double) * (size_t)io.n_t;
