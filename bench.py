@@ -498,6 +498,18 @@ def main():
                                 "roofline_frac_fp64_add": 2.0 * float(ex3.item()) / float(t3.item()) / world / 1e12 / dadd_peak,
                                 "executed_pair_features": float(ex3.item())}
         if world == 1:
+            # the same k-dist heuristic on ALL runs (no subsample) through the fused per-row K-smallest kernel (csrc/topk.cuh)
+            kth_all = torch.empty((n_all,), dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.check(m.lib().mcbb_knn_dist_features_dev(C.c_void_p(X.data_ptr()), n_all, 3, gl.ctypes.data_as(ip),
+                                                       gw.ctypes.data_as(dp), minpts + 1, 1, 0, C.c_void_p(kth_all.data_ptr()),
+                                                       C.c_void_p(0), stream_ptr()))
+            torch.cuda.synchronize()
+            cluster["kdist_all_runs"] = {"time_s": time.perf_counter() - t0, "k": minpts + 1,
+                                         "median": float(kth_all.median().item()), "n_runs": n_all,
+                                         "pairs_per_s": float(n_all) * n_all / (time.perf_counter() - t0)}
+            del kth_all
             # worst case for the early exits: the same points in random order (no locality along the index)
             perm = torch.from_numpy(np.random.default_rng(3).permutation(n_all)).to(dev)
             Xs = X[:, perm].contiguous()

@@ -20,6 +20,7 @@
 
 #include "pair_tiles.cuh"
 #include "multi.cuh"
+#include "topk.cuh"
 
 namespace mcbb {
 
@@ -1166,6 +1167,34 @@ int knn_dist_features_dev(const double* X, long long n, int n_groups, const int3
                           cudaStream_t st) {
     if (n < 1) MCBB_FAIL("k_dist: empty input");
     if ((kth && (k < 1 || k > n)) || (cum && (K < 1 || K > n))) MCBB_FAIL("k_dist: k out of range");
+    {   // fused per-row K-smallest (topk.cuh): no row of D is ever materialised or sorted
+        const int KK = std::max(kth ? k : 1, cum ? K : 1);
+        if (KK <= TOPK_MAX && !tune_get("no_fused_topk", 0)) {
+            GroupTables gt;
+            if (int rc = upload_groups(n_groups, group_len, group_weight, &gt, st)) return rc;
+            TopkArgs a = {};
+            a.X = X;
+            a.n = n;
+            a.F = gt.F;
+            a.fw = gt.fw;
+            a.fmask = gt.fmask;
+            a.early_exit = gt.early_exit;
+            a.KK = KK;
+            a.k = k;
+            a.K = K;
+            MCBB_CUDA_OK(cudaFuncSetAttribute(k_topk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPK_SMEM));
+            const long long step = 65535LL * TILE;
+            for (long long r0 = 0; r0 < n; r0 += step) {
+                a.r0 = r0;
+                a.r1 = std::min(n, r0 + step);
+                a.kth = kth ? kth + r0 : nullptr;
+                a.cum = cum ? cum + r0 : nullptr;
+                k_topk_rows<<<(unsigned)((a.r1 - a.r0 + TILE - 1) / TILE), 256, TOPK_SMEM, st>>>(a);
+                MCBB_LAUNCHED();
+            }
+            return 0;
+        }
+    }
     if (block_rows <= 0) block_rows = std::max<long long>(1, (1LL << 28) / n);
     block_rows = std::min<long long>(block_rows, n);
     if (block_rows * n >= (1LL << 31)) MCBB_FAIL("k_dist: block_rows * n must stay below 2^31");

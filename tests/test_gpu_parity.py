@@ -953,3 +953,39 @@ def test_tma_distance_kernel_equals_tile_kernel_bitwise(gpu, orc, n, gl, gw):
     sub = rng.choice(n, 300, replace=False)
     Dref = orc.distance_matrix(X[sub], glen, gwt)
     assert np.allclose(D_new[np.ix_(sub, sub)], Dref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,gl,gw,k,K", [(3000, [5, 6, 1], [1.0, 0.5, 1.0], 4, 15), (20000, [5, 6, 1], [1.0, 0.5, 1.0], 4, 64),
+                                         (1037, [40, 40, 1], [1.0, 0.25, 1.0], 21, 5), (200, [3], [1.0], 1, 1)])
+def test_fused_topk_equals_sorted_rows(gpu, orc, n, gl, gw, k, K):
+    """k_dist / KNN_dist from the features (src/eval_clustering.jl:1504-1553): the fused per-row K-smallest kernel
+    (csrc/topk.cuh: no row of D materialised or sorted) against the row-block + segmented-sort path, bitwise, and both
+    against numpy on the oracle's matrix for a sample of rows."""
+    m = gpu
+    rng = np.random.default_rng(n + k)
+    F = int(np.sum(gl))
+    centers = rng.normal(0, 3, size=(5, F))
+    X = centers[rng.integers(0, 5, n)] + rng.normal(0, 0.5, size=(n, F))
+    X = np.asfortranarray(X[np.argsort(X[:, -1], kind="stable")])
+    glen, gwt = np.asarray(gl, dtype=np.int32), np.asarray(gw, dtype=np.float64)
+
+    def knn():
+        kth, cum = np.full(n, np.nan), np.full(n, np.nan)
+        m.check(m.lib().mcbb_knn_dist_features(X.ctypes.data_as(m.abi.c_double_p), n, len(gl), glen.ctypes.data_as(m.abi.c_int32_p),
+                                               gwt.ctypes.data_as(m.abi.c_double_p), k, K, 0, kth.ctypes.data_as(m.abi.c_double_p),
+                                               cum.ctypes.data_as(m.abi.c_double_p)))
+        return kth, cum
+    kth_f, cum_f = knn()
+    m.lib().mcbb_test_hook_set(b"no_fused_topk", 1)
+    try:
+        kth_s, cum_s = knn()
+    finally:
+        m.lib().mcbb_test_hook_set(b"no_fused_topk", -2 ** 63)
+    assert np.array_equal(kth_f, kth_s), np.abs(kth_f - kth_s).max()
+    assert np.array_equal(cum_f, cum_s), np.abs(cum_f - cum_s).max()
+    sub = np.sort(rng.choice(n, min(n, 150), replace=False))
+    Dref = orc.distance_matrix(X, glen, gwt)[sub] if n <= 3000 else None
+    if Dref is not None:
+        srt = np.sort(Dref, axis=1)
+        assert np.allclose(kth_f[sub], srt[:, k - 1], rtol=1e-12, atol=1e-12)
+        assert np.allclose(cum_f[sub], srt[:, :K].sum(axis=1), rtol=1e-12, atol=1e-12)
