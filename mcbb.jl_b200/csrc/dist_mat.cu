@@ -10,10 +10,17 @@
 //   * persistent CTAs (one per SM) walk the 128 x 64 tiles of the upper triangle;
 //   * feature slabs (8 features x 128 rows, 8 x 64 columns) arrive by TMA (cp.async.bulk.tensor.2d, tensor maps over
 //     X [F][n]; rows / features past the end are zero-filled by the hardware) into a 3-stage ring, completion on mbarriers;
-//   * every thread owns an 8 x 4 block of pairs (64 FP64 accumulators): 6 128-bit shared-memory loads feed 64 FP64 adds;
-//   * the block is stored straight from registers: 8 consecutive rows of a column are 64 contiguous bytes of D (direct
-//     tile), 4 consecutive columns of a row are 32 contiguous bytes of the mirrored tile — streaming 16-byte stores, no
-//     staging, no barrier; the stores of one tile drain while the next tile is being accumulated.
+//   * every thread owns an 8 x 4 block of pairs (64 FP64 accumulators; rows i*16 + tx, so that the lanes of a warp hold
+//     consecutive rows): 8 + 2 shared-memory loads feed 64 FP64 adds;
+//   * the finished tile is staged ONCE in shared memory in both orientations — [column][row] for D[tile] and, 128-byte
+//     swizzled, [row][column] for the mirrored tile — and leaves through TMA stores (cp.async.bulk.tensor, UTMASTG):
+//     whole 128-byte lines, no LSU traffic, clipped at the matrix edge by the hardware; the stores of one tile drain
+//     while the next tile is being accumulated (the staging is reused only after cp.async.bulk.wait_group.read).
+//     d(i,j) is bitwise symmetric, so a tile that straddles the diagonal simply writes all its elements (some twice, with
+//     identical bits); only the diagonal itself is forced to zero.
+//
+// First version of this kernel (stores straight from registers, no staging): 1.93 ms against 1.40 ms of the staged tile
+// kernel at n = 20 000, F = 19 — every store instruction of the mirrored orientation touched 32 scattered half sectors.
 #include <cuda.h>
 
 #include <algorithm>
@@ -26,9 +33,11 @@ namespace mcbb {
 constexpr int DM_R = 128;     // tile rows
 constexpr int DM_C = 64;      // tile columns
 constexpr int DM_FC = 8;      // features per slab
-constexpr int DM_STAGES = 3;  // slabs in flight
-constexpr int DM_TX = 16;      // thread grid 16 x 16: 8 rows x 4 columns per thread
+constexpr int DM_STAGES = 6;  // slabs in flight: the slab loads of the NEXT tile must be queued before this tile's TMA stores (the TMA unit works in order), or the next tile stalls behind 128 KB of stores
 constexpr unsigned DM_SLAB_BYTES = (DM_R + DM_C) * DM_FC * sizeof(double);
+constexpr int DM_STAGE_A = DM_R * DM_C;            // doubles: [64 columns][128 rows]
+constexpr int DM_STAGE_B = DM_R * DM_C;            // doubles: 4 boxes of [128 rows][16 columns], 128-byte swizzle
+constexpr size_t DM_SMEM = 1024 /* alignment slack */ + sizeof(double) * ((size_t)DM_STAGES * (DM_R + DM_C) * DM_FC + DM_STAGE_A + DM_STAGE_B);
 
 struct DistMatArgs {
     long long n;
@@ -58,8 +67,9 @@ __device__ __forceinline__ void dm_tma_load_2d(const unsigned dst, const CUtenso
         "l"(tmap), "r"(x), "r"(y), "r"(mbar)
         : "memory");
 }
-__device__ __forceinline__ void dm_st2(double* p, const double a, const double b) {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+__device__ __forceinline__ void dm_tma_store_2d(const CUtensorMap* tmap, const int x, const int y, const unsigned src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(src)
+                 : "memory");
 }
 
 // tile index t -> (br, bc): rows br = 0, 1, ... hold nbc - 2 br tiles each (bc = 2 br .. nbc - 1)
@@ -74,12 +84,24 @@ __device__ __forceinline__ void dm_tile_of(const long long t, const int nbc, int
     *bc = 2 * b + (int)(t - ((long long)b * nbc - (long long)b * (b - 1)));
 }
 
-__global__ void __launch_bounds__(256, 1) k_dist_mat_tma(const DistMatArgs a, const __grid_constant__ CUtensorMap tm_rows,
-                                                         const __grid_constant__ CUtensorMap tm_cols) {
-    __shared__ __align__(128) double s_slab[DM_STAGES][(DM_R + DM_C) * DM_FC];  // [stage][8 x 128 rows | 8 x 64 columns]
+// RPT = rows per thread: 8 -> 16 x 16 = 256 threads (8 x 4 pairs each), 4 -> 32 x 16 = 512 threads (4 x 4 pairs each: twice
+// the warps per scheduler to hide the shared-memory and FP64 latencies, at 1.6 x the shared-memory reads per pair)
+template <int RPT>
+__global__ void __launch_bounds__(DM_R / RPT * 16, 1) k_dist_mat_tma(const DistMatArgs a, const __grid_constant__ CUtensorMap tm_rows,
+                                                         const __grid_constant__ CUtensorMap tm_cols,
+                                                         const __grid_constant__ CUtensorMap tm_out,
+                                                         const __grid_constant__ CUtensorMap tm_out_t) {
+    extern __shared__ unsigned char dm_raw[];
     __shared__ __align__(8) unsigned long long s_full[DM_STAGES];
+    // 1024-byte aligned carve-up: the swizzled staging boxes need it
+    unsigned char* base = dm_raw + ((1024u - (dm_smem_u32(dm_raw) & 1023u)) & 1023u);
+    double* s_stB = reinterpret_cast<double*>(base);                      // 64 KB, 4 swizzled boxes
+    double* s_stA = s_stB + DM_STAGE_B;                                   // 64 KB
+    double (*s_slab)[(DM_R + DM_C) * DM_FC] = reinterpret_cast<double (*)[(DM_R + DM_C) * DM_FC]>(s_stA + DM_STAGE_A);
+    constexpr int TXN = DM_R / RPT;   // threads along the rows
+    constexpr int NTH = TXN * 16;
     const int tid = threadIdx.x;
-    const int tx = tid & (DM_TX - 1), ty = tid >> 4;
+    const int tx = tid % TXN, ty = tid / TXN;
     if (tid == 0) {
         for (int s = 0; s < DM_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dm_smem_u32(&s_full[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -108,9 +130,9 @@ __global__ void __launch_bounds__(256, 1) k_dist_mat_tma(const DistMatArgs a, co
         int br, bc;
         dm_tile_of(blockIdx.x + k * gridDim.x, a.nbc, &br, &bc);
         const long long tr = (long long)br * DM_R, tc = (long long)bc * DM_C;
-        double acc[8][4], accg[8][4];
+        double acc[RPT][4], accg[RPT][4];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < RPT; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j] = accg[i][j] = 0.;
         for (int sl = 0; sl < a.n_slabs; sl++, q++) {
@@ -125,15 +147,11 @@ __global__ void __launch_bounds__(256, 1) k_dist_mat_tma(const DistMatArgs a, co
             const int fc = min(DM_FC, a.F - f0);
 #pragma unroll 2
             for (int f = 0; f < fc; f++) {
-                double xr[8], xc[4];
-                const double2* pr = reinterpret_cast<const double2*>(s_r + f * DM_R + tx * 8);
+                double xr[RPT], xc[4];
+                const double* pr = s_r + f * DM_R + tx;  // rows i * TXN + tx: the lanes of a warp hold consecutive rows
                 const double2* pc = reinterpret_cast<const double2*>(s_c + f * DM_C + ty * 4);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double2 t = pr[i];
-                    xr[2 * i] = t.x;
-                    xr[2 * i + 1] = t.y;
-                }
+                for (int i = 0; i < RPT; i++) xr[i] = pr[i * TXN];
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     const double2 t = pc[j];
@@ -141,13 +159,13 @@ __global__ void __launch_bounds__(256, 1) k_dist_mat_tma(const DistMatArgs a, co
                     xc[2 * j + 1] = t.y;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < RPT; i++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) accg[i][j] += fabs(xr[i] - xc[j]);
                 if ((emask >> f) & 1u) {  // group closes: mat_elements += weight * distance_func(...)
                     const double w = __ldg(a.fw + f0 + f);
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
+                    for (int i = 0; i < RPT; i++)
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             acc[i][j] = fma(w, accg[i][j], acc[i][j]);
@@ -156,38 +174,35 @@ __global__ void __launch_bounds__(256, 1) k_dist_mat_tma(const DistMatArgs a, co
                 }
             }
         }
-        // ---- store the 8 x 4 block: direct D[ri, cj] and mirrored D[cj, ri] ------------------------------------------
-        const long long ri0 = tr + tx * 8, cj0 = tc + ty * 4;
-        const bool interior = (tr + DM_R <= a.n) && (tc + DM_C <= a.n) && (tc >= tr + DM_R);
-        if (interior) {
+        // ---- stage the 8 x 4 block in both orientations, then TMA stores -----------------------------------------------
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile has left the staging
+        __syncthreads();
+        const int cj0 = ty * 4;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                double* p = a.D + ri0 + a.n * (cj0 + j);
+        for (int i = 0; i < RPT; i++) {
+            const int r = i * TXN + tx;
+            double v[4];
 #pragma unroll
-                for (int i = 0; i < 8; i += 2) dm_st2(p + i, acc[i][j], acc[i + 1][j]);
-            }
+            for (int j = 0; j < 4; j++) v[j] = (tr + r == tc + cj0 + j) ? 0. : acc[i][j];  // D[p,p] = 0 also for Inf / NaN features
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                double* p = a.D + cj0 + a.n * (ri0 + i);
-                dm_st2(p, acc[i][0], acc[i][1]);
-                dm_st2(p + 2, acc[i][2], acc[i][3]);
-            }
-        } else {  // tiles on the diagonal or at the edge of the matrix: element by element
+            for (int j = 0; j < 4; j++) s_stA[(cj0 + j) * DM_R + r] = v[j];
+            // mirrored: box ty / 4 of [128 rows][16 columns]; 16-byte chunk index XOR (row mod 8) = the 128-byte swizzle
+            double* rowB = s_stB + (ty >> 2) * (DM_R * 16) + r * 16;
+            const int ch = (ty & 3) * 2;
+            *reinterpret_cast<double2*>(rowB + ((ch ^ (r & 7)) << 1)) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(rowB + (((ch + 1) ^ (r & 7)) << 1)) = make_double2(v[2], v[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+        __syncthreads();
+        if (tid == 0) {
+            dm_tma_store_2d(&tm_out, (int)tr, (int)tc, dm_smem_u32(s_stA));  // D[tr.., tc..]: box {128 rows, 64 columns}
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const long long ri = ri0 + i, cj = cj0 + j;
-                    if (ri >= a.n || cj >= a.n || cj < ri) continue;  // below the diagonal: written by another tile's mirror
-                    if (cj == ri) {
-                        __stcs(a.D + ri + a.n * cj, 0.);
-                    } else {
-                        __stcs(a.D + ri + a.n * cj, acc[i][j]);
-                        __stcs(a.D + cj + a.n * ri, acc[i][j]);
-                    }
-                }
+            for (int b = 0; b < 4; b++)                                     // D[tc + 16 b .., tr..]: box {16, 128}
+                dm_tma_store_2d(&tm_out_t, (int)tc + 16 * b, (int)tr, dm_smem_u32(s_stB + b * (DM_R * 16)));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA exits
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -211,11 +226,8 @@ static PFN_encodeTiled encode_tiled_fn() {
 int distance_matrix_tma(const double* X, long long n, int F, const double* fw, const unsigned short* fmask, double* D,
                         cudaStream_t st, bool* handled) {
     *handled = false;
-    // Measured (tools/bench_distmat.py, n = 20 000): 1.93 ms against 1.40 ms of the staged tile kernel at F = 19, 1.16 ms
-    // against 0.83 ms at F = 4 — storing straight from registers leaves every store instruction with 32 scattered half
-    // sectors, and that costs more than the shared-memory staging it saves.  Kept as an opt-in experiment (test hook
-    // "dist_tma" = 1) with its bitwise test; the default path is the staged tile kernel.
-    if (!tune_get("dist_tma", 0)) return 0;
+    // default for shapes that meet the TMA requirements; test hook "dist_tma" = 0 forces the general tile kernel
+    if (!tune_get("dist_tma", 1)) return 0;
     if (n < 2 * DM_R || (n & 1) || n > (1LL << 31) - 1) return 0;  // TMA strides are multiples of 16 bytes: n even
     if ((reinterpret_cast<size_t>(X) & 15) || (reinterpret_cast<size_t>(D) & 15)) return 0;
     PFN_encodeTiled enc = encode_tiled_fn();
@@ -230,6 +242,15 @@ int distance_matrix_tma(const double* X, long long n, int F, const double* fw, c
         return 0;
     if (enc(&tm_cols, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X, gdim, gstr, box_c, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    alignas(64) CUtensorMap tm_out, tm_out_t;
+    const cuuint64_t odim[2] = {(cuuint64_t)n, (cuuint64_t)n};
+    const cuuint32_t box_o[2] = {DM_R, DM_C}, box_t[2] = {16, DM_R};
+    if (enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)D, odim, gstr, box_o, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    if (enc(&tm_out_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)D, odim, gstr, box_t, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 0;
     DistMatArgs a = {};
     a.n = n;
@@ -247,7 +268,13 @@ int distance_matrix_tma(const double* X, long long n, int F, const double* fw, c
     MCBB_CUDA_OK(cudaGetDevice(&dev));
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = (int)std::min<long long>(tiles, (long long)sms);
-    k_dist_mat_tma<<<grid, 256, 0, st>>>(a, tm_rows, tm_cols);
+    if (tune_get("dist_tma_rpt", 8) == 8) {  // measured: 1.04 ms (8 rows per thread) against 1.27 ms (4 rows, 512 threads) at F = 19
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_dist_mat_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM));
+        k_dist_mat_tma<8><<<grid, 256, DM_SMEM, st>>>(a, tm_rows, tm_cols, tm_out, tm_out_t);
+    } else {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_dist_mat_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM));
+        k_dist_mat_tma<4><<<grid, 512, DM_SMEM, st>>>(a, tm_rows, tm_cols, tm_out, tm_out_t);
+    }
     MCBB_LAUNCHED();
     *handled = true;
     return 0;

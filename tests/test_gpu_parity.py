@@ -941,12 +941,17 @@ def test_tma_distance_kernel_equals_tile_kernel_bitwise(gpu, orc, n, gl, gw):
                                              gwt.ctypes.data_as(m.abi.c_double_p), D.ctypes.data_as(m.abi.c_double_p)))
         return D
     before = m.kernel_launch_count()
-    D_old = dist()
-    m.lib().mcbb_test_hook_set(b"dist_tma", 1)  # opt-in experiment: slower than the staged tile kernel
+    D_new = dist()  # default: the TMA kernel where the shape allows it (n even, >= 256)
+    m.lib().mcbb_test_hook_set(b"dist_tma_rpt", 8)  # its 256-thread variant (8 x 4 pairs per thread)
+    m.lib().mcbb_test_hook_set(b"dist_tma", 0)      # ... and the general tile kernel
     try:
-        D_new = dist()
+        D_old = dist()
+        m.lib().mcbb_test_hook_set(b"dist_tma", 1)
+        D_new8 = dist()
     finally:
         m.lib().mcbb_test_hook_set(b"dist_tma", -2 ** 63)
+        m.lib().mcbb_test_hook_set(b"dist_tma_rpt", -2 ** 63)
+    assert np.array_equal(D_new8, D_old)
     assert m.kernel_launch_count() - before >= 2
     assert np.array_equal(D_new, D_old), np.abs(D_new - D_old).max()
     assert np.array_equal(D_new, D_new.T) and np.all(np.diag(D_new) == 0)

@@ -21,12 +21,16 @@ def main():
     dev = torch.device("cuda:0")
     out = {"n": n, "hbm_copy_peak_gbs": 6551.7}
     D = torch.empty((n, n), dtype=torch.float64, device=dev)
-    for name, gl, gw in (("C1_F19", [6, 6, 6, 1], [1.0, 0.5, 0.5, 1.0]), ("C2_F4", [1, 1, 1, 1], [1.0, 0.75, 0.5, 1.0])):
+    cases_ = [("C1_F19", [6, 6, 6, 1], [1.0, 0.5, 0.5, 1.0]), ("C2_F4", [1, 1, 1, 1], [1.0, 0.75, 0.5, 1.0])]
+    for f in filter(None, os.environ.get("FS", "").split(",")):  # FS=8,12,32: one group of f features (scan over F)
+        cases_.append(("F%s" % f, [int(f)], [1.0]))
+    for name, gl, gw in cases_:
         F = sum(gl)
         X = torch.randn((F, n), dtype=torch.float64, device=dev)
         glen, gwt = np.asarray(gl, dtype=np.int32), np.asarray(gw)
-        for kernel, hook in (("tma", 0), ("tiles", 1)):
-            m.lib().mcbb_test_hook_set(b"dist_tma", 1 if kernel == "tma" else -2 ** 63)
+        for kernel, hook in (("tma", 4), ("tma_8rows", 8), ("tiles", 0)):
+            m.lib().mcbb_test_hook_set(b"dist_tma", 1 if hook else 0)
+            m.lib().mcbb_test_hook_set(b"dist_tma_rpt", hook if hook else -2 ** 63)
             best = None
             for _ in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,6 +46,7 @@ def main():
             out["%s_%s" % (name, kernel)] = {"ms": best, "gbs_written": gbs, "frac_of_hbm_copy": gbs / 6551.7,
                                              "fp64_adds_per_s": n * (n - 1) / 2 * 2 * F / (best * 1e-3)}
         m.lib().mcbb_test_hook_set(b"dist_tma", -2 ** 63)
+        m.lib().mcbb_test_hook_set(b"dist_tma_rpt", -2 ** 63)
     print(json.dumps(out))
 
 
