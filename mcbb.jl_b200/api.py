@@ -603,12 +603,37 @@ def _solve_b200(prob, t_save, alg, save_mode, kwargs):
         if np.iscomplexobj(prob.ic):
             saved = saved[:, 0::2] + 1j * saved[:, 1::2]
     if prob.eval_ode_func.failure_handling == "Inf":  # eval_mc_prob.jl:97-119
-        bad = (ret == abi.RET_DTLESSTHANMIN) | (ret == abi.RET_UNSTABLE)
-        feat[bad] = np.inf
-        if mat is not None:
-            mat[bad] = np.inf
-        if glob is not None:
-            glob[bad] = np.inf
+        # A DtLessThanMin / Unstable run becomes Inf only if its solution is EMPTY (it died before the first saved sample)
+        # or its last saved state exceeds 1e11 in some dimension; otherwise the reference warns and evaluates what it has.
+        # The last saved states of the (few) failed runs come from a second, sample-exporting solve of just those runs.
+        bad = np.nonzero((ret == abi.RET_DTLESSTHANMIN) | (ret == abi.RET_UNSTABLE))[0]
+        if len(bad):
+            smp = np.full((len(bad), len(t_save), ic.shape[1]), np.nan)  # SAVE_ALL: [run][sample][dim]; NaN = never reached
+            f2 = np.full((len(bad), nf, pfeat.n_meas), np.nan, order="F")
+            m2 = np.full((len(bad), pfeat.corr_nbins), np.nan, order="F") if mat is not None else None
+            g2 = np.full((len(bad), pfeat.n_global), np.nan, order="F") if glob is not None else None
+            r2 = np.zeros(len(bad), dtype=np.int32)
+            n2 = np.zeros((len(bad), 2), dtype=np.int64, order="F")
+            ic_b, par_b = np.asfortranarray(ic[bad]), np.asfortranarray(par[bad])
+            check(lib().mcbb_solve_features_saved(
+                C.byref(psys.desc), C.byref(o), C.byref(pfeat.opts), len(bad), ic_b.ctypes.data_as(dp),
+                par_b.ctypes.data_as(dp), t_save.ctypes.data_as(dp), len(t_save), f2.ctypes.data_as(dp),
+                m2.ctypes.data_as(dp) if m2 is not None else dp(), g2.ctypes.data_as(dp) if g2 is not None else dp(),
+                r2.ctypes.data_as(abi.c_int32_p), n2.ctypes.data_as(abi.c_int64_p), abi.SAVE_ALL, smp.ctypes.data_as(dp)))
+            reached = ~np.isnan(smp).all(axis=2)                      # [run][sample]: was this sample saved?
+            n_saved = reached.sum(axis=1)
+            last = smp[np.arange(len(bad)), np.maximum(n_saved - 1, 0)]  # sol.u[end] of the truncated solution
+            with np.errstate(invalid="ignore"):
+                empty = n_saved == 0  # length(sol) == 0
+                diverged = empty | (np.abs(last) > 1e11).any(axis=1) | np.isinf(last).any(axis=1)
+            feat[bad[diverged]] = np.inf
+            if mat is not None:
+                mat[bad[diverged]] = np.inf
+            if glob is not None:
+                glob[bad[diverged]] = np.inf
+            if (~diverged).any():
+                import warnings
+                warnings.warn("Failure Handling Warning, DtLessThanMin but Solution not diverging.")  # :117
     return feat, mat, glob, ret, nsteps, saved
 
 

@@ -994,3 +994,27 @@ def test_fused_topk_equals_sorted_rows(gpu, orc, n, gl, gw, k, K):
         srt = np.sort(Dref, axis=1)
         assert np.allclose(kth_f[sub], srt[:, k - 1], rtol=1e-12, atol=1e-12)
         assert np.allclose(cum_f[sub], srt[:, :K].sum(axis=1), rtol=1e-12, atol=1e-12)
+
+
+def test_failure_handling_inf_uses_the_divergence_test(gpu):
+    """failure_handling = :Inf (eval_mc_prob.jl:97-119): a DtLessThanMin / Unstable run becomes Inf only when its solution
+    is empty or its last saved state exceeds 1e11; a run that merely stalls keeps its (NaN) measures and a warning is
+    raised.  Logistic-free check with the Roessler network: a huge `a` makes the y components blow up (Unstable)."""
+    import warnings
+    m = gpu
+    Nr = 3
+    Lp = 2 * np.eye(Nr) - np.roll(np.eye(Nr), 1, 0) - np.roll(np.eye(Nr), -1, 0)
+    pars = m.roessler_parameters(40.0 * np.ones(Nr), 0.2 * np.ones(Nr), 5.7 * np.ones(Nr), 0.05, Lp, Nr)
+    rng = np.random.default_rng(3)
+    rp = m.ODEProblem(m.roessler_network, np.zeros(3 * Nr), (0.0, 60.0), pars)
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std), failure_handling="Inf")
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-1.0, 1.0), 24, pars, ("K", lambda: rng.uniform(0.0, 0.1)), ev, 0.5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sol = m.solve(prob, flag_check_inf_nan=False)
+    failed = (sol.retcode == m.abi.RET_UNSTABLE) | (sol.retcode == m.abi.RET_DTLESSTHANMIN)
+    assert failed.any(), sol.retcode
+    # exponential blow-up at rate 40: by the time the state is non-finite the last saved sample (if any) is far beyond 1e11,
+    # or no sample was saved at all -> Inf, as in the reference
+    assert np.isinf(sol.feat[failed]).all()
+    assert np.isfinite(sol.feat[~failed]).all()
