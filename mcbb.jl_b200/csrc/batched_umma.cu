@@ -53,6 +53,7 @@ struct UmmaArgs {
     int need_kl, kl_bins;
     double kl_nstd, kl_tol;
     double* smp;
+    int lw_mode;                 // light-warp kernel only (batched_umma_lw.cuh)
 };
 
 // TIMING = true: thread 0 of every CTA accumulates clock64() per phase into a.timing (development aid,
@@ -577,6 +578,10 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
 }
 
+}  // namespace mcbb
+#include "batched_umma_lw.cuh"
+namespace mcbb {
+
 template <int JB, int MINB, bool TIMING = false, bool KL = false, int NW = 1>
 static int launch_umma_one(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
     MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING, KL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -722,6 +727,15 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
         for (int k = 0; k < 8; k++) tot += (double)h[k];
         for (int k = 0; k < 8; k++)
             fprintf(stderr, "[umma timing] %-24s %6.2f %%  %10.0f clk per CTA\n", nm[k], 100. * h[k] / tot, (double)h[k] / grid);
+        *handled = true;
+        return 0;
+    }
+    // light-warp variant (batched_umma_lw.cuh): the short last row block carried one element per lane
+    if (pick->nw == 1 && pick->jb == 6 && pick->per_sm == 4 && !a.need_kl && N > 96 && (N - 96) * 6 <= 32 && tune_get("umma_lw", 0)) {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma_lw<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a.lw_mode = (int)tune_get("umma_lw", 0);
+        k_solve_batched_umma_lw<6, 4><<<grid, 128, smem, st>>>(a);
+        MCBB_LAUNCHED();
         *handled = true;
         return 0;
     }

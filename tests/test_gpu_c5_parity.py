@@ -187,3 +187,24 @@ def test_batched_sizes_with_a_matrix_measure_fall_through(gpu, orc, N):
     # a |cor| within rounding of a bin edge may move one pair (two ordered pairs) to the neighbouring bin
     assert d.max() <= 4.0 / npairs + 1e-15 and (d.max(axis=1) < 1e-15).mean() >= 0.7, d.max()
     cases.compare_features(sol.feat, ref, orc, psys, o, pfeat, ic0[idx], par0[idx], ts, min_checked=0.8)
+
+
+@pytest.mark.parametrize("N", [100, 97])
+def test_light_warp_variant_is_bitwise_equal(gpu, N):
+    """csrc/batched_umma_lw.cuh (experiment switch `umma_lw`; measured slower): the warp of the short row block
+    carries one element per lane and the row blocks rotate over the tensor-memory quadrants.  Every reduction adds in the
+    order of the plain mapping, so measures and step counts must be bitwise equal to the default kernel."""
+    m = gpu
+    prob, _ = cases.c5_problem(m, 700, N=N, seed=70 + N, tspan=(0.0, 120.0))
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    f0, _, _, r0, n0 = m.custom_solve_b200(prob, ts)
+    out = []
+    for mode in (1, 2):
+        m.lib().mcbb_test_hook_set(b"umma_lw", mode)
+        try:
+            out.append(m.custom_solve_b200(prob, ts))
+        finally:
+            m.lib().mcbb_test_hook_set(b"umma_lw", -2 ** 63)
+    for f1, _, _, r1, n1 in out:
+        assert np.array_equal(f0, f1, equal_nan=True) and np.array_equal(r0, r1) and np.array_equal(n0, n1)
+    assert np.all(r0 == 0) and np.isfinite(f0).all()
