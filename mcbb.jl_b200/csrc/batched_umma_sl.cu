@@ -16,6 +16,10 @@
 //   * B operands in shared memory, MN-major: a 16-column chunk holds the 8 digit bytes of TWO trajectories, so the
 //     thread of oscillator r publishes Re with one 8-byte store into the X panel and Im with one into the Y panel;
 //     two MMA chains per evaluation (A1 x X panel -> D1, A2 x Y panel -> D2), one commit.
+//   * a SPARSE A1 (every degree <= 8; the notebook's ring has 2 P1 = 2) is not sent through the tensor core at all: Re of
+//     the stage value is staged in shared memory and each oscillator adds its neighbours' differences in ascending order
+//     (template flag A1D: only D2 / the Y panel / A2 exist).  Measured equal in speed to the two-GEMM form — the kernel
+//     is bound by per-warp latency, not by the tensor pipe — but it needs half the tensor memory and digit panels.
 //   * every Runge-Kutta stage vector is thread-private shared memory [oscillator][trajectory][re | im][u, k1..k7];
 //     sums come back with tcgen05.ld into the thread that owns the oscillator: no CTA barrier inside the stage loop.
 //   * statistics of eval_ode_run fused: mean / std of Re and Im in registers (Welford); for the KL-histogram measures
@@ -52,6 +56,8 @@ struct SlArgs {
     const unsigned char* a2_img;
     const int* deg1;              // [128]
     const int* deg2;
+    const unsigned char* nbr1;    // [128][8] neighbours of A1 in ascending order (A1D instantiation: sparse A1 summed directly)
+    int nb1max;                   // largest degree of A1
     const int* filter_pos;        // [128] position of oscillator r in the state_filter, -1 = not reported
     double scalars[MCBB_N_SCALARS];
     int n_par;
@@ -217,8 +223,12 @@ static __device__ __noinline__ void sl_finish_run(const SlFin* __restrict__ fp, 
     if (SMP) __syncthreads();  // the digit panels served as scratch: all done before they are rewritten
 }
 
-// SMP = true: the instantiation that keeps the saved samples (KL-hist measures and / or a correlation matrix measure)
-template <int JB, int MINB, bool SMP>
+// SMP = true: the instantiation that keeps the saved samples (KL-hist measures and / or a correlation matrix measure).
+// A1D = true: A1 has at most 8 neighbours per oscillator (the notebook's ring: 2 P1 = 2), so its coupling sum is taken
+// directly — Re of every stage value is staged in shared memory (double-buffered over the stages) and every oscillator
+// adds its neighbours' differences in ascending order, the very expression of the right-hand side — and only the dense
+// A2 (2 P2 = 44) goes through the tensor core: half the digit panels, half the MMAs, half the tensor-memory read-back.
+template <int JB, int MINB, bool SMP, bool A1D>
 __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -233,9 +243,12 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
     constexpr int RS = 2 * UM_NSLOT * JB + 2;  // row stride (doubles) = 2 (mod 4): conflict-free 128-bit accesses
     static_assert(JB % 2 == 0, "two trajectories share a 16-column chunk of the digit panels");
 
-    unsigned char* sBx = smem;                                  // [JB/2][128][16]  digits of Re, two trajectories per chunk
-    unsigned char* sBy = smem + (JB / 2) * 2048;                // [JB/2][128][16]  digits of Im
-    double* sm_k = (double*)(smem + JB * 2048);                 // [N + 1][JB][2][8] (+2 pad)
+    constexpr int PANEL = A1D ? (JB / 2) * 2048 : JB * 2048;    // digit panels
+    constexpr int XST = A1D ? 2 * JB * 128 * 8 : 0;             // Re of the stage values, [2][JB][128] doubles
+    unsigned char* sBx = smem;                                  // [JB/2][128][16]  digits of Re, two trajectories per chunk (not A1D)
+    unsigned char* sBy = smem + (A1D ? 0 : (JB / 2) * 2048);    // [JB/2][128][16]  digits of Im
+    double* sm_xst = (double*)(smem + PANEL);
+    double* sm_k = (double*)(smem + PANEL + XST);               // [N + 1][JB][2][8] (+2 pad)
     const double* const sm_ts = c_um_ts;                        // [n_t] (constant bank)
     double* sm_red0 = sm_k + (size_t)(N + 1) * RS;              // [4][JB]
     double* sm_red1 = sm_red0 + 4 * JB;                         // [4][JB]
@@ -255,7 +268,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
 #define KX(slot, j) kb[(2 * (j)) * UM_NSLOT + (slot)]
 #define KY(slot, j) kb[(2 * (j) + 1) * UM_NSLOT + (slot)]
 
-    for (int i = tid; i < JB * 2048 / 16; i += 128) ((uint4*)smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (PANEL + XST) / 16; i += 128) ((uint4*)smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < (N + 1) * RS; i += 128) sm_k[i] = 0.;
     const int cw = (blockIdx.x / a.n_sms) & 3;  // the controller lanes sit in a different warp for each resident CTA
     const bool is_ctl = (wid == cw) && lane < JB;
@@ -272,7 +285,8 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(mbar_full));
     }
-    constexpr unsigned TCOLS = (16 * JB + 64) <= 64 ? 64u : (16 * JB + 64) <= 128 ? 128u : (16 * JB + 64) <= 256 ? 256u : 512u;
+    constexpr unsigned TUSE = A1D ? (8 * JB + 32) : (16 * JB + 64);
+    constexpr unsigned TCOLS = TUSE <= 32 ? 32u : TUSE <= 64 ? 64u : TUSE <= 128 ? 128u : TUSE <= 256 ? 256u : 512u;
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)), "n"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -283,12 +297,13 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
     const unsigned tmem_row = tmem_base + ((unsigned)(32 * wid) << 16);
-    const unsigned tmem_d1 = tmem_base, tmem_d2 = tmem_base + NH;
-    const unsigned tmem_a1 = tmem_base + 2 * NH, tmem_a2 = tmem_a1 + 32;
+    constexpr unsigned TD2 = A1D ? 0u : NH, TA = A1D ? NH : 2 * NH;  // column offsets of D2 and of the A operands
+    const unsigned tmem_d1 = tmem_base, tmem_d2 = tmem_base + TD2;
+    const unsigned tmem_a1 = tmem_base + TA, tmem_a2 = tmem_base + TA + (A1D ? 0u : 32u);
     {  // rows of A1, A2 -> lane r: 128 K bytes = 32 columns each
         unsigned w[32];
 #pragma unroll 1
-        for (int which = 0; which < 2; which++) {
+        for (int which = A1D ? 1 : 0; which < 2; which++) {
             const unsigned char* img = which ? a.a2_img : a.a1_img;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                 w[4 * q + 2] = t4.z;
                 w[4 * q + 3] = t4.w;
             }
-            um_tmem_st32(tmem_row + 2 * NH + 32u * which, w);
+            um_tmem_st32(tmem_row + TA + (A1D ? 0u : 32u * which), w);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -314,6 +329,9 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
     const int degh1 = a.deg1[row] << 19, degh2 = a.deg2[row] << 19;  // deg 2^51 in units of the high word
     const double dg1 = (double)a.deg1[row], dg2 = (double)a.deg2[row];
     const int fpos = a.filter_pos[row];
+    // A1D: the (at most 8) neighbours of this oscillator in A1, ascending, one byte each
+    const uint2 nbw = A1D ? reinterpret_cast<const uint2*>(a.nbr1)[row] : make_uint2(0u, 0u);
+    const int nb1 = A1D ? a.deg1[row] : 0, nb1max = A1D ? a.nb1max : 0;
     const double fxs = a.fx_scale, fxi = a.fx_inv;
     const int fx_hi_max = valid ? __double2hiint(a.fx_max) : 0x7fffffff;  // rows >= N never raise the flag
     unsigned phase = 0;
@@ -510,7 +528,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
             }
             if (c.fin)  // uniform over the CTA; out of line: it runs once per trajectory, the loop around it once per step
                 sl_finish_run<SMP>(a.fin, SMP ? a.smp + ((size_t)blockIdx.x * JB + j) * n_t * (2 * N) : nullptr, c.fin_ok != 0,
-                                   c.fin_run, valid ? fpos : -1, amx[j], a2x[j], amy[j], a2y[j], smem, JB * 2048, sm_mx, sm_my,
+                                   c.fin_run, valid ? fpos : -1, amx[j], a2x[j], amy[j], a2y[j], smem, PANEL + XST, sm_mx, sm_my,
                                    sm_var, sm_hist);
             if (c.fresh) {
                 if (valid) {
@@ -523,7 +541,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
             }
         }
         if (all_done) break;
-        clampmask = 0u;  // (the digit panels, lent as scratch above, are rewritten completely by stage (a) of every round)
+        clampmask = 0u;  // (the digit panels and the Re staging, lent as scratch above, are rewritten by stage (a) of every round)
 
         // ---- one round: 6 right-hand-side evaluations of the whole batch (branch-free over the trajectories) --------
 #pragma unroll 1
@@ -560,18 +578,21 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                 // out of the fixed-point range (or NaN)?  One integer compare on the exponent words; the digits of such a
                 // value are meaningless, which is harmless: a step that is ACCEPTED with the flag set invalidates the launch
                 // (the ensemble is repeated on the lane kernels), a rejected one is simply retried with a smaller step
-                const int hmx = max(UM_HI(x) & 0x7fffffff, UM_HI(y) & 0x7fffffff);
+                const int hmx = A1D ? (UM_HI(y) & 0x7fffffff) : max(UM_HI(x) & 0x7fffffff, UM_HI(y) & 0x7fffffff);
                 clampmask |= (hmx >= fx_hi_max ? 1u : 0u) << j;
-                uint2 dx, dy;
-                {
+                if (A1D) {
+                    sm_xst[((s & 1) * JB + j) * 128 + row] = x;  // read by the neighbours after the stage barrier
+                } else {
+                    uint2 dx;
                     const double t = fma(x, fxs, UM_C(1));
                     dx.x = (unsigned)UM_LO(t);
                     dx.y = (unsigned)UM_HI(t) & 0xFFFFFu;
-                    const double t2 = fma(y, fxs, UM_C(1));
-                    dy.x = (unsigned)UM_LO(t2);
-                    dy.y = (unsigned)UM_HI(t2) & 0xFFFFFu;
+                    *reinterpret_cast<uint2*>(sBx_row + (j >> 1) * 2048 + (j & 1) * 8) = dx;  // rows >= N meet zero columns of A
                 }
-                *reinterpret_cast<uint2*>(sBx_row + (j >> 1) * 2048 + (j & 1) * 8) = dx;  // rows >= N meet zero columns of A
+                uint2 dy;
+                const double t2 = fma(y, fxs, UM_C(1));
+                dy.x = (unsigned)UM_LO(t2);
+                dy.y = (unsigned)UM_HI(t2) & 0xFFFFFu;
                 *reinterpret_cast<uint2*>(sBy_row + (j >> 1) * 2048 + (j & 1) * 8) = dy;
             }
             // (b) D1 = A1 X, D2 = A2 Y on the tensor core; publish / issue / wait exactly as in batched_umma.cu
@@ -590,8 +611,9 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                                  "r"(phase)
                                  : "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int ks = 0; ks < KSTEPS; ks++)
-                        um_mma_i8_ts(tmem_d1, tmem_a1 + 8u * ks, um_desc(sBx_addr + ks * 512, 128, 2048), idesc, ks > 0 ? 1u : 0u);
+                    if (!A1D)
+                        for (int ks = 0; ks < KSTEPS; ks++)
+                            um_mma_i8_ts(tmem_d1, tmem_a1 + 8u * ks, um_desc(sBx_addr + ks * 512, 128, 2048), idesc, ks > 0 ? 1u : 0u);
                     for (int ks = 0; ks < KSTEPS; ks++)
                         um_mma_i8_ts(tmem_d2, tmem_a2 + 8u * ks, um_desc(sBy_addr + ks * 512, 128, 2048), idesc, ks > 0 ? 1u : 0u);
                     um_commit(mbar);
@@ -608,27 +630,45 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
             // (c) row r of A1 X and A2 Y from tensor memory -> k = f(z) + coupling
             double kvx[JB], kvy[JB];
             double* const kst = kb + 2 + s;
-            unsigned v1[JB / 2][16], v2[JB / 2][16];  // all loads in flight, one wait
+            unsigned v1[A1D ? 1 : JB / 2][16], v2[JB / 2][16];  // all loads in flight, one wait
 #pragma unroll
             for (int g = 0; g < JB / 2; g++) {
-                um_tmem_ld16_nowait(tmem_row + 16u * g, v1[g]);       // D1 columns of trajectories 2g, 2g + 1
-                um_tmem_ld16_nowait(tmem_row + NH + 16u * g, v2[g]);  // D2
+                if (!A1D) um_tmem_ld16_nowait(tmem_row + 16u * g, v1[g]);  // D1 columns of trajectories 2g, 2g + 1
+                um_tmem_ld16_nowait(tmem_row + TD2 + 16u * g, v2[g]);      // D2
+            }
+            double at[JB];
+            if (A1D) {  // sum_{A1} (x_j - x_i), neighbours in ascending order, while the tensor-memory loads are in flight
+                const double* const xst = sm_xst + (s & 1) * JB * 128;
+#pragma unroll
+                for (int j = 0; j < JB; j++) at[j] = 0.;
+                for (int q = 0; q < nb1max; q++) {
+                    const unsigned nbq = ((q < 4 ? nbw.x : nbw.y) >> (8 * (q & 3))) & 0xffu;
+                    if (q < nb1) {
+#pragma unroll
+                        for (int j = 0; j < JB; j++) at[j] += xst[j * 128 + nbq] - xs[j];
+                    }
+                }
             }
             um_tmem_wait_ld();
 #pragma unroll
             for (int g = 0; g < JB / 2; g++) {
-                um_tmem_landed(v1[g]);
+                if (!A1D) um_tmem_landed(v1[g]);
                 um_tmem_landed(v2[g]);
             }
 #pragma unroll
             for (int j = 0; j < JB; j++) {
-                const unsigned* w1 = v1[j >> 1] + 8 * (j & 1);
                 const unsigned* w2 = v2[j >> 1] + 8 * (j & 1);
-                const double sx = um_recombine(w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], degh1) * fxi;  // (A1 x)_r
                 const double sy = um_recombine(w2[0], w2[1], w2[2], w2[3], w2[4], w2[5], w2[6], degh2) * fxi;  // (A2 y)_r
                 const SlSlotCtl& c = ctl[j];
                 const double x = xs[j], y = ys[j];
-                const double attr = fma(-dg1, x, sx) * c.eP1;  // epsP1 sum_{A1} (x_j - x_i)
+                double attr;  // epsP1 sum_{A1} (x_j - x_i)
+                if (A1D) {
+                    attr = at[j] * c.eP1;
+                } else {
+                    const unsigned* w1 = v1[j >> 1] + 8 * (j & 1);
+                    const double sx = um_recombine(w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], degh1) * fxi;  // (A1 x)_r
+                    attr = fma(-dg1, x, sx) * c.eP1;
+                }
                 const double rep = fma(-dg2, y, sy) * c.eP2;
                 const double cr = c.lam - fma(x, x, y * y);     // lambda - |z|^2
                 kvx[j] = fma(cr, x, -c.om * y) + attr;
@@ -753,22 +793,23 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
 }
 
-static size_t sl_smem_bytes(int JB, int N) {
-    return (size_t)JB * 2048 + sizeof(double) * ((size_t)(N + 1) * (2 * UM_NSLOT * JB + 2) + 8 * (size_t)JB + 3 * 128) +
+static size_t sl_smem_bytes(int JB, int N, bool a1d) {
+    return (size_t)JB * (a1d ? 3072 : 2048) + sizeof(double) * ((size_t)(N + 1) * (2 * UM_NSLOT * JB + 2) + 8 * (size_t)JB + 3 * 128) +
            sizeof(SlSlotCtl) * (size_t)JB + 24 + sizeof(int) * (4 * (size_t)JB + 64) + 128;
 }
 
-template <int JB, int MINB>
-static int launch_sl_one(const SlArgs& a, size_t smem, int grid, bool smp, cudaStream_t st) {
-    if (smp) {
-        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma_sl<JB, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_solve_batched_umma_sl<JB, MINB, true><<<grid, 128, smem, st>>>(a);
-    } else {
-        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma_sl<JB, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_solve_batched_umma_sl<JB, MINB, false><<<grid, 128, smem, st>>>(a);
-    }
+template <int JB, int MINB, bool SMP, bool A1D>
+static int launch_sl_inst(const SlArgs& a, size_t smem, int grid, cudaStream_t st) {
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma_sl<JB, MINB, SMP, A1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_batched_umma_sl<JB, MINB, SMP, A1D><<<grid, 128, smem, st>>>(a);
     MCBB_LAUNCHED();
     return 0;
+}
+
+template <int JB, int MINB>
+static int launch_sl_one(const SlArgs& a, size_t smem, int grid, bool smp, bool a1d, cudaStream_t st) {
+    if (smp) return a1d ? launch_sl_inst<JB, MINB, true, true>(a, smem, grid, st) : launch_sl_inst<JB, MINB, true, false>(a, smem, grid, st);
+    return a1d ? launch_sl_inst<JB, MINB, false, true>(a, smem, grid, st) : launch_sl_inst<JB, MINB, false, false>(a, smem, grid, st);
 }
 
 // Returns handled = true when the problem was run on the tcgen05 path.  `range_overflow` (may be null) receives the
@@ -808,6 +849,17 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
                 deg2[i]++;
             }
         }
+    // sparse A1 (every degree <= 8): summed directly, only A2 on the tensor core
+    int nb1max = 0;
+    for (int i = 0; i < N; i++) nb1max = std::max(nb1max, deg1[i]);
+    const bool a1d = nb1max <= 8 && tune_get("umma_sl_a1d", 1) != 0;
+    std::vector<unsigned char> nbr1(128 * 8, 0);
+    if (a1d)
+        for (int i = 0; i < N; i++) {
+            int q = 0;
+            for (int j = 0; j < N; j++)
+                if (img1[(size_t)i * 128 + j]) nbr1[(size_t)i * 8 + q++] = (unsigned char)j;
+        }
     std::vector<int> fpos(128, -1);
     if (F.filter) {
         std::vector<int> fh(F.n_filter);
@@ -839,6 +891,9 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     int* d_deg2 = (int*)scratch_get(72, sizeof(int) * 128);
     int* d_fpos = (int*)scratch_get(73, sizeof(int) * 128);
     unsigned int* d_ovf = (unsigned int*)scratch_get(74, 64);
+    unsigned char* d_nbr1 = (unsigned char*)scratch_get(93, nbr1.size());
+    if (!d_nbr1) MCBB_FAIL("solve: device allocation failed");
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_nbr1, nbr1.data(), nbr1.size(), cudaMemcpyHostToDevice, st));
     if (!d_img1 || !d_img2 || !d_deg1 || !d_deg2 || !d_fpos || !d_ovf) MCBB_FAIL("solve: device allocation failed");
     MCBB_CUDA_OK(cudaMemcpyAsync(d_img1, img1.data(), img1.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaMemcpyAsync(d_img2, img2.data(), img2.size(), cudaMemcpyHostToDevice, st));
@@ -851,6 +906,8 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     a.a2_img = d_img2;
     a.deg1 = d_deg1;
     a.deg2 = d_deg2;
+    a.nbr1 = d_nbr1;
+    a.nb1max = nb1max;
     a.filter_pos = d_fpos;
     a.ovf = d_ovf;
     for (int q = 0; q < MCBB_N_SCALARS; q++) a.scalars[q] = S.scalars[q];
@@ -871,21 +928,26 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     a.matrix_meas = F.matrix_meas;
     a.corr_nbins = F.corr_nbins;
 
-    struct Cfg { int jb, per_sm; };
-    static const Cfg cfgs[] = {{4, 3}, {4, 2}, {2, 2}, {2, 1}};
+    // 2 trajectories x 5 CTAs per SM (20 warps, 96 registers) beats 4 x 3 (12 warps) by 6 % for mean / std and 3 % with the
+    // KL-hist measures — the kernel is latency-bound per warp, so more resident warps pay — but loses 5 % when the
+    // correlation runs (profiles/r2_sl_jb_variants.jsonl): the first entry is skipped for a matrix measure
+    // (2 x 6 at 80 registers: 132 k against 134 k for 2 x 5 — the gain from more warps ends there)
+    struct Cfg { int jb, per_sm; bool not_with_matrix; };
+    static const Cfg cfgs[] = {{2, 5, true}, {4, 3, false}, {4, 2, false}, {2, 2, false}, {2, 1, false}};
     const int want_jb = (int)tune_get("umma_sl_jb", 0), want_per = (int)tune_get("umma_sl_per_sm", 0);
     const Cfg* pick = nullptr;
     for (const Cfg& c : cfgs) {
         if (want_jb && c.jb != want_jb) continue;
         if (want_per && c.per_sm != want_per) continue;
-        const size_t need = sl_smem_bytes(c.jb, N);
+        if (c.not_with_matrix && F.matrix_meas != MCBB_MAT_NONE && !(want_jb && want_per)) continue;
+        const size_t need = sl_smem_bytes(c.jb, N, a1d);
         if ((need + 1024) * c.per_sm <= (size_t)227 * 1024 && need <= (size_t)226 * 1024) {
             pick = &c;
             break;
         }
     }
     if (!pick) return 0;
-    const size_t smem = sl_smem_bytes(pick->jb, N);
+    const size_t smem = sl_smem_bytes(pick->jb, N, a1d);
     int dev = 0, sms = 148;
     MCBB_CUDA_OK(cudaGetDevice(&dev));
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -923,10 +985,11 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     int rc = 1;
-    if (pick->jb == 4 && pick->per_sm == 3) rc = launch_sl_one<4, 3>(a, smem, grid, smp, st);
-    else if (pick->jb == 4 && pick->per_sm == 2) rc = launch_sl_one<4, 2>(a, smem, grid, smp, st);
-    else if (pick->jb == 2 && pick->per_sm == 2) rc = launch_sl_one<2, 2>(a, smem, grid, smp, st);
-    else if (pick->jb == 2 && pick->per_sm == 1) rc = launch_sl_one<2, 1>(a, smem, grid, smp, st);
+    if (pick->jb == 4 && pick->per_sm == 3) rc = launch_sl_one<4, 3>(a, smem, grid, smp, a1d, st);
+    else if (pick->jb == 4 && pick->per_sm == 2) rc = launch_sl_one<4, 2>(a, smem, grid, smp, a1d, st);
+    else if (pick->jb == 2 && pick->per_sm == 2) rc = launch_sl_one<2, 2>(a, smem, grid, smp, a1d, st);
+    else if (pick->jb == 2 && pick->per_sm == 1) rc = launch_sl_one<2, 1>(a, smem, grid, smp, a1d, st);
+    else if (pick->jb == 2 && pick->per_sm == 5) rc = launch_sl_one<2, 5>(a, smem, grid, smp, a1d, st);
     if (rc) return rc;
     // a run that left the fixed-point range invalidates this launch: the caller falls through to the lane kernels
     unsigned int h_ovf = 0;

@@ -97,11 +97,11 @@ def c3_problem(m, n_mc=400, seed=5, N=10, tspan=(0.0, 200.0), tail=0.9, lam_max=
     return prob, [1.0, 0.0, 1.0]
 
 
-def c4_problem(m, n_mc, N=100, tspan=(0.0, 200.0), tail=0.7, seed=7, corr=True, p_r=0.04):
+def c4_problem(m, n_mc, N=100, tspan=(0.0, 200.0), tail=0.7, seed=7, corr=True, p_r=0.04, P1=None):
     """C4 (paper/stuartlandau/stuart_landau_sathiyadevi-standard-config.ipynb cell 1): Stuart-Landau ring,
     lambda=1, omega=2, r1=0.01 (P1=1), r2=0.22 (P2=22), A1/A2 Watts-Strogatz p_r=0.04 (seed 7 / 7+1000), eps~U(1.8,2.1)
     (seed 8), z0~U(-1,1)+iU(-1,1) (seed 9), measures mean/std/KL of re and im + correlation_ecdf."""
-    P1, P2 = int(round(0.01 * N)) or 1, int(round(0.22 * N))
+    P1, P2 = P1 or int(round(0.01 * N)) or 1, int(round(0.22 * N))
     A1 = watts_strogatz(N, 2 * P1, p_r, seed)
     A2 = watts_strogatz(N, 2 * P2, p_r, seed + 1000)
     pars = m.stuart_landau_sathiyadevi_pars(1.0, 2.0, 1.925, N, P1, P2, A1, A2)

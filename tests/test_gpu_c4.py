@@ -120,6 +120,30 @@ def test_sl_tensor_core_kernel_ring_sizes(gpu, orc, N, filt, corr):
         _check_ecdf(sol.matrix, ref["matrix"], N, min_exact=0.7)
 
 
+@pytest.mark.parametrize("P1,forced", [(1, False), (1, True), (6, False)])
+def test_sl_sparse_and_dense_attractive_coupling(gpu, orc, P1, forced):
+    """A sparse A_1 (every degree <= 8: the notebook's 2 P_1 = 2 ring with rewiring) is summed directly from shared
+    memory and only A_2 goes through the tensor core; a denser A_1 (2 P_1 = 12), or the hook, sends both through it.
+    Each variant against the oracle at converged tolerances, in one launch."""
+    m = gpu
+    prob, _ = cases.c4_problem(m, 48, tspan=(0.0, 40.0), seed=21, corr=False, P1=P1)
+    A1 = np.asarray(prob.pars.A_1)
+    assert (A1.sum(axis=1).max() <= 8) == (P1 == 1)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10 ** 7)
+    if forced:
+        m.lib().mcbb_test_hook_set(b"umma_sl_a1d", 0)
+    try:
+        before = m.kernel_launch_count()
+        sol = m.solve(prob, **kw)
+        assert m.kernel_launch_count() - before == 1
+    finally:
+        m.lib().mcbb_test_hook_set(b"umma_sl_a1d", -2 ** 63)
+    ref, ctx = _ref(m, orc, prob, ic0, par0, **kw)
+    assert np.array_equal(sol.retcode, ref["retcode"]) and np.all(sol.retcode == 0)
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.9)
+
+
 def test_c4_full_size_properties(gpu):
     """20 000 runs at the paper's time span: results do not depend on where a run sits in the ensemble (twins far apart
     are bitwise equal, a shuffled sub-ensemble solved alone reproduces its rows), every run succeeds, amplitudes stay

@@ -1,7 +1,7 @@
 """Times C4's integrate+featurize stage (Stuart-Landau N=100, Watts-Strogatz A_1/A_2, tspan (0,200), tail 0.7) resident on
 the device, for three measure sets: mean/std, + KL-hist, + correlation_ecdf (the notebook's full set).
 
-    python tools/bench_sl.py [n_runs]      prints one JSON object"""
+    python tools/bench_sl.py [n_runs] [hook=value ...]      prints one JSON object (hooks: mcbb_test_hook_set)"""
 import ctypes as C
 import json
 import os
@@ -19,6 +19,9 @@ def main():
     m = load_package()
     m.check(m.lib().mcbb_init(0))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
+    hooks = dict(kv.split("=") for kv in sys.argv[2:])
+    for k, v in hooks.items():
+        m.check(m.lib().mcbb_test_hook_set(k.encode(), int(v)))
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(7)
     ic = np.empty((200, n))
@@ -26,7 +29,7 @@ def main():
     ic[1::2] = rng.uniform(-1, 1, (100, n))
     par = rng.uniform(1.8, 2.1, (1, n))
     ic_d, par_d = torch.from_numpy(ic).to(dev), torch.from_numpy(par).to(dev)
-    out = {"n_runs": n}
+    out = {"n_runs": n, "hooks": hooks}
     sets = {"mean_std": (("mean_real", "std_real", "mean_imag", "std_imag"), False),
             "mean_std_kl": (("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"), False),
             "mean_std_kl_corr_ecdf": (("mean_real", "std_real", "kl_real", "mean_imag", "std_imag", "kl_imag"), True)}
