@@ -277,6 +277,27 @@ int mcbb_knn_dist_features_dev(const double* X_dev, int64_t n, int32_t n_groups,
                                const double* group_weight, int32_t k, int32_t K, int64_t block_rows,
                                double* kth_dev, double* cum_dev, void* stream);
 
+/* ---- histogram-mode features (distance_matrix(...; histograms = true), src/eval_clustering.jl:187-211) -------------
+ * `values` is the slab of ONE per-dimension measure in the layout mcbb_solve_features writes it: [n_dim][n_mc].
+ * mcbb_order_stats: out[i] = the ranks[i]-th smallest value (0-based) over all n_dim * n_mc values — what
+ * _compute_hist_edges (:607-642) needs: rank 0 and count - 1 are the extrema, the two neighbours of a type-7 quantile give
+ * the IQR; *n_nan receives the number of NaNs (they are not ranked).  The edges themselves (a Julia range) are built by the
+ * host from those numbers.
+ * mcbb_hist_rows: replaces _compute_hist_weights (:587-598) + ecdf_hist (:759-762): per run the Float32 histogram of its
+ * n_dim values over the equidistant `edges` (host array; closed = :left, values outside dropped), with use_ecdf != 0 its
+ * Float32 cumulative sum divided by its last entry.  rows_out[b][r] (n_edges - 1 rows of n_mc, the feature layout of
+ * mcbb_distance_matrix / mcbb_dbscan_features) is the row of run order[r] (order NULL: r itself — sort!(sol, prob),
+ * setup_mc_prob.jl:520-536, folded in); normalize != 0 applies (x - lo) / range to every value first (normalize(sol),
+ * setup_mc_prob.jl:635-660).  Bit-identical to the reference arithmetic (no contraction). */
+int mcbb_order_stats(const double* values, int64_t count, int32_t n_ranks, const int64_t* ranks, double* out, int64_t* n_nan);
+int mcbb_order_stats_dev(const double* values_dev, int64_t count, int32_t n_ranks, const int64_t* ranks, double* out,
+                         int64_t* n_nan, void* stream);
+int mcbb_hist_rows(const double* values, int64_t n_mc, int32_t n_dim, const int64_t* order, int32_t normalize, double lo,
+                   double range, const double* edges, int32_t n_edges, int32_t use_ecdf, double* rows_out);
+int mcbb_hist_rows_dev(const double* values_dev, int64_t n_mc, int32_t n_dim, const int64_t* order_dev, int32_t normalize,
+                       double lo, double range, const double* edges, int32_t n_edges, int32_t use_ecdf, double* rows_dev,
+                       void* stream);
+
 /* ---- sparse interchange ------------------------------------------------------------
  * Replace the NonzeroSparseMatrix branch of distance_matrix (src/eval_clustering.jl:541-550 builds it column by
  * column from a dense row; src/sparse_clustering.jl:37-110 is the type): only entries with d < sparse_threshold are

@@ -25,6 +25,7 @@ EXPORTS = [
     "mcbb_test_hook_set", "mcbb_pair_feature_counter",
     "mcbb_multi_init", "mcbb_multi_finalize", "mcbb_multi_info", "mcbb_solve_features_multi", "mcbb_dbscan_features_multi",
     "mcbb_solve_cluster_multi",
+    "mcbb_order_stats", "mcbb_order_stats_dev", "mcbb_hist_rows", "mcbb_hist_rows_dev",
 ]
 
 _lib = None
@@ -80,6 +81,11 @@ def lib():
     L.mcbb_knn_dist_features.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_int32, C.c_int32, C.c_int64, dp, dp]
     L.mcbb_knn_dist_features_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_int32, C.c_int32, C.c_int64, vp, vp,
                                              vp]
+    L.mcbb_order_stats.argtypes = [dp, C.c_int64, C.c_int32, lp, dp, lp]
+    L.mcbb_order_stats_dev.argtypes = [vp, C.c_int64, C.c_int32, lp, dp, lp, vp]
+    L.mcbb_hist_rows.argtypes = [dp, C.c_int64, C.c_int32, lp, C.c_int32, C.c_double, C.c_double, dp, C.c_int32, C.c_int32, dp]
+    L.mcbb_hist_rows_dev.argtypes = [vp, C.c_int64, C.c_int32, vp, C.c_int32, C.c_double, C.c_double, dp, C.c_int32, C.c_int32,
+                                     vp, vp]
     L.mcbb_distance_sparse_count.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_double, ip]
     L.mcbb_distance_sparse_count_dev.argtypes = [vp, C.c_int64, C.c_int32, ip, dp, C.c_double, vp, vp]
     L.mcbb_distance_sparse_fill.argtypes = [dp, C.c_int64, C.c_int32, ip, dp, C.c_double, lp, ip, dp]

@@ -862,6 +862,27 @@ def _compute_hist_edges(data, N_dim, k_bin, nbin_default=50, nbin=None, bin_edge
     (min-bw):bw:(max+bw) with bw = (max-min)/(nbin-1)) or explicit equidistant `bin_edges` switch the rule off."""
     data = np.asarray(data, dtype=np.float64)
     minval, maxval = float(data.min()), float(data.max())
+    q75 = q25 = None
+    if bin_edges is None and nbin is None:
+        q75, q25 = np.percentile(data, [75, 25])  # type-7 quantiles, like StatsBase.iqr
+    return _hist_edges_from_stats(minval, maxval, q25, q75, N_dim, k_bin, nbin_default, nbin, bin_edges)
+
+
+def _quantile_neighbours(count, q):
+    """Type-7 quantile q of `count` sorted values = lerp(x[lo], x[lo + 1], gamma): returns (lo, hi, gamma)."""
+    v = (count - 1) * q
+    lo = int(math.floor(v))
+    return lo, min(lo + 1, count - 1), v - lo
+
+
+def _lerp(a, b, t):
+    """numpy's quantile interpolation (numpy/lib/_function_base_impl.py `_lerp`)."""
+    d = b - a
+    return b - d * (1 - t) if t >= 0.5 else a + d * t
+
+
+def _hist_edges_from_stats(minval, maxval, q25, q75, N_dim, k_bin, nbin_default=50, nbin=None, bin_edges=None):
+    """The rule of _compute_hist_edges on the four numbers it needs (also fed from the device's order statistics)."""
     if bin_edges is not None and nbin is not None:
         raise MCBBError("bin_edges and nbin in kwargs. Please choose only one.")
     if nbin is not None:
@@ -874,7 +895,6 @@ def _compute_hist_edges(data, N_dim, k_bin, nbin_default=50, nbin=None, bin_edge
         if len(edges) < 2:
             raise MCBBError("bin_edges needs all edges of the histogram (one more element than bins)")
         return edges, float(edges[1] - edges[0])
-    q75, q25 = np.percentile(data, [75, 25])  # type-7 quantiles, like StatsBase.iqr
     bw = 0.5 * k_bin * float(q75 - q25) / N_dim ** (1 / 3.0)
     if bw != 0:
         edges = _julia_range(minval - bw, bw, maxval + bw)

@@ -21,7 +21,7 @@ struct ScratchSlot {
     size_t cap = 0;
 };
 constexpr int MAX_DEV = 16;
-constexpr int N_SCRATCH = 96;
+constexpr int N_SCRATCH = 112;
 static ScratchSlot g_scratch[MAX_DEV][N_SCRATCH];
 static std::mutex g_scratch_mu;
 
@@ -133,6 +133,10 @@ int labels_dev(const int* root_label, long long n, long long* assignments, long 
 int gather_columns_dev(const double* X, long long ld, const int* idx, long long m, int F, double* Xout,
                        cudaStream_t st);
 int knn_dist_dense_dev(const double* D, long long n, int k, int K, double* kth, double* cum, cudaStream_t st);
+int hist_rows_dev(const double* values, long long n_mc, int n_dim, const long long* order, int normalize, double lo,
+                  double range, const double* edges_host, int n_edges, int use_ecdf, double* out, cudaStream_t st);
+int order_stats_dev(const double* values, long long count, int n_ranks, const long long* ranks_host, double* out_host,
+                    long long* n_nan_host, cudaStream_t st);
 int knn_dist_features_dev(const double* X, long long n, int n_groups, const int32_t* group_len,
                           const double* group_weight, int k, int K, long long block_rows, double* kth, double* cum,
                           cudaStream_t st);
@@ -749,6 +753,49 @@ int mcbb_knn_dist_dense(const double* D, int64_t n, int32_t k, int32_t K, double
     if (int rc = knn_dist_dense_dev(d_D, n, k, K, kth_out ? d_k : nullptr, cum_out ? d_c : nullptr, st)) return rc;
     if (kth_out) MCBB_CUDA_OK(cudaMemcpyAsync(kth_out, d_k, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (cum_out) MCBB_CUDA_OK(cudaMemcpyAsync(cum_out, d_c, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcbb_order_stats_dev(const double* values_dev, int64_t count, int32_t n_ranks, const int64_t* ranks, double* out,
+                         int64_t* n_nan, void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
+    if (!values_dev || (n_ranks > 0 && (!ranks || !out))) MCBB_FAIL("order_stats: NULL argument");
+    return order_stats_dev(values_dev, count, n_ranks, (const long long*)ranks, out, (long long*)n_nan, (cudaStream_t)stream);
+}
+int mcbb_order_stats(const double* values, int64_t count, int32_t n_ranks, const int64_t* ranks, double* out, int64_t* n_nan) {
+    ApiGuard guard_((cudaStream_t)0);
+    if (!values || (n_ranks > 0 && (!ranks || !out))) MCBB_FAIL("order_stats: NULL argument");
+    if (count < 1) MCBB_FAIL("order_stats: empty input");
+    double* d_v = (double*)scratch_get(100, sizeof(double) * (size_t)count);
+    if (!d_v) MCBB_FAIL("order_stats: device allocation failed");
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_v, values, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, 0));
+    return order_stats_dev(d_v, count, n_ranks, (const long long*)ranks, out, (long long*)n_nan, 0);
+}
+int mcbb_hist_rows_dev(const double* values_dev, int64_t n_mc, int32_t n_dim, const int64_t* order_dev, int32_t normalize,
+                       double lo, double range, const double* edges, int32_t n_edges, int32_t use_ecdf, double* rows_dev,
+                       void* stream) {
+    ApiGuard guard_((cudaStream_t)stream);
+    if (!values_dev || !edges || !rows_dev) MCBB_FAIL("hist_rows: NULL argument");
+    if (n_edges < 2 || n_dim < 1) MCBB_FAIL("hist_rows: needs at least two edges and one dimension");
+    return hist_rows_dev(values_dev, n_mc, n_dim, (const long long*)order_dev, normalize, lo, range, edges, n_edges, use_ecdf,
+                         rows_dev, (cudaStream_t)stream);
+}
+int mcbb_hist_rows(const double* values, int64_t n_mc, int32_t n_dim, const int64_t* order, int32_t normalize, double lo,
+                   double range, const double* edges, int32_t n_edges, int32_t use_ecdf, double* rows_out) {
+    ApiGuard guard_((cudaStream_t)0);
+    if (!values || !edges || !rows_out) MCBB_FAIL("hist_rows: NULL argument");
+    if (n_edges < 2 || n_dim < 1 || n_mc < 1) MCBB_FAIL("hist_rows: needs at least two edges, one dimension and one run");
+    const size_t nv = (size_t)n_mc * (size_t)n_dim, no = (size_t)n_mc * (size_t)(n_edges - 1);
+    double* d_v = (double*)scratch_get(100, sizeof(double) * nv);
+    double* d_o = (double*)scratch_get(101, sizeof(double) * no);
+    long long* d_ord = order ? (long long*)scratch_get(102, sizeof(long long) * (size_t)n_mc) : nullptr;
+    if (!d_v || !d_o || (order && !d_ord)) MCBB_FAIL("hist_rows: device allocation failed");
+    cudaStream_t st = 0;
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_v, values, sizeof(double) * nv, cudaMemcpyHostToDevice, st));
+    if (order) MCBB_CUDA_OK(cudaMemcpyAsync(d_ord, order, sizeof(long long) * (size_t)n_mc, cudaMemcpyHostToDevice, st));
+    if (int rc = hist_rows_dev(d_v, n_mc, n_dim, d_ord, normalize, lo, range, edges, n_edges, use_ecdf, d_o, st)) return rc;
+    MCBB_CUDA_OK(cudaMemcpyAsync(rows_out, d_o, sizeof(double) * no, cudaMemcpyDeviceToHost, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }

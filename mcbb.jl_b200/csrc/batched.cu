@@ -1,6 +1,8 @@
 // batched.cu — block-cooperative ensemble Tsit5 for LARGE phase-oscillator networks (N ~ 24..160):
 // kuramoto_network (src/systems.jl:119-130) and non_local_kuramoto_ring (src/systems.jl:230-239),
-// with the eval_ode_run mean / std statistics (src/eval_mc_prob.jl:191-198) fused into the tail.
+// with the eval_ode_run statistics (src/eval_mc_prob.jl:191-198) fused into the tail: mean / std as running moments,
+// empirical_1D_KL_divergence_hist (the third default measure, eval_mc_prob.jl:312-330) from the saved samples of the
+// runs in flight, kept in a device scratch and reduced by the owning thread when the run finishes.
 //
 // Why a second kernel: one trajectory per lane needs 9 N doubles of state per lane, which no longer fits on
 // chip for N = 100.  Here a CTA integrates a BATCH of B trajectories in lockstep rounds.  Every trajectory
@@ -19,6 +21,7 @@
 #include <vector>
 
 #include "lane_core.cuh"
+#include "umma_common.cuh"  // um_kl_hist
 
 namespace mcbb {
 
@@ -41,6 +44,9 @@ struct BatchArgs {
     int n_meas, meas[MCBB_MAX_MEAS], n_filter, cyclic;
     SolveIO io;
     double* acc;  // [grid][3][NE][nthreads]  mean, M2, cyclic offset (L2-resident scratch)
+    int need_kl, kl_bins;
+    double kl_nstd, kl_tol;
+    double* smp;  // [grid][B][n_t][IG*TI] saved samples of the runs in flight (KL-hist measures only)
 };
 
 // sin and cos together, |x| < ~1e6: Cody-Waite reduction by pi/2 with two FMAs + fdlibm kernel polynomials.
@@ -448,6 +454,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
             const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
             const int ks0 = ctl[b].s0 < 1 ? 1 : ctl[b].s0, ks1 = ctl[b].s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
             if (ks0 < ks1) {
+                double* const smp_b = a.need_kl ? a.smp + ((size_t)blockIdx.x * B + b) * n_t * NP : nullptr;
                 // Welford state in registers across the samples of this step: one L2 round trip per accepted step
                 double am[TI], a2[TI], as[TI];
 #pragma unroll
@@ -480,6 +487,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
                                 x = x - as[r];
                             }
                         }
+                        if (a.need_kl) smp_b[(size_t)k * NP + ig * TI + r] = x;
                         const double delta = x - am[r];
                         if (fabs(delta) <= 1.7976931348623157e308) {
                             const double mnew = fma(delta, rk, am[r]);
@@ -541,8 +549,14 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
                 const double mean = ok ? ACCS(0, e) : nan("");
                 const double m2 = ACCS(1, e);
                 const double sd = ok ? sqrt((m2 < 0. ? 0. : m2) / (double)(n_t - 2)) : nan("");
-                for (int m = 0; m < a.n_meas; m++)
-                    a.io.feat[((long long)m * a.n_filter + pos) * n_mc + run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
+                for (int m = 0; m < a.n_meas; m++) {
+                    double v = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
+                    if (a.meas[m] == MCBB_MEAS_KL_HIST)  // the samples this thread wrote itself: no barrier needed
+                        v = ok ? um_kl_hist(a.smp + ((size_t)blockIdx.x * B + b) * n_t * NP + i, NP, n_t, mean, sd, a.kl_bins,
+                                            a.kl_nstd, a.kl_tol, nullptr)
+                               : nan("");
+                    a.io.feat[((long long)m * a.n_filter + pos) * n_mc + run] = v;
+                }
             }
         }
         __syncthreads();
@@ -580,11 +594,12 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     const int N = S.n_osc;
     constexpr int TI = TI_;
     if (S.system != MCBB_SYS_KURAMOTO_NETWORK && S.system != MCBB_SYS_NONLOCAL_KURAMOTO_RING) return 0;
-    if (o.alg != MCBB_ALG_TSIT5 || F.need_kl || F.n_global > 0 || F.n_comp != 1) return 0;
+    if (o.alg != MCBB_ALG_TSIT5 || F.n_global > 0 || F.n_comp != 1) return 0;
+    if (F.need_kl && (F.kl_bins > UM_MAX_KL_BINS || F.kl_bins < 3 || tune_get("no_batched_kl", 0))) return 0;
     if (F.matrix_meas != MCBB_MAT_NONE) return 0;  // no matrix measure here: the lane kernels compute it
     if (N < 24 || N > 160 || hs == nullptr) return 0;
     for (int m = 0; m < F.n_meas; m++)
-        if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD) return 0;
+        if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD && F.meas[m] != MCBB_MEAS_KL_HIST) return 0;
     if (S.system == MCBB_SYS_NONLOCAL_KURAMOTO_RING)
         for (int p = 0; p < S.n_par; p++)
             if (S.par_slot[p] != 1) return 0;  // only phase_delay sweeps are batched (omega_0, fak enter the tables)
@@ -713,6 +728,15 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     const int grid = (int)std::min<long long>(want, sms);
     a.acc = (double*)scratch_get(54, sizeof(double) * (size_t)grid * 3 * TI * TB * a.nthreads);
     if (!a.acc) MCBB_FAIL("solve: device allocation failed");
+    a.need_kl = F.need_kl;
+    a.kl_bins = F.kl_bins;
+    a.kl_nstd = F.kl_nstd;
+    a.kl_tol = F.kl_tol;
+    a.smp = nullptr;
+    if (F.need_kl) {
+        a.smp = (double*)scratch_get(94, sizeof(double) * (size_t)grid * a.B * (size_t)io.n_t * (size_t)NP);
+        if (!a.smp) MCBB_FAIL("solve: device allocation failed");
+    }
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     int rc;
     if (TB == 2)

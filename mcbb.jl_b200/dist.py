@@ -84,6 +84,75 @@ def dbscan_features_device(X_t, group_len, group_weight, eps, minpts):
     return a, s[: k[0]], c[: k[0]]
 
 
+def order_stats_device(v_t, ranks):
+    """Values at the given 0-based ranks of the ascending order of a torch CUDA tensor, and its NaN count
+    (mcbb_order_stats_dev: one radix sort on the device, a few numbers back)."""
+    rk = np.ascontiguousarray(ranks, dtype=np.int64)
+    out = np.zeros(len(rk), dtype=np.float64)
+    nn = np.zeros(1, dtype=np.int64)
+    check(lib().mcbb_order_stats_dev(_ptr(v_t), v_t.numel(), len(rk), rk.ctypes.data_as(abi.c_int64_p),
+                                     out.ctypes.data_as(abi.c_double_p), nn.ctypes.data_as(abi.c_int64_p), _stream()))
+    return out, int(nn[0])
+
+
+def histogram_features_device(feat_t, n_meas_dim, n_dim, weights, par_t, order_t=None, normalize=True, k_bin=1,
+                              nbin_default=50, use_ecdf=True, skip_zero_weight=True):
+    """Device-resident counterpart of `normalize(sol)` + the feature assembly of `distance_matrix(sol, prob, weights;
+    histograms = true, k_bin)` (src/setup_mc_prob.jl:635-660, src/eval_clustering.jl:187-211, 587-642) for the per-dimension
+    measures and the parameter columns: feat_t [n_meas_dim * n_dim, n] as mcbb_solve_features_dev wrote it, par_t
+    [n_par, n]; order_t (int64 [n], optional) = sortperm of the runs (`sort!(sol, prob)`).  Per measure: extrema and
+    quartile neighbours by one device sort (mcbb_order_stats_dev) -> edges on the host (a Julia range from four numbers) ->
+    Float32 ECDF rows on the device (mcbb_hist_rows_dev).  The measures never leave the device.  Returns
+    (X_t [F, n], group_len, group_weight, hist_edges, bin_widths): bit-identical to the host path (api._assemble_features),
+    ready for dbscan_features_device / dbscan_features_sharded.  weights = one per measure, then one per parameter."""
+    import torch
+
+    from . import api
+    n = feat_t.shape[1]
+    n_par = par_t.shape[0]
+    if len(weights) != n_meas_dim + n_par:
+        raise api.MCBBError("Amount of weights not the same as Measures + Parameters")
+    if order_t is not None:
+        order_t = order_t.to(torch.int64).contiguous()
+    blocks, glen, gw, hist_edges, bin_widths = [], [], [], [], []
+    for mi in range(n_meas_dim):
+        slab = feat_t[mi * n_dim:(mi + 1) * n_dim]
+        assert slab.is_contiguous()
+        count = slab.numel()
+        l25, h25, g25 = api._quantile_neighbours(count, 0.25)
+        l75, h75, g75 = api._quantile_neighbours(count, 0.75)
+        st, n_nan = order_stats_device(slab, [0, count - 1, l25, h25, l75, h75])
+        finite = n_nan == 0 and np.isfinite(st[0]) and np.isfinite(st[1])
+        if skip_zero_weight and weights[mi] == 0 and finite:
+            hist_edges.append(None)
+            bin_widths.append(None)
+            continue
+        if n_nan:
+            raise api.MCBBError("histogram features: measure %d holds NaN values" % (mi + 1))
+        lo, rng = (st[0], st[1] - st[0]) if normalize else (0.0, 1.0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            v = (st - lo) / rng if normalize else st
+        q25, q75 = api._lerp(v[2], v[3], g25), api._lerp(v[4], v[5], g75)
+        edges, bw = api._hist_edges_from_stats(float(v[0]), float(v[1]), q25, q75, n_dim, k_bin, nbin_default)
+        edges = np.ascontiguousarray(edges, dtype=np.float64)
+        rows = torch.empty((len(edges) - 1, n), dtype=torch.float64, device=feat_t.device)
+        check(lib().mcbb_hist_rows_dev(_ptr(slab), n, n_dim, _ptr(order_t) if order_t is not None else C.c_void_p(0),
+                                       1 if normalize else 0, float(lo), float(rng), edges.ctypes.data_as(abi.c_double_p),
+                                       len(edges), 1 if use_ecdf else 0, _ptr(rows), _stream()))
+        blocks.append(rows)
+        glen.append(len(edges) - 1)
+        gw.append(weights[mi] * bw)
+        hist_edges.append(edges)
+        bin_widths.append(bw)
+    par_s = par_t if order_t is None else par_t[:, order_t]
+    for p in range(n_par):
+        blocks.append(par_s[p:p + 1].to(torch.float64))
+        glen.append(1)
+        gw.append(weights[n_meas_dim + p])
+    X_t = torch.cat(blocks, dim=0).contiguous()
+    return X_t, np.asarray(glen, dtype=np.int32), np.asarray(gw, dtype=np.float64), hist_edges, bin_widths
+
+
 _TILE = 64  # pair-tile edge of the stage kernels (csrc/pair_tiles.cuh)
 
 

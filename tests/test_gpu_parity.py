@@ -856,6 +856,49 @@ def test_tensor_core_kernel_default_measures_with_kl(gpu, orc):
     assert np.isfinite(sol.feat[:, :, 2]).mean() > 0.9
 
 
+@pytest.mark.parametrize("system", ["ring", "weighted_network"])
+def test_fp64_batched_kernel_default_measures_with_kl(gpu, orc, system):
+    """The reference's default measures (mean, std, empirical_1D_KL_divergence_hist; eval_mc_prob.jl:191-198) for the
+    systems the FP64 block-cooperative kernel integrates — non_local_kuramoto_ring and a WEIGHTED kuramoto_network — run
+    in that kernel (one launch), the KL from the saved samples of the runs in flight; against the oracle and against
+    the lane kernels (hook)."""
+    m = gpu
+    rng = np.random.default_rng(41)
+    prng = np.random.default_rng(42)
+    if system == "ring":
+        N = 40
+        pars = m.non_local_kuramoto_ring_parameters(N, 0.2, 0.3, lambda x: np.exp(-2 * abs(x)) / (2 * np.pi))
+        rp = m.ODEProblem(m.non_local_kuramoto_ring, np.zeros(N), (0.0, 60.0), pars)
+        sweep = ("phase_delay", lambda: prng.uniform(0.0, 0.6))
+    else:
+        N = 36
+        A = cases.erdos_renyi(N, 0.3, 43) * np.random.default_rng(44).uniform(0.5, 1.5, (N, N))
+        pars = m.kuramoto_network_parameters(0.5, np.random.default_rng(45).normal(0.5, 0.1, N), N, A)
+        rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), (0.0, 60.0), pars)
+        sweep = ("K", lambda: prng.uniform(0.0, 6.0))
+    ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist), cyclic_setback=True)
+    prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 70, pars, sweep, ev, 0.8)
+    ic0, par0 = prob.ic.copy(), prob.par.copy()
+    kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10**7)
+    before = m.kernel_launch_count()
+    sol = m.solve(prob, **kw)
+    assert m.kernel_launch_count() - before == 1, "expected one launch of k_solve_batched"
+    assert sol.feat.shape == (70, N, 3)
+    ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
+    assert np.array_equal(sol.retcode, ref["retcode"]) and np.all(sol.retcode == 0)
+    cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.5)
+    assert np.isfinite(sol.feat[:, :, 2]).mean() > 0.9
+    m.lib().mcbb_test_hook_set(b"no_batched_kl", 1)
+    try:
+        prob.ic, prob.par = ic0.copy(), par0.copy()
+        before = m.kernel_launch_count()
+        sol2 = m.solve(prob, **kw)
+        assert m.kernel_launch_count() - before > 1  # the lane kernels' replay pass
+    finally:
+        m.lib().mcbb_test_hook_set(b"no_batched_kl", -2 ** 63)
+    assert np.nanmax(np.abs(sol2.feat[:, :, :2] - sol.feat[:, :, :2])) < 1e-6
+
+
 def test_tensor_core_kernel_retcodes_and_fixed_dt(gpu, orc):
     """Failure and option paths of the tcgen05 integrator against the oracle: MaxIters at the exact attempt count
     (a mix of finished and truncated runs), NaN measures for truncated runs, and a user-given initial dt."""
@@ -1017,4 +1060,59 @@ def test_failure_handling_inf_uses_the_divergence_test(gpu):
     # exponential blow-up at rate 40: by the time the state is non-finite the last saved sample (if any) is far beyond 1e11,
     # or no sample was saved at all -> Inf, as in the reference
     assert np.isinf(sol.feat[failed]).all()
-    assert np.isfinite(sol.feat[~failed]).all()
+    assert np.isfinite(sol.feat[sol.retcode == 0]).all()  # (a MaxIters run is not touched by :Inf: it keeps its NaN measures)
+
+
+@pytest.mark.parametrize("k_bin,zero_weight", [(1.0, False), (0.25, True)])
+def test_histogram_features_on_the_device_equal_the_host_path(gpu, k_bin, zero_weight):
+    """normalize(sol) + sort!(sol, prob) + the histogram-mode feature assembly of distance_matrix (setup_mc_prob.jl:520-536,
+    635-660; eval_clustering.jl:187-211, 587-642) done on the device — extrema and quartiles by a device sort, Float32 ECDF
+    rows by mcbb_hist_rows_dev — are bit-identical to the host mirror, including a measure whose IQR is zero (the
+    nbin_default fallback) and one that is skipped for its zero weight; the host-buffer entry agrees as well."""
+    import warnings
+
+    import torch
+    m = gpu
+    n, n_dim = 3001, 37
+    rng = np.random.default_rng(17)
+    feat = np.empty((n, n_dim, 4))
+    feat[:, :, 0] = rng.normal(0.3, 1.0, (n, n_dim))
+    feat[:, :, 1] = np.where(rng.random((n, n_dim)) < 0.4, rng.normal(-2, 0.1, (n, n_dim)), rng.normal(3, 0.5, (n, n_dim)))
+    feat[:, :, 2] = np.where(rng.random((n, n_dim)) < 0.1, rng.uniform(0, 5, (n, n_dim)), 1.25)  # IQR = 0
+    feat[:, :, 3] = rng.exponential(2.0, (n, n_dim))
+    par = rng.uniform(0, 1, (n, 1))
+    weights = [1.0, 0.5, 0.25, 0.0 if zero_weight else 0.75, 1.0]
+    order = np.argsort(par[:, 0], kind="stable")
+    sol = m.DEMCBBSol(np.asfortranarray(feat[order]), None, None, np.zeros(n, dtype=np.int32), None, 100, None)
+    prob, _ = cases.c1_problem(m, n_ics=4)
+    prob.par = np.asfortranarray(par[order])
+    prob.N_mc = n
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fm = m.distance_matrix(m.normalize(sol), prob, weights, histograms=True, k_bin=k_bin, materialize=False)
+    dev = torch.device("cuda:0")
+    feat_t = torch.from_numpy(np.ascontiguousarray(feat.transpose(2, 1, 0)).reshape(4 * n_dim, n)).to(dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        X_t, gl, gw, edges, bws = m.dist.histogram_features_device(feat_t, 4, n_dim, weights, torch.from_numpy(par.T.copy()).to(dev),
+                                                                   torch.from_numpy(order).to(dev), k_bin=k_bin)
+    assert np.array_equal(gl, fm.group_len) and np.array_equal(gw, fm.group_weight)
+    assert (edges[3] is None) == zero_weight
+    X = X_t.cpu().numpy().T
+    assert X.shape == fm.X.shape
+    assert np.array_equal(X, fm.X, equal_nan=True)
+    # host-buffer entry on one measure
+    e0 = np.ascontiguousarray(edges[0])
+    slab = np.ascontiguousarray(feat[:, :, 0].T)
+    rows = np.empty((len(e0) - 1, n))
+    lo, hi = feat[:, :, 0].min(), feat[:, :, 0].max()
+    m.check(m.lib().mcbb_hist_rows(slab.ctypes.data_as(m.abi.c_double_p), n, n_dim, order.ctypes.data_as(m.abi.c_int64_p), 1,
+                                   float(lo), float(hi - lo), e0.ctypes.data_as(m.abi.c_double_p), len(e0), 1,
+                                   rows.ctypes.data_as(m.abi.c_double_p)))
+    assert np.array_equal(rows.T, fm.X[:, :len(e0) - 1])
+    st = np.zeros(3)
+    nn = np.zeros(1, dtype=np.int64)
+    rk = np.array([0, slab.size // 2, slab.size - 1], dtype=np.int64)
+    m.check(m.lib().mcbb_order_stats(slab.ctypes.data_as(m.abi.c_double_p), slab.size, 3, rk.ctypes.data_as(m.abi.c_int64_p),
+                                     st.ctypes.data_as(m.abi.c_double_p), nn.ctypes.data_as(m.abi.c_int64_p)))
+    assert np.array_equal(st, np.sort(slab.ravel())[rk]) and nn[0] == 0

@@ -181,41 +181,40 @@ def main(args):
             solve_dev(icx, parx)
             torch.cuda.synchronize()
             t["h2d_solve_s"] = time.perf_counter() - t0
-            Xl = torch.cat([feat_d, mat_d, parx], dim=0)
+            # the measures stay on the device: all-gather -> sortperm by the parameter (sort!(sol, prob),
+            # setup_mc_prob.jl:520-536) -> normalize + histogram edges + Float32 ECDF rows (mcbb_order_stats_dev,
+            # mcbb_hist_rows_dev; bit-identical to the host mirror, tests/test_gpu_parity.py) -> fused DBSCAN.  The
+            # correlation ECDF has weight 0 in the notebook's distance and is not gathered.
+            Xl = torch.cat([feat_d, parx], dim=0)
             if dist is not None:
                 parts = [torch.empty_like(Xl) for _ in range(world)]
                 dist.all_gather(parts, Xl)
                 Xa = torch.cat(parts, dim=1)
             else:
                 Xa = Xl
-            Xa_h = Xa.cpu().numpy()  # [6*100 + 30 + 1, n]: the host stages of the reference work on the measures
+            torch.cuda.synchronize()
             t1 = time.perf_counter()
-            t["allgather_d2h_s"] = t1 - t0 - t["h2d_solve_s"]
-            n_all = Xa_h.shape[1]
-            order = np.argsort(Xa_h[-1], kind="stable")  # sort!(sol, prob), setup_mc_prob.jl:520-536
-            Xa_h = Xa_h[:, order]
-            feat = np.ascontiguousarray(Xa_h[:nm * nf].reshape(nm, nf, n_all).transpose(2, 1, 0))
-            sol = m.DEMCBBSol(np.asfortranarray(feat), np.asfortranarray(Xa_h[nm * nf:nm * nf + nb].T), None,
-                              np.zeros(n_all, dtype=np.int32), None, 400, None)
-            pr = cases.c4_problem(m, 4)[0]
-            pr.par = np.asfortranarray(Xa_h[-1:].T.copy())
-            pr.N_mc = n_all
+            t["allgather_s"] = t1 - t0 - t["h2d_solve_s"]
+            n_all = Xa.shape[1]
+            order = torch.sort(Xa[-1], stable=True).indices
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                sol_n = m.normalize(sol)  # setup_mc_prob.jl:635-660
-                fm = m.distance_matrix(sol_n, pr, WEIGHTS, histograms=True, k_bin=0.25, materialize=False)
+                X_d, gl, gw, _, _ = m.dist.histogram_features_device(Xa[:nm * nf], nm, nf, WEIGHTS[:nm] + WEIGHTS[-1:], Xa[-1:],
+                                                                     order, normalize=True, k_bin=0.25)
+            torch.cuda.synchronize()
             t2 = time.perf_counter()
-            t["host_normalize_hist_s"] = t2 - t1
-            X_d = torch.from_numpy(np.ascontiguousarray(fm.X.T)).to(dev)  # [F, n]
-            gl, gw = fm.group_len, fm.group_weight
+            t["sort_normalize_hist_s"] = t2 - t1
+            pr = cases.c4_problem(m, 4)[0]
+            pr.par = np.asfortranarray(Xa[-1][order].cpu().numpy().reshape(-1, 1))
+            pr.N_mc = n_all
             if world > 1:
                 a_, s_, c_ = m.dist.dbscan_features_sharded(X_d, gl, gw, DB_EPS, DB_MINPTS, rank, world, dist)
             else:
                 a_, s_, c_ = m.dist.dbscan_features_device(X_d, gl, gw, DB_EPS, DB_MINPTS)
             labels = a_.cpu().numpy()
             torch.cuda.synchronize()
-            t["h2d_dbscan_labels_s"] = time.perf_counter() - t2
+            t["dbscan_labels_s"] = time.perf_counter() - t2
             res = m.api.DbscanResult(s_.cpu().numpy(), labels, c_.cpu().numpy())
             cm = m.cluster_membership(pr, res, 0.025, 0.01, min_members=50)  # notebook cell 7
             barrier()
@@ -227,7 +226,7 @@ def main(args):
         t, X_d, gl, gw, a_, s_, c_, cm = pipeline()
         pf = C.c_int64(0)
         m.check(m.lib().mcbb_pair_feature_counter(0, C.byref(pf), stream_ptr()))
-        keys = ("h2d_solve_s", "allgather_d2h_s", "host_normalize_hist_s", "h2d_dbscan_labels_s", "pipeline_s")
+        keys = ("h2d_solve_s", "allgather_s", "sort_normalize_hist_s", "dbscan_labels_s", "pipeline_s")
         tt = torch.tensor([t[k] for k in keys] + [float(pf.value)], dtype=torch.float64, device=dev)
         tsum = tt.clone()
         if dist is not None:
@@ -235,11 +234,12 @@ def main(args):
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         pipe = {k: float(v) for k, v in zip(keys, tt.tolist())}
         pipe["n_runs"] = int(X_d.shape[1])
-        pipe["what"] = ("wall clock, max over ranks: pinned H2D -> integrate+featurize (all measures) -> all-gather + D2H of "
-                        "the measures -> host: sort, normalize, common histogram edges (k_bin 0.25), Float32 ECDF rows "
-                        "-> H2D -> fused (row-sharded) DBSCAN(0.008, 10) -> labels D2H -> cluster_membership")
+        pipe["what"] = ("wall clock, max over ranks: pinned H2D -> integrate+featurize (all measures) -> NCCL all-gather of "
+                        "the measures -> on the device: sortperm by eps, normalize, common histogram edges (k_bin 0.25; "
+                        "quartiles by a device sort), Float32 ECDF rows -> fused (row-sharded) DBSCAN(0.008, 10) -> labels "
+                        "D2H -> cluster_membership")
         n_all, Ftot = int(X_d.shape[1]), int(X_d.shape[0])
-        t_cl = pipe["h2d_dbscan_labels_s"]
+        t_cl = pipe["dbscan_labels_s"]
         executed = float(tsum[5].item())
         cluster = {"n_runs": n_all, "time_s": t_cl, "eps": DB_EPS, "minpts": DB_MINPTS, "n_clusters": int(s_.numel()),
                    "n_noise": int((a_ == 0).sum().item()), "n_features": Ftot,
