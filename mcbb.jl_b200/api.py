@@ -930,6 +930,25 @@ def _compute_hist_weights(meas, edges, use_ecdf=True):
     return H
 
 
+_HIST_ROWS_ON_DEVICE = 1 << 18  # values of one measure from which the rows are built by the library (mcbb_hist_rows)
+
+
+def _hist_rows(meas, edges, use_ecdf=True):
+    """_compute_hist_weights for one measure [N_mc, N_dim]: on the device (mcbb_hist_rows, bit-identical) for anything
+    but toy sizes, where the H2D / D2H round trip costs more than the few numpy passes."""
+    meas = np.asarray(meas, dtype=np.float64)
+    if meas.size < _HIST_ROWS_ON_DEVICE:
+        return _compute_hist_weights(meas, edges, use_ecdf)
+    n_mc, n_dim = meas.shape
+    slab = np.asfortranarray(meas)  # [n_dim][n_mc] in memory
+    e = np.ascontiguousarray(edges, dtype=np.float64)
+    rows = np.empty((n_mc, len(e) - 1), dtype=np.float64, order="F")
+    check(lib().mcbb_hist_rows(slab.ctypes.data_as(abi.c_double_p), n_mc, n_dim, None, 0, 0.0, 1.0,
+                               e.ctypes.data_as(abi.c_double_p), len(e), 1 if use_ecdf else 0,
+                               rows.ctypes.data_as(abi.c_double_p)))
+    return rows.astype(np.float32)
+
+
 class DistanceMatrixHist:
     """DistanceMatrixHist (eval_clustering.jl:62-73)."""
 
@@ -1031,7 +1050,7 @@ def _assemble_features(sol, prob, weights, relative_parameter, histograms, use_e
                 warnings.simplefilter("always")
                 edges, bw = _compute_hist_edges(data, sol.N_dim, k_bin, nbin_default, nbin,
                                                 None if bin_edges is None else bin_edges[mi])
-            return edges, bw, _compute_hist_weights(data, edges, use_ecdf), [str(w.message) for w in rec]
+            return edges, bw, _hist_rows(data, edges, use_ecdf), [str(w.message) for w in rec]
         # the measures are independent and numpy releases the GIL inside its loops: one host thread per measure
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=min(8, max(1, sol.N_meas_dim))) as pool:

@@ -235,6 +235,22 @@ function feature_groups(sol::MCBB.myMCSol, prob::MCBB.myMCProblem, weights::Abst
     hcat(cols...), glen, Vector{Float64}(weights)
 end
 
+"""
+    hist_rows_b200(k, sol, edges; ecdf=true)
+
+`_compute_hist_weights(k, sol, edges, ecdf)` (src/eval_clustering.jl:587-598, 759-762) on the device (`mcbb_hist_rows`):
+N_mc x (length(edges) - 1) matrix of the per-run Float32 histograms / ECDFs of measure `k` over the equidistant `edges`.
+"""
+function hist_rows_b200(k::Int, sol, edges; ecdf::Bool=true)
+    vals = Matrix{Float64}(MCBB.get_measure(sol, k))   # N_mc x N_dim, column-major = the [n_dim][n_mc] slab of the C-ABI
+    e = collect(Float64, edges)
+    rows = Matrix{Float64}(undef, size(vals, 1), length(e) - 1)
+    check(ccall((:mcbb_hist_rows, LIB), Cint,
+                (Ptr{Float64}, Int64, Int32, Ptr{Int64}, Int32, Float64, Float64, Ptr{Float64}, Int32, Int32, Ptr{Float64}),
+                vals, size(vals, 1), size(vals, 2), C_NULL, 0, 0.0, 1.0, e, length(e), ecdf ? 1 : 0, rows))
+    rows
+end
+
 function distance_matrix_b200(sol, prob, weights; relative_parameter::Bool=false, histograms::Bool=false,
                               k_bin::Number=1, nbin_default::Int=50)
     X, glen, gw = feature_groups(sol, prob, weights; relative_parameter=relative_parameter)
@@ -242,7 +258,7 @@ function distance_matrix_b200(sol, prob, weights; relative_parameter::Bool=false
         cols = Matrix{Float64}[]; glen = Int32[]; gw = Float64[]
         for k in 1:sol.N_meas_dim
             edges, bw = MCBB._compute_hist_edges(k, sol, k_bin; nbin_default=nbin_default)
-            push!(cols, Float64.(MCBB._compute_hist_weights(k, sol, edges, true)))
+            push!(cols, hist_rows_b200(k, sol, edges))
             push!(glen, length(edges) - 1); push!(gw, weights[k] * bw)
         end
         par = relative_parameter ? MCBB._relative_parameter(prob) : MCBB.parameter(prob)

@@ -28,9 +28,11 @@ def main():
         F = sum(gl)
         X = torch.randn((F, n), dtype=torch.float64, device=dev)
         glen, gwt = np.asarray(gl, dtype=np.int32), np.asarray(gw)
-        for kernel, hook in (("tma", 4), ("tma_8rows", 8), ("tiles", 0)):
-            m.lib().mcbb_test_hook_set(b"dist_tma", 1 if hook else 0)
-            m.lib().mcbb_test_hook_set(b"dist_tma_rpt", hook if hook else -2 ** 63)
+        variants = (("tma", {}), ("tma_128rows_1cta", {b"dist_tma_r": 128}), ("tma_128rows_512thr", {b"dist_tma_rpt": 4}),
+                    ("tiles", {b"dist_tma": 0}))
+        for kernel, hooks in variants:
+            for key in (b"dist_tma", b"dist_tma_r", b"dist_tma_rpt"):
+                m.lib().mcbb_test_hook_set(key, hooks.get(key, -2 ** 63))
             best = None
             for _ in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,8 +47,8 @@ def main():
             gbs = 8.0 * n * n / (best * 1e-3) / 1e9
             out["%s_%s" % (name, kernel)] = {"ms": best, "gbs_written": gbs, "frac_of_hbm_copy": gbs / 6551.7,
                                              "fp64_adds_per_s": n * (n - 1) / 2 * 2 * F / (best * 1e-3)}
-        m.lib().mcbb_test_hook_set(b"dist_tma", -2 ** 63)
-        m.lib().mcbb_test_hook_set(b"dist_tma_rpt", -2 ** 63)
+        for key in (b"dist_tma", b"dist_tma_r", b"dist_tma_rpt"):
+            m.lib().mcbb_test_hook_set(key, -2 ** 63)
     print(json.dumps(out))
 
 
