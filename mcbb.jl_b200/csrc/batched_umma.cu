@@ -118,9 +118,17 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_full), "n"(4 * NW));
     }
+    // tensor memory: one power-of-two allocation for the accumulators and the A operand — or, for five CTAs per SM with
+    // JB = 4, two (64 accumulator columns + 32 columns of A = 96: five CTAs fit the 512 columns, four of 128 would not)
+    constexpr bool SPLIT = (MINB == 5 && NCOL == 64);
     if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)),
-                     "n"(UmCols<JB>::value));
+        if (SPLIT) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(um_smem_u32(tmem_slot)));
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(um_smem_u32(tmem_slot + 1)));
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(tmem_slot)),
+                         "n"(UmCols<JB>::value));
+        }
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A image and zeros -> visible to the MMA's proxy
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
     const unsigned tmem_row = tmem_base + ((unsigned)(32 * wq) << 16);  // this warp's 32 TMEM lanes
-    const unsigned tmem_a = tmem_base + NCOL;                            // A operand: 32 columns behind the accumulators
+    const unsigned tmem_a = SPLIT ? tmem_slot[1] : tmem_base + NCOL;      // A operand: 32 columns behind the accumulators
     {  // row r of A -> lane r: 128 K bytes = 32 columns (the first warp of every quadrant writes it)
         unsigned w[32];
         if (wid < 4) {
@@ -141,7 +149,7 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
             w[4 * q + 2] = t4.z;
             w[4 * q + 3] = t4.w;
         }
-        um_tmem_st32(tmem_row + NCOL, w);
+        um_tmem_st32(tmem_a + ((unsigned)(32 * wq) << 16), w);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -574,8 +582,14 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
 #undef UM_TICK
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (wid == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
+    if (wid == 0) {
+        if (SPLIT) {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base));
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_a));
+        } else {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UmCols<JB>::value));
+        }
+    }
 }
 
 }  // namespace mcbb
@@ -676,6 +690,8 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     // configurations (trajectories per CTA, CTAs per SM): TMEM columns and shared memory both have to fit
     struct Cfg { int jb, per_sm, nw; };
     static const Cfg cfgs[] = {{6, 4, 1}, {4, 4, 1}, {6, 3, 1}, {8, 2, 1}, {4, 3, 1}, {4, 2, 1}, {2, 2, 1}, {2, 1, 1},
+                               // five CTAs of four trajectories (split tensor-memory allocation, 96 registers): on request
+                               {4, 5, 1},
                                // two threads per oscillator row (experiment switch "umma_nw" = 2)
                                {6, 3, 2}, {6, 4, 2}, {4, 4, 2}, {6, 2, 2}};
     int want_jb = (int)tune_get("umma_jb", 0);
@@ -747,6 +763,7 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     } else if (pick->jb == 6 && pick->per_sm == 4) rc = launch_umma_spec<6, 4>(a, smem, grid, st);
     else if (pick->jb == 6 && pick->per_sm == 3) rc = launch_umma_spec<6, 3>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 4) rc = launch_umma_spec<4, 4>(a, smem, grid, st);
+    else if (pick->jb == 4 && pick->per_sm == 5) rc = launch_umma_spec<4, 5>(a, smem, grid, st);
     else if (pick->jb == 8 && pick->per_sm == 2) rc = launch_umma_spec<8, 2>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 3) rc = launch_umma_spec<4, 3>(a, smem, grid, st);
     else if (pick->jb == 4 && pick->per_sm == 2) rc = launch_umma_spec<4, 2>(a, smem, grid, st);

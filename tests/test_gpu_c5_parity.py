@@ -208,3 +208,22 @@ def test_light_warp_variant_is_bitwise_equal(gpu, N):
     for f1, _, _, r1, n1 in out:
         assert np.array_equal(f0, f1, equal_nan=True) and np.array_equal(r0, r1) and np.array_equal(n0, n1)
     assert np.all(r0 == 0) and np.isfinite(f0).all()
+
+
+def test_five_ctas_of_four_trajectories_is_bitwise_equal(gpu):
+    """Experiment switch umma_jb = 4, umma_per_sm = 5 (two tensor-memory allocations per CTA, 64 + 32 columns, so that five
+    CTAs fit an SM; measured slower than six trajectories x four CTAs): results do not depend on how the
+    trajectories are batched, so measures and step counts are bitwise equal to the default configuration."""
+    m = gpu
+    prob, _ = cases.c5_problem(m, 900, N=100, seed=77, tspan=(0.0, 120.0))
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    f0, _, _, r0, n0 = m.custom_solve_b200(prob, ts)
+    m.lib().mcbb_test_hook_set(b"umma_jb", 4)
+    m.lib().mcbb_test_hook_set(b"umma_per_sm", 5)
+    try:
+        f1, _, _, r1, n1 = m.custom_solve_b200(prob, ts)
+    finally:
+        m.lib().mcbb_test_hook_set(b"umma_jb", -2 ** 63)
+        m.lib().mcbb_test_hook_set(b"umma_per_sm", -2 ** 63)
+    assert np.array_equal(f0, f1, equal_nan=True) and np.array_equal(r0, r1) and np.array_equal(n0, n1)
+    assert np.all(r0 == 0)
