@@ -1117,3 +1117,19 @@ def test_histogram_features_on_the_device_equal_the_host_path(gpu, k_bin, zero_w
     m.check(m.lib().mcbb_order_stats(slab.ctypes.data_as(m.abi.c_double_p), slab.size, 3, rk.ctypes.data_as(m.abi.c_int64_p),
                                      st.ctypes.data_as(m.abi.c_double_p), nn.ctypes.data_as(m.abi.c_int64_p)))
     assert np.array_equal(st, np.sort(slab.ravel())[rk]) and nn[0] == 0
+
+
+def test_host_mirror_builds_large_histogram_rows_on_the_device(gpu):
+    """api._hist_rows sends a measure of >= 2^18 values through mcbb_hist_rows (host buffers) and keeps numpy for toy
+    sizes: both give the same Float32 rows, with and without the ECDF."""
+    m = gpu
+    rng = np.random.default_rng(5)
+    meas = np.asfortranarray(rng.normal(0.0, 1.0, (4100, 70)))
+    assert meas.size >= m.api._HIST_ROWS_ON_DEVICE
+    edges, _ = m.api._compute_hist_edges(meas, 70, 0.5, 50)
+    for ecdf in (True, False):
+        before = m.kernel_launch_count()
+        rows = m.api._hist_rows(meas, edges, ecdf)
+        assert m.kernel_launch_count() - before == 1
+        ref = m.api._compute_hist_weights(meas, edges, ecdf)
+        assert rows.dtype == ref.dtype == np.float32 and np.array_equal(rows, ref, equal_nan=True)
