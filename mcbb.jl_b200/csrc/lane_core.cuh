@@ -62,13 +62,25 @@ MCBB_HD double julia_mod_pos(const double x, const double y) {
     return r;
 }
 
+// a * b + c with both roundings (Julia does not contract): the KL bin layout below is 1-ulp sensitive (the range length
+// flips between 2k and 2k + 1 bins), so every kernel family must take it through the SAME arithmetic — left to the
+// compiler, one inlined copy was contracted to an fma and another was not
+MCBB_HD double mul_add_2r(const double a, const double b, const double c) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(__dmul_rn(a, b), c);
+#else
+    volatile double p = a * b;
+    return p + c;
+#endif
+}
+
 // Julia Base (:)(start, step, stop) length, Float64 fallback path (twiceprecision.jl)
 MCBB_HD int julia_range_len(const double start, const double step, const double stop) {
     const double lf = (stop - start) / step;
     if (lf < 0) return 0;
     if (lf == 0) return 1;
     int len = (int)rint(lf) + 1;
-    const double stop2 = start + (len - 1) * step;
+    const double stop2 = mul_add_2r((double)(len - 1), step, start);
     if ((start < stop && stop < stop2) || (start > stop && stop > stop2)) len -= 1;
     return len;
 }
@@ -230,7 +242,7 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F,
                 const double mu = A(ACC_MEAN, ch), sig = A(ACC_M2, ch);
                 const double k = (nb - 1) / 2.;
                 const double bw = (F.kl_nstd * sig) / k;
-                const double start = mu - k * bw, stop = mu + k * bw;
+                const double start = mul_add_2r(-k, bw, mu), stop = mul_add_2r(k, bw, mu);
                 int nc = 0;
                 if (sig >= F.kl_tol) nc = julia_range_len(start, bw, stop);
                 if (nc > nb) nc = nb;
@@ -296,7 +308,7 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F,
                     if (nc > 0) {
                         const double start = A(ACC_START, ch), bw = A(ACC_BW, ch);
                         const double hb = bw / 2.;
-                        const double last_edge = ((nb - 1) / 2.) * bw + hb;  // `mu` missing: eval_mc_prob.jl:328
+                        const double last_edge = mul_add_2r((nb - 1) / 2., bw, hb);  // `mu` missing: eval_mc_prob.jl:328
                         int lo = 0, hi = nc + 2;
                         while (lo < hi - 1) {
                             const int m = (lo + hi) >> 1;

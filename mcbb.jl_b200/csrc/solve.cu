@@ -314,6 +314,8 @@ int launch_batched_imma(const mcbb_system_desc* hs, const SysDev& S, const Solve
                         const SolveIO& io, cudaStream_t st, bool* handled);
 int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
                            const SolveIO& io, cudaStream_t st, bool* handled);
+int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F, const SolveIO& io,
+                 cudaStream_t st, bool* handled);
 int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o, const FeatDev& F,
                             const SolveIO& io, cudaStream_t st, bool* handled);
 
@@ -342,6 +344,8 @@ int solve_features_launch(const mcbb_system_desc* hs, const SysDev& S, const Sol
         if (int rc = launch_batched_imma(hs, S, o, F, io, st, &handled)) return rc;
         if (handled) return 0;
         if (int rc = launch_batched_kuramoto(hs, S, o, F, io, st, &handled)) return rc;
+        if (handled) return 0;
+        if (int rc = launch_group(hs, S, o, F, io, st, &handled)) return rc;  // small networks: a lane group per trajectory
         if (handled) return 0;
     }
     switch (S.system) {

@@ -155,7 +155,7 @@ static __device__ __noinline__ double um_kl_hist(const double* smp, const long l
     const double NaN = nan("");
     const double kq = (nb - 1) / 2.;
     const double bw = (nstd * sig) / kq;
-    const double start = mu - kq * bw, stop = mu + kq * bw;
+    const double start = mul_add_2r(-kq, bw, mu), stop = mul_add_2r(kq, bw, mu);
     int nc = 0;
     if (sig >= tol) nc = julia_range_len(start, bw, stop);
     if (nc > nb) nc = nb;
@@ -168,7 +168,7 @@ static __device__ __noinline__ double um_kl_hist(const double* smp, const long l
         for (int b = 0; b < nc; b++) hist[b] = 0;
     }
     const double hb = bw / 2.;
-    const double last_edge = kq * bw + hb;  // `mu` missing: eval_mc_prob.jl:328
+    const double last_edge = mul_add_2r(kq, bw, hb);  // `mu` missing: eval_mc_prob.jl:328
     const double e1 = start - hb, ibw = 1. / bw;
     auto edge = [&](const int m) { return fma((double)(m - 1), bw, start) - hb; };  // edges 1..nc (ascending)
     // fit(Histogram, u, edges; closed=:left) = searchsortedlast on the vector [edge(1..nc), last_edge].  Its bisection

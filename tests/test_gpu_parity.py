@@ -1133,3 +1133,62 @@ def test_host_mirror_builds_large_histogram_rows_on_the_device(gpu):
         assert m.kernel_launch_count() - before == 1
         ref = m.api._compute_hist_weights(meas, edges, ecdf)
         assert rows.dtype == ref.dtype == np.float32 and np.array_equal(rows, ref, equal_nan=True)
+
+
+def _solve_both_ways(m, prob, ts, **kw):
+    """(group kernel, lane kernel) results of custom_solve_b200 on the same problem."""
+    a = m.custom_solve_b200(prob, ts, **kw)
+    m.lib().mcbb_test_hook_set(b"no_group", 1)
+    try:
+        b = m.custom_solve_b200(prob, ts, **kw)
+    finally:
+        m.lib().mcbb_test_hook_set(b"no_group", -2 ** 63)
+    return a, b
+
+
+@pytest.mark.parametrize("case", ["c1_default", "c1_cyclic_filter", "net12_weighted", "net20_sparse", "c3", "grid7_filter_kl",
+                                  "c1_maxiters"])
+def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
+    """csrc/group.cu (a group of 8 / 16 / 32 lanes per trajectory, one oscillator per lane) takes the sums over the state
+    in the lane kernel's order, so its measures, return codes and step counts are bitwise those of the lane kernel — for
+    kuramoto_network (C1 and larger, weighted / sparse couplings) and second_order_kuramoto (C3 and a small grid), with
+    KL-hist, cyclic_setback, a state_filter and a MaxIters failure."""
+    m = gpu
+    kw = {}
+    if case.startswith("c1"):
+        prob, _ = cases.c1_problem(m, n_ics=60, seed=3, cyclic=(case == "c1_cyclic_filter"))
+        if case == "c1_cyclic_filter":
+            prob.eval_ode_func = m.EvalOdeRun(state_filter=[2, 5, 6], eval_funcs=(m.mean, m.std), cyclic_setback=True)
+        if case == "c1_maxiters":
+            kw = dict(maxiters=5)
+    elif case.startswith("net"):
+        N = 12 if case == "net12_weighted" else 20
+        rng = np.random.default_rng(N)
+        A = cases.erdos_renyi(N, 0.4, N + 1)
+        if case == "net12_weighted":
+            A = A * rng.uniform(0.5, 1.5, (N, N))
+        pars = m.kuramoto_network_parameters(0.5, rng.normal(0.5, 0.2, N), N, A)
+        rp = m.ODEProblem(m.kuramoto_network, np.zeros(N), (0.0, 50.0), pars)
+        ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist), cyclic_setback=True)
+        kr = np.random.default_rng(N + 2)
+        prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 150, pars, ("K", lambda: kr.uniform(0.0, 6.0)), ev, 0.7)
+    elif case == "c3":
+        prob, _ = cases.c3_problem(m, n_mc=300, tspan=(0.0, 120.0))
+    else:
+        N = 7
+        rng = np.random.default_rng(70)
+        E = cases.ring_incidence(N, [(0, 3), (2, 5)])
+        pars = m.second_order_kuramoto_parameters(N, 0.2, 1.0, E, rng.normal(0.0, 0.5, N))
+        rp = m.ODEProblem(m.second_order_kuramoto, np.zeros(2 * N), (0.0, 80.0), pars)
+        ev = m.EvalOdeRun(state_filter=[1, 3, 8, 9, 14], eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist))
+        lam = np.random.default_rng(71)
+        prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 200, pars, ("coupling", lambda: lam.uniform(0.05, 3.0)),
+                               ev, 0.6)
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    (f0, _, _, r0, n0), (f1, _, _, r1, n1) = _solve_both_ways(m, prob, ts, **kw)
+    assert np.array_equal(r0, r1) and np.array_equal(n0, n1)
+    assert np.array_equal(f0, f1, equal_nan=True), [float(np.nanmax(np.abs(f0[..., q] - f1[..., q]))) for q in range(f0.shape[2])]
+    if case == "c1_maxiters":
+        assert np.all(r0 == m.abi.RET_MAXITERS) and np.isnan(f0).all()
+    else:
+        assert np.all(r0 == 0) and np.isfinite(f0[..., :2]).all()
