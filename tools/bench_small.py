@@ -132,11 +132,13 @@ def main(args):
     achieved = fl / (ms_total * 1e-3) / 1e12
     roofline = {"bound": "fp64_fma" if cfg != "C2" else "latency", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
-                "kernel": "k_solve_lane (one trajectory per lane, state in shared memory)",
+                "kernel": ("k_solve_lane (one trajectory per lane, state in shared memory)" if cfg == "C2" else
+                           "k_solve_group (a group of 8 / 16 lanes per trajectory, one oscillator per lane, stage vectors in "
+                           "registers; bitwise equal to the lane kernel)"),
                 "note": "algorithmic FP64 flops per step attempt (tools/bench_small.py::flops_per_step) x the kernel's step "
-                        "count / CUDA-event time.  These ensembles are far too small to fill the machine for long: C1 is "
-                        "2500 lanes (17 per SM) for 40 time units, C2 is 10^4 x 1000 three-flop iterations — launch and "
-                        "tail latency, not a pipe, bound them"}
+                        "count / CUDA-event time.  C1 and C2 are far too small to fill the machine for long: C1 is 2500 "
+                        "trajectories for 40 time units (31 step attempts each), C2 is 10^4 x 1000 three-flop iterations — "
+                        "launch and tail latency, not a pipe, bound them"}
 
     # ---- the pipeline once as wall clock (through the host mirror, like a user of the reference would) -----------
     import warnings
