@@ -65,15 +65,23 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     constexpr int NC = (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) ? 2 : 1;
     extern __shared__ __align__(16) unsigned char gr_smem[];
     double* s_ts = reinterpret_cast<double*>(gr_smem);                    // [n_t]
-    double* s_mat = s_ts + ((a.io.n_t + 1) & ~1);                         // kuramoto: [N][N]
+    double* s_mat = s_ts + ((a.io.n_t + 1) & ~1);                         // kuramoto: [N][N]; second order: incident-edge tables
+    double* s_nv = s_mat;                                                 // [GR_DEGMAX][G] incidence values
+    int* s_ne = reinterpret_cast<int*>(s_nv + GR_DEGMAX * G);             // [GR_DEGMAX][G] incident edges, ascending
     const int tid = threadIdx.x;
     const int gl = tid & (G - 1);                                         // lane within the group = oscillator / edge index
     const int N = a.N, n_t = a.io.n_t;
     const long long n_mc = a.io.n_mc;
     const SolverDev& o = a.o;
     for (int i = tid; i < n_t; i += GR_THREADS) s_ts[i] = a.io.t_save[i];
-    if (SYS == MCBB_SYS_KURAMOTO_NETWORK)
+    if (SYS == MCBB_SYS_KURAMOTO_NETWORK) {
         for (int i = tid; i < N * N; i += GR_THREADS) s_mat[i] = a.mat[i];
+    } else {
+        for (int i = tid; i < GR_DEGMAX * G; i += GR_THREADS) {
+            s_nv[i] = a.node_val[i];
+            s_ne[i] = a.node_edge[i];
+        }
+    }
     __syncthreads();
     const bool own = gl < N;                       // this lane owns an oscillator
     const int gi = own ? gl : 0;                   // safe index for the table reads of idle lanes
@@ -81,19 +89,12 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     // second order: the two ends of this lane's edge, the incident edges of this lane's node
     int en0 = 0, en1 = 0, deg = 0;
     double ev0 = 0., ev1 = 0.;
-    int ne[GR_DEGMAX];
-    double nv[GR_DEGMAX];
     if (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
         en0 = a.edge_node[gl];
         en1 = a.edge_node[G + gl];
         ev0 = a.edge_val[gl];
         ev1 = a.edge_val[G + gl];
         deg = a.node_deg[gl];
-#pragma unroll
-        for (int q = 0; q < GR_DEGMAX; q++) {
-            ne[q] = a.node_edge[q * G + gl];
-            nv[q] = a.node_val[q * G + gl];
-        }
     }
     int fpos[NC];
 #pragma unroll
@@ -161,8 +162,8 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
 #pragma unroll
             for (int q = 0; q < GR_DEGMAX; q++) {
                 if (q < a.degmax) {  // uniform
-                    const double f = gr_shfl<G>(sv, ne[q]);
-                    if (q < deg) acc += nv[q] * f;
+                    const double f = gr_shfl<G>(sv, s_ne[q * G + gl]);
+                    if (q < deg) acc += s_nv[q * G + gl] * f;
                 }
             }
             const double om = y[1];
@@ -363,18 +364,23 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
         for (int c = 0; c < NC; c++) nan_lane |= own && (tmp[c] != tmp[c]);
         const unsigned nan_ballot = __ballot_sync(0xffffffffu, nan_lane);
         const bool nan_group = ((nan_ballot >> (tid & 31 & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0u;
+        // the two powers of the PI controller, EEst^beta1 and qold^beta2, in ONE call: even lanes take the first, odd
+        // lanes the second, a shuffle hands both to every lane (same inputs, same function: the same bits as two calls)
+        const double EEst = sqrt(e2 / a.n_dim);
+        const bool odd = (gl & 1) != 0;
+        const double pw = pow(odd ? qold : EEst, odd ? o.beta2 : o.beta1);
+        const double pw_e = gr_shfl<G>(pw, 0), pw_q = gr_shfl<G>(pw, 1);
         if (mode == MODE_INIT) {
             mode = MODE_RUN;
             if (!begin_attempt()) end_run();
         } else if (mode == MODE_RUN) {
             natt++;
-            const double EEst = sqrt(e2 / a.n_dim);
             double q, q11 = 0.;
             if (EEst == 0.) {
                 q = 1. / o.qmax;
             } else {
-                q11 = pow(EEst, o.beta1);
-                q = q11 / pow(qold, o.beta2);
+                q11 = pw_e;
+                q = q11 / pw_q;
                 q = fmax(1. / o.qmax, fmin(1. / o.qmin, q / o.gamma));
             }
             const bool accept = !(EEst > 1.);
@@ -517,7 +523,7 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     a.kl_nstd = F.kl_nstd;
     a.kl_tol = F.kl_tol;
     a.io = io;
-    const size_t smem = sizeof(double) * (((size_t)io.n_t + 1) / 2 * 2 + (second ? 0 : (size_t)N * N));
+    const size_t smem = sizeof(double) * (((size_t)io.n_t + 1) / 2 * 2 + (second ? (size_t)GR_DEGMAX * G * 2 : (size_t)N * N));
     if (smem > 200 * 1024) return 0;
     int dev = 0, sms = 148;
     MCBB_CUDA_OK(cudaGetDevice(&dev));
