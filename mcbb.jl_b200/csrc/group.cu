@@ -36,8 +36,8 @@ struct GroupArgs {
     int N, E, n_dim;              // oscillators, edges (second order), state dimensions
     const double* mat;            // kuramoto_network: A [N][N] column-major (device)
     const double* vec_a;          // [N] natural frequencies / drive
-    const int* edge_node;         // [2][G] ends of edge e (second order); -1 = no entry
-    const double* edge_val;       // [2][G]
+    const int* edge_node;         // [2][EPL * G] ends of edge e (second order); -1 = no entry
+    const double* edge_val;       // [2][EPL * G]
     const int* node_deg;          // [G]
     const int* node_edge;         // [GR_DEGMAX][G] incident edges of node i, ascending
     const double* node_val;       // [GR_DEGMAX][G]
@@ -60,7 +60,9 @@ __device__ __forceinline__ double gr_shfl(const double v, const int src) {
 }
 
 // SYS: MCBB_SYS_KURAMOTO_NETWORK (one component per lane) or MCBB_SYS_SECOND_ORDER_KURAMOTO (theta_i, omega_i per lane)
-template <int SYS, int G>
+// EPL: edges per lane (second order): 2 lets a 32-lane group carry up to 64 edges — the paper's N = 30, 3-regular power
+// grid has 45 (paper/kuramoto/1-simulate.jl:22-26); lane l evaluates the sines of edges l and l + G
+template <int SYS, int G, int EPL = 1>
 __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     constexpr int NC = (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) ? 2 : 1;
     extern __shared__ __align__(16) unsigned char gr_smem[];
@@ -87,13 +89,21 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     const int gi = own ? gl : 0;                   // safe index for the table reads of idle lanes
     const double w_i = a.vec_a[gi];
     // second order: the two ends of this lane's edge, the incident edges of this lane's node
-    int en0 = 0, en1 = 0, deg = 0;
-    double ev0 = 0., ev1 = 0.;
+    int en0[EPL], en1[EPL], deg = 0;
+    double ev0[EPL], ev1[EPL];
+#pragma unroll
+    for (int p = 0; p < EPL; p++) {
+        en0[p] = en1[p] = 0;
+        ev0[p] = ev1[p] = 0.;
+    }
     if (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
-        en0 = a.edge_node[gl];
-        en1 = a.edge_node[G + gl];
-        ev0 = a.edge_val[gl];
-        ev1 = a.edge_val[G + gl];
+#pragma unroll
+        for (int p = 0; p < EPL; p++) {  // tables are [2][EPL * G]
+            en0[p] = a.edge_node[p * G + gl];
+            en1[p] = a.edge_node[EPL * G + p * G + gl];
+            ev0[p] = a.edge_val[p * G + gl];
+            ev1[p] = a.edge_val[EPL * G + p * G + gl];
+        }
         deg = a.node_deg[gl];
     }
     int fpos[NC];
@@ -150,19 +160,26 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
             out[0] = fma(KN, c * as - s * ac, w_i);
         } else {
             // lane e: sin of (incidence' theta)_e; entries in ascending node order, as the compressed table lists them
-            double arg = 0.;
-            {
-                const double t0 = gr_shfl<G>(y[0], en0 < 0 ? 0 : en0);
-                const double t1 = gr_shfl<G>(y[0], en1 < 0 ? 0 : en1);
-                if (en0 >= 0) arg += ev0 * t0;
-                if (en1 >= 0) arg += ev1 * t1;
+            double sv[EPL];
+#pragma unroll
+            for (int p = 0; p < EPL; p++) {
+                double arg = 0.;
+                const double t0 = gr_shfl<G>(y[0], en0[p] < 0 ? 0 : en0[p]);
+                const double t1 = gr_shfl<G>(y[0], en1[p] < 0 ? 0 : en1[p]);
+                if (en0[p] >= 0) arg += ev0[p] * t0;
+                if (en1[p] >= 0) arg += ev1[p] * t1;
+                sv[p] = sin(arg);
             }
-            const double sv = sin(arg);
             double acc = 0.;
 #pragma unroll
             for (int q = 0; q < GR_DEGMAX; q++) {
                 if (q < a.degmax) {  // uniform
-                    const double f = gr_shfl<G>(sv, s_ne[q * G + gl]);
+                    const int e = s_ne[q * G + gl];  // edge index: lane e mod G, slot e / G
+                    double f = gr_shfl<G>(sv[0], e & (G - 1));
+                    if (EPL == 2) {
+                        const double f1 = gr_shfl<G>(sv[EPL - 1], e & (G - 1));
+                        f = (e >= G) ? f1 : f;
+                    }
                     if (q < deg) acc += s_nv[q * G + gl] * f;
                 }
             }
@@ -425,10 +442,10 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     }
 }
 
-template <int SYS, int G>
+template <int SYS, int G, int EPL = 1>
 static int launch_group_one(const GroupArgs& a, size_t smem, int grid, cudaStream_t st) {
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_group<SYS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_group<SYS, G><<<grid, GR_THREADS, smem, st>>>(a);
+    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_group<SYS, G, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_group<SYS, G, EPL><<<grid, GR_THREADS, smem, st>>>(a);
     MCBB_LAUNCHED();
     return 0;
 }
@@ -446,8 +463,9 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
         if (F.meas[m] != MCBB_MEAS_MEAN && F.meas[m] != MCBB_MEAS_STD && F.meas[m] != MCBB_MEAS_KL_HIST) return 0;
     const bool second = S.system == MCBB_SYS_SECOND_ORDER_KURAMOTO;
     const int E = second ? S.n_edges : 0;
-    const int width = std::max(N, E);
-    if (N < 2 || width > 32) return 0;
+    if (N < 2 || N > 32 || E > 64) return 0;
+    const int EPL = E > 32 ? 2 : 1;  // edges per lane
+    const int width = std::max(N, EPL == 2 ? 32 : E);
     const int G = width <= 8 ? 8 : (width <= 16 ? 16 : 32);
 
     GroupArgs a = {};
@@ -456,8 +474,9 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     a.n_dim = S.n_dim;
     a.mat = S.mat_a;
     a.vec_a = S.vec_a;
-    std::vector<int> edge_node(2 * G, -1), node_deg(G, 0), node_edge(GR_DEGMAX * G, 0), fpos(2 * G, -1);
-    std::vector<double> edge_val(2 * G, 0.), node_val(GR_DEGMAX * G, 0.);
+    const int EW = EPL * G;  // edge slots
+    std::vector<int> edge_node(2 * EW, -1), node_deg(G, 0), node_edge(GR_DEGMAX * G, 0), fpos(2 * G, -1);
+    std::vector<double> edge_val(2 * EW, 0.), node_val(GR_DEGMAX * G, 0.);
     int degmax = 0;
     if (second) {
         for (int e = 0; e < E; e++) {
@@ -466,8 +485,8 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
                 const double w = hs->mat_a[i + (size_t)N * e];
                 if (w == 0.) continue;
                 if (cnt == 2 || node_deg[i] == GR_DEGMAX) return 0;  // not an edge / a hub: the lane kernel takes it
-                edge_node[cnt * G + e] = i;
-                edge_val[cnt * G + e] = w;
+                edge_node[cnt * EW + e] = i;
+                edge_val[cnt * EW + e] = w;
                 cnt++;
                 node_edge[node_deg[i] * G + i] = e;
                 node_val[node_deg[i] * G + i] = w;
@@ -490,8 +509,8 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
             fpos[(d / N) * G + (d % N)] = ii;
         }
     }
-    int* d_int = (int*)scratch_get(103, sizeof(int) * (size_t)(2 * G + G + GR_DEGMAX * G + 2 * G));
-    double* d_dbl = (double*)scratch_get(104, sizeof(double) * (size_t)(2 * G + GR_DEGMAX * G));
+    int* d_int = (int*)scratch_get(103, sizeof(int) * (size_t)(2 * EW + G + GR_DEGMAX * G + 2 * G));
+    double* d_dbl = (double*)scratch_get(104, sizeof(double) * (size_t)(2 * EW + GR_DEGMAX * G));
     if (!d_int || !d_dbl) MCBB_FAIL("solve: device allocation failed");
     std::vector<int> hi;
     hi.insert(hi.end(), edge_node.begin(), edge_node.end());
@@ -505,11 +524,11 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     MCBB_CUDA_OK(cudaMemcpyAsync(d_dbl, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));  // the staging vectors are stack-owned
     a.edge_node = d_int;
-    a.node_deg = d_int + 2 * G;
-    a.node_edge = d_int + 3 * G;
-    a.fpos = d_int + 3 * G + GR_DEGMAX * G;
+    a.node_deg = d_int + 2 * EW;
+    a.node_edge = d_int + 2 * EW + G;
+    a.fpos = d_int + 2 * EW + G + GR_DEGMAX * G;
     a.edge_val = d_dbl;
-    a.node_val = d_dbl + 2 * G;
+    a.node_val = d_dbl + 2 * EW;
     for (int q = 0; q < MCBB_N_SCALARS; q++) a.scalars[q] = S.scalars[q];
     a.n_par = S.n_par;
     for (int p = 0; p < MCBB_MAX_PAR; p++) a.par_slot[p] = S.par_slot[p];
@@ -539,7 +558,9 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     }
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     int rc;
-    if (second)
+    if (second && EPL == 2)
+        rc = launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32, 2>(a, smem, grid, st);
+    else if (second)
         rc = G == 8 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 8>(a, smem, grid, st)
                     : (G == 16 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 16>(a, smem, grid, st)
                                : launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32>(a, smem, grid, st));

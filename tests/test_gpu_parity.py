@@ -1147,12 +1147,12 @@ def _solve_both_ways(m, prob, ts, **kw):
 
 
 @pytest.mark.parametrize("case", ["c1_default", "c1_cyclic_filter", "net12_weighted", "net20_sparse", "c3", "grid7_filter_kl",
-                                  "c1_maxiters"])
+                                  "c1_maxiters", "grid30_paper"])
 def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
     """csrc/group.cu (a group of 8 / 16 / 32 lanes per trajectory, one oscillator per lane) takes the sums over the state
     in the lane kernel's order, so its measures, return codes and step counts are bitwise those of the lane kernel — for
     kuramoto_network (C1 and larger, weighted / sparse couplings) and second_order_kuramoto (C3 and a small grid), with
-    KL-hist, cyclic_setback, a state_filter and a MaxIters failure."""
+    KL-hist, cyclic_setback, a state_filter, a MaxIters failure and the paper's 30-node grid (45 edges: two per lane)."""
     m = gpu
     kw = {}
     if case.startswith("c1"):
@@ -1174,6 +1174,9 @@ def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
         prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 150, pars, ("K", lambda: kr.uniform(0.0, 6.0)), ev, 0.7)
     elif case == "c3":
         prob, _ = cases.c3_problem(m, n_mc=300, tspan=(0.0, 120.0))
+    elif case == "grid30_paper":  # the paper's size: N = 30, 3-regular, 45 edges -> two edges per lane of a 32-lane group
+        prob, _ = cases.c3_problem(m, n_mc=160, N=30, seed=9, tspan=(0.0, 60.0))
+        assert prob.pars.pack(prob.par_names).desc.n_edges == 45
     else:
         N = 7
         rng = np.random.default_rng(70)
