@@ -17,6 +17,7 @@
 //
 //   kuramoto_network (systems.jl:119-130):  du_i = w_i + K/N (cos u_i (A sin u)_i - sin u_i (A cos u)_i), lane i holds
 //       row i of A in shared memory and gathers sin u_j, cos u_j for j = 0 .. N-1 in order.
+//   kuramoto (mean field, systems.jl:85-94): the same with the two plain sums over all oscillators.
 //   second_order_kuramoto (systems.jl:198-202):  lane e < N_edges evaluates sin((E' theta)_e) from the two ends of edge e;
 //       lane i < N owns (theta_i, omega_i) and adds its incident flows in ascending edge order.
 // Features: mean / std (Welford, per lane), cyclic_setback, state_filter, KL-hist from the saved samples of the run in a
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     for (int i = tid; i < n_t; i += GR_THREADS) s_ts[i] = a.io.t_save[i];
     if (SYS == MCBB_SYS_KURAMOTO_NETWORK) {
         for (int i = tid; i < N * N; i += GR_THREADS) s_mat[i] = a.mat[i];
-    } else {
+    } else if (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) {
         for (int i = tid; i < GR_DEGMAX * G; i += GR_THREADS) {
             s_nv[i] = a.node_val[i];
             s_ne[i] = a.node_edge[i];
@@ -144,7 +145,17 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
 
     // right-hand side of the whole group: y (this lane's components) -> out.  All lanes of the warp execute it together.
     auto rhs = [&](const double (&y)[NC], double (&out)[NC]) {
-        if constexpr (SYS == MCBB_SYS_KURAMOTO_NETWORK) {
+        if constexpr (SYS == MCBB_SYS_KURAMOTO) {  // mean field, systems.jl:85-94: the two sums in index order
+            double s, c;
+            sincos(y[0], &s, &c);
+            double sum_s = 0., sum_c = 0.;
+            for (int j = 0; j < N; j++) {
+                sum_s += gr_shfl<G>(s, j);
+                sum_c += gr_shfl<G>(c, j);
+            }
+            const double KN = sc[0] / (double)N;
+            out[0] = fma(KN, c * sum_s - s * sum_c, w_i);
+        } else if constexpr (SYS == MCBB_SYS_KURAMOTO_NETWORK) {
             double s, c;
             sincos(y[0], &s, &c);
             double as = 0., ac = 0.;
@@ -456,7 +467,8 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     *handled = false;
     const int N = S.n_osc;
     if (hs == nullptr || tune_get("no_group", 0)) return 0;
-    if (S.system != MCBB_SYS_KURAMOTO_NETWORK && S.system != MCBB_SYS_SECOND_ORDER_KURAMOTO) return 0;
+    if (S.system != MCBB_SYS_KURAMOTO_NETWORK && S.system != MCBB_SYS_SECOND_ORDER_KURAMOTO && S.system != MCBB_SYS_KURAMOTO)
+        return 0;
     if (o.alg != MCBB_ALG_TSIT5 || F.n_global > 0 || F.n_comp != 1 || F.matrix_meas != MCBB_MAT_NONE) return 0;
     if (F.need_kl && (F.kl_bins > UM_MAX_KL_BINS || F.kl_bins < 3)) return 0;
     for (int m = 0; m < F.n_meas; m++)
@@ -506,6 +518,7 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
         for (int ii = 0; ii < F.n_filter; ii++) {
             const int d = F.filter ? fh[ii] - 1 : ii;  // state dimension: theta_0..theta_{N-1}, then omega_0..
             if (d < 0 || d >= S.n_dim) return 0;
+            if (fpos[(d / N) * G + (d % N)] >= 0) return 0;  // a dimension listed twice: the lane kernel reports it twice
             fpos[(d / N) * G + (d % N)] = ii;
         }
     }
@@ -542,7 +555,8 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     a.kl_nstd = F.kl_nstd;
     a.kl_tol = F.kl_tol;
     a.io = io;
-    const size_t smem = sizeof(double) * (((size_t)io.n_t + 1) / 2 * 2 + (second ? (size_t)GR_DEGMAX * G * 2 : (size_t)N * N));
+    const bool net = S.system == MCBB_SYS_KURAMOTO_NETWORK;
+    const size_t smem = sizeof(double) * (((size_t)io.n_t + 1) / 2 * 2 + (second ? (size_t)GR_DEGMAX * G * 2 : (net ? (size_t)N * N : 0)));
     if (smem > 200 * 1024) return 0;
     int dev = 0, sms = 148;
     MCBB_CUDA_OK(cudaGetDevice(&dev));
@@ -564,6 +578,10 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
         rc = G == 8 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 8>(a, smem, grid, st)
                     : (G == 16 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 16>(a, smem, grid, st)
                                : launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32>(a, smem, grid, st));
+    else if (!net)
+        rc = G == 8 ? launch_group_one<MCBB_SYS_KURAMOTO, 8>(a, smem, grid, st)
+                    : (G == 16 ? launch_group_one<MCBB_SYS_KURAMOTO, 16>(a, smem, grid, st)
+                               : launch_group_one<MCBB_SYS_KURAMOTO, 32>(a, smem, grid, st));
     else
         rc = G == 8 ? launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 8>(a, smem, grid, st)
                     : (G == 16 ? launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 16>(a, smem, grid, st)

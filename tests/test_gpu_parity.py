@@ -1147,7 +1147,7 @@ def _solve_both_ways(m, prob, ts, **kw):
 
 
 @pytest.mark.parametrize("case", ["c1_default", "c1_cyclic_filter", "net12_weighted", "net20_sparse", "c3", "grid7_filter_kl",
-                                  "c1_maxiters", "grid30_paper"])
+                                  "c1_maxiters", "grid30_paper", "meanfield9"])
 def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
     """csrc/group.cu (a group of 8 / 16 / 32 lanes per trajectory, one oscillator per lane) takes the sums over the state
     in the lane kernel's order, so its measures, return codes and step counts are bitwise those of the lane kernel — for
@@ -1172,6 +1172,14 @@ def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
         ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist), cyclic_setback=True)
         kr = np.random.default_rng(N + 2)
         prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 150, pars, ("K", lambda: kr.uniform(0.0, 6.0)), ev, 0.7)
+    elif case == "meanfield9":  # all-to-all kuramoto (systems.jl:85-94)
+        N = 9
+        rng = np.random.default_rng(90)
+        pars = m.kuramoto_parameters(0.5, rng.normal(0.5, 0.3, N), N)
+        rp = m.ODEProblem(m.kuramoto, np.zeros(N), (0.0, 60.0), pars)
+        ev = m.EvalOdeRun(eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist), cyclic_setback=True)
+        kr = np.random.default_rng(91)
+        prob = m.DEMCBBProblem(rp, lambda: rng.uniform(-np.pi, np.pi), 140, pars, ("K", lambda: kr.uniform(0.0, 4.0)), ev, 0.7)
     elif case == "c3":
         prob, _ = cases.c3_problem(m, n_mc=300, tspan=(0.0, 120.0))
     elif case == "grid30_paper":  # the paper's size: N = 30, 3-regular, 45 edges -> two edges per lane of a 32-lane group
