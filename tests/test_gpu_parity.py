@@ -1147,7 +1147,7 @@ def _solve_both_ways(m, prob, ts, **kw):
 
 
 @pytest.mark.parametrize("case", ["c1_default", "c1_cyclic_filter", "net12_weighted", "net20_sparse", "c3", "grid7_filter_kl",
-                                  "c1_maxiters", "grid30_paper", "meanfield9"])
+                                  "c1_maxiters", "grid30_paper", "meanfield9", "c1_dt_dtmax_tight"])
 def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
     """csrc/group.cu (a group of 8 / 16 / 32 lanes per trajectory, one oscillator per lane) takes the sums over the state
     in the lane kernel's order, so its measures, return codes and step counts are bitwise those of the lane kernel — for
@@ -1161,6 +1161,8 @@ def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
             prob.eval_ode_func = m.EvalOdeRun(state_filter=[2, 5, 6], eval_funcs=(m.mean, m.std), cyclic_setback=True)
         if case == "c1_maxiters":
             kw = dict(maxiters=5)
+        if case == "c1_dt_dtmax_tight":  # user dt (no initdt probe), a dtmax that clips, tight tolerances (rejections)
+            kw = dict(dt=0.05, dtmax=0.4, reltol=1e-8, abstol=1e-8)
     elif case.startswith("net"):
         N = 12 if case == "net12_weighted" else 20
         rng = np.random.default_rng(N)
