@@ -1205,3 +1205,31 @@ def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
         assert np.all(r0 == m.abi.RET_MAXITERS) and np.isnan(f0).all()
     else:
         assert np.all(r0 == 0) and np.isfinite(f0[..., :2]).all()
+
+
+def test_order_stats_counts_nans_and_the_device_assembly_rejects_them(gpu):
+    """mcbb_order_stats ranks the finite values in ascending order (negative zero, infinities and subnormals included)
+    and reports how many NaNs the measure holds; histogram_features_device refuses a measure with NaNs (the reference's
+    quantile would be NaN and its edge range meaningless) with a MCBBError, like every other argument error."""
+    import torch
+    m = gpu
+    rng = np.random.default_rng(12)
+    v = rng.normal(size=5000)
+    v[:7] = [np.inf, -np.inf, 0.0, -0.0, 5e-324, -5e-324, 1e308]
+    v[100:103] = np.nan
+    rk = np.array([0, 1, 2500, 4995, 4996], dtype=np.int64)
+    out = np.zeros(len(rk))
+    nn = np.zeros(1, dtype=np.int64)
+    m.check(m.lib().mcbb_order_stats(v.ctypes.data_as(m.abi.c_double_p), v.size, len(rk), rk.ctypes.data_as(m.abi.c_int64_p),
+                                     out.ctypes.data_as(m.abi.c_double_p), nn.ctypes.data_as(m.abi.c_int64_p)))
+    ref = np.sort(v[~np.isnan(v)])
+    assert nn[0] == 3 and np.array_equal(out, ref[rk])
+    dev = torch.device("cuda:0")
+    feat = torch.from_numpy(v[:4000].reshape(8, 500).copy()).to(dev)
+    par = torch.from_numpy(rng.uniform(size=(1, 500))).to(dev)
+    with pytest.raises(m.MCBBError, match="NaN"):
+        m.dist.histogram_features_device(feat, 1, 8, [1.0, 1.0], par)
+    with pytest.raises(m.MCBBError, match="rank out of range"):
+        bad = np.array([5000], dtype=np.int64)
+        m.check(m.lib().mcbb_order_stats(v.ctypes.data_as(m.abi.c_double_p), v.size, 1, bad.ctypes.data_as(m.abi.c_int64_p),
+                                         out.ctypes.data_as(m.abi.c_double_p), nn.ctypes.data_as(m.abi.c_int64_p)))
