@@ -467,6 +467,28 @@ MCBB_HD void lane_main(const SysDev& S, const SolverDev& o_in, const FeatDev& F,
                 start_pass();
             }
         }
+        // Maps (FunctionMap): iterations of the transient produce no sample and cannot fail except by a non-finite
+        // state or maxiters — they run in a tight loop here instead of one full round each (C2: 800 of 1000 iterations).
+        // Exactly the generic sequence (rhs -> count the attempt -> commit -> begin the next attempt); an iteration
+        // that would produce a sample, reach the end of the span or a NaN is left to the round below, untouched.
+        if (alg == MCBB_ALG_FUNCTIONMAP) {
+            while (mode == MODE_RUN && ret == 0) {
+                const double tnew = t + 1.;
+                if (!(tnew < o.t1)) break;
+                if (isave < n_t && tsave[isave] <= tnew) break;
+                rhs_lane<SYS>(S, L.tabs, sc, &X(SLOT_U, 0), &X(SLOT_TMP, 0), &X(SLOT_SCR, 0), bs);
+                bool bad = false;
+                for (int d = 0; d < n; d++) bad |= (X(SLOT_TMP, d) != X(SLOT_TMP, d));
+                if (bad) break;
+                natt += (pass == 0);
+                t = tnew;
+                for (int d = 0; d < n; d++) X(SLOT_U, d) = X(SLOT_TMP, d);
+                if (!begin_attempt()) {
+                    end_pass();
+                    break;
+                }
+            }
+        }
         if (wq.all_done(mode == MODE_DONE)) break;
 
         // ---- one round of R right-hand-side evaluations, stage-aligned across the warp -----------------
