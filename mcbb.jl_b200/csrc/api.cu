@@ -52,6 +52,11 @@ ApiGuard::ApiGuard(cudaStream_t st) : dev_(current_device_slot()) {
 }
 ApiGuard::~ApiGuard() { g_dev[dev_].mu.unlock(); }
 
+size_t scratch_size(int slot) {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    return g_scratch[current_device_slot()][slot].cap;
+}
+
 void* scratch_get(int slot, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     if (bytes == 0) bytes = 16;

@@ -68,7 +68,10 @@ struct SlArgs {
     int need_kl, kl_bins;
     double kl_nstd, kl_tol;
     int matrix_meas, corr_nbins;
-    double* smp;                  // [grid][JB][n_t][2N] saved samples of the runs in flight (KL / correlation)
+    double* smp;                  // [runs of the chunk][n_t][2N] saved samples (KL / correlation: reduced by k_sl_post)
+    double* stat;                 // [runs of the chunk][N][4] mean / M2 of Re and Im as the run finished
+    int* okflag;                  // [runs of the chunk] run succeeded and delivered all samples
+    long long run_begin, run_end; // the runs this launch integrates (one chunk of the ensemble when samples are kept)
     double fx_scale, fx_inv, fx_max;  // 2^50 / R, R / 2^50, largest representable magnitude
     unsigned int* ovf;            // number of runs that accepted a clamped stage
     const SlFin* fin;             // device copy of the finish parameters
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
             }
             if (c.mode == MODE_FETCH) {
                 const long long run = (long long)atomicAdd(a.io.work_counter, 1ULL);
-                if (run >= n_mc) {
+                if (run >= a.run_end) {
                     c.mode = MODE_DONE;
                 } else {
                     double sc[MCBB_N_SCALARS];
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                         }
                         const double x = fma(dts, lx, kx[0]), y = fma(dts, ly, ky[0]);
                         if (SMP && valid)
-                            *reinterpret_cast<double2*>(a.smp + (((size_t)blockIdx.x * JB + j) * n_t + k) * (2 * N) + 2 * row) =
+                            // (a run that finished with this step has already handed its slot to the next run: fin_run)
+                            *reinterpret_cast<double2*>(a.smp + (((size_t)((c.fin ? c.fin_run : c.run) - a.run_begin)) * n_t + k) * (2 * N) + 2 * row) =
                                 make_double2(x, y);
                         const double rk = um_div(1., (double)k);
                         const double dx = x - amx[j], dy = y - amy[j];
@@ -526,10 +530,19 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
                 KX(1, j) = kx[7];  // FSAL
                 KY(1, j) = ky[7];
             }
-            if (c.fin)  // uniform over the CTA; out of line: it runs once per trajectory, the loop around it once per step
-                sl_finish_run<SMP>(a.fin, SMP ? a.smp + ((size_t)blockIdx.x * JB + j) * n_t * (2 * N) : nullptr, c.fin_ok != 0,
-                                   c.fin_run, valid ? fpos : -1, amx[j], a2x[j], amy[j], a2y[j], smem, PANEL + XST, sm_mx, sm_my,
-                                   sm_var, sm_hist);
+            if (c.fin) {  // uniform over the CTA
+                if (SMP) {
+                    // the KL histograms and the correlation need the whole series: the moments go to a scratch and
+                    // k_sl_post reduces the saved samples of every run of the chunk afterwards, one CTA per run — inside
+                    // this kernel the reduction stalled the three other trajectories of the CTA for its whole length
+                    const size_t rl = (size_t)(c.fin_run - a.run_begin);
+                    if (valid) *reinterpret_cast<double4*>(a.stat + (rl * N + row) * 4) = make_double4(amx[j], a2x[j], amy[j], a2y[j]);
+                    if (tid == 0) a.okflag[rl] = c.fin_ok;
+                } else {
+                    sl_finish_run<false>(a.fin, nullptr, c.fin_ok != 0, c.fin_run, valid ? fpos : -1, amx[j], a2x[j], amy[j], a2y[j],
+                                         smem, PANEL + XST, sm_mx, sm_my, sm_var, sm_hist);
+                }
+            }
             if (c.fresh) {
                 if (valid) {
                     KX(0, j) = a.io.ic[(long long)(2 * row) * n_mc + c.run];
@@ -793,6 +806,26 @@ __global__ void __launch_bounds__(128, MINB) k_solve_batched_umma_sl(const SlArg
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
 }
 
+// KL histograms and the correlation ECDF / histogram of the runs of one chunk from their saved samples: one CTA per run,
+// thread r = oscillator r — the reduction sl_finish_run<true> does, with the whole machine instead of one stalled CTA.
+__global__ void __launch_bounds__(128) k_sl_post(const SlFin* __restrict__ fin, double* smp, const double* __restrict__ stat,
+                                                 const int* __restrict__ okflag, const int* __restrict__ filter_pos,
+                                                 const long long run_begin, const int scratch_bytes) {
+    extern __shared__ __align__(16) unsigned char post_smem[];
+    unsigned char* scratch = post_smem;
+    double* sm_mx = reinterpret_cast<double*>(post_smem + scratch_bytes);
+    double* sm_my = sm_mx + 128;
+    double* sm_var = sm_my + 128;
+    int* sm_hist = reinterpret_cast<int*>(sm_var + 128);
+    const int tid = threadIdx.x, N = fin->N, n_t = fin->n_t;
+    const size_t rl = blockIdx.x;
+    const bool valid = tid < N;
+    double4 st = make_double4(0., 0., 0., 0.);
+    if (valid) st = *reinterpret_cast<const double4*>(stat + (rl * N + tid) * 4);
+    sl_finish_run<true>(fin, smp + rl * (size_t)n_t * (2 * N), okflag[rl] != 0, run_begin + (long long)rl, valid ? filter_pos[tid] : -1,
+                        st.x, st.y, st.z, st.w, scratch, scratch_bytes, sm_mx, sm_my, sm_var, sm_hist);
+}
+
 static size_t sl_smem_bytes(int JB, int N, bool a1d) {
     return (size_t)JB * (a1d ? 3072 : 2048) + sizeof(double) * ((size_t)(N + 1) * (2 * UM_NSLOT * JB + 2) + 8 * (size_t)JB + 3 * 128) +
            sizeof(SlSlotCtl) * (size_t)JB + 24 + sizeof(int) * (4 * (size_t)JB + 64) + 128;
@@ -929,17 +962,15 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     a.corr_nbins = F.corr_nbins;
 
     // 2 trajectories x 5 CTAs per SM (20 warps, 96 registers) beats 4 x 3 (12 warps) by 6 % for mean / std and 3 % with the
-    // KL-hist measures — the kernel is latency-bound per warp, so more resident warps pay — but loses 5 % when the
-    // correlation runs (profiles/r2_sl_jb_variants.jsonl): the first entry is skipped for a matrix measure
-    // (2 x 6 at 80 registers: 132 k against 134 k for 2 x 5 — the gain from more warps ends there)
-    struct Cfg { int jb, per_sm; bool not_with_matrix; };
-    static const Cfg cfgs[] = {{2, 5, true}, {4, 3, false}, {4, 2, false}, {2, 2, false}, {2, 1, false}};
+    // KL-hist measures — the kernel is latency-bound per warp, so more resident warps pay (profiles/r2_sl_jb_variants.jsonl;
+    // 2 x 6 at 80 registers: 132 k against 134 k for 2 x 5 — the gain from more warps ends there)
+    struct Cfg { int jb, per_sm; };
+    static const Cfg cfgs[] = {{2, 5}, {4, 3}, {4, 2}, {2, 2}, {2, 1}};
     const int want_jb = (int)tune_get("umma_sl_jb", 0), want_per = (int)tune_get("umma_sl_per_sm", 0);
     const Cfg* pick = nullptr;
     for (const Cfg& c : cfgs) {
         if (want_jb && c.jb != want_jb) continue;
         if (want_per && c.per_sm != want_per) continue;
-        if (c.not_with_matrix && F.matrix_meas != MCBB_MAT_NONE && !(want_jb && want_per)) continue;
         const size_t need = sl_smem_bytes(c.jb, N, a1d);
         if ((need + 1024) * c.per_sm <= (size_t)227 * 1024 && need <= (size_t)226 * 1024) {
             pick = &c;
@@ -952,14 +983,7 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     MCBB_CUDA_OK(cudaGetDevice(&dev));
     MCBB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     a.n_sms = sms;
-    const long long want = (io.n_mc + pick->jb - 1) / pick->jb;
-    const int grid = (int)std::min<long long>(want, (long long)sms * pick->per_sm);
     const bool smp = F.need_kl || F.matrix_meas != MCBB_MAT_NONE;
-    a.smp = nullptr;
-    if (smp) {
-        a.smp = (double*)scratch_get(39, sizeof(double) * (size_t)grid * pick->jb * (size_t)io.n_t * (size_t)(2 * N));
-        if (!a.smp) MCBB_FAIL("solve: device allocation failed");
-    }
     SlFin hf = {};
     hf.N = N;
     hf.n_t = io.n_t;
@@ -982,15 +1006,48 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     MCBB_CUDA_OK(cudaMemcpyAsync(d_fin, &hf, sizeof(SlFin), cudaMemcpyHostToDevice, st));
     MCBB_CUDA_OK(cudaStreamSynchronize(st));  // hf is stack-owned
     a.fin = d_fin;
-    MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
     MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
-    int rc = 1;
-    if (pick->jb == 4 && pick->per_sm == 3) rc = launch_sl_one<4, 3>(a, smem, grid, smp, a1d, st);
-    else if (pick->jb == 4 && pick->per_sm == 2) rc = launch_sl_one<4, 2>(a, smem, grid, smp, a1d, st);
-    else if (pick->jb == 2 && pick->per_sm == 2) rc = launch_sl_one<2, 2>(a, smem, grid, smp, a1d, st);
-    else if (pick->jb == 2 && pick->per_sm == 1) rc = launch_sl_one<2, 1>(a, smem, grid, smp, a1d, st);
-    else if (pick->jb == 2 && pick->per_sm == 5) rc = launch_sl_one<2, 5>(a, smem, grid, smp, a1d, st);
-    if (rc) return rc;
+
+    // Measures that need the whole series (KL-hist, correlation): the ensemble is integrated in chunks whose saved samples
+    // fit a scratch (test hook "sl_post_mb"), each chunk followed by k_sl_post.  Other measure sets: one launch.
+    const size_t run_bytes = sizeof(double) * (size_t)io.n_t * (size_t)(2 * N);
+    long long chunk = io.n_mc;
+    if (smp) {
+        // at most 64 GB and at most half of what is free on the device right now (the scratch is kept for the next call)
+        size_t free_b = 0, total_b = 0;
+        MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        size_t cap = std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(39));
+        if (const long long mb = tune_get("sl_post_mb", 0)) cap = (size_t)mb << 20;
+        chunk = std::max<long long>(1, std::min<long long>(io.n_mc, (long long)(cap / run_bytes)));
+        a.smp = (double*)scratch_get(39, run_bytes * (size_t)chunk);
+        a.stat = (double*)scratch_get(106, sizeof(double) * 4 * (size_t)N * (size_t)chunk);
+        a.okflag = (int*)scratch_get(107, sizeof(int) * (size_t)chunk);
+        if (!a.smp || !a.stat || !a.okflag) MCBB_FAIL("solve: device allocation failed");
+    }
+    const int post_scratch = smp ? (F.need_kl ? F.kl_bins * 256 : 0) : 0;
+    const size_t post_smem = (size_t)post_scratch + sizeof(double) * 3 * 128 + sizeof(int) * 64;
+    for (long long r0 = 0; r0 < io.n_mc; r0 += chunk) {
+        const long long r1 = std::min<long long>(io.n_mc, r0 + chunk);
+        a.run_begin = r0;
+        a.run_end = r1;
+        const unsigned long long c0 = (unsigned long long)r0;
+        MCBB_CUDA_OK(cudaMemcpyAsync(io.work_counter, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));  // c0 is stack-owned
+        const long long want = (r1 - r0 + pick->jb - 1) / pick->jb;
+        const int grid = (int)std::min<long long>(want, (long long)sms * pick->per_sm);
+        int rc = 1;
+        if (pick->jb == 4 && pick->per_sm == 3) rc = launch_sl_one<4, 3>(a, smem, grid, smp, a1d, st);
+        else if (pick->jb == 4 && pick->per_sm == 2) rc = launch_sl_one<4, 2>(a, smem, grid, smp, a1d, st);
+        else if (pick->jb == 2 && pick->per_sm == 2) rc = launch_sl_one<2, 2>(a, smem, grid, smp, a1d, st);
+        else if (pick->jb == 2 && pick->per_sm == 1) rc = launch_sl_one<2, 1>(a, smem, grid, smp, a1d, st);
+        else if (pick->jb == 2 && pick->per_sm == 5) rc = launch_sl_one<2, 5>(a, smem, grid, smp, a1d, st);
+        if (rc) return rc;
+        if (smp) {
+            MCBB_CUDA_OK(cudaFuncSetAttribute(k_sl_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem));
+            k_sl_post<<<(unsigned)(r1 - r0), 128, post_smem, st>>>(d_fin, a.smp, a.stat, a.okflag, d_fpos, r0, post_scratch);
+            MCBB_LAUNCHED();
+        }
+    }
     // a run that left the fixed-point range invalidates this launch: the caller falls through to the lane kernels
     unsigned int h_ovf = 0;
     MCBB_CUDA_OK(cudaMemcpyAsync(&h_ovf, d_ovf, sizeof(h_ovf), cudaMemcpyDeviceToHost, st));

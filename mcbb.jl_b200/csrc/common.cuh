@@ -99,6 +99,7 @@ SolverDev resolve_solver(const mcbb_solver_opts* o);
 
 // host-side cache of device scratch buffers (freed by mcbb_finalize)
 void* scratch_get(int slot, size_t bytes);
+size_t scratch_size(int slot);  // bytes currently cached for the slot on this device
 void scratch_free_all();
 
 // test / experiment switches: set only through mcbb_test_hook_set (never from the environment), 0 / default in production

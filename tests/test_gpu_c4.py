@@ -10,6 +10,14 @@ from tests import cases
 pytestmark = pytest.mark.gpu
 
 
+def _launches(prob):
+    """One launch of k_solve_batched_umma_sl; measure sets that need the whole series (KL-hist, correlation) add one
+    launch of k_sl_post, which reduces the saved samples of all runs afterwards (one CTA per run)."""
+    ev = prob.eval_ode_func
+    series = any("kl" in str(getattr(f, "__name__", f)).lower() for f in ev.eval_funcs) or bool(ev.matrix_eval_funcs)
+    return 2 if series else 1
+
+
 def _ref(m, orc, prob, ic0, par0, **kw):
     psys, pfeat = prob.pars.pack(prob.par_names), prob.eval_ode_func.pack()
     o = m.abi.solver_opts(m.abi.ALG_TSIT5, prob.p.tspan, **kw)
@@ -38,7 +46,7 @@ def test_c4_tensor_core_kernel_converged_every_run(gpu, orc):
     kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10 ** 7)
     before = m.kernel_launch_count()
     sol = m.solve(prob, **kw)
-    assert m.kernel_launch_count() - before == 1, "expected one launch of k_solve_batched_umma_sl"
+    assert m.kernel_launch_count() - before == _launches(prob) == 2, "expected k_solve_batched_umma_sl + k_sl_post"
     ref, ctx = _ref(m, orc, prob, ic0, par0, **kw)
     assert np.array_equal(sol.retcode, ref["retcode"]) and np.all(sol.retcode == 0)
     stats = cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.9)
@@ -111,7 +119,7 @@ def test_sl_tensor_core_kernel_ring_sizes(gpu, orc, N, filt, corr):
     kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10 ** 7)
     before = m.kernel_launch_count()
     sol = m.solve(prob, **kw)
-    assert m.kernel_launch_count() - before == 1
+    assert m.kernel_launch_count() - before == _launches(prob)
     ref, ctx = _ref(m, orc, prob, ic0, par0, **kw)
     assert np.array_equal(sol.retcode, ref["retcode"])
     assert sol.feat.shape[1] == (N if filt is None else len(filt))
@@ -136,7 +144,7 @@ def test_sl_sparse_and_dense_attractive_coupling(gpu, orc, P1, forced):
     try:
         before = m.kernel_launch_count()
         sol = m.solve(prob, **kw)
-        assert m.kernel_launch_count() - before == 1
+        assert m.kernel_launch_count() - before == _launches(prob)
     finally:
         m.lib().mcbb_test_hook_set(b"umma_sl_a1d", -2 ** 63)
     ref, ctx = _ref(m, orc, prob, ic0, par0, **kw)
@@ -161,7 +169,7 @@ def test_c4_full_size_properties(gpu):
     ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
     before = m.kernel_launch_count()
     feat, _, _, ret, ns = m.custom_solve_b200(prob, ts)
-    assert m.kernel_launch_count() - before == 1
+    assert m.kernel_launch_count() - before == _launches(prob)
     assert np.all(ret == 0) and np.isfinite(feat[:, :, [0, 1, 3, 4]]).all()
     assert np.abs(feat[:, :, [0, 3]]).max() < 2.0 and feat[:, :, [1, 4]].max() < 2.0
     assert np.array_equal(feat[src], feat[dst], equal_nan=True) and np.array_equal(ns[src], ns[dst])
@@ -170,3 +178,27 @@ def test_c4_full_size_properties(gpu):
     sub.ic, sub.par, sub.N_mc = np.asfortranarray(prob.ic[pick]), np.asfortranarray(prob.par[pick]), len(pick)
     f2, _, _, r2, n2 = m.custom_solve_b200(sub, ts)
     assert np.array_equal(f2, feat[pick], equal_nan=True) and np.array_equal(n2, ns[pick]) and np.all(r2 == 0)
+
+
+def test_series_measures_are_reduced_chunk_by_chunk(gpu):
+    """KL-hist and the correlation need every saved sample of a run: the ensemble is integrated in chunks whose samples fit
+    a device scratch, each followed by k_sl_post (one CTA per run).  A scratch of 20 MB (31 runs per chunk) must give bitwise
+    the results of a single chunk — measures, matrix measure, return codes, step counts — and so must a chunk size that
+    does not divide the ensemble."""
+    m = gpu
+    prob, _ = cases.c4_problem(m, 150, tspan=(0.0, 40.0))
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    before = m.kernel_launch_count()
+    f0, m0, _, r0, n0 = m.custom_solve_b200(prob, ts)
+    assert m.kernel_launch_count() - before == 2
+    for mb, launches in ((20, 10), (64, 4)):  # 31 runs per chunk -> 5 chunks; 100 per chunk -> 2
+        m.lib().mcbb_test_hook_set(b"sl_post_mb", mb)
+        try:
+            before = m.kernel_launch_count()
+            f1, m1, _, r1, n1 = m.custom_solve_b200(prob, ts)
+            assert m.kernel_launch_count() - before == launches
+        finally:
+            m.lib().mcbb_test_hook_set(b"sl_post_mb", -2 ** 63)
+        assert np.array_equal(f0, f1, equal_nan=True) and np.array_equal(m0, m1, equal_nan=True)
+        assert np.array_equal(r0, r1) and np.array_equal(n0, n1)
+    assert np.all(r0 == 0) and np.isfinite(m0).all()
