@@ -48,11 +48,16 @@ struct UmmaArgs {
     int n_meas, meas[MCBB_MAX_MEAS], n_filter, cyclic;
     SolveIO io;
     unsigned long long* timing;  // [8] phase clocks (TIMING builds only)
-    // empirical_1D_KL_divergence_hist (eval_mc_prob.jl:312-330): the saved samples of the runs in flight are kept in
-    // a global scratch [slot][n_t][N] and binned once mean and std are final
+    // empirical_1D_KL_divergence_hist (eval_mc_prob.jl:312-330): the saved samples of the runs of a chunk are kept in
+    // a global scratch [run][n_t][N], mean / std / success of every run in `stat` / `okflag`, and binned after the solve by
+    // k_umma_kl_post (one thread per run and oscillator) — inside the integrator the binning of a finished run stalled
+    // the five other trajectories of its CTA
     int need_kl, kl_bins;
     double kl_nstd, kl_tol;
     double* smp;
+    double* stat;                // [runs of the chunk][N][2] mean, std
+    int* okflag;                 // [runs of the chunk]
+    long long run_begin, run_end;  // KL instantiation: the runs of this launch
     int lw_mode;                 // light-warp kernel only (batched_umma_lw.cuh)
 };
 
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
             }
             if (c.mode == MODE_FETCH) {
                 const long long run = (long long)atomicAdd(a.io.work_counter, 1ULL);
-                if (run >= n_mc) {
+                if (run >= (KL ? a.run_end : n_mc)) {
                     c.mode = MODE_DONE;
                 } else {
                     double sc[MCBB_N_SCALARS];
@@ -333,7 +338,8 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
                                 x = x - as[jj];
                             }
                         }
-                        if (KL && valid) a.smp[(((size_t)blockIdx.x * JB + j) * n_t + k) * N + row] = x;
+                        // (a run that finished with this step has already handed its slot to the next run: fin_run)
+                        if (KL && valid) a.smp[(((size_t)((c.fin ? c.fin_run : c.run) - a.run_begin)) * n_t + k) * N + row] = x;
                         const double delta = x - am[jj];
                         if (fabs(delta) <= 1.7976931348623157e308) {
                             const double mnew = fma(delta, um_div(1., (double)k), am[jj]);
@@ -354,15 +360,14 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
                 const bool ok = c.fin_ok != 0;
                 const double mean = ok ? am[jj] : nan("");
                 const double sd = ok ? sqrt((a2[jj] < 0. ? 0. : a2[jj]) / (double)(n_t - 2)) : nan("");
-                double kl = nan("");
-                if (KL && ok)
-                    kl = um_kl_hist(a.smp + ((size_t)blockIdx.x * JB + j) * n_t * N + row, N, n_t, mean, sd, a.kl_bins, a.kl_nstd,
-                                    a.kl_tol,
-                                    // the digit panel is dead between two rounds: lend it as histogram scratch
-                                    (JB * 2048 >= a.kl_bins * 256) ? reinterpret_cast<unsigned short*>(sB) + tid : nullptr);
+                if (KL) {
+                    const size_t rl = (size_t)(c.fin_run - a.run_begin);
+                    *reinterpret_cast<double2*>(a.stat + (rl * N + row) * 2) = make_double2(mean, sd);
+                    if (row == 0) a.okflag[rl] = ok ? 1 : 0;
+                }
                 for (int m = 0; m < a.n_meas; m++)
-                    a.io.feat[((long long)m * a.n_filter + fpos) * n_mc + c.fin_run] =
-                        (a.meas[m] == MCBB_MEAS_MEAN) ? mean : (a.meas[m] == MCBB_MEAS_STD) ? sd : kl;
+                    if (!KL || a.meas[m] != MCBB_MEAS_KL_HIST)  // the KL measures are written by k_umma_kl_post
+                        a.io.feat[((long long)m * a.n_filter + fpos) * n_mc + c.fin_run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
             }
             if (c.fresh) {
                 if (valid) {
@@ -373,7 +378,6 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
                 am[jj] = a2[jj] = as[jj] = 0.;
             }
         }
-        if (KL && any_fin) __syncthreads();  // the digit panel served as histogram scratch: all done before it is rewritten
         if (all_done) break;
         UM_TICK(1)  // samples, update, results, refill
 
@@ -596,6 +600,23 @@ __global__ void __launch_bounds__(128 * NW, MINB) k_solve_batched_umma(const Umm
 #include "batched_umma_lw.cuh"
 namespace mcbb {
 
+// KL-hist measures of the runs of one chunk from their saved samples: one CTA per run, thread r = oscillator r
+__global__ void __launch_bounds__(128) k_umma_kl_post(const UmmaArgs a, const long long n_runs) {
+    extern __shared__ __align__(16) unsigned char klp_smem[];  // [kl_bins][128] histogram counters
+    const int tid = threadIdx.x, N = a.N, n_t = a.io.n_t;
+    const size_t rl = blockIdx.x;
+    if ((long long)rl >= n_runs || tid >= N) return;
+    const int fpos = a.filter_pos[tid];
+    if (fpos < 0) return;
+    const double2 ms = *reinterpret_cast<const double2*>(a.stat + (rl * N + tid) * 2);
+    double kl = nan("");
+    if (a.okflag[rl])
+        kl = um_kl_hist(a.smp + rl * (size_t)n_t * N + tid, N, n_t, ms.x, ms.y, a.kl_bins, a.kl_nstd, a.kl_tol,
+                        reinterpret_cast<unsigned short*>(klp_smem) + tid);
+    for (int m = 0; m < a.n_meas; m++)
+        if (a.meas[m] == MCBB_MEAS_KL_HIST) a.io.feat[((long long)m * a.n_filter + fpos) * a.io.n_mc + a.run_begin + (long long)rl] = kl;
+}
+
 template <int JB, int MINB, bool TIMING = false, bool KL = false, int NW = 1>
 static int launch_umma_one(const UmmaArgs& a, size_t smem, int grid, cudaStream_t st) {
     MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_batched_umma<JB, MINB, TIMING, KL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -721,12 +742,48 @@ int launch_batched_umma(const mcbb_system_desc* hs, const SysDev& S, const Solve
     a.kl_nstd = F.kl_nstd;
     a.kl_tol = F.kl_tol;
     a.smp = nullptr;
+    MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     if (a.need_kl) {
-        a.smp = (double*)scratch_get(39, sizeof(double) * (size_t)grid * pick->jb * (size_t)io.n_t * (size_t)N);
-        if (!a.smp) MCBB_FAIL("solve: device allocation failed");
+        // the ensemble in chunks whose saved samples fit the free device memory (<= 64 GB; test hook "umma_post_mb"), each
+        // followed by the binning kernel
+        const size_t run_bytes = sizeof(double) * (size_t)io.n_t * (size_t)N;
+        size_t free_b = 0, total_b = 0;
+        MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        size_t cap = std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(39));
+        if (const long long mb = tune_get("umma_post_mb", 0)) cap = (size_t)mb << 20;
+        const long long chunk = std::max<long long>(1, std::min<long long>(io.n_mc, (long long)(cap / run_bytes)));
+        a.smp = (double*)scratch_get(39, run_bytes * (size_t)chunk);
+        a.stat = (double*)scratch_get(106, sizeof(double) * 2 * (size_t)N * (size_t)chunk);
+        a.okflag = (int*)scratch_get(107, sizeof(int) * (size_t)chunk);
+        if (!a.smp || !a.stat || !a.okflag) MCBB_FAIL("solve: device allocation failed");
+        const size_t post_smem = (size_t)a.kl_bins * 256;
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_umma_kl_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem));
+        for (long long r0 = 0; r0 < io.n_mc; r0 += chunk) {
+            const long long r1 = std::min<long long>(io.n_mc, r0 + chunk);
+            a.run_begin = r0;
+            a.run_end = r1;
+            const unsigned long long c0 = (unsigned long long)r0;
+            MCBB_CUDA_OK(cudaMemcpyAsync(io.work_counter, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+            MCBB_CUDA_OK(cudaStreamSynchronize(st));  // c0 is stack-owned
+            const int g = (int)std::min<long long>((r1 - r0 + pick->jb - 1) / pick->jb, (long long)sms * pick->per_sm);
+            int rk = 1;
+            if (pick->jb == 6 && pick->per_sm == 4) rk = launch_umma_spec<6, 4>(a, smem, g, st);
+            else if (pick->jb == 6 && pick->per_sm == 3) rk = launch_umma_spec<6, 3>(a, smem, g, st);
+            else if (pick->jb == 4 && pick->per_sm == 4) rk = launch_umma_spec<4, 4>(a, smem, g, st);
+            else if (pick->jb == 4 && pick->per_sm == 5) rk = launch_umma_spec<4, 5>(a, smem, g, st);
+            else if (pick->jb == 8 && pick->per_sm == 2) rk = launch_umma_spec<8, 2>(a, smem, g, st);
+            else if (pick->jb == 4 && pick->per_sm == 3) rk = launch_umma_spec<4, 3>(a, smem, g, st);
+            else if (pick->jb == 4 && pick->per_sm == 2) rk = launch_umma_spec<4, 2>(a, smem, g, st);
+            else if (pick->jb == 2 && pick->per_sm == 2) rk = launch_umma_spec<2, 2>(a, smem, g, st);
+            else if (pick->jb == 2 && pick->per_sm == 1) rk = launch_umma_spec<2, 1>(a, smem, g, st);
+            if (rk) return rk;
+            k_umma_kl_post<<<(unsigned)(r1 - r0), 128, post_smem, st>>>(a, r1 - r0);
+            MCBB_LAUNCHED();
+        }
+        *handled = true;
+        return 0;
     }
     MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-    MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
     int rc = 1;
     if (tune_get("umma_timing", 0) && pick->jb == 4 && (pick->per_sm == 4 || pick->per_sm == 2)) {  // development aid
         a.timing = (unsigned long long*)scratch_get(63, 64);

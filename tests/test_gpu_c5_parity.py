@@ -227,3 +227,26 @@ def test_five_ctas_of_four_trajectories_is_bitwise_equal(gpu):
         m.lib().mcbb_test_hook_set(b"umma_per_sm", -2 ** 63)
     assert np.array_equal(f0, f1, equal_nan=True) and np.array_equal(r0, r1) and np.array_equal(n0, n1)
     assert np.all(r0 == 0)
+
+
+def test_kl_measures_are_binned_chunk_by_chunk(gpu):
+    """The KL-hist measure of the tensor-core integrator is evaluated after the solve by k_umma_kl_post from the saved
+    samples of a chunk of runs.  A 20 MB scratch (65 runs per chunk at N = 100, 400 save times) and a chunk size that does
+    not divide the ensemble give bitwise the results of one chunk."""
+    m = gpu
+    prob, _ = cases.c5_problem(m, 300, N=100, seed=81, tspan=(0.0, 100.0))
+    prob.eval_ode_func = m.EvalOdeRun(eval_funcs=(m.mean, m.std, m.empirical_1D_KL_divergence_hist), cyclic_setback=True)
+    ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
+    before = m.kernel_launch_count()
+    f0, _, _, r0, n0 = m.custom_solve_b200(prob, ts)
+    assert m.kernel_launch_count() - before == 2  # k_solve_batched_umma + k_umma_kl_post
+    for mb, launches in ((20, 10), (61, 4)):  # 65 runs per chunk -> 5 chunks; 199 per chunk -> 2
+        m.lib().mcbb_test_hook_set(b"umma_post_mb", mb)
+        try:
+            before = m.kernel_launch_count()
+            f1, _, _, r1, n1 = m.custom_solve_b200(prob, ts)
+            assert m.kernel_launch_count() - before == launches
+        finally:
+            m.lib().mcbb_test_hook_set(b"umma_post_mb", -2 ** 63)
+        assert np.array_equal(f0, f1, equal_nan=True) and np.array_equal(r0, r1) and np.array_equal(n0, n1)
+    assert np.all(r0 == 0) and np.isfinite(f0[..., 2]).mean() > 0.9
