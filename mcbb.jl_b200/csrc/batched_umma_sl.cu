@@ -826,6 +826,124 @@ __global__ void __launch_bounds__(128) k_sl_post(const SlFin* __restrict__ fin, 
                         st.x, st.y, st.z, st.w, scratch, scratch_bytes, sm_mx, sm_my, sm_var, sm_hist);
 }
 
+// The matrix measure of one run per CTA, tiled through shared memory: thread b owns the 4 x 4 tile number b of the upper
+// triangle of the N x N complex correlation for the WHOLE series (32 accumulators), the centred samples arrive in chunks
+// of SLC_K save times ([k][2N] doubles, centred while they are staged: no in-place pass over the scratch).  Same products
+// in the same order as sl_corr_hist — which re-read every sample row from L2 once per tile (11.6 MB per run at N = 100) and
+// ran at 13 % of the DFMA peak.
+constexpr int SLC_K = 32;
+// MAXT: threads per CTA >= tiles of the upper triangle (351 at N <= 104, 528 at N = 128)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) k_sl_corr_post(const SlFin* __restrict__ fin, const double* __restrict__ smp,
+                                                             const double* __restrict__ stat, const int* __restrict__ okflag,
+                                                             const long long run_begin) {
+    extern __shared__ __align__(16) unsigned char slc_smem[];
+    const int tid = threadIdx.x, nth = blockDim.x, N = fin->N, n_t = fin->n_t, nb = fin->corr_nbins, n2 = 2 * N;
+    // one complex sample = one 16-byte chunk; the chunk of oscillator i sits at i ^ ((i >> 3) & 7) of its row, so that the
+    // lanes of a warp, which read the four consecutive columns of consecutive tiles (64-byte stride), spread over all banks
+    const int rs = 2 * ((N + 7) & ~7);                        // row stride (doubles)
+    double* s_x = reinterpret_cast<double*>(slc_smem);        // [SLC_K][rs]
+    double* s_mu = s_x + (size_t)SLC_K * rs;                  // [2N] means (re, im interleaved)
+    double* s_var = s_mu + n2;                                // [N]
+    int* s_hist = reinterpret_cast<int*>(s_var + N);          // [nb]
+    const size_t rl = blockIdx.x;
+    const long long run = run_begin + (long long)rl, n_mc = fin->n_mc;
+    if (!okflag[rl]) {
+        for (int b = tid; b < nb; b += nth) fin->matrix[(long long)b * n_mc + run] = nan("");
+        return;
+    }
+    for (int i = tid; i < N; i += nth) {
+        const double4 st = *reinterpret_cast<const double4*>(stat + (rl * N + i) * 4);  // amx, a2x, amy, a2y
+        s_mu[2 * i] = st.x;
+        s_mu[2 * i + 1] = st.z;
+        s_var[i] = st.y + st.w;
+    }
+    for (int b = tid; b < nb; b += nth) s_hist[b] = 0;
+    const int NBk = (N + 3) >> 2;
+    const int n_blocks = NBk * (NBk + 1) / 2;
+    const bool work = tid < n_blocks;
+    int bi = 0, bj = 0;
+    if (work) {
+        int rem = tid;  // tile id -> (bi, bj), bi <= bj, rows enumerated bi = 0, 1, ... with NBk - bi entries each
+        while (rem >= NBk - bi) {
+            rem -= NBk - bi;
+            bi++;
+        }
+        bj = bi + rem;
+    }
+    // the last tile row / column may reach past N: clamp the loads to valid rows, the pairs are skipped below
+    const int ia = min(4 * bi, N - 4 < 0 ? 0 : N - 4), ic = min(4 * bj, N - 4 < 0 ? 0 : N - 4);
+    const int sa = 4 * bi - ia, sc = 4 * bj - ic;
+    double re[4][4], im[4][4];
+    int oa[4], oc[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        oa[p] = 2 * ((ia + p) ^ (((ia + p) >> 3) & 7));
+        oc[p] = 2 * ((ic + p) ^ (((ic + p) >> 3) & 7));
+#pragma unroll
+        for (int q = 0; q < 4; q++) re[p][q] = im[p][q] = 0.;
+    }
+    const double* const src = smp + rl * (size_t)n_t * n2;
+    for (int k0 = 1; k0 < n_t; k0 += SLC_K) {
+        const int kc = min(SLC_K, n_t - k0);
+        __syncthreads();  // the previous chunk is consumed (first pass: s_mu / s_var / s_hist are written)
+        for (int e = tid; e < kc * n2; e += nth) {
+            const int kk = e / n2, d = e - kk * n2, i = d >> 1;
+            s_x[kk * rs + 2 * (i ^ ((i >> 3) & 7)) + (d & 1)] = __ldcs(src + (size_t)k0 * n2 + e) - s_mu[d];
+        }
+        __syncthreads();
+        if (work) {
+#pragma unroll 4
+            for (int kk = 0; kk < kc; kk++) {
+                const double* row = s_x + (size_t)kk * rs;
+                double2 za[4], zc[4];
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    za[p] = *reinterpret_cast<const double2*>(row + oa[p]);
+                    zc[p] = *reinterpret_cast<const double2*>(row + oc[p]);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {  // (a + ib)(c - id)
+                        re[p][q] = fma(za[p].x, zc[q].x, re[p][q]);
+                        re[p][q] = fma(za[p].y, zc[q].y, re[p][q]);
+                        im[p][q] = fma(za[p].y, zc[q].x, im[p][q]);
+                        im[p][q] = fma(-za[p].x, zc[q].y, im[p][q]);
+                    }
+            }
+        }
+    }
+    if (work) {
+        const double step = 1. / (double)nb;
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = ia + p, j = ic + q;
+                if (p < sa || q < sc) continue;  // rows of a clamped window that belong to the previous tile
+                if (i >= j || j >= N) continue;
+                const double den = sqrt(s_var[i]) * sqrt(s_var[j]);
+                const double c = hypot(re[p][q] / den, im[p][q] / den);
+                if (c != c) continue;  // zero-variance oscillator: dropped, as in the lane kernels and the oracle
+                double f = c / step + 1.;  // Base.searchsortedlast on the range 0:1/nbins:1
+                f = fmin(fmax(f, 1.), (double)(nb + 1));
+                const int n0 = (int)rint(f);
+                const int idx = (c < (double)(n0 - 1) / (double)nb) ? n0 - 1 : n0;
+                if (idx >= 1 && idx <= nb) atomicAdd(&s_hist[idx - 1], 2);
+            }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0., cum = 0.;
+        for (int b = 0; b < nb; b++) tot += (double)s_hist[b];
+        for (int b = 0; b < nb; b++) {
+            cum += (double)s_hist[b];
+            fin->matrix[(long long)b * n_mc + run] = (fin->matrix_meas == MCBB_MAT_CORR_HIST) ? (double)s_hist[b] : cum / tot;
+        }
+    }
+}
+
 static size_t sl_smem_bytes(int JB, int N, bool a1d) {
     return (size_t)JB * (a1d ? 3072 : 2048) + sizeof(double) * ((size_t)(N + 1) * (2 * UM_NSLOT * JB + 2) + 8 * (size_t)JB + 3 * 128) +
            sizeof(SlSlotCtl) * (size_t)JB + 24 + sizeof(int) * (4 * (size_t)JB + 64) + 128;
@@ -1001,10 +1119,12 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     hf.kl_tol = F.kl_tol;
     hf.feat = io.feat;
     hf.matrix = io.matrix;
-    SlFin* d_fin = (SlFin*)scratch_get(92, sizeof(SlFin));
+    SlFin* d_fin = (SlFin*)scratch_get(92, 2 * sizeof(SlFin));
     if (!d_fin) MCBB_FAIL("solve: device allocation failed");
-    MCBB_CUDA_OK(cudaMemcpyAsync(d_fin, &hf, sizeof(SlFin), cudaMemcpyHostToDevice, st));
-    MCBB_CUDA_OK(cudaStreamSynchronize(st));  // hf is stack-owned
+    SlFin hf2[2] = {hf, hf};
+    hf2[1].matrix_meas = MCBB_MAT_NONE;  // k_sl_post: measures only — the matrix measure has its own kernel
+    MCBB_CUDA_OK(cudaMemcpyAsync(d_fin, hf2, 2 * sizeof(SlFin), cudaMemcpyHostToDevice, st));
+    MCBB_CUDA_OK(cudaStreamSynchronize(st));  // hf2 is stack-owned
     a.fin = d_fin;
     MCBB_CUDA_OK(cudaMemcpyToSymbolAsync(c_um_ts, io.t_save, sizeof(double) * io.n_t, 0, cudaMemcpyDeviceToDevice, st));
 
@@ -1044,8 +1164,21 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
         if (rc) return rc;
         if (smp) {
             MCBB_CUDA_OK(cudaFuncSetAttribute(k_sl_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem));
-            k_sl_post<<<(unsigned)(r1 - r0), 128, post_smem, st>>>(d_fin, a.smp, a.stat, a.okflag, d_fpos, r0, post_scratch);
+            k_sl_post<<<(unsigned)(r1 - r0), 128, post_smem, st>>>(d_fin + 1, a.smp, a.stat, a.okflag, d_fpos, r0, post_scratch);
             MCBB_LAUNCHED();
+            if (F.matrix_meas != MCBB_MAT_NONE) {
+                const int nbk = (N + 3) / 4, tiles = nbk * (nbk + 1) / 2;
+                const int threads = ((tiles + 31) / 32) * 32;
+                const size_t csm = sizeof(double) * ((size_t)SLC_K * 2 * ((N + 7) & ~7) + 2 * N + N) + sizeof(int) * 64;
+                if (threads <= 352) {
+                    MCBB_CUDA_OK(cudaFuncSetAttribute(k_sl_corr_post<352>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+                    k_sl_corr_post<352><<<(unsigned)(r1 - r0), threads, csm, st>>>(d_fin, a.smp, a.stat, a.okflag, r0);
+                } else {
+                    MCBB_CUDA_OK(cudaFuncSetAttribute(k_sl_corr_post<544>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+                    k_sl_corr_post<544><<<(unsigned)(r1 - r0), threads, csm, st>>>(d_fin, a.smp, a.stat, a.okflag, r0);
+                }
+                MCBB_LAUNCHED();
+            }
         }
     }
     // a run that left the fixed-point range invalidates this launch: the caller falls through to the lane kernels

@@ -14,8 +14,9 @@ def _launches(prob):
     """One launch of k_solve_batched_umma_sl; measure sets that need the whole series (KL-hist, correlation) add one
     launch of k_sl_post, which reduces the saved samples of all runs afterwards (one CTA per run)."""
     ev = prob.eval_ode_func
-    series = any("kl" in str(getattr(f, "__name__", f)).lower() for f in ev.eval_funcs) or bool(ev.matrix_eval_funcs)
-    return 2 if series else 1
+    kl = any("kl" in str(getattr(f, "__name__", f)).lower() for f in ev.eval_funcs)
+    corr = bool(ev.matrix_eval_funcs)
+    return 1 + int(kl or corr) + int(corr)  # integrator, k_sl_post (measures), k_sl_corr_post (matrix measure)
 
 
 def _ref(m, orc, prob, ic0, par0, **kw):
@@ -46,7 +47,7 @@ def test_c4_tensor_core_kernel_converged_every_run(gpu, orc):
     kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10 ** 7)
     before = m.kernel_launch_count()
     sol = m.solve(prob, **kw)
-    assert m.kernel_launch_count() - before == _launches(prob) == 2, "expected k_solve_batched_umma_sl + k_sl_post"
+    assert m.kernel_launch_count() - before == _launches(prob) == 3, "expected k_solve_batched_umma_sl + k_sl_post + k_sl_corr_post"
     ref, ctx = _ref(m, orc, prob, ic0, par0, **kw)
     assert np.array_equal(sol.retcode, ref["retcode"]) and np.all(sol.retcode == 0)
     stats = cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.9)
@@ -190,8 +191,8 @@ def test_series_measures_are_reduced_chunk_by_chunk(gpu):
     ts = m.tsave_array(prob.p, 400, prob.rel_transient_time)
     before = m.kernel_launch_count()
     f0, m0, _, r0, n0 = m.custom_solve_b200(prob, ts)
-    assert m.kernel_launch_count() - before == 2
-    for mb, launches in ((20, 10), (64, 4)):  # 31 runs per chunk -> 5 chunks; 100 per chunk -> 2
+    assert m.kernel_launch_count() - before == 3
+    for mb, launches in ((20, 15), (64, 6)):  # 31 runs per chunk -> 5 chunks; 100 per chunk -> 2
         m.lib().mcbb_test_hook_set(b"sl_post_mb", mb)
         try:
             before = m.kernel_launch_count()
