@@ -884,14 +884,32 @@ __global__ void __launch_bounds__(MAXT) k_sl_corr_post(const SlFin* __restrict__
         for (int q = 0; q < 4; q++) re[p][q] = im[p][q] = 0.;
     }
     const double* const src = smp + rl * (size_t)n_t * n2;
+    // the samples of the NEXT chunk travel to registers while the current one is multiplied (the scratch is HBM-cold: the
+    // first version waited for every load — ncu: long scoreboard 3.4 stalls per issue, FP64 pipe 31 %)
+    constexpr int PRE = 19;  // >= SLC_K * 2N / MAXT (blockDim is always MAXT)
+    double pre[PRE];
+    auto prefetch = [&](const int k0) {
+        const int cnt = min(SLC_K, n_t - k0) * n2;
+#pragma unroll
+        for (int q = 0; q < PRE; q++) {
+            const int e = tid + q * MAXT;
+            pre[q] = (k0 < n_t && e < cnt) ? __ldcs(src + (size_t)k0 * n2 + e) : 0.;
+        }
+    };
+    prefetch(1);
     for (int k0 = 1; k0 < n_t; k0 += SLC_K) {
         const int kc = min(SLC_K, n_t - k0);
         __syncthreads();  // the previous chunk is consumed (first pass: s_mu / s_var / s_hist are written)
-        for (int e = tid; e < kc * n2; e += nth) {
-            const int kk = e / n2, d = e - kk * n2, i = d >> 1;
-            s_x[kk * rs + 2 * (i ^ ((i >> 3) & 7)) + (d & 1)] = __ldcs(src + (size_t)k0 * n2 + e) - s_mu[d];
+#pragma unroll
+        for (int q = 0; q < PRE; q++) {
+            const int e = tid + q * MAXT;
+            if (e < kc * n2) {
+                const int kk = e / n2, d = e - kk * n2, i = d >> 1;
+                s_x[kk * rs + 2 * (i ^ ((i >> 3) & 7)) + (d & 1)] = pre[q] - s_mu[d];
+            }
         }
         __syncthreads();
+        prefetch(k0 + SLC_K);
         if (work) {
 #pragma unroll 4
             for (int kk = 0; kk < kc; kk++) {
@@ -1168,7 +1186,7 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
             MCBB_LAUNCHED();
             if (F.matrix_meas != MCBB_MAT_NONE) {
                 const int nbk = (N + 3) / 4, tiles = nbk * (nbk + 1) / 2;
-                const int threads = ((tiles + 31) / 32) * 32;
+                const int threads = ((tiles + 31) / 32) * 32 <= 352 ? 352 : 544;  // always the template's MAXT: idle threads help staging
                 const size_t csm = sizeof(double) * ((size_t)SLC_K * 2 * ((N + 7) & ~7) + 2 * N + N) + sizeof(int) * 64;
                 if (threads <= 352) {
                     MCBB_CUDA_OK(cudaFuncSetAttribute(k_sl_corr_post<352>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
