@@ -46,7 +46,10 @@ struct BatchArgs {
     double* acc;  // [grid][3][NE][nthreads]  mean, M2, cyclic offset (L2-resident scratch)
     int need_kl, kl_bins;
     double kl_nstd, kl_tol;
-    double* smp;  // [grid][B][n_t][IG*TI] saved samples of the runs in flight (KL-hist measures only)
+    double* smp;  // [runs of the chunk][n_t][IG*TI] saved samples (KL-hist measures only; binned by k_batched_kl_post)
+    double* stat;   // [runs of the chunk][IG*TI][2] mean, std of every run as it finished
+    int* okflag;    // [runs of the chunk]
+    long long run_begin, run_end;  // the runs this launch integrates (one chunk of the ensemble when samples are kept)
 };
 
 // sin and cos together, |x| < ~1e6: Cody-Waite reduction by pi/2 with two FMAs + fdlibm kernel polynomials.
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
             c.fresh = 0;
             if (c.mode == MODE_FETCH) {
                 const long long run = (long long)atomicAdd(a.io.work_counter, 1ULL);
-                if (run >= n_mc) {
+                if (run >= a.run_end) {
                     c.mode = MODE_DONE;
                 } else {
                     double sc[MCBB_N_SCALARS];
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
             const double dts = ctl[b].dts_old, t_old = ctl[b].t_old;
             const int ks0 = ctl[b].s0 < 1 ? 1 : ctl[b].s0, ks1 = ctl[b].s1;  // sample 0 is dropped (eval_mc_prob.jl:152)
             if (ks0 < ks1) {
-                double* const smp_b = a.need_kl ? a.smp + ((size_t)blockIdx.x * B + b) * n_t * NP : nullptr;
+                double* const smp_b = a.need_kl ? a.smp + (size_t)(ctl[b].run - a.run_begin) * n_t * NP : nullptr;
                 // Welford state in registers across the samples of this step: one L2 round trip per accepted step
                 double am[TI], a2[TI], as[TI];
 #pragma unroll
@@ -544,19 +547,19 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
             for (int r = 0; r < TI; r++) {
                 const int i = ig * TI + r, e = r * TB + q;
                 if (i >= N) continue;
+                if (a.need_kl && i == 0) a.okflag[(size_t)(run - a.run_begin)] = ok ? 1 : 0;
                 const int pos = a.filter_pos[i];
                 if (pos < 0) continue;
                 const double mean = ok ? ACCS(0, e) : nan("");
                 const double m2 = ACCS(1, e);
                 const double sd = ok ? sqrt((m2 < 0. ? 0. : m2) / (double)(n_t - 2)) : nan("");
-                for (int m = 0; m < a.n_meas; m++) {
-                    double v = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
-                    if (a.meas[m] == MCBB_MEAS_KL_HIST)  // the samples this thread wrote itself: no barrier needed
-                        v = ok ? um_kl_hist(a.smp + ((size_t)blockIdx.x * B + b) * n_t * NP + i, NP, n_t, mean, sd, a.kl_bins,
-                                            a.kl_nstd, a.kl_tol, nullptr)
-                               : nan("");
-                    a.io.feat[((long long)m * a.n_filter + pos) * n_mc + run] = v;
+                if (a.need_kl) {  // the KL measures are binned after the solve: the whole block would wait here otherwise
+                    const size_t rl = (size_t)(run - a.run_begin);
+                    *reinterpret_cast<double2*>(a.stat + (rl * NP + i) * 2) = make_double2(mean, sd);
                 }
+                for (int m = 0; m < a.n_meas; m++)
+                    if (a.meas[m] != MCBB_MEAS_KL_HIST)
+                        a.io.feat[((long long)m * a.n_filter + pos) * n_mc + run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
             }
         }
         __syncthreads();
@@ -574,6 +577,20 @@ __global__ void __launch_bounds__(256, 1) k_solve_batched(const BatchArgs a) {
     }
 #undef KS
 #undef ACCS
+}
+
+// KL-hist measures of the runs of one chunk from their saved samples: one CTA per run, thread i = oscillator i
+__global__ void __launch_bounds__(192) k_batched_kl_post(const BatchArgs a, const int NP, const long long n_runs) {
+    const int i = threadIdx.x, n_t = a.io.n_t;
+    const size_t rl = blockIdx.x;
+    if ((long long)rl >= n_runs || i >= a.N) return;
+    const int pos = a.filter_pos[i];
+    if (pos < 0) return;
+    const double2 ms = *reinterpret_cast<const double2*>(a.stat + (rl * NP + i) * 2);
+    double kl = nan("");
+    if (a.okflag[rl]) kl = um_kl_hist(a.smp + rl * (size_t)n_t * NP + i, NP, n_t, ms.x, ms.y, a.kl_bins, a.kl_nstd, a.kl_tol, nullptr);
+    for (int m = 0; m < a.n_meas; m++)
+        if (a.meas[m] == MCBB_MEAS_KL_HIST) a.io.feat[((long long)m * a.n_filter + pos) * a.io.n_mc + a.run_begin + (long long)rl] = kl;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -733,17 +750,40 @@ int launch_batched_kuramoto(const mcbb_system_desc* hs, const SysDev& S, const S
     a.kl_nstd = F.kl_nstd;
     a.kl_tol = F.kl_tol;
     a.smp = nullptr;
+    // KL-hist: the ensemble in chunks whose saved samples fit the free device memory (<= 64 GB; hook "batched_post_mb"),
+    // each followed by the binning kernel.  Other measure sets: one launch.
+    long long chunk = io.n_mc;
     if (F.need_kl) {
-        a.smp = (double*)scratch_get(94, sizeof(double) * (size_t)grid * a.B * (size_t)io.n_t * (size_t)NP);
-        if (!a.smp) MCBB_FAIL("solve: device allocation failed");
+        const size_t run_bytes = sizeof(double) * (size_t)io.n_t * (size_t)NP;
+        size_t free_b = 0, total_b = 0;
+        MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        size_t cap = std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(94));
+        if (const long long mb = tune_get("batched_post_mb", 0)) cap = (size_t)mb << 20;
+        chunk = std::max<long long>(1, std::min<long long>(io.n_mc, (long long)(cap / run_bytes)));
+        a.smp = (double*)scratch_get(94, run_bytes * (size_t)chunk);
+        a.stat = (double*)scratch_get(108, sizeof(double) * 2 * (size_t)NP * (size_t)chunk);
+        a.okflag = (int*)scratch_get(109, sizeof(int) * (size_t)chunk);
+        if (!a.smp || !a.stat || !a.okflag) MCBB_FAIL("solve: device allocation failed");
     }
-    MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-    int rc;
-    if (TB == 2)
-        rc = unit ? launch_variant<2, true>(a, smem, grid, st) : launch_variant<2, false>(a, smem, grid, st);
-    else
-        rc = unit ? launch_variant<4, true>(a, smem, grid, st) : launch_variant<4, false>(a, smem, grid, st);
-    if (rc) return rc;
+    for (long long r0 = 0; r0 < io.n_mc; r0 += chunk) {
+        const long long r1 = std::min<long long>(io.n_mc, r0 + chunk);
+        a.run_begin = r0;
+        a.run_end = r1;
+        const unsigned long long c0 = (unsigned long long)r0;
+        MCBB_CUDA_OK(cudaMemcpyAsync(io.work_counter, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));  // c0 is stack-owned
+        const int g = (int)std::min<long long>((r1 - r0 + a.B - 1) / a.B, (long long)grid);
+        int rc;
+        if (TB == 2)
+            rc = unit ? launch_variant<2, true>(a, smem, g, st) : launch_variant<2, false>(a, smem, g, st);
+        else
+            rc = unit ? launch_variant<4, true>(a, smem, g, st) : launch_variant<4, false>(a, smem, g, st);
+        if (rc) return rc;
+        if (F.need_kl) {
+            k_batched_kl_post<<<(unsigned)(r1 - r0), 192, 0, st>>>(a, NP, r1 - r0);
+            MCBB_LAUNCHED();
+        }
+    }
     *handled = true;
     return 0;
 }

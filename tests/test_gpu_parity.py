@@ -882,12 +882,23 @@ def test_fp64_batched_kernel_default_measures_with_kl(gpu, orc, system):
     kw = dict(reltol=1e-9, abstol=1e-9, maxiters=10**7)
     before = m.kernel_launch_count()
     sol = m.solve(prob, **kw)
-    assert m.kernel_launch_count() - before == 1, "expected one launch of k_solve_batched"
+    assert m.kernel_launch_count() - before == 2, "expected k_solve_batched + k_batched_kl_post"
     assert sol.feat.shape == (70, N, 3)
     ref, ctx = _oracle_ref(m, orc, prob, ic0, par0, **kw)
     assert np.array_equal(sol.retcode, ref["retcode"]) and np.all(sol.retcode == 0)
     cases.compare_features(sol.feat, ref, orc, *ctx, min_checked=0.5)
     assert np.isfinite(sol.feat[:, :, 2]).mean() > 0.9
+    # the KL binning runs after the solve, chunk by chunk (k_batched_kl_post): a 1 MB sample scratch (8 runs per chunk)
+    # must give bitwise the same measures as one chunk
+    m.lib().mcbb_test_hook_set(b"batched_post_mb", 1)
+    try:
+        prob.ic, prob.par = ic0.copy(), par0.copy()
+        before = m.kernel_launch_count()
+        sol3 = m.solve(prob, **kw)
+        assert m.kernel_launch_count() - before >= 10
+    finally:
+        m.lib().mcbb_test_hook_set(b"batched_post_mb", -2 ** 63)
+    assert np.array_equal(sol3.feat, sol.feat, equal_nan=True) and np.array_equal(sol3.nsteps, sol.nsteps)
     m.lib().mcbb_test_hook_set(b"no_batched_kl", 1)
     try:
         prob.ic, prob.par = ic0.copy(), par0.copy()
