@@ -52,7 +52,10 @@ struct GroupArgs {
     int need_kl, kl_bins;
     double kl_nstd, kl_tol;
     SolveIO io;
-    double* smp;                  // [groups in flight][n_t][n_dim] saved samples (KL only)
+    double* smp;                  // [runs of the chunk][n_t][n_dim] saved samples (KL only; binned by k_group_kl_post)
+    double* stat;                 // [runs of the chunk][n_dim][2] mean, std of every reported dimension
+    int* okflag;                  // [runs of the chunk]
+    long long run_begin, run_end; // the runs this launch integrates (one chunk of the ensemble when samples are kept)
 };
 
 template <int G>
@@ -110,8 +113,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     int fpos[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) fpos[c] = own ? a.fpos[c * G + gl] : -1;
-    const long long slot = ((long long)blockIdx.x * GR_THREADS + tid) / G;  // this group's sample scratch
-    double* const smp = a.need_kl ? a.smp + slot * (long long)n_t * a.n_dim : nullptr;
+    double* smp = nullptr;  // this run's rows of the sample scratch (KL only)
     const double NaN = nan("");
 
     // ---- trajectory state: registers -------------------------------------------------------------------------------
@@ -227,16 +229,15 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
             const double m2 = a2[c];
             const double mean = ok ? am[c] : NaN;
             const double sd = ok ? sqrt((m2 < 0. ? 0. : m2) / (double)(n_t - 2)) : NaN;
-            for (int m = 0; m < a.n_meas; m++) {
-                double v = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
-                if (a.meas[m] == MCBB_MEAS_KL_HIST)
-                    v = ok ? um_kl_hist(smp + (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO ? c * N + gl : gl), a.n_dim, n_t, mean, sd,
-                                        a.kl_bins, a.kl_nstd, a.kl_tol, nullptr)
-                           : NaN;
-                a.io.feat[((long long)m * a.n_filter + fpos[c]) * n_mc + run] = v;
-            }
+            if (a.need_kl)  // the KL measures are binned after the solve (k_group_kl_post): the other groups of the warp would wait
+                *reinterpret_cast<double2*>(a.stat + ((size_t)(run - a.run_begin) * a.n_dim +
+                                                      (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO ? c * N + gl : gl)) * 2) = make_double2(mean, sd);
+            for (int m = 0; m < a.n_meas; m++)
+                if (a.meas[m] != MCBB_MEAS_KL_HIST)
+                    a.io.feat[((long long)m * a.n_filter + fpos[c]) * n_mc + run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
         }
         if (gl == 0) {
+            if (a.need_kl) a.okflag[run - a.run_begin] = ok ? 1 : 0;
             if (a.io.retcode) a.io.retcode[run] = ret;
             if (a.io.nsteps) {
                 a.io.nsteps[run] = natt;
@@ -288,9 +289,10 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
         r = __shfl_sync(0xffffffffu, r, 0, G);
         if (mode == MODE_FETCH) {
             run = r;
-            if (run >= n_mc) {
+            if (run >= a.run_end) {
                 mode = MODE_DONE;
             } else {
+                if (a.need_kl) smp = a.smp + (size_t)(run - a.run_begin) * n_t * a.n_dim;
 #pragma unroll
                 for (int q = 0; q < MCBB_N_SCALARS; q++) sc[q] = a.scalars[q];
                 for (int p = 0; p < a.n_par; p++) sc[a.par_slot[p]] = a.io.par[(long long)p * n_mc + run];
@@ -453,6 +455,22 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     }
 }
 
+// KL-hist measures of the runs of one chunk from their saved samples: one thread per (run, state dimension)
+__global__ void __launch_bounds__(128) k_group_kl_post(const GroupArgs a, const int* __restrict__ fpos_dim, const long long n_runs) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_runs * a.n_dim) return;
+    const long long rl = id / a.n_dim;
+    const int d = (int)(id - rl * a.n_dim);
+    const int pos = fpos_dim[d];
+    if (pos < 0) return;
+    const double2 ms = *reinterpret_cast<const double2*>(a.stat + ((size_t)rl * a.n_dim + d) * 2);
+    double kl = nan("");
+    if (a.okflag[rl])
+        kl = um_kl_hist(a.smp + (size_t)rl * a.io.n_t * a.n_dim + d, a.n_dim, a.io.n_t, ms.x, ms.y, a.kl_bins, a.kl_nstd, a.kl_tol, nullptr);
+    for (int m = 0; m < a.n_meas; m++)
+        if (a.meas[m] == MCBB_MEAS_KL_HIST) a.io.feat[((long long)m * a.n_filter + pos) * a.io.n_mc + a.run_begin + rl] = kl;
+}
+
 template <int SYS, int G, int EPL = 1>
 static int launch_group_one(const GroupArgs& a, size_t smem, int grid, cudaStream_t st) {
     MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_group<SYS, G, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -522,7 +540,7 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
             fpos[(d / N) * G + (d % N)] = ii;
         }
     }
-    int* d_int = (int*)scratch_get(103, sizeof(int) * (size_t)(2 * EW + G + GR_DEGMAX * G + 2 * G));
+    int* d_int = (int*)scratch_get(103, sizeof(int) * (size_t)(2 * EW + G + GR_DEGMAX * G + 2 * G + S.n_dim));
     double* d_dbl = (double*)scratch_get(104, sizeof(double) * (size_t)(2 * EW + GR_DEGMAX * G));
     if (!d_int || !d_dbl) MCBB_FAIL("solve: device allocation failed");
     std::vector<int> hi;
@@ -530,6 +548,7 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     hi.insert(hi.end(), node_deg.begin(), node_deg.end());
     hi.insert(hi.end(), node_edge.begin(), node_edge.end());
     hi.insert(hi.end(), fpos.begin(), fpos.end());
+    for (int d = 0; d < S.n_dim; d++) hi.push_back(fpos[(d / N) * G + (d % N)]);  // by state dimension, for the KL post kernel
     std::vector<double> hd;
     hd.insert(hd.end(), edge_val.begin(), edge_val.end());
     hd.insert(hd.end(), node_val.begin(), node_val.end());
@@ -566,27 +585,52 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     const int per_sm = (int)std::max<long long>(1, std::min<long long>(tune_get("group_per_sm", 4), (long long)(220 * 1024) / (long long)(smem + 1024)));
     const int grid = (int)std::min<long long>(want, (long long)sms * per_sm);
     a.smp = nullptr;
+    // KL-hist: the ensemble in chunks whose saved samples fit the free device memory (<= 64 GB; hook "group_post_mb"), each
+    // followed by the binning kernel.  Other measure sets: one launch.
+    long long chunk = io.n_mc;
+    const int* d_fpos_dim = d_int + 2 * EW + G + GR_DEGMAX * G + 2 * G;
     if (F.need_kl) {
-        a.smp = (double*)scratch_get(105, sizeof(double) * (size_t)grid * per_block * (size_t)io.n_t * (size_t)S.n_dim);
-        if (!a.smp) MCBB_FAIL("solve: device allocation failed");
+        const size_t run_bytes = sizeof(double) * (size_t)io.n_t * (size_t)S.n_dim;
+        size_t free_b = 0, total_b = 0;
+        MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        size_t cap = std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(105));
+        if (const long long mb = tune_get("group_post_mb", 0)) cap = (size_t)mb << 20;
+        chunk = std::max<long long>(1, std::min<long long>(io.n_mc, (long long)(cap / run_bytes)));
+        a.smp = (double*)scratch_get(105, run_bytes * (size_t)chunk);
+        a.stat = (double*)scratch_get(110, sizeof(double) * 2 * (size_t)S.n_dim * (size_t)chunk);
+        a.okflag = (int*)scratch_get(111, sizeof(int) * (size_t)chunk);
+        if (!a.smp || !a.stat || !a.okflag) MCBB_FAIL("solve: device allocation failed");
     }
-    MCBB_CUDA_OK(cudaMemsetAsync(io.work_counter, 0, sizeof(unsigned long long), st));
-    int rc;
-    if (second && EPL == 2)
-        rc = launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32, 2>(a, smem, grid, st);
-    else if (second)
-        rc = G == 8 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 8>(a, smem, grid, st)
-                    : (G == 16 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 16>(a, smem, grid, st)
-                               : launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32>(a, smem, grid, st));
-    else if (!net)
-        rc = G == 8 ? launch_group_one<MCBB_SYS_KURAMOTO, 8>(a, smem, grid, st)
-                    : (G == 16 ? launch_group_one<MCBB_SYS_KURAMOTO, 16>(a, smem, grid, st)
-                               : launch_group_one<MCBB_SYS_KURAMOTO, 32>(a, smem, grid, st));
-    else
-        rc = G == 8 ? launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 8>(a, smem, grid, st)
-                    : (G == 16 ? launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 16>(a, smem, grid, st)
-                               : launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 32>(a, smem, grid, st));
-    if (rc) return rc;
+    for (long long r0 = 0; r0 < io.n_mc; r0 += chunk) {
+        const long long r1 = std::min<long long>(io.n_mc, r0 + chunk);
+        a.run_begin = r0;
+        a.run_end = r1;
+        const unsigned long long c0 = (unsigned long long)r0;
+        MCBB_CUDA_OK(cudaMemcpyAsync(io.work_counter, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+        MCBB_CUDA_OK(cudaStreamSynchronize(st));  // c0 is stack-owned
+        const int g = (int)std::min<long long>((r1 - r0 + per_block - 1) / per_block, (long long)grid);
+        int rc;
+        if (second && EPL == 2)
+            rc = launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32, 2>(a, smem, g, st);
+        else if (second)
+            rc = G == 8 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 8>(a, smem, g, st)
+                        : (G == 16 ? launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 16>(a, smem, g, st)
+                                   : launch_group_one<MCBB_SYS_SECOND_ORDER_KURAMOTO, 32>(a, smem, g, st));
+        else if (!net)
+            rc = G == 8 ? launch_group_one<MCBB_SYS_KURAMOTO, 8>(a, smem, g, st)
+                        : (G == 16 ? launch_group_one<MCBB_SYS_KURAMOTO, 16>(a, smem, g, st)
+                                   : launch_group_one<MCBB_SYS_KURAMOTO, 32>(a, smem, g, st));
+        else
+            rc = G == 8 ? launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 8>(a, smem, g, st)
+                        : (G == 16 ? launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 16>(a, smem, g, st)
+                                   : launch_group_one<MCBB_SYS_KURAMOTO_NETWORK, 32>(a, smem, g, st));
+        if (rc) return rc;
+        if (F.need_kl) {
+            const long long nthr = (r1 - r0) * S.n_dim;
+            k_group_kl_post<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(a, d_fpos_dim, r1 - r0);
+            MCBB_LAUNCHED();
+        }
+    }
     *handled = true;
     return 0;
 }

@@ -1212,6 +1212,13 @@ def test_group_kernel_equals_lane_kernel_bitwise(gpu, orc, case):
     (f0, _, _, r0, n0), (f1, _, _, r1, n1) = _solve_both_ways(m, prob, ts, **kw)
     assert np.array_equal(r0, r1) and np.array_equal(n0, n1)
     assert np.array_equal(f0, f1, equal_nan=True), [float(np.nanmax(np.abs(f0[..., q] - f1[..., q]))) for q in range(f0.shape[2])]
+    # KL measures are binned after the solve, chunk by chunk (k_group_kl_post): a 1 MB sample scratch = many chunks
+    m.lib().mcbb_test_hook_set(b"group_post_mb", 1)
+    try:
+        f2, _, _, r2, n2 = m.custom_solve_b200(prob, ts, **kw)
+    finally:
+        m.lib().mcbb_test_hook_set(b"group_post_mb", -2 ** 63)
+    assert np.array_equal(f0, f2, equal_nan=True) and np.array_equal(r0, r2) and np.array_equal(n0, n2)
     if case == "c1_maxiters":
         assert np.all(r0 == m.abi.RET_MAXITERS) and np.isnan(f0).all()
     else:
