@@ -1152,9 +1152,13 @@ int launch_batched_umma_sl(const mcbb_system_desc* hs, const SysDev& S, const So
     long long chunk = io.n_mc;
     if (smp) {
         // at most 64 GB and at most half of what is free on the device right now (the scratch is kept for the next call)
-        size_t free_b = 0, total_b = 0;
-        MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-        size_t cap = std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(39));
+        // (cudaMemGetInfo costs milliseconds: only ensembles whose samples exceed 2 GB ask how much memory is free)
+        size_t cap = (size_t)2 << 30;
+        if (run_bytes * (size_t)io.n_mc > cap) {
+            size_t free_b = 0, total_b = 0;
+            MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+            cap = std::max<size_t>(cap, std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(39)));
+        }
         if (const long long mb = tune_get("sl_post_mb", 0)) cap = (size_t)mb << 20;
         chunk = std::max<long long>(1, std::min<long long>(io.n_mc, (long long)(cap / run_bytes)));
         a.smp = (double*)scratch_get(39, run_bytes * (size_t)chunk);

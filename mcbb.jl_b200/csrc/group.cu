@@ -66,7 +66,8 @@ __device__ __forceinline__ double gr_shfl(const double v, const int src) {
 // SYS: MCBB_SYS_KURAMOTO_NETWORK (one component per lane) or MCBB_SYS_SECOND_ORDER_KURAMOTO (theta_i, omega_i per lane)
 // EPL: edges per lane (second order): 2 lets a 32-lane group carry up to 64 edges — the paper's N = 30, 3-regular power
 // grid has 45 (paper/kuramoto/1-simulate.jl:22-26); lane l evaluates the sines of edges l and l + G
-template <int SYS, int G, int EPL = 1>
+// KL: the instantiation that keeps the saved samples for the KL-hist measures
+template <int SYS, int G, int EPL = 1, bool KL = false>
 __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
     constexpr int NC = (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO) ? 2 : 1;
     extern __shared__ __align__(16) unsigned char gr_smem[];
@@ -229,15 +230,15 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
             const double m2 = a2[c];
             const double mean = ok ? am[c] : NaN;
             const double sd = ok ? sqrt((m2 < 0. ? 0. : m2) / (double)(n_t - 2)) : NaN;
-            if (a.need_kl)  // the KL measures are binned after the solve (k_group_kl_post): the other groups of the warp would wait
+            if (KL)  // the KL measures are binned after the solve (k_group_kl_post): the other groups of the warp would wait
                 *reinterpret_cast<double2*>(a.stat + ((size_t)(run - a.run_begin) * a.n_dim +
                                                       (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO ? c * N + gl : gl)) * 2) = make_double2(mean, sd);
             for (int m = 0; m < a.n_meas; m++)
-                if (a.meas[m] != MCBB_MEAS_KL_HIST)
+                if (!KL || a.meas[m] != MCBB_MEAS_KL_HIST)
                     a.io.feat[((long long)m * a.n_filter + fpos[c]) * n_mc + run] = (a.meas[m] == MCBB_MEAS_MEAN) ? mean : sd;
         }
         if (gl == 0) {
-            if (a.need_kl) a.okflag[run - a.run_begin] = ok ? 1 : 0;
+            if (KL) a.okflag[run - a.run_begin] = ok ? 1 : 0;
             if (a.io.retcode) a.io.retcode[run] = ret;
             if (a.io.nsteps) {
                 a.io.nsteps[run] = natt;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
                         xv = xv - as_[c];
                     }
                 }
-                if (smp && own) smp[(long long)isave * a.n_dim + (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO ? c * N + gl : gl)] = xv;
+                if (KL && own) smp[(long long)isave * a.n_dim + (SYS == MCBB_SYS_SECOND_ORDER_KURAMOTO ? c * N + gl : gl)] = xv;
                 const double mean = am[c];
                 const double delta = xv - mean;
                 if (fabs(delta) <= 1.7976931348623157e308) {
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_solve_group(const GroupArgs a) {
             if (run >= a.run_end) {
                 mode = MODE_DONE;
             } else {
-                if (a.need_kl) smp = a.smp + (size_t)(run - a.run_begin) * n_t * a.n_dim;
+                if (KL) smp = a.smp + (size_t)(run - a.run_begin) * n_t * a.n_dim;
 #pragma unroll
                 for (int q = 0; q < MCBB_N_SCALARS; q++) sc[q] = a.scalars[q];
                 for (int p = 0; p < a.n_par; p++) sc[a.par_slot[p]] = a.io.par[(long long)p * n_mc + run];
@@ -473,8 +474,13 @@ __global__ void __launch_bounds__(128) k_group_kl_post(const GroupArgs a, const 
 
 template <int SYS, int G, int EPL = 1>
 static int launch_group_one(const GroupArgs& a, size_t smem, int grid, cudaStream_t st) {
-    MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_group<SYS, G, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_group<SYS, G, EPL><<<grid, GR_THREADS, smem, st>>>(a);
+    if (a.need_kl) {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_group<SYS, G, EPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_solve_group<SYS, G, EPL, true><<<grid, GR_THREADS, smem, st>>>(a);
+    } else {
+        MCBB_CUDA_OK(cudaFuncSetAttribute(k_solve_group<SYS, G, EPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_solve_group<SYS, G, EPL, false><<<grid, GR_THREADS, smem, st>>>(a);
+    }
     MCBB_LAUNCHED();
     return 0;
 }
@@ -591,9 +597,13 @@ int launch_group(const mcbb_system_desc* hs, const SysDev& S, const SolverDev& o
     const int* d_fpos_dim = d_int + 2 * EW + G + GR_DEGMAX * G + 2 * G;
     if (F.need_kl) {
         const size_t run_bytes = sizeof(double) * (size_t)io.n_t * (size_t)S.n_dim;
-        size_t free_b = 0, total_b = 0;
-        MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-        size_t cap = std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(105));
+        // (cudaMemGetInfo costs milliseconds: only ensembles whose samples exceed 2 GB ask how much memory is free)
+        size_t cap = (size_t)2 << 30;
+        if (run_bytes * (size_t)io.n_mc > cap) {
+            size_t free_b = 0, total_b = 0;
+            MCBB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+            cap = std::max<size_t>(cap, std::min<size_t>((size_t)64 << 30, free_b / 2 + scratch_size(105)));
+        }
         if (const long long mb = tune_get("group_post_mb", 0)) cap = (size_t)mb << 20;
         chunk = std::max<long long>(1, std::min<long long>(io.n_mc, (long long)(cap / run_bytes)));
         a.smp = (double*)scratch_get(105, run_bytes * (size_t)chunk);
