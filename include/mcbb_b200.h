@@ -24,6 +24,11 @@
  *     a different stream than the device's previous call first waits for that stream to drain.  So: any number of host
  *     threads may call concurrently (different devices overlap, one device takes turns), results are never corrupted
  *     by mixing streams, but only ONE stream per device overlaps with the host — use one stream per device.
+ *   - Device memory: the library keeps its work buffers cached per device between calls and releases them in
+ *     mcbb_finalize.  Measure sets that need the whole saved series of a run (KL-hist, the correlation measures) keep the
+ *     saved samples of a CHUNK of runs on the device and reduce them after the chunk is integrated; the chunk is sized to
+ *     at most 64 GB and at most half of the device memory that is free at the time of the call (ensembles whose samples
+ *     take less than 2 GB never ask), so the results do not depend on it and a busy device only means more chunks.
  */
 #ifndef MCBB_B200_H
 #define MCBB_B200_H
