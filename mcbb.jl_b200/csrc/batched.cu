@@ -1,8 +1,8 @@
 // batched.cu — block-cooperative ensemble Tsit5 for LARGE phase-oscillator networks (N ~ 24..160):
 // kuramoto_network (src/systems.jl:119-130) and non_local_kuramoto_ring (src/systems.jl:230-239),
 // with the eval_ode_run statistics (src/eval_mc_prob.jl:191-198) fused into the tail: mean / std as running moments,
-// empirical_1D_KL_divergence_hist (the third default measure, eval_mc_prob.jl:312-330) from the saved samples of the
-// runs in flight, kept in a device scratch and reduced by the owning thread when the run finishes.
+// empirical_1D_KL_divergence_hist (the third default measure, eval_mc_prob.jl:312-330) from the saved samples of a chunk
+// of runs, kept in a device scratch and binned after the chunk is integrated (k_batched_kl_post).
 //
 // Why a second kernel: one trajectory per lane needs 9 N doubles of state per lane, which no longer fits on
 // chip for N = 100.  Here a CTA integrates a BATCH of B trajectories in lockstep rounds.  Every trajectory

@@ -23,9 +23,10 @@
 //   * every Runge-Kutta stage vector is thread-private shared memory [oscillator][trajectory][re | im][u, k1..k7];
 //     sums come back with tcgen05.ld into the thread that owns the oscillator: no CTA barrier inside the stage loop.
 //   * statistics of eval_ode_run fused: mean / std of Re and Im in registers (Welford); for the KL-histogram measures
-//     and correlation_ecdf / correlation_hist (eval_mc_prob.jl:312-330, 462-488) the saved samples of the runs in flight
-//     go to a device scratch [slot][n_t][2N] and are reduced by the CTA when the run finishes: KL per oscillator thread,
-//     the N x N complex correlation as a register-tiled 4 x 4 FP64 product over the upper triangle.
+//     and correlation_ecdf / correlation_hist (eval_mc_prob.jl:312-330, 462-488) the saved samples of a CHUNK of runs
+//     go to a device scratch [run][n_t][2N] and are reduced after the chunk is integrated: k_sl_post (KL per oscillator
+//     thread, one CTA per run) and k_sl_corr_post (the N x N complex correlation as 4 x 4 FP64 register tiles over the
+//     upper triangle, samples tiled through shared memory).
 //   * error control as DiffEqBase does it for a Complex{Float64} state: one scale abstol + max(|z0|, |z1|) reltol per
 //     complex element (complex modulus), RMS over N elements (calculate_residuals / ODE_DEFAULT_NORM).
 //
