@@ -647,3 +647,25 @@ def test_cluster_means_measures_and_per_cluster_getters(mcbb):
     assert np.isclose(res.cluster_measures_global[0, 0, 1], glob[ind & (ca == 0), 0].mean())
     with pytest.warns(UserWarning, match="No clusters"):
         assert m.cluster_means(sol, m.DbscanResult(np.zeros(0, int), np.zeros(n, int), np.zeros(0, int))) is False
+
+
+def test_quantile_neighbours_and_lerp_reproduce_numpy_percentile(mcbb):
+    """The device path of the histogram edges (dist.histogram_features_device) gets the two order statistics around a
+    type-7 quantile from mcbb_order_stats and interpolates on the host: api._quantile_neighbours + api._lerp must be
+    numpy's percentile (the host path's StatsBase.iqr stand-in) bit for bit, and _hist_edges_from_stats the rule of
+    _compute_hist_edges."""
+    api = mcbb.api
+    rng = np.random.default_rng(4)
+    for n in (2, 5, 17, 1000, 20001):
+        x = np.sort(rng.normal(size=n) * rng.uniform(0.1, 50))
+        for q in (0.25, 0.75, 0.5, 0.0, 1.0):
+            lo, hi, g = api._quantile_neighbours(n, q)
+            assert api._lerp(x[lo], x[hi], g) == np.percentile(x, 100 * q), (n, q)
+    data = rng.normal(size=(400, 9))
+    srt = np.sort(data.ravel())
+    l25, h25, g25 = api._quantile_neighbours(srt.size, 0.25)
+    l75, h75, g75 = api._quantile_neighbours(srt.size, 0.75)
+    e_ref, bw_ref = api._compute_hist_edges(data, 9, 0.5, 50)
+    e, bw = api._hist_edges_from_stats(srt[0], srt[-1], api._lerp(srt[l25], srt[h25], g25), api._lerp(srt[l75], srt[h75], g75),
+                                       9, 0.5, 50)
+    assert bw == bw_ref and np.array_equal(e, e_ref)
